@@ -1,0 +1,76 @@
+"""ctypes binding of include/akugpu.h.  Fails loudly when libakugpu.so is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class AkuGpuError(RuntimeError):
+    """Raised for any non-zero return code of the C ABI (the reference's SWIG layer maps
+    its `throw std::string` to RuntimeError the same way, aku/swig/PPToolbox.i:14-30)."""
+
+    def __init__(self, code, msg):
+        super().__init__("akugpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "libakugpu.so")
+
+
+SYMBOLS = {
+    # name: (restype, argtypes)
+    "akugpu_create": (C.c_void_p, [C.c_int]),
+    "akugpu_destroy": (None, [C.c_void_p]),
+    "akugpu_last_error": (C.c_char_p, [C.c_void_p]),
+    "akugpu_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "akugpu_synchronize": (C.c_int, [C.c_void_p]),
+    "akugpu_launch_count": (C.c_int64, [C.c_void_p]),
+    "akugpu_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "akugpu_stage_times_reset": (C.c_int, [C.c_void_p, C.c_int]),
+    "akugpu_frontend_load_config": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "akugpu_frontend_load_config_text": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "akugpu_frontend_dim": (C.c_int, [C.c_void_p]),
+    "akugpu_frontend_sample_rate": (C.c_int, [C.c_void_p]),
+    "akugpu_frontend_frame_rate": (C.c_float, [C.c_void_p]),
+    "akugpu_frontend_num_frames": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "akugpu_frontend_set_parameters": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "akugpu_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "akugpu_features_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_char_p,
+                                        C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "akugpu_model_read": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "akugpu_model_load_diag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "akugpu_model_num_states": (C.c_int, [C.c_void_p]),
+    "akugpu_model_dim": (C.c_int, [C.c_void_p]),
+    "akugpu_model_num_gaussians": (C.c_int, [C.c_void_p]),
+    "akugpu_gmm_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "akugpu_gmm_lna": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "akugpu_phone_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "akugpu_lna_header": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "akugpu_set_chunk_frames": (C.c_int, [C.c_void_p, C.c_int64]),
+    "akugpu_set_scorer_variant": (C.c_int, [C.c_void_p, C.c_int]),
+    "akugpu_pipe_rates": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+}
+
+
+def load_library():
+    """Loads libakugpu.so (built in-tree by __graft_entry__.build()) and types every symbol
+    include/akugpu.h declares.  Loading needs libcudart's dependencies only; no GPU is touched
+    until akugpu_create()."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise AkuGpuError(-1, "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C aaltoasr_b200/csrc); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)   # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib

@@ -1,0 +1,481 @@
+// api.cu -- the extern "C" boundary declared in include/akugpu.h.
+// No C++ type and no exception crosses it; every entry point converts
+// akugpu::Error into a return code + akugpu_last_error().
+#include "ctx.hpp"
+#include "kernels.hpp"
+#include <string.h>
+#include <fstream>
+#include <sstream>
+
+using namespace akugpu;
+
+static std::string g_create_err;
+
+#define API_BEGIN                                             \
+  if (!ctx) return AKUGPU_E_ARG;                              \
+  try {                                                       \
+    AKU_CUDA(cudaSetDevice(ctx->device));
+#define API_END                                               \
+    return AKUGPU_OK;                                         \
+  } catch (const Error &e) {                                  \
+    ctx->err = e.msg;                                         \
+    return e.code;                                            \
+  } catch (const std::exception &e) {                         \
+    ctx->err = e.what();                                      \
+    return AKUGPU_E_ARG;                                      \
+  }
+
+namespace akugpu {
+
+StageScope::StageScope(akugpu_ctx *c, int s) : ctx(c), stage(s), l0(c->launches)
+{
+  if (!ctx->timer.enabled) return;
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!ctx->timer.pool.empty()) { e = ctx->timer.pool.back(); ctx->timer.pool.pop_back(); }
+    else AKU_CUDA(cudaEventCreate(&e));
+    return e;
+  };
+  e0 = get(); e1 = get();
+  AKU_CUDA(cudaEventRecord(e0, ctx->stream));
+}
+StageScope::~StageScope()
+{
+  if (!ctx->timer.enabled || !e0) return;
+  cudaEventRecord(e1, ctx->stream);
+  ctx->timer.pending.push_back(std::make_pair(stage, std::make_pair(e0, e1)));
+  ctx->timer.launches[stage] += ctx->launches - l0;
+}
+
+}  // namespace akugpu
+
+static void require_model(akugpu_ctx *ctx)
+{
+  if (!ctx->have_model) throw Error(AKUGPU_E_STATE, "no acoustic model loaded (akugpu_model_read / akugpu_model_load_diag)");
+}
+static void require_frontend(akugpu_ctx *ctx)
+{
+  if (!ctx->fe.configured) throw Error(AKUGPU_E_STATE, "no feature configuration loaded (akugpu_frontend_load_config)");
+}
+
+// Scores frames [0,F) of device-resident features chunk by chunk and emits LNA records.
+// out may be host (pipelined D2H on a second stream), device (written in place) or NULL.
+static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, int64_t F, int precision, int lnabytes,
+                         int normalize, uint8_t *out, uint64_t *checksum_out)
+{
+  const int S = ctx->hm.S;
+  if (lnabytes != 2 && lnabytes != 4) throw Error(AKUGPU_E_ARG, "lnabytes must be 2 or 4");
+  if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
+  if (F <= 0 || S <= 0) { if (checksum_out) *checksum_out = 0; return; }
+  int64_t chunk = std::max<int64_t>(128, (ctx->chunk_frames + 127) / 128 * 128);
+  if (chunk > F) chunk = (F + 127) / 128 * 128;
+  const size_t rec = (size_t)S * lnabytes;
+  const bool out_dev = out && is_device_ptr(out);
+  const bool out_host = out && !out_dev;
+  const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
+  ctx->d_sll.reserve((size_t)S * chunk * esz);
+  if (!out_dev) { ctx->d_lna[0].reserve(chunk * rec); if (out_host) ctx->d_lna[1].reserve(chunk * rec); }
+  if (checksum_out) { ctx->d_chk.reserve(8); AKU_CUDA(cudaMemsetAsync(ctx->d_chk.p, 0, 8, ctx->stream)); }
+  int c = 0;
+  for (int64_t c0 = 0; c0 < F; c0 += chunk, ++c) {
+    const int64_t c1 = std::min(F, c0 + chunk), nf = c1 - c0;
+    const int b = out_host ? (c & 1) : 0;
+    uint8_t *dst = out_dev ? out + c0 * rec : ctx->d_lna[b].as<uint8_t>();
+    if (out_host && c >= 2) AKU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));
+    if (precision == AKUGPU_F32) {
+      { StageScope sc(ctx, 1); launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
+      { StageScope sc(ctx, 2); launch_lna_f32(ctx, ctx->d_sll.as<float>(), chunk, S, nf, lnabytes, normalize, dst); }
+    } else {
+      { StageScope sc(ctx, 1); launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk); }
+      { StageScope sc(ctx, 2); launch_lna_f64(ctx, ctx->d_sll.as<double>(), chunk, S, nf, lnabytes, normalize, dst); }
+    }
+    if (checksum_out) launch_checksum(ctx, dst, nf * rec, ctx->d_chk.as<unsigned long long>());
+    if (out_host) {
+      AKU_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+      AKU_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[b], 0));
+      AKU_CUDA(cudaMemcpyAsync(out + c0 * rec, dst, nf * rec, cudaMemcpyDeviceToHost, ctx->copy_out));
+      AKU_CUDA(cudaEventRecord(ctx->ev_out[b], ctx->copy_out));
+    }
+  }
+  if (checksum_out) {
+    unsigned long long h = 0;
+    AKU_CUDA(cudaMemcpyAsync(&h, ctx->d_chk.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+    *checksum_out = h;
+  }
+  if (out_host) AKU_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// Makes `src` (host or device) available on the device; returns the device pointer.
+static const void *to_device(akugpu_ctx *ctx, const void *src, size_t bytes, DevBuf &scratch)
+{
+  if (is_device_ptr(src)) return src;
+  scratch.reserve(std::max<size_t>(bytes, 16));
+  AKU_CUDA(cudaMemcpyAsync(scratch.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return scratch.p;
+}
+
+extern "C" {
+
+akugpu_ctx *akugpu_create(int device)
+{
+  try {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      throw Error(AKUGPU_E_CUDA, std::string("no CUDA device available (") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                     "); akugpu has no CPU fallback");
+    }
+    if (device < 0 || device >= n) throw Error(AKUGPU_E_ARG, fmt("device %d out of range (0..%d)", device, n - 1));
+    AKU_CUDA(cudaSetDevice(device));
+    akugpu_ctx *ctx = new akugpu_ctx;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    AKU_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+      delete ctx;
+      throw Error(AKUGPU_E_CUDA, fmt("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                                     prop.minor));
+    }
+    AKU_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    AKU_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    AKU_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+      AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    }
+    return ctx;
+  } catch (const Error &e) {
+    g_create_err = e.msg;
+    return nullptr;
+  }
+}
+
+void akugpu_destroy(akugpu_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto &p : ctx->timer.pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
+  for (auto e : ctx->timer.pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+  }
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  delete ctx;
+}
+
+const char *akugpu_last_error(akugpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int akugpu_set_stream(akugpu_ctx *ctx, void *cuda_stream)
+{
+  API_BEGIN
+  if (cuda_stream) {
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+  } else if (!ctx->own_stream) {
+    AKU_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  API_END
+}
+
+int akugpu_synchronize(akugpu_ctx *ctx)
+{
+  API_BEGIN
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  AKU_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  API_END
+}
+
+int64_t akugpu_launch_count(akugpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int akugpu_stage_times_reset(akugpu_ctx *ctx, int enable)
+{
+  API_BEGIN
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &p : ctx->timer.pending) { ctx->timer.pool.push_back(p.second.first); ctx->timer.pool.push_back(p.second.second); }
+  ctx->timer.pending.clear();
+  for (int i = 0; i < 3; i++) { ctx->timer.ms[i] = 0; ctx->timer.launches[i] = 0; }
+  ctx->timer.enabled = enable != 0;
+  API_END
+}
+
+int akugpu_stage_times(akugpu_ctx *ctx, double ms_out[3], int64_t launches_out[3])
+{
+  API_BEGIN
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &p : ctx->timer.pending) {
+    float ms = 0;
+    AKU_CUDA(cudaEventElapsedTime(&ms, p.second.first, p.second.second));
+    ctx->timer.ms[p.first] += ms;
+    ctx->timer.pool.push_back(p.second.first);
+    ctx->timer.pool.push_back(p.second.second);
+  }
+  ctx->timer.pending.clear();
+  for (int i = 0; i < 3; i++) {
+    if (ms_out) ms_out[i] = ctx->timer.ms[i];
+    if (launches_out) launches_out[i] = ctx->timer.launches[i];
+  }
+  API_END
+}
+
+// ---- front-end ---------------------------------------------------------------------
+int akugpu_frontend_load_config_text(akugpu_ctx *ctx, const char *cfg_text)
+{
+  API_BEGIN
+  if (!cfg_text) throw Error(AKUGPU_E_ARG, "cfg_text is NULL");
+  frontend_parse(ctx, cfg_text);
+  API_END
+}
+
+int akugpu_frontend_load_config(akugpu_ctx *ctx, const char *cfg_path)
+{
+  API_BEGIN
+  if (!cfg_path) throw Error(AKUGPU_E_ARG, "cfg_path is NULL");
+  std::ifstream in(cfg_path, std::ios::binary);
+  if (!in) throw Error(AKUGPU_E_IO, std::string("could not open ") + cfg_path);
+  std::ostringstream ss;
+  ss << in.rdbuf();
+  frontend_parse(ctx, ss.str());
+  API_END
+}
+
+int akugpu_frontend_dim(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[ctx->fe.last].dim : AKUGPU_E_STATE; }
+int akugpu_frontend_sample_rate(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[0].sample_rate : AKUGPU_E_STATE; }
+float akugpu_frontend_frame_rate(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[0].frame_rate : -1.f; }
+int64_t akugpu_frontend_num_frames(akugpu_ctx *ctx, int64_t n_samples)
+{
+  if (!ctx || !ctx->fe.configured) return AKUGPU_E_STATE;
+  return frontend_num_frames(ctx->fe, n_samples);
+}
+
+int akugpu_frontend_set_parameters(akugpu_ctx *ctx, const char *module_name, const char *text)
+{
+  API_BEGIN
+  require_frontend(ctx);
+  if (!module_name || !text) throw Error(AKUGPU_E_ARG, "module_name/text is NULL");
+  frontend_set_parameters(ctx, module_name, text);
+  API_END
+}
+
+static void frame_offsets_of(akugpu_ctx *ctx, const int64_t *utt_offsets, int n_utts, std::vector<int64_t> &uo,
+                             std::vector<int64_t> &fo)
+{
+  if (n_utts < 0 || !utt_offsets) throw Error(AKUGPU_E_ARG, "utt_offsets is NULL or n_utts < 0");
+  uo.assign(utt_offsets, utt_offsets + n_utts + 1);
+  fo.assign(n_utts + 1, 0);
+  for (int u = 0; u < n_utts; u++) {
+    if (uo[u + 1] < uo[u]) throw Error(AKUGPU_E_ARG, "utt_offsets must be non-decreasing");
+    int64_t n = frontend_num_frames(ctx->fe, uo[u + 1] - uo[u]);
+    if (n <= 0) throw Error(AKUGPU_E_ARG, fmt("utterance %d: audio shorter than frame", u));   // aku/FeatureModules.cc:409
+    fo[u + 1] = fo[u] + n;
+  }
+}
+
+int akugpu_features(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts, void *out, int out_f64,
+                    int64_t *frame_offsets)
+{
+  API_BEGIN
+  require_frontend(ctx);
+  std::vector<int64_t> uo, fo;
+  frame_offsets_of(ctx, utt_offsets, n_utts, uo, fo);
+  if (frame_offsets) memcpy(frame_offsets, fo.data(), fo.size() * sizeof(int64_t));
+  if (out && n_utts > 0) {
+    if (!pcm) throw Error(AKUGPU_E_ARG, "pcm is NULL");
+    const int dim = ctx->fe.mods[ctx->fe.last].dim;
+    const size_t esz = out_f64 ? 8 : 4;
+    const int16_t *d_pcm = (const int16_t *)to_device(ctx, pcm, (size_t)uo[n_utts] * 2, ctx->d_pcm);
+    const bool odev = is_device_ptr(out);
+    void *d_out = out;
+    if (!odev) { ctx->d_feats.reserve((size_t)fo[n_utts] * dim * esz); d_out = ctx->d_feats.p; }
+    { StageScope sc(ctx, 0); frontend_run_batch(ctx, d_pcm, uo, fo, d_out, out_f64); }
+    if (!odev) AKU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)fo[n_utts] * dim * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  API_END
+}
+
+int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples, int start_frame, int end_frame,
+                          const char *module_name, void *out, int out_f64, int *dim_out)
+{
+  API_BEGIN
+  require_frontend(ctx);
+  int target = -1;
+  if (module_name && module_name[0]) {
+    for (size_t i = 0; i < ctx->fe.mods.size(); i++)
+      if (ctx->fe.mods[i].name == module_name) target = (int)i;
+    if (target < 0) throw Error(AKUGPU_E_ARG, std::string("unknown module requested: ") + module_name);
+  }
+  const int dim = ctx->fe.mods[target < 0 ? ctx->fe.last : target].dim;
+  if (dim_out) *dim_out = dim;
+  if (out && end_frame > start_frame) {
+    if (!pcm) throw Error(AKUGPU_E_ARG, "pcm is NULL");
+    const size_t esz = out_f64 ? 8 : 4;
+    const int64_t n = end_frame - start_frame;
+    const int16_t *d_pcm = (const int16_t *)to_device(ctx, pcm, (size_t)n_samples * 2, ctx->d_pcm);
+    const bool odev = is_device_ptr(out);
+    void *d_out = out;
+    if (!odev) { ctx->d_feats.reserve((size_t)n * dim * esz); d_out = ctx->d_feats.p; }
+    { StageScope sc(ctx, 0); frontend_run_range(ctx, d_pcm, n_samples, start_frame, end_frame, target, d_out, out_f64); }
+    if (!odev) AKU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * dim * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  API_END
+}
+
+// ---- model -------------------------------------------------------------------------
+int akugpu_model_read(akugpu_ctx *ctx, const char *base)
+{
+  API_BEGIN
+  if (!base) throw Error(AKUGPU_E_ARG, "base is NULL");
+  ctx->have_model = false;
+  model_read_files(base, ctx->hm);
+  model_pack(ctx);
+  API_END
+}
+
+int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim, const int32_t *mix_offsets,
+                           const int32_t *mix_gauss, const double *mix_weight, const double *means, const double *covs)
+{
+  API_BEGIN
+  if (n_states < 0 || n_gauss < 0 || dim <= 0 || !mix_offsets || (n_gauss && (!means || !covs)))
+    throw Error(AKUGPU_E_ARG, "bad model sizes / NULL arrays");
+  ctx->have_model = false;
+  HostModel &hm = ctx->hm;
+  hm.S = n_states; hm.G = n_gauss; hm.D = dim;
+  hm.mix_off.assign(mix_offsets, mix_offsets + n_states + 1);
+  if (hm.mix_off[0] != 0) throw Error(AKUGPU_E_ARG, "mix_offsets[0] must be 0");
+  const int K = hm.mix_off[n_states];
+  for (int s = 0; s < n_states; s++)
+    if (hm.mix_off[s + 1] < hm.mix_off[s]) throw Error(AKUGPU_E_ARG, "mix_offsets must be non-decreasing");
+  if (K && (!mix_gauss || !mix_weight)) throw Error(AKUGPU_E_ARG, "mix_gauss/mix_weight is NULL");
+  hm.mix_gauss.assign(mix_gauss, mix_gauss + K);
+  hm.mix_w.assign(mix_weight, mix_weight + K);
+  for (int k = 0; k < K; k++)
+    if (hm.mix_gauss[k] < 0 || hm.mix_gauss[k] >= n_gauss) throw Error(AKUGPU_E_ARG, fmt("mix_gauss[%d] out of range", k));
+  for (int s = 0; s < n_states; s++) {   // Mixture::normalize_weights, aku/Distributions.cc:2068-2075
+    double sum = 0;
+    for (int k = hm.mix_off[s]; k < hm.mix_off[s + 1]; k++) sum += hm.mix_w[k];
+    for (int k = hm.mix_off[s]; k < hm.mix_off[s + 1]; k++) hm.mix_w[k] /= sum;
+  }
+  hm.mean.assign(means, means + (size_t)n_gauss * dim);
+  hm.cov.assign(covs, covs + (size_t)n_gauss * dim);
+  model_pack(ctx);
+  API_END
+}
+
+int akugpu_model_num_states(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->hm.S : AKUGPU_E_STATE; }
+int akugpu_model_dim(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->hm.D : AKUGPU_E_STATE; }
+int akugpu_model_num_gaussians(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->hm.G : AKUGPU_E_STATE; }
+
+// ---- scoring -----------------------------------------------------------------------
+int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)
+{
+  API_BEGIN
+  require_model(ctx);
+  if (n_frames < 0 || (n_frames && (!feats || !out))) throw Error(AKUGPU_E_ARG, "bad n_frames / NULL buffers");
+  if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
+  const int S = ctx->hm.S, D = ctx->hm.D;
+  if (n_frames == 0 || S == 0) return AKUGPU_OK;
+  const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
+  const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
+  int64_t chunk = std::max<int64_t>(128, (ctx->chunk_frames + 127) / 128 * 128);
+  if (chunk > n_frames) chunk = (n_frames + 127) / 128 * 128;
+  ctx->d_sll.reserve((size_t)S * chunk * esz);
+  const bool odev = is_device_ptr(out);
+  uint8_t *d_out = (uint8_t *)out;
+  if (!odev) { ctx->d_tmp.reserve((size_t)n_frames * S * esz); d_out = ctx->d_tmp.as<uint8_t>(); }
+  for (int64_t c0 = 0; c0 < n_frames; c0 += chunk) {
+    const int64_t c1 = std::min(n_frames, c0 + chunk);
+    StageScope sc(ctx, 1);
+    if (precision == AKUGPU_F32) {
+      launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      launch_transpose_f32(ctx, ctx->d_sll.as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
+    } else {
+      launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
+      launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
+    }
+  }
+  if (!odev) AKU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_frames * S * esz, cudaMemcpyDeviceToHost, ctx->stream));
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+int akugpu_gmm_lna(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, int lnabytes,
+                   int normalize, uint8_t *out)
+{
+  API_BEGIN
+  require_model(ctx);
+  if (n_frames < 0 || (n_frames && !feats)) throw Error(AKUGPU_E_ARG, "bad n_frames / NULL feats");
+  const void *d_feats = to_device(ctx, feats, (size_t)n_frames * ctx->hm.D * (feats_f64 ? 8 : 4), ctx->d_feats);
+  score_to_lna(ctx, d_feats, feats_f64, n_frames, precision, lnabytes, normalize, out, nullptr);
+  API_END
+}
+
+int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts, int precision,
+                       int lnabytes, int normalize, uint8_t *out, int64_t *frame_offsets, uint64_t *checksum_out)
+{
+  API_BEGIN
+  require_frontend(ctx);
+  require_model(ctx);
+  const int dim = ctx->fe.mods[ctx->fe.last].dim;
+  if (dim != ctx->hm.D)
+    throw Error(AKUGPU_E_STATE, fmt("Feature dimension (%d) and model dimension (%d) don't agree", dim, ctx->hm.D));
+  std::vector<int64_t> uo, fo;
+  frame_offsets_of(ctx, utt_offsets, n_utts, uo, fo);
+  if (frame_offsets) memcpy(frame_offsets, fo.data(), fo.size() * sizeof(int64_t));
+  if (n_utts == 0) { if (checksum_out) *checksum_out = 0; return AKUGPU_OK; }
+  if (!pcm) throw Error(AKUGPU_E_ARG, "pcm is NULL");
+  const int feats_f64 = precision == AKUGPU_F64;
+  const int16_t *d_pcm = (const int16_t *)to_device(ctx, pcm, (size_t)uo[n_utts] * 2, ctx->d_pcm);
+  ctx->d_feats.reserve((size_t)fo[n_utts] * dim * (feats_f64 ? 8 : 4));
+  { StageScope sc(ctx, 0); frontend_run_batch(ctx, d_pcm, uo, fo, ctx->d_feats.p, feats_f64); }
+  score_to_lna(ctx, ctx->d_feats.p, feats_f64, fo[n_utts], precision, lnabytes, normalize, out, checksum_out);
+  API_END
+}
+
+int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5])
+{
+  if (!out5) return AKUGPU_E_ARG;
+  out5[0] = (n_states >> 24) & 255; out5[1] = (n_states >> 16) & 255; out5[2] = (n_states >> 8) & 255; out5[3] = n_states & 255;
+  out5[4] = (uint8_t)lnabytes;
+  return AKUGPU_OK;
+}
+
+int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames)
+{
+  API_BEGIN
+  if (frames < 128) throw Error(AKUGPU_E_ARG, "chunk must be >= 128 frames");
+  ctx->chunk_frames = frames;
+  API_END
+}
+
+int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant)
+{
+  API_BEGIN
+  if (variant < 0 || variant > 2) throw Error(AKUGPU_E_ARG, "variant must be 0, 1 or 2");
+  ctx->scorer_variant = variant;
+  if (ctx->have_model) model_pack(ctx);
+  API_END
+}
+
+int akugpu_pipe_rates(akugpu_ctx *ctx, double out[4])
+{
+  API_BEGIN
+  if (!out) throw Error(AKUGPU_E_ARG, "out is NULL");
+  pipe_rates(ctx, out);
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+// ctx.hpp -- context object behind the C ABI (include/akugpu.h).
+// Owns every device allocation; nothing allocated here crosses the boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <memory>
+#include "../../include/akugpu.h"
+
+namespace akugpu {
+
+struct Error {
+  int code;
+  std::string msg;
+  Error(int c, const std::string &m) : code(c), msg(m) {}
+};
+
+inline std::string fmt(const char *f, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, f); vsnprintf(buf, sizeof buf, f, ap); va_end(ap);
+  return std::string(buf);
+}
+
+#define AKU_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      throw ::akugpu::Error(AKUGPU_E_CUDA, ::akugpu::fmt("%s:%d: %s: %s", __FILE__, __LINE__, #call, \
+                                                       cudaGetErrorString(e_)));       \
+  } while (0)
+
+// Growable device buffer (never shrinks).
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) AKU_CUDA(cudaFree(p));
+    p = nullptr; cap = 0;
+    AKU_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return (T *)p; }
+  ~DevBuf() { release(); }
+};
+struct PinnedBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) AKU_CUDA(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    AKU_CUDA(cudaMallocHost(&p, bytes));
+    cap = bytes;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return (T *)p; }
+  ~PinnedBuf() { release(); }
+};
+
+inline bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------------------------
+// Acoustic model, host view (doubles, as read) and packed device images.
+struct HostModel {
+  int S = 0, G = 0, D = 0;
+  std::vector<int32_t> mix_off;     // [S+1]
+  std::vector<int32_t> mix_gauss;   // [K]
+  std::vector<double> mix_w;        // [K] normalised
+  std::vector<double> mean, cov;    // [G*D]
+};
+
+// fp32 scorer image: tiles of TC = 16*GR component slots, see gmm_kernels.cu.
+struct PackedF32 {
+  int GR = 0;            // component slots per thread (4 or 8)
+  int TC = 0;            // component slots per tile
+  int DP = 0;            // dim pairs
+  int n_tiles = 0;
+  size_t tile_floats = 0;
+  DevBuf params;         // n_tiles * tile_floats floats
+  DevBuf tile_state0;    // int32 [n_tiles+1]: first state of each tile
+  DevBuf st_grp;         // int32 [S+1]: first thread-group (global numbering) of each state
+  DevBuf center;         // float [2*DP] feature centre
+  DevBuf center64;       // double [2*DP]
+};
+// fp64 scorer image: plain arrays in the reference's own order.
+struct PackedF64 {
+  DevBuf mean, prec;     // double [G*D]
+  DevBuf cst;            // double [G]   m_constant
+  DevBuf mix_off, mix_gauss;  // int32
+  DevBuf mix_w;          // double [K]
+};
+
+// ---------------------------------------------------------------------------------
+// Front-end module graph (parsed from the reference's feature configuration).
+enum ModType { M_AUDIOFILE, M_FFT, M_MEL, M_POWER, M_MEL_POWER, M_DCT, M_DELTA, M_MERGE, M_CONCAT,
+               M_NORMALIZATION, M_LIN_TRANSFORM, M_MEAN_SUBTRACTOR };
+
+struct Module {
+  std::string name;
+  ModType type;
+  std::vector<int> src;     // indices of source modules
+  int dim = 0;
+  int left = 0, right = 0;  // own context (frames)
+  // audiofile
+  int sample_rate = 0, window_width = 0, copy_borders = 1;
+  float frame_rate = 125.f, window_advance = 0.f, emph = 0.97f;
+  // fft
+  int magnitude = 1, log = 0;
+  // mel
+  int root = 0;
+  std::vector<float> bin_edges;
+  // dct
+  int zeroth = 0;
+  // delta
+  int width = 2;
+  float norm = 10.f;
+  // normalization / lin_transform
+  std::vector<float> v_mean, v_scale, matrix, bias;
+  bool matrix_defined = false, bias_defined = false;
+  // mean_subtractor: left/right hold the +1-extended offsets, width = left+right-1
+  int ms_width = 0;
+  // device copies of parameters
+  std::shared_ptr<DevBuf> d_a, d_b;
+  // extended frame range this module must be evaluated on for an utterance:
+  // [-ext_left, n_frames-1+ext_right]
+  int ext_left = 0, ext_right = 0;
+};
+
+struct Frontend {
+  bool configured = false;
+  std::vector<Module> mods;
+  int last = -1;
+  // fused static path: audiofile -> fft -> {mel->dct, power, mel_power...}
+  std::shared_ptr<DevBuf> d_window;   // float [W] hamming
+  std::shared_ptr<DevBuf> d_twiddle;  // float2 [W/2] or DFT table
+};
+
+struct StageTimer {
+  bool enabled = false;
+  double ms[3] = {0, 0, 0};
+  int64_t launches[3] = {0, 0, 0};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+  std::vector<cudaEvent_t> pool;
+};
+
+}  // namespace akugpu
+
+struct akugpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;       // compute stream
+  bool own_stream = true;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 148;
+  int64_t chunk_frames = 16384;
+  int scorer_variant = 0;
+
+  akugpu::HostModel hm;
+  bool have_model = false;
+  akugpu::PackedF32 p32;
+  akugpu::PackedF64 p64;
+  bool have_p64 = false;
+
+  akugpu::Frontend fe;
+  akugpu::StageTimer timer;
+
+  // scratch
+  akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk;
+  akugpu::DevBuf d_fe[8];
+  std::vector<std::shared_ptr<akugpu::DevBuf>> fe_bufs;   // per-module output matrices (grow-only)
+  akugpu::PinnedBuf h_in[2], h_out[2];
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
+};

@@ -1,0 +1,888 @@
+// frontend.cu -- B200 feature front-end: config parser, module graph and kernels.
+//
+// Mirrors the reference's FeatureGenerator / FeatureModule plugin chain, but computes
+// whole utterances (all frames of a batch per launch) instead of one frame per call:
+//   config text  FeatureGenerator::load_configuration  aku/FeatureGenerator.cc:97-219
+//                ModuleConfig::read                    aku/ModuleConfig.cc:166-203
+//   audiofile    AudioFileModule                       aku/FeatureModules.cc:328-440
+//   fft          FFTModule                             aku/FeatureModules.cc:476-566
+//   mel          MelModule                             aku/FeatureModules.cc:776-849
+//   power        PowerModule                           aku/FeatureModules.cc:875-885
+//   mel_power    MelPowerModule                        aku/FeatureModules.cc:908-919
+//   dct          DCTModule                             aku/FeatureModules.cc:938-979
+//   delta        DeltaModule                           aku/FeatureModules.cc:999-1037
+//   normalization NormalizationModule                  aku/FeatureModules.cc:1057-1142
+//   lin_transform LinTransformModule                   aku/FeatureModules.cc:1167-1269
+//   merge        MergerModule                          aku/FeatureModules.cc:1340-1364
+//   mean_subtractor MeanSubtractorModule               aku/FeatureModules.cc:1385-1454
+//   concat       ConcatModule                          aku/FeatureModules.cc:1473-1501
+//
+// The reference mixes float and double on purpose-by-accident; every kernel below
+// keeps the same type at the same place (float pre-emphasis, float Hamming table made
+// with cosf, float FFT, sqrtf/logf, float mel accumulators, cosf DCT basis with double
+// accumulation, float power accumulator, double deltas ...) and blocks FMA contraction
+// where the x86 build has none, so that everything except the FFT's internal rounding
+// order is bit-for-bit the reference's arithmetic.
+//
+// Layout: every module output is a row-major double matrix [rows][dim] in HBM.  A row is
+// one (utterance, frame) pair; each utterance carries a halo of H frames on both sides
+// (H = largest context any module needs) so that context modules never special-case
+// borders: only the base module clamps the frame index (first/last window replicated,
+// aku/FeatureModules.cc:381-397), exactly like the reference.
+#include "ctx.hpp"
+#include "kernels.hpp"
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+#include <sstream>
+
+namespace akugpu {
+
+// ===================================================================================
+// config parsing
+namespace {
+
+struct Block {
+  std::vector<std::pair<std::string, std::string>> kv;
+  const std::string *find(const std::string &k) const {
+    for (auto &p : kv) if (p.first == k) return &p.second;
+    return nullptr;
+  }
+};
+
+std::string trim(const std::string &s) {
+  size_t b = 0, e = s.size();
+  while (e > b && (s[e - 1] == ' ' || s[e - 1] == '\t' || s[e - 1] == '\r' || s[e - 1] == '\n')) e--;
+  while (b < e && (s[b] == ' ' || s[b] == '\t')) b++;
+  return s.substr(b, e - b);
+}
+std::vector<std::string> split_ws(const std::string &s) {
+  std::vector<std::string> out;
+  size_t i = 0;
+  while (i < s.size()) {
+    while (i < s.size() && (s[i] == ' ' || s[i] == '\t')) i++;
+    size_t b = i;
+    while (i < s.size() && s[i] != ' ' && s[i] != '\t') i++;
+    if (i > b) out.push_back(s.substr(b, i - b));
+  }
+  return out;
+}
+long to_long(const std::string &s) {
+  char *e;
+  long v = strtol(s.c_str(), &e, 10);
+  if (s.empty() || *e) throw Error(AKUGPU_E_CONFIG, "invalid integer value: " + s);
+  return v;
+}
+float to_float(const std::string &s) {   // aku/str.cc:261-282: strtod narrowed to float
+  char *e;
+  float v = (float)strtod(s.c_str(), &e);
+  if (s.empty() || *e) throw Error(AKUGPU_E_CONFIG, "invalid float value: " + s);
+  return v;
+}
+bool get_int(const Block &b, const char *k, int &v) { auto p = b.find(k); if (!p) return false; v = (int)to_long(*p); return true; }
+bool get_float(const Block &b, const char *k, float &v) { auto p = b.find(k); if (!p) return false; v = to_float(*p); return true; }
+bool get_fvec(const Block &b, const char *k, std::vector<float> &v) {
+  auto p = b.find(k);
+  if (!p) return false;
+  auto f = split_ws(*p);
+  v.resize(f.size());
+  for (size_t i = 0; i < f.size(); i++) v[i] = to_float(f[i]);
+  return true;
+}
+
+void parse_blocks(const std::string &text, std::vector<Block> &blocks, bool bare)
+{
+  std::istringstream in(text);
+  std::string line;
+  int lineno = 0;
+  if (bare) {   // key/value lines only (set_parameters)
+    Block b;
+    while (std::getline(in, line)) {
+      line = trim(line);
+      if (line.empty()) continue;
+      size_t sp = line.find_first_of(" \t");
+      if (sp == std::string::npos) throw Error(AKUGPU_E_CONFIG, "value missing for option: " + line);
+      b.kv.push_back(std::make_pair(line.substr(0, sp), trim(line.substr(sp))));
+    }
+    blocks.push_back(b);
+    return;
+  }
+  while (std::getline(in, line)) {
+    lineno++;
+    line = trim(line);
+    if (line.empty()) continue;
+    if (line != "module") throw Error(AKUGPU_E_CONFIG, fmt("expected keyword 'module' on line %d: ", lineno) + line);
+    Block b;
+    bool first = true, closed = false;
+    while (std::getline(in, line)) {
+      lineno++;
+      line = trim(line);
+      if (line.empty()) continue;
+      if (first) {
+        if (line != "{") throw Error(AKUGPU_E_CONFIG, "'{' expected in module config file: " + line);
+        first = false;
+        continue;
+      }
+      if (line == "}") { closed = true; break; }
+      size_t sp = line.find_first_of(" \t");
+      if (sp == std::string::npos) throw Error(AKUGPU_E_CONFIG, "value missing for option: " + line);
+      std::string key = line.substr(0, sp);
+      if (b.find(key)) throw Error(AKUGPU_E_CONFIG, "value redefined: " + line);
+      b.kv.push_back(std::make_pair(key, trim(line.substr(sp))));
+    }
+    if (!closed) throw Error(AKUGPU_E_CONFIG, "unexpected end of module config file");
+    blocks.push_back(b);
+  }
+}
+
+template <class T>
+std::shared_ptr<DevBuf> upload_vec(const std::vector<T> &v, cudaStream_t st)
+{
+  auto b = std::make_shared<DevBuf>();
+  b->reserve(std::max<size_t>(16, v.size() * sizeof(T)));
+  if (!v.empty()) {
+    AKU_CUDA(cudaMemcpyAsync(b->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    AKU_CUDA(cudaStreamSynchronize(st));
+  }
+  return b;
+}
+
+void check_lin_transform(Module &m, int src_dim)
+{
+  // LinTransformModule::check_transform_parameters, aku/FeatureModules.cc:1203-1241
+  if (m.matrix.empty()) {
+    m.matrix_defined = false;
+  } else {
+    m.matrix_defined = true;
+    if ((int)m.matrix.size() != m.dim * src_dim) throw Error(AKUGPU_E_CONFIG, "LinTransformModule: Invalid matrix dimension");
+  }
+  if (m.bias.empty()) {
+    m.bias_defined = false;
+  } else {
+    m.bias_defined = true;
+    if ((int)m.bias.size() != m.dim) throw Error(AKUGPU_E_CONFIG, "LinTransformModule: Invalid bias dimension");
+  }
+}
+
+void read_normalization(Module &m, const Block &b)
+{
+  // NormalizationModule::set_module_config / set_parameters, aku/FeatureModules.cc:1057-1110
+  get_fvec(b, "mean", m.v_mean);
+  if ((int)m.v_mean.size() != m.dim) throw Error(AKUGPU_E_CONFIG, "NormalizationModule: Invalid mean dimension");
+  if (b.find("var") && b.find("scale"))
+    throw Error(AKUGPU_E_CONFIG, "NormalizationModule: Both scale and var can not be defined simultaneously");
+  if (get_fvec(b, "var", m.v_scale)) {
+    if ((int)m.v_scale.size() != m.dim) throw Error(AKUGPU_E_CONFIG, "Normalization module: Invalid variance dimension");
+    for (int i = 0; i < m.dim; i++) m.v_scale[i] = 1 / sqrtf(m.v_scale[i]);
+  } else if (get_fvec(b, "scale", m.v_scale)) {
+    if ((int)m.v_scale.size() != m.dim) throw Error(AKUGPU_E_CONFIG, "NormalizationModule: Invalid scale dimension");
+  }
+}
+
+void upload_module_params(akugpu_ctx *ctx, Module &m, const std::vector<Module> &mods)
+{
+  cudaStream_t st = ctx->stream;
+  switch (m.type) {
+    case M_FFT: {
+      const int N = mods[m.src[0]].dim;
+      std::vector<float> win(N);
+      for (int i = 0; i < N; i++) win[i] = .54 - .46 * cosf(2 * M_PI * i / (N - 1.0));   // aku/FeatureModules.cc:488-490
+      m.d_a = upload_vec(win, st);
+      std::vector<float> tw(2 * (size_t)N);   // e^{-2 pi i k / N}
+      for (int k = 0; k < N; k++) {
+        double a = -2.0 * M_PI * k / N;
+        tw[2 * k] = (float)cos(a);
+        tw[2 * k + 1] = (float)sin(a);
+      }
+      m.d_b = upload_vec(tw, st);
+      break;
+    }
+    case M_MEL: m.d_a = upload_vec(m.bin_edges, st); break;
+    case M_DCT: {
+      const int sd = mods[m.src[0]].dim;
+      const int bias = m.zeroth ? 1 : 0;
+      std::vector<float> tab((size_t)m.dim * sd, 1.0f);   // row 0 of a zeroth-component DCT is a plain sum
+      for (int i = 0; i < m.dim - bias; i++)
+        for (int b = 0; b < sd; b++) tab[(size_t)(i + bias) * sd + b] = cosf((i + 1) * (b + 0.5) * M_PI / sd);   // :977
+      m.d_a = upload_vec(tab, st);
+      break;
+    }
+    case M_NORMALIZATION:
+      m.d_a = upload_vec(m.v_mean, st);
+      m.d_b = upload_vec(m.v_scale, st);
+      break;
+    case M_LIN_TRANSFORM:
+      m.d_a = upload_vec(m.matrix, st);
+      m.d_b = upload_vec(m.bias, st);
+      break;
+    default: break;
+  }
+}
+
+}  // namespace
+
+void frontend_parse(akugpu_ctx *ctx, const std::string &text)
+{
+  std::vector<Block> blocks;
+  parse_blocks(text, blocks, false);
+  if (blocks.empty()) throw Error(AKUGPU_E_CONFIG, "feature configuration defines no modules");
+  Frontend fe;
+  std::map<std::string, int> by_name;
+  for (size_t bi = 0; bi < blocks.size(); bi++) {
+    const Block &b = blocks[bi];
+    const std::string *type = b.find("type"), *name = b.find("name");
+    if (!type) throw Error(AKUGPU_E_CONFIG, fmt("type not defined for module %d", (int)bi));
+    if (!name) throw Error(AKUGPU_E_CONFIG, fmt("name not defined for module %d", (int)bi));
+    if (name->find_first_of(" \t\n") != std::string::npos) throw Error(AKUGPU_E_CONFIG, "module name may not contain whitespaces");
+    Module m;
+    m.name = *name;
+    static const struct { const char *s; ModType t; } types[] = {
+        {"audiofile", M_AUDIOFILE}, {"fft", M_FFT}, {"mel", M_MEL}, {"power", M_POWER}, {"mel_power", M_MEL_POWER},
+        {"dct", M_DCT}, {"delta", M_DELTA}, {"merge", M_MERGE}, {"concat", M_CONCAT},
+        {"normalization", M_NORMALIZATION}, {"lin_transform", M_LIN_TRANSFORM}, {"mean_subtractor", M_MEAN_SUBTRACTOR}};
+    bool known = false;
+    for (auto &t : types) if (*type == t.s) { m.type = t.t; known = true; }
+    if (!known) {
+      if (*type == "pre" || *type == "vtln" || *type == "sr_norm" || *type == "quanteq")
+        throw Error(AKUGPU_E_CONFIG, "module type '" + *type + "' is not supported by the GPU front-end");
+      throw Error(AKUGPU_E_CONFIG, "Unknown module type '" + *type + "'");
+    }
+    if (fe.mods.empty() && m.type != M_AUDIOFILE) throw Error(AKUGPU_E_CONFIG, "first module should be a base module");
+    if (by_name.count(m.name)) throw Error(AKUGPU_E_CONFIG, "multiple definitions of module name: " + m.name);
+    const std::string *sources = b.find("sources");
+    if (fe.mods.empty() && sources) throw Error(AKUGPU_E_CONFIG, "can not define sources for the first module");
+    if (!fe.mods.empty() && !sources) throw Error(AKUGPU_E_CONFIG, "sources not defined for module: " + m.name);
+    if (sources) {
+      for (auto &s : split_ws(*sources)) {
+        auto it = by_name.find(s);
+        if (it == by_name.end()) throw Error(AKUGPU_E_CONFIG, "unknown source module: " + s);
+        m.src.push_back(it->second);
+      }
+      if (m.src.empty()) throw Error(AKUGPU_E_CONFIG, "sources not defined for module: " + m.name);
+      if (m.type != M_MERGE && m.src.size() != 1)   // FeatureModule::add_source, aku/FeatureModules.cc:160-166
+        throw Error(AKUGPU_E_CONFIG, "multiple sources are not allowed for module: " + m.name);
+    }
+    const int sdim = m.src.empty() ? 0 : fe.mods[m.src.back()].dim;
+    switch (m.type) {
+      case M_AUDIOFILE: {
+        if (!get_int(b, "sample_rate", m.sample_rate)) throw Error(AKUGPU_E_CONFIG, "AudioFileModule: Must set sample rate");
+        m.emph = 0.97; get_float(b, "pre_emph_coef", m.emph);
+        m.frame_rate = 125; get_float(b, "frame_rate", m.frame_rate);
+        m.window_advance = m.sample_rate / m.frame_rate;
+        m.window_width = (int)(2 * m.sample_rate / m.frame_rate);
+        get_int(b, "window_width", m.window_width);
+        m.dim = m.window_width;
+        int raw = 0; get_int(b, "raw", raw);   // container format is the host reader's business
+        m.copy_borders = 1; get_int(b, "copy_borders", m.copy_borders);
+        if (m.window_width < 2 || m.window_advance <= 0) throw Error(AKUGPU_E_CONFIG, "AudioFileModule: bad window geometry");
+        break;
+      }
+      case M_FFT:
+        if (fe.mods[m.src[0]].type != M_AUDIOFILE)
+          throw Error(AKUGPU_E_CONFIG, "fft module must read the audiofile module directly");
+        m.magnitude = 1; get_int(b, "magnitude", m.magnitude);
+        m.log = 0; get_int(b, "log", m.log);
+        m.dim = sdim / 2 + 1;
+        break;
+      case M_MEL: {
+        m.root = 0; get_int(b, "root", m.root);
+        const int sr = fe.mods[0].sample_rate;
+        m.dim = (int)((21 + 2) * log10f(1 + sr / 1400.0) / log10f(1 + 16000 / 1400.0) - 2);   // :784-785
+        int edges = m.dim + 2;
+        float rate = sr;
+        float mel_step = 2595 * log10f(1.0 + rate / 1400.0) / edges;
+        m.bin_edges.resize(edges);
+        for (int i = 0; i < edges; i++)
+          m.bin_edges[i] = 1400.0 * (pow(10, (i + 1) * mel_step / 2595) - 1) * (sdim - 1) / rate;   // :799-801
+        break;
+      }
+      case M_POWER: case M_MEL_POWER: m.dim = 1; break;
+      case M_DCT:
+        m.dim = 12; get_int(b, "dim", m.dim);
+        if (m.dim < 1) throw Error(AKUGPU_E_CONFIG, "DCTModule: Dimension must be > 0");
+        m.zeroth = 0; get_int(b, "zeroth", m.zeroth);
+        break;
+      case M_DELTA:
+        m.dim = sdim;
+        m.width = 2; get_int(b, "width", m.width);
+        m.norm = 2 * m.width * (m.width + 1) * (2 * m.width + 1) / 6;   // int arithmetic, then float (:1007)
+        get_float(b, "normalization", m.norm);
+        if (m.width < 1) throw Error(AKUGPU_E_CONFIG, "DeltaModule: Delta width must be > 0");
+        m.left = m.right = m.width;
+        break;
+      case M_MERGE:
+        m.dim = 0;
+        for (int s : m.src) m.dim += fe.mods[s].dim;
+        break;
+      case M_CONCAT:
+        get_int(b, "left", m.left); get_int(b, "right", m.right);
+        if (m.left < 0 || m.right < 0) throw Error(AKUGPU_E_CONFIG, "ConcatModule: context spans must be >= 0");
+        m.dim = sdim * (1 + m.left + m.right);
+        break;
+      case M_NORMALIZATION:
+        m.dim = sdim;
+        m.v_mean.assign(m.dim, 0.f);
+        m.v_scale.assign(m.dim, 1.f);
+        read_normalization(m, b);
+        break;
+      case M_LIN_TRANSFORM:
+        m.dim = sdim;
+        get_fvec(b, "matrix", m.matrix); get_fvec(b, "bias", m.bias);
+        get_int(b, "dim", m.dim);
+        if (m.dim < 1) throw Error(AKUGPU_E_CONFIG, "LinTransformModule: Dimension must be > 0");
+        check_lin_transform(m, sdim);
+        break;
+      case M_MEAN_SUBTRACTOR: {
+        m.dim = sdim;
+        int l = 75, r = 75;
+        get_int(b, "left", l); get_int(b, "right", r);
+        if (l + 1 < 1 || r + 1 < 1) throw Error(AKUGPU_E_CONFIG, "MeanSubtractorModule: context widths must be >= 0");
+        m.left = l; m.right = r;          // frames actually averaged: [t-l, t+r]
+        m.ms_width = l + r + 1;
+        break;
+      }
+    }
+    upload_module_params(ctx, m, fe.mods);
+    by_name[m.name] = (int)fe.mods.size();
+    fe.mods.push_back(m);
+  }
+  fe.last = (int)fe.mods.size() - 1;
+  fe.configured = true;
+  ctx->fe = fe;
+}
+
+void frontend_set_parameters(akugpu_ctx *ctx, const std::string &module, const std::string &text)
+{
+  Frontend &fe = ctx->fe;
+  int idx = -1;
+  for (size_t i = 0; i < fe.mods.size(); i++) if (fe.mods[i].name == module) idx = (int)i;
+  if (idx < 0) throw Error(AKUGPU_E_ARG, "unknown module requested: " + module);
+  Module &m = fe.mods[idx];
+  std::vector<Block> blocks;
+  parse_blocks(text, blocks, true);
+  const Block &b = blocks[0];
+  if (m.type == M_NORMALIZATION) {
+    read_normalization(m, b);
+  } else if (m.type == M_LIN_TRANSFORM) {
+    m.matrix.clear(); m.bias.clear();
+    get_fvec(b, "matrix", m.matrix); get_fvec(b, "bias", m.bias);
+    check_lin_transform(m, fe.mods[m.src[0]].dim);
+  } else {
+    return;   // FeatureModule::set_parameters default is a no-op (aku/FeatureModule.hh:107)
+  }
+  upload_module_params(ctx, m, fe.mods);
+}
+
+int64_t frontend_num_frames(const Frontend &fe, int64_t n_samples)
+{
+  // Sequential generate(0),generate(1),.. reports eof on the first frame whose window
+  // [ws, ws+W+1) runs past the file (aku/FeatureModules.cc:399-404), ws = (int)(f*advance).
+  const Module &a = fe.mods[0];
+  if (n_samples < a.window_width + 1) return 0;
+  int64_t f = (int64_t)((float)(n_samples - a.window_width - 1) / a.window_advance);
+  while (f > 0 && (int64_t)(int)((int)f * a.window_advance) + a.window_width + 1 > n_samples) f--;
+  while ((int64_t)(int)((int)(f + 1) * a.window_advance) + a.window_width + 1 <= n_samples) f++;
+  return f + 1;
+}
+
+// ===================================================================================
+// kernels
+struct UttDesc {
+  int64_t pcm_off;     // first sample of the utterance in the PCM buffer
+  int64_t n_samples;
+  int64_t row_off;     // first row (frame start-H) of the utterance in every module buffer
+  int64_t out_off;     // first row of the utterance in the gathered output
+  int n_frames;        // valid frames 0..n_frames-1
+  int start;           // reference frame number of the first output row
+  int n_rows_out;      // output rows (frames start .. start+n_rows_out-1)
+  int pad;
+};
+
+__device__ __forceinline__ void row_to_frame(const int *__restrict__ row_utt, const UttDesc *__restrict__ utts,
+                                             int64_t r, int H, int &u, int &t)
+{
+  u = row_utt[r];
+  t = utts[u].start - H + (int)(r - utts[u].row_off);
+}
+
+// audiofile + fft for power-of-two windows.  One CTA = FPB frames, N/2-point complex FFT of the
+// even/odd packed real signal in shared memory, then the real-FFT split.
+template <int N>
+__global__ void __launch_bounds__(256)
+fe_spectrum_pow2(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                 int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
+                 const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out)
+{
+  constexpr int M = N / 2;                 // complex FFT size
+  constexpr int TPF = (M / 2 < 32) ? 32 : ((M / 2 > 256) ? 256 : M / 2);   // threads per frame
+  constexpr int FPB = 256 / TPF;
+  constexpr int LOGM = (M == 64) ? 6 : (M == 128) ? 7 : (M == 256) ? 8 : (M == 512) ? 9 : (M == 1024) ? 10 : 5;
+  __shared__ float2 z[FPB][M + 1];
+  const int fl = threadIdx.x / TPF, tl = threadIdx.x % TPF;
+  const int64_t r = (int64_t)blockIdx.x * FPB + fl;
+  const bool valid = r < n_rows;
+  int u = 0, t = 0;
+  if (valid) row_to_frame(row_utt, utts, r, H, u, t);
+  const UttDesc ud = utts[u];
+  // window start: AudioFileModule::generate, aku/FeatureModules.cc:378-397
+  int tc = t;
+  if (copy_borders) tc = min(max(t, 0), ud.n_frames - 1);
+  const int ws = (int)(tc * adv);
+  const int16_t *x = pcm + ud.pcm_off;
+  for (int k = tl; k < M; k += TPF) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      int i = 2 * k + e;
+      int64_t p0 = (int64_t)ws + i, p1 = p0 + 1;
+      float s0 = (valid && p0 >= 0 && p0 < ud.n_samples) ? (float)x[p0] : 0.f;
+      float s1 = (valid && p1 >= 0 && p1 < ud.n_samples) ? (float)x[p1] : 0.f;
+      float pe = __fsub_rn(s1, __fmul_rn(emph, s0));                    // float pre-emphasis (:429)
+      v[e] = (float)__dmul_rn((double)window[i], (double)pe);           // float window * double sample -> float (:531)
+    }
+    z[fl][__brev((unsigned)k) >> (32 - LOGM)] = make_float2(v[0], v[1]);
+  }
+  __syncthreads();
+  // radix-2 DIT, M-point; twiddle e^{-2 pi i j / len} = tw[j * N / len]
+  for (int len = 2; len <= M; len <<= 1) {
+    const int half = len >> 1;
+    for (int b = tl; b < M / 2; b += TPF) {
+      int j = b & (half - 1);
+      int i0 = ((b - j) << 1) + j, i1 = i0 + half;
+      float2 w = tw[j * (N / len)];
+      float2 a = z[fl][i0], c = z[fl][i1];
+      float2 wc = make_float2(c.x * w.x - c.y * w.y, c.x * w.y + c.y * w.x);
+      z[fl][i0] = make_float2(a.x + wc.x, a.y + wc.y);
+      z[fl][i1] = make_float2(a.x - wc.x, a.y - wc.y);
+    }
+    __syncthreads();
+  }
+  // split: X[k] = (Z[k]+conj(Z[M-k]))/2 - i e^{-2 pi i k/N} (Z[k]-conj(Z[M-k]))/2 ,  k = 0..M
+  if (valid) {
+    double *o = out + r * (M + 1);
+    for (int k = tl; k <= M; k += TPF) {
+      float2 a = z[fl][k == M ? 0 : k], b = z[fl][k == 0 ? 0 : M - k];
+      float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+      float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
+      float2 w = (k == M) ? make_float2(-1.f, 0.f) : tw[k];
+      // -i * w * d
+      float2 wd = make_float2(w.x * d.x - w.y * d.y, w.x * d.y + w.y * d.x);
+      float re = e.x + wd.y, im = e.y - wd.x;
+      float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));       // float power (:534-537)
+      if (magnitude) p = sqrtf(p);
+      if (do_log) p = logf(p);
+      o[k] = (double)p;
+    }
+  }
+}
+
+// Generic window length: direct DFT with the twiddle table (O(N^2); correctness path for the
+// non-power-of-two windows 44.1/48 kHz configurations produce).
+__global__ void __launch_bounds__(128)
+fe_spectrum_dft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
+                const float2 *__restrict__ tw, int N, int magnitude, int do_log, double *__restrict__ out)
+{
+  extern __shared__ float xs[];
+  const int64_t r = blockIdx.x;
+  int u, t;
+  row_to_frame(row_utt, utts, r, H, u, t);
+  const UttDesc ud = utts[u];
+  int tc = t;
+  if (copy_borders) tc = min(max(t, 0), ud.n_frames - 1);
+  const int ws = (int)(tc * adv);
+  const int16_t *x = pcm + ud.pcm_off;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    int64_t p0 = (int64_t)ws + i, p1 = p0 + 1;
+    float s0 = (p0 >= 0 && p0 < ud.n_samples) ? (float)x[p0] : 0.f;
+    float s1 = (p1 >= 0 && p1 < ud.n_samples) ? (float)x[p1] : 0.f;
+    float pe = __fsub_rn(s1, __fmul_rn(emph, s0));
+    xs[i] = (float)__dmul_rn((double)window[i], (double)pe);
+  }
+  __syncthreads();
+  const int nb = N / 2 + 1;
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    float re = 0.f, im = 0.f;
+    int idx = 0;
+    for (int n = 0; n < N; n++) {
+      float2 w = tw[idx];
+      re = fmaf(xs[n], w.x, re);
+      im = fmaf(xs[n], w.y, im);
+      idx += k;
+      if (idx >= N) idx -= N;
+    }
+    float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+    if (magnitude) p = sqrtf(p);
+    if (do_log) p = logf(p);
+    out[r * nb + k] = (double)p;
+  }
+}
+
+// MelModule::generate, aku/FeatureModules.cc:806-849; one thread per (row, bin).
+__global__ void fe_mel(const double *__restrict__ src, int sdim, int64_t n_rows, const float *__restrict__ edges, int dim,
+                       int root, double *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  int64_t r = i / dim;
+  int b = (int)(i - r * dim);
+  const double *data = src + r * sdim;
+  float val = 0, sum = 0, scale;
+  float beg = __fsub_rn(edges[b], 1.f);
+  float end = edges[b + 1];
+  int t = (int)fmaxf(ceilf(beg), 0.0f);
+  while (t < end) {
+    scale = __fdiv_rn(__fsub_rn((float)t, beg), __fsub_rn(end, beg));
+    val = (float)__dadd_rn((double)val, __dmul_rn((double)scale, data[min(t, sdim - 1)]));
+    sum = __fadd_rn(sum, scale);
+    t++;
+  }
+  beg = end;
+  end = edges[b + 2];
+  while (t < end) {
+    scale = __fdiv_rn(__fsub_rn(end, (float)t), __fsub_rn(end, beg));
+    val = (float)__dadd_rn((double)val, __dmul_rn((double)scale, data[min(t, sdim - 1)]));
+    sum = __fadd_rn(sum, scale);
+    t++;
+  }
+  double o;
+  if (root) o = pow((double)__fdiv_rn(val, sum), 0.1);
+  else o = (double)logf(__fadd_rn(__fdiv_rn(val, sum), 1.f));
+  out[r * dim + b] = o;
+}
+
+// PowerModule (:875-885) and MelPowerModule (:908-919); one thread per row, float accumulator.
+__global__ void fe_power(const double *__restrict__ src, int sdim, int64_t n_rows, int use_exp, double *__restrict__ out)
+{
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const double *s = src + r * sdim;
+  float power = 0;
+  for (int i = 0; i < sdim; i++) power = (float)__dadd_rn((double)power, use_exp ? exp(s[i]) : s[i]);
+  out[r] = log(__dadd_rn((double)power, 1e-10));
+}
+
+// DCTModule::generate (:956-979); table[i][b] = cosf(...) as float, double accumulate in b order.
+__global__ void fe_dct(const double *__restrict__ src, int sdim, int64_t n_rows, const float *__restrict__ table, int dim,
+                       double *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  int64_t r = i / dim;
+  int c = (int)(i - r * dim);
+  const double *s = src + r * sdim;
+  const float *tb = table + (size_t)c * sdim;
+  double acc = 0.0;
+  for (int b = 0; b < sdim; b++) acc = __dadd_rn(acc, __dmul_rn(s[b], (double)tb[b]));
+  out[r * dim + c] = acc;
+}
+
+// Rows of a neighbouring frame stay inside the utterance's own row block because the halo H
+// covers every module's context; the clamp only protects rows nobody consumes.
+__device__ __forceinline__ int64_t nb_row(int64_t r, int k, int64_t lo, int64_t hi)
+{
+  int64_t q = r + k;
+  return q < lo ? lo : (q > hi ? hi : q);
+}
+
+// DeltaModule::generate (:1019-1037)
+__global__ void fe_delta(const double *__restrict__ src, int dim, int64_t n_rows, const int *__restrict__ row_utt,
+                         const UttDesc *__restrict__ utts, int H, int width, float norm, double *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  int64_t r = i / dim;
+  int c = (int)(i - r * dim);
+  const UttDesc ud = utts[row_utt[r]];
+  const int64_t lo = ud.row_off, hi = ud.row_off + ud.n_rows_out + 2 * H - 1;
+  double acc = 0;
+  for (int k = 1; k <= width; k++) {
+    double rv = src[nb_row(r, k, lo, hi) * dim + c], lv = src[nb_row(r, -k, lo, hi) * dim + c];
+    acc = __dadd_rn(acc, __dmul_rn((double)k, __dsub_rn(rv, lv)));
+  }
+  out[r * dim + c] = __ddiv_rn(acc, (double)norm);
+}
+
+// merge / concat: copy `sdim` columns of the source row shifted by `shift` frames to column `col0`.
+__global__ void fe_copy(const double *__restrict__ src, int sdim, int64_t n_rows, const int *__restrict__ row_utt,
+                        const UttDesc *__restrict__ utts, int H, int shift, double *__restrict__ out, int odim, int col0)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * sdim) return;
+  int64_t r = i / sdim;
+  int c = (int)(i - r * sdim);
+  int64_t q = r;
+  if (shift) {
+    const UttDesc ud = utts[row_utt[r]];
+    q = nb_row(r, shift, ud.row_off, ud.row_off + ud.n_rows_out + 2 * H - 1);
+  }
+  out[r * odim + col0 + c] = src[q * sdim + c];
+}
+
+// NormalizationModule::generate (:1136-1142)
+__global__ void fe_norm(const double *__restrict__ src, int dim, int64_t n_rows, const float *__restrict__ mean,
+                        const float *__restrict__ scale, double *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  int c = (int)(i % dim);
+  out[i] = __dmul_rn(__dsub_rn(src[i], (double)mean[c]), (double)scale[c]);
+}
+
+// LinTransformModule::generate (:1244-1269)
+__global__ void fe_lintrans(const double *__restrict__ src, int sdim, int64_t n_rows, const float *__restrict__ mat,
+                            int has_mat, const float *__restrict__ bias, int has_bias, int dim, double *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  int64_t r = i / dim;
+  int c = (int)(i - r * dim);
+  const double *s = src + r * sdim;
+  double acc;
+  if (has_mat) {
+    acc = 0;
+    const float *m = mat + (size_t)c * sdim;
+    for (int j = 0; j < sdim; j++) acc = __dadd_rn(acc, __dmul_rn((double)m[j], s[j]));
+  } else {
+    acc = s[c];
+  }
+  if (has_bias) acc = __dadd_rn(acc, (double)bias[c]);
+  out[r * dim + c] = acc;
+}
+
+// MeanSubtractorModule::generate, full-window branch (:1436-1447): mean over frames t-left..t+right.
+__global__ void fe_meansub(const double *__restrict__ src, int dim, int64_t n_rows, const int *__restrict__ row_utt,
+                           const UttDesc *__restrict__ utts, int H, int left, int right, double *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  int64_t r = i / dim;
+  int c = (int)(i - r * dim);
+  const UttDesc ud = utts[row_utt[r]];
+  const int64_t lo = ud.row_off, hi = ud.row_off + ud.n_rows_out + 2 * H - 1;
+  double m = 0;
+  for (int k = -left; k <= right; k++) m = __dadd_rn(m, src[nb_row(r, k, lo, hi) * dim + c]);
+  m = __ddiv_rn(m, (double)(left + right + 1));
+  out[i] = __dsub_rn(src[i], m);
+}
+
+// Drop the halo: rows (u, start..start+n_rows_out-1) -> dense output, float or double.
+template <class T>
+__global__ void fe_gather(const double *__restrict__ src, int dim, const UttDesc *__restrict__ utts,
+                          const int *__restrict__ row_utt, int64_t n_rows, int H, T *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  int64_t r = i / dim;
+  int c = (int)(i - r * dim);
+  const UttDesc ud = utts[row_utt[r]];
+  int64_t k = r - ud.row_off - H;
+  if (k < 0 || k >= ud.n_rows_out) return;
+  out[(ud.out_off + k) * dim + c] = (T)src[i];
+}
+
+// ===================================================================================
+// graph execution
+namespace {
+
+inline unsigned grid1(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+struct Plan {
+  std::vector<char> needed;
+  int H = 0;
+};
+
+Plan make_plan(const Frontend &fe, int target)
+{
+  Plan p;
+  const int n = (int)fe.mods.size();
+  p.needed.assign(n, 0);
+  std::vector<int> el(n, 0), er(n, 0);
+  p.needed[target] = 1;
+  for (int m = target; m >= 0; m--) {
+    if (!p.needed[m]) continue;
+    const Module &mod = fe.mods[m];
+    for (int s : mod.src) {
+      p.needed[s] = 1;
+      el[s] = std::max(el[s], el[m] + mod.left);
+      er[s] = std::max(er[s], er[m] + mod.right);
+    }
+  }
+  for (int m = 0; m < n; m++) if (p.needed[m]) p.H = std::max(p.H, std::max(el[m], er[m]));
+  return p;
+}
+
+// Runs the graph for a set of utterance descriptors whose PCM is device resident.
+void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts, int target, void *d_out, int out_f64,
+               int64_t out_row_base)
+{
+  const Frontend &fe = ctx->fe;
+  if (target < 0) target = fe.last;
+  Plan plan = make_plan(fe, target);
+  const int H = plan.H;
+  int64_t n_rows = 0;
+  for (auto &u : utts) { u.row_off = n_rows; n_rows += (int64_t)u.n_rows_out + 2 * H; }
+  if (n_rows == 0) return;
+  std::vector<int> row_utt((size_t)n_rows);
+  for (size_t u = 0; u < utts.size(); u++)
+    for (int64_t r = utts[u].row_off; r < utts[u].row_off + utts[u].n_rows_out + 2 * H; r++) row_utt[(size_t)r] = (int)u;
+  cudaStream_t st = ctx->stream;
+  DevBuf &d_utts = ctx->d_fe[0], &d_rowutt = ctx->d_fe[1];
+  d_utts.reserve(utts.size() * sizeof(UttDesc));
+  d_rowutt.reserve(row_utt.size() * sizeof(int));
+  AKU_CUDA(cudaMemcpyAsync(d_utts.p, utts.data(), utts.size() * sizeof(UttDesc), cudaMemcpyHostToDevice, st));
+  AKU_CUDA(cudaMemcpyAsync(d_rowutt.p, row_utt.data(), row_utt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  // the pageable sources above must stay alive until the copies are done
+  AKU_CUDA(cudaStreamSynchronize(st));
+  const UttDesc *du = d_utts.as<UttDesc>();
+  const int *dr = d_rowutt.as<int>();
+
+  // one buffer per needed module (the base module is fused into fft and has none)
+  std::vector<std::shared_ptr<DevBuf>> buf(fe.mods.size());
+  const Module &base = fe.mods[0];
+  for (int m = 1; m <= target; m++) {
+    if (!plan.needed[m]) continue;
+    const Module &mod = fe.mods[m];
+    if (mod.type != M_FFT)
+      for (int s : mod.src)
+        if (s == 0) throw Error(AKUGPU_E_CONFIG, "the audiofile module can only feed an fft module");
+    if ((int)ctx->fe_bufs.size() <= m) ctx->fe_bufs.resize(m + 1);
+    if (!ctx->fe_bufs[m]) ctx->fe_bufs[m] = std::make_shared<DevBuf>();
+    buf[m] = ctx->fe_bufs[m];
+    buf[m]->reserve((size_t)n_rows * mod.dim * sizeof(double));
+    double *o = buf[m]->as<double>();
+    const double *s0 = mod.src.empty() || mod.src[0] == 0 ? nullptr : buf[mod.src[0]]->as<double>();
+    const int sdim = mod.src.empty() ? 0 : fe.mods[mod.src[0]].dim;
+    const int64_t ne = n_rows * mod.dim;
+    switch (mod.type) {
+      case M_FFT: {
+        const int N = base.window_width;
+        const float *win = mod.d_a->as<float>();
+        const float2 *tw = mod.d_b->as<float2>();
+#define SPEC_POW2(NN)                                                                                               \
+  case NN: {                                                                                                        \
+    constexpr int M_ = NN / 2;                                                                                      \
+    constexpr int TPF_ = (M_ / 2 < 32) ? 32 : ((M_ / 2 > 256) ? 256 : M_ / 2);                                      \
+    constexpr int FPB_ = 256 / TPF_;                                                                                \
+    fe_spectrum_pow2<NN><<<grid1(n_rows, FPB_), 256, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,        \
+                                                              base.emph, base.copy_borders, win, tw, mod.magnitude, \
+                                                              mod.log, o);                                          \
+    break;                                                                                                          \
+  }
+        switch (N) {
+          SPEC_POW2(128)
+          SPEC_POW2(256)
+          SPEC_POW2(512)
+          SPEC_POW2(1024)
+          SPEC_POW2(2048)
+          default:
+            fe_spectrum_dft<<<(unsigned)n_rows, 128, N * sizeof(float), st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,
+                                                                             base.emph, base.copy_borders, win, tw, N,
+                                                                             mod.magnitude, mod.log, o);
+        }
+#undef SPEC_POW2
+        break;
+      }
+      case M_MEL:
+        fe_mel<<<grid1(ne, 256), 256, 0, st>>>(s0, sdim, n_rows, mod.d_a->as<float>(), mod.dim, mod.root, o);
+        break;
+      case M_POWER:
+        fe_power<<<grid1(n_rows, 128), 128, 0, st>>>(s0, sdim, n_rows, 0, o);
+        break;
+      case M_MEL_POWER:
+        fe_power<<<grid1(n_rows, 128), 128, 0, st>>>(s0, sdim, n_rows, 1, o);
+        break;
+      case M_DCT:
+        fe_dct<<<grid1(ne, 256), 256, 0, st>>>(s0, sdim, n_rows, mod.d_a->as<float>(), mod.dim, o);
+        break;
+      case M_DELTA:
+        fe_delta<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, dr, du, H, mod.width, mod.norm, o);
+        break;
+      case M_MERGE: {
+        int col = 0;
+        for (int s : mod.src) {
+          const int sd = fe.mods[s].dim;
+          fe_copy<<<grid1(n_rows * sd, 256), 256, 0, st>>>(buf[s]->as<double>(), sd, n_rows, dr, du, H, 0, o, mod.dim, col);
+          ctx->launches++;
+          col += sd;
+        }
+        ctx->launches--;
+        break;
+      }
+      case M_CONCAT: {
+        int col = 0;
+        for (int k = -mod.left; k <= mod.right; k++) {
+          fe_copy<<<grid1(n_rows * sdim, 256), 256, 0, st>>>(s0, sdim, n_rows, dr, du, H, k, o, mod.dim, col);
+          ctx->launches++;
+          col += sdim;
+        }
+        ctx->launches--;
+        break;
+      }
+      case M_NORMALIZATION:
+        fe_norm<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, mod.d_a->as<float>(), mod.d_b->as<float>(), o);
+        break;
+      case M_LIN_TRANSFORM:
+        fe_lintrans<<<grid1(ne, 256), 256, 0, st>>>(s0, sdim, n_rows, mod.d_a->as<float>(), mod.matrix_defined ? 1 : 0,
+                                                    mod.d_b->as<float>(), mod.bias_defined ? 1 : 0, mod.dim, o);
+        break;
+      case M_MEAN_SUBTRACTOR:
+        fe_meansub<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, dr, du, H, mod.left, mod.right, o);
+        break;
+      default:
+        throw Error(AKUGPU_E_CONFIG, "module '" + mod.name + "' cannot be evaluated here");
+    }
+    AKU_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (target == 0) throw Error(AKUGPU_E_CONFIG, "the raw audiofile module output is not materialised on the GPU");
+  const int dim = fe.mods[target].dim;
+  if (out_f64)
+    fe_gather<double><<<grid1(n_rows * dim, 256), 256, 0, st>>>(buf[target]->as<double>(), dim, du, dr, n_rows, H,
+                                                                (double *)d_out + out_row_base * dim);
+  else
+    fe_gather<float><<<grid1(n_rows * dim, 256), 256, 0, st>>>(buf[target]->as<double>(), dim, du, dr, n_rows, H,
+                                                               (float *)d_out + out_row_base * dim);
+  AKU_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+}  // namespace
+
+void frontend_run_range(akugpu_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, int start, int end, int target,
+                        void *d_out, int out_f64)
+{
+  const int64_t nf = frontend_num_frames(ctx->fe, n_samples);
+  if (nf <= 0) throw Error(AKUGPU_E_ARG, "audio shorter than frame");
+  std::vector<UttDesc> utts(1);
+  UttDesc &u = utts[0];
+  u.pcm_off = 0; u.n_samples = n_samples; u.row_off = 0; u.out_off = 0;
+  u.n_frames = (int)nf; u.start = start; u.n_rows_out = end - start; u.pad = 0;
+  run_graph(ctx, d_pcm, utts, target, d_out, out_f64, 0);
+}
+
+void frontend_run_batch(akugpu_ctx *ctx, const int16_t *d_pcm, const std::vector<int64_t> &utt_off,
+                        const std::vector<int64_t> &frame_off, void *d_out, int out_f64)
+{
+  const int n = (int)utt_off.size() - 1;
+  const int64_t max_rows = 262144;   // rows per pass: bounds the module buffers (spectrum: rows*129*8 B)
+  int u0 = 0;
+  while (u0 < n) {
+    std::vector<UttDesc> utts;
+    int64_t rows = 0;
+    int u1 = u0;
+    while (u1 < n && (u1 == u0 || rows + (frame_off[u1 + 1] - frame_off[u1]) <= max_rows)) {
+      UttDesc u;
+      u.pcm_off = utt_off[u1]; u.n_samples = utt_off[u1 + 1] - utt_off[u1]; u.row_off = 0;
+      u.out_off = frame_off[u1] - frame_off[u0];
+      u.n_frames = (int)(frame_off[u1 + 1] - frame_off[u1]); u.start = 0; u.n_rows_out = u.n_frames; u.pad = 0;
+      rows += u.n_frames;
+      utts.push_back(u);
+      u1++;
+    }
+    run_graph(ctx, d_pcm, utts, -1, d_out, out_f64, frame_off[u0]);
+    u0 = u1;
+  }
+}
+
+}  // namespace akugpu

@@ -1,0 +1,51 @@
+// kernels.hpp -- launchers shared between the translation units of libakugpu.so.
+#pragma once
+#include "ctx.hpp"
+#include <algorithm>
+
+namespace akugpu {
+
+// gmm_kernels.cu
+size_t gmm_f32_smem_bytes(const PackedF32 &p);
+void launch_gmm_f32(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll,
+                    int64_t ldF);
+void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, double *lin,
+                    int64_t ldF);
+void launch_transpose_f32(akugpu_ctx *ctx, const float *in, int64_t ldF, int S, int64_t F, float *out);
+void launch_transpose_f64(akugpu_ctx *ctx, const double *in, int64_t ldF, int S, int64_t F, double *out);
+void pipe_rates(akugpu_ctx *ctx, double out[4]);
+
+// lna_kernels.cu
+void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
+                    uint8_t *out);
+void launch_lna_f64(akugpu_ctx *ctx, const double *lin, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
+                    uint8_t *out);
+void launch_checksum(akugpu_ctx *ctx, const uint8_t *buf, int64_t nbytes, unsigned long long *acc);
+
+// model.cu
+void model_read_files(const std::string &base, HostModel &hm);
+void model_pack(akugpu_ctx *ctx);
+
+// frontend_config.cc / frontend_kernels.cu
+void frontend_parse(akugpu_ctx *ctx, const std::string &text);
+void frontend_set_parameters(akugpu_ctx *ctx, const std::string &module, const std::string &text);
+int64_t frontend_num_frames(const Frontend &fe, int64_t n_samples);
+// Computes module `target` (or the last module when target<0) for ONE utterance whose PCM is on the
+// device, for frames [start,end) in reference frame numbering; writes [end-start][dim] float or double.
+void frontend_run_range(akugpu_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, int start, int end, int target,
+                        void *d_out, int out_f64);
+// Batch: all utterances, frames 0..n_u-1 each, into d_out [sum n_u][dim].
+void frontend_run_batch(akugpu_ctx *ctx, const int16_t *d_pcm, const std::vector<int64_t> &utt_off,
+                        const std::vector<int64_t> &frame_off, void *d_out, int out_f64);
+
+// stage timing (api.cu)
+struct StageScope {
+  akugpu_ctx *ctx;
+  int stage;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int64_t l0;
+  StageScope(akugpu_ctx *c, int s);
+  ~StageScope();
+};
+
+}  // namespace akugpu

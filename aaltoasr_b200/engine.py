@@ -1,0 +1,231 @@
+"""Thin object wrapper over the C ABI (include/akugpu.h).
+
+Buffers may be numpy arrays (host) or torch tensors (CUDA or pinned host); only their
+address crosses the boundary.  All arithmetic happens in libakugpu.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import AkuGpuError, load_library
+
+F32 = 0   # AKUGPU_F32: throughput mode
+F64 = 1   # AKUGPU_F64: parity mode (the reference's arithmetic in double)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return C.c_void_p(x.data_ptr())
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return C.c_void_p(x.ctypes.data)
+    raise TypeError("expected numpy array or torch tensor, got %r" % type(x))
+
+
+def _is_f64(x):
+    if _is_torch(x):
+        import torch
+        if x.dtype == torch.float64:
+            return 1
+        if x.dtype == torch.float32:
+            return 0
+    else:
+        if x.dtype == np.float64:
+            return 1
+        if x.dtype == np.float32:
+            return 0
+    raise TypeError("features must be float32 or float64")
+
+
+class AkuGpu:
+    """One context = one GPU = one host thread (not thread-safe, like the reference classes)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = self._lib.akugpu_create(int(device))
+        if not self._h:
+            raise AkuGpuError(-1, self._lib.akugpu_last_error(None).decode())
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.akugpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AkuGpuError(rc, self._lib.akugpu_last_error(self._h).decode())
+
+    # ---- context ----
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._lib.akugpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def synchronize(self):
+        self._ck(self._lib.akugpu_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._lib.akugpu_launch_count(self._h))
+
+    def stage_times_reset(self, enable=True):
+        self._ck(self._lib.akugpu_stage_times_reset(self._h, 1 if enable else 0))
+
+    def stage_times(self):
+        ms = (C.c_double * 3)()
+        n = (C.c_int64 * 3)()
+        self._ck(self._lib.akugpu_stage_times(self._h, ms, n))
+        return {"frontend": (ms[0], n[0]), "gmm": (ms[1], n[1]), "lna": (ms[2], n[2])}
+
+    def set_chunk_frames(self, frames):
+        self._ck(self._lib.akugpu_set_chunk_frames(self._h, int(frames)))
+
+    def set_scorer_variant(self, variant):
+        self._ck(self._lib.akugpu_set_scorer_variant(self._h, int(variant)))
+
+    def pipe_rates(self):
+        out = (C.c_double * 4)()
+        self._ck(self._lib.akugpu_pipe_rates(self._h, out))
+        return {"ffma": out[0], "ffma2": out[1], "dfma": out[2], "ex2": out[3]}
+
+    # ---- front-end ----
+    def frontend_load_config(self, path):
+        self._ck(self._lib.akugpu_frontend_load_config(self._h, str(path).encode()))
+
+    def frontend_load_config_text(self, text):
+        self._ck(self._lib.akugpu_frontend_load_config_text(self._h, text.encode()))
+
+    def frontend_set_parameters(self, module, text):
+        self._ck(self._lib.akugpu_frontend_set_parameters(self._h, module.encode(), text.encode()))
+
+    @property
+    def feature_dim(self):
+        d = self._lib.akugpu_frontend_dim(self._h)
+        if d < 0:
+            raise AkuGpuError(d, "no feature configuration loaded")
+        return d
+
+    @property
+    def sample_rate(self):
+        return self._lib.akugpu_frontend_sample_rate(self._h)
+
+    @property
+    def frame_rate(self):
+        return float(self._lib.akugpu_frontend_frame_rate(self._h))
+
+    def num_frames(self, n_samples):
+        n = self._lib.akugpu_frontend_num_frames(self._h, int(n_samples))
+        if n < 0:
+            raise AkuGpuError(int(n), "no feature configuration loaded")
+        return int(n)
+
+    def frame_offsets(self, utt_offsets):
+        uo = np.ascontiguousarray(utt_offsets, dtype=np.int64)
+        fo = np.zeros(len(uo), dtype=np.int64)
+        self._ck(self._lib.akugpu_features(self._h, None, _ptr(uo), len(uo) - 1, None, 0, _ptr(fo)))
+        return fo
+
+    def features(self, pcm, utt_offsets=None, dtype=np.float32, out=None):
+        """pcm: int16 array/tensor (all utterances concatenated); returns ([F x dim], frame_offsets)."""
+        n = int(pcm.numel() if _is_torch(pcm) else pcm.size)
+        uo = np.ascontiguousarray(utt_offsets if utt_offsets is not None else [0, n], dtype=np.int64)
+        fo = self.frame_offsets(uo)
+        if out is None:
+            out = np.empty((int(fo[-1]), self.feature_dim), dtype=dtype)
+        self._ck(self._lib.akugpu_features(self._h, _ptr(pcm), _ptr(uo), len(uo) - 1, _ptr(out), _is_f64(out), _ptr(fo)))
+        return out, fo
+
+    def features_range(self, pcm, start, end, module=None, dtype=np.float64):
+        """Frames [start,end) of one utterance in the reference's frame numbering (may leave the file)."""
+        n = int(pcm.numel() if _is_torch(pcm) else pcm.size)
+        dim = C.c_int(0)
+        self._ck(self._lib.akugpu_features_range(self._h, None, n, 0, 0, module.encode() if module else None, None, 0,
+                                                 C.byref(dim)))
+        out = np.empty((max(0, end - start), dim.value), dtype=dtype)
+        self._ck(self._lib.akugpu_features_range(self._h, _ptr(pcm), n, int(start), int(end),
+                                                 module.encode() if module else None, _ptr(out), _is_f64(out),
+                                                 C.byref(dim)))
+        return out
+
+    # ---- model ----
+    def model_read(self, base):
+        self._ck(self._lib.akugpu_model_read(self._h, str(base).encode()))
+
+    def model_load_diag(self, mix_offsets, mix_gauss, mix_weight, means, covs):
+        mo = np.ascontiguousarray(mix_offsets, dtype=np.int32)
+        mg = np.ascontiguousarray(mix_gauss, dtype=np.int32)
+        mw = np.ascontiguousarray(mix_weight, dtype=np.float64)
+        mu = np.ascontiguousarray(means, dtype=np.float64)
+        cv = np.ascontiguousarray(covs, dtype=np.float64)
+        if mu.ndim != 2 or mu.shape != cv.shape:
+            raise ValueError("means/covs must be [G x D]")
+        self._ck(self._lib.akugpu_model_load_diag(self._h, len(mo) - 1, mu.shape[0], mu.shape[1], _ptr(mo), _ptr(mg),
+                                                  _ptr(mw), _ptr(mu), _ptr(cv)))
+
+    @property
+    def num_states(self):
+        return self._lib.akugpu_model_num_states(self._h)
+
+    @property
+    def model_dim(self):
+        return self._lib.akugpu_model_dim(self._h)
+
+    @property
+    def num_gaussians(self):
+        return self._lib.akugpu_model_num_gaussians(self._h)
+
+    # ---- scoring ----
+    def gmm_score(self, feats, precision=F32, out=None):
+        F = int(feats.shape[0])
+        if out is None:
+            out = np.empty((F, self.num_states), dtype=np.float64 if precision == F64 else np.float32)
+        self._ck(self._lib.akugpu_gmm_score(self._h, _ptr(feats), _is_f64(feats), F, precision, _ptr(out)))
+        return out
+
+    def gmm_lna(self, feats, precision=F32, lnabytes=2, normalize=True, out=None):
+        F = int(feats.shape[0])
+        if out is None:
+            out = np.empty((F, self.num_states * lnabytes), dtype=np.uint8)
+        self._ck(self._lib.akugpu_gmm_lna(self._h, _ptr(feats), _is_f64(feats), F, precision, lnabytes,
+                                          1 if normalize else 0, _ptr(out)))
+        return out
+
+    def phone_probs(self, pcm, utt_offsets=None, precision=F32, lnabytes=2, normalize=True, out=None, discard=False,
+                    checksum=False):
+        """PCM -> LNA records for a batch of utterances.  Returns (records [F x S*lnabytes] or None,
+        frame_offsets, checksum or None)."""
+        n = int(pcm.numel() if _is_torch(pcm) else pcm.size)
+        uo = np.ascontiguousarray(utt_offsets if utt_offsets is not None else [0, n], dtype=np.int64)
+        fo = np.zeros(len(uo), dtype=np.int64)
+        if out is None and not discard:
+            fo = self.frame_offsets(uo)
+            out = np.empty((int(fo[-1]), self.num_states * lnabytes), dtype=np.uint8)
+        chk = C.c_uint64(0)
+        self._ck(self._lib.akugpu_phone_probs(self._h, _ptr(pcm), _ptr(uo), len(uo) - 1, precision, lnabytes,
+                                              1 if normalize else 0, _ptr(out), _ptr(fo),
+                                              C.byref(chk) if checksum else None))
+        return out, fo, (int(chk.value) if checksum else None)
+
+    def lna_header(self, lnabytes):
+        buf = np.zeros(5, dtype=np.uint8)
+        self._lib.akugpu_lna_header(self.num_states, lnabytes, _ptr(buf))
+        return buf.tobytes()

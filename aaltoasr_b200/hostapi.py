@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's call surface for the accelerated path.
+
+Same names, argument meaning and error behaviour as the reference classes, so that code
+(and tests) written against them read the same:
+
+  FeatureGenerator  aku/FeatureGenerator.hh:23-123   load_configuration / open / generate(frame) /
+                                                      eof / last_frame / dim / frame_rate / sample_rate
+  HmmSet            aku/HmmSet.hh:94-571              read_all / reset_cache / precompute_likelihoods /
+                                                      state_likelihood / num_states / dim
+  PhoneProbs        aku/phone_probs.cc:46-267,        the tool's loop: recipe -> LNA files
+                    aku/PhoneProbsToolbox.cc:135-222  (PPToolbox: read_configuration/read_models/generate)
+
+The reference pulls one frame at a time through ring buffers and scores every Gaussian for
+that one frame.  Here the per-frame methods are served from whole-utterance results computed
+on the GPU (features once per open(), likelihoods once per utterance), which is what lets
+the same API run at B200 speed.  Errors surface as AkuGpuError (a RuntimeError), as the
+reference's SWIG layer turns `throw std::string` into RuntimeError.
+"""
+import os
+
+import numpy as np
+
+from . import formats
+from ._lib import AkuGpuError
+from .engine import AkuGpu, F32, F64
+
+
+class FeatureGenerator:
+    def __init__(self, engine=None, device=0):
+        self.engine = engine if engine is not None else AkuGpu(device)
+        self._pcm = None
+        self._feats = None
+        self._n = 0
+        self._eof_on_last_frame = False
+
+    def load_configuration(self, path_or_file):
+        if hasattr(path_or_file, "read"):
+            self.engine.frontend_load_config_text(path_or_file.read())
+        else:
+            self.engine.frontend_load_config(path_or_file)
+
+    def load_configuration_text(self, text):
+        self.engine.frontend_load_config_text(text)
+
+    def open(self, filename):
+        pcm, sr = formats.read_wav(filename)
+        if sr != self.engine.sample_rate:
+            # aku/FeatureModules.cc:254-261
+            raise AkuGpuError(-2, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree."
+                              % (sr, self.engine.sample_rate))
+        self.open_pcm(pcm)
+
+    def open_pcm(self, pcm):
+        self._pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        self._n = self.engine.num_frames(self._pcm.size)
+        if self._n <= 0:
+            raise AkuGpuError(-2, "audio shorter than frame")   # aku/FeatureModules.cc:409
+        self._feats, _ = self.engine.features(self._pcm, dtype=np.float64)
+        self._eof_on_last_frame = False
+
+    def close(self):
+        self._pcm = self._feats = None
+
+    def generate(self, frame):
+        """Feature vector of `frame` (any integer; frames outside the file behave as in the
+        reference: first/last window replicated at the base module)."""
+        if self._pcm is None:
+            raise AkuGpuError(-5, "no audio opened")
+        self._eof_on_last_frame = frame >= self._n
+        if 0 <= frame < self._n:
+            return self._feats[frame]
+        return self.engine.features_range(self._pcm, frame, frame + 1)[0]
+
+    def features(self):
+        """All frames 0..last_frame() at once, [F x dim] float64."""
+        return self._feats
+
+    def eof(self):
+        return self._eof_on_last_frame
+
+    def last_frame(self):
+        return self._n - 1
+
+    def dim(self):
+        return self.engine.feature_dim
+
+    def frame_rate(self):
+        return self.engine.frame_rate
+
+    def sample_rate(self):
+        return self.engine.sample_rate
+
+    def module_output(self, name, start, end):
+        return self.engine.features_range(self._pcm, start, end, module=name)
+
+
+class HmmSet:
+    def __init__(self, engine=None, device=0, precision=F64):
+        self.engine = engine if engine is not None else AkuGpu(device)
+        self.precision = precision
+        self._lik = None
+        self._row = None
+        self._utt = None
+
+    def read_all(self, base):
+        self.engine.model_read(base)
+
+    def num_states(self):
+        return self.engine.num_states
+
+    def dim(self):
+        return self.engine.model_dim
+
+    # Whole-utterance entry: score every frame once, then serve the per-frame API from it.
+    def set_utterance_features(self, feats):
+        feats = np.ascontiguousarray(feats)
+        self._utt = feats
+        out = self.engine.gmm_score(feats, precision=self.precision)
+        self._lik = out if self.precision == F64 else np.maximum(np.exp(out.astype(np.float64)), 1e-50)
+
+    def reset_cache(self):
+        self._row = None
+
+    def precompute_likelihoods(self, feature):
+        """feature: a frame index into the utterance given to set_utterance_features(), or a
+        feature vector (scored on the spot: the F=1 case of the same kernel)."""
+        if isinstance(feature, (int, np.integer)):
+            self._row = self._lik[int(feature)]
+        else:
+            v = np.ascontiguousarray(feature, dtype=np.float64).reshape(1, -1)
+            out = self.engine.gmm_score(v, precision=self.precision)[0]
+            self._row = out if self.precision == F64 else np.maximum(np.exp(out.astype(np.float64)), 1e-50)
+
+    def state_likelihood(self, state, feature=None):
+        if self._row is None:
+            self.precompute_likelihoods(feature)
+        return float(self._row[state])
+
+
+class PhoneProbs:
+    """aku/phone_probs as an object (and the PPToolbox method names)."""
+
+    def __init__(self, engine=None, device=0, precision=F32, lnabytes=2, normalize=True):
+        self.engine = engine if engine is not None else AkuGpu(device)
+        self.precision = precision
+        self.lnabytes = lnabytes
+        self.normalize = normalize
+
+    # PPToolbox names (aku/swig/PPToolbox.i:59-66)
+    def read_configuration(self, cfg):
+        self.engine.frontend_load_config(cfg)
+
+    def read_models(self, base):
+        self.engine.model_read(base)
+
+    def generate(self, audio_path, lna_path):
+        pcm, sr = formats.read_wav(audio_path)
+        if sr != self.engine.sample_rate:
+            raise AkuGpuError(-2, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree."
+                              % (sr, self.engine.sample_rate))
+        rec, _, _ = self.engine.phone_probs(pcm, precision=self.precision, lnabytes=self.lnabytes,
+                                            normalize=self.normalize)
+        formats.write_lna(lna_path, rec, self.engine.num_states, self.lnabytes)
+        return rec.shape[0]
+
+    def run_recipe(self, recipe_path, out_dir="", batch=1, bindex=1, no_overwrite=False, audio_ext_lna=False,
+                   max_batch_samples=64 << 20):
+        """The tool's recipe loop (aku/phone_probs.cc:135-267): utterances of this batch share GPU
+        launches; output files are per utterance like the reference's."""
+        infos = formats.read_recipe(recipe_path)
+        if batch > 1:   # contiguous split like Recipe::read (aku/Recipe.cc:63-115)
+            n = len(infos)
+            per, rem = divmod(n, batch)
+            start = (bindex - 1) * per + min(bindex - 1, rem)
+            infos = infos[start:start + per + (1 if bindex - 1 < rem else 0)]
+        todo = []
+        for info in infos:
+            if audio_ext_lna or "lna" not in info:
+                name = os.path.splitext(os.path.basename(info["audio"]))[0] + ".lna"
+            else:
+                name = info["lna"]
+            path = os.path.join(out_dir, name) if out_dir else name
+            if no_overwrite and os.path.exists(path) and os.path.getsize(path) > 0:
+                continue
+            todo.append((info, path))
+        written = 0
+        i = 0
+        while i < len(todo):
+            pcms, j, tot = [], i, 0
+            while j < len(todo) and (j == i or tot < max_batch_samples):
+                pcm, sr = formats.read_wav(todo[j][0]["audio"])
+                if sr != self.engine.sample_rate:
+                    raise AkuGpuError(-2, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree."
+                                      % (sr, self.engine.sample_rate))
+                pcms.append(pcm)
+                tot += pcm.size
+                j += 1
+            uo = np.zeros(len(pcms) + 1, dtype=np.int64)
+            uo[1:] = np.cumsum([p.size for p in pcms])
+            rec, fo, _ = self.engine.phone_probs(np.concatenate(pcms), uo, precision=self.precision,
+                                                 lnabytes=self.lnabytes, normalize=self.normalize)
+            fr = self.engine.frame_rate
+            for k in range(len(pcms)):
+                info, path = todo[i + k]
+                a, b = int(fo[k]), int(fo[k + 1])
+                s = int(float(info.get("start-time", 0) or 0) * fr)          # aku/phone_probs.cc:199-206
+                e = int(float(info.get("end-time", 0) or 0) * fr)
+                if e == 0:
+                    e = b - a
+                formats.write_lna(path, rec[a + min(s, b - a):a + min(e, b - a)], self.engine.num_states, self.lnabytes)
+                written += 1
+            i = j
+        return written

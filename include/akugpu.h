@@ -1,0 +1,158 @@
+/* akugpu.h -- C ABI of the B200-native acoustic front-end for AaltoASR.
+ *
+ * One shared library (aaltoasr_b200/libakugpu.so), plain pointers and sizes, no
+ * C++/torch types, no exceptions across the boundary.  Each entry point names
+ * the reference interface it replaces (paths relative to the AaltoASR tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (AKUGPU_E_*); the message
+ *     is available from akugpu_last_error(ctx)   [reference: `throw std::string`,
+ *     e.g. aku/FeatureModules.cc:334, aku/Distributions.cc:2872].
+ *   - data pointers may be HOST or DEVICE memory; the library detects which with
+ *     cudaPointerGetAttributes.  Host buffers are staged through pinned memory and
+ *     overlapped with compute; device buffers are used in place.
+ *   - one context per host thread / GPU; a context is not thread-safe (the
+ *     reference classes are not re-entrant either: aku/HmmSet.hh:550-553).
+ *   - frames are rows; features are row-major [frames x dim].
+ *   - there is NO CPU fallback: without a CUDA device akugpu_create() fails.
+ */
+#ifndef AKUGPU_H
+#define AKUGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct akugpu_ctx akugpu_ctx;
+
+enum {
+  AKUGPU_OK = 0,
+  AKUGPU_E_CUDA = -1,      /* CUDA runtime error                                  */
+  AKUGPU_E_ARG = -2,       /* bad argument / inconsistent sizes                   */
+  AKUGPU_E_CONFIG = -3,    /* feature configuration not supported / malformed     */
+  AKUGPU_E_MODEL = -4,     /* model files malformed / unsupported PDF type        */
+  AKUGPU_E_STATE = -5,     /* call order (no model / no front-end configured)     */
+  AKUGPU_E_IO = -6         /* file could not be read / written                    */
+};
+
+/* Arithmetic of the Gaussian scorer + LNA epilogue.
+ * F32: throughput mode (float log-probs within 1e-4 relative of the reference).
+ * F64: parity mode, follows aku/Distributions.cc:1041-1062,2079-2086 and
+ *      aku/phone_probs.cc:225-259 operation by operation in double. */
+enum { AKUGPU_F32 = 0, AKUGPU_F64 = 1 };
+
+/* ---- context ----------------------------------------------------------------- */
+akugpu_ctx *akugpu_create(int device);             /* NULL if no usable CUDA device */
+void        akugpu_destroy(akugpu_ctx *ctx);
+const char *akugpu_last_error(akugpu_ctx *ctx);    /* ctx may be NULL: last create() error */
+/* Use an existing CUDA stream (cudaStream_t) for all work; NULL = context's own. */
+int         akugpu_set_stream(akugpu_ctx *ctx, void *cuda_stream);
+int         akugpu_synchronize(akugpu_ctx *ctx);
+/* Number of kernels this library has launched on ctx since creation. */
+int64_t     akugpu_launch_count(akugpu_ctx *ctx);
+/* Device time (ms, CUDA events on the launching stream) spent in the named stage
+ * since the last akugpu_stage_times_reset(): 0 front-end, 1 GMM scorer, 2 LNA epilogue. */
+int         akugpu_stage_times(akugpu_ctx *ctx, double ms_out[3], int64_t launches_out[3]);
+int         akugpu_stage_times_reset(akugpu_ctx *ctx, int enable);
+
+/* ---- feature front-end ---------------------------------------------------------
+ * Replaces FeatureGenerator::load_configuration (aku/FeatureGenerator.cc:97-219)
+ * and the module classes of aku/FeatureModules.cc.  The text is the reference's
+ * own `module { name .. type .. sources .. }` format.  Supported module types:
+ * audiofile, fft, mel, power, mel_power, dct, delta, merge, concat, normalization,
+ * lin_transform, mean_subtractor.  Others return AKUGPU_E_CONFIG. */
+int   akugpu_frontend_load_config(akugpu_ctx *ctx, const char *cfg_path);
+int   akugpu_frontend_load_config_text(akugpu_ctx *ctx, const char *cfg_text);
+int   akugpu_frontend_dim(akugpu_ctx *ctx);            /* FeatureGenerator::dim()         */
+int   akugpu_frontend_sample_rate(akugpu_ctx *ctx);    /* FeatureGenerator::sample_rate() */
+float akugpu_frontend_frame_rate(akugpu_ctx *ctx);     /* FeatureGenerator::frame_rate()  */
+/* Number of frames the reference generates before eof() for an audio file of
+ * n_samples samples (aku/FeatureModules.cc:371-424: frame f is valid iff
+ * (int)(f*window_advance) + window_width + 1 <= n_samples). */
+int64_t akugpu_frontend_num_frames(akugpu_ctx *ctx, int64_t n_samples);
+/* FeatureModule::set_parameters for a named module (aku/FeatureModule.hh:107):
+ * `text` holds `key value...` lines as in a config block (e.g. "matrix ...", "bias ..."). */
+int   akugpu_frontend_set_parameters(akugpu_ctx *ctx, const char *module_name, const char *text);
+
+/* Batch feature computation: replaces the per-frame FeatureGenerator::generate(f)
+ * loop (aku/FeatureGenerator.cc:267-273) for whole utterances.
+ *   pcm            int16 mono samples of all utterances, concatenated
+ *   utt_offsets    [n_utts+1] sample offsets into pcm (host memory)
+ *   out            [total_frames x dim] features, float (out_f64=0) or double
+ *   frame_offsets  [n_utts+1] receives the frame offset of each utterance (host)
+ * Frames of utterance u are 0 .. num_frames(len_u)-1, borders handled as the
+ * reference does (first/last window replicated, aku/FeatureModules.cc:381-422).
+ * Pass out=NULL to only fill frame_offsets. */
+int akugpu_features(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts,
+                    void *out, int out_f64, int64_t *frame_offsets);
+/* Same pipeline for an explicit frame range [start,end) of ONE utterance, frames
+ * outside the file behaving as in the reference (feacat --start-frame/--end-frame,
+ * aku/feacat.cc:96-110).  module_name != NULL returns that module's output
+ * instead of the last module's (FeatureGenerator::module(name)->at(f)). */
+int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples,
+                          int start_frame, int end_frame, const char *module_name,
+                          void *out, int out_f64, int *dim_out);
+
+/* ---- acoustic model --------------------------------------------------------------
+ * Replaces HmmSet::read_all / read_mc / read_ph / read_gk (aku/HmmSet.cc:157-357,
+ * aku/Distributions.cc:2812-2910) and the parameter side of DiagonalGaussian
+ * (aku/Distributions.cc:1132-1150,1274-1288) and Mixture (:2419-2434,2068-2075). */
+int akugpu_model_read(akugpu_ctx *ctx, const char *base);   /* base.mc, base.ph, base.gk */
+/* Direct load.  State s owns components mix_offsets[s] .. mix_offsets[s+1]-1;
+ * component k refers to Gaussian mix_gauss[k] with weight mix_weight[k]
+ * (weights are re-normalised per state like Mixture::normalize_weights()).
+ * means/covs are [G x D]; cov <= 0 disables that dimension exactly as the
+ * reference does. */
+int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim,
+                           const int32_t *mix_offsets, const int32_t *mix_gauss,
+                           const double *mix_weight, const double *means, const double *covs);
+int akugpu_model_num_states(akugpu_ctx *ctx);   /* HmmSet::num_states()  */
+int akugpu_model_dim(akugpu_ctx *ctx);          /* HmmSet::dim()         */
+int akugpu_model_num_gaussians(akugpu_ctx *ctx);
+
+/* ---- scoring -----------------------------------------------------------------------
+ * Replaces, for F frames at once, HmmSet::precompute_likelihoods +
+ * HmmSet::state_likelihood (aku/HmmSet.cc:485-501, aku/HmmSet.hh:309):
+ *   precision F32: out = float  [F x S] natural-log state likelihoods
+ *   precision F64: out = double [F x S] linear state likelihoods floored at 1e-50
+ *                  (exactly what state_likelihood() returns). */
+int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames,
+                     int precision, void *out);
+
+/* Scores + the normalise/quantise loop of aku/phone_probs.cc:225-262.
+ *   lnabytes 2: big-endian uint16 codes; 4: IEEE float32 little-endian
+ *   normalize 0 == phone_probs --no-normalization
+ *   out       [n_frames x S x lnabytes] bytes, no header.  */
+int akugpu_gmm_lna(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames,
+                   int precision, int lnabytes, int normalize, uint8_t *out);
+
+/* Whole path for a batch of utterances: PCM -> features -> scores -> LNA records
+ * (aku/phone_probs.cc:145-267 minus file I/O).  out receives the records of all
+ * utterances back to back (no per-file header); frame_offsets as in akugpu_features.
+ * out may be NULL (discard; for kernel-only timing) and checksum_out non-NULL to
+ * receive a 64-bit sum of all output bytes computed on the device. */
+int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts,
+                       int precision, int lnabytes, int normalize,
+                       uint8_t *out, int64_t *frame_offsets, uint64_t *checksum_out);
+
+/* Writes the 5-byte LNA header (aku/phone_probs.cc:213-214): big-endian uint32
+ * num_states, then lnabytes. */
+int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5]);
+
+/* ---- tuning / introspection ---------------------------------------------------- */
+/* Frames scored per chunk of the pipelined batch path (default 16384). */
+int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames);
+/* Kernel variant of the fp32 scorer: 0 = auto, 1 = FFMA (8 frames x 8 comps / thread),
+ * 2 = packed FFMA2 (8 frames x 4 comps x 2 dims / thread). */
+int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant);
+/* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
+ * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2. */
+int akugpu_pipe_rates(akugpu_ctx *ctx, double out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AKUGPU_H */

@@ -1,0 +1,41 @@
+#!/bin/bash
+# Builds the reference's OWN sources (read in place from $AKU_REF, default
+# /root/reference) into oracle/_ref/: the unmodified aku library + its literal
+# phone_probs and feacat tools, against the header shims in oracle/shim/ for the
+# two third-party dependencies that are absent here (LapackPP 2.5.4, libsndfile,
+# plus two Boost headers) and the reference's vendored KissFFT.
+# TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's
+# cpu_baseline / --impl reference legs may execute what this produces.
+# No reference source is copied into the repository; outputs are git-ignored.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+R="${AKU_REF:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$R/aku" ]; then
+  echo "build_ref.sh: $R/aku not found; keeping prebuilt oracle/_ref as is" >&2
+  exit 0
+fi
+mkdir -p "$OUT/obj"
+CXXFLAGS="-O2 -std=gnu++11 -DKISS_FFT -DDLLIMPORT= -fPIC -fpermissive -w -I$HERE/shim -I$R/aku -I$R/vendor/kiss_fft"
+LIBSRC="FeatureGenerator FeatureModules AudioReader ModuleConfig HmmSet PhnReader ModelModules SpeakerConfig Recipe conf io str endian Distributions LinearAlgebra HmmNetBaumWelch Lattice Viterbi PhonePool MllrTrainer ziggurat mtw LmbfgsOptimize RegClassTree SegErrorEvaluator util PhoneProbsToolbox"
+pids=()
+for f in $LIBSRC phone_probs feacat; do
+  if [ ! -f "$OUT/obj/$f.o" ] || [ "$R/aku/$f.cc" -nt "$OUT/obj/$f.o" ] || [ "$HERE/shim/lapackpp.h" -nt "$OUT/obj/$f.o" ] || [ "$HERE/shim/sndfile.h" -nt "$OUT/obj/$f.o" ]; then
+    g++ $CXXFLAGS -c "$R/aku/$f.cc" -o "$OUT/obj/$f.o" &
+    pids+=($!)
+  fi
+done
+for f in kiss_fft kiss_fftr; do
+  gcc -O2 -fPIC -w -I"$R/vendor/kiss_fft" -c "$R/vendor/kiss_fft/$f.c" -o "$OUT/obj/$f.o" &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+LIBOBJ=""
+for f in $LIBSRC kiss_fft kiss_fftr; do LIBOBJ="$LIBOBJ $OUT/obj/$f.o"; done
+rm -f "$OUT/libaku_ref.a"
+ar rcs "$OUT/libaku_ref.a" $LIBOBJ
+g++ -O2 -o "$OUT/ref_phone_probs" "$OUT/obj/phone_probs.o" "$OUT/libaku_ref.a" -lm
+g++ -O2 -o "$OUT/ref_feacat" "$OUT/obj/feacat.o" "$OUT/libaku_ref.a" -lm
+# Thin C-callable view of the reference classes for pytest (oracle/ref_capi.cc is ours).
+g++ $CXXFLAGS -shared -o "$OUT/libref_capi.so" "$HERE/ref_capi.cc" "$OUT/libaku_ref.a" -lm
+echo "oracle/_ref built: ref_phone_probs ref_feacat libref_capi.so"

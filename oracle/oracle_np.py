@@ -1,0 +1,459 @@
+"""oracle_np.py -- numpy restatement of the reference's hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product may import this module; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, and
+only as the checker.
+
+Every function restates one reference routine and cites it (paths relative to the AaltoASR
+tree).  The restatement is pinned against the reference itself: tests/test_oracle.py checks
+it against the aku/tests golden vectors (via tests/golden/aku_tests.npz) and against outputs
+of the reference's own code built into oracle/_ref (features to <=1e-5 absolute -- only the
+FFT's internal rounding order differs -- and the GMM+LNA stage bit for bit).
+
+Float/double placement follows the reference exactly: float
+pre-emphasis, float Hamming table (cosf), float32 FFT (the KissFFT build), sqrtf/logf,
+float mel accumulators, cosf DCT basis with double accumulation, float power accumulator,
+double deltas; double Gaussians; float/double hybrid LNA normalisation.
+"""
+import math
+
+import numpy as np
+
+f32 = np.float32
+# libm exp/log element by element: numpy's SIMD exp/log differ from glibc's in the last bit,
+# and the reference links glibc.
+_exp = np.frompyfunc(lambda v: math.exp(v) if v > -745.2 else 0.0, 1, 1)
+_log = np.frompyfunc(math.log, 1, 1)
+
+
+# ------------------------------------------------------------------------------------
+# feature configuration  (FeatureGenerator::load_configuration, aku/FeatureGenerator.cc:97-219;
+#                         ModuleConfig::read, aku/ModuleConfig.cc:166-203)
+def parse_config(text):
+    mods, cur, state = [], None, 0
+    for raw in text.splitlines():
+        line = raw.strip(" \t\r\n")
+        if not line:
+            continue
+        if state == 0:
+            if line != "module":
+                raise ValueError("expected keyword 'module': " + line)
+            cur, state = {}, 1
+        elif state == 1:
+            if line != "{":
+                raise ValueError("'{' expected in module config file: " + line)
+            state = 2
+        elif line == "}":
+            mods.append(cur)
+            state = 0
+        else:
+            parts = line.split(None, 1)
+            if len(parts) < 2:
+                raise ValueError("value missing for option: " + line)
+            if parts[0] in cur:
+                raise ValueError("value redefined: " + line)
+            cur[parts[0]] = parts[1].strip()
+    if state != 0:
+        raise ValueError("unexpected end of module config file")
+    return mods
+
+
+def _fvec(s):
+    return np.array([f32(float(x)) for x in s.split()], dtype=f32)
+
+
+class Pipeline:
+    """The module chain evaluated for whole utterances; frame indices follow the reference
+    (negative / past-EOF frames replicate the first / last window at the base module only)."""
+
+    def __init__(self, cfg_text, fft_dtype=np.float32):
+        self.mods = parse_config(cfg_text)
+        self.fft_dtype = fft_dtype
+        self.by_name = {}
+        for i, m in enumerate(self.mods):
+            m["sources"] = m.get("sources", "").split()
+            self.by_name[m["name"]] = i
+        self._setup()
+
+    # set_module_config of every module type
+    def _setup(self):
+        for m in self.mods:
+            t = m["type"]
+            src = [self.mods[self.by_name[s]] for s in m["sources"]]
+            sdim = src[-1]["dim"] if src else 0
+            m["left"] = m["right"] = 0
+            if t == "audiofile":   # aku/FeatureModules.cc:328-360
+                sr = int(m["sample_rate"])
+                m["sr"] = sr
+                m["emph"] = f32(float(m.get("pre_emph_coef", 0.97)))
+                m["frate"] = f32(float(m.get("frame_rate", 125)))
+                m["adv"] = f32(f32(sr) / m["frate"])
+                m["W"] = int(m["window_width"]) if "window_width" in m else int(f32(2 * sr) / m["frate"])
+                m["copy_borders"] = int(m.get("copy_borders", 1))
+                m["dim"] = m["W"]
+            elif t == "fft":       # :476-518
+                N = sdim
+                m["magnitude"] = int(m.get("magnitude", 1))
+                m["log"] = int(m.get("log", 0))
+                m["dim"] = N // 2 + 1
+                m["window"] = np.array(
+                    [f32(.54 - .46 * float(_cosf(2 * math.pi * i / (N - 1.0)))) for i in range(N)], dtype=f32)
+            elif t == "mel":       # :776-802
+                sr = self.mods[0]["sr"]
+                m["root"] = int(m.get("root", 0))
+                num = f32(f32(21 + 2) * _log10f(1 + sr / 1400.0))
+                m["dim"] = int(f32(f32(num / _log10f(1 + 16000 / 1400.0)) - f32(2)))
+                edges = m["dim"] + 2
+                rate = f32(sr)
+                mel_step = f32(f32(f32(2595) * _log10f(1.0 + float(rate) / 1400.0)) / f32(edges))
+                m["edges"] = np.array(
+                    [f32(1400.0 * (math.pow(10, float(f32(f32(f32(i + 1) * mel_step) / f32(2595)))) - 1) * (sdim - 1)
+                         / float(rate)) for i in range(edges)], dtype=f32)
+            elif t in ("power", "mel_power"):
+                m["dim"] = 1
+            elif t == "dct":       # :938-979
+                m["dim"] = int(m.get("dim", 12))
+                m["zeroth"] = int(m.get("zeroth", 0))
+                bias = 1 if m["zeroth"] else 0
+                tab = np.ones((m["dim"], sdim), dtype=f32)
+                for i in range(m["dim"] - bias):
+                    for b in range(sdim):
+                        tab[i + bias, b] = _cosf((i + 1) * (b + 0.5) * math.pi / sdim)
+                m["table"] = tab
+            elif t == "delta":     # :999-1016
+                m["dim"] = sdim
+                w = int(m.get("width", 2))
+                m["width"] = w
+                m["norm"] = f32(float(m["normalization"])) if "normalization" in m else f32(2 * w * (w + 1) * (2 * w + 1) // 6)
+                m["left"] = m["right"] = w
+            elif t == "merge":
+                m["dim"] = sum(s["dim"] for s in src)
+            elif t == "concat":    # :1473-1485
+                m["left"], m["right"] = int(m.get("left", 0)), int(m.get("right", 0))
+                m["dim"] = sdim * (1 + m["left"] + m["right"])
+            elif t == "normalization":   # :1057-1080
+                m["dim"] = sdim
+                m["mean_v"] = _fvec(m["mean"]) if "mean" in m else np.zeros(sdim, f32)
+                if "var" in m:
+                    m["scale_v"] = np.array([f32(f32(1) / np.sqrt(v, dtype=f32)) for v in _fvec(m["var"])], dtype=f32)
+                elif "scale" in m:
+                    m["scale_v"] = _fvec(m["scale"])
+                else:
+                    m["scale_v"] = np.ones(sdim, f32)
+            elif t == "lin_transform":   # :1167-1241
+                m["dim"] = int(m.get("dim", sdim))
+                m["matrix_v"] = _fvec(m["matrix"]).reshape(m["dim"], sdim) if "matrix" in m else None
+                m["bias_v"] = _fvec(m["bias"]) if "bias" in m else None
+            elif t == "mean_subtractor":  # :1385-1405
+                m["dim"] = sdim
+                m["left"], m["right"] = int(m.get("left", 75)), int(m.get("right", 75))
+            else:
+                raise ValueError("Unknown module type '%s'" % t)
+
+    @property
+    def dim(self):
+        return self.mods[-1]["dim"]
+
+    def num_frames(self, n_samples):
+        """Frames before eof(): frame f is whole iff (int)(f*adv)+W+1 <= N (aku/FeatureModules.cc:399-404)."""
+        a = self.mods[0]
+        f = 0
+        while int(f32(f32(f) * a["adv"])) + a["W"] + 1 <= n_samples:
+            f += 1
+        return f
+
+    def run(self, pcm, start=0, end=None, module=None):
+        """Output of `module` (default: last) for frames [start,end) (default end: first eof frame)."""
+        pcm = np.asarray(pcm, dtype=np.int16)
+        n = self.num_frames(pcm.size)
+        if n <= 0:
+            raise ValueError("audio shorter than frame")
+        if end is None:
+            end = n
+        tgt = self.by_name[module] if module else len(self.mods) - 1
+        # frame range each module is needed on (context propagated from the target back to the base),
+        # so that every module is evaluated exactly once
+        need = {tgt: [start, end]}
+        for mi in range(tgt, -1, -1):
+            if mi not in need:
+                continue
+            m = self.mods[mi]
+            for sname in m["sources"]:
+                si = self.by_name[sname]
+                lo, hi = need[mi][0] - m["left"], need[mi][1] + m["right"]
+                if si in need:
+                    need[si] = [min(need[si][0], lo), max(need[si][1], hi)]
+                else:
+                    need[si] = [lo, hi]
+        cache = {}
+        for mi in range(0, tgt + 1):
+            if mi in need and self.mods[mi]["type"] != "audiofile":
+                lo, hi = need[mi]
+                cache[mi] = (lo, self._eval(mi, np.arange(lo, hi), pcm, n, cache))
+        lo, arr = cache[tgt]
+        return arr[start - lo:end - lo]
+
+    def _eval(self, mi, frames, pcm, n, cache):
+        m = self.mods[mi]
+        t = m["type"]
+        src = [self.by_name[s] for s in m["sources"]]
+        def ev(si, fr):
+            lo, arr = cache[si]
+            return arr[fr[0] - lo:fr[-1] + 1 - lo]
+        if t == "fft":
+            return self._spectrum(m, self.mods[src[0]], frames, pcm, n)
+        if t == "audiofile":
+            raise ValueError("audiofile output is only consumed by fft")
+        if t == "mel":
+            return _mel(m, ev(src[0], frames))
+        if t == "power":       # :875-885  float accumulator, natural log
+            x = ev(src[0], frames)
+            p = np.zeros(x.shape[0], dtype=f32)
+            for i in range(x.shape[1]):
+                p = (p.astype(np.float64) + x[:, i]).astype(f32)
+            return np.log(p.astype(np.float64) + 1e-10)[:, None]
+        if t == "mel_power":   # :908-919
+            x = ev(src[0], frames)
+            p = np.zeros(x.shape[0], dtype=f32)
+            for i in range(x.shape[1]):
+                p = (p.astype(np.float64) + np.exp(x[:, i])).astype(f32)
+            return np.log(p.astype(np.float64) + 1e-10)[:, None]
+        if t == "dct":         # :956-979  double accumulate in b order
+            x = ev(src[0], frames)
+            out = np.zeros((x.shape[0], m["dim"]))
+            for b in range(x.shape[1]):
+                out += x[:, b:b + 1] * m["table"][:, b].astype(np.float64)[None, :]
+            return out
+        if t == "delta":       # :1019-1037
+            acc = np.zeros((len(frames), m["dim"]))
+            for k in range(1, m["width"] + 1):
+                acc += k * (ev(src[0], frames + k) - ev(src[0], frames - k))
+            return acc / float(m["norm"])
+        if t == "merge":
+            return np.concatenate([ev(s, frames) for s in src], axis=1)
+        if t == "concat":
+            return np.concatenate([ev(src[0], frames + k) for k in range(-m["left"], m["right"] + 1)], axis=1)
+        if t == "normalization":   # :1136-1142
+            x = ev(src[0], frames)
+            return (x - m["mean_v"].astype(np.float64)) * m["scale_v"].astype(np.float64)
+        if t == "lin_transform":   # :1244-1269
+            x = ev(src[0], frames)
+            if m["matrix_v"] is not None:
+                out = np.zeros((x.shape[0], m["dim"]))
+                M = m["matrix_v"].astype(np.float64)
+                for j in range(x.shape[1]):
+                    out += M[:, j][None, :] * x[:, j:j + 1]
+            else:
+                out = x[:, :m["dim"]].copy()
+            if m["bias_v"] is not None:
+                out = out + m["bias_v"].astype(np.float64)
+            return out
+        if t == "mean_subtractor":  # :1414-1454 (full-window branch; the recursive branch differs by ~1e-15)
+            x = ev(src[0], frames)
+            acc = np.zeros_like(x)
+            for k in range(-m["left"], m["right"] + 1):
+                acc += ev(src[0], frames + k)
+            return x - acc / float(m["left"] + m["right"] + 1)
+        raise ValueError(t)
+
+    def _spectrum(self, m, a, frames, pcm, n):
+        """AudioFileModule::generate (:371-440) + FFTModule::generate (:521-566)."""
+        W, N = a["W"], pcm.size
+        out = np.empty((len(frames), m["dim"]))
+        x = np.concatenate([pcm.astype(f32), np.zeros(W + 2, f32)])
+        uniq = {}
+        for i, fr in enumerate(frames):
+            fc = min(max(int(fr), 0), n - 1) if a["copy_borders"] else int(fr)
+            if fc in uniq:
+                out[i] = out[uniq[fc]]
+                continue
+            uniq[fc] = i
+            ws = int(f32(f32(fc) * a["adv"]))
+            idx = np.arange(ws, ws + W + 1)
+            ok = (idx >= 0) & (idx < N)
+            seg = np.where(ok, x[np.clip(idx, 0, N + W)], f32(0)).astype(f32)
+            pre = (seg[1:] - (a["emph"] * seg[:-1]).astype(f32)).astype(f32)              # float pre-emphasis
+            win = (m["window"].astype(np.float64) * pre.astype(np.float64)).astype(f32)     # float*double -> float
+            spec = np.fft.rfft(win.astype(self.fft_dtype))
+            if self.fft_dtype == np.float32:
+                spec = _fft_float32(win)
+            re, im = spec.real.astype(f32), spec.imag.astype(f32)
+            p = (re * re + im * im).astype(f32)
+            if m["magnitude"]:
+                p = np.sqrt(p, dtype=f32)
+            if m["log"]:
+                p = np.log(p, dtype=f32)
+            out[i] = p.astype(np.float64)
+        return out
+
+
+def _fft_float32(x):
+    """Real FFT in float32 arithmetic (radix-2 for powers of two, like the float KissFFT build,
+    vendor/kiss_fft; numpy's pocketfft in float64 rounded otherwise)."""
+    n = x.size
+    if n & (n - 1):
+        return np.fft.rfft(x.astype(np.float64)).astype(np.complex64)
+    a = x.astype(np.complex64)
+    # iterative radix-2 DIT in complex64
+    bits = n.bit_length() - 1
+    rev = np.array([int(format(i, "0%db" % bits)[::-1], 2) for i in range(n)])
+    a = a[rev]
+    length = 2
+    while length <= n:
+        half = length // 2
+        w = np.exp(-2j * np.pi * np.arange(half) / length).astype(np.complex64)
+        a = a.reshape(-1, length)
+        t = (a[:, half:] * w).astype(np.complex64)
+        a = np.concatenate([a[:, :half] + t, a[:, :half] - t], axis=1).astype(np.complex64)
+        a = a.reshape(-1)
+        length *= 2
+    return a[:n // 2 + 1]
+
+
+def _cosf(x):
+    return np.cos(f32(x), dtype=f32)
+
+
+def _log10f(x):
+    return np.log10(f32(x), dtype=f32)
+
+
+def _mel(m, data):
+    """MelModule::generate, aku/FeatureModules.cc:806-849 (float val/sum/scale)."""
+    edges = m["edges"]
+    out = np.empty((data.shape[0], m["dim"]))
+    for b in range(m["dim"]):
+        val = np.zeros(data.shape[0], dtype=f32)
+        s = f32(0)
+        beg = f32(edges[b] - f32(1))
+        end = edges[b + 1]
+        t = int(max(np.ceil(beg), f32(0)))
+        while t < end:
+            scale = f32(f32(f32(t) - beg) / f32(end - beg))
+            val = (val.astype(np.float64) + np.float64(scale) * data[:, t]).astype(f32)
+            s = f32(s + scale)
+            t += 1
+        beg = end
+        end = edges[b + 2]
+        while t < end:
+            scale = f32(f32(end - f32(t)) / f32(end - beg))
+            val = (val.astype(np.float64) + np.float64(scale) * data[:, t]).astype(f32)
+            s = f32(s + scale)
+            t += 1
+        if m["root"]:
+            out[:, b] = np.power((val / s).astype(np.float64), 0.1)
+        else:
+            out[:, b] = np.log((val / s).astype(f32) + f32(1), dtype=f32).astype(np.float64)
+    return out
+
+
+# ------------------------------------------------------------------------------------
+# acoustic model
+def read_model(base):
+    """HmmSet::read_all: .mc (aku/HmmSet.cc:157-180), .ph (:209-329), .gk (aku/Distributions.cc:2812-2910)."""
+    tok = open(base + ".mc").read().split()
+    n = int(tok[0]); p = 1
+    mix = []
+    for _ in range(n):
+        k = int(tok[p]); p += 1
+        idx = [int(tok[p + 2 * j]) for j in range(k)]
+        w = [float(tok[p + 2 * j + 1]) for j in range(k)]
+        p += 2 * k
+        mix.append((idx, w))
+    tok = open(base + ".ph").read().split()
+    assert tok[0] == "PHONE"
+    phones = int(tok[1]); p = 2
+    S = 0
+    for _ in range(phones):
+        states = int(tok[p + 1]) - 2
+        p += 3 + 2
+        for s in range(states):
+            S = max(S, int(tok[p]) + 1); p += 1
+        for s in range(states + 2):
+            ntr = int(tok[p + 1]); p += 2 + 2 * ntr
+    tok = open(base + ".gk").read().split()
+    G, D, typ = int(tok[0]), int(tok[1]), tok[2]
+    p = 3
+    means = np.empty((G, D)); covs = np.empty((G, D))
+    for g in range(G):
+        if typ == "variable":
+            assert tok[p] == "diag", "only diagonal Gaussians are restated"
+            p += 1
+        means[g] = [float(v) for v in tok[p:p + D]]; p += D
+        covs[g] = [float(v) for v in tok[p:p + D]]; p += D
+    off = [0]; mg = []; mw = []
+    for s in range(S):
+        idx, w = mix[s]
+        mg += idx; mw += w; off.append(len(mg))
+    return dict(mix_offsets=np.array(off, np.int32), mix_gauss=np.array(mg, np.int32),
+                mix_weight=np.array(mw, np.float64), means=means, covs=covs)
+
+
+def gaussian_params(means, covs):
+    """DiagonalGaussian::read (:1132-1150) + set_constant (:1274-1288)."""
+    covs = np.asarray(covs, dtype=np.float64)
+    prec = np.where(covs > 0, 1.0 / np.where(covs > 0, covs, 1.0), 0.0)
+    cst = np.ones(covs.shape[0])
+    for i in range(covs.shape[1]):      # sequential product, as the reference multiplies
+        cst = cst * prec[:, i]
+    ok = cst > 0
+    cst = np.where(ok, np.log(np.sqrt(np.where(ok, cst, 1.0))), cst)
+    return prec, cst
+
+
+def state_likelihoods(model, feats, block=256):
+    """HmmSet::precompute_likelihoods (aku/HmmSet.cc:485-501) for every frame: linear state
+    likelihoods floored at 1e-50.  Sums run in the reference's order (dims then components)."""
+    feats = np.asarray(feats, dtype=np.float64)
+    mu = np.asarray(model["means"], dtype=np.float64)
+    prec, cst = gaussian_params(mu, model["covs"])
+    off, mg = model["mix_offsets"], model["mix_gauss"]
+    w = np.asarray(model["mix_weight"], dtype=np.float64).copy()
+    S = len(off) - 1
+    for s in range(S):                  # Mixture::normalize_weights (:2068-2075)
+        a, b = off[s], off[s + 1]
+        tot = 0.0
+        for k in range(a, b):
+            tot += w[k]
+        w[a:b] = w[a:b] / tot
+    F, D = feats.shape
+    out = np.empty((F, S))
+    for f0 in range(0, F, block):
+        x = feats[f0:f0 + block]
+        ll = np.zeros((x.shape[0], mu.shape[0]))
+        for i in range(D):              # ll += d*d*prec, left to right (:1052-1056)
+            d = x[:, i:i + 1] - mu[None, :, i]
+            ll += d * d * prec[None, :, i]
+        ll *= -0.5
+        ll += cst[None, :]
+        lik = _exp(ll).astype(np.float64)   # DiagonalGaussian::compute_likelihood (:1036)
+        for s in range(S):              # Mixture::compute_likelihood (:2079-2086)
+            acc = np.zeros(x.shape[0])
+            for k in range(off[s], off[s + 1]):
+                acc += w[k] * lik[:, mg[k]]
+            out[f0:f0 + x.shape[0], s] = np.maximum(acc, 1e-50)
+    return out
+
+
+def lna_records(lik, lnabytes=2, normalize=True):
+    """The normalise/quantise loop of aku/phone_probs.cc:225-262.  lik: linear state
+    likelihoods [F x S] (double).  Returns (bytes [F x S*lnabytes] uint8, float32 log-probs)."""
+    with np.errstate(under="ignore"):
+        obs = np.asarray(lik, dtype=np.float64).astype(f32)            # obs_log_probs is vector<float>
+    F, S = obs.shape
+    Z = np.zeros(F)
+    for s in range(S):                                                 # double accumulator, state order
+        Z += obs[:, s].astype(np.float64)
+    if not normalize:
+        Z[:] = 1
+    Z[Z == 0] = 1
+    x = obs.astype(np.float64) / Z[:, None]
+    lp = np.where(x < 1e-50, math.log(1e-50), _log(np.where(x < 1e-50, 1.0, x)).astype(np.float64)).astype(f32)   # util::safe_log
+    if lnabytes == 4:
+        return lp.astype("<f4").view(np.uint8).reshape(F, S * 4), lp
+    lpd = lp.astype(np.float64)
+    code = np.where(lpd < -36.008, 65535, (-1820.0 * lpd + .5).astype(np.int64))    # (int) truncates toward zero
+    hi = (code >> 8) & 255
+    lo = code & 255
+    rec = np.stack([hi, lo], axis=2).astype(np.uint8).reshape(F, S * 2)
+    return rec, lp

@@ -1,0 +1,136 @@
+// oracle/ref_capi.cc -- C-callable view of the REFERENCE's own classes
+// (aku::FeatureGenerator, aku::HmmSet), linked against the reference objects
+// that oracle/build_ref.sh compiles from /root/reference/aku in place.
+//
+// TEST INFRASTRUCTURE ONLY.  It gives pytest (ctypes) double-precision access
+// to what the reference computes, so that the numpy/C restatements in oracle/
+// and the CUDA product can be checked against the real thing:
+//   * features:    FeatureGenerator::generate(f)          (aku/FeatureGenerator.cc:267-273)
+//   * likelihoods: HmmSet::precompute_likelihoods + state_likelihood
+//                                                          (aku/HmmSet.cc:485-501, aku/HmmSet.hh:309)
+// The LNA byte stream itself is produced by the literal aku/phone_probs.cc,
+// built as oracle/_ref/ref_phone_probs.
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <exception>
+#include "io.hh"
+#include "FeatureGenerator.hh"
+#include "FeatureModules.hh"
+#include "HmmSet.hh"
+
+using namespace aku;
+
+static std::string g_err;
+static int fail(const std::string &m) { g_err = m; return -1; }
+
+extern "C" {
+
+const char *ref_last_error() { return g_err.c_str(); }
+
+// Runs the reference feature pipeline on one audio file.
+// Writes frames [start, end) (end<0: until the reference reports EOF) as doubles
+// into out[max_frames*dim]; returns the number of frames written, dim in *dim_out.
+long ref_features(const char *cfg_path, const char *audio_path, int start, int end,
+                  double *out, long max_frames, int *dim_out, int *last_frame_out, float *frame_rate_out)
+{
+  try {
+    FeatureGenerator gen;
+    gen.load_configuration(io::Stream(cfg_path));
+    gen.open(audio_path);
+    int dim = gen.dim();
+    if (dim_out) *dim_out = dim;
+    if (frame_rate_out) *frame_rate_out = gen.frame_rate();
+    long n = 0;
+    for (int f = start; end < 0 || f < end; f++) {
+      const FeatureVec fea = gen.generate(f);
+      if (end < 0 && gen.eof()) break;
+      if (n >= max_frames) break;
+      for (int i = 0; i < dim; i++) out[n * dim + i] = fea[i];
+      n++;
+    }
+    if (last_frame_out) *last_frame_out = gen.last_frame();
+    gen.close();
+    return n;
+  } catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
+// Output of an intermediate module (by name) for frames [start,end).
+long ref_module_output(const char *cfg_path, const char *audio_path, const char *module_name,
+                       int start, int end, double *out, long max_frames, int *dim_out)
+{
+  try {
+    FeatureGenerator gen;
+    gen.load_configuration(io::Stream(cfg_path));
+    gen.open(audio_path);
+    FeatureModule *m = gen.module(module_name);
+    int dim = m->dim();
+    if (dim_out) *dim_out = dim;
+    long n = 0;
+    for (int f = start; f < end && n < max_frames; f++) {
+      const FeatureVec fea = m->at(f);
+      for (int i = 0; i < dim; i++) out[n * dim + i] = fea[i];
+      n++;
+    }
+    gen.close();
+    return n;
+  } catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
+struct RefModel { HmmSet model; };
+
+void *ref_model_open(const char *base)
+{
+  try {
+    RefModel *m = new RefModel;
+    m->model.read_all(base);
+    return m;
+  } catch (std::string &s) { fail(s); return NULL; }
+  catch (std::exception &e) { fail(e.what()); return NULL; }
+}
+void ref_model_close(void *h) { delete (RefModel *)h; }
+int ref_model_num_states(void *h) { return ((RefModel *)h)->model.num_states(); }
+int ref_model_dim(void *h) { return ((RefModel *)h)->model.dim(); }
+int ref_model_num_gaussians(void *h) { return ((RefModel *)h)->model.get_pool()->size(); }
+
+// Linear state likelihoods (double, floored at 1e-50 by the reference) for F frames.
+int ref_state_likelihoods(void *h, const double *feats, long F, int D, double *out /*[F*S]*/)
+{
+  try {
+    HmmSet &model = ((RefModel *)h)->model;
+    if (D != model.dim()) return fail("feature dim != model dim");
+    int S = model.num_states();
+    FeatureVec fv;
+    Vector v(D);
+    for (long f = 0; f < F; f++) {
+      for (int i = 0; i < D; i++) v(i) = feats[f * D + i];
+      FeatureVec fea(&v, D);
+      model.reset_cache();
+      model.precompute_likelihoods(fea);
+      for (int s = 0; s < S; s++) out[f * S + s] = model.state_likelihood(s, fea);
+    }
+    return 0;
+  } catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
+// Per-Gaussian log-likelihoods (double) straight from the pool.
+int ref_gaussian_loglik(void *h, const double *feats, long F, int D, double *out /*[F*G]*/)
+{
+  try {
+    HmmSet &model = ((RefModel *)h)->model;
+    PDFPool *pool = model.get_pool();
+    int G = pool->size();
+    Vector v(D);
+    for (long f = 0; f < F; f++) {
+      for (int i = 0; i < D; i++) v(i) = feats[f * D + i];
+      for (int g = 0; g < G; g++) out[f * G + g] = pool->get_pdf(g)->compute_log_likelihood(v);
+    }
+    return 0;
+  } catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
+}  // extern "C"
