@@ -470,7 +470,7 @@ int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant)
   API_END
 }
 
-int akugpu_pipe_rates(akugpu_ctx *ctx, double out[4])
+int akugpu_pipe_rates(akugpu_ctx *ctx, double out[8])
 {
   API_BEGIN
   if (!out) throw Error(AKUGPU_E_ARG, "out is NULL");

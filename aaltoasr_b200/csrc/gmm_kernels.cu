@@ -411,64 +411,133 @@ void launch_transpose_f64(akugpu_ctx *ctx, const double *in, int64_t ldF, int S,
 }
 
 // ------------------------------------------------------------------------------------
-// Issue-pipe micro-benchmarks (akugpu_pipe_rates): dependent chains, 8 independent
-// accumulators per thread, enough warps to saturate each pipe.
+// Issue-pipe micro-benchmarks (akugpu_pipe_rates): 8 independent chains per thread, enough warps to
+// saturate each pipe.  Modes 0-3 are the classic constant-operand chains; 4-7 use the scorer's own
+// operand pattern (all-register, no memory) to expose register-bandwidth limits:
+//   4: a = fma(b, c, a) with three distinct varying registers
+//   5: same with FFMA2
+//   6: the scorer's inner tile, FFMA:  t = fma(x_i, s_j, m_j); acc_ij = fma(t, t, acc_ij)   (8x8)
+//   7: the scorer's inner tile, FFMA2 (8x4 packed)
 template <int MODE>
 __global__ void pipe_rate_kernel(float *out, int iters)
 {
-  float a[8];
+  float a[8], b[8], c[8];
   double da[8];
-  float2 a2[8];
+  float2 a2[8], b2[8], c2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     a[i] = threadIdx.x * 1e-3f + i;
+    b[i] = 0.999f + (threadIdx.x + i) * 1e-9f;
+    c[i] = 1e-3f * (i + 1);
     da[i] = a[i];
     a2[i] = make_float2(a[i], a[i] + 0.5f);
+    b2[i] = make_float2(b[i], b[i]);
+    c2[i] = make_float2(c[i], c[i]);
   }
-  const float m = 0.999f + threadIdx.x * 1e-9f, c = 1e-3f;
+  const float m = 0.999f + threadIdx.x * 1e-9f, cc = 1e-3f;
+  float acc[8][8];
+  float2 acc2[8][4];
+  if (MODE == 6) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = i + j;
+  }
+  if (MODE == 7) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(i, j);
+  }
   for (int it = 0; it < iters; ++it) {
+    if (MODE <= 5) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < 4; ++r) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (MODE == 0) a[i] = fmaf(a[i], m, c);
-        if (MODE == 1) a2[i] = __ffma2_rn(a2[i], make_float2(m, m), make_float2(c, c));
-        if (MODE == 2) da[i] = fma(da[i], (double)m, (double)c);
-        if (MODE == 3) a[i] = ex2f(a[i]);
+        for (int i = 0; i < 8; ++i) {
+          if (MODE == 0) a[i] = fmaf(a[i], m, cc);
+          if (MODE == 1) a2[i] = __ffma2_rn(a2[i], make_float2(m, m), make_float2(cc, cc));
+          if (MODE == 2) da[i] = fma(da[i], (double)m, (double)cc);
+          if (MODE == 3) a[i] = ex2f(a[i]);
+          if (MODE == 4) a[i] = fmaf(b[i], c[i], a[i]);
+          if (MODE == 5) a2[i] = __ffma2_rn(b2[i], c2[i], a2[i]);
+        }
       }
+    } else if (MODE == 6) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(a[i], b[j], c[j]);
+          acc[i][j] = fmaf(t, t, acc[i][j]);
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += 1e-7f;   // keep the loop from being hoisted
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = __ffma2_rn(a2[i], b2[j], c2[j]);
+          acc2[i][j] = __ffma2_rn(t, t, acc2[i][j]);
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a2[i].x += 1e-7f;
     }
   }
   float s = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += a[i] + (float)da[i] + a2[i].x + a2[i].y;
+  if (MODE == 6) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += acc[i][j];
+  }
+  if (MODE == 7) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s += acc2[i][j].x + acc2[i][j].y;
+  }
   if (s == 123.456f) out[0] = s;
 }
 
-void pipe_rates(akugpu_ctx *ctx, double out[4])
+template <int MODE>
+static float time_pipe(akugpu_ctx *ctx, float *d, int iters, int blocks, int threads, cudaEvent_t e0, cudaEvent_t e1)
+{
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    AKU_CUDA(cudaEventRecord(e0, ctx->stream));
+    pipe_rate_kernel<MODE><<<blocks, threads, 0, ctx->stream>>>(d, iters);
+    AKU_CUDA(cudaEventRecord(e1, ctx->stream));
+    AKU_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    AKU_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+    ctx->launches++;
+  }
+  return best;
+}
+
+void pipe_rates(akugpu_ctx *ctx, double out[8])
 {
   DevBuf d; d.reserve(16);
   cudaEvent_t e0, e1;
   AKU_CUDA(cudaEventCreate(&e0));
   AKU_CUDA(cudaEventCreate(&e1));
-  const int iters = 2048, blocks = ctx->sm_count * 4, threads = 512;
-  for (int mode = 0; mode < 4; ++mode) {
-    float best = 1e30f;
-    for (int rep = 0; rep < 4; ++rep) {
-      AKU_CUDA(cudaEventRecord(e0, ctx->stream));
-      if (mode == 0) pipe_rate_kernel<0><<<blocks, threads, 0, ctx->stream>>>(d.as<float>(), iters);
-      if (mode == 1) pipe_rate_kernel<1><<<blocks, threads, 0, ctx->stream>>>(d.as<float>(), iters);
-      if (mode == 2) pipe_rate_kernel<2><<<blocks, threads, 0, ctx->stream>>>(d.as<float>(), iters);
-      if (mode == 3) pipe_rate_kernel<3><<<blocks, threads, 0, ctx->stream>>>(d.as<float>(), iters);
-      AKU_CUDA(cudaEventRecord(e1, ctx->stream));
-      AKU_CUDA(cudaEventSynchronize(e1));
-      float ms;
-      AKU_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-      if (rep > 0 && ms < best) best = ms;
-      ctx->launches++;
-    }
-    double ops = (double)blocks * threads * iters * 32.0 * (mode == 1 ? 2.0 : 1.0);
-    out[mode] = ops / (best * 1e-3);
-  }
+  const int iters = 2048, blocks = ctx->sm_count * 4, threads = 256;
+  float ms[8];
+  ms[0] = time_pipe<0>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  ms[1] = time_pipe<1>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  ms[2] = time_pipe<2>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  ms[3] = time_pipe<3>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  ms[4] = time_pipe<4>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  ms[5] = time_pipe<5>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  ms[6] = time_pipe<6>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  ms[7] = time_pipe<7>(ctx, d.as<float>(), iters, blocks, threads, e0, e1);
+  const double per_iter[8] = {32, 64, 32, 32, 32, 64, 128, 128};   // lane-ops per thread per iteration
+  for (int mode = 0; mode < 8; ++mode) out[mode] = (double)blocks * threads * iters * per_iter[mode] / (ms[mode] * 1e-3);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
 }

@@ -13,7 +13,7 @@ void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f
                     int64_t ldF);
 void launch_transpose_f32(akugpu_ctx *ctx, const float *in, int64_t ldF, int S, int64_t F, float *out);
 void launch_transpose_f64(akugpu_ctx *ctx, const double *in, int64_t ldF, int S, int64_t F, double *out);
-void pipe_rates(akugpu_ctx *ctx, double out[4]);
+void pipe_rates(akugpu_ctx *ctx, double out[8]);
 
 // lna_kernels.cu
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,

@@ -103,9 +103,10 @@ class AkuGpu:
         self._ck(self._lib.akugpu_set_scorer_variant(self._h, int(variant)))
 
     def pipe_rates(self):
-        out = (C.c_double * 4)()
+        out = (C.c_double * 8)()
         self._ck(self._lib.akugpu_pipe_rates(self._h, out))
-        return {"ffma": out[0], "ffma2": out[1], "dfma": out[2], "ex2": out[3]}
+        return {"ffma": out[0], "ffma2": out[1], "dfma": out[2], "ex2": out[3], "ffma_3reg": out[4],
+                "ffma2_3reg": out[5], "tile_ffma": out[6], "tile_ffma2": out[7]}
 
     # ---- front-end ----
     def frontend_load_config(self, path):

@@ -149,8 +149,10 @@ int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames);
  * 2 = packed FFMA2 (8 frames x 4 comps x 2 dims / thread). */
 int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant);
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
- * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2. */
-int akugpu_pipe_rates(akugpu_ctx *ctx, double out[4]);
+ * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2 with constant
+ * operands; out[4] FFMA and out[5] FFMA2 with three distinct register operands; out[6] / out[7]
+ * the scorer's own register tile (FFMA 8x8 / FFMA2 8x4) without memory traffic. */
+int akugpu_pipe_rates(akugpu_ctx *ctx, double out[8]);
 
 #ifdef __cplusplus
 }

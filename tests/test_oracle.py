@@ -1,0 +1,108 @@
+"""CPU tests: the oracle (oracle/oracle_np.py) against the reference's golden vectors.
+
+Pins the checker before it is trusted: (1) the reference's own aku/tests goldens
+(tests/golden/aku_tests.npz, re-encoded from aku/tests/*.ref), (2) outputs of the reference's
+code built from source (tests/golden/ref_small.npz, ref_edge.npz; generator:
+tests/golden/make_golden.py), (3) the live reference library when oracle/_ref is present.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_np, ref
+
+
+def test_aku_golden_mfcc_p_dd(aku_tests):
+    """aku/tests/mfcc_p_dd.script: frames -10..80 of short.wav, 39-dim; the .ref holds the pass
+    twice (second pass re-reads the written config).  Golden precision is %8.2f."""
+    P = oracle_np.Pipeline(aku_tests["mfcc_p_dd_cfg"])
+    out = P.run(aku_tests["short_wav"], -10, 81)
+    gold = aku_tests["mfcc_p_dd_ref"]
+    assert gold.shape == (182, 39)
+    assert out.shape == (91, 39)
+    assert np.abs(out - gold[:91]).max() <= 0.0051
+    assert np.abs(out - gold[91:]).max() <= 0.0051
+    assert P.num_frames(aku_tests["short_wav"].size) == 73
+
+
+def test_aku_golden_mfcc_cms_norm(aku_tests):
+    """aku/tests/mfcc_cms_norm.script: frames -15..90 on the 73-frame file; power spectrum,
+    delta widths 2/3, normalization, 39x39 lin_transform, mean_subtractor 50/25, after-EOF borders."""
+    P = oracle_np.Pipeline(aku_tests["mfcc_cms_norm_cfg"])
+    out = P.run(aku_tests["short_wav"], -15, 91)
+    gold = aku_tests["mfcc_cms_norm_ref"]
+    assert out.shape == gold.shape == (106, 39)
+    assert np.abs(out - gold).max() <= 0.0051
+
+
+def test_aku_golden_pre_test(aku_tests):
+    """aku/tests/pre_test.script: feacat -H --raw-output frames 10..60 then read back: the rows are
+    the float32-rounded 39-dim features of frames 10..60."""
+    P = oracle_np.Pipeline(aku_tests["mfcc_p_dd_cfg"])
+    out = P.run(aku_tests["short_wav"], 10, 61).astype(np.float32).astype(np.float64)
+    gold = aku_tests["pre_test_ref"]
+    assert out.shape == gold.shape == (51, 39)
+    assert np.abs(out - gold).max() <= 0.0051
+
+
+def test_random_access_equals_sequential(aku_tests):
+    """aku/tests/random_feature_test.cc: any access order gives the same frames."""
+    P = oracle_np.Pipeline(aku_tests["mfcc_p_dd_cfg"])
+    seq = P.run(aku_tests["short_wav"], -10, 81)
+    rng = np.random.default_rng(0)
+    for f in rng.integers(-10, 81, size=25):
+        assert np.array_equal(P.run(aku_tests["short_wav"], int(f), int(f) + 1)[0], seq[f + 10])
+
+
+@pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
+def test_features_vs_reference(case, request):
+    g = request.getfixturevalue(case)
+    P = oracle_np.Pipeline(g["cfg"])
+    assert P.num_frames(g["pcm"].size) == g["feats"].shape[0] == int(g["last_frame"]) + 1
+    assert np.abs(P.run(g["pcm"]) - g["feats"]).max() <= 1e-5
+    ext = P.run(g["pcm"], int(g["ext_start"]), int(g["ext_start"]) + g["feats_ext"].shape[0])
+    assert np.abs(ext - g["feats_ext"]).max() <= 1e-5
+    for mod, tol in (("fft", 2e-2), ("mel", 5e-6), ("power", 5e-6), ("mfcc", 2e-5), ("delta1", 1e-5), ("delta2", 1e-5)):
+        got = P.run(g["pcm"], -3, 12, module=mod)
+        assert np.abs(got - g["mod_" + mod]).max() <= tol, mod
+
+
+@pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
+def test_gmm_lna_bit_exact_vs_reference(case, request):
+    """State likelihoods equal the reference's doubles bit for bit; LNA bytes equal the files the
+    literal aku/phone_probs.cc wrote (2/4 bytes, with and without -N)."""
+    g = request.getfixturevalue(case)
+    lik = oracle_np.state_likelihoods(g["model"], g["feats"])
+    assert np.array_equal(lik, g["lik"])
+    S = lik.shape[1]
+    for nb in (2, 4):
+        for nonorm in (False, True):
+            blob = g["lna%d%s" % (nb, "_nonorm" if nonorm else "")]
+            assert bytes(blob[:5]) == S.to_bytes(4, "big") + bytes([nb])
+            rec, _ = oracle_np.lna_records(lik, nb, normalize=not nonorm)
+            assert np.array_equal(rec.reshape(-1), blob[5:])
+
+
+def test_edge_case_covers_the_regimes(ref_edge):
+    ll = np.log(ref_edge["lik"])
+    assert (ref_edge["lik"] == 1e-50).mean() > 0.1                      # floored (double underflow / tiny)
+    assert ((ll >= -103.97) & (ll < -87.34)).sum() > 20                  # fp32 denormal range
+    assert (ll > -87).mean() > 0.2                                       # normal range
+    rec, lp = oracle_np.lna_records(ref_edge["lik"], 2)
+    codes = rec.reshape(rec.shape[0], -1, 2)
+    assert (codes == 255).all(axis=2).any() and not (codes == 255).all()  # some saturated, not all
+    assert (lp > -1e-3).any()                                            # near-certain posteriors
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_live_reference_matches_golden(ref_small, tmp_path):
+    """The committed fixtures really are what the reference build produces."""
+    from aaltoasr_b200 import formats
+    wav, cfg = str(tmp_path / "a.wav"), str(tmp_path / "a.cfg")
+    formats.write_wav(wav, ref_small["pcm"], 16000)
+    open(cfg, "w").write(ref_small["cfg"])
+    feats, last, rate = ref.features(cfg, wav)
+    assert np.array_equal(feats, ref_small["feats"]) and rate == 125.0
+    formats.write_model(str(tmp_path / "m"), **ref_small["model"])
+    M = ref.Model(str(tmp_path / "m"))
+    assert np.array_equal(M.state_likelihoods(feats), ref_small["lik"])
+    M.close()
