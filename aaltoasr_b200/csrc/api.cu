@@ -49,6 +49,19 @@ StageScope::~StageScope()
 
 }  // namespace akugpu
 
+// Frames per chunk of the scoring pipeline.  Auto (chunk_frames == 0): exactly one wave of the fp32
+// scorer (sm_count x resident CTAs x 64 frames) so that no launch ends in a partial wave; an explicit
+// value is rounded to whole waves when it is at least one wave.  Always a multiple of 128.
+static int64_t pick_chunk(akugpu_ctx *ctx, int64_t F)
+{
+  const int64_t wave = gmm_wave_frames(ctx);
+  int64_t chunk = ctx->chunk_frames <= 0 ? wave : ctx->chunk_frames;
+  if (chunk >= wave) chunk = chunk / wave * wave;
+  chunk = (chunk + 127) / 128 * 128;
+  if (chunk > F) chunk = (F + 127) / 128 * 128;
+  return chunk;
+}
+
 static void require_model(akugpu_ctx *ctx)
 {
   if (!ctx->have_model) throw Error(AKUGPU_E_STATE, "no acoustic model loaded (akugpu_model_read / akugpu_model_load_diag)");
@@ -67,8 +80,7 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
   if (lnabytes != 2 && lnabytes != 4) throw Error(AKUGPU_E_ARG, "lnabytes must be 2 or 4");
   if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
   if (F <= 0 || S <= 0) { if (checksum_out) *checksum_out = 0; return; }
-  int64_t chunk = std::max<int64_t>(128, (ctx->chunk_frames + 127) / 128 * 128);
-  if (chunk > F) chunk = (F + 127) / 128 * 128;
+  const int64_t chunk = pick_chunk(ctx, F);
   const size_t rec = (size_t)S * lnabytes;
   const bool out_dev = out && is_device_ptr(out);
   const bool out_host = out && !out_dev;
@@ -390,8 +402,7 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   if (n_frames == 0 || S == 0) return AKUGPU_OK;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
   const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
-  int64_t chunk = std::max<int64_t>(128, (ctx->chunk_frames + 127) / 128 * 128);
-  if (chunk > n_frames) chunk = (n_frames + 127) / 128 * 128;
+  const int64_t chunk = pick_chunk(ctx, n_frames);
   ctx->d_sll.reserve((size_t)S * chunk * esz);
   const bool odev = is_device_ptr(out);
   uint8_t *d_out = (uint8_t *)out;
@@ -456,7 +467,7 @@ int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5])
 int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames)
 {
   API_BEGIN
-  if (frames < 128) throw Error(AKUGPU_E_ARG, "chunk must be >= 128 frames");
+  if (frames != 0 && frames < 128) throw Error(AKUGPU_E_ARG, "chunk must be 0 (auto) or >= 128 frames");
   ctx->chunk_frames = frames;
   API_END
 }

@@ -89,8 +89,6 @@ struct PackedF32 {
   int n_tiles = 0;
   size_t tile_floats = 0;
   DevBuf params;         // n_tiles * tile_floats floats
-  DevBuf tile_state0;    // int32 [n_tiles+1]: first state of each tile
-  DevBuf st_grp;         // int32 [S+1]: first thread-group (global numbering) of each state
   DevBuf center;         // float [2*DP] feature centre
   DevBuf center64;       // double [2*DP]
 };
@@ -165,7 +163,7 @@ struct akugpu_ctx {
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
-  int64_t chunk_frames = 16384;
+  int64_t chunk_frames = 0;   // 0 = auto: one full wave of the scorer per chunk
   int scorer_variant = 0;
 
   akugpu::HostModel hm;

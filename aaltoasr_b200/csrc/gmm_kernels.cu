@@ -36,14 +36,18 @@
 
 namespace akugpu {
 
-constexpr int TF = 128;          // frames per CTA tile
+constexpr int TF = 64;           // frames per CTA tile
 constexpr int FR = 8;            // frames per thread
-constexpr int NTH = 256;
-constexpr int NFG = TF / FR;     // 16 frame groups
+constexpr int NTH = 128;
+constexpr int NFG = TF / FR;     // 8 frame groups
 constexpr int NCG = NTH / NFG;   // 16 component groups
+#ifndef GMM_DP_UNROLL
+#define GMM_DP_UNROLL 2
+#endif
+constexpr int TAB_INTS = 32;     // per-tile state table appended to the stage image
+constexpr int kDpUnroll = GMM_DP_UNROLL;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr float PAD_NEGC = 1.0e30f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -95,12 +99,29 @@ struct AccT<GR, false> { float v[FR][GR]; };
 template <int GR>
 struct AccT<GR, true> { float2 v[FR][GR]; };
 
+// One (frame, component, dim-pair) update: t = x*s + m ; acc += t*t.
+template <bool F2, bool FIRST, class A>
+__device__ __forceinline__ void gmm_step(A &acc, float x0, float x1, const float4 &p, float nc)
+{
+  if constexpr (F2) {
+    float2 tt = __ffma2_rn(make_float2(x0, x1), make_float2(p.x, p.y), make_float2(p.z, p.w));
+    acc = __ffma2_rn(tt, tt, FIRST ? make_float2(nc, 0.f) : acc);
+  } else {
+    float t0 = fmaf(x0, p.x, p.z);
+    float t1 = fmaf(x1, p.y, p.w);
+    acc = fmaf(t0, t0, FIRST ? nc : acc);
+    acc = fmaf(t1, t1, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------
+// grid.x = frame tiles (64 frames), grid.y = split of the component tiles (only used when there
+// are too few frame tiles to fill the chip).  4 CTAs of 128 threads are resident per SM so that
+// one CTA's log-sum-exp epilogue hides under the other CTAs' FMA loops.
 template <int GR, bool F2>
-__global__ void __launch_bounds__(NTH, 2)
+__global__ void __launch_bounds__(NTH, F2 ? 4 : 2)
 gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t f_end, int D, int DP,
              const float *__restrict__ params, size_t tile_floats, int n_tiles, int tiles_per_cta,
-             const int *__restrict__ tile_state0, const int2 *__restrict__ st_grp,
              const float *__restrict__ center, const double *__restrict__ center64,
              float *__restrict__ sll, int64_t ldF)
 {
@@ -113,8 +134,8 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int fg = (warp & 1) * 8 + (lane & 7);
-  const int cg = (warp >> 1) * 4 + (lane >> 3);
+  const int fg = lane & 7;                 // frame group: frames k*16 + fg*2 + {0,1}, k = 0..3
+  const int cg = warp * 4 + (lane >> 3);   // component group
 
   const int64_t f0 = f_begin + (int64_t)blockIdx.x * TF;
   const int t_begin = blockIdx.y * tiles_per_cta;
@@ -161,27 +182,25 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
     unsigned char *stage = stage0 + (size_t)b * stage_bytes;
     const float4 *ps = reinterpret_cast<const float4 *>(stage);
     const float *cs = reinterpret_cast<const float *>(stage + (size_t)DP * TC * sizeof(float4));
+    const int *tab = reinterpret_cast<const int *>(cs + TC);
     mbar_wait(&full_bar[b], phase[b]);
     phase[b] ^= 1;
 
     AccT<GR, F2> acc;
 #pragma unroll
     for (int j = 0; j < GR; ++j) {
-      float nc = cs[j * NCG + cg];
+      const float nc = cs[j * NCG + cg];     // accumulators start at -c
 #pragma unroll
       for (int i = 0; i < FR; ++i) {
         if constexpr (F2) acc.v[i][j] = make_float2(nc, 0.f);
         else acc.v[i][j] = nc;
       }
     }
-
-#pragma unroll 2
+#pragma unroll (kDpUnroll)
     for (int dp = 0; dp < DP; ++dp) {
-      float4 xv[FR / 2];
+      float4 xv[FR / 2], pv[GR];
 #pragma unroll
-      for (int k = 0; k < FR / 2; ++k)
-        xv[k] = *reinterpret_cast<const float4 *>(&xs[dp * TF + k * 32 + fg * 2]);
-      float4 pv[GR];
+      for (int k = 0; k < FR / 2; ++k) xv[k] = *reinterpret_cast<const float4 *>(&xs[dp * TF + k * 16 + fg * 2]);
 #pragma unroll
       for (int j = 0; j < GR; ++j) pv[j] = ps[dp * TC + j * NCG + cg];
 #pragma unroll
@@ -189,20 +208,11 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
         const float x0 = (i & 1) ? xv[i >> 1].z : xv[i >> 1].x;
         const float x1 = (i & 1) ? xv[i >> 1].w : xv[i >> 1].y;
 #pragma unroll
-        for (int j = 0; j < GR; ++j) {
-          if constexpr (F2) {
-            float2 tt = __ffma2_rn(make_float2(x0, x1), make_float2(pv[j].x, pv[j].y), make_float2(pv[j].z, pv[j].w));
-            acc.v[i][j] = __ffma2_rn(tt, tt, acc.v[i][j]);
-          } else {
-            float t0 = fmaf(x0, pv[j].x, pv[j].z);
-            float t1 = fmaf(x1, pv[j].y, pv[j].w);
-            acc.v[i][j] = fmaf(t0, t0, acc.v[i][j]);
-            acc.v[i][j] = fmaf(t1, t1, acc.v[i][j]);
-          }
-        }
+        for (int j = 0; j < GR; ++j) gmm_step<F2, false>(acc.v[i][j], x0, x1, pv[j], 0.f);
       }
     }
-    __syncthreads();   // everyone is done reading this stage: reuse it for the partials
+    __syncthreads();   // everyone is done reading this stage's parameters: reuse its head for the partials
+                       // (the state table sits at the tail of the image and stays intact)
 
     // Thread-level log-sum-exp over its GR components: a = min(-ll), sum = sum exp(ll + a).
     float2 *part = reinterpret_cast<float2 *>(stage);   // [NCG][TF]
@@ -221,27 +231,29 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < GR; ++j) sum += ex2f(fmaf(v[j], -LOG2E, al));
-      const int fr = (i >> 1) * 32 + fg * 2 + (i & 1);
+      const int fr = (i >> 1) * 16 + fg * 2 + (i & 1);
       part[cg * TF + fr] = make_float2(a, sum);
     }
     __syncthreads();
 
     // Combine the thread-groups of each state of this tile; write state log-likelihoods.
     {
-      const int s0 = tile_state0[t];
-      const int nst = tile_state0[t + 1] - s0;
-      for (int idx = tid; idx < nst * TF; idx += NTH) {
-        const int ls = idx >> 7, fr = idx & (TF - 1);
-        const int2 sg = st_grp[s0 + ls];
-        const int g0 = sg.x - t * NCG;
-        float A = part[g0 * TF + fr].x;
-        for (int g = 1; g < sg.y; ++g) A = fminf(A, part[(g0 + g) * TF + fr].x);
-        float tot = 0.f;
-        for (int g = 0; g < sg.y; ++g) {
-          float2 p = part[(g0 + g) * TF + fr];
-          tot = fmaf(p.y, ex2f((A - p.x) * LOG2E), tot);
+      const int nst = tab[0], s0 = tab[1];
+      const int fr = tid & (TF - 1);
+      // thread handles frame (tid & 63) of local states (tid >> 6), +2, +4, ..
+      for (int ls = tid >> 6; ls < nst; ls += NTH / TF) {
+        {
+          const int e = tab[2 + ls];
+          const int g0 = e & 255, ng = e >> 8;
+          float A = part[g0 * TF + fr].x;
+          for (int g = 1; g < ng; ++g) A = fminf(A, part[(g0 + g) * TF + fr].x);
+          float tot = 0.f;
+          for (int g = 0; g < ng; ++g) {
+            float2 p = part[(g0 + g) * TF + fr];
+            tot = fmaf(p.y, ex2f((A - p.x) * LOG2E), tot);
+          }
+          sll[(int64_t)(s0 + ls) * ldF + (f0 - f_begin) + fr] = fmaf(lg2f(tot), LN2, -A);
         }
-        sll[(int64_t)(s0 + ls) * ldF + (f0 - f_begin) + fr] = fmaf(lg2f(tot), LN2, -A);
       }
     }
     __syncthreads();
@@ -345,26 +357,31 @@ static void launch_f32_t(akugpu_ctx *ctx, const void *feats, int feats_f64, int6
   const PackedF32 &p = ctx->p32;
   const HostModel &hm = ctx->hm;
   size_t smem = gmm_f32_smem_bytes(p);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     AKU_CUDA(cudaFuncSetAttribute(gmm_diag_f32<GR, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_smem = smem;
   }
   int64_t nf = f_end - f_begin;
   int ftiles = (int)((nf + TF - 1) / TF);
-  // Split the component tiles over grid.y only when there are too few frame tiles to fill the chip.
-  int target = 2 * ctx->sm_count;
+  // One wave = sm_count * resident CTAs.  Full chunks are sized to whole waves by the caller
+  // (gmm_wave_frames); a short chunk splits the component tiles over grid.y to fill the chip.
+  const int wave = ctx->sm_count * (F2 ? 4 : 2);
   int ysplit = 1;
-  if (ftiles < target) ysplit = std::min(p.n_tiles, (target + ftiles - 1) / ftiles);
+  if (ftiles < wave) ysplit = std::min(p.n_tiles, std::max(1, wave / ftiles));
   int tiles_per_cta = (p.n_tiles + ysplit - 1) / ysplit;
   ysplit = (p.n_tiles + tiles_per_cta - 1) / tiles_per_cta;
   dim3 grid(ftiles, ysplit);
   gmm_diag_f32<GR, F2><<<grid, NTH, smem, ctx->stream>>>(
       feats, feats_f64, f_begin, f_end, hm.D, p.DP, p.params.as<float>(), p.tile_floats, p.n_tiles, tiles_per_cta,
-      p.tile_state0.as<int>(), p.st_grp.as<int2>(), p.center.as<float>(), p.center64.as<double>(), sll, ldF);
+      p.center.as<float>(), p.center64.as<double>(), sll, ldF);
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
 }
+
+// Frames per full wave of the fp32 scorer (chunks should be a multiple of this).
+int64_t gmm_wave_frames(akugpu_ctx *ctx) { return (int64_t)ctx->sm_count * (ctx->p32.GR == 4 ? 4 : 2) * TF; }
+int gmm_frame_tile() { return TF; }
 
 void launch_gmm_f32(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll,
                     int64_t ldF)

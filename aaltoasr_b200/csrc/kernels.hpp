@@ -7,6 +7,8 @@ namespace akugpu {
 
 // gmm_kernels.cu
 size_t gmm_f32_smem_bytes(const PackedF32 &p);
+int64_t gmm_wave_frames(akugpu_ctx *ctx);
+int gmm_frame_tile();
 void launch_gmm_f32(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll,
                     int64_t ldF);
 void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, double *lin,

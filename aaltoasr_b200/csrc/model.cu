@@ -193,7 +193,8 @@ void model_pack(akugpu_ctx *ctx)
   if (maxK > p.TC)
     throw Error(AKUGPU_E_MODEL, fmt("a mixture has %d components; the scorer supports at most %d per state", maxK, p.TC));
   p.DP = (D + 1) / 2;
-  p.tile_floats = (size_t)p.DP * p.TC * 4 + p.TC;
+  const int TAB_INTS = 32;   // per-tile state table: [0] #states, [1] first state, [2+ls] first group | groups << 8
+  p.tile_floats = (size_t)p.DP * p.TC * 4 + p.TC + TAB_INTS;
 
   std::vector<double> cen(2 * p.DP, 0.0);
   if (G > 0)
@@ -220,6 +221,13 @@ void model_pack(akugpu_ctx *ctx)
   for (int t = 0; t < p.n_tiles; t++) {
     float *C = img.data() + (size_t)t * p.tile_floats + (size_t)p.DP * p.TC * 4;
     for (int i = 0; i < p.TC; i++) C[i] = 1.0e30f;
+    int32_t *tab = reinterpret_cast<int32_t *>(C + p.TC);
+    tab[0] = tile_state0[t + 1] - tile_state0[t];
+    tab[1] = tile_state0[t];
+    for (int ls = 0; ls < tab[0]; ls++) {
+      int s = tile_state0[t] + ls;
+      tab[2 + ls] = (st_grp[2 * s] % NCG) | (st_grp[2 * s + 1] << 8);
+    }
   }
   for (int s = 0; s < S; s++) {
     int K = hm.mix_off[s + 1] - hm.mix_off[s];
@@ -245,8 +253,6 @@ void model_pack(akugpu_ctx *ctx)
   }
   std::vector<float> cenf(cen.begin(), cen.end());
   upload(p.params, img, ctx->stream);
-  upload(p.tile_state0, tile_state0, ctx->stream);
-  upload(p.st_grp, st_grp, ctx->stream);
   upload(p.center, cenf, ctx->stream);
   upload(p.center64, cen, ctx->stream);
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));

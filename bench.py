@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- acoustic frames/sec of the accelerated path (MFCC front-end + diagonal-GMM
+log-likelihoods + LNA encoding) on N B200s, and the reference's own CPU path beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
+  python bench.py --impl reference [--steps K] [--warmup W]       reference arm (CPU, rank 0 only)
+
+Workload (BASELINE.json configs[1]): a 1000-utterance synthetic batch (10 s of 16 kHz audio each,
+1248 frames per utterance), 39-dim MFCC+delta+delta-delta, 5000-state x 16-mixture diagonal GMM,
+2-byte LNA output.  One step = one pass of the hot path over that batch (per GPU: weak scaling,
+utterances are independent, no data-path collective).
+
+  value : frames/s with PCM already resident in HBM and LNA written to HBM (CUDA events)
+  e2e   : the same through the host-buffer entry point: PCM from pinned host memory, LNA bytes
+          back to pinned host memory, copies inside the timed region
+  roofline : the scorer kernel (gmm_diag_f32) against the FP32-FMA pipe (measured live with the
+          library's own FFMA2 micro-benchmark) -- batched scoring is compute bound; the HBM view
+          of the same kernel is reported next to it against MEASURED_PEAKS.json
+  cpu_baseline : the reference's own FeatureGenerator + HmmSet code (oracle/_ref, built from
+          /root/reference) on the host cores, on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_UTTS = 1000
+UTT_SAMPLES = 160000
+N_STATES, N_MIX = 5000, 16
+LNABYTES = 2
+SAMPLE_RATE = 16000
+WORKLOAD = "1000 utterances x 10 s @16 kHz, 39-dim MFCC+d+dd, 5000-state x 16-mix diag GMM, 2-byte LNA"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_audio(rank, n_utts):
+    from aaltoasr_b200 import synth
+    out = np.empty(n_utts * UTT_SAMPLES, dtype=np.int16)
+    block = 50
+    for b0 in range(0, n_utts, block):
+        nb = min(block, n_utts - b0)
+        # one long seeded stream per block, cut into utterances (fast; every utterance differs)
+        x = synth.synth_audio(2000 + 1000 * rank + b0, nb * UTT_SAMPLES, SAMPLE_RATE)
+        out[b0 * UTT_SAMPLES:(b0 + nb) * UTT_SAMPLES] = x
+    return out
+
+
+def make_model(eng):
+    """Same model on every rank: means drawn from the features of 16 fixed utterances."""
+    from aaltoasr_b200 import synth
+    pcm = np.concatenate([synth.synth_audio(2000 + i, UTT_SAMPLES, SAMPLE_RATE) for i in range(16)])
+    uo = np.arange(17, dtype=np.int64) * UTT_SAMPLES
+    feats, _ = eng.features(pcm, uo, dtype=np.float64)
+    return synth.synth_diag_model(2999, feats, N_STATES, N_MIX)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        # samples under load only (the idle ones before/after the region pull the median down)
+        load = [s for s, p in zip(sm, power) if p > 300] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own classes from oracle/_ref on the host cores
+def _ref_worker(args):
+    base, cfg, wav, n_frames = args
+    from oracle import oracle_np, ref
+    M = ref.Model(base)                       # model load is not timed
+    t0 = time.perf_counter()
+    feats, _, _ = ref.features(cfg, wav, 0, n_frames)          # FeatureGenerator::generate per frame
+    lik = M.state_likelihoods(feats)                           # HmmSet::precompute_likelihoods + state_likelihood
+    rec, _ = oracle_np.lna_records(lik, LNABYTES)              # normalise + quantise (aku/phone_probs.cc:225-262)
+    dt = time.perf_counter() - t0
+    M.close()
+    return dt, int(rec.shape[0])
+
+
+def reference_fixture(tmp, model, n_wavs):
+    from aaltoasr_b200 import formats, synth
+    cfg = os.path.join(tmp, "mfcc.cfg")
+    open(cfg, "w").write(synth.mfcc39_config(SAMPLE_RATE))
+    base = os.path.join(tmp, "model")
+    t0 = time.time()
+    formats.write_model(base, **model)
+    log("reference arm: wrote %s.gk/.mc/.ph in %.1f s" % (base, time.time() - t0))
+    wavs = []
+    for i in range(n_wavs):
+        w = os.path.join(tmp, "u%d.wav" % i)
+        formats.write_wav(w, synth.synth_audio(2000 + i, UTT_SAMPLES, SAMPLE_RATE), SAMPLE_RATE)
+        wavs.append(w)
+    return cfg, base, wavs
+
+
+def run_reference_sample(cfg, base, wavs, cores, frames_per_core):
+    """One bounded sample: every core scores `frames_per_core` frames of its own utterance with the
+    reference's code.  Returns (frames/s, seconds)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(base, cfg, wavs[i % len(wavs)], frames_per_core) for i in range(cores)])
+    frames = sum(r[1] for r in res)
+    secs = max(r[0] for r in res)
+    return frames / secs, secs
+
+
+def ref_model_from_oracle():
+    """Model for the reference arm without a GPU: means from the oracle's features (same seeds)."""
+    from aaltoasr_b200 import synth
+    from oracle import oracle_np
+    P = oracle_np.Pipeline(synth.mfcc39_config(SAMPLE_RATE))
+    feats = np.concatenate([P.run(synth.synth_audio(2000 + i, UTT_SAMPLES, SAMPLE_RATE)) for i in range(16)])
+    return synth.synth_diag_model(2999, feats, N_STATES, N_MIX)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    cores = os.cpu_count() or 1
+    frames_per_core = 384
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg, base, wavs = reference_fixture(tmp, ref_model_from_oracle(), min(cores, 16))
+        for _ in range(args.warmup):
+            run_reference_sample(cfg, base, wavs, cores, 32)
+        t_total, f_total = 0.0, 0
+        for _ in range(args.steps):
+            fps, secs = run_reference_sample(cfg, base, wavs, cores, frames_per_core)
+            t_total += secs
+            f_total += fps * secs
+    value = f_total / t_total
+    sample = "%d frames per core on %d cores per step (FeatureGenerator + HmmSet from oracle/_ref, model load excluded)" % (
+        frames_per_core, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA)", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=N_UTTS, help="utterances per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from aaltoasr_b200 import AkuGpu, F32, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the accelerated path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_utts = args.utts
+
+    eng = AkuGpu(local)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)        # torch.cuda.Event then times the library's launches
+    eng.frontend_load_config_text(synth.mfcc39_config(SAMPLE_RATE))
+    model = make_model(eng)
+    eng.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
+    t0 = time.time()
+    pcm = make_audio(rank, n_utts)
+    uo = np.arange(n_utts + 1, dtype=np.int64) * UTT_SAMPLES
+    fo = eng.frame_offsets(uo)
+    F = int(fo[-1])
+    rec = N_STATES * LNABYTES
+    log("rank %d: %d utterances, %d frames, audio generated in %.1f s" % (rank, n_utts, F, time.time() - t0))
+
+    pcm_d = torch.from_numpy(pcm).cuda()
+    out_d = torch.empty((F, rec), dtype=torch.uint8, device="cuda")
+    # e2e buffers: pinned PCM; LNA drained through one pinned buffer per sub-batch (a writer would stream it out)
+    sub = min(n_utts, 100)
+    pcm_p = torch.from_numpy(pcm).pin_memory()
+    out_p = torch.empty((int(fo[sub]), rec), dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        eng.phone_probs(pcm_d, uo, precision=F32, lnabytes=LNABYTES, out=out_d)
+
+    def step_e2e():
+        for u0 in range(0, n_utts, sub):
+            u1 = min(n_utts, u0 + sub)
+            eng.phone_probs(pcm_p[u0 * UTT_SAMPLES:u1 * UTT_SAMPLES], uo[u0:u1 + 1] - uo[u0], precision=F32,
+                            lnabytes=LNABYTES, out=out_p[:int(fo[u1] - fo[u0])])
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    eng.stage_times_reset(True)
+    l0 = eng.launch_count()
+    ms_res = timed(step_resident, args.steps)
+    launches = eng.launch_count() - l0
+    st = eng.stage_times()
+    eng.stage_times_reset(False)
+    clk = clocks.stop()
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    total_frames = F * world
+    value = total_frames * args.steps / (ms_res * 1e-3)
+    e2e_val = total_frames * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (the scorer), per launch, measured in the timed region ----
+        gmm_ms, gmm_launches = st["gmm"]
+        frames_per_launch = F * args.steps / max(1, gmm_launches)
+        avg_ms = gmm_ms / max(1, gmm_launches)
+        G = N_STATES * N_MIX
+        flop_per_frame = G * 39 * 2 * 2.0                    # 2 FMA per (component, dim), 2 flop each
+        achieved_tf = flop_per_frame * frames_per_launch / (avg_ms * 1e-3) / 1e12
+        rates = eng.pipe_rates()
+        peak_tf = 2.0 * rates["tile_ffma2"] / 1e12           # FP32 FMA pipe, measured live (lane-FMA/s x 2 flop)
+        hbm_peak, hbm_src = measured_peaks()
+        bytes_per_frame = 39 * 4 + N_STATES * 4              # features in, state log-likelihoods out
+        param_bytes = G * (2 * 40 + 1) * 4
+        alg_bytes = bytes_per_frame * frames_per_launch + param_bytes
+        hbm_gbs = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": "gmm_diag_f32<4,true>", "bound": "fp32_fma", "achieved": achieved_tf, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                    "peak_source": "library FFMA2 register-tile micro-benchmark, this run",
+                    "launches": int(gmm_launches), "avg_launch_ms": avg_ms,
+                    "share_of_step": gmm_ms / (ms_res if ms_res > 0 else 1),
+                    "hbm_view": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,
+                                 "algorithmic_bytes_per_launch": alg_bytes},
+                    "stage_ms": {"frontend": st["frontend"][0], "gmm": gmm_ms, "lna": st["lna"][0]}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
+                    cores = os.cpu_count() or 1
+                    with tempfile.TemporaryDirectory() as tmp:
+                        cfg, base, wavs = reference_fixture(tmp, model, min(cores, 16))
+                        fps, secs = run_reference_sample(cfg, base, wavs, cores, 384)
+                    cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
+                           "sample": "384 frames per core on %d cores, %.1f s (reference FeatureGenerator + HmmSet from "
+                                     "oracle/_ref, model load excluded)" % (cores, secs)}
+                else:
+                    cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
+                           "sample": "oracle/_ref not built on this box"}
+            except Exception as e:   # the baseline is reported, never required
+                cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+        line = {
+            "metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if n_utts == N_UTTS else WORKLOAD.replace("1000 utterances", "%d utterances" % n_utts),
+                       "utterances_per_gpu": n_utts, "frames_per_gpu": F, "precision": "F32 throughput mode",
+                       "l2_policy": "inputs+outputs per step (%.1f GB) exceed L2; no flush needed" % (F * rec / 1e9),
+                       "parallelism": "utterance shards, one process per GPU, no data-path collective"},
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(pcm.nbytes),
+                    "d2h_bytes_per_step": int(F * rec), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -143,7 +143,8 @@ int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_o
 int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5]);
 
 /* ---- tuning / introspection ---------------------------------------------------- */
-/* Frames scored per chunk of the pipelined batch path (default 16384). */
+/* Frames scored per chunk of the pipelined batch path.  0 (default) = one full wave of the
+ * scorer (SM count x resident CTAs x 64 frames = 37888 on B200). */
 int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames);
 /* Kernel variant of the fp32 scorer: 0 = auto, 1 = FFMA (8 frames x 8 comps / thread),
  * 2 = packed FFMA2 (8 frames x 4 comps x 2 dims / thread). */

@@ -29,7 +29,7 @@ out_d = torch.empty((F, 5000 * 2), dtype=torch.uint8, device="cuda")
 for variant in (1, 2):
     eng.set_scorer_variant(variant)
     eng.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
-    for chunk in (4096, 16384, 65536):
+    for chunk in (16384, 0, 75776):
         eng.set_chunk_frames(chunk)
         eng.phone_probs(pcm_d, uo, lnabytes=2, out=out_d)
         eng.stage_times_reset(True)
@@ -46,7 +46,7 @@ for variant in (1, 2):
               % (variant, chunk, dt, F / dt, st["frontend"][0], gmm_ms, st["lna"][0], flops / gmm_ms / 1e9, F / gmm_ms * 1e3))
 eng.set_scorer_variant(0)
 eng.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
-eng.set_chunk_frames(16384)
+eng.set_chunk_frames(0)
 # parity mode throughput on a slice
 t0 = time.time()
 eng.gmm_lna(feats[:4096], precision=F64, lnabytes=2)

@@ -190,10 +190,10 @@ def test_phone_probs_batch_and_chunking(engine, ref_small):
     try:
         engine.set_chunk_frames(128)
         small, fo, _ = engine.phone_probs(np.concatenate(cuts), uo, lnabytes=2)
-        engine.set_chunk_frames(16384)
+        engine.set_chunk_frames(0)
         big, fo2, _ = engine.phone_probs(np.concatenate(cuts), uo, lnabytes=2)
     finally:
-        engine.set_chunk_frames(16384)
+        engine.set_chunk_frames(0)
     assert np.array_equal(fo, fo2) and np.array_equal(small, big)
     for k, c in enumerate(cuts):
         one, _, _ = engine.phone_probs(c, lnabytes=2)
