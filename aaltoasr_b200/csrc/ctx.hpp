@@ -81,16 +81,17 @@ struct HostModel {
   std::vector<double> mean, cov;    // [G*D]
 };
 
-// fp32 scorer image: tiles of TC = 16*GR component slots, see gmm_kernels.cu.
+// fp32 scorer image: tiles of 8 slots x 16 components, see gmm_kernels.cu.
 struct PackedF32 {
-  int GR = 0;            // component slots per thread (4 or 8)
-  int TC = 0;            // component slots per tile
-  int DP = 0;            // dim pairs
+  bool packed_ffma2 = true;  // FFMA2 (default) or plain FFMA instructions
+  int DP = 0;                // dim pairs
   int n_tiles = 0;
   size_t tile_floats = 0;
-  DevBuf params;         // n_tiles * tile_floats floats
-  DevBuf center;         // float [2*DP] feature centre
-  DevBuf center64;       // double [2*DP]
+  DevBuf params;             // n_tiles * tile_floats floats
+  DevBuf center;             // float [2*DP] feature centre
+  DevBuf center64;           // double [2*DP]
+  std::vector<char> clean;   // [n_tiles] 1 = every queue starts a new state at this tile
+  std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;   // ysplit -> (count, device int[count+1])
 };
 // fp64 scorer image: plain arrays in the reference's own order.
 struct PackedF64 {

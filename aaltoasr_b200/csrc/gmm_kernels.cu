@@ -17,35 +17,38 @@
 //   gmm_diag_f64         parity mode.  Same operation order as the reference in
 //     double (no FMA contraction), linear-domain mixture sum, 1e-50 floor.
 //
-// Data layout (fp32 image, built by pack_model_f32 in model.cu)
-//   component slots are grouped into tiles of TC = 16*GR slots; a state's slots are
-//   contiguous, padded to a multiple of GR, and never straddle a tile.  One tile is
-//   one contiguous "stage image" in HBM:
-//        float4 P[DP][TC]   {s(2dp), s(2dp+1), m(2dp), m(2dp+1)}  slot-permuted
-//        float  C[TC]       -(log w + log sqrt(prod prec))   (i.e. -c ; +1e30 for pads)
-//   fetched with ONE cp.async.bulk (TMA 1-D, UBLKCP) per stage into a 2-deep ring,
-//   completion on an mbarrier.  Slot permutation: the j-th slot of thread-group cg
-//   sits at position j*16+cg so that a warp's LDS.128 are conflict free.
+// Data layout (fp32 image, built by model_pack in model.cu)
+//   A "slot" is 16 component positions of ONE state (padded with weight-0 components); a state
+//   with K components owns ceil(K/16) slots.  Slots are dealt into 8 queues, one per warp of a
+//   CTA, a state's slots staying consecutive in one queue.  Tile t = the t-th slot of each queue
+//   = 128 components, stored as one contiguous "stage image" in HBM:
+//        float4 P[DP][128]  {s(2dp), s(2dp+1), m(2dp), m(2dp+1)}     component = warp*16 + j
+//        float  C[128]      -(log w + log sqrt(prod prec))           (+1e30 for padding)
+//        int    META[8]     per warp: state<<2 | first<<1 | last     (-1: padding slot)
+//   fetched with ONE cp.async.bulk (TMA 1-D, UBLKCP) per stage into a 2-deep ring, completion on
+//   an mbarrier; the last warp to finish a stage re-arms its buffer (no CTA-wide barrier).
 //
-// CTA = 256 threads = 16 frame-groups x 16 component-groups; thread tile = 8 frames
-// x GR components; CTA tile = 128 frames x TC components per stage.  Output is
-// state-major  sll[state][ldF]  (fp32 natural-log likelihood), coalesced over frames,
+// CTA = 256 threads = 8 independent warps over the same 128 frames; warp tile = 128 frames x 16
+// components, thread tile = 4 frames x 16 components.  The FMAs are packed FFMA2 over FRAME
+// pairs: (x[f0],x[f1]) * s + m with s and m as scalar-broadcast operands (SASS `R.F32`), which
+// measured 94-96% of the FP32 pipe in isolation against 74% for three 64-bit operands
+// (scripts/micro_occ2.cu).  Because a thread owns every component of its slot, the mixture
+// log-sum-exp is entirely in registers, carried across the slots of a big state; there is no
+// shared-memory exchange and no __syncthreads in the loop.  Output is state-major
+// sll[state][ldF] (fp32 natural-log likelihood), coalesced 256-byte row segments per warp,
 // which is also the order the LNA epilogue (lna_kernels.cu) sweeps it in.
 #include "ctx.hpp"
 #include "kernels.hpp"
 
 namespace akugpu {
 
-constexpr int TF = 64;           // frames per CTA tile
-constexpr int FR = 8;            // frames per thread
-constexpr int NTH = 128;
-constexpr int NFG = TF / FR;     // 8 frame groups
-constexpr int NCG = NTH / NFG;   // 16 component groups
-#ifndef GMM_DP_UNROLL
-#define GMM_DP_UNROLL 2
-#endif
-constexpr int TAB_INTS = 32;     // per-tile state table appended to the stage image
-constexpr int kDpUnroll = GMM_DP_UNROLL;
+constexpr int TF = 128;          // frames per CTA (and per warp) tile
+constexpr int NTH = 256;
+constexpr int NW = NTH / 32;     // warps = slots per tile
+constexpr int GR = 16;           // components per slot
+constexpr int TC = NW * GR;      // components per tile
+constexpr int NPAIR = TF / 2;    // frame pairs per tile
+constexpr int CTAS_PER_SM = 2;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -92,59 +95,36 @@ __device__ __forceinline__ float lg2f(float x) {
   return y;
 }
 
-template <int GR, bool F2>
-struct AccT;
-template <int GR>
-struct AccT<GR, false> { float v[FR][GR]; };
-template <int GR>
-struct AccT<GR, true> { float2 v[FR][GR]; };
-
-// One (frame, component, dim-pair) update: t = x*s + m ; acc += t*t.
-template <bool F2, bool FIRST, class A>
-__device__ __forceinline__ void gmm_step(A &acc, float x0, float x1, const float4 &p, float nc)
-{
-  if constexpr (F2) {
-    float2 tt = __ffma2_rn(make_float2(x0, x1), make_float2(p.x, p.y), make_float2(p.z, p.w));
-    acc = __ffma2_rn(tt, tt, FIRST ? make_float2(nc, 0.f) : acc);
-  } else {
-    float t0 = fmaf(x0, p.x, p.z);
-    float t1 = fmaf(x1, p.y, p.w);
-    acc = fmaf(t0, t0, FIRST ? nc : acc);
-    acc = fmaf(t1, t1, acc);
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// grid.x = frame tiles (64 frames), grid.y = split of the component tiles (only used when there
-// are too few frame tiles to fill the chip).  4 CTAs of 128 threads are resident per SM so that
-// one CTA's log-sum-exp epilogue hides under the other CTAs' FMA loops.
-template <int GR, bool F2>
-__global__ void __launch_bounds__(NTH, F2 ? 4 : 2)
-gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t f_end, int D, int DP,
-             const float *__restrict__ params, size_t tile_floats, int n_tiles, int tiles_per_cta,
+// grid.x = frame tiles (128 frames); grid.y = ranges of component tiles (more than one only when
+// there are too few frame tiles to fill the chip; range boundaries never cut a state's slots).
+// 2 CTAs x 8 warps are resident per SM; every warp runs its own tile loop.
+// DPC > 0: number of dim pairs known at compile time (20 for 39/40-dim features); 0: runtime.
+template <bool F2, int DPC>
+__global__ void __launch_bounds__(NTH, CTAS_PER_SM)
+gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t f_end, int D, int DP_rt,
+             const float *__restrict__ params, size_t tile_floats, const int *__restrict__ range_begin,
              const float *__restrict__ center, const double *__restrict__ center64,
-             float *__restrict__ sll, int64_t ldF)
+             float *__restrict__ sll, int64_t ldF, int dbg)
 {
-  constexpr int TC = NCG * GR;
+  const int DP = DPC > 0 ? DPC : DP_rt;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t stage_bytes = (uint32_t)(tile_floats * sizeof(float));
-  float2 *xs = reinterpret_cast<float2 *>(smem_raw);                         // [DP][TF]
-  unsigned char *stage0 = smem_raw + (size_t)DP * TF * sizeof(float2);
+  // xs[dp][pair] = {x[f0][2dp], x[f1][2dp], x[f0][2dp+1], x[f1][2dp+1]},  f0 = 2*pair, f1 = 2*pair+1
+  float4 *xs = reinterpret_cast<float4 *>(smem_raw);
+  unsigned char *stage0 = smem_raw + (size_t)DP * NPAIR * sizeof(float4);
   __shared__ uint64_t full_bar[2];
+  __shared__ int done_cnt[2];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int fg = lane & 7;                 // frame group: frames k*16 + fg*2 + {0,1}, k = 0..3
-  const int cg = warp * 4 + (lane >> 3);   // component group
-
   const int64_t f0 = f_begin + (int64_t)blockIdx.x * TF;
-  const int t_begin = blockIdx.y * tiles_per_cta;
-  const int t_end = min(n_tiles, t_begin + tiles_per_cta);
+  const int t_begin = range_begin[blockIdx.y], t_end = range_begin[blockIdx.y + 1];
   if (t_begin >= t_end) return;
 
   if (tid == 0) {
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
+    done_cnt[0] = done_cnt[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -156,8 +136,7 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
       tma_load_1d(stage0 + stage_bytes, params + (size_t)(t_begin + 1) * tile_floats, stage_bytes, &full_bar[1]);
     }
   }
-
-  // Frame tile -> shared, transposed to [dim pair][frame] and centred.
+  // Frame tile -> shared, centred, regrouped into frame pairs.
   {
     const int D2 = 2 * DP;
     float *xsf = reinterpret_cast<float *>(xs);
@@ -171,96 +150,113 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
         else
           v = reinterpret_cast<const float *>(feats)[gf * D + d] - center[d];
       }
-      xsf[((d >> 1) * TF + fr) * 2 + (d & 1)] = v;
+      xsf[((d >> 1) * NPAIR + (fr >> 1)) * 4 + (d & 1) * 2 + (fr & 1)] = v;
     }
   }
   __syncthreads();
 
-  uint32_t phase[2] = {0, 0};
+  // log-sum-exp state carried across the slots of a multi-slot state lives in shared memory
+  // (only touched by states with more than 16 components): run[q][tid] = {a.x, a.y, s.x, s.y}
+  float4 *run = reinterpret_cast<float4 *>(stage0 + 2 * (size_t)stage_bytes);
+  uint32_t phase = 0;                                   // bit b = parity to wait for on buffer b
+  float *const out_col = sll + (f0 - f_begin) + 2 * lane;
   for (int t = t_begin; t < t_end; ++t) {
     const int b = (t - t_begin) & 1;
     unsigned char *stage = stage0 + (size_t)b * stage_bytes;
-    const float4 *ps = reinterpret_cast<const float4 *>(stage);
+    const float4 *ps = reinterpret_cast<const float4 *>(stage) + warp * GR;
     const float *cs = reinterpret_cast<const float *>(stage + (size_t)DP * TC * sizeof(float4));
-    const int *tab = reinterpret_cast<const int *>(cs + TC);
-    mbar_wait(&full_bar[b], phase[b]);
-    phase[b] ^= 1;
+    if (!(dbg & 2) || t < t_begin + 2) mbar_wait(&full_bar[b], (phase >> b) & 1);
+    phase ^= 1u << b;
 
-    AccT<GR, F2> acc;
+    float2 acc[2][GR];                                // [pair][component] = -(log-likelihood) of 2 frames
 #pragma unroll
-    for (int j = 0; j < GR; ++j) {
-      const float nc = cs[j * NCG + cg];     // accumulators start at -c
-#pragma unroll
-      for (int i = 0; i < FR; ++i) {
-        if constexpr (F2) acc.v[i][j] = make_float2(nc, 0.f);
-        else acc.v[i][j] = nc;
-      }
+    for (int c = 0; c < GR; ++c) {
+      const float nc = cs[warp * GR + c];             // accumulators start at -c
+      acc[0][c] = make_float2(nc, nc);
+      acc[1][c] = make_float2(nc, nc);
     }
-#pragma unroll (kDpUnroll)
+#pragma unroll 2
     for (int dp = 0; dp < DP; ++dp) {
-      float4 xv[FR / 2], pv[GR];
+      const float4 xa = xs[dp * NPAIR + lane];        // frames 2*lane, 2*lane+1
+      const float4 xb = xs[dp * NPAIR + 32 + lane];   // frames 64+2*lane, 65+2*lane
 #pragma unroll
-      for (int k = 0; k < FR / 2; ++k) xv[k] = *reinterpret_cast<const float4 *>(&xs[dp * TF + k * 16 + fg * 2]);
-#pragma unroll
-      for (int j = 0; j < GR; ++j) pv[j] = ps[dp * TC + j * NCG + cg];
-#pragma unroll
-      for (int i = 0; i < FR; ++i) {
-        const float x0 = (i & 1) ? xv[i >> 1].z : xv[i >> 1].x;
-        const float x1 = (i & 1) ? xv[i >> 1].w : xv[i >> 1].y;
-#pragma unroll
-        for (int j = 0; j < GR; ++j) gmm_step<F2, false>(acc.v[i][j], x0, x1, pv[j], 0.f);
-      }
-    }
-    __syncthreads();   // everyone is done reading this stage's parameters: reuse its head for the partials
-                       // (the state table sits at the tail of the image and stays intact)
-
-    // Thread-level log-sum-exp over its GR components: a = min(-ll), sum = sum exp(ll + a).
-    float2 *part = reinterpret_cast<float2 *>(stage);   // [NCG][TF]
-#pragma unroll
-    for (int i = 0; i < FR; ++i) {
-      float v[GR];
-#pragma unroll
-      for (int j = 0; j < GR; ++j) {
-        if constexpr (F2) v[j] = acc.v[i][j].x + acc.v[i][j].y;
-        else v[j] = acc.v[i][j];
-      }
-      float a = v[0];
-#pragma unroll
-      for (int j = 1; j < GR; ++j) a = fminf(a, v[j]);
-      const float al = a * LOG2E;
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < GR; ++j) sum += ex2f(fmaf(v[j], -LOG2E, al));
-      const int fr = (i >> 1) * 16 + fg * 2 + (i & 1);
-      part[cg * TF + fr] = make_float2(a, sum);
-    }
-    __syncthreads();
-
-    // Combine the thread-groups of each state of this tile; write state log-likelihoods.
-    {
-      const int nst = tab[0], s0 = tab[1];
-      const int fr = tid & (TF - 1);
-      // thread handles frame (tid & 63) of local states (tid >> 6), +2, +4, ..
-      for (int ls = tid >> 6; ls < nst; ls += NTH / TF) {
-        {
-          const int e = tab[2 + ls];
-          const int g0 = e & 255, ng = e >> 8;
-          float A = part[g0 * TF + fr].x;
-          for (int g = 1; g < ng; ++g) A = fminf(A, part[(g0 + g) * TF + fr].x);
-          float tot = 0.f;
-          for (int g = 0; g < ng; ++g) {
-            float2 p = part[(g0 + g) * TF + fr];
-            tot = fmaf(p.y, ex2f((A - p.x) * LOG2E), tot);
-          }
-          sll[(int64_t)(s0 + ls) * ldF + (f0 - f_begin) + fr] = fmaf(lg2f(tot), LN2, -A);
+      for (int c = 0; c < GR; ++c) {
+        const float4 p = ps[dp * TC + c];             // warp-uniform address: broadcast
+        if constexpr (F2) {
+          // s and m enter as scalar-broadcast operands
+          float2 t0 = __ffma2_rn(make_float2(xa.x, xa.y), make_float2(p.x, p.x), make_float2(p.z, p.z));
+          float2 u0 = __ffma2_rn(make_float2(xb.x, xb.y), make_float2(p.x, p.x), make_float2(p.z, p.z));
+          float2 t1 = __ffma2_rn(make_float2(xa.z, xa.w), make_float2(p.y, p.y), make_float2(p.w, p.w));
+          float2 u1 = __ffma2_rn(make_float2(xb.z, xb.w), make_float2(p.y, p.y), make_float2(p.w, p.w));
+          acc[0][c] = __ffma2_rn(t0, t0, acc[0][c]);
+          acc[1][c] = __ffma2_rn(u0, u0, acc[1][c]);
+          acc[0][c] = __ffma2_rn(t1, t1, acc[0][c]);
+          acc[1][c] = __ffma2_rn(u1, u1, acc[1][c]);
+        } else {
+          float a0 = fmaf(xa.x, p.x, p.z), a1 = fmaf(xa.y, p.x, p.z), a2 = fmaf(xa.z, p.y, p.w), a3 = fmaf(xa.w, p.y, p.w);
+          float b0 = fmaf(xb.x, p.x, p.z), b1 = fmaf(xb.y, p.x, p.z), b2 = fmaf(xb.z, p.y, p.w), b3 = fmaf(xb.w, p.y, p.w);
+          acc[0][c].x = fmaf(a0, a0, acc[0][c].x); acc[0][c].y = fmaf(a1, a1, acc[0][c].y);
+          acc[1][c].x = fmaf(b0, b0, acc[1][c].x); acc[1][c].y = fmaf(b1, b1, acc[1][c].y);
+          acc[0][c].x = fmaf(a2, a2, acc[0][c].x); acc[0][c].y = fmaf(a3, a3, acc[0][c].y);
+          acc[1][c].x = fmaf(b2, b2, acc[1][c].x); acc[1][c].y = fmaf(b3, b3, acc[1][c].y);
         }
       }
     }
-    __syncthreads();
-    if (tid == 0 && t + 2 < t_end) {
-      fence_proxy_async();
-      mbar_expect_tx(&full_bar[b], stage_bytes);
-      tma_load_1d(stage, params + (size_t)(t + 2) * tile_floats, stage_bytes, &full_bar[b]);
+    const int meta = reinterpret_cast<const int *>(cs + TC)[warp];
+
+    // This warp is done with the stage buffer; the last of the 8 warps re-arms it.
+    __syncwarp();
+    if (lane == 0) {
+      const int old = atomicAdd(&done_cnt[b], 1);
+      if (old == NW - 1) {
+        done_cnt[b] = 0;
+        __threadfence_block();
+        if (t + 2 < t_end && !(dbg & 2)) {
+          fence_proxy_async();
+          mbar_expect_tx(&full_bar[b], stage_bytes);
+          tma_load_1d(stage, params + (size_t)(t + 2) * tile_floats, stage_bytes, &full_bar[b]);
+        }
+      }
+    }
+    if (dbg & 1) {   // experiment: no log-sum-exp epilogue
+      float r = 0.f;
+#pragma unroll
+      for (int c = 0; c < GR; ++c) r += acc[0][c].x + acc[0][c].y + acc[1][c].x + acc[1][c].y;
+      if (r == 1.2345f) out_col[0] = r;
+      continue;
+    }
+
+    // Mixture log-sum-exp over the slot, in registers: a = min(-ll), s = sum exp(ll + a).
+    const bool first = (meta & 2) != 0, last = (meta & 1) != 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float2 a = acc[q][0];
+#pragma unroll
+      for (int c = 1; c < GR; ++c) { a.x = fminf(a.x, acc[q][c].x); a.y = fminf(a.y, acc[q][c].y); }
+      float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!first) {
+        prev = run[q * NTH + tid];
+        a.x = fminf(a.x, prev.x); a.y = fminf(a.y, prev.y);
+      }
+      const float2 al = make_float2(a.x * LOG2E, a.y * LOG2E);
+      const float2 nl = make_float2(-LOG2E, -LOG2E);
+      float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < GR; c += 2) {
+        float2 e0 = __ffma2_rn(acc[q][c], nl, al), e1 = __ffma2_rn(acc[q][c + 1], nl, al);
+        s0 = __fadd2_rn(s0, make_float2(ex2f(e0.x), ex2f(e0.y)));
+        s1 = __fadd2_rn(s1, make_float2(ex2f(e1.x), ex2f(e1.y)));
+      }
+      float2 sum = __fadd2_rn(s0, s1);
+      if (!first) {
+        float2 e = __ffma2_rn(make_float2(prev.x, prev.y), nl, al);
+        sum = __ffma2_rn(make_float2(prev.z, prev.w), make_float2(ex2f(e.x), ex2f(e.y)), sum);
+      }
+      if (!last) run[q * NTH + tid] = make_float4(a.x, a.y, sum.x, sum.y);
+      if (last && meta >= 0) {
+        const float2 res = make_float2(fmaf(lg2f(sum.x), LN2, -a.x), fmaf(lg2f(sum.y), LN2, -a.y));
+        *reinterpret_cast<float2 *>(out_col + (int64_t)(meta >> 2) * ldF + q * 64) = res;
+      }
     }
   }
 }
@@ -347,10 +343,38 @@ __global__ void transpose_sf(const T *__restrict__ in, int64_t ldF, int S, int64
 // ------------------------------------------------------------------------------------
 // launchers
 size_t gmm_f32_smem_bytes(const PackedF32 &p) {
-  return (size_t)p.DP * TF * sizeof(float2) + 2 * p.tile_floats * sizeof(float);
+  return (size_t)p.DP * NPAIR * sizeof(float4) + 2 * p.tile_floats * sizeof(float) + 2 * NTH * sizeof(float4);
 }
 
-template <int GR, bool F2>
+// Frames per full wave of the fp32 scorer (chunks should be a multiple of this).
+int64_t gmm_wave_frames(akugpu_ctx *ctx) { return (int64_t)ctx->sm_count * CTAS_PER_SM * TF; }
+int gmm_frame_tile() { return TF; }
+
+// Splits the component tiles into `want` ranges whose boundaries are "clean" tiles (every queue
+// starts a new state there).  Cached per ysplit in the packed model.
+static const int *tile_ranges(akugpu_ctx *ctx, int want, int &got)
+{
+  PackedF32 &p = ctx->p32;
+  auto it = p.ranges.find(want);
+  if (it == p.ranges.end()) {
+    std::vector<int> r(1, 0);
+    for (int k = 1; k < want; ++k) {
+      int target = (int)((int64_t)p.n_tiles * k / want);
+      while (target < p.n_tiles && !p.clean[target]) target++;
+      if (target > r.back() && target < p.n_tiles) r.push_back(target);
+    }
+    r.push_back(p.n_tiles);
+    auto buf = std::make_shared<DevBuf>();
+    buf->reserve(r.size() * sizeof(int));
+    AKU_CUDA(cudaMemcpyAsync(buf->p, r.data(), r.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = p.ranges.emplace(want, std::make_pair((int)r.size() - 1, buf)).first;
+  }
+  got = it->second.first;
+  return it->second.second->as<int>();
+}
+
+template <bool F2, int DPC>
 static void launch_f32_t(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end,
                          float *sll, int64_t ldF)
 {
@@ -359,35 +383,38 @@ static void launch_f32_t(akugpu_ctx *ctx, const void *feats, int feats_f64, int6
   size_t smem = gmm_f32_smem_bytes(p);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    AKU_CUDA(cudaFuncSetAttribute(gmm_diag_f32<GR, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AKU_CUDA(cudaFuncSetAttribute(gmm_diag_f32<F2, DPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   int64_t nf = f_end - f_begin;
   int ftiles = (int)((nf + TF - 1) / TF);
-  // One wave = sm_count * resident CTAs.  Full chunks are sized to whole waves by the caller
+  // One wave = sm_count * 2 resident CTAs.  Full chunks are sized to whole waves by the caller
   // (gmm_wave_frames); a short chunk splits the component tiles over grid.y to fill the chip.
-  const int wave = ctx->sm_count * (F2 ? 4 : 2);
+  const int wave = ctx->sm_count * CTAS_PER_SM;
+  int want = 1;
+  if (ftiles < wave) want = std::min(p.n_tiles, std::max(1, wave / ftiles));
   int ysplit = 1;
-  if (ftiles < wave) ysplit = std::min(p.n_tiles, std::max(1, wave / ftiles));
-  int tiles_per_cta = (p.n_tiles + ysplit - 1) / ysplit;
-  ysplit = (p.n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+  const int *ranges = tile_ranges(ctx, want, ysplit);
   dim3 grid(ftiles, ysplit);
-  gmm_diag_f32<GR, F2><<<grid, NTH, smem, ctx->stream>>>(
-      feats, feats_f64, f_begin, f_end, hm.D, p.DP, p.params.as<float>(), p.tile_floats, p.n_tiles, tiles_per_cta,
-      p.center.as<float>(), p.center64.as<double>(), sll, ldF);
+  gmm_diag_f32<F2, DPC><<<grid, NTH, smem, ctx->stream>>>(feats, feats_f64, f_begin, f_end, hm.D, p.DP, p.params.as<float>(),
+                                                     p.tile_floats, ranges, p.center.as<float>(),
+                                                     p.center64.as<double>(), sll, ldF,
+                                                     getenv("AKUGPU_DBG") ? atoi(getenv("AKUGPU_DBG")) : 0);
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
 }
 
-// Frames per full wave of the fp32 scorer (chunks should be a multiple of this).
-int64_t gmm_wave_frames(akugpu_ctx *ctx) { return (int64_t)ctx->sm_count * (ctx->p32.GR == 4 ? 4 : 2) * TF; }
-int gmm_frame_tile() { return TF; }
-
 void launch_gmm_f32(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll,
                     int64_t ldF)
 {
-  if (ctx->p32.GR == 4) launch_f32_t<4, true>(ctx, feats, feats_f64, f_begin, f_end, sll, ldF);
-  else launch_f32_t<8, false>(ctx, feats, feats_f64, f_begin, f_end, sll, ldF);
+  const bool dp20 = ctx->p32.DP == 20;
+  if (ctx->p32.packed_ffma2) {
+    if (dp20) launch_f32_t<true, 20>(ctx, feats, feats_f64, f_begin, f_end, sll, ldF);
+    else launch_f32_t<true, 0>(ctx, feats, feats_f64, f_begin, f_end, sll, ldF);
+  } else {
+    if (dp20) launch_f32_t<false, 20>(ctx, feats, feats_f64, f_begin, f_end, sll, ldF);
+    else launch_f32_t<false, 0>(ctx, feats, feats_f64, f_begin, f_end, sll, ldF);
+  }
 }
 
 void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, double *lin,

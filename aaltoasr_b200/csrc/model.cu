@@ -180,21 +180,13 @@ void model_pack(akugpu_ctx *ctx)
     upload(p.mix_w, hm.mix_w, ctx->stream);
     ctx->have_p64 = true;
   }
-  // ---- fp32 image ----
+  // ---- fp32 image: slots of 16 components dealt into 8 warp queues (gmm_kernels.cu) ----
   PackedF32 &p = ctx->p32;
-  int maxK = 0;
-  for (int s = 0; s < S; s++) maxK = std::max(maxK, hm.mix_off[s + 1] - hm.mix_off[s]);
-  int variant = ctx->scorer_variant;
-  if (variant == 0) variant = 2;
-  if (variant == 2 && maxK > 64) variant = 1;
-  p.GR = (variant == 2) ? 4 : 8;
-  const int NCG = 16;
-  p.TC = NCG * p.GR;
-  if (maxK > p.TC)
-    throw Error(AKUGPU_E_MODEL, fmt("a mixture has %d components; the scorer supports at most %d per state", maxK, p.TC));
+  const int NW = 8, GR = 16, TC = NW * GR, META_INTS = 8;
+  p.packed_ffma2 = ctx->scorer_variant != 1;
+  p.ranges.clear();
   p.DP = (D + 1) / 2;
-  const int TAB_INTS = 32;   // per-tile state table: [0] #states, [1] first state, [2+ls] first group | groups << 8
-  p.tile_floats = (size_t)p.DP * p.TC * 4 + p.TC + TAB_INTS;
+  p.tile_floats = (size_t)p.DP * TC * 4 + TC + META_INTS;
 
   std::vector<double> cen(2 * p.DP, 0.0);
   if (G > 0)
@@ -203,51 +195,46 @@ void model_pack(akugpu_ctx *ctx)
       for (int g = 0; g < G; g++) s += hm.mean[(size_t)g * D + d];
       cen[d] = s / G;
     }
-  // tile assignment: states in order, never straddling a tile
-  std::vector<int32_t> tile_state0(1, 0);
-  std::vector<int32_t> st_grp(2 * (size_t)S);
-  int used = 0, tile = 0;
+  // Deal the states to the shortest queue, in state order; a state's slots stay consecutive.
+  struct Slot { int state, k0, first, last; };
+  std::vector<std::vector<Slot>> queue(NW);
   for (int s = 0; s < S; s++) {
-    int K = hm.mix_off[s + 1] - hm.mix_off[s];
-    int ng = std::max(1, (K + p.GR - 1) / p.GR);
-    if (used + ng > NCG) { tile++; tile_state0.push_back(s); used = 0; }
-    st_grp[2 * s] = tile * NCG + used;
-    st_grp[2 * s + 1] = ng;
-    used += ng;
+    const int K = hm.mix_off[s + 1] - hm.mix_off[s];
+    const int ns = std::max(1, (K + GR - 1) / GR);
+    int q = 0;
+    for (int w = 1; w < NW; w++) if (queue[w].size() < queue[q].size()) q = w;
+    for (int i = 0; i < ns; i++) queue[q].push_back(Slot{s, i * GR, i == 0, i == ns - 1});
   }
-  p.n_tiles = S > 0 ? tile + 1 : 0;
-  tile_state0.push_back(S);
-  std::vector<float> img((size_t)p.n_tiles * p.tile_floats, 0.f);
-  for (int t = 0; t < p.n_tiles; t++) {
-    float *C = img.data() + (size_t)t * p.tile_floats + (size_t)p.DP * p.TC * 4;
-    for (int i = 0; i < p.TC; i++) C[i] = 1.0e30f;
-    int32_t *tab = reinterpret_cast<int32_t *>(C + p.TC);
-    tab[0] = tile_state0[t + 1] - tile_state0[t];
-    tab[1] = tile_state0[t];
-    for (int ls = 0; ls < tab[0]; ls++) {
-      int s = tile_state0[t] + ls;
-      tab[2 + ls] = (st_grp[2 * s] % NCG) | (st_grp[2 * s + 1] << 8);
-    }
-  }
-  for (int s = 0; s < S; s++) {
-    int K = hm.mix_off[s + 1] - hm.mix_off[s];
-    int g0 = st_grp[2 * s];
-    int t = g0 / NCG;
-    float *P = img.data() + (size_t)t * p.tile_floats;
-    float *C = P + (size_t)p.DP * p.TC * 4;
-    for (int k = 0; k < K; k++) {
-      int cg = (g0 % NCG) + k / p.GR, j = k % p.GR;
-      int slot = j * NCG + cg;
-      int g = hm.mix_gauss[hm.mix_off[s] + k];
-      double w = hm.mix_w[hm.mix_off[s] + k];
-      double c = (w > 0 ? log(w) : -1.0e30) + cst[g];
-      C[slot] = (c > -1.0e30) ? (float)(-c) : 1.0e30f;
-      for (int d = 0; d < D; d++) {
-        float sf = (float)sqrt(0.5 * prec[(size_t)g * D + d]);
-        float mf = (float)(-(hm.mean[(size_t)g * D + d] - cen[d]) * (double)sf);
-        float *q = P + ((size_t)(d >> 1) * p.TC + slot) * 4;
-        q[d & 1] = sf;
-        q[2 + (d & 1)] = mf;
+  size_t T = 0;
+  for (int w = 0; w < NW; w++) T = std::max(T, queue[w].size());
+  p.n_tiles = (int)T;
+  p.clean.assign(T, 1);
+  std::vector<float> img(T * p.tile_floats, 0.f);
+  for (size_t t = 0; t < T; t++) {
+    float *P = img.data() + t * p.tile_floats;
+    float *C = P + (size_t)p.DP * TC * 4;
+    int32_t *meta = reinterpret_cast<int32_t *>(C + TC);
+    for (int i = 0; i < TC; i++) C[i] = 1.0e30f;
+    for (int w = 0; w < NW; w++) {
+      if (t >= queue[w].size()) { meta[w] = -1; continue; }   // padding slot: computed, never written
+      const Slot &sl = queue[w][t];
+      meta[w] = (sl.state << 2) | (sl.first << 1) | sl.last;
+      if (!sl.first) p.clean[t] = 0;
+      const int K = hm.mix_off[sl.state + 1] - hm.mix_off[sl.state];
+      for (int j = 0; j < GR && sl.k0 + j < K; j++) {
+        const int k = hm.mix_off[sl.state] + sl.k0 + j;
+        const int g = hm.mix_gauss[k];
+        const double wgt = hm.mix_w[k];
+        const double c = (wgt > 0 ? log(wgt) : -1.0e30) + cst[g];
+        const int comp = w * GR + j;
+        C[comp] = (c > -1.0e30) ? (float)(-c) : 1.0e30f;
+        for (int d = 0; d < D; d++) {
+          float sf = (float)sqrt(0.5 * prec[(size_t)g * D + d]);
+          float mf = (float)(-(hm.mean[(size_t)g * D + d] - cen[d]) * (double)sf);
+          float *q = P + ((size_t)(d >> 1) * TC + comp) * 4;
+          q[d & 1] = sf;
+          q[2 + (d & 1)] = mf;
+        }
       }
     }
   }
