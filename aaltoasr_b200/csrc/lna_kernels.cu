@@ -80,19 +80,28 @@ lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int norma
   if (normalize) {
     double R = 0.0;
     for (int sb = w * 8; sb < S; sb += 64) {
+      // 8 independent loads in flight, then one rescale per batch
+      float L[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) L[j] = (sb + j < S) ? __ldcs(col + (int64_t)(sb + j) * ldF) : -INFINITY;
+      float bm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { L[j] = log_of_float_cast(L[j]); bm = fmaxf(bm, L[j]); }
+      if (bm == -INFINITY) continue;
+      // the running maximum is excluded from R: R = sum over all other terms of exp(L - Mx)
+      bool excl = false;
+      if (bm > Mx) {
+        R = (Mx == -INFINITY) ? 0.0 : (R + 1.0) * (double)__expf(Mx - bm);
+        Mx = bm;
+        excl = true;          // the first element equal to the new maximum is the excluded one
+      }
+      float acc = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        int s = sb + j;
-        if (s < S) {
-          float L = log_of_float_cast(col[(int64_t)s * ldF]);
-          if (L > Mx) {
-            R = (Mx == -INFINITY) ? 0.0 : (R + 1.0) * (double)__expf(Mx - L);
-            Mx = L;
-          } else if (L != -INFINITY) {
-            R += (double)__expf(L - Mx);
-          }
-        }
+        if (excl && L[j] == Mx) { excl = false; continue; }
+        if (L[j] != -INFINITY) acc += __expf(L[j] - Mx);
       }
+      R += (double)acc;
     }
     sh_M[w][lane] = Mx;
     sh_R[w][lane] = R;
@@ -114,12 +123,18 @@ lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int norma
   }
 
   for (int s_round = 0; s_round < S; s_round += 64) {
+    float Lv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int s = s_round + w * 8 + j;
+      Lv[j] = (s < S) ? __ldcs(col + (int64_t)s * ldF) : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int s = s_round + w * 8 + j;
       float lp = LP_FLOOR;
       if (s < S) {
-        float L = log_of_float_cast(col[(int64_t)s * ldF]);
+        float L = log_of_float_cast(Lv[j]);
         if (normalize) {
           if (Mx != -INFINITY && L != -INFINITY) lp = (float)((double)(L - Mx) - lognorm);
         } else {
