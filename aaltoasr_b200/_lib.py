@@ -40,6 +40,7 @@ SYMBOLS = {
     "akugpu_features_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_char_p,
                                         C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "akugpu_model_read": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "akugpu_model_read_files": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "akugpu_model_load_diag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "akugpu_model_num_states": (C.c_int, [C.c_void_p]),

@@ -352,7 +352,18 @@ int akugpu_model_read(akugpu_ctx *ctx, const char *base)
   API_BEGIN
   if (!base) throw Error(AKUGPU_E_ARG, "base is NULL");
   ctx->have_model = false;
-  model_read_files(base, ctx->hm);
+  const std::string b(base);
+  model_read_files(b + ".gk", b + ".mc", b + ".ph", ctx->hm);   // HmmSet::read_all, aku/HmmSet.cc:352-357
+  model_pack(ctx);
+  API_END
+}
+
+int akugpu_model_read_files(akugpu_ctx *ctx, const char *gk_path, const char *mc_path, const char *ph_path)
+{
+  API_BEGIN
+  if (!gk_path || !mc_path || !ph_path) throw Error(AKUGPU_E_ARG, "a model path is NULL");
+  ctx->have_model = false;
+  model_read_files(gk_path, mc_path, ph_path, ctx->hm);
   model_pack(ctx);
   API_END
 }

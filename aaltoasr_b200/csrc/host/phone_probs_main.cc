@@ -1,0 +1,179 @@
+// akugpu_phone_probs -- the reference tool aku/phone_probs.cc re-hosted on the GPU library.
+// Same flags (aku/phone_probs.cc:60-81) and the same per-utterance LNA files; utterances of a recipe
+// are batched into GPU calls.  Flags that select paths outside the accelerated scope
+// (-S speakers, -C clusters) are refused rather than ignored.
+#include <errno.h>
+#include <math.h>
+#include <stdlib.h>
+#include <sys/stat.h>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include "akugpu.hh"
+
+struct Utt { std::string audio, lna; double start_time, end_time; };
+
+static bool file_nonempty(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
+
+// Recipe::read (aku/Recipe.cc:24-147): key=value fields; keys persist across lines like the reference's map.
+static std::vector<Utt> read_recipe(const std::string &path, int batch, int bindex)
+{
+  std::ifstream in(path.c_str());
+  if (!in) throw std::string("could not open recipe ") + path;
+  std::vector<Utt> all;
+  std::map<std::string, std::string> kv;
+  std::string line;
+  while (std::getline(in, line)) {
+    size_t b = line.find_first_not_of(" \t\r");
+    if (b == std::string::npos || line[b] == '#') continue;
+    std::istringstream ss(line);
+    std::string f;
+    while (ss >> f) { size_t e = f.find('='); if (e != std::string::npos) kv[f.substr(0, e)] = f.substr(e + 1); }
+    Utt u;
+    u.audio = kv["audio"]; u.lna = kv["lna"];
+    u.start_time = kv.count("start-time") ? atof(kv["start-time"].c_str()) : 0;
+    u.end_time = kv.count("end-time") ? atof(kv["end-time"].c_str()) : 0;
+    all.push_back(u);
+  }
+  if (batch <= 1) return all;
+  if (bindex < 1 || bindex > batch) throw std::string("Invalid batch index");
+  // contiguous split (aku/Recipe.cc:63-115, no speaker clustering)
+  size_t n = all.size(), per = n / batch, rem = n % batch;
+  size_t start = (bindex - 1) * per + std::min<size_t>(bindex - 1, rem);
+  size_t cnt = per + ((size_t)(bindex - 1) < rem ? 1 : 0);
+  return std::vector<Utt>(all.begin() + start, all.begin() + start + cnt);
+}
+
+int main(int argc, char **argv)
+{
+  std::string base, gk, mc, ph, cfg, recipe, outdir;
+  int lnabytes = 2, batch = 0, bindex = 0, info = 0, device = 0, precision = AKUGPU_F32;
+  bool raw_input = false, lna_by_audio = false, no_overwrite = false, no_norm = false;
+  long max_batch_samples = 64L << 20;
+  try {
+    for (int i = 1; i < argc; i++) {
+      std::string a = argv[i], v;
+      size_t eq = a.find('=');
+      if (a.compare(0, 2, "--") == 0 && eq != std::string::npos) { v = a.substr(eq + 1); a = a.substr(0, eq); }
+      auto val = [&]() -> std::string {
+        if (!v.empty()) return v;
+        if (i + 1 >= argc) throw std::string("missing value for ") + a;
+        return argv[++i];
+      };
+      if (a == "-h" || a == "--help") {
+        printf("usage: akugpu_phone_probs [OPTION...]\n"
+               "  -b, --base=BASENAME    base filename for model files\n  -g, --gk=FILE  -m, --mc=FILE  -p, --ph=FILE\n"
+               "  -c, --config=FILE      feature configuration\n  -r, --recipe=FILE      recipe file\n"
+               "  -a, --lnabyaudio       name LNA files by the audio file\n  -o, --output-dir=DIR   base path for LNAs\n"
+               "  -R, --raw-input        raw audio input\n      --lnabytes=INT     2 (default) or 4\n"
+               "  -n, --no-overwrite     skip existing non-empty LNA files\n  -N, --no-normalization\n"
+               "  -B, --batch=INT  -I, --bindex=INT   recipe batching\n  -i, --info=INT\n"
+               "      --precision=f32|f64   throughput (default) or parity arithmetic\n      --device=INT\n");
+        return 0;
+      } else if (a == "-b" || a == "--base") base = val();
+      else if (a == "-g" || a == "--gk") gk = val();
+      else if (a == "-m" || a == "--mc") mc = val();
+      else if (a == "-p" || a == "--ph") ph = val();
+      else if (a == "-c" || a == "--config") cfg = val();
+      else if (a == "-r" || a == "--recipe") recipe = val();
+      else if (a == "-o" || a == "--output-dir") outdir = val();
+      else if (a == "-a" || a == "--lnabyaudio") lna_by_audio = true;
+      else if (a == "-R" || a == "--raw-input") raw_input = true;
+      else if (a == "--lnabytes") lnabytes = atoi(val().c_str());
+      else if (a == "-n" || a == "--no-overwrite") no_overwrite = true;
+      else if (a == "-N" || a == "--no-normalization") no_norm = true;
+      else if (a == "-B" || a == "--batch") batch = atoi(val().c_str());
+      else if (a == "-I" || a == "--bindex") bindex = atoi(val().c_str());
+      else if (a == "-i" || a == "--info") info = atoi(val().c_str());
+      else if (a == "--precision") precision = (val() == "f64") ? AKUGPU_F64 : AKUGPU_F32;
+      else if (a == "--device") device = atoi(val().c_str());
+      else if (a == "-S" || a == "--speakers" || a == "-C" || a == "--clusters" || a == "--eval-minc" || a == "--eval-ming")
+        throw std::string("option ") + a + " selects a path outside the accelerated scope (speaker adaptation / Gaussian clustering)";
+      else throw std::string("unknown option ") + a;
+    }
+    if (cfg.empty()) throw std::string("Must give --config");
+    if (recipe.empty()) throw std::string("Must give --recipe");
+    if (lnabytes != 2 && lnabytes != 4) throw std::string("Invalid number of bytes for probabilities in LNA file");   // aku/phone_probs.cc:121
+    if (!outdir.empty() && outdir[outdir.size() - 1] != '/') outdir += "/";
+
+    akugpu::Engine eng(device);
+    akugpu::FeatureGenerator gen(eng);
+    gen.load_configuration(cfg);
+    akugpu::HmmSet model(eng);
+    if (!base.empty()) model.read_all(base);
+    else if (!gk.empty() && !mc.empty() && !ph.empty()) model.read_files(gk, mc, ph);
+    else throw std::string("Must give either --base or all --gk, --mc and --ph");
+    if (gen.dim() != model.dim()) {   // aku/phone_probs.cc:125-131
+      char msg[200];
+      snprintf(msg, sizeof msg, "Feature dimension (%d) and model dimension (%d) don't agree", gen.dim(), model.dim());
+      throw std::string(msg);
+    }
+    const int S = model.num_states();
+    std::vector<Utt> utts = read_recipe(recipe, batch, bindex);
+    // output names (aku/phone_probs.cc:155-176) and --no-overwrite (:180-190)
+    std::vector<Utt> todo;
+    for (size_t k = 0; k < utts.size(); k++) {
+      Utt u = utts[k];
+      if (lna_by_audio || u.lna.empty()) {
+        std::string f = u.audio;
+        size_t sl = f.rfind('/'); if (sl != std::string::npos) f = f.substr(sl + 1);
+        size_t dot = f.rfind('.'); if (dot != std::string::npos) f = f.substr(0, dot);
+        u.lna = f + ".lna";
+      }
+      u.lna = outdir + u.lna;
+      if (no_overwrite && file_nonempty(u.lna)) continue;
+      todo.push_back(u);
+    }
+    const float fr = gen.frame_rate();
+    size_t i = 0;
+    std::vector<uint8_t> rec;
+    while (i < todo.size()) {
+      std::vector<int16_t> pcm;
+      std::vector<int64_t> uo(1, 0);
+      size_t j = i;
+      while (j < todo.size() && (j == i || (long)pcm.size() < max_batch_samples)) {
+        std::vector<int16_t> one;
+        int rate = 0;
+        akugpu::read_audio(todo[j].audio, gen.sample_rate(), raw_input, one, rate);
+        if (rate != gen.sample_rate()) {
+          char msg[256];
+          snprintf(msg, sizeof msg, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree.", rate, gen.sample_rate());
+          throw std::string(msg);
+        }
+        pcm.insert(pcm.end(), one.begin(), one.end());
+        uo.push_back((int64_t)pcm.size());
+        j++;
+      }
+      const int n = (int)(j - i);
+      std::vector<int64_t> fo(n + 1, 0);
+      akugpu::check(eng.ctx(), akugpu_features(eng.ctx(), NULL, uo.data(), n, NULL, 0, fo.data()));
+      rec.resize((size_t)fo[n] * S * lnabytes);
+      akugpu::check(eng.ctx(), akugpu_phone_probs(eng.ctx(), pcm.data(), uo.data(), n, precision, lnabytes, no_norm ? 0 : 1,
+                                                  rec.data(), fo.data(), NULL));
+      for (int k = 0; k < n; k++) {
+        const Utt &u = todo[i + k];
+        if (info > 0) printf("Processing file: %s\n", u.audio.c_str());
+        int64_t nf = fo[k + 1] - fo[k];
+        int64_t s = (int64_t)(u.start_time * fr), e = (int64_t)(u.end_time * fr);   // aku/phone_probs.cc:199-206
+        if (e == 0 || e > nf) e = nf;
+        if (s > e) s = e;
+        FILE *fp = fopen(u.lna.c_str(), "wb");
+        if (!fp) throw std::string("could not open ") + u.lna + " for writing";
+        uint8_t hdr[5];
+        akugpu_lna_header(S, lnabytes, hdr);
+        if (fwrite(hdr, 1, 5, fp) != 5 ||
+            fwrite(&rec[(size_t)(fo[k] + s) * S * lnabytes], 1, (size_t)(e - s) * S * lnabytes, fp) != (size_t)(e - s) * S * lnabytes)
+          throw std::string("Write error");
+        fclose(fp);
+      }
+      i = j;
+    }
+  } catch (std::string &str) {
+    fprintf(stderr, "exception: %s\n", str.c_str());
+    return 1;
+  } catch (std::exception &e) {
+    fprintf(stderr, "exception: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

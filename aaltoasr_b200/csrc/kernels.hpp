@@ -25,7 +25,7 @@ void launch_lna_f64(akugpu_ctx *ctx, const double *lin, int64_t ldF, int S, int6
 void launch_checksum(akugpu_ctx *ctx, const uint8_t *buf, int64_t nbytes, unsigned long long *acc);
 
 // model.cu
-void model_read_files(const std::string &base, HostModel &hm);
+void model_read_files(const std::string &gk_path, const std::string &mc_path, const std::string &ph_path, HostModel &hm);
 void model_pack(akugpu_ctx *ctx);
 
 // frontend_config.cc / frontend_kernels.cu

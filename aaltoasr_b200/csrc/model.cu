@@ -60,15 +60,15 @@ struct Tokens {
 
 }  // namespace
 
-void model_read_files(const std::string &base, HostModel &hm)
+void model_read_files(const std::string &gk_path, const std::string &mc_path, const std::string &ph_path, HostModel &hm)
 {
   // --- .mc ---
   std::vector<std::vector<int32_t>> mc_idx;
   std::vector<std::vector<double>> mc_w;
   {
-    Tokens t(base + ".mc");
+    Tokens t(mc_path);
     long n = t.integer();
-    if (n < 0) throw Error(AKUGPU_E_MODEL, "negative mixture count in " + base + ".mc");
+    if (n < 0) throw Error(AKUGPU_E_MODEL, "negative mixture count in " + mc_path);
     mc_idx.resize(n);
     mc_w.resize(n);
     for (long i = 0; i < n; i++) {
@@ -82,8 +82,8 @@ void model_read_files(const std::string &base, HostModel &hm)
   // --- .ph --- only the state -> mixture binding matters for scoring
   int n_states = 0;
   {
-    Tokens t(base + ".ph");
-    if (t.word() != "PHONE") throw Error(AKUGPU_E_MODEL, base + ".ph: first token is not PHONE");
+    Tokens t(ph_path);
+    if (t.word() != "PHONE") throw Error(AKUGPU_E_MODEL, ph_path + ": first token is not PHONE");
     long phones = t.integer();
     for (long h = 0; h < phones; h++) {
       t.integer();                 // index
@@ -102,14 +102,14 @@ void model_read_files(const std::string &base, HostModel &hm)
     }
   }
   if (n_states > (int)mc_idx.size())
-    throw Error(AKUGPU_E_MODEL, fmt("%s.ph refers to mixture %d but %s.mc has only %d", base.c_str(), n_states - 1,
-                                    base.c_str(), (int)mc_idx.size()));
+    throw Error(AKUGPU_E_MODEL, fmt("%s refers to mixture %d but %s has only %d", ph_path.c_str(), n_states - 1,
+                                    mc_path.c_str(), (int)mc_idx.size()));
   // --- .gk ---
   {
-    Tokens t(base + ".gk");
+    Tokens t(gk_path);
     long G = t.integer(), D = t.integer();
     std::string type = t.word();
-    if (G < 0 || D <= 0) throw Error(AKUGPU_E_MODEL, "bad header in " + base + ".gk");
+    if (G < 0 || D <= 0) throw Error(AKUGPU_E_MODEL, "bad header in " + gk_path);
     hm.G = (int)G; hm.D = (int)D;
     hm.mean.assign((size_t)G * D, 0.0);
     hm.cov.assign((size_t)G * D, 0.0);

@@ -101,6 +101,8 @@ int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples
  * aku/Distributions.cc:2812-2910) and the parameter side of DiagonalGaussian
  * (aku/Distributions.cc:1132-1150,1274-1288) and Mixture (:2419-2434,2068-2075). */
 int akugpu_model_read(akugpu_ctx *ctx, const char *base);   /* base.mc, base.ph, base.gk */
+/* The same with the three files named separately (phone_probs -g/-m/-p, aku/phone_probs.cc:99-105). */
+int akugpu_model_read_files(akugpu_ctx *ctx, const char *gk_path, const char *mc_path, const char *ph_path);
 /* Direct load.  State s owns components mix_offsets[s] .. mix_offsets[s+1]-1;
  * component k refers to Gaussian mix_gauss[k] with weight mix_weight[k]
  * (weights are re-normalised per state like Mixture::normalize_weights()).

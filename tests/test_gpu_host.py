@@ -1,0 +1,116 @@
+"""GPU tests of the host side above the C ABI: the Python mirrors of FeatureGenerator / HmmSet /
+phone_probs, and the C++ tool aaltoasr_b200/akugpu_phone_probs (same flags as aku/phone_probs.cc)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from aaltoasr_b200 import F32, F64, FeatureGenerator, HmmSet, PhoneProbs, formats
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "aaltoasr_b200", "akugpu_phone_probs")
+
+
+def write_case(tmp_path, g, n=3):
+    cfg = str(tmp_path / "mfcc.cfg")
+    open(cfg, "w").write(g["cfg"])
+    base = str(tmp_path / "model")
+    formats.write_model(base, **g["model"])
+    pcm = g["pcm"]
+    cuts = [pcm, pcm[:9000], pcm[4000:20000]][:n]
+    lines = []
+    for i, c in enumerate(cuts):
+        w = str(tmp_path / ("utt%d.wav" % i))
+        formats.write_wav(w, c, 16000)
+        lines.append("audio=%s lna=utt%d.lna" % (w, i))
+    rec = str(tmp_path / "recipe")
+    open(rec, "w").write("\n".join(lines) + "\n")
+    return cfg, base, rec, cuts
+
+
+def test_feature_generator_and_hmmset_mirror(engine, ref_small, tmp_path):
+    """The reference's per-frame call pattern (aku/phone_probs.cc:217-230) on the mirrors."""
+    g = ref_small
+    cfg, base, _, _ = write_case(tmp_path, g, 1)
+    gen = FeatureGenerator(engine)
+    gen.load_configuration(cfg)
+    gen.open(str(tmp_path / "utt0.wav"))
+    model = HmmSet(engine, precision=F64)
+    model.read_all(base)
+    assert gen.dim() == model.dim() == 39 and gen.frame_rate() == 125.0
+    assert gen.last_frame() == int(g["last_frame"]) and model.num_states() == g["lik"].shape[1]
+    model.set_utterance_features(g["feats"])          # score the reference's features: doubles must match
+    f = 0
+    while True:
+        fea = gen.generate(f)
+        if gen.eof():
+            break
+        assert np.abs(fea - g["feats"][f]).max() <= 1e-5
+        model.reset_cache()
+        model.precompute_likelihoods(f)
+        for s in (0, 5, model.num_states() - 1):
+            assert abs(model.state_likelihood(s) - g["lik"][f, s]) <= 4.5e-16 * g["lik"][f, s]
+        f += 1
+    assert f == g["feats"].shape[0]
+    assert np.abs(gen.generate(-3) - g["feats_ext"][-3 - int(g["ext_start"])]).max() <= 1e-5
+    # a feature vector instead of a frame index: the F=1 case of the same kernel
+    model.reset_cache()
+    model.precompute_likelihoods(g["feats"][7])
+    assert abs(model.state_likelihood(3) - g["lik"][7, 3]) <= 4.5e-16 * g["lik"][7, 3]
+
+
+@pytest.mark.parametrize("lnabytes", [2, 4])
+def test_cpp_tool_matches_python_and_reference(engine, ref_small, tmp_path, lnabytes):
+    g = ref_small
+    cfg, base, rec, cuts = write_case(tmp_path, g)
+    out_cpp, out_py = tmp_path / "cpp", tmp_path / "py"
+    out_cpp.mkdir(); out_py.mkdir()
+    r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out_cpp), "--lnabytes=%d" % lnabytes, "-i", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    pp = PhoneProbs(engine, precision=F32, lnabytes=lnabytes)
+    pp.read_configuration(cfg)
+    pp.read_models(base)
+    assert pp.run_recipe(rec, str(out_py)) == len(cuts)
+    for i in range(len(cuts)):
+        a = open(str(out_cpp / ("utt%d.lna" % i)), "rb").read()
+        b = open(str(out_py / ("utt%d.lna" % i)), "rb").read()
+        assert a == b                                     # both hosts drive the same library
+    # utterance 0 is the golden case: header identical, records within the throughput-mode bar
+    want = g["lna%d" % lnabytes]
+    got = np.frombuffer(open(str(out_cpp / "utt0.lna"), "rb").read(), dtype=np.uint8)
+    assert bytes(got[:5]) == bytes(want[:5]) and got.size == want.size
+    if lnabytes == 4:
+        x, y = got[5:].view("<f4"), want[5:].view("<f4")
+        assert (np.abs(x - y) / np.abs(y)).max() <= 1e-4
+    else:
+        d = np.abs(got[5:].view(">u2").astype(int) - want[5:].view(">u2").astype(int))
+        assert d.max() <= 1 and (d != 0).mean() <= 0.03
+    lp, S, nb = formats.read_lna(str(out_cpp / "utt0.lna"))      # decoder-side reader contract
+    assert (S, nb) == (g["lik"].shape[1], lnabytes) and lp.shape == g["lik"].shape
+
+
+def test_cpp_tool_flags(engine, ref_small, tmp_path):
+    g = ref_small
+    cfg, base, rec, cuts = write_case(tmp_path, g)
+    out = tmp_path / "o"; out.mkdir()
+    run = lambda *a: subprocess.run([TOOL] + list(a), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    # -B/-I batching: batch 2 of 2 holds only the last utterance (contiguous split, aku/Recipe.cc:63-115)
+    assert run("-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-B", "2", "-I", "2").returncode == 0
+    assert sorted(os.listdir(str(out))) == ["utt2.lna"]
+    # --no-overwrite keeps an existing file untouched; parity precision and -N work together
+    before = open(str(out / "utt2.lna"), "rb").read()
+    assert run("-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-n", "-N", "--precision=f64").returncode == 0
+    assert open(str(out / "utt2.lna"), "rb").read() == before
+    got = np.frombuffer(open(str(out / "utt0.lna"), "rb").read(), dtype=np.uint8)
+    d = np.abs(got[5:].view(">u2").astype(int) - g["lna2_nonorm"][5:].view(">u2").astype(int))
+    assert d.max() <= 1
+    # errors like the reference's
+    r = run("-c", cfg, "-r", rec)
+    assert r.returncode != 0 and b"Must give either --base or all --gk, --mc and --ph" in r.stderr
+    r = run("-b", base, "-c", cfg, "-r", rec, "--lnabytes=3")
+    assert r.returncode != 0 and b"Invalid number of bytes" in r.stderr
+    r = run("-g", base + ".gk", "-m", base + ".mc", "-p", base + ".ph", "-c", cfg, "-r", rec, "-o", str(out), "-a")
+    assert r.returncode == 0
