@@ -43,6 +43,8 @@ SYMBOLS = {
     "akugpu_model_read_files": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "akugpu_model_load_diag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "akugpu_model_load_full": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "akugpu_model_num_states": (C.c_int, [C.c_void_p]),
     "akugpu_model_dim": (C.c_int, [C.c_void_p]),
     "akugpu_model_num_gaussians": (C.c_int, [C.c_void_p]),

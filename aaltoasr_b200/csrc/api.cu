@@ -54,6 +54,12 @@ StageScope::~StageScope()
 // value is rounded to whole waves when it is at least one wave.  Always a multiple of 128.
 static int64_t pick_chunk(akugpu_ctx *ctx, int64_t F)
 {
+  if (ctx->hm.n_full > 0) {   // full-covariance path keeps a [G][chunk] double matrix: bound it to ~1 GB
+    int64_t chunk = std::max<int64_t>(128, ((int64_t)1 << 27) / std::max(1, ctx->hm.G) / 128 * 128);
+    if (ctx->chunk_frames > 0) chunk = std::min<int64_t>(chunk, (ctx->chunk_frames + 127) / 128 * 128);
+    if (chunk > F) chunk = (F + 127) / 128 * 128;
+    return chunk;
+  }
   const int64_t wave = gmm_wave_frames(ctx);
   int64_t chunk = ctx->chunk_frames <= 0 ? wave : ctx->chunk_frames;
   if (chunk >= wave) chunk = chunk / wave * wave;
@@ -80,6 +86,7 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
   if (lnabytes != 2 && lnabytes != 4) throw Error(AKUGPU_E_ARG, "lnabytes must be 2 or 4");
   if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
   if (F <= 0 || S <= 0) { if (checksum_out) *checksum_out = 0; return; }
+  if (ctx->hm.n_full > 0) precision = AKUGPU_F64;   // full-covariance pools are scored in double
   const int64_t chunk = pick_chunk(ctx, F);
   const size_t rec = (size_t)S * lnabytes;
   const bool out_dev = out && is_device_ptr(out);
@@ -98,7 +105,9 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
       { StageScope sc(ctx, 1); launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
       { StageScope sc(ctx, 2); launch_lna_f32(ctx, ctx->d_sll.as<float>(), chunk, S, nf, lnabytes, normalize, dst); }
     } else {
-      { StageScope sc(ctx, 1); launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk); }
+      { StageScope sc(ctx, 1);
+        if (ctx->hm.n_full > 0) launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
+        else launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk); }
       { StageScope sc(ctx, 2); launch_lna_f64(ctx, ctx->d_sll.as<double>(), chunk, S, nf, lnabytes, normalize, dst); }
     }
     if (checksum_out) launch_checksum(ctx, dst, nf * rec, ctx->d_chk.as<unsigned long long>());
@@ -394,6 +403,27 @@ int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim, 
   }
   hm.mean.assign(means, means + (size_t)n_gauss * dim);
   hm.cov.assign(covs, covs + (size_t)n_gauss * dim);
+  hm.full_index.clear(); hm.full_cov.clear(); hm.n_full = 0;
+  model_pack(ctx);
+  API_END
+}
+
+int akugpu_model_load_full(akugpu_ctx *ctx, int n_states, int n_gauss, int dim, const int32_t *mix_offsets,
+                           const int32_t *mix_gauss, const double *mix_weight, const double *means,
+                           const double *full_covs)
+{
+  API_BEGIN
+  if (n_states < 0 || n_gauss <= 0 || dim <= 0 || !mix_offsets || !means || !full_covs)
+    throw Error(AKUGPU_E_ARG, "bad model sizes / NULL arrays");
+  std::vector<double> zeros((size_t)n_gauss * dim, 1.0);
+  int rc = akugpu_model_load_diag(ctx, n_states, n_gauss, dim, mix_offsets, mix_gauss, mix_weight, means, zeros.data());
+  if (rc != 0) return rc;
+  HostModel &hm = ctx->hm;
+  hm.full_index.resize(n_gauss);
+  for (int g = 0; g < n_gauss; g++) hm.full_index[g] = g;
+  hm.full_cov.assign(full_covs, full_covs + (size_t)n_gauss * dim * dim);
+  hm.n_full = n_gauss;
+  ctx->have_model = false;
   model_pack(ctx);
   API_END
 }
@@ -413,15 +443,25 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   if (n_frames == 0 || S == 0) return AKUGPU_OK;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
   const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
+  const bool full = ctx->hm.n_full > 0;
   const int64_t chunk = pick_chunk(ctx, n_frames);
-  ctx->d_sll.reserve((size_t)S * chunk * esz);
+  ctx->d_sll.reserve((size_t)S * chunk * (full ? 8 : esz));
+  if (full && precision == AKUGPU_F32) ctx->d_lna[0].reserve((size_t)S * chunk * 4);
   const bool odev = is_device_ptr(out);
   uint8_t *d_out = (uint8_t *)out;
   if (!odev) { ctx->d_tmp.reserve((size_t)n_frames * S * esz); d_out = ctx->d_tmp.as<uint8_t>(); }
   for (int64_t c0 = 0; c0 < n_frames; c0 += chunk) {
     const int64_t c1 = std::min(n_frames, c0 + chunk);
     StageScope sc(ctx, 1);
-    if (precision == AKUGPU_F32) {
+    if (full) {
+      launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
+      if (precision == AKUGPU_F32) {
+        launch_lin_to_log_f32(ctx, ctx->d_sll.as<double>(), (int64_t)S * chunk, ctx->d_lna[0].as<float>());
+        launch_transpose_f32(ctx, ctx->d_lna[0].as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
+      } else {
+        launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
+      }
+    } else if (precision == AKUGPU_F32) {
       launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
       launch_transpose_f32(ctx, ctx->d_sll.as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
     } else {

@@ -78,7 +78,11 @@ struct HostModel {
   std::vector<int32_t> mix_off;     // [S+1]
   std::vector<int32_t> mix_gauss;   // [K]
   std::vector<double> mix_w;        // [K] normalised
-  std::vector<double> mean, cov;    // [G*D]
+  std::vector<double> mean, cov;    // [G*D]  (cov: diagonal; unused rows for full Gaussians)
+  // full-covariance Gaussians (aku/Distributions.cc:1467-1488): full_index[g] = row in full_cov, -1 = diagonal
+  std::vector<int32_t> full_index;  // [G] (empty = all diagonal)
+  std::vector<double> full_cov;     // [n_full * D * D] row-major, as read
+  int n_full = 0;
 };
 
 // fp32 scorer image: tiles of 8 slots x 16 components, see gmm_kernels.cu.
@@ -99,6 +103,12 @@ struct PackedF64 {
   DevBuf cst;            // double [G]   m_constant
   DevBuf mix_off, mix_gauss;  // int32
   DevBuf mix_w;          // double [K]
+  // full-covariance part (exponential form, aku/Distributions.cc:1437-1446,1530-1547)
+  int n_full = 0, L = 0;       // L = D(D+3)/2
+  DevBuf theta;                // double [L][n_full]   exponential parameters, one column per full Gaussian
+  DevBuf full_norm, full_cst;  // double [n_full]      m_exponential_normalizer, m_constant
+  DevBuf full_gauss;           // int32  [n_full]      pool index of each full Gaussian
+  DevBuf diag_gauss;           // int32  [G - n_full]  pool indices of the diagonal Gaussians
 };
 
 // ---------------------------------------------------------------------------------

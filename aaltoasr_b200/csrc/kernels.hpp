@@ -17,6 +17,11 @@ void launch_transpose_f32(akugpu_ctx *ctx, const float *in, int64_t ldF, int S, 
 void launch_transpose_f64(akugpu_ctx *ctx, const double *in, int64_t ldF, int S, int64_t F, double *out);
 void pipe_rates(akugpu_ctx *ctx, double out[8]);
 
+// gmm_full.cu
+void launch_gmm_full_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, double *lin,
+                         int64_t ldF);
+void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float *out);
+
 // lna_kernels.cu
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
                     uint8_t *out);

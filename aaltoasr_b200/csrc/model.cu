@@ -114,19 +114,27 @@ void model_read_files(const std::string &gk_path, const std::string &mc_path, co
     hm.mean.assign((size_t)G * D, 0.0);
     hm.cov.assign((size_t)G * D, 0.0);
     bool variable = (type == "variable");
-    if (!variable && type != "diagonal_cov") {
-      if (type == "full_cov") throw Error(AKUGPU_E_MODEL, "full-covariance pools are not supported by the diagonal scorer");
-      throw Error(AKUGPU_E_MODEL, "Unknown model type " + type);
-    }
+    if (!variable && type != "diagonal_cov" && type != "full_cov") throw Error(AKUGPU_E_MODEL, "Unknown model type " + type);
+    hm.full_index.assign(G, -1);
+    hm.full_cov.clear();
+    hm.n_full = 0;
     for (long g = 0; g < G; g++) {
+      bool full = (type == "full_cov");
       if (variable) {
         std::string gt = t.word();
-        if (gt != "diag")
-          throw Error(AKUGPU_E_MODEL, "Gaussian type '" + gt + "' is not supported by the diagonal scorer");
+        if (gt == "full") full = true;
+        else if (gt != "diag")    // precision_subspace / pcgmm / scgmm need USE_SUBSPACE_COV, which no build defines
+          throw Error(AKUGPU_E_MODEL, "Unknown model type\n" + gt);
       }
       for (long d = 0; d < D; d++) hm.mean[g * D + d] = t.real();
-      for (long d = 0; d < D; d++) hm.cov[g * D + d] = t.real();
+      if (full) {
+        hm.full_index[g] = hm.n_full++;
+        for (long d = 0; d < D * D; d++) hm.full_cov.push_back(t.real());
+      } else {
+        for (long d = 0; d < D; d++) hm.cov[g * D + d] = t.real();
+      }
     }
+    if (hm.n_full == 0) hm.full_index.clear();
   }
   hm.S = n_states;
   hm.mix_off.assign(1, 0);
@@ -142,6 +150,53 @@ void model_read_files(const std::string &gk_path, const std::string &mc_path, co
       hm.mix_w.push_back(mc_w[s][k] / sum);
     }
     hm.mix_off.push_back((int32_t)hm.mix_gauss.size());
+  }
+}
+
+// ---- full-covariance load-time algebra (FullCovarianceGaussian::set_covariance, aku/Distributions.cc:1560-1586)
+// Cholesky A = L L^T of a symmetric matrix; false if not positive definite (the reference's is_spd test,
+// aku/LinearAlgebra.cc:421-434, asks for all eigenvalues > 0, which is the same condition).
+static bool cholesky(const std::vector<double> &A, int n, std::vector<double> &Lw)
+{
+  Lw.assign((size_t)n * n, 0.0);
+  for (int j = 0; j < n; j++) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d -= Lw[(size_t)j * n + k] * Lw[(size_t)j * n + k];
+    if (!(d > 0)) return false;
+    d = sqrt(d);
+    Lw[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double v = A[(size_t)i * n + j];
+      for (int k = 0; k < j; k++) v -= Lw[(size_t)i * n + k] * Lw[(size_t)j * n + k];
+      Lw[(size_t)i * n + j] = v / d;
+    }
+  }
+  return true;
+}
+// LU with partial pivoting + inverse, the algorithm behind LinearAlgebra::inverse (aku/LinearAlgebra.cc:508-515).
+static void lu_inverse(const std::vector<double> &M, int n, std::vector<double> &inv)
+{
+  std::vector<double> A(M);
+  std::vector<int> piv(n);
+  for (int k = 0; k < n; k++) {
+    int p = k; double best = fabs(A[(size_t)k * n + k]);
+    for (int i = k + 1; i < n; i++) if (fabs(A[(size_t)i * n + k]) > best) { best = fabs(A[(size_t)i * n + k]); p = i; }
+    piv[k] = p;
+    if (p != k) for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
+    if (A[(size_t)k * n + k] != 0.0)
+      for (int i = k + 1; i < n; i++) {
+        A[(size_t)i * n + k] /= A[(size_t)k * n + k];
+        for (int j = k + 1; j < n; j++) A[(size_t)i * n + j] -= A[(size_t)i * n + k] * A[(size_t)k * n + j];
+      }
+  }
+  inv.assign((size_t)n * n, 0.0);
+  std::vector<double> b(n);
+  for (int c = 0; c < n; c++) {
+    for (int i = 0; i < n; i++) b[i] = (i == c) ? 1.0 : 0.0;
+    for (int k = 0; k < n; k++) if (piv[k] != k) std::swap(b[k], b[piv[k]]);
+    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) b[i] -= A[(size_t)i * n + j] * b[j];
+    for (int i = n - 1; i >= 0; i--) { for (int j = i + 1; j < n; j++) b[i] -= A[(size_t)i * n + j] * b[j]; b[i] /= A[(size_t)i * n + i]; }
+    for (int i = 0; i < n; i++) inv[(size_t)i * n + c] = b[i];
   }
 }
 
@@ -178,7 +233,54 @@ void model_pack(akugpu_ctx *ctx)
     upload(p.mix_off, hm.mix_off, ctx->stream);
     upload(p.mix_gauss, hm.mix_gauss, ctx->stream);
     upload(p.mix_w, hm.mix_w, ctx->stream);
+    // full-covariance Gaussians: exponential parameters (recompute_exponential_parameters, :1530-1547)
+    p.n_full = hm.n_full;
+    p.L = D * (D + 3) / 2;
+    if (hm.n_full > 0) {
+      const int nf = hm.n_full, L = p.L;
+      std::vector<double> theta((size_t)L * nf, 0.0), fnorm(nf, 0.0), fcst(nf, 0.0);
+      std::vector<int32_t> fg(nf), dg;
+      std::vector<double> P, chol, Pm(D);
+      for (int g = 0; g < G; g++) {
+        const int fi = hm.full_index[g];
+        if (fi < 0) { dg.push_back(g); continue; }
+        fg[fi] = g;
+        std::vector<double> cov(hm.full_cov.begin() + (size_t)fi * D * D, hm.full_cov.begin() + (size_t)(fi + 1) * D * D);
+        if (!cholesky(cov, D, chol)) continue;   // not SPD: precision = 0, constant = 0 (set_covariance :1578-1582)
+        lu_inverse(cov, D, P);
+        if (!cholesky(P, D, chol)) continue;
+        double det = 1;                           // spd_determinant (aku/LinearAlgebra.cc:26-38)
+        for (int i = 0; i < D; i++) det *= chol[(size_t)i * D + i];
+        det *= det;
+        fcst[fi] = log(sqrt(det));
+        const double *mu = &hm.mean[(size_t)g * D];
+        double dot = 0;
+        for (int i = 0; i < D; i++) {
+          double s = 0;
+          for (int j = 0; j < D; j++) s += P[(size_t)i * D + j] * mu[j];
+          Pm[i] = s;
+        }
+        for (int i = 0; i < D; i++) dot += Pm[i] * mu[i];
+        fnorm[fi] = -0.5 * dot;
+        for (int i = 0; i < D; i++) theta[(size_t)i * nf + fi] = Pm[i];
+        int pos = D;                              // map_m2v (aku/LinearAlgebra.cc:220-238): lower triangle, off-diagonals x sqrt(2)
+        for (int i = 0; i < D; i++)
+          for (int j = 0; j <= i; j++, pos++)
+            theta[(size_t)pos * nf + fi] = -0.5 * ((i == j) ? P[(size_t)i * D + j] : sqrt(2.0) * P[(size_t)i * D + j]);
+      }
+      upload(p.theta, theta, ctx->stream);
+      upload(p.full_norm, fnorm, ctx->stream);
+      upload(p.full_cst, fcst, ctx->stream);
+      upload(p.full_gauss, fg, ctx->stream);
+      upload(p.diag_gauss, dg, ctx->stream);
+    }
     ctx->have_p64 = true;
+  }
+  if (hm.n_full > 0) {   // the fp32 image covers diagonal pools only; full-covariance models score in double
+    AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->p32.n_tiles = 0;
+    ctx->have_model = true;
+    return;
   }
   // ---- fp32 image: slots of 16 components dealt into 8 warp queues (gmm_kernels.cu) ----
   PackedF32 &p = ctx->p32;

@@ -182,6 +182,17 @@ class AkuGpu:
         self._ck(self._lib.akugpu_model_load_diag(self._h, len(mo) - 1, mu.shape[0], mu.shape[1], _ptr(mo), _ptr(mg),
                                                   _ptr(mw), _ptr(mu), _ptr(cv)))
 
+    def model_load_full(self, mix_offsets, mix_gauss, mix_weight, means, full_covs):
+        mo = np.ascontiguousarray(mix_offsets, dtype=np.int32)
+        mg = np.ascontiguousarray(mix_gauss, dtype=np.int32)
+        mw = np.ascontiguousarray(mix_weight, dtype=np.float64)
+        mu = np.ascontiguousarray(means, dtype=np.float64)
+        cv = np.ascontiguousarray(full_covs, dtype=np.float64)
+        if mu.ndim != 2 or cv.shape != (mu.shape[0], mu.shape[1], mu.shape[1]):
+            raise ValueError("means must be [G x D], full_covs [G x D x D]")
+        self._ck(self._lib.akugpu_model_load_full(self._h, len(mo) - 1, mu.shape[0], mu.shape[1], _ptr(mo), _ptr(mg),
+                                                  _ptr(mw), _ptr(mu), _ptr(cv)))
+
     @property
     def num_states(self):
         return self._lib.akugpu_model_num_states(self._h)

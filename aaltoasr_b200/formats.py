@@ -44,18 +44,25 @@ def read_wav(path):
     raise ValueError("%s: no data chunk" % path)
 
 
-def write_model(base, mix_offsets, mix_gauss, mix_weight, means, covs):
+def write_model(base, mix_offsets, mix_gauss, mix_weight, means, covs=None, full_covs=None, full_mask=None):
     """Writes base.gk / base.mc / base.ph (legacy PHONE format, one single-state phone per
-    mixture so that state k <-> mixture k, as HmmSet::read_legacy_ph binds them)."""
+    mixture so that state k <-> mixture k, as HmmSet::read_legacy_ph binds them).
+    covs: [G x D] diagonal variances; full_covs: [G x D x D] for the Gaussians where full_mask is set
+    (all of them when full_mask is None and covs is None)."""
     means = np.asarray(means, dtype=np.float64)
-    covs = np.asarray(covs, dtype=np.float64)
     G, D = means.shape
+    if full_covs is not None and full_mask is None:
+        full_mask = np.ones(G, dtype=bool) if covs is None else np.zeros(G, dtype=bool)
     S = len(mix_offsets) - 1
     with open(base + ".gk", "w") as f:
         f.write("%d %d variable\n" % (G, D))
         for g in range(G):
-            f.write("diag " + " ".join(repr(float(v)) for v in means[g]) + " " +
-                    " ".join(repr(float(v)) for v in covs[g]) + "\n")
+            if full_mask is not None and full_mask[g]:
+                f.write("full " + " ".join(repr(float(v)) for v in means[g]) + " " +
+                        " ".join(repr(float(v)) for v in np.asarray(full_covs[g], dtype=np.float64).reshape(-1)) + "\n")
+            else:
+                f.write("diag " + " ".join(repr(float(v)) for v in means[g]) + " " +
+                        " ".join(repr(float(v)) for v in np.asarray(covs[g], dtype=np.float64)) + "\n")
     with open(base + ".mc", "w") as f:
         f.write("%d\n" % S)
         for s in range(S):

@@ -111,6 +111,13 @@ int akugpu_model_read_files(akugpu_ctx *ctx, const char *gk_path, const char *mc
 int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim,
                            const int32_t *mix_offsets, const int32_t *mix_gauss,
                            const double *mix_weight, const double *means, const double *covs);
+/* All-full-covariance pool (FullCovarianceGaussian, aku/Distributions.cc:1467-1488,1560-1586):
+ * full_covs is [G x D x D] row-major.  Pools mixing `diag` and `full` lines come through
+ * akugpu_model_read.  Full-covariance models are scored in double (exponential form,
+ * aku/Distributions.cc:1437-1446) whatever precision is requested. */
+int akugpu_model_load_full(akugpu_ctx *ctx, int n_states, int n_gauss, int dim,
+                           const int32_t *mix_offsets, const int32_t *mix_gauss,
+                           const double *mix_weight, const double *means, const double *full_covs);
 int akugpu_model_num_states(akugpu_ctx *ctx);   /* HmmSet::num_states()  */
 int akugpu_model_dim(akugpu_ctx *ctx);          /* HmmSet::dim()         */
 int akugpu_model_num_gaussians(akugpu_ctx *ctx);

@@ -374,19 +374,65 @@ def read_model(base):
     tok = open(base + ".gk").read().split()
     G, D, typ = int(tok[0]), int(tok[1]), tok[2]
     p = 3
-    means = np.empty((G, D)); covs = np.empty((G, D))
+    means = np.empty((G, D)); covs = np.ones((G, D))
+    full_mask = np.zeros(G, dtype=bool); full_covs = np.zeros((G, D, D))
     for g in range(G):
+        full = typ == "full_cov"
         if typ == "variable":
-            assert tok[p] == "diag", "only diagonal Gaussians are restated"
+            full = tok[p] == "full"
+            assert tok[p] in ("diag", "full")
             p += 1
         means[g] = [float(v) for v in tok[p:p + D]]; p += D
-        covs[g] = [float(v) for v in tok[p:p + D]]; p += D
+        if full:
+            full_mask[g] = True
+            full_covs[g] = np.array([float(v) for v in tok[p:p + D * D]]).reshape(D, D); p += D * D
+        else:
+            covs[g] = [float(v) for v in tok[p:p + D]]; p += D
     off = [0]; mg = []; mw = []
     for s in range(S):
         idx, w = mix[s]
         mg += idx; mw += w; off.append(len(mg))
-    return dict(mix_offsets=np.array(off, np.int32), mix_gauss=np.array(mg, np.int32),
-                mix_weight=np.array(mw, np.float64), means=means, covs=covs)
+    out = dict(mix_offsets=np.array(off, np.int32), mix_gauss=np.array(mg, np.int32),
+               mix_weight=np.array(mw, np.float64), means=means, covs=covs)
+    if full_mask.any():
+        out["full_mask"], out["full_covs"] = full_mask, full_covs
+    return out
+
+
+def full_gaussian_params(mean, cov):
+    """FullCovarianceGaussian::set_covariance (aku/Distributions.cc:1560-1586) +
+    recompute_exponential_parameters (:1530-1547) + LinearAlgebra::map_m2v (aku/LinearAlgebra.cc:220-238).
+    Returns (theta [D(D+3)/2], normalizer, constant); a non-SPD covariance gives zeros (precision = 0)."""
+    D = mean.size
+    L = D * (D + 3) // 2
+    try:
+        np.linalg.cholesky(cov)
+        P = np.linalg.inv(cov)
+        ch = np.linalg.cholesky(P)
+    except np.linalg.LinAlgError:
+        return np.zeros(L), 0.0, 0.0
+    det = np.prod(np.diag(ch)) ** 2
+    cst = math.log(math.sqrt(det))
+    Pm = P @ mean
+    theta = np.empty(L)
+    theta[:D] = Pm
+    pos = D
+    for i in range(D):
+        for j in range(i + 1):
+            theta[pos] = -0.5 * (P[i, j] if i == j else math.sqrt(2.0) * P[i, j])
+            pos += 1
+    return theta, -0.5 * float(Pm @ mean), cst
+
+
+def exponential_feature(f):
+    """PDFPool::precompute_likelihoods (aku/Distributions.cc:2664-2672): [f ; map_m2v(f f^T)]."""
+    D = f.shape[1]
+    cols = [f]
+    for i in range(D):
+        for j in range(i + 1):
+            m = f[:, i] * f[:, j]
+            cols.append((m if i == j else math.sqrt(2.0) * m)[:, None])
+    return np.concatenate(cols, axis=1)
 
 
 def gaussian_params(means, covs):
@@ -418,6 +464,7 @@ def state_likelihoods(model, feats, block=256):
         w[a:b] = w[a:b] / tot
     F, D = feats.shape
     out = np.empty((F, S))
+    full_cache = {}
     for f0 in range(0, F, block):
         x = feats[f0:f0 + block]
         ll = np.zeros((x.shape[0], mu.shape[0]))
@@ -426,6 +473,14 @@ def state_likelihoods(model, feats, block=256):
             ll += d * d * prec[None, :, i]
         ll *= -0.5
         ll += cst[None, :]
+        if "full_mask" in model:              # FullCovarianceGaussian::compute_log_likelihood_exponential (:1437-1446)
+            phi = exponential_feature(x)
+            for g in np.nonzero(model["full_mask"])[0]:
+                th, nrm, c = full_cache.setdefault(int(g), full_gaussian_params(mu[g], np.asarray(model["full_covs"][g], dtype=np.float64)))
+                dot = np.zeros(x.shape[0])
+                for l in range(th.size):      # Blas_Dot_Prod, index order
+                    dot += phi[:, l] * th[l]
+                ll[:, g] = (dot + nrm) + c
         lik = _exp(ll).astype(np.float64)   # DiagonalGaussian::compute_likelihood (:1036)
         for s in range(S):              # Mixture::compute_likelihood (:2079-2086)
             acc = np.zeros(x.shape[0])

@@ -34,6 +34,11 @@ def ref_edge():
 
 
 @pytest.fixture(scope="session")
+def ref_full():
+    return load_golden("ref_full")
+
+
+@pytest.fixture(scope="session")
 def aku_tests():
     z = np.load(os.path.join(GOLDEN, "aku_tests.npz"))
     return {k: (str(z[k]) if k.endswith("_cfg") else z[k]) for k in z.files}

@@ -12,6 +12,7 @@ Run in the dev container (needs /root/reference and oracle/_ref built by oracle/
                   outside the file), intermediate module outputs, linear state likelihoods,
                   and the LNA files written by the literal aku/phone_probs.cc (2 and 4 bytes,
                   with and without normalisation).
+  ref_full.npz    the same for a mixed diagonal / full-covariance pool (FullCovarianceGaussian, exponential form)
   ref_edge.npz    the same for a handmade edge-case model (underflow / denormal / floor regimes,
                   zero-variance dimensions, tiny weights).
 """
@@ -88,6 +89,26 @@ def edge_model(feats, seed):
                 means=np.array(means), covs=np.array(covs))
 
 
+def full_model(feats, seed):
+    """Mixed pool for BASELINE config 5 semantics: every other Gaussian has a full covariance
+    diag(U(0.5,2) var) + 0.1 A A^T (A: D x 4), SPD by construction.  (A non-SPD covariance is undefined
+    behaviour in the reference: set_covariance leaves the exponential parameters unsized and the next
+    precompute_likelihoods reads past them, so it is not part of the fixture.)"""
+    rng = np.random.default_rng(seed)
+    D, S, M = feats.shape[1], 8, 3
+    G = S * M
+    sd = feats.std(axis=0)
+    means = feats[rng.integers(0, feats.shape[0], G)] + 0.3 * sd * rng.standard_normal((G, D))
+    A = rng.standard_normal((G, D, 4)) * sd[None, :, None]
+    full = np.array([np.diag(rng.uniform(0.5, 2, D) * sd ** 2) + 0.1 * A[g] @ A[g].T for g in range(G)])
+    mask = np.zeros(G, dtype=bool)
+    mask[::2] = True
+    covs = rng.uniform(0.5, 2, (G, D)) * sd ** 2
+    return dict(mix_offsets=np.arange(0, G + 1, M, dtype=np.int32), mix_gauss=np.arange(G, dtype=np.int32),
+                mix_weight=rng.dirichlet(np.ones(M), S).reshape(-1), means=means, covs=covs, full_covs=full,
+                full_mask=mask)
+
+
 def run_case(name, pcm, model, tmp):
     wav = os.path.join(tmp, name + ".wav")
     cfg = os.path.join(tmp, name + ".cfg")
@@ -131,6 +152,7 @@ def main():
         feats, _, _ = ref.features(cfg, wav)
         run_case("ref_small", pcm, small_model(feats, 7002), tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
+        run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 
 
 if __name__ == "__main__":

@@ -158,6 +158,47 @@ def test_gmm_lna_throughput_mode_tolerance(engine, case, variant, request):
         engine.set_scorer_variant(0)
 
 
+def test_full_covariance_pool(engine, ref_full, tmp_path):
+    """FullCovarianceGaussian path (exponential form, double): mixed diag/full pool read from .gk,
+    and an all-full pool through akugpu_model_load_full."""
+    from aaltoasr_b200 import formats
+    g = ref_full
+    base = str(tmp_path / "full")
+    formats.write_model(base, **g["model"])
+    engine.model_read(base)
+    assert engine.num_states == 8 and engine.num_gaussians == 24
+    lik = engine.gmm_score(g["feats"], precision=F64)
+    assert (np.abs(lik - g["lik"]) / g["lik"]).max() <= 1e-10
+    ll32 = engine.gmm_score(g["feats"], precision=F32)
+    assert np.abs(ll32 - np.log(g["lik"])).max() <= 1e-5
+    for nb in (2, 4):
+        rec = engine.gmm_lna(g["feats"], precision=F64, lnabytes=nb)
+        want = g["lna%d" % nb][5:]
+        if nb == 4:
+            x, y = lna4(rec).reshape(-1), want.view("<f4")
+            assert (np.abs(x - y) / np.abs(y)).max() <= 1e-6
+        else:
+            d = np.abs(codes2(rec).reshape(-1) - want.view(">u2").astype(np.int64))
+            assert d.max() <= 1 and (d != 0).mean() <= 1e-3
+    # all-full pool through the direct loader vs the oracle
+    m = g["model"]
+    fm = m["full_mask"]
+    idx = np.nonzero(fm)[0]
+    sub = dict(mix_offsets=np.arange(0, len(idx) + 1, 3, dtype=np.int32), mix_gauss=np.arange(len(idx), dtype=np.int32),
+               mix_weight=np.ones(len(idx)), means=m["means"][idx], covs=m["covs"][idx], full_covs=m["full_covs"][idx],
+               full_mask=np.ones(len(idx), dtype=bool))
+    engine.model_load_full(sub["mix_offsets"], sub["mix_gauss"], sub["mix_weight"], sub["means"], sub["full_covs"])
+    got = engine.gmm_score(g["feats"][:32], precision=F64)
+    want = oracle_np.state_likelihoods(sub, g["feats"][:32])
+    assert (np.abs(got - want) / want).max() <= 1e-10
+    # end to end from PCM with the full-covariance model
+    engine.frontend_load_config_text(g["cfg"])
+    engine.model_read(base)
+    rec4, fo, _ = engine.phone_probs(g["pcm"], lnabytes=4)
+    y = g["lna4"][5:].view("<f4").reshape(rec4.shape[0], -1)
+    assert (np.abs(lna4(rec4) - y) / np.abs(y)).max() <= 1e-4
+
+
 @pytest.mark.parametrize("precision", [F32, F64])
 def test_phone_probs_end_to_end(engine, ref_small, precision):
     """PCM -> LNA through the fused batch entry point vs the files the literal phone_probs wrote."""
