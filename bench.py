@@ -270,7 +270,7 @@ def main():
     keep_out = F * rec <= 60e9
     out_d = torch.empty((F, rec), dtype=torch.uint8, device="cuda") if keep_out else None
     # e2e buffers: pinned PCM; LNA drained through one pinned buffer per sub-batch (a writer would stream it out)
-    sub = min(n_utts, 100)
+    sub = min(n_utts, 250)
     pcm_p = torch.from_numpy(pcm).pin_memory()
     out_p = torch.empty((int(fo[sub]), rec), dtype=torch.uint8).pin_memory()
 
