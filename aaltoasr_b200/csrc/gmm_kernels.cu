@@ -169,39 +169,40 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
     phase ^= 1u << b;
 
     float2 acc[2][GR];                                // [pair][component] = -(log-likelihood) of 2 frames
-#pragma unroll
-    for (int c = 0; c < GR; ++c) {
-      const float nc = cs[warp * GR + c];             // accumulators start at -c
-      acc[0][c] = make_float2(nc, nc);
-      acc[1][c] = make_float2(nc, nc);
-    }
-#pragma unroll 2
-    for (int dp = 0; dp < DP; ++dp) {
+    // One dim pair of the slot for this thread's 4 frames.  FIRST: the accumulators start at -c, which
+    // enters the first FFMA2 as a scalar-broadcast addend (no accumulator initialisation moves).
+    auto dim_pair = [&](int dp, auto first_tag) {
+      constexpr bool FIRST = decltype(first_tag)::value;
       const float4 xa = xs[dp * NPAIR + lane];        // frames 2*lane, 2*lane+1
       const float4 xb = xs[dp * NPAIR + 32 + lane];   // frames 64+2*lane, 65+2*lane
 #pragma unroll
       for (int c = 0; c < GR; ++c) {
         const float4 p = ps[dp * TC + c];             // warp-uniform address: broadcast
+        float nc = 0.f;
+        if constexpr (FIRST) nc = cs[warp * GR + c];
         if constexpr (F2) {
           // s and m enter as scalar-broadcast operands
           float2 t0 = __ffma2_rn(make_float2(xa.x, xa.y), make_float2(p.x, p.x), make_float2(p.z, p.z));
           float2 u0 = __ffma2_rn(make_float2(xb.x, xb.y), make_float2(p.x, p.x), make_float2(p.z, p.z));
           float2 t1 = __ffma2_rn(make_float2(xa.z, xa.w), make_float2(p.y, p.y), make_float2(p.w, p.w));
           float2 u1 = __ffma2_rn(make_float2(xb.z, xb.w), make_float2(p.y, p.y), make_float2(p.w, p.w));
-          acc[0][c] = __ffma2_rn(t0, t0, acc[0][c]);
-          acc[1][c] = __ffma2_rn(u0, u0, acc[1][c]);
+          acc[0][c] = __ffma2_rn(t0, t0, FIRST ? make_float2(nc, nc) : acc[0][c]);
+          acc[1][c] = __ffma2_rn(u0, u0, FIRST ? make_float2(nc, nc) : acc[1][c]);
           acc[0][c] = __ffma2_rn(t1, t1, acc[0][c]);
           acc[1][c] = __ffma2_rn(u1, u1, acc[1][c]);
         } else {
           float a0 = fmaf(xa.x, p.x, p.z), a1 = fmaf(xa.y, p.x, p.z), a2 = fmaf(xa.z, p.y, p.w), a3 = fmaf(xa.w, p.y, p.w);
           float b0 = fmaf(xb.x, p.x, p.z), b1 = fmaf(xb.y, p.x, p.z), b2 = fmaf(xb.z, p.y, p.w), b3 = fmaf(xb.w, p.y, p.w);
-          acc[0][c].x = fmaf(a0, a0, acc[0][c].x); acc[0][c].y = fmaf(a1, a1, acc[0][c].y);
-          acc[1][c].x = fmaf(b0, b0, acc[1][c].x); acc[1][c].y = fmaf(b1, b1, acc[1][c].y);
+          acc[0][c].x = fmaf(a0, a0, FIRST ? nc : acc[0][c].x); acc[0][c].y = fmaf(a1, a1, FIRST ? nc : acc[0][c].y);
+          acc[1][c].x = fmaf(b0, b0, FIRST ? nc : acc[1][c].x); acc[1][c].y = fmaf(b1, b1, FIRST ? nc : acc[1][c].y);
           acc[0][c].x = fmaf(a2, a2, acc[0][c].x); acc[0][c].y = fmaf(a3, a3, acc[0][c].y);
           acc[1][c].x = fmaf(b2, b2, acc[1][c].x); acc[1][c].y = fmaf(b3, b3, acc[1][c].y);
         }
       }
-    }
+    };
+    dim_pair(0, std::true_type());
+#pragma unroll 2
+    for (int dp = 1; dp < DP; ++dp) dim_pair(dp, std::false_type());
     const int meta = reinterpret_cast<const int *>(cs + TC)[warp];
 
     // This warp is done with the stage buffer; the last of the 8 warps re-arms it.

@@ -5,7 +5,9 @@
 
 constexpr int NPAIR = 64, TC = 128, DP = 20, GR = 16;
 
-// STAGED = 0: one endless loop over the same smem;  1: re-init accumulators from smem every 20 dp (a "stage")
+// STAGED 0: bare loop; 1: re-init + min-sink; 2: re-init + atomic + full sum; 3: full sum only (no re-init);
+// 5: atomic + min-sink (no re-init)
+// (old) STAGED = 0: one endless loop over the same smem;  1: re-init accumulators from smem every 20 dp (a "stage")
 // 2: + warp-level atomic + fence at each stage end (the re-arm protocol without TMA)
 template <int STAGED>
 __global__ void __launch_bounds__(256, 2) k(float *out, int stages, int stagger_ns)
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(256, 2) k(float *out, int stages, int stagger_
     for (int q = 0; q < slot; q++) __nanosleep(stagger_ns);
   }
   for (int t = 0; t < stages; t++) {
-    if (STAGED >= 1) {
+    if (STAGED == 1 || STAGED == 2 || STAGED == 4) {
 #pragma unroll
       for (int c = 0; c < GR; c++) { float nc = cs[warp * GR + c]; acc[0][c] = make_float2(nc, nc); acc[1][c] = make_float2(nc, nc); }
     }
@@ -48,16 +50,22 @@ __global__ void __launch_bounds__(256, 2) k(float *out, int stages, int stagger_
         acc[1][c] = __ffma2_rn(u1, u1, acc[1][c]);
       }
     }
-    if (STAGED >= 2) {
+    if (STAGED == 2 || STAGED == 5) {
       __syncwarp();
       if (lane == 0) {
         int old = atomicAdd(&done_cnt, 1);
         if (old == 7) { done_cnt = 0; __threadfence_block(); }
       }
     }
-    if (STAGED >= 1) {
+    if (STAGED == 2 || STAGED == 3) {
 #pragma unroll
       for (int c = 0; c < GR; c++) r += acc[0][c].x + acc[0][c].y + acc[1][c].x + acc[1][c].y;
+    }
+    if (STAGED == 1 || STAGED == 4 || STAGED == 5) {   // cheap sink that keeps every accumulator alive
+      float2 m = acc[0][0];
+#pragma unroll
+      for (int c = 0; c < GR; c++) { m.x = fminf(m.x, fminf(acc[0][c].x, acc[1][c].x)); m.y = fminf(m.y, fminf(acc[0][c].y, acc[1][c].y)); }
+      r += m.x + m.y;
     }
   }
   for (int c = 0; c < GR; c++) r += acc[0][c].x + acc[0][c].y + acc[1][c].x + acc[1][c].y;
@@ -89,6 +97,7 @@ void run(int sms, int stagger_ns)
 int main()
 {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
-  for (int ns : {0, 1000, 2000, 3500}) { run<0>(p.multiProcessorCount, ns); run<2>(p.multiProcessorCount, ns); }
+  int n = p.multiProcessorCount;
+  run<0>(n, 0); run<1>(n, 0); run<2>(n, 0); run<3>(n, 0); run<5>(n, 0);
   return 0;
 }
