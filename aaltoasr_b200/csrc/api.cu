@@ -54,6 +54,12 @@ StageScope::~StageScope()
 // value is rounded to whole waves when it is at least one wave.  Always a multiple of 128.
 static int64_t pick_chunk(akugpu_ctx *ctx, int64_t F)
 {
+  if (ctx->scorer_variant == 3 && ctx->ptc.ready) {   // tensor-core scorer: one CTA per SM, 128 frames each
+    const int64_t wave = gmm_tc_wave_frames(ctx);
+    int64_t chunk = ctx->chunk_frames <= 0 ? wave : std::max<int64_t>(128, (ctx->chunk_frames + 127) / 128 * 128);
+    if (chunk > F) chunk = (F + 127) / 128 * 128;
+    return chunk;
+  }
   if (ctx->hm.n_full > 0) {   // full-covariance path keeps a [G][chunk] double matrix: bound it to ~1 GB
     int64_t chunk = std::max<int64_t>(128, ((int64_t)1 << 27) / std::max(1, ctx->hm.G) / 128 * 128);
     if (ctx->chunk_frames > 0) chunk = std::min<int64_t>(chunk, (ctx->chunk_frames + 127) / 128 * 128);
@@ -86,7 +92,8 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
   if (lnabytes != 2 && lnabytes != 4) throw Error(AKUGPU_E_ARG, "lnabytes must be 2 or 4");
   if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
   if (F <= 0 || S <= 0) { if (checksum_out) *checksum_out = 0; return; }
-  if (ctx->hm.n_full > 0) precision = AKUGPU_F64;   // full-covariance pools are scored in double
+  const bool use_tc = ctx->scorer_variant == 3 && ctx->ptc.ready && precision == AKUGPU_F32;
+  if (ctx->hm.n_full > 0 && !use_tc) precision = AKUGPU_F64;   // full-covariance pools are scored in double
   const int64_t chunk = pick_chunk(ctx, F);
   const size_t rec = (size_t)S * lnabytes;
   const bool out_dev = out && is_device_ptr(out);
@@ -102,7 +109,9 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
     uint8_t *dst = out_dev ? out + c0 * rec : ctx->d_lna[b].as<uint8_t>();
     if (out_host && c >= 2) AKU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));
     if (precision == AKUGPU_F32) {
-      { StageScope sc(ctx, 1); launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
+      { StageScope sc(ctx, 1);
+        if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+        else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
       { StageScope sc(ctx, 2); launch_lna_f32(ctx, ctx->d_sll.as<float>(), chunk, S, nf, lnabytes, normalize, dst); }
     } else {
       { StageScope sc(ctx, 1);
@@ -443,7 +452,8 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   if (n_frames == 0 || S == 0) return AKUGPU_OK;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
   const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
-  const bool full = ctx->hm.n_full > 0;
+  const bool use_tc = ctx->scorer_variant == 3 && ctx->ptc.ready && precision == AKUGPU_F32;
+  const bool full = ctx->hm.n_full > 0 && !use_tc;
   const int64_t chunk = pick_chunk(ctx, n_frames);
   ctx->d_sll.reserve((size_t)S * chunk * (full ? 8 : esz));
   if (full && precision == AKUGPU_F32) ctx->d_lna[0].reserve((size_t)S * chunk * 4);
@@ -462,7 +472,8 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
         launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
       }
     } else if (precision == AKUGPU_F32) {
-      launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
       launch_transpose_f32(ctx, ctx->d_sll.as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
     } else {
       launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
@@ -526,7 +537,7 @@ int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames)
 int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant)
 {
   API_BEGIN
-  if (variant < 0 || variant > 2) throw Error(AKUGPU_E_ARG, "variant must be 0, 1 or 2");
+  if (variant < 0 || variant > 3) throw Error(AKUGPU_E_ARG, "variant must be 0..3");
   ctx->scorer_variant = variant;
   if (ctx->have_model) model_pack(ctx);
   API_END

@@ -111,6 +111,15 @@ struct PackedF64 {
   DevBuf diag_gauss;           // int32  [G - n_full]  pool indices of the diagonal Gaussians
 };
 
+// tensor-core scorer image (gmm_tc.cu): bf16x3-split expanded parameters, slot-ordered rows
+struct PackedTC {
+  bool ready = false, full = false;
+  int L = 0, Kp = 0, n_tiles = 0;
+  DevBuf B, bias, meta, center;
+  std::vector<char> clean;
+  std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;
+};
+
 // ---------------------------------------------------------------------------------
 // Front-end module graph (parsed from the reference's feature configuration).
 enum ModType { M_AUDIOFILE, M_FFT, M_MEL, M_POWER, M_MEL_POWER, M_DCT, M_DELTA, M_MERGE, M_CONCAT,
@@ -181,6 +190,7 @@ struct akugpu_ctx {
   bool have_model = false;
   akugpu::PackedF32 p32;
   akugpu::PackedF64 p64;
+  akugpu::PackedTC ptc;
   bool have_p64 = false;
 
   akugpu::Frontend fe;

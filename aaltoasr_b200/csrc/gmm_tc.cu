@@ -1,0 +1,446 @@
+// gmm_tc.cu -- tensor-core scorer (tcgen05 + TMEM + TMA) for sm_100a.  EXPERIMENTAL throughput mode
+// (akugpu_set_scorer_variant(ctx, 3)); the default fp32 path stays gmm_diag_f32.
+//
+// Every Gaussian log-likelihood of the path is an inner product of an expanded feature with an
+// expanded parameter vector plus a per-component constant:
+//   full covariance (the reference's own exponential form, aku/Distributions.cc:1437-1446, 2664-2672):
+//       ll = < [f ; vec(f f^T)] , [P mu ; -1/2 vec(P)] > + normalizer + constant        (length D(D+3)/2)
+//   diagonal (aku/Distributions.cc:1041-1062 expanded):
+//       ll = < [f^2 ; f] , [-1/2 p ; p mu] > - 1/2 sum p mu^2 + constant                 (length 2D)
+//   (a per-dimension [f^2, f, 1] layout that keeps the accumulator near the final value was tried and
+//    measured WORSE: the tensor-core accumulate error grows with the number of K steps, not with the
+//    partial-sum magnitude)
+// so a frame tile x component tile of log-likelihoods is a GEMM.  bf16 tensor cores with one pass
+// are off by orders of magnitude; here both operands are split into three
+// bf16 terms (x = x1 + x2 + x3) and the six products with i+j <= 4 are laid side by side along K:
+//       A' = [A1 A2 A3 A1 A2 A1] ,  B' = [B1 B1 B1 B2 B2 B3]      (K' = 6 K, fp32 accumulation)
+// which gives ~2^-24 relative operand error with plain kind::f16 MMAs.  Features and means are centred
+// first so that the cancellation between the quadratic and linear terms stays small.
+//
+// Kernel (one CTA = 128 frames, loops over 128-component tiles):
+//   warp 0    TMA producer: cp.async.bulk.tensor.2d of A' and B' k-blocks (128 x 64 bf16, SWIZZLE_128B)
+//             into a 4-stage ring, completion on mbarriers
+//   warp 1    MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16),
+//             accumulators in TMEM (2 x 128 columns, double buffered), tcgen05.commit frees smem stages
+//             and publishes finished accumulators
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x16 (one slot of 16 components per load, thread = frame row),
+//             add the component constants, mixture log-sum-exp in registers (carried across the slots
+//             of a big state), coalesced stores of state log-likelihoods sll[state][frame]
+#include "ctx.hpp"
+#include "kernels.hpp"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace akugpu {
+
+namespace tc {
+constexpr int BM = 128, BN = 128, BK = 64;        // tile: frames x components x k (bf16 elements)
+constexpr int STAGES = 3;                          // 3 x 32 KB: two CTAs (and their 2 x 256 TMEM columns) per SM
+constexpr int GR = 16;                             // components per slot
+constexpr int SLOTS = BN / GR;
+constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nTC_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra TC_DONE;\nbra TC_WAIT;\nTC_DONE:\n}\n" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4, LBO = 1,
+// SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, K-major both, N>>3, M>>4.
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// Expanded, centred, bf16x3-split features:  A'[frame][K'] , K' = 6*L padded to a multiple of 64.
+__global__ void tc_expand_feats(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t nf, int64_t rows,
+                                int D, int L, int Kp, int full, const double *__restrict__ center,
+                                __nv_bfloat16 *__restrict__ A)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * L) return;
+  const int64_t fr = i / L;
+  const int l = (int)(i - fr * L);
+  float v = 0.f;
+  if (fr < nf) {
+    auto x = [&](int d) -> double {
+      double t = feats_f64 ? reinterpret_cast<const double *>(feats)[(f_begin + fr) * D + d]
+                           : (double)reinterpret_cast<const float *>(feats)[(f_begin + fr) * D + d];
+      return t - center[d];
+    };
+    if (full) {
+      if (l < D) v = (float)x(l);
+      else {
+        int pos = l - D, r = 0;
+        while ((r + 1) * (r + 2) / 2 <= pos) r++;
+        const int c = pos - r * (r + 1) / 2;
+        const double m = x(r) * x(c);
+        v = (float)((r == c) ? m : sqrt(2.0) * m);
+      }
+    } else {
+      v = (l < D) ? (float)(x(l) * x(l)) : (float)x(l - D);
+    }
+  }
+  const __nv_bfloat16 a1 = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(a1);
+  const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+  __nv_bfloat16 *row = A + fr * Kp;
+  row[l] = a1; row[L + l] = a2; row[2 * L + l] = a3; row[3 * L + l] = a1; row[4 * L + l] = a2; row[5 * L + l] = a1;
+  if (l == 0) for (int k = 6 * L; k < Kp; k++) row[k] = __float2bfloat16_rn(0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int kblocks,
+              const int *__restrict__ range_begin, const float *__restrict__ bias, const int *__restrict__ meta,
+              float *__restrict__ sll, int64_t ldF)
+{
+  using namespace tc;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float sbias[2][BN];
+  __shared__ int smeta[2][SLOTS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n_begin = range_begin[blockIdx.y], n_end = range_begin[blockIdx.y + 1];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: 256 columns = two 128 x 128 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int it = 0;
+    for (int n = n_begin; n < n_end; n++) {
+      for (int kb = 0; kb < kblocks; kb++, it++) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        unsigned char *a_dst = smem + (size_t)s * STAGE_BYTES;
+        tma_load_2d(a_dst, &mapA, kb * BK, m0, &full_bar[s]);
+        tma_load_2d(a_dst + BM * BK * 2, &mapB, kb * BK, n * BN, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    int it = 0;
+    for (int n = n_begin; n < n_end; n++) {
+      const int a = (n - n_begin) & 1, use = (n - n_begin) >> 1;
+      if (use > 0) mbar_wait(&tmem_empty[a], (use - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + a * BN;
+      for (int kb = 0; kb < kblocks; kb++, it++) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES), b_addr = a_addr + BM * BK * 2;
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++)
+          umma_bf16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), (kb | k) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);          // smem stage reusable once these MMAs have read it
+      }
+      umma_commit(&tmem_full[a]);            // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = one frame row of the tile =====
+    const int q = warp - 4;                                   // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 128;                         // 0..127 among the epilogue threads
+    const int64_t frame = (int64_t)m0 + q * 32 + lane;
+    float run_a = 0.f, run_s = 0.f;
+    for (int n = n_begin; n < n_end; n++) {
+      const int a = (n - n_begin) & 1, use = (n - n_begin) >> 1;
+      // component constants and slot table of this tile -> shared, issued BEFORE waiting for the
+      // accumulator so that the global-load latency hides under the tile's MMAs
+      sbias[a][et] = __ldg(bias + (size_t)n * BN + et);
+      if (et < SLOTS) smeta[a][et] = __ldg(meta + n * SLOTS + et);
+      mbar_wait(&tmem_full[a], use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // the 4 epilogue warps only
+#pragma unroll 2
+      for (int sl = 0; sl < SLOTS; sl++) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + sl * GR;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+            "tcgen05.wait::ld.sync.aligned;\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+        const int mt = smeta[a][sl];
+        const float4 *bp = reinterpret_cast<const float4 *>(&sbias[a][sl * GR]);
+        float v[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+          const float4 b = bp[c4];
+          v[4 * c4 + 0] = __uint_as_float(r[4 * c4 + 0]) + b.x;
+          v[4 * c4 + 1] = __uint_as_float(r[4 * c4 + 1]) + b.y;
+          v[4 * c4 + 2] = __uint_as_float(r[4 * c4 + 2]) + b.z;
+          v[4 * c4 + 3] = __uint_as_float(r[4 * c4 + 3]) + b.w;
+        }
+        const bool first = (mt & 2) != 0, last = (mt & 1) != 0;
+        float mx = v[0];
+#pragma unroll
+        for (int c = 1; c < 16; c++) mx = fmaxf(mx, v[c]);
+        if (!first) mx = fmaxf(mx, run_a);
+        const float ml = mx * LOG2E;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          s0 += ex2f(fmaf(v[c], LOG2E, -ml));
+          s1 += ex2f(fmaf(v[c + 1], LOG2E, -ml));
+        }
+        float sum = s0 + s1;
+        if (!first) sum = fmaf(run_s, ex2f(fmaf(run_a, LOG2E, -ml)), sum);
+        run_a = mx;
+        run_s = sum;
+        if (last && mt >= 0) sll[(int64_t)(mt >> 2) * ldF + frame] = fmaf(lg2f(sum), LN2, mx);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[a]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static void make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols)
+{
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void *p = nullptr;
+    AKU_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw Error(AKUGPU_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = (EncodeTiledFn)p;
+  }
+  cuuint64_t dims[2] = {cols, rows};                  // innermost first
+  cuuint64_t strides[1] = {cols * 2};                 // bytes, dims 1..
+  cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(AKUGPU_E_CUDA, fmt("cuTensorMapEncodeTiled failed (%d)", (int)r));
+}
+
+static inline uint16_t bf16_bits(float v)   // round to nearest even
+{
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float v; memcpy(&v, &u, 4); return v; }
+
+// Builds B' (slot-ordered components x K'), the per-component constants and the slot table.
+void model_pack_tc(akugpu_ctx *ctx)
+{
+  const HostModel &hm = ctx->hm;
+  PackedTC &p = ctx->ptc;
+  const int S = hm.S, G = hm.G, D = hm.D;
+  p.full = hm.n_full > 0;
+  if (p.full && hm.n_full != G) throw Error(AKUGPU_E_MODEL, "the tensor-core scorer needs an all-diagonal or an all-full pool");
+  p.L = p.full ? D * (D + 3) / 2 : 2 * D;
+  p.Kp = (6 * p.L + tc::BK - 1) / tc::BK * tc::BK;
+  std::vector<double> cen(D, 0.0);
+  for (int d = 0; d < D; d++) { double s = 0; for (int g = 0; g < G; g++) s += hm.mean[(size_t)g * D + d]; cen[d] = G ? s / G : 0; }
+  // per-Gaussian expanded parameters for CENTRED features (double)
+  std::vector<double> theta((size_t)G * p.L, 0.0), gconst(G, 0.0);
+  std::vector<double> P, chol, Pm(D), mu(D);
+  for (int g = 0; g < G; g++) {
+    for (int d = 0; d < D; d++) mu[d] = hm.mean[(size_t)g * D + d] - cen[d];
+    double *th = &theta[(size_t)g * p.L];
+    if (!p.full) {
+      double c = 1, q = 0;
+      for (int d = 0; d < D; d++) {
+        const double cv = hm.cov[(size_t)g * D + d], pr = cv > 0 ? 1 / cv : 0;
+        c *= pr;
+        th[d] = -0.5 * pr;
+        th[D + d] = pr * mu[d];
+        q += pr * mu[d] * mu[d];
+      }
+      if (c > 0) c = log(sqrt(c));
+      gconst[g] = c - 0.5 * q;
+    } else {
+      std::vector<double> cov(hm.full_cov.begin() + (size_t)hm.full_index[g] * D * D,
+                              hm.full_cov.begin() + (size_t)(hm.full_index[g] + 1) * D * D);
+      if (!host_cholesky(cov, D, chol)) { gconst[g] = 0; continue; }
+      host_lu_inverse(cov, D, P);
+      if (!host_cholesky(P, D, chol)) { gconst[g] = 0; continue; }
+      double det = 1;
+      for (int i = 0; i < D; i++) det *= chol[(size_t)i * D + i];
+      det *= det;
+      double dot = 0;
+      for (int i = 0; i < D; i++) { double s = 0; for (int j = 0; j < D; j++) s += P[(size_t)i * D + j] * mu[j]; Pm[i] = s; }
+      for (int i = 0; i < D; i++) dot += Pm[i] * mu[i];
+      for (int i = 0; i < D; i++) th[i] = Pm[i];
+      int pos = D;
+      for (int i = 0; i < D; i++)
+        for (int j = 0; j <= i; j++, pos++) th[pos] = -0.5 * ((i == j) ? P[(size_t)i * D + j] : sqrt(2.0) * P[(size_t)i * D + j]);
+      gconst[g] = log(sqrt(det)) - 0.5 * dot;
+    }
+  }
+  // slots in state order; tiles of 8 slots; a tile is "clean" when it starts a new state
+  std::vector<int> slot_state, slot_k0, slot_flags;
+  for (int s = 0; s < S; s++) {
+    const int K = hm.mix_off[s + 1] - hm.mix_off[s];
+    const int ns = std::max(1, (K + tc::GR - 1) / tc::GR);
+    for (int i = 0; i < ns; i++) { slot_state.push_back(s); slot_k0.push_back(i * tc::GR); slot_flags.push_back(((i == 0) << 1) | (i == ns - 1)); }
+  }
+  const int n_slots = (int)slot_state.size();
+  p.n_tiles = (n_slots + tc::SLOTS - 1) / tc::SLOTS;
+  const size_t rows = (size_t)p.n_tiles * tc::BN;
+  std::vector<uint16_t> B(rows * p.Kp, 0);
+  std::vector<float> bias(rows, -1.0e30f);
+  std::vector<int32_t> meta((size_t)p.n_tiles * tc::SLOTS, -1);
+  p.clean.assign(p.n_tiles, 1);
+  for (int sl = 0; sl < n_slots; sl++) {
+    const int s = slot_state[sl];
+    meta[sl] = (s << 2) | slot_flags[sl];
+    if (sl % tc::SLOTS == 0 && !(slot_flags[sl] & 2)) p.clean[sl / tc::SLOTS] = 0;
+    const int K = hm.mix_off[s + 1] - hm.mix_off[s];
+    for (int j = 0; j < tc::GR && slot_k0[sl] + j < K; j++) {
+      const int k = hm.mix_off[s] + slot_k0[sl] + j, g = hm.mix_gauss[k];
+      const double w = hm.mix_w[k];
+      const size_t row = (size_t)sl * tc::GR + j;
+      bias[row] = w > 0 ? (float)(log(w) + gconst[g]) : -1.0e30f;
+      uint16_t *br = &B[row * p.Kp];
+      for (int l = 0; l < p.L; l++) {
+        const float v = (float)theta[(size_t)g * p.L + l];
+        const uint16_t b1 = bf16_bits(v);
+        const float r1 = v - bf16_val(b1);
+        const uint16_t b2 = bf16_bits(r1);
+        const uint16_t b3 = bf16_bits(r1 - bf16_val(b2));
+        br[l] = b1; br[p.L + l] = b1; br[2 * p.L + l] = b1; br[3 * p.L + l] = b2; br[4 * p.L + l] = b2; br[5 * p.L + l] = b3;
+      }
+    }
+  }
+  auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+    b.reserve(std::max<size_t>(bytes, 16));
+    AKU_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  };
+  up(p.B, B.data(), B.size() * 2);
+  up(p.bias, bias.data(), bias.size() * 4);
+  up(p.meta, meta.data(), meta.size() * 4);
+  up(p.center, cen.data(), cen.size() * 8);
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  p.ranges.clear();
+  p.ready = true;
+}
+
+static const int *tc_ranges(akugpu_ctx *ctx, int want, int &got)
+{
+  PackedTC &p = ctx->ptc;
+  auto it = p.ranges.find(want);
+  if (it == p.ranges.end()) {
+    std::vector<int> r(1, 0);
+    for (int k = 1; k < want; ++k) {
+      int target = (int)((int64_t)p.n_tiles * k / want);
+      while (target < p.n_tiles && !p.clean[target]) target++;
+      if (target > r.back() && target < p.n_tiles) r.push_back(target);
+    }
+    r.push_back(p.n_tiles);
+    auto buf = std::make_shared<DevBuf>();
+    buf->reserve(r.size() * sizeof(int));
+    AKU_CUDA(cudaMemcpyAsync(buf->p, r.data(), r.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = p.ranges.emplace(want, std::make_pair((int)r.size() - 1, buf)).first;
+  }
+  got = it->second.first;
+  return it->second.second->as<int>();
+}
+
+int64_t gmm_tc_wave_frames(akugpu_ctx *ctx) { return (int64_t)ctx->sm_count * 2 * tc::BM; }
+
+void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF)
+{
+  PackedTC &p = ctx->ptc;
+  const HostModel &hm = ctx->hm;
+  const int64_t nf = f_end - f_begin;
+  if (nf <= 0) return;
+  const int64_t rows = (nf + tc::BM - 1) / tc::BM * tc::BM;
+  ctx->d_fe[4].reserve((size_t)rows * p.Kp * 2);
+  __nv_bfloat16 *A = ctx->d_fe[4].as<__nv_bfloat16>();
+  const int64_t ne = rows * p.L;
+  tc_expand_feats<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(feats, feats_f64, f_begin, nf, rows, hm.D, p.L, p.Kp,
+                                                                       p.full ? 1 : 0, p.center.as<double>(), A);
+  CUtensorMap mapA, mapB;
+  make_map(&mapA, A, (uint64_t)rows, (uint64_t)p.Kp);
+  make_map(&mapB, p.B.p, (uint64_t)p.n_tiles * tc::BN, (uint64_t)p.Kp);
+  const int ftiles = (int)(rows / tc::BM);
+  int want = 1;
+  if (ftiles < 2 * ctx->sm_count) want = std::min(p.n_tiles, std::max(1, 2 * ctx->sm_count / ftiles));
+  int ysplit = 1;
+  const int *ranges = tc_ranges(ctx, want, ysplit);
+  const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + 1024;
+  static bool attr = false;
+  if (!attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  dim3 grid(ftiles, ysplit);
+  gmm_tc_kernel<<<grid, 256, smem, ctx->stream>>>(mapA, mapB, p.Kp / tc::BK, ranges, p.bias.as<float>(), p.meta.as<int>(), sll, ldF);
+  AKU_CUDA(cudaGetLastError());
+  ctx->launches += 2;
+}
+
+}  // namespace akugpu

@@ -156,7 +156,7 @@ void model_read_files(const std::string &gk_path, const std::string &mc_path, co
 // ---- full-covariance load-time algebra (FullCovarianceGaussian::set_covariance, aku/Distributions.cc:1560-1586)
 // Cholesky A = L L^T of a symmetric matrix; false if not positive definite (the reference's is_spd test,
 // aku/LinearAlgebra.cc:421-434, asks for all eigenvalues > 0, which is the same condition).
-static bool cholesky(const std::vector<double> &A, int n, std::vector<double> &Lw)
+bool host_cholesky(const std::vector<double> &A, int n, std::vector<double> &Lw)
 {
   Lw.assign((size_t)n * n, 0.0);
   for (int j = 0; j < n; j++) {
@@ -174,7 +174,7 @@ static bool cholesky(const std::vector<double> &A, int n, std::vector<double> &L
   return true;
 }
 // LU with partial pivoting + inverse, the algorithm behind LinearAlgebra::inverse (aku/LinearAlgebra.cc:508-515).
-static void lu_inverse(const std::vector<double> &M, int n, std::vector<double> &inv)
+void host_lu_inverse(const std::vector<double> &M, int n, std::vector<double> &inv)
 {
   std::vector<double> A(M);
   std::vector<int> piv(n);
@@ -246,9 +246,9 @@ void model_pack(akugpu_ctx *ctx)
         if (fi < 0) { dg.push_back(g); continue; }
         fg[fi] = g;
         std::vector<double> cov(hm.full_cov.begin() + (size_t)fi * D * D, hm.full_cov.begin() + (size_t)(fi + 1) * D * D);
-        if (!cholesky(cov, D, chol)) continue;   // not SPD: precision = 0, constant = 0 (set_covariance :1578-1582)
-        lu_inverse(cov, D, P);
-        if (!cholesky(P, D, chol)) continue;
+        if (!host_cholesky(cov, D, chol)) continue;   // not SPD: precision = 0, constant = 0 (set_covariance :1578-1582)
+        host_lu_inverse(cov, D, P);
+        if (!host_cholesky(P, D, chol)) continue;
         double det = 1;                           // spd_determinant (aku/LinearAlgebra.cc:26-38)
         for (int i = 0; i < D; i++) det *= chol[(size_t)i * D + i];
         det *= det;
@@ -279,6 +279,8 @@ void model_pack(akugpu_ctx *ctx)
   if (hm.n_full > 0) {   // the fp32 image covers diagonal pools only; full-covariance models score in double
     AKU_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->p32.n_tiles = 0;
+    ctx->ptc.ready = false;
+    if (ctx->scorer_variant == 3 && hm.n_full == G) model_pack_tc(ctx);
     ctx->have_model = true;
     return;
   }
@@ -345,6 +347,8 @@ void model_pack(akugpu_ctx *ctx)
   upload(p.center, cenf, ctx->stream);
   upload(p.center64, cen, ctx->stream);
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->ptc.ready = false;
+  if (ctx->scorer_variant == 3) model_pack_tc(ctx);
   ctx->have_model = true;
 }
 

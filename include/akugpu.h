@@ -155,8 +155,9 @@ int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5]);
 /* Frames scored per chunk of the pipelined batch path.  0 (default) = one full wave of the
  * scorer (SM count x resident CTAs x 64 frames = 37888 on B200). */
 int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames);
-/* Kernel variant of the fp32 scorer: 0 = auto, 1 = FFMA (8 frames x 8 comps / thread),
- * 2 = packed FFMA2 (8 frames x 4 comps x 2 dims / thread). */
+/* Kernel variant of the throughput-mode scorer: 0 = default (packed FFMA2 on the FP32 pipe),
+ * 1 = the same kernel with plain FFMA, 2 = FFMA2 (explicit), 3 = EXPERIMENTAL tensor-core scorer
+ * (tcgen05, bf16x3-split expanded form; all-diagonal or all-full pools). */
 int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant);
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
  * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2 with constant
