@@ -114,7 +114,7 @@ struct PackedF64 {
 // tensor-core scorer image (gmm_tc.cu): bf16x3-split expanded parameters, slot-ordered rows
 struct PackedTC {
   bool ready = false, full = false;
-  int L = 0, Kp = 0, n_tiles = 0;
+  int L = 0, Lm = 0, Kp = 0, n_tiles = 0;
   DevBuf B, bias, meta, center;
   std::vector<char> clean;
   std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;

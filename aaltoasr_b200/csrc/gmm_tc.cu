@@ -13,7 +13,8 @@
 // so a frame tile x component tile of log-likelihoods is a GEMM.  bf16 tensor cores with one pass
 // are off by orders of magnitude; here both operands are split into three
 // bf16 terms (x = x1 + x2 + x3) and the six products with i+j <= 4 are laid side by side along K:
-//       A' = [A1 A2 A3 A1 A2 A1] ,  B' = [B1 B1 B1 B2 B2 B3]      (K' = 6 K, fp32 accumulation)
+//       A' = [A1 | A2 A3 A1 A2 A1] ,  B' = [B1 | B1 B1 B2 B2 B3]      (K' = 6 K, fp32 accumulation;
+//       the leading block and the five corrections accumulate into separate TMEM accumulators)
 // which gives ~2^-24 relative operand error with plain kind::f16 MMAs.  Features and means are centred
 // first so that the cancellation between the quadratic and linear terms stays small.
 //
@@ -21,7 +22,7 @@
 //   warp 0    TMA producer: cp.async.bulk.tensor.2d of A' and B' k-blocks (128 x 64 bf16, SWIZZLE_128B)
 //             into a 4-stage ring, completion on mbarriers
 //   warp 1    MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16),
-//             accumulators in TMEM (2 x 128 columns, double buffered), tcgen05.commit frees smem stages
+//             accumulators in TMEM (main + correction, 2 x 128 columns), tcgen05.commit frees smem stages
 //             and publishes finished accumulators
 //   warps 4-7 epilogue: tcgen05.ld 32x32b.x16 (one slot of 16 components per load, thread = frame row),
 //             add the component constants, mixture log-sum-exp in registers (carried across the slots
@@ -90,7 +91,7 @@ __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f3
 // ------------------------------------------------------------------------------------------------
 // Expanded, centred, bf16x3-split features:  A'[frame][K'] , K' = 6*L padded to a multiple of 64.
 __global__ void tc_expand_feats(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t nf, int64_t rows,
-                                int D, int L, int Kp, int full, const double *__restrict__ center,
+                                int D, int L, int Lm, int Kp, int full, const double *__restrict__ center,
                                 __nv_bfloat16 *__restrict__ A)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,13 +123,19 @@ __global__ void tc_expand_feats(const void *__restrict__ feats, int feats_f64, i
   const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
   const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
   __nv_bfloat16 *row = A + fr * Kp;
-  row[l] = a1; row[L + l] = a2; row[2 * L + l] = a3; row[3 * L + l] = a1; row[4 * L + l] = a2; row[5 * L + l] = a1;
-  if (l == 0) for (int k = 6 * L; k < Kp; k++) row[k] = __float2bfloat16_rn(0.f);
+  // [ A1 | pad to Lm ][ A2 A3 A1 A2 A1 | pad to Kp ]   against   [ B1 ][ B1 B1 B2 B2 B3 ]
+  row[l] = a1;
+  __nv_bfloat16 *cr = row + Lm;
+  cr[l] = a2; cr[L + l] = a3; cr[2 * L + l] = a1; cr[3 * L + l] = a2; cr[4 * L + l] = a1;
+  if (l == 0) {
+    for (int k = L; k < Lm; k++) row[k] = __float2bfloat16_rn(0.f);
+    for (int k = Lm + 5 * L; k < Kp; k++) row[k] = __float2bfloat16_rn(0.f);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2)
-gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int kblocks,
+gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int kblocks, int kb_main,
               const int *__restrict__ range_begin, const float *__restrict__ bias, const int *__restrict__ meta,
               float *__restrict__ sll, int64_t ldF)
 {
@@ -146,10 +153,10 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }   // only [0] is used
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 256 columns = two 128 x 128 fp32 accumulators
+  if (warp == 1) {   // TMEM: 256 columns = main accumulator [0,128) + correction accumulator [128,256)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -175,18 +182,23 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     // ===== MMA issuer =====
     int it = 0;
     for (int n = n_begin; n < n_end; n++) {
-      const int a = (n - n_begin) & 1, use = (n - n_begin) >> 1;
+      const int a = 0, use = n - n_begin;
       if (use > 0) mbar_wait(&tmem_empty[a], (use - 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + a * BN;
       for (int kb = 0; kb < kblocks; kb++, it++) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES), b_addr = a_addr + BM * BK * 2;
+        // the leading bf16 terms (A1.B1) go to the main accumulator, the five correction products to a
+        // second one: the tensor core's accumulate error scales with the accumulator's magnitude times the
+        // number of K steps, and the corrections are 2^-8 smaller
+        const bool main_blk = kb < kb_main;
+        const uint32_t tmem_d = tmem_base + (main_blk ? 0 : BN);
+        const int kfirst = main_blk ? 0 : kb_main;
 #pragma unroll
         for (int k = 0; k < BK / 16; k++)
-          umma_bf16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), (kb | k) ? 1u : 0u);
+          umma_bf16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), ((kb - kfirst) | k) ? 1u : 0u);
         umma_commit(&empty_bar[s]);          // smem stage reusable once these MMAs have read it
       }
       umma_commit(&tmem_full[a]);            // accumulator complete
@@ -198,35 +210,42 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int64_t frame = (int64_t)m0 + q * 32 + lane;
     float run_a = 0.f, run_s = 0.f;
     for (int n = n_begin; n < n_end; n++) {
-      const int a = (n - n_begin) & 1, use = (n - n_begin) >> 1;
+      const int a = 0, use = n - n_begin;
       // component constants and slot table of this tile -> shared, issued BEFORE waiting for the
       // accumulator so that the global-load latency hides under the tile's MMAs
-      sbias[a][et] = __ldg(bias + (size_t)n * BN + et);
-      if (et < SLOTS) smeta[a][et] = __ldg(meta + n * SLOTS + et);
+      const int sb = (n - n_begin) & 1;                          // constants are double buffered by tile parity
+      sbias[sb][et] = __ldg(bias + (size_t)n * BN + et);
+      if (et < SLOTS) smeta[sb][et] = __ldg(meta + n * SLOTS + et);
       mbar_wait(&tmem_full[a], use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the 4 epilogue warps only
 #pragma unroll 2
       for (int sl = 0; sl < SLOTS; sl++) {
-        uint32_t r[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + sl * GR;
+        uint32_t r[16], rc[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + sl * GR;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-            "tcgen05.wait::ld.sync.aligned;\n"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
             : "r"(taddr)
             : "memory");
-        const int mt = smeta[a][sl];
-        const float4 *bp = reinterpret_cast<const float4 *>(&sbias[a][sl * GR]);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+            "tcgen05.wait::ld.sync.aligned;\n"
+            : "=r"(rc[0]), "=r"(rc[1]), "=r"(rc[2]), "=r"(rc[3]), "=r"(rc[4]), "=r"(rc[5]), "=r"(rc[6]), "=r"(rc[7]), "=r"(rc[8]),
+              "=r"(rc[9]), "=r"(rc[10]), "=r"(rc[11]), "=r"(rc[12]), "=r"(rc[13]), "=r"(rc[14]), "=r"(rc[15])
+            : "r"(taddr + BN)
+            : "memory");
+        const int mt = smeta[sb][sl];
+        const float4 *bp = reinterpret_cast<const float4 *>(&sbias[sb][sl * GR]);
         float v[16];
 #pragma unroll
         for (int c4 = 0; c4 < 4; c4++) {
           const float4 b = bp[c4];
-          v[4 * c4 + 0] = __uint_as_float(r[4 * c4 + 0]) + b.x;
-          v[4 * c4 + 1] = __uint_as_float(r[4 * c4 + 1]) + b.y;
-          v[4 * c4 + 2] = __uint_as_float(r[4 * c4 + 2]) + b.z;
-          v[4 * c4 + 3] = __uint_as_float(r[4 * c4 + 3]) + b.w;
+          v[4 * c4 + 0] = (__uint_as_float(r[4 * c4 + 0]) + __uint_as_float(rc[4 * c4 + 0])) + b.x;
+          v[4 * c4 + 1] = (__uint_as_float(r[4 * c4 + 1]) + __uint_as_float(rc[4 * c4 + 1])) + b.y;
+          v[4 * c4 + 2] = (__uint_as_float(r[4 * c4 + 2]) + __uint_as_float(rc[4 * c4 + 2])) + b.z;
+          v[4 * c4 + 3] = (__uint_as_float(r[4 * c4 + 3]) + __uint_as_float(rc[4 * c4 + 3])) + b.w;
         }
         const bool first = (mt & 2) != 0, last = (mt & 1) != 0;
         float mx = v[0];
@@ -303,7 +322,8 @@ void model_pack_tc(akugpu_ctx *ctx)
   p.full = hm.n_full > 0;
   if (p.full && hm.n_full != G) throw Error(AKUGPU_E_MODEL, "the tensor-core scorer needs an all-diagonal or an all-full pool");
   p.L = p.full ? D * (D + 3) / 2 : 2 * D;
-  p.Kp = (6 * p.L + tc::BK - 1) / tc::BK * tc::BK;
+  p.Lm = (p.L + tc::BK - 1) / tc::BK * tc::BK;                       // leading terms, padded to whole k-blocks
+  p.Kp = p.Lm + (5 * p.L + tc::BK - 1) / tc::BK * tc::BK;          // + the five correction products
   std::vector<double> cen(D, 0.0);
   for (int d = 0; d < D; d++) { double s = 0; for (int g = 0; g < G; g++) s += hm.mean[(size_t)g * D + d]; cen[d] = G ? s / G : 0; }
   // per-Gaussian expanded parameters for CENTRED features (double)
@@ -373,7 +393,9 @@ void model_pack_tc(akugpu_ctx *ctx)
         const float r1 = v - bf16_val(b1);
         const uint16_t b2 = bf16_bits(r1);
         const uint16_t b3 = bf16_bits(r1 - bf16_val(b2));
-        br[l] = b1; br[p.L + l] = b1; br[2 * p.L + l] = b1; br[3 * p.L + l] = b2; br[4 * p.L + l] = b2; br[5 * p.L + l] = b3;
+        br[l] = b1;
+        uint16_t *bc = br + p.Lm;
+        bc[l] = b1; bc[p.L + l] = b1; bc[2 * p.L + l] = b2; bc[3 * p.L + l] = b2; bc[4 * p.L + l] = b3;
       }
     }
   }
@@ -424,7 +446,7 @@ void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_
   ctx->d_fe[4].reserve((size_t)rows * p.Kp * 2);
   __nv_bfloat16 *A = ctx->d_fe[4].as<__nv_bfloat16>();
   const int64_t ne = rows * p.L;
-  tc_expand_feats<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(feats, feats_f64, f_begin, nf, rows, hm.D, p.L, p.Kp,
+  tc_expand_feats<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(feats, feats_f64, f_begin, nf, rows, hm.D, p.L, p.Lm, p.Kp,
                                                                        p.full ? 1 : 0, p.center.as<double>(), A);
   CUtensorMap mapA, mapB;
   make_map(&mapA, A, (uint64_t)rows, (uint64_t)p.Kp);
@@ -438,7 +460,7 @@ void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_
   static bool attr = false;
   if (!attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   dim3 grid(ftiles, ysplit);
-  gmm_tc_kernel<<<grid, 256, smem, ctx->stream>>>(mapA, mapB, p.Kp / tc::BK, ranges, p.bias.as<float>(), p.meta.as<int>(), sll, ldF);
+  gmm_tc_kernel<<<grid, 256, smem, ctx->stream>>>(mapA, mapB, p.Kp / tc::BK, p.Lm / tc::BK, ranges, p.bias.as<float>(), p.meta.as<int>(), sll, ldF);
   AKU_CUDA(cudaGetLastError());
   ctx->launches += 2;
 }

@@ -126,7 +126,37 @@ def test_gmm_lna_parity_mode_bit_exact(engine, case, request):
             assert np.array_equal(rec.reshape(-1), want[5:]), (case, nb, nonorm, (rec.reshape(-1) != want[5:]).sum())
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+def test_tensor_core_variant_tolerance(engine, ref_small, ref_full):
+    """tcgen05 scorer (variant 3): bf16x3-split expanded form, fp32 accumulation in TMEM (leading terms and
+    corrections in separate accumulators).  Diagonal pools meet the same bars as the FP32-pipe kernel
+    (test_gmm_lna_throughput_mode_tolerance runs it too); the full-covariance contraction (K' = 4928)
+    is held to 2e-4 absolute on the log-likelihoods."""
+    engine.set_scorer_variant(3)
+    try:
+        g = ref_small
+        load_model(engine, g["model"])
+        feats32 = g["feats"].astype(np.float32)
+        ll = engine.gmm_score(feats32, precision=F32).astype(np.float64)
+        assert np.abs(ll - np.log(g["lik"])).max() <= 3e-5
+        got4 = lna4(engine.gmm_lna(feats32, precision=F32, lnabytes=4))
+        want4 = lna4(g["lna4"][5:]).reshape(got4.shape)
+        rel = np.abs(got4 - want4) / np.abs(want4)
+        assert (rel <= REL_TOL).all(), rel.max()
+        d = np.abs(codes2(engine.gmm_lna(feats32, precision=F32, lnabytes=2)) - codes2(g["lna2"][5:]).reshape(got4.shape))
+        assert d.max() <= 1 and (d != 0).mean() <= 0.02, (d.max(), (d != 0).mean())
+        # all-full pool
+        m = ref_full["model"]
+        idx = np.nonzero(m["full_mask"])[0]
+        off = np.arange(0, len(idx) + 1, 3, dtype=np.int32)
+        engine.model_load_full(off, np.arange(len(idx), dtype=np.int32), np.ones(len(idx)), m["means"][idx], m["full_covs"][idx])
+        ll = engine.gmm_score(ref_full["feats"].astype(np.float32), precision=F32).astype(np.float64)
+        want = np.log(engine.gmm_score(ref_full["feats"], precision=F64))
+        assert np.abs(ll - want).max() <= 2e-4
+    finally:
+        engine.set_scorer_variant(0)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
 def test_gmm_lna_throughput_mode_tolerance(engine, case, variant, request):
     g = request.getfixturevalue(case)
