@@ -52,9 +52,9 @@ StageScope::~StageScope()
 // Frames per chunk of the scoring pipeline.  Auto (chunk_frames == 0): exactly one wave of the fp32
 // scorer (sm_count x resident CTAs x 64 frames) so that no launch ends in a partial wave; an explicit
 // value is rounded to whole waves when it is at least one wave.  Always a multiple of 128.
-static int64_t pick_chunk(akugpu_ctx *ctx, int64_t F)
+static int64_t pick_chunk(akugpu_ctx *ctx, int64_t F, bool use_tc)
 {
-  if (ctx->scorer_variant == 3 && ctx->ptc.ready) {   // tensor-core scorer: one CTA per SM, 128 frames each
+  if (use_tc) {   // tensor-core scorer
     const int64_t wave = gmm_tc_wave_frames(ctx);
     int64_t chunk = ctx->chunk_frames <= 0 ? wave : std::max<int64_t>(128, (ctx->chunk_frames + 127) / 128 * 128);
     if (chunk > F) chunk = (F + 127) / 128 * 128;
@@ -92,9 +92,9 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
   if (lnabytes != 2 && lnabytes != 4) throw Error(AKUGPU_E_ARG, "lnabytes must be 2 or 4");
   if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
   if (F <= 0 || S <= 0) { if (checksum_out) *checksum_out = 0; return; }
-  const bool use_tc = ctx->scorer_variant == 3 && ctx->ptc.ready && precision == AKUGPU_F32;
+  const bool use_tc = ctx->ptc.ready && precision == AKUGPU_F32;
   if (ctx->hm.n_full > 0 && !use_tc) precision = AKUGPU_F64;   // full-covariance pools are scored in double
-  const int64_t chunk = pick_chunk(ctx, F);
+  const int64_t chunk = pick_chunk(ctx, F, use_tc);
   const size_t rec = (size_t)S * lnabytes;
   const bool out_dev = out && is_device_ptr(out);
   const bool out_host = out && !out_dev;
@@ -452,9 +452,9 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   if (n_frames == 0 || S == 0) return AKUGPU_OK;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
   const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
-  const bool use_tc = ctx->scorer_variant == 3 && ctx->ptc.ready && precision == AKUGPU_F32;
+  const bool use_tc = ctx->ptc.ready && precision == AKUGPU_F32;
   const bool full = ctx->hm.n_full > 0 && !use_tc;
-  const int64_t chunk = pick_chunk(ctx, n_frames);
+  const int64_t chunk = pick_chunk(ctx, n_frames, use_tc);
   ctx->d_sll.reserve((size_t)S * chunk * (full ? 8 : esz));
   if (full && precision == AKUGPU_F32) ctx->d_lna[0].reserve((size_t)S * chunk * 4);
   const bool odev = is_device_ptr(out);

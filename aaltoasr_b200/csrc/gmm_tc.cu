@@ -134,7 +134,13 @@ __global__ void tc_expand_feats(const void *__restrict__ feats, int feats_f64, i
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+// ARES = true : the frame tile's whole A' row block (kblocks x 16 KB) stays resident in shared memory and only B'
+//               streams through the ring; one CTA per SM, 512 TMEM columns = two (main, correction) accumulator
+//               pairs, so the epilogue of tile n overlaps the MMAs of tile n+1.  Used when A' fits (diagonal pools).
+// ARES = false: A' and B' both stream (full-covariance pools, K' = 4928); two CTAs per SM with one accumulator
+//               pair each.
+template <bool ARES>
+__global__ void __launch_bounds__(384, ARES ? 1 : 2)
 gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int kblocks, int kb_main,
               const int *__restrict__ range_begin, const float *__restrict__ bias, const int *__restrict__ meta,
               float *__restrict__ sll, int64_t ldF)
@@ -142,8 +148,12 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   using namespace tc;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2], a_full;
   __shared__ uint32_t tmem_base_smem;
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr int TMEM_COLS = ARES ? 512 : 256;
+  unsigned char *ring = ARES ? smem + (size_t)kblocks * A_BYTES : smem;      // B' ring (ARES) or A'+B' ring
+  constexpr uint32_t RING_STAGE = ARES ? B_BYTES : STAGE_BYTES;
   __shared__ __align__(16) float sbias[2][BN];
   __shared__ int smeta[2][SLOTS];
 
@@ -153,11 +163,12 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }   // only [0] is used
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    mbar_init(&a_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 256 columns = main accumulator [0,128) + correction accumulator [128,256)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+  if (warp == 1) {   // TMEM: per accumulator pair 256 columns = main [0,128) + correction [128,256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -168,33 +179,40 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     int it = 0;
+    if (ARES) {
+      mbar_expect_tx(&a_full, (uint32_t)kblocks * A_BYTES);
+      for (int kb = 0; kb < kblocks; kb++) tma_load_2d(smem + (size_t)kb * A_BYTES, &mapA, kb * BK, m0, &a_full);
+    }
     for (int n = n_begin; n < n_end; n++) {
       for (int kb = 0; kb < kblocks; kb++, it++) {
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        unsigned char *a_dst = smem + (size_t)s * STAGE_BYTES;
-        tma_load_2d(a_dst, &mapA, kb * BK, m0, &full_bar[s]);
-        tma_load_2d(a_dst + BM * BK * 2, &mapB, kb * BK, n * BN, &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], RING_STAGE);
+        unsigned char *dst = ring + (size_t)s * RING_STAGE;
+        if (!ARES) { tma_load_2d(dst, &mapA, kb * BK, m0, &full_bar[s]); dst += A_BYTES; }
+        tma_load_2d(dst, &mapB, kb * BK, n * BN, &full_bar[s]);
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
     int it = 0;
+    if (ARES) mbar_wait(&a_full, 0);
     for (int n = n_begin; n < n_end; n++) {
-      const int a = 0, use = n - n_begin;
+      const int a = ARES ? ((n - n_begin) & 1) : 0, use = ARES ? ((n - n_begin) >> 1) : (n - n_begin);
       if (use > 0) mbar_wait(&tmem_empty[a], (use - 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int kb = 0; kb < kblocks; kb++, it++) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES), b_addr = a_addr + BM * BK * 2;
+        const uint32_t ring_addr = smem_u32(ring + (size_t)s * RING_STAGE);
+        const uint32_t a_addr = ARES ? smem_u32(smem + (size_t)kb * A_BYTES) : ring_addr;
+        const uint32_t b_addr = ARES ? ring_addr : ring_addr + A_BYTES;
         // the leading bf16 terms (A1.B1) go to the main accumulator, the five correction products to a
         // second one: the tensor core's accumulate error scales with the accumulator's magnitude times the
         // number of K steps, and the corrections are 2^-8 smaller
         const bool main_blk = kb < kb_main;
-        const uint32_t tmem_d = tmem_base + (main_blk ? 0 : BN);
+        const uint32_t tmem_d = tmem_base + a * 2 * BN + (main_blk ? 0 : BN);
         const int kfirst = main_blk ? 0 : kb_main;
 #pragma unroll
         for (int k = 0; k < BK / 16; k++)
@@ -205,24 +223,27 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread = one frame row of the tile =====
-    const int q = warp - 4;                                   // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 128;                         // 0..127 among the epilogue threads
+    // 8 epilogue warps: warp w may only touch TMEM lanes 32*(w%4)..+31, so two warps share each lane quarter
+    // and split the tile's 8 slots between them (a state's slots never straddle a half tile, see model_pack_tc)
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;                         // which 4 slots of the tile
+    const int et = threadIdx.x - 128;                         // 0..255 among the epilogue threads
     const int64_t frame = (int64_t)m0 + q * 32 + lane;
     float run_a = 0.f, run_s = 0.f;
     for (int n = n_begin; n < n_end; n++) {
-      const int a = 0, use = n - n_begin;
+      const int a = ARES ? ((n - n_begin) & 1) : 0, use = ARES ? ((n - n_begin) >> 1) : (n - n_begin);
       // component constants and slot table of this tile -> shared, issued BEFORE waiting for the
       // accumulator so that the global-load latency hides under the tile's MMAs
       const int sb = (n - n_begin) & 1;                          // constants are double buffered by tile parity
-      sbias[sb][et] = __ldg(bias + (size_t)n * BN + et);
-      if (et < SLOTS) smeta[sb][et] = __ldg(meta + n * SLOTS + et);
+      if (et < BN) sbias[sb][et] = __ldg(bias + (size_t)n * BN + et);
+      else if (et < BN + SLOTS) smeta[sb][et - BN] = __ldg(meta + n * SLOTS + et - BN);
       mbar_wait(&tmem_full[a], use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // the 4 epilogue warps only
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps only
 #pragma unroll 2
-      for (int sl = 0; sl < SLOTS; sl++) {
+      for (int sl = half * (SLOTS / 2); sl < (half + 1) * (SLOTS / 2); sl++) {
         uint32_t r[16], rc[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + sl * GR;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 2 * BN + sl * GR;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -274,7 +295,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -364,9 +385,13 @@ void model_pack_tc(akugpu_ctx *ctx)
   }
   // slots in state order; tiles of 8 slots; a tile is "clean" when it starts a new state
   std::vector<int> slot_state, slot_k0, slot_flags;
+  const int HALF = tc::SLOTS / 2;
   for (int s = 0; s < S; s++) {
     const int K = hm.mix_off[s + 1] - hm.mix_off[s];
     const int ns = std::max(1, (K + tc::GR - 1) / tc::GR);
+    if (ns > HALF) throw Error(AKUGPU_E_MODEL, fmt("the tensor-core scorer handles at most %d components per state (state %d has %d)", HALF * tc::GR, s, K));
+    // the two epilogue warps of a lane quarter each own one half tile: pad so that no state straddles one
+    while ((int)slot_state.size() % HALF + ns > HALF) { slot_state.push_back(-1); slot_k0.push_back(0); slot_flags.push_back(3); }
     for (int i = 0; i < ns; i++) { slot_state.push_back(s); slot_k0.push_back(i * tc::GR); slot_flags.push_back(((i == 0) << 1) | (i == ns - 1)); }
   }
   const int n_slots = (int)slot_state.size();
@@ -378,6 +403,7 @@ void model_pack_tc(akugpu_ctx *ctx)
   p.clean.assign(p.n_tiles, 1);
   for (int sl = 0; sl < n_slots; sl++) {
     const int s = slot_state[sl];
+    if (s < 0) continue;                                   // padding slot: meta stays -1, bias -1e30
     meta[sl] = (s << 2) | slot_flags[sl];
     if (sl % tc::SLOTS == 0 && !(slot_flags[sl] & 2)) p.clean[sl / tc::SLOTS] = 0;
     const int K = hm.mix_off[s + 1] - hm.mix_off[s];
@@ -434,7 +460,18 @@ static const int *tc_ranges(akugpu_ctx *ctx, int want, int &got)
   return it->second.second->as<int>();
 }
 
-int64_t gmm_tc_wave_frames(akugpu_ctx *ctx) { return (int64_t)ctx->sm_count * 2 * tc::BM; }
+// A' resident when its row block plus the B' ring fits the 227 KB of shared memory.
+static bool gmm_tc_a_resident(const PackedTC &p)
+{
+  // Measured on B200 (profiles/r01_tc_*): streaming both operands with two CTAs per SM (6 x 32 KB in flight)
+  // beats the resident-A variant, whose 3-deep 16 KB B' ring cannot cover the L2 latency.  Resident A stays
+  // available behind AKUGPU_TC_ARES=1 for experiments.
+  static const char *force = getenv("AKUGPU_TC_ARES");
+  if (!force) return false;
+  if (force) return atoi(force) != 0 && (size_t)(p.Kp / tc::BK) * tc::BM * tc::BK * 2 + (size_t)tc::STAGES * tc::BN * tc::BK * 2 + 2048 <= 227 * 1024;
+  return (size_t)(p.Kp / tc::BK) * tc::BM * tc::BK * 2 + (size_t)tc::STAGES * tc::BN * tc::BK * 2 + 2048 <= 227 * 1024;
+}
+int64_t gmm_tc_wave_frames(akugpu_ctx *ctx) { return (int64_t)ctx->sm_count * (gmm_tc_a_resident(ctx->ptc) ? 1 : 2) * tc::BM; }
 
 void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF)
 {
@@ -452,15 +489,27 @@ void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_
   make_map(&mapA, A, (uint64_t)rows, (uint64_t)p.Kp);
   make_map(&mapB, p.B.p, (uint64_t)p.n_tiles * tc::BN, (uint64_t)p.Kp);
   const int ftiles = (int)(rows / tc::BM);
+  const int kblocks = p.Kp / tc::BK;
+  const bool ares = gmm_tc_a_resident(p);
+  const int per_sm = ares ? 1 : 2;
   int want = 1;
-  if (ftiles < 2 * ctx->sm_count) want = std::min(p.n_tiles, std::max(1, 2 * ctx->sm_count / ftiles));
+  if (ftiles < per_sm * ctx->sm_count) want = std::min(p.n_tiles, std::max(1, per_sm * ctx->sm_count / ftiles));
   int ysplit = 1;
   const int *ranges = tc_ranges(ctx, want, ysplit);
-  const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + 1024;
-  static bool attr = false;
-  if (!attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   dim3 grid(ftiles, ysplit);
-  gmm_tc_kernel<<<grid, 256, smem, ctx->stream>>>(mapA, mapB, p.Kp / tc::BK, p.Lm / tc::BK, ranges, p.bias.as<float>(), p.meta.as<int>(), sll, ldF);
+  if (ares) {
+    const size_t smem = (size_t)kblocks * tc::BM * tc::BK * 2 + (size_t)tc::STAGES * tc::BN * tc::BK * 2 + 1024;
+    static size_t attr = 0;
+    if (smem > attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    gmm_tc_kernel<true><<<grid, 384, smem, ctx->stream>>>(mapA, mapB, kblocks, p.Lm / tc::BK, ranges, p.bias.as<float>(),
+                                                          p.meta.as<int>(), sll, ldF);
+  } else {
+    const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + 1024;
+    static bool attr = false;
+    if (!attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    gmm_tc_kernel<false><<<grid, 384, smem, ctx->stream>>>(mapA, mapB, kblocks, p.Lm / tc::BK, ranges, p.bias.as<float>(),
+                                                           p.meta.as<int>(), sll, ldF);
+  }
   AKU_CUDA(cudaGetLastError());
   ctx->launches += 2;
 }

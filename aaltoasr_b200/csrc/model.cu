@@ -207,6 +207,18 @@ static void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st)
   if (!v.empty()) AKU_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
 }
 
+// The tensor-core scorer is the default throughput kernel (variant 0 or 3) for pools that are all diagonal or all
+// full with at most 64 components per state; variants 1/2 force the FP32-pipe kernel.
+static bool tc_wanted(akugpu_ctx *ctx)
+{
+  const HostModel &hm = ctx->hm;
+  if (ctx->scorer_variant == 1 || ctx->scorer_variant == 2) return false;
+  if (hm.n_full != 0 && hm.n_full != hm.G) return false;
+  for (int s = 0; s < hm.S; s++)
+    if (hm.mix_off[s + 1] - hm.mix_off[s] > 64) return false;
+  return hm.S > 0 && hm.G > 0;
+}
+
 void model_pack(akugpu_ctx *ctx)
 {
   const HostModel &hm = ctx->hm;
@@ -280,7 +292,7 @@ void model_pack(akugpu_ctx *ctx)
     AKU_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->p32.n_tiles = 0;
     ctx->ptc.ready = false;
-    if (ctx->scorer_variant == 3 && hm.n_full == G) model_pack_tc(ctx);
+    if (tc_wanted(ctx)) model_pack_tc(ctx);
     ctx->have_model = true;
     return;
   }
@@ -348,7 +360,7 @@ void model_pack(akugpu_ctx *ctx)
   upload(p.center64, cen, ctx->stream);
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->ptc.ready = false;
-  if (ctx->scorer_variant == 3) model_pack_tc(ctx);
+  if (tc_wanted(ctx)) model_pack_tc(ctx);
   ctx->have_model = true;
 }
 

@@ -155,9 +155,11 @@ int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5]);
 /* Frames scored per chunk of the pipelined batch path.  0 (default) = one full wave of the
  * scorer (SM count x resident CTAs x 64 frames = 37888 on B200). */
 int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames);
-/* Kernel variant of the throughput-mode scorer: 0 = default (packed FFMA2 on the FP32 pipe),
- * 1 = the same kernel with plain FFMA, 2 = FFMA2 (explicit), 3 = EXPERIMENTAL tensor-core scorer
- * (tcgen05, bf16x3-split expanded form; all-diagonal or all-full pools). */
+/* Kernel variant of the throughput-mode (F32) scorer:
+ *   0 = default: the tensor-core scorer (tcgen05 + TMEM + TMA, bf16x3-split expanded form) for pools
+ *       that are all diagonal or all full covariance with <= 64 components per state, otherwise the
+ *       FP32-pipe kernel (diagonal) or the double path (mixed pools);
+ *   1 = FP32-pipe kernel with plain FFMA, 2 = FP32-pipe kernel with packed FFMA2, 3 = same as 0. */
 int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant);
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
  * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2 with constant
