@@ -109,10 +109,16 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
     uint8_t *dst = out_dev ? out + c0 * rec : ctx->d_lna[b].as<uint8_t>();
     if (out_host && c >= 2) AKU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));
     if (precision == AKUGPU_F32) {
-      { StageScope sc(ctx, 1);
-        if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
-        else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
-      { StageScope sc(ctx, 2); launch_lna_f32(ctx, ctx->d_sll.as<float>(), chunk, S, nf, lnabytes, normalize, dst); }
+      const float2 *norm = nullptr;
+      if (use_tc) {   // times its own stages; also yields the per-frame normaliser when it sweeps all states
+        ctx->d_norm.reserve((size_t)chunk * sizeof(float2));
+        if (launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, ctx->d_norm.as<float2>()))
+          norm = ctx->d_norm.as<float2>();
+      } else {
+        StageScope sc(ctx, 1);
+        launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      }
+      { StageScope sc(ctx, 2); launch_lna_f32(ctx, ctx->d_sll.as<float>(), chunk, S, nf, lnabytes, normalize, norm, dst); }
     } else {
       { StageScope sc(ctx, 1);
         if (ctx->hm.n_full > 0) launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
@@ -472,7 +478,7 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
         launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
       }
     } else if (precision == AKUGPU_F32) {
-      if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
       else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
       launch_transpose_f32(ctx, ctx->d_sll.as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
     } else {

@@ -197,7 +197,7 @@ struct akugpu_ctx {
   akugpu::StageTimer timer;
 
   // scratch
-  akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk;
+  akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk, d_norm;
   akugpu::DevBuf d_fe[8];
   std::vector<std::shared_ptr<akugpu::DevBuf>> fe_bufs;   // per-module output matrices (grow-only)
   akugpu::PinnedBuf h_in[2], h_out[2];

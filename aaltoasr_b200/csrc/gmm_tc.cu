@@ -31,6 +31,7 @@
 #include "kernels.hpp"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include "lna_common.cuh"
 #include <math.h>
 
 namespace akugpu {
@@ -143,7 +144,7 @@ template <bool ARES>
 __global__ void __launch_bounds__(384, ARES ? 1 : 2)
 gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int kblocks, int kb_main,
               const int *__restrict__ range_begin, const float *__restrict__ bias, const int *__restrict__ meta,
-              float *__restrict__ sll, int64_t ldF)
+              float *__restrict__ sll, int64_t ldF, float2 *__restrict__ norm)
 {
   using namespace tc;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -156,6 +157,8 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   constexpr uint32_t RING_STAGE = ARES ? B_BYTES : STAGE_BYTES;
   __shared__ __align__(16) float sbias[2][BN];
   __shared__ int smeta[2][SLOTS];
+  __shared__ float sM[8][32];
+  __shared__ double sR[8][32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
@@ -230,6 +233,9 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int et = threadIdx.x - 128;                         // 0..255 among the epilogue threads
     const int64_t frame = (int64_t)m0 + q * 32 + lane;
     float run_a = 0.f, run_s = 0.f;
+    // fused first pass of the LNA epilogue (aku/phone_probs.cc:227-232): running maximum of the float-cast
+    // state likelihoods of this frame and the sum of all the other terms relative to it
+    float nMx = -INFINITY, nR = 0.f;   // fp32 is enough: the sum is relative to the maximum (error ~1e-6 of lognorm)
     for (int n = n_begin; n < n_end; n++) {
       const int a = ARES ? ((n - n_begin) & 1) : 0, use = ARES ? ((n - n_begin) >> 1) : (n - n_begin);
       // component constants and slot table of this tile -> shared, issued BEFORE waiting for the
@@ -284,11 +290,37 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (!first) sum = fmaf(run_s, ex2f(fmaf(run_a, LOG2E, -ml)), sum);
         run_a = mx;
         run_s = sum;
-        if (last && mt >= 0) sll[(int64_t)(mt >> 2) * ldF + frame] = fmaf(lg2f(sum), LN2, mx);
+        if (last && mt >= 0) {
+          const float res = fmaf(lg2f(sum), LN2, mx);
+          sll[(int64_t)(mt >> 2) * ldF + frame] = res;
+          if (norm) {
+            const float Lc = log_of_float_cast(res);
+            if (Lc > nMx) {
+              nR = (nMx == -INFINITY) ? 0.f : (nR + 1.f) * ex2f((nMx - Lc) * LOG2E);
+              nMx = Lc;
+            } else {
+              nR += ex2f((Lc - nMx) * LOG2E);      // exp2(-inf) = 0 covers flushed states
+            }
+          }
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[a]);
+    }
+    if (norm) {   // the two warps of a lane quarter merge their halves; one float2 per frame
+      sM[warp - 4][lane] = nMx;
+      sR[warp - 4][lane] = (double)nR;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) {
+        const float oM = sM[q + 4][lane];
+        const double oR = sR[q + 4][lane];
+        float gM = nMx;
+        double Rt = (double)nR;
+        if (oM > nMx) { gM = oM; Rt = oR + ((nMx == -INFINITY) ? 0.0 : (1.0 + (double)nR) * exp((double)(nMx - oM))); }
+        else if (oM != -INFINITY) Rt = (double)nR + (1.0 + oR) * exp((double)(oM - nMx));
+        norm[frame] = make_float2(gM, (float)log1p(Rt));
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -473,18 +505,23 @@ static bool gmm_tc_a_resident(const PackedTC &p)
 }
 int64_t gmm_tc_wave_frames(akugpu_ctx *ctx) { return (int64_t)ctx->sm_count * (gmm_tc_a_resident(ctx->ptc) ? 1 : 2) * tc::BM; }
 
-void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF)
+bool launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF,
+                   float2 *norm)
 {
   PackedTC &p = ctx->ptc;
   const HostModel &hm = ctx->hm;
   const int64_t nf = f_end - f_begin;
-  if (nf <= 0) return;
+  if (nf <= 0) return false;
   const int64_t rows = (nf + tc::BM - 1) / tc::BM * tc::BM;
   ctx->d_fe[4].reserve((size_t)rows * p.Kp * 2);
   __nv_bfloat16 *A = ctx->d_fe[4].as<__nv_bfloat16>();
   const int64_t ne = rows * p.L;
-  tc_expand_feats<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(feats, feats_f64, f_begin, nf, rows, hm.D, p.L, p.Lm, p.Kp,
-                                                                       p.full ? 1 : 0, p.center.as<double>(), A);
+  {
+    StageScope sc(ctx, 0);   // feature expansion is accounted to the front-end stage
+    tc_expand_feats<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(feats, feats_f64, f_begin, nf, rows, hm.D, p.L, p.Lm,
+                                                                         p.Kp, p.full ? 1 : 0, p.center.as<double>(), A);
+    ctx->launches++;
+  }
   CUtensorMap mapA, mapB;
   make_map(&mapA, A, (uint64_t)rows, (uint64_t)p.Kp);
   make_map(&mapB, p.B.p, (uint64_t)p.n_tiles * tc::BN, (uint64_t)p.Kp);
@@ -497,21 +534,24 @@ void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_
   int ysplit = 1;
   const int *ranges = tc_ranges(ctx, want, ysplit);
   dim3 grid(ftiles, ysplit);
+  if (ysplit != 1) norm = nullptr;        // a frame's states are spread over several CTAs: the LNA kernel does both passes
+  StageScope sc(ctx, 1);
   if (ares) {
     const size_t smem = (size_t)kblocks * tc::BM * tc::BK * 2 + (size_t)tc::STAGES * tc::BN * tc::BK * 2 + 1024;
     static size_t attr = 0;
     if (smem > attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
     gmm_tc_kernel<true><<<grid, 384, smem, ctx->stream>>>(mapA, mapB, kblocks, p.Lm / tc::BK, ranges, p.bias.as<float>(),
-                                                          p.meta.as<int>(), sll, ldF);
+                                                          p.meta.as<int>(), sll, ldF, norm);
   } else {
     const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + 1024;
     static bool attr = false;
     if (!attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     gmm_tc_kernel<false><<<grid, 384, smem, ctx->stream>>>(mapA, mapB, kblocks, p.Lm / tc::BK, ranges, p.bias.as<float>(),
-                                                           p.meta.as<int>(), sll, ldF);
+                                                           p.meta.as<int>(), sll, ldF, norm);
   }
   AKU_CUDA(cudaGetLastError());
-  ctx->launches += 2;
+  ctx->launches++;
+  return norm != nullptr;
 }
 
 }  // namespace akugpu

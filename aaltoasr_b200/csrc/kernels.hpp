@@ -25,13 +25,16 @@ void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float 
 // gmm_tc.cu (tensor-core scorer, experimental)
 void model_pack_tc(akugpu_ctx *ctx);
 int64_t gmm_tc_wave_frames(akugpu_ctx *ctx);
-void launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF);
+// Returns true when the launch also produced the per-frame normaliser norm[frame] = {max, log1p(sum of the others)}
+// (only when one CTA sweeps every component tile of its frames).
+bool launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF,
+                   float2 *norm);
 bool host_cholesky(const std::vector<double> &A, int n, std::vector<double> &Lw);
 void host_lu_inverse(const std::vector<double> &M, int n, std::vector<double> &inv);
 
 // lna_kernels.cu
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
-                    uint8_t *out);
+                    const float2 *norm, uint8_t *out);
 void launch_lna_f64(akugpu_ctx *ctx, const double *lin, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
                     uint8_t *out);
 void launch_checksum(akugpu_ctx *ctx, const uint8_t *buf, int64_t nbytes, unsigned long long *acc);

@@ -21,23 +21,9 @@
 //          reference's sequence of operations, states summed in index order.
 #include "ctx.hpp"
 #include "kernels.hpp"
+#include "lna_common.cuh"
 
 namespace akugpu {
-
-constexpr float LN_2M150 = -103.97207708399179f;   // ln 2^-150: (float)x == 0 at or below this
-constexpr float LN_2M126 = -87.33654475055310f;    // ln 2^-126: smallest normal float
-constexpr float LN_2P149 = 103.27892990343184f;    // 149 ln 2
-constexpr float LP_FLOOR = -115.12925464970229f;   // (float) log(1e-50)
-
-// ln( (float) exp(v) ), -inf when the float is zero.
-__device__ __forceinline__ float log_of_float_cast(float v)
-{
-  if (v >= LN_2M126) return v;
-  if (v <= LN_2M150) return -INFINITY;
-  float q = rintf(expf(v + LN_2P149));
-  if (q < 1.f) return -INFINITY;
-  return logf(q) - LN_2P149;
-}
 
 template <int B>
 __device__ __forceinline__ void lna_store(uint8_t *dst, float lp);
@@ -63,7 +49,8 @@ __device__ __forceinline__ void lna_store<2>(uint8_t *dst, float lp)
 // CTA = 32 frames (lanes) x 8 warps; warp w owns states r*64 + w*8 .. +7 of every round r.
 template <int B>
 __global__ void __launch_bounds__(256)
-lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int normalize, uint8_t *__restrict__ out)
+lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int normalize, const float2 *__restrict__ norm,
+        uint8_t *__restrict__ out)
 {
   typedef typename std::conditional<B == 2, uint16_t, uint32_t>::type elem_t;
   __shared__ float sh_M[8][32];
@@ -77,7 +64,11 @@ lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int norma
 
   float Mx = -INFINITY;
   double lognorm = 0.0;
-  if (normalize) {
+  if (normalize && norm) {            // normaliser already computed by the scorer's epilogue (gmm_tc.cu)
+    const float2 nm = norm[fvalid ? f : 0];
+    Mx = nm.x;
+    lognorm = (double)nm.y;
+  } else if (normalize) {
     double R = 0.0;
     for (int sb = w * 8; sb < S; sb += 64) {
       // 8 independent loads in flight, then one rescale per batch
@@ -207,12 +198,12 @@ __global__ void checksum_kernel(const uint8_t *__restrict__ buf, int64_t nbytes,
 }
 
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
-                    uint8_t *out)
+                    const float2 *norm, uint8_t *out)
 {
   if (nf <= 0) return;
   unsigned grid = (unsigned)((nf + 31) / 32);
-  if (lnabytes == 2) lna_f32<2><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, normalize, out);
-  else lna_f32<4><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, normalize, out);
+  if (lnabytes == 2) lna_f32<2><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, normalize, norm, out);
+  else lna_f32<4><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, normalize, norm, out);
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
 }
