@@ -236,13 +236,23 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     // fused first pass of the LNA epilogue (aku/phone_probs.cc:227-232): running maximum of the float-cast
     // state likelihoods of this frame and the sum of all the other terms relative to it
     float nMx = -INFINITY, nR = 0.f;   // fp32 is enough: the sum is relative to the maximum (error ~1e-6 of lognorm)
+    // component constants / slot table are fetched one tile ahead into a register (software pipelining): the
+    // global-load latency hides behind the current tile's epilogue instead of sitting in front of it
+    auto fetch = [&](int n) -> uint32_t {
+      if (n >= n_end) return 0u;
+      if (et < BN) return __float_as_uint(__ldg(bias + (size_t)n * BN + et));
+      if (et < BN + SLOTS) return (uint32_t)__ldg(meta + n * SLOTS + et - BN);
+      return 0u;
+    };
+    uint32_t pre = fetch(n_begin);
     for (int n = n_begin; n < n_end; n++) {
       const int a = ARES ? ((n - n_begin) & 1) : 0, use = ARES ? ((n - n_begin) >> 1) : (n - n_begin);
       // component constants and slot table of this tile -> shared, issued BEFORE waiting for the
       // accumulator so that the global-load latency hides under the tile's MMAs
       const int sb = (n - n_begin) & 1;                          // constants are double buffered by tile parity
-      if (et < BN) sbias[sb][et] = __ldg(bias + (size_t)n * BN + et);
-      else if (et < BN + SLOTS) smeta[sb][et - BN] = __ldg(meta + n * SLOTS + et - BN);
+      if (et < BN) sbias[sb][et] = __uint_as_float(pre);
+      else if (et < BN + SLOTS) smeta[sb][et - BN] = (int)pre;
+      pre = fetch(n + 1);
       mbar_wait(&tmem_full[a], use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps only

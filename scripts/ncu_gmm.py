@@ -18,7 +18,7 @@ feats, fo = eng.features(pcm, uo, dtype=np.float32)
 model = synth.synth_diag_model(2999, feats[:3000].astype(np.float64), 5000, 16)
 eng.set_scorer_variant(variant)
 eng.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
-eng.set_chunk_frames(65536)
+eng.set_chunk_frames(0)
 for _ in range(3):
     eng.phone_probs(pcm, uo, lnabytes=2, discard=True)
 print("done", fo[-1], "frames")
