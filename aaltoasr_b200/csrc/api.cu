@@ -52,10 +52,10 @@ StageScope::~StageScope()
 // Frames per chunk of the scoring pipeline.  Auto (chunk_frames == 0): exactly one wave of the fp32
 // scorer (sm_count x resident CTAs x 64 frames) so that no launch ends in a partial wave; an explicit
 // value is rounded to whole waves when it is at least one wave.  Always a multiple of 128.
-static int64_t pick_chunk(akugpu_ctx *ctx, int64_t F, bool use_tc)
+static int64_t pick_chunk(akugpu_ctx *ctx, int64_t F, int use_tc)
 {
-  if (use_tc) {   // tensor-core scorer
-    const int64_t wave = gmm_tc_wave_frames(ctx);
+  if (use_tc) {   // tensor-core scorers: 1 = bf16x3 (two CTAs per SM), 2 = fp16x2 (one CTA per SM; two waves per chunk)
+    const int64_t wave = use_tc == 2 ? 2 * gmm_tc16_wave_frames(ctx) : gmm_tc_wave_frames(ctx);
     int64_t chunk = ctx->chunk_frames <= 0 ? wave : std::max<int64_t>(128, (ctx->chunk_frames + 127) / 128 * 128);
     if (chunk > F) chunk = (F + 127) / 128 * 128;
     return chunk;
@@ -85,14 +85,32 @@ static void require_frontend(akugpu_ctx *ctx)
 
 // Scores frames [0,F) of device-resident features chunk by chunk and emits LNA records.
 // out may be host (pipelined D2H on a second stream), device (written in place) or NULL.
-static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, int64_t F, int precision, int lnabytes,
-                         int normalize, uint8_t *out, uint64_t *checksum_out)
+// Which tensor-core scorer serves throughput-mode calls: 2 = fp16x2 (diagonal pools), 1 = bf16x3, 0 = none.
+static int tc_mode(akugpu_ctx *ctx, int precision)
+{
+  if (precision != AKUGPU_F32) return 0;
+  if (ctx->ptc16.ready && !ctx->tc16_suspended) return 2;
+  return ctx->ptc.ready ? 1 : 0;
+}
+
+// The fp16x2 scorer flags features outside the fp16 range of its scaled terms; such a call is redone with the
+// bf16x3 kernel (no range limit), packed on first need.
+static bool tc16_needs_redo(akugpu_ctx *ctx, int mode)
+{
+  if (mode != 2 || !gmm_tc16_overflowed(ctx)) return false;
+  if (!ctx->ptc.ready) model_pack_tc(ctx);
+  return true;
+}
+
+static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f64, int64_t F, int precision, int lnabytes,
+                              int normalize, uint8_t *out, uint64_t *checksum_out, int *mode_out)
 {
   const int S = ctx->hm.S;
   if (lnabytes != 2 && lnabytes != 4) throw Error(AKUGPU_E_ARG, "lnabytes must be 2 or 4");
   if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
   if (F <= 0 || S <= 0) { if (checksum_out) *checksum_out = 0; return; }
-  const bool use_tc = ctx->ptc.ready && precision == AKUGPU_F32;
+  const int use_tc = tc_mode(ctx, precision);
+  *mode_out = use_tc;
   if (ctx->hm.n_full > 0 && !use_tc) precision = AKUGPU_F64;   // full-covariance pools are scored in double
   const int64_t chunk = pick_chunk(ctx, F, use_tc);
   const size_t rec = (size_t)S * lnabytes;
@@ -112,8 +130,10 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
       const float2 *norm = nullptr;
       if (use_tc) {   // times its own stages; also yields the per-frame normaliser when it sweeps all states
         ctx->d_norm.reserve((size_t)chunk * sizeof(float2));
-        if (launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, ctx->d_norm.as<float2>()))
-          norm = ctx->d_norm.as<float2>();
+        const bool got = use_tc == 2
+                             ? launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, ctx->d_norm.as<float2>())
+                             : launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, ctx->d_norm.as<float2>());
+        if (got) norm = ctx->d_norm.as<float2>();
       } else {
         StageScope sc(ctx, 1);
         launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
@@ -141,6 +161,19 @@ static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, in
   }
   if (out_host) AKU_CUDA(cudaStreamSynchronize(ctx->copy_out));
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, int64_t F, int precision, int lnabytes,
+                         int normalize, uint8_t *out, uint64_t *checksum_out)
+{
+  int mode = 0;
+  score_to_lna_impl(ctx, d_feats, feats_f64, F, precision, lnabytes, normalize, out, checksum_out, &mode);
+  if (tc16_needs_redo(ctx, mode)) {
+    ctx->tc16_suspended = true;
+    try { score_to_lna_impl(ctx, d_feats, feats_f64, F, precision, lnabytes, normalize, out, checksum_out, &mode); }
+    catch (...) { ctx->tc16_suspended = false; throw; }
+    ctx->tc16_suspended = false;
+  }
 }
 
 // Makes `src` (host or device) available on the device; returns the device pointer.
@@ -458,14 +491,17 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   if (n_frames == 0 || S == 0) return AKUGPU_OK;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
   const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
-  const bool use_tc = ctx->ptc.ready && precision == AKUGPU_F32;
+  const bool odev = is_device_ptr(out);
+  uint8_t *d_out = (uint8_t *)out;
+  if (!odev) { ctx->d_tmp.reserve((size_t)n_frames * S * esz); d_out = ctx->d_tmp.as<uint8_t>(); }
+  ctx->tc16_suspended = false;
+  bool redo = false;
+  do {   // a second pass only when the fp16x2 scorer met a feature outside its range (see tc16_needs_redo)
+  const int use_tc = tc_mode(ctx, precision);
   const bool full = ctx->hm.n_full > 0 && !use_tc;
   const int64_t chunk = pick_chunk(ctx, n_frames, use_tc);
   ctx->d_sll.reserve((size_t)S * chunk * (full ? 8 : esz));
   if (full && precision == AKUGPU_F32) ctx->d_lna[0].reserve((size_t)S * chunk * 4);
-  const bool odev = is_device_ptr(out);
-  uint8_t *d_out = (uint8_t *)out;
-  if (!odev) { ctx->d_tmp.reserve((size_t)n_frames * S * esz); d_out = ctx->d_tmp.as<uint8_t>(); }
   for (int64_t c0 = 0; c0 < n_frames; c0 += chunk) {
     const int64_t c1 = std::min(n_frames, c0 + chunk);
     StageScope sc(ctx, 1);
@@ -478,7 +514,8 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
         launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
       }
     } else if (precision == AKUGPU_F32) {
-      if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
+      if (use_tc == 2) launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
+      else if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
       else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
       launch_transpose_f32(ctx, ctx->d_sll.as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
     } else {
@@ -486,6 +523,9 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
       launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
     }
   }
+  redo = !redo && tc16_needs_redo(ctx, use_tc);
+  ctx->tc16_suspended = redo;
+  } while (redo);
   if (!odev) AKU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_frames * S * esz, cudaMemcpyDeviceToHost, ctx->stream));
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));
   API_END
@@ -543,7 +583,7 @@ int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames)
 int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant)
 {
   API_BEGIN
-  if (variant < 0 || variant > 3) throw Error(AKUGPU_E_ARG, "variant must be 0..3");
+  if (variant < 0 || variant > 4) throw Error(AKUGPU_E_ARG, "variant must be 0..4");
   ctx->scorer_variant = variant;
   if (ctx->have_model) model_pack(ctx);
   API_END

@@ -120,6 +120,16 @@ struct PackedTC {
   std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;
 };
 
+// fp16x2 tensor-core scorer image (gmm_tc16.cu): diagonal pools, hi/lo-split expanded parameters with per-term
+// power-of-two scaling, the component constant folded into two extra K terms
+struct PackedTC16 {
+  bool ready = false;
+  int D = 0, L = 0, NCH = 0, KB = 0, n_tiles = 0;   // L = 2D+2 terms, NCH = K16 chunks per half, KB = 64-wide k-blocks
+  DevBuf B, meta, center, escale, flag;
+  std::vector<char> clean;
+  std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;
+};
+
 // ---------------------------------------------------------------------------------
 // Front-end module graph (parsed from the reference's feature configuration).
 enum ModType { M_AUDIOFILE, M_FFT, M_MEL, M_POWER, M_MEL_POWER, M_DCT, M_DELTA, M_MERGE, M_CONCAT,
@@ -185,12 +195,14 @@ struct akugpu_ctx {
   int sm_count = 148;
   int64_t chunk_frames = 0;   // 0 = auto: one full wave of the scorer per chunk
   int scorer_variant = 0;
+  bool tc16_suspended = false;   // set while a call is redone with the bf16x3 kernel after an fp16 range overflow
 
   akugpu::HostModel hm;
   bool have_model = false;
   akugpu::PackedF32 p32;
   akugpu::PackedF64 p64;
   akugpu::PackedTC ptc;
+  akugpu::PackedTC16 ptc16;
   bool have_p64 = false;
 
   akugpu::Frontend fe;

@@ -32,6 +32,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "lna_common.cuh"
+#include "tc_common.cuh"
 #include <math.h>
 
 namespace akugpu {
@@ -42,51 +43,11 @@ constexpr int STAGES = 3;                          // 3 x 32 KB: two CTAs (and t
 constexpr int GR = 16;                             // components per slot
 constexpr int SLOTS = BN / GR;
 constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
-constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nTC_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra TC_DONE;\nbra TC_WAIT;\nTC_DONE:\n}\n" ::"r"(
-          smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4, LBO = 1,
-// SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout type 2.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, K-major both, N>>3, M>>4.
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
+constexpr uint32_t IDESC = umma_idesc(BM, BN, true);
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
-      : "memory");
+  umma_f16(tmem_d, da, db, IDESC, accumulate);
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
@@ -347,7 +308,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static void make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols)
+void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16)
 {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -361,7 +322,7 @@ static void make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols)
   cuuint64_t strides[1] = {cols * 2};                 // bytes, dims 1..
   cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(AKUGPU_E_CUDA, fmt("cuTensorMapEncodeTiled failed (%d)", (int)r));
 }
@@ -375,6 +336,21 @@ static inline uint16_t bf16_bits(float v)   // round to nearest even
   return (uint16_t)(u >> 16);
 }
 static inline float bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float v; memcpy(&v, &u, 4); return v; }
+
+// Slots (16 component positions of one state) in state order; tiles of 8 slots.  The epilogue warps of a TMEM lane
+// quarter each own `group` consecutive slots of a tile: padding slots (state -1) keep a state from straddling a group.
+void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state, std::vector<int> &slot_k0, std::vector<int> &slot_flags)
+{
+  const int HALF = group;        // slots handled by one epilogue warp: no state straddles such a group
+  slot_state.clear(); slot_k0.clear(); slot_flags.clear();
+  for (int s = 0; s < hm.S; s++) {
+    const int K = hm.mix_off[s + 1] - hm.mix_off[s];
+    const int ns = std::max(1, (K + tc::GR - 1) / tc::GR);
+    if (ns > HALF) throw Error(AKUGPU_E_MODEL, fmt("the tensor-core scorer handles at most %d components per state (state %d has %d)", HALF * tc::GR, s, K));
+    while ((int)slot_state.size() % HALF + ns > HALF) { slot_state.push_back(-1); slot_k0.push_back(0); slot_flags.push_back(3); }
+    for (int i = 0; i < ns; i++) { slot_state.push_back(s); slot_k0.push_back(i * tc::GR); slot_flags.push_back(((i == 0) << 1) | (i == ns - 1)); }
+  }
+}
 
 // Builds B' (slot-ordered components x K'), the per-component constants and the slot table.
 void model_pack_tc(akugpu_ctx *ctx)
@@ -425,17 +401,8 @@ void model_pack_tc(akugpu_ctx *ctx)
       gconst[g] = log(sqrt(det)) - 0.5 * dot;
     }
   }
-  // slots in state order; tiles of 8 slots; a tile is "clean" when it starts a new state
   std::vector<int> slot_state, slot_k0, slot_flags;
-  const int HALF = tc::SLOTS / 2;
-  for (int s = 0; s < S; s++) {
-    const int K = hm.mix_off[s + 1] - hm.mix_off[s];
-    const int ns = std::max(1, (K + tc::GR - 1) / tc::GR);
-    if (ns > HALF) throw Error(AKUGPU_E_MODEL, fmt("the tensor-core scorer handles at most %d components per state (state %d has %d)", HALF * tc::GR, s, K));
-    // the two epilogue warps of a lane quarter each own one half tile: pad so that no state straddles one
-    while ((int)slot_state.size() % HALF + ns > HALF) { slot_state.push_back(-1); slot_k0.push_back(0); slot_flags.push_back(3); }
-    for (int i = 0; i < ns; i++) { slot_state.push_back(s); slot_k0.push_back(i * tc::GR); slot_flags.push_back(((i == 0) << 1) | (i == ns - 1)); }
-  }
+  tc_build_slots(hm, tc::SLOTS / 2, slot_state, slot_k0, slot_flags);
   const int n_slots = (int)slot_state.size();
   p.n_tiles = (n_slots + tc::SLOTS - 1) / tc::SLOTS;
   const size_t rows = (size_t)p.n_tiles * tc::BN;
@@ -480,23 +447,25 @@ void model_pack_tc(akugpu_ctx *ctx)
   p.ready = true;
 }
 
-static const int *tc_ranges(akugpu_ctx *ctx, int want, int &got)
+// Splits the component tiles into `want` contiguous ranges that start on "clean" tiles (a tile that begins a new
+// state), for launches with fewer frame tiles than SMs.  Cached per split count on the device.
+const int *tc_tile_ranges(akugpu_ctx *ctx, int n_tiles, const std::vector<char> &clean,
+                          std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> &ranges, int want, int &got)
 {
-  PackedTC &p = ctx->ptc;
-  auto it = p.ranges.find(want);
-  if (it == p.ranges.end()) {
+  auto it = ranges.find(want);
+  if (it == ranges.end()) {
     std::vector<int> r(1, 0);
     for (int k = 1; k < want; ++k) {
-      int target = (int)((int64_t)p.n_tiles * k / want);
-      while (target < p.n_tiles && !p.clean[target]) target++;
-      if (target > r.back() && target < p.n_tiles) r.push_back(target);
+      int target = (int)((int64_t)n_tiles * k / want);
+      while (target < n_tiles && !clean[target]) target++;
+      if (target > r.back() && target < n_tiles) r.push_back(target);
     }
-    r.push_back(p.n_tiles);
+    r.push_back(n_tiles);
     auto buf = std::make_shared<DevBuf>();
     buf->reserve(r.size() * sizeof(int));
     AKU_CUDA(cudaMemcpyAsync(buf->p, r.data(), r.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     AKU_CUDA(cudaStreamSynchronize(ctx->stream));
-    it = p.ranges.emplace(want, std::make_pair((int)r.size() - 1, buf)).first;
+    it = ranges.emplace(want, std::make_pair((int)r.size() - 1, buf)).first;
   }
   got = it->second.first;
   return it->second.second->as<int>();
@@ -533,8 +502,8 @@ bool launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_
     ctx->launches++;
   }
   CUtensorMap mapA, mapB;
-  make_map(&mapA, A, (uint64_t)rows, (uint64_t)p.Kp);
-  make_map(&mapB, p.B.p, (uint64_t)p.n_tiles * tc::BN, (uint64_t)p.Kp);
+  tc_make_map(&mapA, A, (uint64_t)rows, (uint64_t)p.Kp, false);
+  tc_make_map(&mapB, p.B.p, (uint64_t)p.n_tiles * tc::BN, (uint64_t)p.Kp, false);
   const int ftiles = (int)(rows / tc::BM);
   const int kblocks = p.Kp / tc::BK;
   const bool ares = gmm_tc_a_resident(p);
@@ -542,7 +511,7 @@ bool launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_
   int want = 1;
   if (ftiles < per_sm * ctx->sm_count) want = std::min(p.n_tiles, std::max(1, per_sm * ctx->sm_count / ftiles));
   int ysplit = 1;
-  const int *ranges = tc_ranges(ctx, want, ysplit);
+  const int *ranges = tc_tile_ranges(ctx, p.n_tiles, p.clean, p.ranges, want, ysplit);
   dim3 grid(ftiles, ysplit);
   if (ysplit != 1) norm = nullptr;        // a frame's states are spread over several CTAs: the LNA kernel does both passes
   StageScope sc(ctx, 1);

@@ -29,6 +29,14 @@ int64_t gmm_tc_wave_frames(akugpu_ctx *ctx);
 // (only when one CTA sweeps every component tile of its frames).
 bool launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF,
                    float2 *norm);
+// gmm_tc16.cu (fp16x2 tensor-core scorer for diagonal pools; A' built in the kernel and resident in shared memory)
+bool tc16_supported(const HostModel &hm);
+void model_pack_tc16(akugpu_ctx *ctx);
+int64_t gmm_tc16_wave_frames(akugpu_ctx *ctx);
+bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, float *sll, int64_t ldF,
+                     float2 *norm);
+// true (and clears the flag) when a launch since the last call met a feature outside the fp16 range of the scaled terms
+bool gmm_tc16_overflowed(akugpu_ctx *ctx);
 bool host_cholesky(const std::vector<double> &A, int n, std::vector<double> &Lw);
 void host_lu_inverse(const std::vector<double> &M, int n, std::vector<double> &inv);
 

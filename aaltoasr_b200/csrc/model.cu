@@ -213,6 +213,8 @@ static bool tc_wanted(akugpu_ctx *ctx)
 {
   const HostModel &hm = ctx->hm;
   if (ctx->scorer_variant == 1 || ctx->scorer_variant == 2) return false;
+  // diagonal pools go to the fp16x2 kernel (gmm_tc16.cu); the bf16x3 image is then packed only on demand
+  if (ctx->scorer_variant != 4 && tc16_supported(hm)) return false;
   if (hm.n_full != 0 && hm.n_full != hm.G) return false;
   for (int s = 0; s < hm.S; s++)
     if (hm.mix_off[s + 1] - hm.mix_off[s] > 64) return false;
@@ -292,6 +294,7 @@ void model_pack(akugpu_ctx *ctx)
     AKU_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->p32.n_tiles = 0;
     ctx->ptc.ready = false;
+    ctx->ptc16.ready = false;
     if (tc_wanted(ctx)) model_pack_tc(ctx);
     ctx->have_model = true;
     return;
@@ -360,7 +363,16 @@ void model_pack(akugpu_ctx *ctx)
   upload(p.center64, cen, ctx->stream);
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->ptc.ready = false;
+  ctx->ptc16.ready = false;
   if (tc_wanted(ctx)) model_pack_tc(ctx);
+  else if (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) model_pack_tc16(ctx);
+  // packing can decline (a component constant outside the fp16 range): fall back to the bf16x3 image
+  if (!ctx->ptc16.ready && !ctx->ptc.ready && (ctx->scorer_variant == 0 || ctx->scorer_variant == 3)) {
+    const HostModel &h = ctx->hm;
+    bool ok = h.S > 0 && h.G > 0;
+    for (int s = 0; s < h.S && ok; s++) ok = h.mix_off[s + 1] - h.mix_off[s] <= 64;
+    if (ok) model_pack_tc(ctx);
+  }
   ctx->have_model = true;
 }
 

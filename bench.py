@@ -13,7 +13,7 @@ utterances are independent, no data-path collective).
   value : frames/s with PCM already resident in HBM and LNA written to HBM (CUDA events)
   e2e   : the same through the host-buffer entry point: PCM from pinned host memory, LNA bytes
           back to pinned host memory, copies inside the timed region
-  roofline : the scorer kernel (gmm_tc_kernel, tcgen05) against the measured bf16 tensor peak
+  roofline : the scorer kernel (gmm_tc16_kernel, tcgen05) against the measured bf16 tensor peak
           (MEASURED_PEAKS.json) -- batched scoring is compute bound; the HBM view of the same
           launches is reported next to it
   cpu_baseline : the reference's own FeatureGenerator + HmmSet code (oracle/_ref, built from
@@ -329,40 +329,45 @@ def main():
         G = N_STATES * N_MIX
         hbm_peak, hbm_src = measured_peaks()
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        # Dominant kernel = gmm_tc_kernel (tcgen05): issued MMA work per launch = 2 * K' * padded components * padded frames
-        L = 2 * 39
-        Lm = -(-L // 64) * 64
-        Kp = Lm + -(-5 * L // 64) * 64                       # leading block + five bf16x3 correction products
+        # Dominant kernel = gmm_tc16_kernel (tcgen05, fp16 hi/lo split): per (frame tile, component tile) it issues
+        # 3 * NCH MMAs of M128 N128 K16 (NCH = ceil((2D+2)/16) = 5): MAIN = Ah.Bh, CORR = Ah.Bl + Al.Bh
+        D = 39
+        nch = -(-(2 * D + 2) // 16)
+        Kp = 3 * nch * 16                                      # K terms issued per (frame, component)
         comps = -(-N_STATES * (-(-N_MIX // 16) * 16) // 128) * 128
         frames_pad = -(-int(frames_per_launch) // 128) * 128
         mma_flop = 2.0 * Kp * comps * frames_pad
         achieved_tf = mma_flop / (avg_ms * 1e-3) / 1e12
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)  # kernel timed inside a long step -> sustained figure
-        useful_flop = G * 39 * 4.0 * frames_per_launch         # the reference's own count: sub, mul, mul, add per (component, dim)
-        bytes_per_frame = 39 * 4 + N_STATES * 4                # features in, state log-likelihoods out
-        param_bytes = comps * Kp * 2
+        useful_flop = G * D * 4.0 * frames_per_launch          # the reference's own count: sub, mul, mul, add per (component, dim)
+        bytes_per_frame = D * 4 + N_STATES * 4                 # features in, state log-likelihoods out
+        param_bytes = comps * (-(-2 * nch // 4) * 64) * 2      # B' = [Bh | Bl], fp16, k-blocks of 64
         alg_bytes = bytes_per_frame * frames_per_launch + param_bytes
         hbm_gbs = alg_bytes / (avg_ms * 1e-3) / 1e9
         traffic = None
-        tr = os.path.join(ROOT, "profiles", "r01_gmm_tc_ncu_full.txt")
+        tr = os.path.join(ROOT, "profiles", "r01_gmm_tc16_ncu_full.txt")
         if os.path.exists(tr):
             for ln in open(tr):
                 if "traffic (dram read+write) bytes" in ln:
                     traffic = float(ln.split(":")[1])
         rates = eng.pipe_rates()
-        roofline = {"kernel": "gmm_tc_kernel (tcgen05 kind::f16, bf16x3-split expanded form)", "bound": "tensor",
-                    "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+        # second co-limit of this kernel: one exp2 per (frame, component) on the MUFU pipe
+        mufu_rate = G * frames_per_launch / (avg_ms * 1e-3)
+        roofline = {"kernel": "gmm_tc16_kernel (tcgen05 kind::f16, fp16 hi/lo-split expanded form, A' resident in shared memory)",
+                    "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                     "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md sustained)",
                     "launches": int(gmm_launches), "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch,
                     "share_of_step": gmm_ms / (ms_res if ms_res > 0 else 1),
                     "issued_mma_flop_per_launch": mma_flop, "useful_flop_per_launch": useful_flop,
-                    "note": "K' = %d per component for 78 useful terms (6 bf16 split products, k-block padding)" % Kp,
+                    "note": "K' = %d issued per component for %d useful terms (3 fp16 split products); co-limit MUFU: "
+                            "%.2e exp2/s of %.2e measured pipe rate" % (Kp, 2 * D, mufu_rate, rates["ex2"]),
+                    "mufu_view": {"achieved": mufu_rate, "peak": rates["ex2"], "unit": "exp2/s", "frac": mufu_rate / rates["ex2"]},
                     "hbm_view": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,
                                  "algorithmic_bytes_per_launch": alg_bytes},
                     "fp32_pipe_peak_tflops": 2.0 * rates["tile_ffma2"] / 1e12,
-                    "stage_ms": {"frontend+expand": st["frontend"][0], "gmm": gmm_ms, "lna": st["lna"][0]}}
+                    "stage_ms": {"frontend": st["frontend"][0], "gmm": gmm_ms, "lna": st["lna"][0]}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -383,7 +388,7 @@ def main():
         line = {
             "metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2->f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if (n_utts == N_UTTS or args.config == 4) else WORKLOAD.replace("1000 utterances", "%d utterances" % n_utts),
                        "utterances_per_gpu": n_utts, "frames_per_gpu": F, "precision": "F32 throughput mode",
                        "l2_policy": "inputs+outputs per step (%.1f GB) exceed L2; no flush needed" % (F * rec / 1e9),

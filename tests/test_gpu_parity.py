@@ -126,12 +126,14 @@ def test_gmm_lna_parity_mode_bit_exact(engine, case, request):
             assert np.array_equal(rec.reshape(-1), want[5:]), (case, nb, nonorm, (rec.reshape(-1) != want[5:]).sum())
 
 
-def test_tensor_core_variant_tolerance(engine, ref_small, ref_full):
-    """tcgen05 scorer (variant 3): bf16x3-split expanded form, fp32 accumulation in TMEM (leading terms and
-    corrections in separate accumulators).  Diagonal pools meet the same bars as the FP32-pipe kernel
-    (test_gmm_lna_throughput_mode_tolerance runs it too); the full-covariance contraction (K' = 4928)
-    is held to 2e-4 absolute on the log-likelihoods."""
-    engine.set_scorer_variant(3)
+@pytest.mark.parametrize("variant", [3, 4])
+def test_tensor_core_variant_tolerance(engine, ref_small, ref_full, variant):
+    """tcgen05 scorers: variant 3 (= default) is the fp16x2-split kernel for diagonal pools (gmm_tc16.cu), variant 4
+    forces the bf16x3-split kernel (gmm_tc.cu), which also serves full-covariance pools; fp32 accumulation in TMEM
+    with leading terms and corrections in separate accumulators.  Diagonal pools meet the same bars as the
+    FP32-pipe kernel (test_gmm_lna_throughput_mode_tolerance runs them too); the full-covariance contraction
+    (K' = 4928) is held to 2e-4 absolute on the log-likelihoods."""
+    engine.set_scorer_variant(variant)
     try:
         g = ref_small
         load_model(engine, g["model"])
@@ -156,7 +158,7 @@ def test_tensor_core_variant_tolerance(engine, ref_small, ref_full):
         engine.set_scorer_variant(0)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
 def test_gmm_lna_throughput_mode_tolerance(engine, case, variant, request):
     g = request.getfixturevalue(case)
@@ -186,6 +188,26 @@ def test_gmm_lna_throughput_mode_tolerance(engine, case, variant, request):
             assert (d <= 1).mean() >= 0.999 and (d != 0).mean() <= 0.02, (d.max(), (d != 0).mean())
     finally:
         engine.set_scorer_variant(0)
+
+
+def test_fp16_range_fallback(engine, ref_small):
+    """A feature far outside the fp16 range of the default scorer's scaled terms makes the call fall back to the
+    bf16x3 kernel: results stay finite and the other frames are unchanged."""
+    g = ref_small
+    load_model(engine, g["model"])
+    feats = g["feats"].astype(np.float32).copy()
+    clean = engine.gmm_score(feats, precision=F32)
+    feats[7, 3] = 3.0e4
+    l0 = engine.launch_count()
+    got = engine.gmm_score(feats, precision=F32)
+    assert engine.launch_count() - l0 >= 4          # first attempt + the bf16x3 redo (expansion, scorer, transposes)
+    assert np.isfinite(got).all() and got[7].max() < -1e5
+    keep = np.arange(feats.shape[0]) != 7
+    assert np.abs(got[keep] - clean[keep]).max() <= 3e-5
+    # and the default kernel is back for the next call
+    l0 = engine.launch_count()
+    again = engine.gmm_score(g["feats"].astype(np.float32), precision=F32)
+    assert engine.launch_count() - l0 == 2 and np.array_equal(again, clean)
 
 
 def test_full_covariance_pool(engine, ref_full, tmp_path):
