@@ -155,6 +155,114 @@ lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int norma
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// lna_f32_rows: same results as lna_f32, laid out for HBM bandwidth.  CTA = 32 frames (lanes) x 8 warps; a round
+// covers 256 states (2-byte codes) or 128 states (floats): every lane reads its frame's column (a warp reads one
+// 128 B line per state, 16 loads in flight per thread), converts in fp32 only, and packs the records into a
+// double-buffered shared tile [frame][128 words]; after ONE barrier per round each warp streams four frame rows out
+// as 128 B line stores.  Used when the rows are 4-byte aligned (S * B % 4 == 0).
+//
+// All arithmetic is fp32 and bit-identical to the double expressions of lna_f32:
+//   * lp = (float)((double)(L - Mx) - (double)lognorm_f) is the correctly rounded difference of two floats, i.e. the
+//     fp32 subtraction (the scorer's normaliser is a float);
+//   * (double)lp < -36.008 holds exactly when lp < 0xc2100831 (the smallest float above -36.008);
+//   * (int)(-1820.0 * (double)lp + .5): the double expression is exact (24 x 11 bits), so it is the truncation
+//     towards zero of the exact value -- for lp <= 0 one round-down fma (lna_code16_f32_neg); for any sign the
+//     nearest integer of fmaf(-1820, lp, .5), moved one step towards zero when the sign of fmaf(-1820, lp, .5 - k)
+//     (an fma's sign is the exact sign) says k overshot.
+__device__ __noinline__ uint32_t lna_code16_f32_wide(float lp)     // absurd magnitudes / NaN: the double expression itself
+{
+  const int temp = (int)(-1820.0 * (double)lp + .5);
+  return (uint32_t)temp & 0xFFFFu;
+}
+// any sign (un-normalised log-likelihoods can be positive: negative codes wrap like the reference's two's complement)
+__device__ __forceinline__ uint32_t lna_code16_f32(float lp)
+{
+  if (lp < __uint_as_float(0xc2100831u)) return 0xFFFFu;
+  const float t = fmaf(-1820.f, lp, 0.5f);
+  if (!(fabsf(t) < 4194304.f)) return lna_code16_f32_wide(lp);
+  float kf = (t + 12582912.f) - 12582912.f;                   // nearest integer (ties to even), |kf| < 2^22
+  const float d = fmaf(-1820.f, lp, 0.5f - kf);               // sign of (exact value - kf); 0.5 - kf is exact
+  if (kf > 0.f && d < 0.f) kf -= 1.f;                         // (int) truncates towards zero
+  else if (kf < 0.f && d > 0.f) kf += 1.f;
+  return (__float_as_uint(kf + 12582912.f) - 0x4B400000u) & 0xFFFFu;
+}
+// lp <= 0 (normalised records): floor(-1820 lp + .5) in ONE round-down fma: the exact value + 2^22 lands in
+// [2^22, 2^23) where the fp32 grid is 0.5, rounding down to that grid and dropping the half bit is the floor.
+__device__ __forceinline__ uint32_t lna_code16_f32_neg(float lp)
+{
+  const uint32_t m = __float_as_uint(__fmaf_rd(-1820.f, lp, 4194304.5f));
+  return (lp < __uint_as_float(0xc2100831u)) ? 0xFFFFu : ((m >> 1) & 0xFFFFu);
+}
+__device__ __noinline__ float log_of_float_cast_rare(float v) { return log_of_float_cast(v); }
+
+template <int B, bool NORM>
+__global__ void __launch_bounds__(256)
+lna_f32_rows(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, const float2 *__restrict__ norm, uint8_t *__restrict__ out)
+{
+  constexpr int SPR = (B == 2) ? 256 : 128;      // states per round
+  constexpr int SPW = SPR / 8;                   // states per warp and round
+  constexpr int NB = 16;                         // loads in flight per thread
+  constexpr int TW = 128;                        // 32-bit words per frame row of the tile
+  __shared__ uint32_t tile[2][32][TW + 1];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int64_t f0 = (int64_t)blockIdx.x * 32;
+  const int64_t f = f0 + lane;
+  const bool fvalid = f < nf;
+  float Mx = 0.f, lognorm = 0.f;
+  if (NORM) {
+    const float2 nm = norm[fvalid ? f : 0];
+    // every state flushed to zero (Mx = -inf): Z = 1 and every record is the floor; +inf makes L - Mx = -inf
+    Mx = (nm.x == -INFINITY) ? INFINITY : nm.x;
+    lognorm = nm.y;
+  }
+  const int rounds = (S + SPR - 1) / SPR;
+  const float *src = sll + (fvalid ? f : 0) + (int64_t)(w * SPW) * ldF;
+  for (int r = 0; r < rounds; r++, src += (int64_t)SPR * ldF) {
+    uint32_t(*tl)[TW + 1] = tile[r & 1];
+    const int sw = r * SPR + w * SPW;
+#pragma unroll
+    for (int b = 0; b < SPW; b += NB) {
+      float lp[NB];
+      const float *p = src + (int64_t)b * ldF;
+#pragma unroll
+      for (int j = 0; j < NB; ++j, p += ldF) lp[j] = (sw + b + j < S) ? __ldcs(p) : 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float L = lp[j];
+        if (L < LN_2M126) L = log_of_float_cast_rare(L);       // fp32-denormal / zero range of the float cast: rare
+        const float v = NORM ? (L - Mx) - lognorm : L;
+        lp[j] = fmaxf(v, LP_FLOOR);                            // also catches -inf and NaN
+      }
+      if (B == 2) {
+#pragma unroll
+        for (int j = 0; j < NB; j += 2) {
+          const uint32_t c0 = NORM ? lna_code16_f32_neg(lp[j]) : lna_code16_f32(lp[j]);
+          const uint32_t c1 = NORM ? lna_code16_f32_neg(lp[j + 1]) : lna_code16_f32(lp[j + 1]);
+          tl[lane][(w * SPW + b + j) >> 1] = __byte_perm(c0, c1, 0x4501);   // big-endian codes, two per word
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) tl[lane][w * SPW + b + j] = __float_as_uint(lp[j]);
+      }
+    }
+    __syncthreads();
+    const int nwords = min(SPR, S - r * SPR) * B / 4;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int fr = w * 4 + rr;
+      const int64_t gf = f0 + fr;
+      if (gf < nf) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((size_t)gf * S + (size_t)r * SPR) * B);
+#pragma unroll
+        for (int k = 0; k < TW / 32; ++k)
+          if (lane + 32 * k < nwords) __stcs(dst + lane + 32 * k, tl[fr][lane + 32 * k]);
+      }
+    }
+    // no second barrier: the next round fills the other buffer, and the one after that is behind the next barrier
+  }
+}
+
 // Parity mode: one thread per frame, states in index order, doubles throughout.
 template <int B>
 __global__ void __launch_bounds__(128)
@@ -202,6 +310,16 @@ void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64
 {
   if (nf <= 0) return;
   unsigned grid = (unsigned)((nf + 31) / 32);
+  // row-streaming kernel: needs the scorer's per-frame normaliser (or no normalisation) and 4-byte aligned rows
+  if ((!normalize || norm) && ((size_t)S * lnabytes) % 4 == 0 && ((uintptr_t)out & 3) == 0 && !getenv("AKUGPU_LNA_OLD")) {
+    if (lnabytes == 2 && normalize) lna_f32_rows<2, true><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
+    else if (lnabytes == 2) lna_f32_rows<2, false><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
+    else if (normalize) lna_f32_rows<4, true><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
+    else lna_f32_rows<4, false><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
+    AKU_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return;
+  }
   if (lnabytes == 2) lna_f32<2><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, normalize, norm, out);
   else lna_f32<4><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, normalize, norm, out);
   AKU_CUDA(cudaGetLastError());

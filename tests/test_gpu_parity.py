@@ -190,6 +190,22 @@ def test_gmm_lna_throughput_mode_tolerance(engine, case, variant, request):
         engine.set_scorer_variant(0)
 
 
+@pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
+def test_lna_row_kernel_identical_to_column_kernel(engine, case, request, monkeypatch):
+    """The bandwidth-oriented epilogue (lna_f32_rows, fp32-only arithmetic) writes the same bytes as the original
+    column kernel (double expressions) -- both lnabytes, with and without normalisation, incl. the edge model."""
+    g = request.getfixturevalue(case)
+    load_model(engine, g["model"])
+    feats32 = g["feats"].astype(np.float32)
+    for nb in (2, 4):
+        for normalize in (True, False):
+            new = engine.gmm_lna(feats32, precision=F32, lnabytes=nb, normalize=normalize)
+            monkeypatch.setenv("AKUGPU_LNA_OLD", "1")
+            old = engine.gmm_lna(feats32, precision=F32, lnabytes=nb, normalize=normalize)
+            monkeypatch.delenv("AKUGPU_LNA_OLD")
+            assert np.array_equal(new, old), (case, nb, normalize, (new != old).mean())
+
+
 def test_fp16_range_fallback(engine, ref_small):
     """A feature far outside the fp16 range of the default scorer's scaled terms makes the call fall back to the
     bf16x3 kernel: results stay finite and the other frames are unchanged."""
@@ -347,6 +363,14 @@ def test_full_size_properties(engine, big_case):
     a = engine.gmm_lna(b["feats"][idx].astype(np.float32), lnabytes=2)
     c = engine.gmm_lna(b["feats"][idx][perm].astype(np.float32), lnabytes=2)
     assert np.array_equal(a[perm], c)
+    # (d2) the row-streaming LNA kernel and the column kernel write identical bytes at full width
+    import os
+    os.environ["AKUGPU_LNA_OLD"] = "1"
+    try:
+        c_old = engine.gmm_lna(b["feats"][idx][perm].astype(np.float32), lnabytes=2)
+    finally:
+        del os.environ["AKUGPU_LNA_OLD"]
+    assert np.array_equal(c, c_old)
     # (e) both kernel variants within tolerance of each other
     engine.set_scorer_variant(1)
     try:
