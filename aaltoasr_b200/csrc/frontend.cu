@@ -398,6 +398,10 @@ struct UttDesc {
   int pad;
 };
 
+constexpr int fe_log2(int v) { return v <= 1 ? 0 : 1 + fe_log2(v >> 1); }
+// threads cooperating on one frame: the largest power of two <= min(256, max(32, M/2))
+constexpr int fe_threads_per_frame(int M) { return M / 2 >= 256 ? 256 : (M / 2 <= 32 ? 32 : (1 << fe_log2(M / 2))); }
+
 __device__ __forceinline__ void row_to_frame(const int *__restrict__ row_utt, const UttDesc *__restrict__ utts,
                                              int64_t r, int H, int &u, int &t)
 {
@@ -405,18 +409,22 @@ __device__ __forceinline__ void row_to_frame(const int *__restrict__ row_utt, co
   t = utts[u].start - H + (int)(r - utts[u].row_off);
 }
 
-// audiofile + fft for power-of-two windows.  One CTA = FPB frames, N/2-point complex FFT of the
-// even/odd packed real signal in shared memory, then the real-FFT split.
+// audiofile + fft for windows of 2^k or 3 * 2^k samples (16 kHz -> 256, 48 kHz -> 768, ...).  One CTA = FPB frames;
+// the real signal is packed even/odd into an M = N/2-point complex FFT in shared memory: R = 1 or 3 interleaved
+// radix-2 DIT sub-transforms of P = M/R points, one radix-3 combination pass when R = 3, then the real-FFT split.
 template <int N>
 __global__ void __launch_bounds__(256)
-fe_spectrum_pow2(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
-                 int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
-                 const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out)
+fe_spectrum_fft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
+                const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out)
 {
   constexpr int M = N / 2;                 // complex FFT size
-  constexpr int TPF = (M / 2 < 32) ? 32 : ((M / 2 > 256) ? 256 : M / 2);   // threads per frame
+  constexpr int R = (N % 3 == 0) ? 3 : 1;  // odd radix
+  constexpr int P = M / R;                 // power-of-two sub-transform
+  static_assert((P & (P - 1)) == 0 && P >= 16, "window must be 2^k or 3 * 2^k samples");
+  constexpr int TPF = fe_threads_per_frame(M);
   constexpr int FPB = 256 / TPF;
-  constexpr int LOGM = (M == 64) ? 6 : (M == 128) ? 7 : (M == 256) ? 8 : (M == 512) ? 9 : (M == 1024) ? 10 : 5;
+  constexpr int LOGP = fe_log2(P);
   __shared__ float2 z[FPB][M + 1];
   const int fl = threadIdx.x / TPF, tl = threadIdx.x % TPF;
   const int64_t r = (int64_t)blockIdx.x * FPB + fl;
@@ -440,20 +448,41 @@ fe_spectrum_pow2(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
       float pe = __fsub_rn(s1, __fmul_rn(emph, s0));                    // float pre-emphasis (:429)
       v[e] = (float)__dmul_rn((double)window[i], (double)pe);           // float window * double sample -> float (:531)
     }
-    z[fl][__brev((unsigned)k) >> (32 - LOGM)] = make_float2(v[0], v[1]);
+    // decimation in time by R, each sub-sequence in bit-reversed order
+    const int sub = k % R, m = k / R;
+    z[fl][sub * P + (int)(__brev((unsigned)m) >> (32 - LOGP))] = make_float2(v[0], v[1]);
   }
   __syncthreads();
-  // radix-2 DIT, M-point; twiddle e^{-2 pi i j / len} = tw[j * N / len]
-  for (int len = 2; len <= M; len <<= 1) {
+  // radix-2 DIT on the R sub-transforms; twiddle e^{-2 pi i j / len} = tw[j * N / len]
+  for (int len = 2; len <= P; len <<= 1) {
     const int half = len >> 1;
     for (int b = tl; b < M / 2; b += TPF) {
-      int j = b & (half - 1);
-      int i0 = ((b - j) << 1) + j, i1 = i0 + half;
+      const int sub = b / (P / 2), bb = b - sub * (P / 2);
+      int j = bb & (half - 1);
+      int i0 = sub * P + ((bb - j) << 1) + j, i1 = i0 + half;
       float2 w = tw[j * (N / len)];
       float2 a = z[fl][i0], c = z[fl][i1];
       float2 wc = make_float2(c.x * w.x - c.y * w.y, c.x * w.y + c.y * w.x);
       z[fl][i0] = make_float2(a.x + wc.x, a.y + wc.y);
       z[fl][i1] = make_float2(a.x - wc.x, a.y - wc.y);
+    }
+    __syncthreads();
+  }
+  if (R == 3) {
+    // Z[k + qP] = Y0[k] + w3^q W_M^k Y1[k] + w3^2q W_M^2k Y2[k],  W_M^k = tw[2k],  w3 = e^{-2 pi i / 3}
+    const float c3 = -0.5f, s3 = -0.86602540378443864676f;
+    for (int k = tl; k < P; k += TPF) {
+      const float2 y0 = z[fl][k], y1 = z[fl][P + k], y2 = z[fl][2 * P + k];
+      const float2 w1 = tw[2 * k], w2 = tw[4 * k];
+      const float2 t1 = make_float2(y1.x * w1.x - y1.y * w1.y, y1.x * w1.y + y1.y * w1.x);
+      const float2 t2 = make_float2(y2.x * w2.x - y2.y * w2.y, y2.x * w2.y + y2.y * w2.x);
+      const float2 sum = make_float2(t1.x + t2.x, t1.y + t2.y), dif = make_float2(t1.x - t2.x, t1.y - t2.y);
+      // w3 t1 + conj(w3) t2 = c3 * sum + i s3 * dif ;  conj(w3) t1 + w3 t2 = c3 * sum - i s3 * dif
+      const float2 base = make_float2(y0.x + c3 * sum.x, y0.y + c3 * sum.y);
+      const float2 rot = make_float2(-s3 * dif.y, s3 * dif.x);
+      z[fl][k] = make_float2(y0.x + sum.x, y0.y + sum.y);
+      z[fl][P + k] = make_float2(base.x + rot.x, base.y + rot.y);
+      z[fl][2 * P + k] = make_float2(base.x - rot.x, base.y - rot.y);
     }
     __syncthreads();
   }
@@ -759,28 +788,30 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
         const int N = base.window_width;
         const float *win = mod.d_a->as<float>();
         const float2 *tw = mod.d_b->as<float2>();
-#define SPEC_POW2(NN)                                                                                               \
+#define SPEC_FFT(NN)                                                                                                \
   case NN: {                                                                                                        \
-    constexpr int M_ = NN / 2;                                                                                      \
-    constexpr int TPF_ = (M_ / 2 < 32) ? 32 : ((M_ / 2 > 256) ? 256 : M_ / 2);                                      \
-    constexpr int FPB_ = 256 / TPF_;                                                                                \
-    fe_spectrum_pow2<NN><<<grid1(n_rows, FPB_), 256, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,        \
-                                                              base.emph, base.copy_borders, win, tw, mod.magnitude, \
-                                                              mod.log, o);                                          \
+    constexpr int FPB_ = 256 / fe_threads_per_frame(NN / 2);                                                        \
+    fe_spectrum_fft<NN><<<grid1(n_rows, FPB_), 256, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,         \
+                                                             base.emph, base.copy_borders, win, tw, mod.magnitude,  \
+                                                             mod.log, o);                                           \
     break;                                                                                                          \
   }
         switch (N) {
-          SPEC_POW2(128)
-          SPEC_POW2(256)
-          SPEC_POW2(512)
-          SPEC_POW2(1024)
-          SPEC_POW2(2048)
+          SPEC_FFT(128)
+          SPEC_FFT(256)
+          SPEC_FFT(512)
+          SPEC_FFT(1024)
+          SPEC_FFT(2048)
+          SPEC_FFT(192)
+          SPEC_FFT(384)
+          SPEC_FFT(768)
+          SPEC_FFT(1536)
           default:
             fe_spectrum_dft<<<(unsigned)n_rows, 128, N * sizeof(float), st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,
                                                                              base.emph, base.copy_borders, win, tw, N,
                                                                              mod.magnitude, mod.log, o);
         }
-#undef SPEC_POW2
+#undef SPEC_FFT
         break;
       }
       case M_MEL:

@@ -140,8 +140,8 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
+  if (warp == 0 && elect_one()) {
+    // ===== TMA producer (elect.sync: see tc_common.cuh) =====
     int it = 0;
     if (ARES) {
       mbar_expect_tx(&a_full, (uint32_t)kblocks * A_BYTES);
@@ -157,7 +157,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tma_load_2d(dst, &mapB, kb * BK, n * BN, &full_bar[s]);
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===== MMA issuer =====
     int it = 0;
     if (ARES) mbar_wait(&a_full, 0);

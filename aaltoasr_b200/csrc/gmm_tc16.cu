@@ -63,16 +63,6 @@ constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 constexpr float BIAS_OFF = -65504.f;               // bias of absent components: exp() underflows to exactly 0
 }  // namespace tc16
 
-// Exactly one lane of the (converged) calling warp returns true.  elect.sync tells the compiler that the branch is
-// single-threaded, so tcgen05.mma / commit / TMA are emitted straight (a plain `lane == 0` test makes it wrap every one
-// of them in a uniformisation loop: measured ~200 clk per MMA issue instead of the pipe's 64-87).
-__device__ __forceinline__ bool elect_one()
-{
-  uint32_t p;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
-  return p != 0;
-}
-
 template <int NCH>
 __global__ void __launch_bounds__(tc16::THREADS, 1)
 gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapB, int tslots, const int *__restrict__ range_begin,

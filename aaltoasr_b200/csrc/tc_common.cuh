@@ -56,6 +56,16 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// Exactly one lane of the (converged) calling warp returns true.  elect.sync tells the compiler that the branch is
+// single-threaded, so tcgen05.mma / commit / TMA are emitted straight (a plain `lane == 0` test makes it wrap every one
+// of them in a uniformisation loop: measured ~200 clk per MMA issue instead of the pipe's 64-87).
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+  return p != 0;
+}
+
 #define AKU_TMEM_LD16(r, taddr)                                                                                              \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"    \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \

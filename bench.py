@@ -216,6 +216,146 @@ def reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------
+def _event_time(torch, stream, fn, reps):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_feature_sweep(args, local):
+    """BASELINE.json configs[2]: FeatureGenerator only (audiofile -> fft -> mel -> dct + power -> delta -> delta-delta),
+    sample rates 8-64 kHz at the reference's default window (sample_rate / 62.5) and window widths 256-2048 at 16 kHz.
+    Algorithmic HBM bytes per frame = 2 * hop (PCM in, each sample once) + 4 * dim (features out)."""
+    import torch
+    from aaltoasr_b200 import AkuGpu, synth
+    eng = AkuGpu(local)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    hbm_peak, hbm_src = measured_peaks()
+    settings = [(sr, None) for sr in (8000, 16000, 32000, 48000, 64000)] + [(16000, ww) for ww in (256, 512, 1024, 2048)]
+    secs, n_utts = 60, 16
+    sweep, head = [], None
+    for sr, ww in settings:
+        cfg = synth.mfcc39_config(sr)
+        if ww:
+            cfg = cfg.replace("sample_rate %d" % sr, "sample_rate %d\n  window_width %d" % (sr, ww))
+        eng.frontend_load_config_text(cfg)
+        one = synth.synth_audio(3000 + sr // 1000, secs * sr, sr)
+        pcm = np.tile(one, n_utts)
+        uo = np.arange(n_utts + 1, dtype=np.int64) * one.size
+        fo = eng.frame_offsets(uo)
+        F, dim = int(fo[-1]), eng.feature_dim
+        pcm_d = torch.from_numpy(pcm).cuda()
+        out_d = torch.empty((F, dim), dtype=torch.float32, device="cuda")
+        pcm_p = torch.from_numpy(pcm).pin_memory()
+        out_p = torch.empty((F, dim), dtype=torch.float32).pin_memory()
+        is_head = sr == 16000 and ww is None
+        reps = args.steps if is_head else 3
+        for _ in range(args.warmup if is_head else 2):
+            eng.features(pcm_d, uo, out=out_d)
+        l0 = eng.launch_count()
+        ms = _event_time(torch, stream, lambda: eng.features(pcm_d, uo, out=out_d), reps)
+        launches = eng.launch_count() - l0
+        ms_e2e = _event_time(torch, stream, lambda: eng.features(pcm_p, uo, out=out_p), reps)
+        hop = sr / 125.0
+        alg = (2 * hop + 4 * dim) * F
+        row = {"sample_rate": sr, "window": ww or int(sr / 62.5), "frames": F, "frames_per_s": F / (ms * 1e-3),
+               "e2e_frames_per_s": F / (ms_e2e * 1e-3), "audio_x_realtime": F / 125.0 / (ms * 1e-3),
+               "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "hbm_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+        sweep.append(row)
+        log("config 3: %d Hz window %d: %.1f M frames/s resident, %.1f M e2e, %.1f GB/s algorithmic" % (
+            sr, row["window"], row["frames_per_s"] / 1e6, row["e2e_frames_per_s"] / 1e6, row["algorithmic_GBps"]))
+        if is_head:
+            head = dict(row, ms=ms, ms_e2e=ms_e2e, launches=launches, h2d=int(pcm.nbytes), d2h=int(F * dim * 4))
+    eng.close()
+    return {"metric": "acoustic frames/sec (FeatureGenerator only: MFCC+d+dd)", "value": head["frames_per_s"], "unit": "frames/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": {"workload": "feature-only sweep; headline = 16 x 60 s @16 kHz, 256-sample window, 39-dim MFCC+d+dd",
+                       "l2_policy": "PCM + module buffers per step exceed L2"},
+            "e2e": {"value": head["e2e_frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": head["h2d"],
+                    "d2h_bytes_per_step": head["d2h"], "ms_per_step": head["ms_e2e"]},
+            "gpu_launches": int(head["launches"]),
+            "roofline": {"kernel": "front-end module kernels (fe_spectrum_pow2 dominant)", "bound": "hbm",
+                         "achieved": head["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
+                         "traffic": None, "peak_source": hbm_src,
+                         "note": "module outputs are separate double matrices: actual traffic is ~10x the algorithmic 412 B/frame; "
+                                 "the FFT stage is FP32/shared-memory bound (DESIGN.md 4.4)"},
+            "sweep": sweep, "cpu_baseline": None}
+
+
+def bench_full_cov(args, local):
+    """BASELINE.json configs[4]: 2000-state x 16-mixture full-covariance pool (FullCovarianceGaussian; the subspace
+    classes are dead code in the reference build), features resident -> LNA, tensor-core expanded form."""
+    import torch
+    from aaltoasr_b200 import AkuGpu, synth
+    eng = AkuGpu(local)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.frontend_load_config_text(synth.mfcc39_config(SAMPLE_RATE))
+    S, M, D = 2000, 16, 39
+    n_utts = args.utts or 100
+    base = [synth.synth_audio(2000 + i, UTT_SAMPLES, SAMPLE_RATE) for i in range(8)]
+    pcm = np.concatenate([base[i % 8] for i in range(n_utts)])
+    uo = np.arange(n_utts + 1, dtype=np.int64) * UTT_SAMPLES
+    feats, fo = eng.features(pcm, uo, dtype=np.float32)
+    F = int(fo[-1])
+    rng = np.random.default_rng(5999)
+    G = S * M
+    f64 = feats[:20000].astype(np.float64)
+    sd = f64.std(axis=0)
+    means = f64[rng.integers(0, f64.shape[0], G)] + 0.3 * sd * rng.standard_normal((G, D))
+    A = rng.standard_normal((G, D, 4)) * sd[None, :, None]
+    full = np.einsum("gik,gjk->gij", A, A) * 0.1
+    full[:, np.arange(D), np.arange(D)] += rng.uniform(0.5, 2, (G, D)) * sd ** 2
+    t0 = time.time()
+    eng.model_load_full(np.arange(0, G + 1, M, dtype=np.int32), np.arange(G, dtype=np.int32),
+                        rng.dirichlet(np.ones(M), S).reshape(-1), means, full)
+    log("config 5: model packed in %.1f s, %d frames" % (time.time() - t0, F))
+    feats_d = torch.from_numpy(feats).cuda()
+    out_d = torch.empty((F, S * LNABYTES), dtype=torch.uint8, device="cuda")
+    feats_p = torch.from_numpy(feats).pin_memory()
+    out_p = torch.empty((F, S * LNABYTES), dtype=torch.uint8).pin_memory()
+    for _ in range(args.warmup):
+        eng.gmm_lna(feats_d, lnabytes=LNABYTES, out=out_d)
+    eng.stage_times_reset(True)
+    l0 = eng.launch_count()
+    ms = _event_time(torch, stream, lambda: eng.gmm_lna(feats_d, lnabytes=LNABYTES, out=out_d), args.steps)
+    launches = eng.launch_count() - l0
+    st = eng.stage_times()
+    eng.stage_times_reset(False)
+    ms_e2e = _event_time(torch, stream, lambda: eng.gmm_lna(feats_p, lnabytes=LNABYTES, out=out_p), args.steps)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    L = D * (D + 3) // 2
+    Kp = -(-L // 64) * 64 + -(-5 * L // 64) * 64
+    gmm_ms, gmm_launches = st["gmm"]
+    # the stage also holds the feature expansion kernel; the MMA work is what is counted
+    mma_flop = 2.0 * Kp * G * (-(-F // 128) * 128) * args.steps
+    achieved = mma_flop / (gmm_ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    eng.close()
+    return {"metric": "acoustic frames/sec (full-covariance GMM log-lik -> LNA)", "value": F / (ms * 1e-3), "unit": "frames/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32", "data": "synthetic",
+            "config": {"workload": "%d utterances x 10 s, 39-dim features resident, 2000-state x 16-mix full-covariance GMM, 2-byte LNA" % n_utts,
+                       "frames_per_gpu": F, "l2_policy": "expanded features + outputs per step exceed L2"},
+            "e2e": {"value": F / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(feats.nbytes),
+                    "d2h_bytes_per_step": int(F * S * LNABYTES), "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "gmm_tc_kernel<false> (tcgen05 kind::f16, bf16x3-split exponential form, K' = %d)" % Kp,
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "launches": int(gmm_launches), "stage_ms": {"gmm+expand": gmm_ms, "lna": st["lna"][0]},
+                         "useful_flop_per_frame": 2.0 * L * G},
+            "cpu_baseline": None}
+
+
+# --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,9 +363,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=None, help="utterances per GPU (default: the BASELINE config)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 4],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 = 1000 utts, 5000x16 (default, the metric's config); "
-                         "4 = 100 h over 8 GPUs (4500 utts per GPU), 10000x32, LNA discarded after the checksum-free write")
+                         "3 = feature-only sweep (8-64 kHz, 256-2048-point windows); "
+                         "4 = 100 h over 8 GPUs (4500 utts per GPU), 10000x32, LNA discarded after the checksum-free write; "
+                         "5 = 2000-state x 16-mix full-covariance pool")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -245,6 +387,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     global N_STATES, N_MIX, WORKLOAD
+    if args.config in (3, 5):
+        if world > 1:
+            raise SystemExit("bench.py --config %d is a single-GPU configuration" % args.config)
+        line = (bench_feature_sweep if args.config == 3 else bench_full_cov)(args, local)
+        print(json.dumps(line))
+        return
     if args.config == 4:
         N_STATES, N_MIX = 10000, 32
         WORKLOAD = "100 h @16 kHz sharded by utterance (4500 x 10 s per GPU), 39-dim MFCC+d+dd, 10000-state x 32-mix diag GMM, 2-byte LNA"

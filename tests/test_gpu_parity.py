@@ -91,9 +91,11 @@ def test_features_batch_equals_single(engine, ref_small):
         assert np.array_equal(batch[fo[k]:fo[k + 1]], single)
 
 
-@pytest.mark.parametrize("sr,ww", [(8000, None), (16000, 512), (32000, None), (16000, 2048), (48000, None), (16000, 400)])
+@pytest.mark.parametrize("sr,ww", [(8000, None), (16000, 512), (32000, None), (16000, 2048), (48000, None), (16000, 400),
+                                   (24000, None), (16000, 1536), (12000, None)])
 def test_features_sweep_vs_oracle(engine, sr, ww):
-    """Config 3: other sample rates / window widths (768 and 400 are not powers of two)."""
+    """Config 3: other sample rates / window widths: 2^k and 3 * 2^k (192, 384, 768, 1536) go through the shared-memory
+    FFT, 400 through the direct DFT."""
     from aaltoasr_b200 import synth
     cfg = synth.mfcc39_config(sr)
     if ww:
