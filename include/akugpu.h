@@ -153,13 +153,15 @@ int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5]);
 
 /* ---- tuning / introspection ---------------------------------------------------- */
 /* Frames scored per chunk of the pipelined batch path.  0 (default) = one full wave of the
- * scorer (SM count x resident CTAs x 64 frames = 37888 on B200). */
+ * scorer (two waves of SM count x 128 frames = 37888 on B200). */
 int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames);
 /* Kernel variant of the throughput-mode (F32) scorer:
- *   0 = default: the tensor-core scorer (tcgen05 + TMEM + TMA, bf16x3-split expanded form) for pools
- *       that are all diagonal or all full covariance with <= 64 components per state, otherwise the
- *       FP32-pipe kernel (diagonal) or the double path (mixed pools);
- *   1 = FP32-pipe kernel with plain FFMA, 2 = FP32-pipe kernel with packed FFMA2, 3 = same as 0. */
+ *   0 = default: tensor-core scorers (tcgen05 + TMEM + TMA, expanded form): the fp16 hi/lo-split kernel for diagonal
+ *       pools with <= 64 components per state and dim <= 63, the bf16x3-split kernel for full-covariance pools (and as
+ *       the fallback when a feature leaves the fp16 range); otherwise the FP32-pipe kernel (diagonal) or the double
+ *       path (mixed pools);
+ *   1 = FP32-pipe kernel with plain FFMA, 2 = FP32-pipe kernel with packed FFMA2, 3 = same as 0,
+ *   4 = force the bf16x3-split tensor-core kernel. */
 int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant);
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
  * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2 with constant
