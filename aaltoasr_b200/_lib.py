@@ -45,6 +45,10 @@ SYMBOLS = {
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "akugpu_model_load_full": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "akugpu_model_read_clustering": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "akugpu_model_set_clustering": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "akugpu_model_set_clustering_min_evals": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "akugpu_model_use_clustering": (C.c_int, [C.c_void_p, C.c_int]),
     "akugpu_model_num_states": (C.c_int, [C.c_void_p]),
     "akugpu_model_dim": (C.c_int, [C.c_void_p]),
     "akugpu_model_num_gaussians": (C.c_int, [C.c_void_p]),

@@ -86,9 +86,12 @@ static void require_frontend(akugpu_ctx *ctx)
 // Scores frames [0,F) of device-resident features chunk by chunk and emits LNA records.
 // out may be host (pipelined D2H on a second stream), device (written in place) or NULL.
 // Which tensor-core scorer serves throughput-mode calls: 2 = fp16x2 (diagonal pools), 1 = bf16x3, 0 = none.
+static bool clustering_on(akugpu_ctx *ctx) { return ctx->hm.use_clustering && ctx->hm.n_clusters > 0; }
+
 static int tc_mode(akugpu_ctx *ctx, int precision)
 {
   if (precision != AKUGPU_F32) return 0;
+  if (clustering_on(ctx)) return 0;      // the clustering approximation is evaluated in double (reference semantics)
   if (ctx->ptc16.ready && !ctx->tc16_suspended) return 2;
   return ctx->ptc.ready ? 1 : 0;
 }
@@ -112,6 +115,7 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
   const int use_tc = tc_mode(ctx, precision);
   *mode_out = use_tc;
   if (ctx->hm.n_full > 0 && !use_tc) precision = AKUGPU_F64;   // full-covariance pools are scored in double
+  if (clustering_on(ctx)) precision = AKUGPU_F64;
   const int64_t chunk = pick_chunk(ctx, F, use_tc);
   const size_t rec = (size_t)S * lnabytes;
   const bool out_dev = out && is_device_ptr(out);
@@ -452,6 +456,7 @@ int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim, 
   hm.mean.assign(means, means + (size_t)n_gauss * dim);
   hm.cov.assign(covs, covs + (size_t)n_gauss * dim);
   hm.full_index.clear(); hm.full_cov.clear(); hm.n_full = 0;
+  hm.clear_clustering();
   model_pack(ctx);
   API_END
 }
@@ -473,6 +478,47 @@ int akugpu_model_load_full(akugpu_ctx *ctx, int n_states, int n_gauss, int dim, 
   hm.n_full = n_gauss;
   ctx->have_model = false;
   model_pack(ctx);
+  API_END
+}
+
+// ---- Gaussian clustering (phone_probs -C / --eval-minc / --eval-ming) ----------------
+int akugpu_model_read_clustering(akugpu_ctx *ctx, const char *gcl_path)
+{
+  API_BEGIN
+  require_model(ctx);
+  if (!gcl_path) throw Error(AKUGPU_E_ARG, "gcl_path is NULL");
+  model_read_clustering(gcl_path, ctx->hm);
+  model_pack_clustering(ctx);
+  API_END
+}
+
+int akugpu_model_set_clustering(akugpu_ctx *ctx, int n_clusters, const int32_t *gauss_index, const int32_t *cluster_index,
+                                int64_t n_pairs)
+{
+  API_BEGIN
+  require_model(ctx);
+  if (n_pairs < 0 || (n_pairs && (!gauss_index || !cluster_index))) throw Error(AKUGPU_E_ARG, "bad n_pairs / NULL arrays");
+  model_set_clustering(ctx->hm, n_clusters, gauss_index, cluster_index, n_pairs);
+  model_pack_clustering(ctx);
+  API_END
+}
+
+int akugpu_model_set_clustering_min_evals(akugpu_ctx *ctx, double min_clusters, double min_gaussians)
+{
+  API_BEGIN
+  require_model(ctx);
+  HostModel &hm = ctx->hm;                 // HmmSet::set_clustering_min_evals, aku/HmmSet.cc:1360-1366
+  hm.eval_min_clusters = (int)(min_clusters * hm.n_clusters);
+  hm.eval_min_gaussians = (int)(min_gaussians * hm.G);
+  hm.use_clustering = true;
+  API_END
+}
+
+int akugpu_model_use_clustering(akugpu_ctx *ctx, int on)
+{
+  API_BEGIN
+  require_model(ctx);
+  ctx->hm.use_clustering = on != 0;        // PDFPool::set_use_clustering, aku/Distributions.hh:238
   API_END
 }
 
@@ -498,7 +544,7 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   bool redo = false;
   do {   // a second pass only when the fp16x2 scorer met a feature outside its range (see tc16_needs_redo)
   const int use_tc = tc_mode(ctx, precision);
-  const bool full = ctx->hm.n_full > 0 && !use_tc;
+  const bool full = (ctx->hm.n_full > 0 && !use_tc) || clustering_on(ctx);    // scored in double whatever was asked
   const int64_t chunk = pick_chunk(ctx, n_frames, use_tc);
   ctx->d_sll.reserve((size_t)S * chunk * (full ? 8 : esz));
   if (full && precision == AKUGPU_F32) ctx->d_lna[0].reserve((size_t)S * chunk * 4);
@@ -506,7 +552,8 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
     const int64_t c1 = std::min(n_frames, c0 + chunk);
     StageScope sc(ctx, 1);
     if (full) {
-      launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
+      if (ctx->hm.n_full > 0) launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
+      else launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
       if (precision == AKUGPU_F32) {
         launch_lin_to_log_f32(ctx, ctx->d_sll.as<double>(), (int64_t)S * chunk, ctx->d_lna[0].as<float>());
         launch_transpose_f32(ctx, ctx->d_lna[0].as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));

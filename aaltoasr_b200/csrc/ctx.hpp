@@ -83,6 +83,17 @@ struct HostModel {
   std::vector<int32_t> full_index;  // [G] (empty = all diagonal)
   std::vector<double> full_cov;     // [n_full * D * D] row-major, as read
   int n_full = 0;
+  // Gaussian clustering (PDFPool::read_clustering aku/Distributions.cc:3115-3170, precompute_likelihoods :2685-2722)
+  int n_clusters = 0;
+  std::vector<std::vector<int32_t>> cluster_gauss;   // members as listed (a Gaussian may be listed twice, see model.cu)
+  std::vector<int32_t> gauss_cluster;                // [G] cluster of each Gaussian, -1 = not listed
+  std::vector<double> c_mean, c_cov;                 // [C * D] moment-matched diagonal centres (Gaussian::merge :854-897)
+  bool use_clustering = false;
+  int eval_min_clusters = 1, eval_min_gaussians = 1; // PDFPool defaults (:2572-2574)
+  void clear_clustering() {
+    n_clusters = 0; cluster_gauss.clear(); gauss_cluster.clear(); c_mean.clear(); c_cov.clear();
+    use_clustering = false; eval_min_clusters = eval_min_gaussians = 1;
+  }
 };
 
 // fp32 scorer image: tiles of 8 slots x 16 components, see gmm_kernels.cu.
@@ -109,6 +120,8 @@ struct PackedF64 {
   DevBuf full_norm, full_cst;  // double [n_full]      m_exponential_normalizer, m_constant
   DevBuf full_gauss;           // int32  [n_full]      pool index of each full Gaussian
   DevBuf diag_gauss;           // int32  [G - n_full]  pool indices of the diagonal Gaussians
+  // Gaussian clustering: centres as a pool of C one-component "states", cluster of each Gaussian, member counts
+  DevBuf c_mean, c_prec, c_cst, c_mix_off, c_mix_gauss, c_mix_w, g2c, c_size;
 };
 
 // tensor-core scorer image (gmm_tc.cu): bf16x3-split expanded parameters, slot-ordered rows
@@ -209,7 +222,7 @@ struct akugpu_ctx {
   akugpu::StageTimer timer;
 
   // scratch
-  akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk, d_norm;
+  akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk, d_norm, d_clik, d_csel;
   akugpu::DevBuf d_fe[8];
   std::vector<std::shared_ptr<akugpu::DevBuf>> fe_bufs;   // per-module output matrices (grow-only)
   akugpu::PinnedBuf h_in[2], h_out[2];

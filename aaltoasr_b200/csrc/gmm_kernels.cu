@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(256)
 gmm_diag_f64(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t f_end, int D,
              const double *__restrict__ mean, const double *__restrict__ prec, const double *__restrict__ cst,
              const int *__restrict__ mix_off, const int *__restrict__ mix_gauss, const double *__restrict__ mix_w,
-             int S, double *__restrict__ lin, int64_t ldF)
+             int S, double *__restrict__ lin, int64_t ldF, double floor_at, const int *__restrict__ g2c,
+             const unsigned char *__restrict__ csel, const double *__restrict__ clik)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *xs = reinterpret_cast<double *>(smem_raw);   // [D][128]
@@ -306,18 +307,80 @@ gmm_diag_f64(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
         }
       }
       const double c = cst[g];
+      // Gaussian clustering (PDFPool::precompute_likelihoods, aku/Distributions.cc:2685-2722): a Gaussian of a cluster
+      // that was not among the best ones takes its cluster centre's likelihood -- unless that is not > 0, in which
+      // case PDFPool::compute_likelihood (:2637-2644) evaluates the Gaussian after all
+      const int cl = g2c ? g2c[g] : -1;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         double v = __dadd_rn(__dmul_rn(ll[i], -0.5), c);
-        l[i] = __dadd_rn(l[i], __dmul_rn(w, exp(v)));
+        double e = exp(v);
+        if (cl >= 0) {
+          const int64_t at = (int64_t)cl * ldF + (f0 - f_begin) + lane + 32 * i;
+          if (!csel[at]) { const double ce = clik[at]; if (ce > 0) e = ce; }
+        }
+        l[i] = __dadd_rn(l[i], __dmul_rn(w, e));
       }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double v = l[i];
-      if (v < 1e-50) v = 1e-50;
+      if (v < floor_at) v = floor_at;
       lin[(int64_t)s * ldF + (f0 - f_begin) + lane + 32 * i] = v;
     }
+  }
+}
+
+// Which clusters are evaluated exactly for a frame: clusters in descending order of their centre's likelihood, taken
+// while (clusters so far < min_clusters) or (Gaussians so far < min_gaussians) -- the reference pops a
+// std::priority_queue (aku/Distributions.cc:2686-2708).  One CTA per frame: bitonic sort of (likelihood, index) in
+// shared memory (ties go to the lower index; among equal POSITIVE likelihoods the reference's order is that of
+// libstdc++'s heap, among zero likelihoods the choice does not change any result because such clusters' members are
+// evaluated exactly either way), then a prefix sum of the member counts in sorted order.
+__global__ void __launch_bounds__(256)
+cluster_select(const double *__restrict__ clik, int64_t ldF, int C, int Cp, int64_t nf, const int *__restrict__ csize,
+               int min_clusters, int min_gaussians, unsigned char *__restrict__ csel)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *key = reinterpret_cast<double *>(smem_raw);                 // [Cp]
+  int *idx = reinterpret_cast<int *>(key + Cp);                       // [Cp]
+  int *cum = idx + Cp;                                                // [Cp] inclusive prefix of member counts
+  __shared__ int part[256];
+  const int64_t f = blockIdx.x;
+  if (f >= nf) return;
+  for (int i = threadIdx.x; i < Cp; i += 256) {
+    key[i] = i < C ? clik[(int64_t)i * ldF + f] : -1.0;               // padding sorts last (likelihoods are >= 0)
+    idx[i] = i;
+  }
+  __syncthreads();
+  for (int k = 2; k <= Cp; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < Cp; i += 256) {
+        const int p = i ^ j;
+        if (p > i) {
+          const bool desc = (i & k) == 0;                               // final order: descending
+          const double a = key[i], b = key[p];
+          const int ia = idx[i], ib = idx[p];
+          const bool a_first = (a > b) || (a == b && ia < ib);          // a belongs before b
+          if (desc ? !a_first : a_first) { key[i] = b; key[p] = a; idx[i] = ib; idx[p] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  // inclusive prefix sum of the member counts in sorted order (each thread a contiguous run)
+  const int per = (Cp + 255) / 256;
+  const int b0 = threadIdx.x * per, b1 = min(Cp, b0 + per);
+  int run = 0;
+  for (int i = b0; i < b1; i++) { run += (idx[i] < C) ? csize[idx[i]] : 0; cum[i] = run; }
+  part[threadIdx.x] = run;
+  __syncthreads();
+  int base = 0;
+  for (int t = 0; t < threadIdx.x; t++) base += part[t];
+  for (int i = b0; i < b1; i++) {
+    const int c = idx[i];
+    if (c >= C) continue;
+    const int before = base + cum[i] - csize[c];                       // Gaussians evaluated before this cluster
+    csel[(int64_t)c * ldF + f] = (i < min_clusters || before < min_gaussians) ? 1 : 0;
   }
 }
 
@@ -431,11 +494,43 @@ void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f
   }
   int64_t nf = f_end - f_begin;
   int ftiles = (int)((nf + 127) / 128);
+  const int *g2c = nullptr;
+  const unsigned char *csel = nullptr;
+  const double *clik = nullptr;
+  if (hm.use_clustering && hm.n_clusters > 0) {
+    // centre likelihoods (unfloored), then the per-frame choice of the clusters to evaluate exactly
+    const int C = hm.n_clusters;
+    int Cp = 2;
+    while (Cp < C) Cp <<= 1;
+    const size_t sel_smem = (size_t)Cp * (sizeof(double) + 2 * sizeof(int));
+    if (sel_smem > 200 * 1024) throw Error(AKUGPU_E_MODEL, fmt("too many Gaussian clusters (%d) for the selection kernel", C));
+    ctx->d_clik.reserve((size_t)C * ldF * sizeof(double));
+    ctx->d_csel.reserve((size_t)C * ldF);
+    int ys = std::max(1, std::min((C + 7) / 8, (4 * ctx->sm_count + ftiles - 1) / ftiles));
+    gmm_diag_f64<<<dim3(ftiles, ys), 256, smem, ctx->stream>>>(feats, feats_f64, f_begin, f_end, hm.D, p.c_mean.as<double>(),
+                                                              p.c_prec.as<double>(), p.c_cst.as<double>(), p.c_mix_off.as<int>(),
+                                                              p.c_mix_gauss.as<int>(), p.c_mix_w.as<double>(), C,
+                                                              ctx->d_clik.as<double>(), ldF, -1.0, nullptr, nullptr, nullptr);
+    AKU_CUDA(cudaGetLastError());
+    static size_t attr_sel = 0;
+    if (sel_smem > attr_sel) {
+      AKU_CUDA(cudaFuncSetAttribute(cluster_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+      attr_sel = sel_smem;
+    }
+    cluster_select<<<(unsigned)nf, 256, sel_smem, ctx->stream>>>(ctx->d_clik.as<double>(), ldF, C, Cp, nf, p.c_size.as<int>(),
+                                                                 hm.eval_min_clusters, hm.eval_min_gaussians,
+                                                                 ctx->d_csel.as<unsigned char>());
+    AKU_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    g2c = p.g2c.as<int>();
+    csel = ctx->d_csel.as<unsigned char>();
+    clik = ctx->d_clik.as<double>();
+  }
   int ysplit = std::max(1, std::min((hm.S + 7) / 8, (4 * ctx->sm_count + ftiles - 1) / ftiles));
   dim3 grid(ftiles, ysplit);
   gmm_diag_f64<<<grid, 256, smem, ctx->stream>>>(feats, feats_f64, f_begin, f_end, hm.D, p.mean.as<double>(),
                                                  p.prec.as<double>(), p.cst.as<double>(), p.mix_off.as<int>(),
-                                                 p.mix_gauss.as<int>(), p.mix_w.as<double>(), hm.S, lin, ldF);
+                                                 p.mix_gauss.as<int>(), p.mix_w.as<double>(), hm.S, lin, ldF, 1e-50, g2c, csel, clik);
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
 }

@@ -140,6 +140,11 @@ public:
   }
   int num_states() const { return akugpu_model_num_states(m_e.ctx()); }
   int dim() const { return akugpu_model_dim(m_e.ctx()); }
+  // Gaussian clustering approximation (aku/HmmSet.cc:1354-1366)
+  void read_clustering(const std::string &filename) { check(m_e.ctx(), akugpu_model_read_clustering(m_e.ctx(), filename.c_str())); }
+  void set_clustering_min_evals(double min_clusters = 1.0, double min_gaussians = 1.0) {
+    check(m_e.ctx(), akugpu_model_set_clustering_min_evals(m_e.ctx(), min_clusters, min_gaussians));
+  }
   // Scores every frame of an utterance at once; the per-frame calls below index into the result.
   void set_utterance(const double *feats, int64_t n_frames) {
     m_lik.resize((size_t)n_frames * m_S);

@@ -1,7 +1,7 @@
 // akugpu_phone_probs -- the reference tool aku/phone_probs.cc re-hosted on the GPU library.
 // Same flags (aku/phone_probs.cc:60-81) and the same per-utterance LNA files; utterances of a recipe
-// are batched into GPU calls.  Flags that select paths outside the accelerated scope
-// (-S speakers, -C clusters) are refused rather than ignored.
+// are batched into GPU calls (-C clusters / --eval-minc / --eval-ming included: the Gaussian-clustering
+// approximation).  -S speakers selects a path outside the accelerated scope and is refused rather than ignored.
 #include <errno.h>
 #include <math.h>
 #include <stdlib.h>
@@ -46,7 +46,8 @@ static std::vector<Utt> read_recipe(const std::string &path, int batch, int bind
 
 int main(int argc, char **argv)
 {
-  std::string base, gk, mc, ph, cfg, recipe, outdir;
+  std::string base, gk, mc, ph, cfg, recipe, outdir, clusters;
+  double eval_minc = 0, eval_ming = 0.1;       // defaults of aku/phone_probs.cc:74-75
   int lnabytes = 2, batch = 0, bindex = 0, info = 0, device = 0, precision = AKUGPU_F32;
   bool raw_input = false, lna_by_audio = false, no_overwrite = false, no_norm = false;
   long max_batch_samples = 64L << 20;
@@ -67,6 +68,8 @@ int main(int argc, char **argv)
                "  -a, --lnabyaudio       name LNA files by the audio file\n  -o, --output-dir=DIR   base path for LNAs\n"
                "  -R, --raw-input        raw audio input\n      --lnabytes=INT     2 (default) or 4\n"
                "  -n, --no-overwrite     skip existing non-empty LNA files\n  -N, --no-normalization\n"
+               "  -C, --clusters=FILE    Gaussian clustering (.gcl)\n      --eval-minc=FLOAT  minimum ratio of top clusters to evaluate (0)\n"
+               "      --eval-ming=FLOAT  minimum ratio of Gaussians to evaluate (0.1)\n"
                "  -B, --batch=INT  -I, --bindex=INT   recipe batching\n  -i, --info=INT\n"
                "      --precision=f32|f64   throughput (default) or parity arithmetic\n      --device=INT\n");
         return 0;
@@ -87,8 +90,11 @@ int main(int argc, char **argv)
       else if (a == "-i" || a == "--info") info = atoi(val().c_str());
       else if (a == "--precision") precision = (val() == "f64") ? AKUGPU_F64 : AKUGPU_F32;
       else if (a == "--device") device = atoi(val().c_str());
-      else if (a == "-S" || a == "--speakers" || a == "-C" || a == "--clusters" || a == "--eval-minc" || a == "--eval-ming")
-        throw std::string("option ") + a + " selects a path outside the accelerated scope (speaker adaptation / Gaussian clustering)";
+      else if (a == "-C" || a == "--clusters") clusters = val();
+      else if (a == "--eval-minc") eval_minc = atof(val().c_str());
+      else if (a == "--eval-ming") eval_ming = atof(val().c_str());
+      else if (a == "-S" || a == "--speakers")
+        throw std::string("option ") + a + " selects a path outside the accelerated scope (speaker adaptation)";
       else throw std::string("unknown option ") + a;
     }
     if (cfg.empty()) throw std::string("Must give --config");
@@ -103,6 +109,10 @@ int main(int argc, char **argv)
     if (!base.empty()) model.read_all(base);
     else if (!gk.empty() && !mc.empty() && !ph.empty()) model.read_files(gk, mc, ph);
     else throw std::string("Must give either --base or all --gk, --mc and --ph");
+    if (!clusters.empty()) {          // aku/phone_probs.cc:112-117
+      model.read_clustering(clusters);
+      model.set_clustering_min_evals(eval_minc, eval_ming);
+    }
     if (gen.dim() != model.dim()) {   // aku/phone_probs.cc:125-131
       char msg[200];
       snprintf(msg, sizeof msg, "Feature dimension (%d) and model dimension (%d) don't agree", gen.dim(), model.dim());

@@ -48,6 +48,9 @@ void launch_lna_f64(akugpu_ctx *ctx, const double *lin, int64_t ldF, int S, int6
 void launch_checksum(akugpu_ctx *ctx, const uint8_t *buf, int64_t nbytes, unsigned long long *acc);
 
 // model.cu
+void model_read_clustering(const std::string &gcl_path, HostModel &hm);
+void model_set_clustering(HostModel &hm, int n_clusters, const int32_t *gauss_index, const int32_t *cluster_index, int64_t n_pairs);
+void model_pack_clustering(akugpu_ctx *ctx);
 void model_read_files(const std::string &gk_path, const std::string &mc_path, const std::string &ph_path, HostModel &hm);
 void model_pack(akugpu_ctx *ctx);
 

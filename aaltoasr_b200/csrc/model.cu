@@ -60,8 +60,79 @@ struct Tokens {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Gaussian clustering (phone_probs -C file.gcl --eval-minc x --eval-ming y; aku/phone_probs.cc:112-117).
+// .gcl: number of clusters, then `gauss_index cluster_index` pairs (PDFPool::read_clustering, aku/Distributions.cc:3115-3147).
+// The reference reads pairs in a `while (in) { in >> g >> c; ... }` loop: after the last pair the stream is still good, the
+// next extraction fails at end of file without touching g and c, and the last pair is recorded a SECOND time.  That
+// duplicate counts in the cluster's size (the min-Gaussians budget) and weighs twice in its centre, so it is kept.
+void model_set_clustering(HostModel &hm, int n_clusters, const int32_t *gauss_index, const int32_t *cluster_index, int64_t n_pairs)
+{
+  const int G = hm.G, D = hm.D;
+  if (hm.n_full > 0) throw Error(AKUGPU_E_MODEL, "Gaussian clustering is supported for diagonal pools only");
+  if (n_clusters < 0 || (double)n_clusters > 0.3 * G)
+    throw Error(AKUGPU_E_MODEL, fmt("PDFPool::read_clustering(): Number of clusters (%d) seems insensible compared to the number of Gaussians (%d).",
+                                    n_clusters, G));
+  hm.clear_clustering();
+  hm.n_clusters = n_clusters;
+  hm.cluster_gauss.assign(n_clusters, std::vector<int32_t>());
+  hm.gauss_cluster.assign(G, -1);
+  for (int64_t i = 0; i < n_pairs; i++) {
+    const int g = gauss_index[i], c = cluster_index[i];
+    if (g >= G || g < 0) throw Error(AKUGPU_E_MODEL, "PDFPool::read_clustering(): Gauss index out of bounds\n");
+    if (c >= n_clusters || c < 0) throw Error(AKUGPU_E_MODEL, "PDFPool::read_clustering(): Cluster index out of bounds\n");
+    if (hm.gauss_cluster[g] >= 0 && hm.gauss_cluster[g] != c)
+      throw Error(AKUGPU_E_MODEL, fmt("Gaussian %d is assigned to clusters %d and %d: not supported", g, hm.gauss_cluster[g], c));
+    hm.gauss_cluster[g] = c;
+    hm.cluster_gauss[c].push_back(g);
+  }
+  // centres: Gaussian::merge with unit weights, diagonal kept (DiagonalGaussian::set_covariance :1208-1234), in the
+  // reference's order of operations: sum of (cov + mu mu), sum of mu, scale by the reciprocal, subtract mean*mean
+  hm.c_mean.assign((size_t)n_clusters * D, 0.0);
+  hm.c_cov.assign((size_t)n_clusters * D, 0.0);
+  for (int c = 0; c < n_clusters; c++) {
+    const std::vector<int32_t> &L = hm.cluster_gauss[c];
+    double wsum = 0;
+    for (size_t i = 0; i < L.size(); i++) wsum += 1.0;
+    const bool even = wsum < 1e-15;
+    const double cw = even ? 1.0 / (double)L.size() : 1.0;      // empty cluster: 0/0 in the reference as well
+    if (even) wsum = 1;
+    double *mu = &hm.c_mean[(size_t)c * D], *cv = &hm.c_cov[(size_t)c * D];
+    for (size_t i = 0; i < L.size(); i++)
+      for (int d = 0; d < D; d++) {
+        const double m = hm.mean[(size_t)L[i] * D + d];
+        const double cur = hm.cov[(size_t)L[i] * D + d] + m * m;
+        cv[d] += cw * cur;
+        mu[d] += cw * m;
+      }
+    const double r = 1.0 / wsum;
+    for (int d = 0; d < D; d++) { mu[d] *= r; cv[d] *= r; }
+    for (int d = 0; d < D; d++) cv[d] += -1.0 * mu[d] * mu[d];
+  }
+}
+
+void model_read_clustering(const std::string &gcl_path, HostModel &hm)
+{
+  std::ifstream in(gcl_path.c_str());
+  if (!in) throw Error(AKUGPU_E_IO, "PDFPool::read_clustering(): could not open " + gcl_path);
+  int n = 0;
+  in >> n;
+  std::vector<int32_t> gi, ci;
+  int g = 0, c = 0;
+  bool any = false;
+  while (in) {                       // see above: the failed read after the last pair repeats it
+    int a, b;
+    if (in >> a >> b) { g = a; c = b; any = true; }
+    else if (!any) break;            // no pair at all: the reference would use uninitialised indices
+    gi.push_back(g);
+    ci.push_back(c);
+  }
+  model_set_clustering(hm, n, gi.data(), ci.data(), (int64_t)gi.size());
+}
+
 void model_read_files(const std::string &gk_path, const std::string &mc_path, const std::string &ph_path, HostModel &hm)
 {
+  hm.clear_clustering();
   // --- .mc ---
   std::vector<std::vector<int32_t>> mc_idx;
   std::vector<std::vector<double>> mc_w;
@@ -209,6 +280,38 @@ static void upload(DevBuf &b, const std::vector<T> &v, cudaStream_t st)
 
 // The tensor-core scorer is the default throughput kernel (variant 0 or 3) for pools that are all diagonal or all
 // full with at most 64 components per state; variants 1/2 force the FP32-pipe kernel.
+// Device image of the clustering: the centres as a pool of one-component states for gmm_diag_f64, cluster ids, sizes.
+void model_pack_clustering(akugpu_ctx *ctx)
+{
+  const HostModel &hm = ctx->hm;
+  PackedF64 &p = ctx->p64;
+  const int C = hm.n_clusters, D = hm.D;
+  if (C <= 0) return;
+  std::vector<double> prec((size_t)C * D), cst(C), w(C, 1.0);
+  std::vector<int32_t> off(C + 1), idx(C), sz(C);
+  for (int c = 0; c < C; c++) {
+    double k = 1;
+    for (int d = 0; d < D; d++) {
+      const double cv = hm.c_cov[(size_t)c * D + d], pr = cv > 0 ? 1 / cv : 0;
+      prec[(size_t)c * D + d] = pr;
+      k *= pr;
+    }
+    if (k > 0) k = log(sqrt(k));
+    cst[c] = k;
+    off[c] = c; idx[c] = c; sz[c] = (int32_t)hm.cluster_gauss[c].size();
+  }
+  off[C] = C;
+  upload(p.c_mean, hm.c_mean, ctx->stream);
+  upload(p.c_prec, prec, ctx->stream);
+  upload(p.c_cst, cst, ctx->stream);
+  upload(p.c_mix_off, off, ctx->stream);
+  upload(p.c_mix_gauss, idx, ctx->stream);
+  upload(p.c_mix_w, w, ctx->stream);
+  upload(p.g2c, hm.gauss_cluster, ctx->stream);
+  upload(p.c_size, sz, ctx->stream);
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 static bool tc_wanted(akugpu_ctx *ctx)
 {
   const HostModel &hm = ctx->hm;

@@ -193,6 +193,25 @@ class AkuGpu:
         self._ck(self._lib.akugpu_model_load_full(self._h, len(mo) - 1, mu.shape[0], mu.shape[1], _ptr(mo), _ptr(mg),
                                                   _ptr(mw), _ptr(mu), _ptr(cv)))
 
+    # ---- Gaussian clustering (phone_probs -C / --eval-minc / --eval-ming) ----
+    def read_clustering(self, path):
+        """HmmSet::read_clustering (aku/HmmSet.cc:1354)."""
+        self._ck(self._lib.akugpu_model_read_clustering(self._h, str(path).encode()))
+
+    def set_clustering(self, n_clusters, gauss_index, cluster_index):
+        gi = np.ascontiguousarray(gauss_index, dtype=np.int32)
+        ci = np.ascontiguousarray(cluster_index, dtype=np.int32)
+        if gi.shape != ci.shape:
+            raise ValueError("gauss_index / cluster_index must have the same length")
+        self._ck(self._lib.akugpu_model_set_clustering(self._h, int(n_clusters), _ptr(gi), _ptr(ci), gi.size))
+
+    def set_clustering_min_evals(self, min_clusters=1.0, min_gaussians=1.0):
+        """HmmSet::set_clustering_min_evals (aku/HmmSet.cc:1360): switches the approximation on."""
+        self._ck(self._lib.akugpu_model_set_clustering_min_evals(self._h, float(min_clusters), float(min_gaussians)))
+
+    def use_clustering(self, on=True):
+        self._ck(self._lib.akugpu_model_use_clustering(self._h, 1 if on else 0))
+
     @property
     def num_states(self):
         return self._lib.akugpu_model_num_states(self._h)

@@ -111,6 +111,13 @@ class HmmSet:
     def dim(self):
         return self.engine.model_dim
 
+    # Gaussian clustering approximation (aku/HmmSet.cc:1354-1366)
+    def read_clustering(self, filename):
+        self.engine.read_clustering(filename)
+
+    def set_clustering_min_evals(self, min_clusters=1.0, min_gaussians=1.0):
+        self.engine.set_clustering_min_evals(min_clusters, min_gaussians)
+
     # Whole-utterance entry: score every frame once, then serve the per-frame API from it.
     def set_utterance_features(self, feats):
         feats = np.ascontiguousarray(feats)

@@ -118,6 +118,22 @@ int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim,
 int akugpu_model_load_full(akugpu_ctx *ctx, int n_states, int n_gauss, int dim,
                            const int32_t *mix_offsets, const int32_t *mix_gauss,
                            const double *mix_weight, const double *means, const double *full_covs);
+/* Gaussian clustering approximation (phone_probs -C file.gcl --eval-minc x --eval-ming y, aku/phone_probs.cc:73-75,112-117):
+ * per frame the cluster centres are scored, the Gaussians of the best clusters are evaluated exactly until both minima are
+ * reached, the others take their centre's likelihood (PDFPool::precompute_likelihoods, aku/Distributions.cc:2685-2722).
+ *   akugpu_model_read_clustering           HmmSet::read_clustering (aku/HmmSet.cc:1354, aku/Distributions.cc:3115-3170):
+ *                                          `n_clusters` then `gauss_index cluster_index` pairs; centres by moment matching
+ *   akugpu_model_set_clustering            the same from memory (pairs exactly as they would be read)
+ *   akugpu_model_set_clustering_min_evals  HmmSet::set_clustering_min_evals (aku/HmmSet.cc:1360): ratios of clusters /
+ *                                          Gaussians; switches the approximation on
+ *   akugpu_model_use_clustering            PDFPool::set_use_clustering
+ * While it is on, scoring runs in the double path whatever precision is requested (diagonal pools only); loading a
+ * model clears it. */
+int akugpu_model_read_clustering(akugpu_ctx *ctx, const char *gcl_path);
+int akugpu_model_set_clustering(akugpu_ctx *ctx, int n_clusters, const int32_t *gauss_index,
+                                const int32_t *cluster_index, int64_t n_pairs);
+int akugpu_model_set_clustering_min_evals(akugpu_ctx *ctx, double min_clusters, double min_gaussians);
+int akugpu_model_use_clustering(akugpu_ctx *ctx, int on);
 int akugpu_model_num_states(akugpu_ctx *ctx);   /* HmmSet::num_states()  */
 int akugpu_model_dim(akugpu_ctx *ctx);          /* HmmSet::dim()         */
 int akugpu_model_num_gaussians(akugpu_ctx *ctx);

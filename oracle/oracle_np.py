@@ -447,9 +447,68 @@ def gaussian_params(means, covs):
     return prec, cst
 
 
-def state_likelihoods(model, feats, block=256):
+def parse_clustering(text):
+    """PDFPool::read_clustering (aku/Distributions.cc:3115-3147): cluster count, then `gauss cluster` pairs read in a
+    `while (in) { in >> g >> c; ... }` loop -- after the last pair the stream is still good, the next extraction
+    fails without touching g and c, and the last pair is recorded once more.  Returns (n_clusters, gauss[], cluster[])."""
+    tok = text.split()
+    n = int(tok[0])
+    vals = [int(t) for t in tok[1:]]
+    gi, ci = vals[0::2], vals[1::2]
+    if len(gi) > len(ci):
+        gi = gi[:len(ci)]
+    if gi:
+        gi.append(gi[-1])
+        ci.append(ci[-1])
+    return n, np.array(gi, dtype=np.int32), np.array(ci, dtype=np.int32)
+
+
+def cluster_centers(model, n_clusters, gauss, cluster):
+    """Centres by moment matching with unit weights, diagonal kept: Gaussian::merge (aku/Distributions.cc:854-897) +
+    DiagonalGaussian::set_covariance (:1208-1234), operations in the reference's order.  Returns (means, covs, members)."""
+    mu = np.asarray(model["means"], dtype=np.float64)
+    cv = np.asarray(model["covs"], dtype=np.float64)
+    D = mu.shape[1]
+    members = [[] for _ in range(n_clusters)]
+    for g, c in zip(gauss, cluster):
+        members[int(c)].append(int(g))
+    cm = np.zeros((n_clusters, D))
+    cc = np.zeros((n_clusters, D))
+    for c, L in enumerate(members):
+        wsum = 0.0
+        for _ in L:
+            wsum += 1.0
+        for g in L:
+            cur = cv[g] + mu[g] * mu[g]
+            cc[c] = cc[c] + 1.0 * cur
+            cm[c] = cm[c] + 1.0 * mu[g]
+        r = 1.0 / wsum
+        cm[c] = cm[c] * r
+        cc[c] = cc[c] * r
+        cc[c] = cc[c] + (-1.0 * cm[c]) * cm[c]
+    return cm, cc, members
+
+
+def _diag_loglik(x, mu, prec, cst):
+    ll = np.zeros((x.shape[0], mu.shape[0]))
+    for i in range(x.shape[1]):         # ll += d*d*prec, left to right (:1052-1056)
+        d = x[:, i:i + 1] - mu[None, :, i]
+        ll += d * d * prec[None, :, i]
+    ll *= -0.5
+    ll += cst[None, :]
+    return ll
+
+
+def state_likelihoods(model, feats, block=256, clustering=None):
     """HmmSet::precompute_likelihoods (aku/HmmSet.cc:485-501) for every frame: linear state
-    likelihoods floored at 1e-50.  Sums run in the reference's order (dims then components)."""
+    likelihoods floored at 1e-50.  Sums run in the reference's order (dims then components).
+    clustering = dict(n_clusters, gauss, cluster, min_clusters, min_gaussians) (the two ratios of
+    HmmSet::set_clustering_min_evals) switches on the clustered branch of PDFPool::precompute_likelihoods
+    (aku/Distributions.cc:2685-2722): clusters in descending order of their centre's likelihood (the reference pops a
+    std::priority_queue; ties here go to the lower index), members of the leading clusters evaluated exactly while
+    (clusters < min) or (Gaussians < min), the rest take the centre's likelihood -- and, because
+    PDFPool::compute_likelihood (:2637-2644) only trusts cached values > 0, a centre likelihood of 0 means the Gaussian is
+    evaluated exactly after all."""
     feats = np.asarray(feats, dtype=np.float64)
     mu = np.asarray(model["means"], dtype=np.float64)
     prec, cst = gaussian_params(mu, model["covs"])
@@ -465,6 +524,16 @@ def state_likelihoods(model, feats, block=256):
     F, D = feats.shape
     out = np.empty((F, S))
     full_cache = {}
+    if clustering is not None:
+        C = int(clustering["n_clusters"])
+        cm, cc, members = cluster_centers(model, C, clustering["gauss"], clustering["cluster"])
+        cprec, ccst = gaussian_params(cm, cc)
+        csize = np.array([len(L) for L in members])
+        g2c = np.full(mu.shape[0], -1)
+        for c, L in enumerate(members):
+            g2c[L] = c
+        min_c = int(clustering["min_clusters"] * C)
+        min_g = int(clustering["min_gaussians"] * mu.shape[0])
     for f0 in range(0, F, block):
         x = feats[f0:f0 + block]
         ll = np.zeros((x.shape[0], mu.shape[0]))
@@ -482,6 +551,20 @@ def state_likelihoods(model, feats, block=256):
                     dot += phi[:, l] * th[l]
                 ll[:, g] = (dot + nrm) + c
         lik = _exp(ll).astype(np.float64)   # DiagonalGaussian::compute_likelihood (:1036)
+        if clustering is not None:
+            clik = _exp(_diag_loglik(x, cm, cprec, ccst)).astype(np.float64)
+            for t in range(x.shape[0]):
+                order = sorted(range(C), key=lambda c: (-clik[t, c], c))
+                sel = np.zeros(C, dtype=bool)
+                n_c = n_g = 0
+                for c in order:
+                    if not (n_c < min_c or n_g < min_g):
+                        break
+                    sel[c] = True
+                    n_c += 1
+                    n_g += csize[c]
+                use_centre = (g2c >= 0) & ~sel[np.maximum(g2c, 0)] & (clik[t, np.maximum(g2c, 0)] > 0)
+                lik[t, use_centre] = clik[t, g2c[use_centre]]
         for s in range(S):              # Mixture::compute_likelihood (:2079-2086)
             acc = np.zeros(x.shape[0])
             for k in range(off[s], off[s + 1]):

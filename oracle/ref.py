@@ -37,6 +37,8 @@ def lib():
             getattr(_lib, f).argtypes = [C.c_void_p]
         _lib.ref_state_likelihoods.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]
         _lib.ref_gaussian_loglik.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]
+        _lib.ref_model_read_clustering.argtypes = [C.c_void_p, C.c_char_p]
+        _lib.ref_model_set_clustering_min_evals.argtypes = [C.c_void_p, C.c_double, C.c_double]
     return _lib
 
 
@@ -92,6 +94,14 @@ class Model:
         if lib().ref_state_likelihoods(self.h, feats.ctypes.data, feats.shape[0], feats.shape[1], out.ctypes.data):
             raise _err()
         return out
+
+    def read_clustering(self, path):
+        if lib().ref_model_read_clustering(self.h, path.encode()):
+            raise _err()
+
+    def set_clustering_min_evals(self, min_clusters, min_gaussians):
+        if lib().ref_model_set_clustering_min_evals(self.h, float(min_clusters), float(min_gaussians)):
+            raise _err()
 
     def gaussian_loglik(self, feats):
         feats = np.ascontiguousarray(feats, dtype=np.float64)

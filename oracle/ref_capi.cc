@@ -95,6 +95,20 @@ int ref_model_num_states(void *h) { return ((RefModel *)h)->model.num_states(); 
 int ref_model_dim(void *h) { return ((RefModel *)h)->model.dim(); }
 int ref_model_num_gaussians(void *h) { return ((RefModel *)h)->model.get_pool()->size(); }
 
+// Gaussian clustering approximation: HmmSet::read_clustering + set_clustering_min_evals (aku/HmmSet.cc:1354-1366).
+int ref_model_read_clustering(void *h, const char *path)
+{
+  try { ((RefModel *)h)->model.read_clustering(path); return 0; }
+  catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+int ref_model_set_clustering_min_evals(void *h, double min_clusters, double min_gaussians)
+{
+  try { ((RefModel *)h)->model.set_clustering_min_evals(min_clusters, min_gaussians); return 0; }
+  catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
 // Linear state likelihoods (double, floored at 1e-50 by the reference) for F frames.
 int ref_state_likelihoods(void *h, const double *feats, long F, int D, double *out /*[F*S]*/)
 {

@@ -39,6 +39,13 @@ def ref_full():
 
 
 @pytest.fixture(scope="session")
+def ref_clust():
+    d = load_golden("ref_clust")
+    d["gcl"] = str(d["gcl"])
+    return d
+
+
+@pytest.fixture(scope="session")
 def aku_tests():
     z = np.load(os.path.join(GOLDEN, "aku_tests.npz"))
     return {k: (str(z[k]) if k.endswith("_cfg") else z[k]) for k in z.files}

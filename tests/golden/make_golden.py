@@ -13,6 +13,9 @@ Run in the dev container (needs /root/reference and oracle/_ref built by oracle/
                   and the LNA files written by the literal aku/phone_probs.cc (2 and 4 bytes,
                   with and without normalisation).
   ref_full.npz    the same for a mixed diagonal / full-covariance pool (FullCovarianceGaussian, exponential form)
+  ref_clust.npz   the Gaussian-clustering approximation (phone_probs -C x.gcl --eval-minc/--eval-ming) on the ref_small
+                  model: .gcl text (12 clusters, three Gaussians left unlisted), state likelihoods of the reference's
+                  HmmSet for three (min_clusters, min_gaussians) settings, and the LNA files of the literal phone_probs.
   ref_edge.npz    the same for a handmade edge-case model (underflow / denormal / floor regimes,
                   zero-variance dimensions, tiny weights).
 """
@@ -140,6 +143,52 @@ def run_case(name, pcm, model, tmp):
     print(name, "frames", feats.shape, "states", lik.shape[1], "loglik range", np.log(lik).min(), np.log(lik).max())
 
 
+def clust_case(pcm, model, tmp):
+    """Clustering fixture on the ref_small inputs."""
+    name = "ref_clust"
+    rng = np.random.default_rng(7004)
+    wav = os.path.join(tmp, name + ".wav"); cfg = os.path.join(tmp, name + ".cfg"); base = os.path.join(tmp, name)
+    formats.write_wav(wav, pcm, 16000)
+    open(cfg, "w").write(synth.mfcc39_config())
+    formats.write_model(base, **model)
+    feats, _, _ = ref.features(cfg, wav)
+    G, C = model["means"].shape[0], 12
+    sd = feats.std(axis=0)
+    seeds = model["means"][rng.choice(G, C, replace=False)]
+    assign = np.argmin((((model["means"][:, None, :] - seeds[None]) / sd) ** 2).sum(axis=2), axis=1)
+    listed = np.ones(G, dtype=bool)
+    listed[rng.choice(G, 3, replace=False)] = False
+    order = rng.permutation(np.nonzero(listed)[0])
+    gcl = "%d\n" % C + "".join("%d %d\n" % (g, assign[g]) for g in order)
+    gpath = os.path.join(tmp, name + ".gcl")
+    open(gpath, "w").write(gcl)
+    gpath2 = os.path.join(tmp, name + "_nonl.gcl")
+    open(gpath2, "w").write(gcl.rstrip("\n"))               # no trailing newline: same pairs, same EOF behaviour
+    settings = [(0.0, 0.25), (0.3, 0.1), (0.0, 0.1)]
+    out = dict(gcl=gcl, settings=np.array(settings), feats=feats, **{"model_" + k: v for k, v in model.items()})
+    for k, (mc, mg) in enumerate(settings):
+        M = ref.Model(base)
+        M.read_clustering(gpath if k != 1 else gpath2)
+        M.set_clustering_min_evals(mc, mg)
+        out["lik%d" % k] = M.state_likelihoods(feats)
+        M.close()
+    rec = os.path.join(tmp, name + ".recipe")
+    open(rec, "w").write("audio=%s lna=%s.lna\n" % (wav, name))
+    for nb in (2, 4):
+        od = os.path.join(tmp, "c%d" % nb)
+        os.makedirs(od, exist_ok=True)
+        ref.phone_probs(cfg, base, rec, od, nb, extra=["-C", gpath, "--eval-ming=0.25"])
+        out["lna%d" % nb] = np.frombuffer(open(os.path.join(od, name + ".lna"), "rb").read(), dtype=np.uint8)
+    M = ref.Model(base)
+    exact = M.state_likelihoods(feats)
+    M.close()
+    out["lik_exact"] = exact
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "frames", feats.shape[0], "G", G, "C", C,
+          "states differing from exact evaluation: %.1f%% / %.1f%% / %.1f%%" % tuple(
+              100 * (out["lik%d" % k] != exact).mean() for k in range(3)))
+
+
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
@@ -151,6 +200,7 @@ def main():
         open(cfg, "w").write(synth.mfcc39_config())
         feats, _, _ = ref.features(cfg, wav)
         run_case("ref_small", pcm, small_model(feats, 7002), tmp)
+        clust_case(pcm, small_model(feats, 7002), tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
         run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 

@@ -114,3 +114,38 @@ def test_cpp_tool_flags(engine, ref_small, tmp_path):
     assert r.returncode != 0 and b"Invalid number of bytes" in r.stderr
     r = run("-g", base + ".gk", "-m", base + ".mc", "-p", base + ".ph", "-c", cfg, "-r", rec, "-o", str(out), "-a")
     assert r.returncode == 0
+
+
+def test_cpp_tool_gaussian_clustering(engine, ref_clust, tmp_path):
+    """akugpu_phone_probs -C x.gcl --eval-ming=0.25 writes the bytes the literal aku/phone_probs.cc wrote with the same
+    flags, when fed the reference's features' audio is replaced by the parity path (f64) on the same WAV: the feature
+    front-ends differ by ~1e-6, so codes are held to +-1; the GMM stage itself is checked byte-exactly in
+    test_gpu_parity.py::test_gaussian_clustering_parity."""
+    from aaltoasr_b200 import synth
+    g = ref_clust
+    cfg = str(tmp_path / "mfcc.cfg")
+    open(cfg, "w").write(synth.mfcc39_config())
+    base = str(tmp_path / "model")
+    formats.write_model(base, **g["model"])
+    gcl = str(tmp_path / "c.gcl")
+    open(gcl, "w").write(g["gcl"])
+    w = str(tmp_path / "utt0.wav")
+    formats.write_wav(w, synth.synth_audio(7001, 24000), 16000)
+    rec = str(tmp_path / "recipe")
+    open(rec, "w").write("audio=%s lna=utt0.lna\n" % w)
+    out = tmp_path / "o"; out.mkdir()
+    r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-C", gcl, "--eval-ming=0.25", "--precision=f64"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    got = np.frombuffer(open(str(out / "utt0.lna"), "rb").read(), dtype=np.uint8)
+    want = g["lna2"]
+    assert bytes(got[:5]) == bytes(want[:5]) and got.size == want.size
+    d = np.abs(got[5:].view(">u2").astype(int) - want[5:].view(">u2").astype(int))
+    assert d.max() <= 1 and (d != 0).mean() <= 0.03, (d.max(), (d != 0).mean())
+    # and it differs from the exact evaluation (the flag is not ignored)
+    out2 = tmp_path / "o2"; out2.mkdir()
+    r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out2), "--precision=f64"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0
+    exact = np.frombuffer(open(str(out2 / "utt0.lna"), "rb").read(), dtype=np.uint8)
+    assert (exact != got).mean() > 0.2

@@ -208,6 +208,42 @@ def test_lna_row_kernel_identical_to_column_kernel(engine, case, request, monkey
             assert np.array_equal(new, old), (case, nb, normalize, (new != old).mean())
 
 
+def test_gaussian_clustering_parity(engine, ref_clust, tmp_path):
+    """phone_probs -C x.gcl --eval-minc/--eval-ming (section 8f-1): state likelihoods within CUDA-exp ulps of the
+    reference's HmmSet for three settings, LNA bytes identical to the literal phone_probs output; the .gcl reader
+    (file) and the in-memory loader agree; throughput-mode requests are served by the same double path."""
+    g = ref_clust
+    load_model(engine, g["model"])
+    gpath = str(tmp_path / "c.gcl")
+    open(gpath, "w").write(g["gcl"])
+    n, gi, ci = oracle_np.parse_clustering(g["gcl"])
+    for k, (mc, mg) in enumerate(g["settings"]):
+        if k % 2 == 0:
+            engine.read_clustering(gpath)
+        else:
+            engine.set_clustering(n, gi, ci)
+        engine.set_clustering_min_evals(mc, mg)
+        lik = engine.gmm_score(g["feats"], precision=F64)
+        want = g["lik%d" % k]
+        rel = np.abs(lik - want) / want
+        assert rel.max() <= 4.5e-16, (k, rel.max())
+    engine.read_clustering(gpath)
+    engine.set_clustering_min_evals(0.0, 0.25)
+    for nb in (2, 4):
+        want = g["lna%d" % nb]
+        for prec in (F64, F32):
+            rec = engine.gmm_lna(g["feats"], precision=prec, lnabytes=nb)
+            assert np.array_equal(rec.reshape(-1), want[5:]), (nb, prec, (rec.reshape(-1) != want[5:]).sum())
+    # switched off: exact evaluation again
+    engine.use_clustering(False)
+    lik = engine.gmm_score(g["feats"], precision=F64)
+    assert (np.abs(lik - g["lik_exact"]) / g["lik_exact"]).max() <= 4.5e-16
+    with pytest.raises(AkuGpuError, match="seems insensible"):
+        engine.set_clustering(60, gi, ci)
+    load_model(engine, g["model"])          # loading a model clears the clustering
+    assert (np.abs(engine.gmm_score(g["feats"], precision=F64) - g["lik_exact"]) / g["lik_exact"]).max() <= 4.5e-16
+
+
 def test_fp16_range_fallback(engine, ref_small):
     """A feature far outside the fp16 range of the default scorer's scaled terms makes the call fall back to the
     bf16x3 kernel: results stay finite and the other frames are unchanged."""

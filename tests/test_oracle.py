@@ -66,6 +66,26 @@ def test_features_vs_reference(case, request):
         assert np.abs(got - g["mod_" + mod]).max() <= tol, mod
 
 
+def test_gaussian_clustering_bit_exact_vs_reference(ref_clust):
+    """Clustered branch of PDFPool::precompute_likelihoods (phone_probs -C --eval-minc --eval-ming): the restatement
+    equals the reference's HmmSet bit for bit for three settings (incl. the reader's repeated last pair and the
+    unlisted Gaussians), and the LNA bytes equal the literal phone_probs -C x.gcl --eval-ming=0.25 output."""
+    g = ref_clust
+    n, gi, ci = oracle_np.parse_clustering(g["gcl"])
+    assert n == 12 and gi[-1] == gi[-2] and ci[-1] == ci[-2]
+    for k, (mc, mg) in enumerate(g["settings"]):
+        cl = dict(n_clusters=n, gauss=gi, cluster=ci, min_clusters=mc, min_gaussians=mg)
+        lik = oracle_np.state_likelihoods(g["model"], g["feats"], clustering=cl)
+        assert np.array_equal(lik, g["lik%d" % k]), k
+        assert (lik != g["lik_exact"]).mean() > 0.5          # the approximation really is one
+    for nb in (2, 4):
+        rec, _ = oracle_np.lna_records(g["lik0"], nb)
+        assert np.array_equal(rec.reshape(-1), g["lna%d" % nb][5:])
+    # without the repeated last pair the centres and the Gaussian budget differ
+    cl = dict(n_clusters=n, gauss=gi[:-1], cluster=ci[:-1], min_clusters=0.0, min_gaussians=0.25)
+    assert not np.array_equal(oracle_np.state_likelihoods(g["model"], g["feats"], clustering=cl), g["lik0"])
+
+
 @pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
 def test_gmm_lna_bit_exact_vs_reference(case, request):
     """State likelihoods equal the reference's doubles bit for bit; LNA bytes equal the files the
