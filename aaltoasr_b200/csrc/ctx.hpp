@@ -173,7 +173,7 @@ struct Module {
   // mean_subtractor: left/right hold the +1-extended offsets, width = left+right-1
   int ms_width = 0;
   // device copies of parameters
-  std::shared_ptr<DevBuf> d_a, d_b;
+  std::shared_ptr<DevBuf> d_a, d_b, d_c;
   // extended frame range this module must be evaluated on for an utterance:
   // [-ext_left, n_frames-1+ext_right]
   int ext_left = 0, ext_right = 0;

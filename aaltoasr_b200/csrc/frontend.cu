@@ -197,7 +197,42 @@ void upload_module_params(akugpu_ctx *ctx, Module &m, const std::vector<Module> 
       m.d_b = upload_vec(tw, st);
       break;
     }
-    case M_MEL: m.d_a = upload_vec(m.bin_edges, st); break;
+    case M_MEL: {
+      // Triangle weights and their sums, tap by tap in the reference's float arithmetic (MelModule::generate,
+      // aku/FeatureModules.cc:809-843: scale = (t - beg) / (end - beg) rising, (end - t) / (end - beg) falling; the
+      // host's SSE float operations round exactly like the device's __f*_rn), so that the kernels do not divide.
+      // d_a: float scales in tap order; d_b: int {first spectrum bin, taps, offset into d_a} per mel bin; d_c: float sums.
+      std::vector<float> scales, sums;
+      std::vector<int> desc;
+      for (int b = 0; b < m.dim; b++) {
+        float sum = 0, scale;
+        float beg = m.bin_edges[b] - 1.f;
+        float end = m.bin_edges[b + 1];
+        int t = (int)fmaxf(ceilf(beg), 0.0f);
+        const int t0 = t, off = (int)scales.size();
+        while (t < end) {
+          scale = ((float)t - beg) / (end - beg);
+          scales.push_back(scale);
+          sum = sum + scale;
+          t++;
+        }
+        beg = end;
+        end = m.bin_edges[b + 2];
+        while (t < end) {
+          scale = (end - (float)t) / (end - beg);
+          scales.push_back(scale);
+          sum = sum + scale;
+          t++;
+        }
+        desc.push_back(t0); desc.push_back(t - t0); desc.push_back(off);
+        sums.push_back(sum);
+      }
+      if (scales.empty()) scales.push_back(0.f);
+      m.d_a = upload_vec(scales, st);
+      m.d_b = upload_vec(desc, st);
+      m.d_c = upload_vec(sums, st);
+      break;
+    }
     case M_DCT: {
       const int sd = mods[m.src[0]].dim;
       const int bias = m.zeroth ? 1 : 0;
@@ -409,6 +444,36 @@ __device__ __forceinline__ void row_to_frame(const int *__restrict__ row_utt, co
   t = utts[u].start - H + (int)(r - utts[u].row_off);
 }
 
+// MelModule::generate, aku/FeatureModules.cc:806-849, one bin from the precomputed triangle weights (see
+// upload_module_params).  SRC yields the spectrum value as a double.
+struct MelTable { const float *scale; const int *desc; const float *sum; };
+template <class SRC>
+__device__ __forceinline__ double mel_bin(SRC data, int sdim, const MelTable mt, int b, int root)
+{
+  const int t0 = mt.desc[3 * b], n = mt.desc[3 * b + 1];
+  const float *sc = mt.scale + mt.desc[3 * b + 2];
+  float val = 0;
+  for (int i = 0; i < n; i++)       // float accumulator fed through a double product, as the reference's `val += scale * data`
+    val = (float)__dadd_rn((double)val, __dmul_rn((double)sc[i], data(min(t0 + i, sdim - 1))));
+  const float sum = mt.sum[b];
+  if (root) return pow((double)__fdiv_rn(val, sum), 0.1);
+  return (double)logf(__fadd_rn(__fdiv_rn(val, sum), 1.f));
+}
+
+// Fused path fft -> {mel -> dct, power} -> merge (the static part of an MFCC chain): instead of a spectrum matrix the
+// FFT kernel keeps the frame's spectrum in shared memory and writes the merged row (dct columns + power column).
+struct FuseStatic {
+  int on = 0;
+  int mel_dim = 0, mel_root = 0;
+  MelTable mel = {nullptr, nullptr, nullptr};
+  int dct_dim = 0, dct_col = 0;
+  const float *dct_table = nullptr;
+  int pow_col = -1;            // -1: no power module
+  int odim = 0;
+  double *out = nullptr;       // [rows][odim]
+};
+constexpr int FUSE_MAX_MEL = 64;
+
 // audiofile + fft for windows of 2^k or 3 * 2^k samples (16 kHz -> 256, 48 kHz -> 768, ...).  One CTA = FPB frames;
 // the real signal is packed even/odd into an M = N/2-point complex FFT in shared memory: R = 1 or 3 interleaved
 // radix-2 DIT sub-transforms of P = M/R points, one radix-3 combination pass when R = 3, then the real-FFT split.
@@ -416,7 +481,7 @@ template <int N>
 __global__ void __launch_bounds__(256)
 fe_spectrum_fft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
                 int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
-                const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out)
+                const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out, const FuseStatic fuse)
 {
   constexpr int M = N / 2;                 // complex FFT size
   constexpr int R = (N % 3 == 0) ? 3 : 1;  // odd radix
@@ -487,7 +552,9 @@ fe_spectrum_fft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utt
     __syncthreads();
   }
   // split: X[k] = (Z[k]+conj(Z[M-k]))/2 - i e^{-2 pi i k/N} (Z[k]-conj(Z[M-k]))/2 ,  k = 0..M
-  if (valid) {
+  __shared__ float pw[FPB][M + 2];         // fused path: the frame's spectrum stays on chip
+  __shared__ double melv[FPB][FUSE_MAX_MEL];
+  {
     double *o = out + r * (M + 1);
     for (int k = tl; k <= M; k += TPF) {
       float2 a = z[fl][k == M ? 0 : k], b = z[fl][k == 0 ? 0 : M - k];
@@ -500,9 +567,68 @@ fe_spectrum_fft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utt
       float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));       // float power (:534-537)
       if (magnitude) p = sqrtf(p);
       if (do_log) p = logf(p);
-      o[k] = (double)p;
+      if (fuse.on) pw[fl][k] = p;
+      else if (valid) o[k] = (double)p;
     }
   }
+  if (!fuse.on) return;
+  __syncthreads();
+  // mel bins (one thread each) next to the power sum (one thread): the operations of fe_mel / fe_power on the
+  // on-chip spectrum.  power: float(double(p) + double(s)) of two floats is the fp32 sum (the double sum is exact or
+  // the smaller term is below a quarter ulp), so the float accumulator of PowerModule (:875-885) is a chain of FADDs.
+  {
+    const float *sp = pw[fl];
+    if (tl < fuse.mel_dim)
+      melv[fl][tl] = mel_bin([sp](int t) { return (double)sp[t]; }, M + 1, fuse.mel, tl, fuse.mel_root);
+  }
+  if (fuse.pow_col >= 0 && threadIdx.x < FPB) {           // the FPB power sums share warp 0
+    const float *sp = pw[threadIdx.x];
+    const int64_t rr = (int64_t)blockIdx.x * FPB + threadIdx.x;
+    float power = 0;
+    for (int i = 0; i <= M; i++) power = __fadd_rn(power, sp[i]);
+    if (rr < n_rows) fuse.out[rr * fuse.odim + fuse.pow_col] = log(__dadd_rn((double)power, 1e-10));
+  }
+  __syncthreads();
+  if (valid && tl < fuse.dct_dim) {                       // DCTModule::generate (:956-979)
+    const float *tb = fuse.dct_table + (size_t)tl * fuse.mel_dim;
+    double acc = 0.0;
+    for (int b = 0; b < fuse.mel_dim; b++) acc = __dadd_rn(acc, __dmul_rn(melv[fl][b], (double)tb[b]));
+    fuse.out[r * fuse.odim + fuse.dct_col + tl] = acc;
+  }
+}
+
+// Fused tail  X -> delta -> delta -> merge(X, d1, d2) -> output rows without the halo (DeltaModule::generate :1019-1037
+// applied twice, MergerModule :1352-1364): one thread per (output row, column of X); the same operations in the same
+// order as the per-module kernels, the intermediate rows recomputed instead of stored.
+constexpr int FUSE_MAX_WIDTH = 4;
+template <class T>
+__global__ void fe_delta2_merge(const double *__restrict__ src, int dim, int64_t n_rows, const UttDesc *__restrict__ utts,
+                                const int *__restrict__ row_utt, int H, int w1, float norm1, int w2, float norm2,
+                                T *__restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  const int64_t r = i / dim;                               // row in the haloed matrices
+  const int c = (int)(i - r * dim);
+  const UttDesc ud = utts[row_utt[r]];
+  const int64_t k = r - ud.row_off - H;                    // frame within the utterance's output
+  if (k < 0 || k >= ud.n_rows_out) return;                 // halo rows only feed their neighbours
+  const int64_t q = ud.out_off + k;
+  const double *x = src + r * dim + c;
+  double d1[2 * FUSE_MAX_WIDTH + 1];
+  for (int j = -w2; j <= w2; j++) {
+    double acc = 0;
+    for (int kk = 1; kk <= w1; kk++)
+      acc = __dadd_rn(acc, __dmul_rn((double)kk, __dsub_rn(x[(int64_t)(j + kk) * dim], x[(int64_t)(j - kk) * dim])));
+    d1[j + FUSE_MAX_WIDTH] = __ddiv_rn(acc, (double)norm1);
+  }
+  double acc = 0;
+  for (int kk = 1; kk <= w2; kk++)
+    acc = __dadd_rn(acc, __dmul_rn((double)kk, __dsub_rn(d1[kk + FUSE_MAX_WIDTH], d1[-kk + FUSE_MAX_WIDTH])));
+  T *o = out + q * (3 * dim);
+  o[c] = (T)x[0];
+  o[dim + c] = (T)d1[FUSE_MAX_WIDTH];
+  o[2 * dim + c] = (T)__ddiv_rn(acc, (double)norm2);
 }
 
 // Generic window length: direct DFT with the twiddle table (O(N^2); correctness path for the
@@ -548,7 +674,7 @@ fe_spectrum_dft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utt
 }
 
 // MelModule::generate, aku/FeatureModules.cc:806-849; one thread per (row, bin).
-__global__ void fe_mel(const double *__restrict__ src, int sdim, int64_t n_rows, const float *__restrict__ edges, int dim,
+__global__ void fe_mel(const double *__restrict__ src, int sdim, int64_t n_rows, const MelTable mt, int dim,
                        int root, double *__restrict__ out)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -556,28 +682,7 @@ __global__ void fe_mel(const double *__restrict__ src, int sdim, int64_t n_rows,
   int64_t r = i / dim;
   int b = (int)(i - r * dim);
   const double *data = src + r * sdim;
-  float val = 0, sum = 0, scale;
-  float beg = __fsub_rn(edges[b], 1.f);
-  float end = edges[b + 1];
-  int t = (int)fmaxf(ceilf(beg), 0.0f);
-  while (t < end) {
-    scale = __fdiv_rn(__fsub_rn((float)t, beg), __fsub_rn(end, beg));
-    val = (float)__dadd_rn((double)val, __dmul_rn((double)scale, data[min(t, sdim - 1)]));
-    sum = __fadd_rn(sum, scale);
-    t++;
-  }
-  beg = end;
-  end = edges[b + 2];
-  while (t < end) {
-    scale = __fdiv_rn(__fsub_rn(end, (float)t), __fsub_rn(end, beg));
-    val = (float)__dadd_rn((double)val, __dmul_rn((double)scale, data[min(t, sdim - 1)]));
-    sum = __fadd_rn(sum, scale);
-    t++;
-  }
-  double o;
-  if (root) o = pow((double)__fdiv_rn(val, sum), 0.1);
-  else o = (double)logf(__fadd_rn(__fdiv_rn(val, sum), 1.f));
-  out[r * dim + b] = o;
+  out[r * dim + b] = mel_bin([data](int t) { return data[t]; }, sdim, mt, b, root);
 }
 
 // PowerModule (:875-885) and MelPowerModule (:908-919); one thread per row, float accumulator.
@@ -587,7 +692,7 @@ __global__ void fe_power(const double *__restrict__ src, int sdim, int64_t n_row
   if (r >= n_rows) return;
   const double *s = src + r * sdim;
   float power = 0;
-  for (int i = 0; i < sdim; i++) power = (float)__dadd_rn((double)power, use_exp ? exp(s[i]) : s[i]);
+  for (int i = 0; i < sdim; i++) power = (float)__dadd_rn((double)power, use_exp ? exp(s[i]) : s[i]);   // double(float)+double: see fe_spectrum_fft
   out[r] = log(__dadd_rn((double)power, 1e-10));
 }
 
@@ -766,21 +871,75 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
   const UttDesc *du = d_utts.as<UttDesc>();
   const int *dr = d_rowutt.as<int>();
 
-  // one buffer per needed module (the base module is fused into fft and has none)
-  std::vector<std::shared_ptr<DevBuf>> buf(fe.mods.size());
+  // ---- fusion patterns (the canonical MFCC chain); anything else runs module by module ----
+  const int nm = (int)fe.mods.size();
+  std::vector<std::vector<int>> cons(nm);
+  for (int m = 1; m <= target; m++)
+    if (plan.needed[m]) for (int sidx : fe.mods[m].src) cons[sidx].push_back(m);
+  std::vector<char> skip(nm, 0);
   const Module &base = fe.mods[0];
+  const char *no_fuse = getenv("AKUGPU_FE_NOFUSE");     // tests compare the fused kernels with the module-by-module path
+  // (1) fft -> {mel -> dct, power} -> merge
+  int f_fft = -1, f_mel = -1, f_dct = -1, f_pow = -1, f_out = -1;
+  for (int m = 1; m <= target && f_fft < 0 && !no_fuse; m++) {
+    if (!plan.needed[m] || fe.mods[m].type != M_FFT || m == target) continue;
+    const int N = base.window_width;
+    const bool fft_ok = N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 192 || N == 384 || N == 768 || N == 1536;
+    if (!fft_ok) break;
+    int mel = -1, pw = -1;
+    bool ok = true;
+    for (int c : cons[m]) {
+      if (fe.mods[c].type == M_MEL && mel < 0) mel = c;
+      else if (fe.mods[c].type == M_POWER && pw < 0) pw = c;
+      else ok = false;
+    }
+    if (!ok || mel < 0 || mel == target || cons[mel].size() != 1 || fe.mods[cons[mel][0]].type != M_DCT) break;
+    const int dct = cons[mel][0];
+    const int tpf = fe_threads_per_frame(N / 2);
+    if (fe.mods[mel].dim > tpf || fe.mods[mel].dim > FUSE_MAX_MEL || fe.mods[dct].dim > tpf) break;
+    if (pw < 0) {
+      if (dct == target) break;      // the dct rows themselves are the result: nothing to merge into, keep it simple
+      f_fft = m; f_mel = mel; f_dct = dct; f_out = dct;
+    } else {
+      if (pw == target || dct == target || cons[pw].size() != 1 || cons[dct].size() != 1 || cons[pw][0] != cons[dct][0]) break;
+      const int mg = cons[pw][0];
+      const Module &M = fe.mods[mg];
+      if (M.type != M_MERGE || M.src.size() != 2) break;
+      f_fft = m; f_mel = mel; f_dct = dct; f_pow = pw; f_out = mg;
+    }
+  }
+  if (f_fft >= 0) { skip[f_mel] = 1; if (f_pow >= 0) { skip[f_pow] = 1; skip[f_dct] = 1; } if (f_out != f_dct) skip[f_out] = 1; else skip[f_dct] = 1; }
+  // (2) X -> delta -> delta -> merge(X, d1, d2) == target
+  int g_x = -1, g_d1 = -1, g_d2 = -1;
+  if (!no_fuse && fe.mods[target].type == M_MERGE && fe.mods[target].src.size() == 3) {
+    const std::vector<int> &sv = fe.mods[target].src;
+    const int x = sv[0], d1 = sv[1], d2 = sv[2];
+    if (x > 0 && fe.mods[d1].type == M_DELTA && fe.mods[d2].type == M_DELTA && fe.mods[d1].src[0] == x && fe.mods[d2].src[0] == d1 &&
+        cons[d1].size() == 2 && cons[d2].size() == 1 && fe.mods[d1].width <= FUSE_MAX_WIDTH && fe.mods[d2].width <= FUSE_MAX_WIDTH &&
+        fe.mods[x].type != M_FFT && fe.mods[x].type != M_AUDIOFILE) {
+      g_x = x; g_d1 = d1; g_d2 = d2;
+      skip[d1] = skip[d2] = skip[target] = 1;
+    }
+  }
+
+  // one buffer per module that is materialised (the base module is fused into fft and has none)
+  std::vector<std::shared_ptr<DevBuf>> buf(fe.mods.size());
   for (int m = 1; m <= target; m++) {
     if (!plan.needed[m]) continue;
-    const Module &mod = fe.mods[m];
-    if (mod.type != M_FFT)
-      for (int s : mod.src)
-        if (s == 0) throw Error(AKUGPU_E_CONFIG, "the audiofile module can only feed an fft module");
+    if ((skip[m] && m != f_out) || m == f_fft) continue;
     if ((int)ctx->fe_bufs.size() <= m) ctx->fe_bufs.resize(m + 1);
     if (!ctx->fe_bufs[m]) ctx->fe_bufs[m] = std::make_shared<DevBuf>();
     buf[m] = ctx->fe_bufs[m];
-    buf[m]->reserve((size_t)n_rows * mod.dim * sizeof(double));
-    double *o = buf[m]->as<double>();
-    const double *s0 = mod.src.empty() || mod.src[0] == 0 ? nullptr : buf[mod.src[0]]->as<double>();
+    buf[m]->reserve((size_t)n_rows * fe.mods[m].dim * sizeof(double));
+  }
+  for (int m = 1; m <= target; m++) {
+    if (!plan.needed[m] || skip[m]) continue;
+    const Module &mod = fe.mods[m];
+    if (mod.type != M_FFT)
+      for (int sidx : mod.src)
+        if (sidx == 0) throw Error(AKUGPU_E_CONFIG, "the audiofile module can only feed an fft module");
+    double *o = buf[m] ? buf[m]->as<double>() : nullptr;
+    const double *s0 = mod.src.empty() || mod.src[0] == 0 ? nullptr : (buf[mod.src[0]] ? buf[mod.src[0]]->as<double>() : nullptr);
     const int sdim = mod.src.empty() ? 0 : fe.mods[mod.src[0]].dim;
     const int64_t ne = n_rows * mod.dim;
     switch (mod.type) {
@@ -788,12 +947,27 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
         const int N = base.window_width;
         const float *win = mod.d_a->as<float>();
         const float2 *tw = mod.d_b->as<float2>();
+        FuseStatic fuse;
+        if (m == f_fft) {
+          const Module &mel = fe.mods[f_mel], &dct = fe.mods[f_dct];
+          fuse.on = 1;
+          fuse.mel_dim = mel.dim; fuse.mel_root = mel.root;
+          fuse.mel = MelTable{mel.d_a->as<float>(), mel.d_b->as<int>(), mel.d_c->as<float>()};
+          fuse.dct_dim = dct.dim; fuse.dct_table = dct.d_a->as<float>();
+          fuse.odim = fe.mods[f_out].dim;
+          fuse.out = buf[f_out]->as<double>();
+          if (f_pow >= 0) {   // column order of the merge
+            const bool dct_first = fe.mods[f_out].src[0] == f_dct;
+            fuse.dct_col = dct_first ? 0 : 1;
+            fuse.pow_col = dct_first ? dct.dim : 0;
+          }
+        }
 #define SPEC_FFT(NN)                                                                                                \
   case NN: {                                                                                                        \
     constexpr int FPB_ = 256 / fe_threads_per_frame(NN / 2);                                                        \
     fe_spectrum_fft<NN><<<grid1(n_rows, FPB_), 256, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,         \
                                                              base.emph, base.copy_borders, win, tw, mod.magnitude,  \
-                                                             mod.log, o);                                           \
+                                                             mod.log, o, fuse);                                     \
     break;                                                                                                          \
   }
         switch (N) {
@@ -815,7 +989,8 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
         break;
       }
       case M_MEL:
-        fe_mel<<<grid1(ne, 256), 256, 0, st>>>(s0, sdim, n_rows, mod.d_a->as<float>(), mod.dim, mod.root, o);
+        fe_mel<<<grid1(ne, 256), 256, 0, st>>>(s0, sdim, n_rows, MelTable{mod.d_a->as<float>(), mod.d_b->as<int>(), mod.d_c->as<float>()},
+                                               mod.dim, mod.root, o);
         break;
       case M_POWER:
         fe_power<<<grid1(n_rows, 128), 128, 0, st>>>(s0, sdim, n_rows, 0, o);
@@ -868,7 +1043,16 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
   }
   if (target == 0) throw Error(AKUGPU_E_CONFIG, "the raw audiofile module output is not materialised on the GPU");
   const int dim = fe.mods[target].dim;
-  if (out_f64)
+  if (g_x >= 0) {
+    const Module &D1 = fe.mods[g_d1], &D2 = fe.mods[g_d2];
+    const int xd = fe.mods[g_x].dim;
+    if (out_f64)
+      fe_delta2_merge<double><<<grid1(n_rows * xd, 256), 256, 0, st>>>(buf[g_x]->as<double>(), xd, n_rows, du, dr, H, D1.width, D1.norm,
+                                                                      D2.width, D2.norm, (double *)d_out + out_row_base * dim);
+    else
+      fe_delta2_merge<float><<<grid1(n_rows * xd, 256), 256, 0, st>>>(buf[g_x]->as<double>(), xd, n_rows, du, dr, H, D1.width, D1.norm,
+                                                                     D2.width, D2.norm, (float *)d_out + out_row_base * dim);
+  } else if (out_f64)
     fe_gather<double><<<grid1(n_rows * dim, 256), 256, 0, st>>>(buf[target]->as<double>(), dim, du, dr, n_rows, H,
                                                                 (double *)d_out + out_row_base * dim);
   else

@@ -91,6 +91,28 @@ def test_features_batch_equals_single(engine, ref_small):
         assert np.array_equal(batch[fo[k]:fo[k + 1]], single)
 
 
+@pytest.mark.parametrize("sr", [8000, 16000, 48000])
+def test_fused_frontend_identical_to_module_by_module(engine, sr, monkeypatch):
+    """The fused kernels (fft+mel+power+dct+merge in one, delta+delta+merge+gather in one) perform the same operations
+    in the same order as the per-module kernels: features are bit-identical, float and double output."""
+    from aaltoasr_b200 import synth
+    engine.frontend_load_config_text(synth.mfcc39_config(sr))
+    pcm = synth.synth_audio(3100 + sr // 1000, sr * 2, sr)
+    cuts = [pcm, pcm[: sr // 2], pcm[sr // 3:]]
+    uo = np.concatenate([[0], np.cumsum([c.size for c in cuts])])
+    for dt in (np.float64, np.float32):
+        l0 = engine.launch_count()
+        fused, fo = engine.features(np.concatenate(cuts), uo, dtype=dt)
+        n_fused = engine.launch_count() - l0
+        monkeypatch.setenv("AKUGPU_FE_NOFUSE", "1")
+        l0 = engine.launch_count()
+        plain, _ = engine.features(np.concatenate(cuts), uo, dtype=dt)
+        n_plain = engine.launch_count() - l0
+        monkeypatch.delenv("AKUGPU_FE_NOFUSE")
+        assert np.array_equal(fused, plain)
+        assert n_fused == 2 and n_plain >= 10, (n_fused, n_plain)
+
+
 @pytest.mark.parametrize("sr,ww", [(8000, None), (16000, 512), (32000, None), (16000, 2048), (48000, None), (16000, 400),
                                    (24000, None), (16000, 1536), (12000, None)])
 def test_features_sweep_vs_oracle(engine, sr, ww):
