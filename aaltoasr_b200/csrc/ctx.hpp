@@ -136,8 +136,9 @@ struct PackedTC {
 // fp16x2 tensor-core scorer image (gmm_tc16.cu): diagonal pools, hi/lo-split expanded parameters with per-term
 // power-of-two scaling, the component constant folded into two extra K terms
 struct PackedTC16 {
-  bool ready = false;
-  int D = 0, L = 0, NCH = 0, KB = 0, n_tiles = 0;   // L = 2D+2 terms, NCH = K16 chunks per half, KB = 64-wide k-blocks
+  bool ready = false, full = false, stream = false;   // stream: A' too wide for shared memory (full covariance), streamed like B'
+  int D = 0, L = 0, NCH = 0, KB = 0, n_tiles = 0;   // L = terms incl. the 2 constant ones, NCH = K16 chunks per half, KB = 64-wide k-blocks
+  int half = 0, Kp = 0;                              // columns of Bh (= offset of Bl) and of a whole row
   DevBuf B, meta, center, escale, flag;
   std::vector<char> clean;
   std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;

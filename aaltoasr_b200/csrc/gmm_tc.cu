@@ -352,26 +352,24 @@ void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state
   }
 }
 
-// Builds B' (slot-ordered components x K'), the per-component constants and the slot table.
-void model_pack_tc(akugpu_ctx *ctx)
+// Expanded parameters of every Gaussian for CENTRED features (double): ll = <expand(x - c), theta_g> + gconst_g.
+//   diagonal (L = 2D):        theta = [-p/2 ; p m],  gconst = log sqrt(prod p) - 1/2 sum p m^2        (m = mu - c)
+//   full (L = D(D+3)/2):      theta = [P m ; -1/2 vec(P)] (lower triangle, off-diagonals x sqrt 2; the reference's own
+//                             exponential form, aku/Distributions.cc:1530-1547), gconst = log sqrt(det P) - 1/2 m'Pm
+void tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<double> &cen, std::vector<double> &theta,
+                        std::vector<double> &gconst)
 {
-  const HostModel &hm = ctx->hm;
-  PackedTC &p = ctx->ptc;
-  const int S = hm.S, G = hm.G, D = hm.D;
-  p.full = hm.n_full > 0;
-  if (p.full && hm.n_full != G) throw Error(AKUGPU_E_MODEL, "the tensor-core scorer needs an all-diagonal or an all-full pool");
-  p.L = p.full ? D * (D + 3) / 2 : 2 * D;
-  p.Lm = (p.L + tc::BK - 1) / tc::BK * tc::BK;                       // leading terms, padded to whole k-blocks
-  p.Kp = p.Lm + (5 * p.L + tc::BK - 1) / tc::BK * tc::BK;          // + the five correction products
-  std::vector<double> cen(D, 0.0);
+  const int G = hm.G, D = hm.D;
+  cen.assign(D, 0.0);
   for (int d = 0; d < D; d++) { double s = 0; for (int g = 0; g < G; g++) s += hm.mean[(size_t)g * D + d]; cen[d] = G ? s / G : 0; }
   // per-Gaussian expanded parameters for CENTRED features (double)
-  std::vector<double> theta((size_t)G * p.L, 0.0), gconst(G, 0.0);
+  theta.assign((size_t)G * L, 0.0);
+  gconst.assign(G, 0.0);
   std::vector<double> P, chol, Pm(D), mu(D);
   for (int g = 0; g < G; g++) {
     for (int d = 0; d < D; d++) mu[d] = hm.mean[(size_t)g * D + d] - cen[d];
-    double *th = &theta[(size_t)g * p.L];
-    if (!p.full) {
+    double *th = &theta[(size_t)g * L];
+    if (!full) {
       double c = 1, q = 0;
       for (int d = 0; d < D; d++) {
         const double cv = hm.cov[(size_t)g * D + d], pr = cv > 0 ? 1 / cv : 0;
@@ -401,6 +399,21 @@ void model_pack_tc(akugpu_ctx *ctx)
       gconst[g] = log(sqrt(det)) - 0.5 * dot;
     }
   }
+}
+
+// Builds B' (slot-ordered components x K'), the per-component constants and the slot table.
+void model_pack_tc(akugpu_ctx *ctx)
+{
+  const HostModel &hm = ctx->hm;
+  PackedTC &p = ctx->ptc;
+  const int S = hm.S, G = hm.G, D = hm.D;
+  p.full = hm.n_full > 0;
+  if (p.full && hm.n_full != G) throw Error(AKUGPU_E_MODEL, "the tensor-core scorer needs an all-diagonal or an all-full pool");
+  p.L = p.full ? D * (D + 3) / 2 : 2 * D;
+  p.Lm = (p.L + tc::BK - 1) / tc::BK * tc::BK;                       // leading terms, padded to whole k-blocks
+  p.Kp = p.Lm + (5 * p.L + tc::BK - 1) / tc::BK * tc::BK;          // + the five correction products
+  std::vector<double> cen, theta, gconst;
+  tc_expanded_params(hm, p.full, p.L, cen, theta, gconst);
   std::vector<int> slot_state, slot_k0, slot_flags;
   tc_build_slots(hm, tc::SLOTS / 2, slot_state, slot_k0, slot_flags);
   const int n_slots = (int)slot_state.size();

@@ -63,24 +63,30 @@ constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 constexpr float BIAS_OFF = -65504.f;               // bias of absent components: exp() underflows to exactly 0
 }  // namespace tc16
 
+// NCH > 0: A' resident (built in the kernel), B' streamed one component tile per ring slot.
+// NCH == 0: streaming variant for wide expansions (full covariance: K = D(D+3)/2 + 2 = 821): A' = [Ah | Al] comes
+//           from an expansion kernel through TMA like B' = [Bh | Bl]; a ring stage = the same 64-wide k-block of the
+//           four halves (64 KB); `nkb` k-blocks per half, `tslots` stages.
 template <int NCH>
 __global__ void __launch_bounds__(tc16::THREADS, 1)
-gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapB, int tslots, const int *__restrict__ range_begin,
+gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nkb, int tslots,
+                const int *__restrict__ range_begin,
                 const int *__restrict__ meta, const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t nf, int D,
                 const double *__restrict__ center, const float *__restrict__ escale, float *__restrict__ sll, int64_t ldF,
                 float2 *__restrict__ norm, int *__restrict__ ovf_flag)
 {
   using namespace tc;
   using namespace tc16;
-  constexpr int KB = (2 * NCH + 3) / 4;                       // 64-wide k-blocks of A' and of B'
-  constexpr uint32_t SLOT_BYTES = KB * BLOCK_BYTES;           // one component tile of B'
+  constexpr bool STREAM = NCH == 0;
+  constexpr int KB = STREAM ? 4 : (2 * NCH + 3) / 4;          // 64-wide k-blocks of A' and of B' (STREAM: per ring stage)
+  constexpr uint32_t SLOT_BYTES = KB * BLOCK_BYTES;           // one component tile of B' / one stage of {Ah, Al, Bh, Bl}
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[MAX_TSLOTS], empty_bar[MAX_TSLOTS], tmem_full[2], tmem_empty[2], a_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float sM[EPI_WARPS][32];
   __shared__ double sR[EPI_WARPS][32];
-  unsigned char *ring = smem + SLOT_BYTES;                    // A' occupies the first KB blocks
+  unsigned char *ring = STREAM ? smem : smem + SLOT_BYTES;    // resident A' occupies the first KB blocks
   float *stage_x = reinterpret_cast<float *>(ring + (size_t)tslots * SLOT_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,6 +113,20 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapB, int tslots, const int 
       // ===== TMA producer: one component tile of B' (KB k-blocks, one barrier) per ring slot =====
       int slot = 0;
       uint32_t ph = 0;
+      if (STREAM) {
+        const int half = nkb * BK;                           // columns of Ah / Bh
+        for (int n = n_begin; n < n_end; n++)
+          for (int kb = 0; kb < nkb; kb++) {
+            mbar_wait(&empty_bar[slot], ph ^ 1);
+            mbar_expect_tx(&full_bar[slot], SLOT_BYTES);
+            unsigned char *dst = ring + (size_t)slot * SLOT_BYTES;
+            tma_load_2d(dst, &mapA, kb * BK, m0, &full_bar[slot]);
+            tma_load_2d(dst + BLOCK_BYTES, &mapA, half + kb * BK, m0, &full_bar[slot]);
+            tma_load_2d(dst + 2 * BLOCK_BYTES, &mapB, kb * BK, n * BN, &full_bar[slot]);
+            tma_load_2d(dst + 3 * BLOCK_BYTES, &mapB, half + kb * BK, n * BN, &full_bar[slot]);
+            if (++slot == tslots) { slot = 0; ph ^= 1; }
+          }
+      } else
       for (int n = n_begin; n < n_end; n++) {
         mbar_wait(&empty_bar[slot], ph ^ 1);                 // a fresh barrier passes the wait on the previous phase
         mbar_expect_tx(&full_bar[slot], SLOT_BYTES);
@@ -123,10 +143,35 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapB, int tslots, const int 
       // operand sits at block c/4, byte offset (c%4)*32 of the 128 B swizzle row
       auto chunk_off = [](int c) -> uint32_t { return ((uint32_t)(c >> 2) * BLOCK_BYTES + (uint32_t)(c & 3) * 32u) >> 4; };
       const uint64_t a_desc0 = umma_desc(smem_u32(smem));
-      mbar_wait(&a_full, 0);                        // A' written by the epilogue warps (generic proxy, fenced)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int slot = 0;
       uint32_t ph = 0;
+      if (STREAM) {
+        constexpr uint32_t BLK = BLOCK_BYTES >> 4;           // descriptor units
+        for (int n = n_begin; n < n_end; n++) {
+          const int i = n - n_begin, a = i & 1;
+          mbar_wait(&tmem_empty[a], ((i >> 1) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_main = tmem_base + a * 2 * BN, d_corr = d_main + BN;
+          for (int kb = 0; kb < nkb; kb++) {
+            mbar_wait(&full_bar[slot], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t ah = umma_desc(smem_u32(ring) + (uint32_t)slot * SLOT_BYTES);     // Ah | Al | Bh | Bl
+            const uint64_t al = ah + BLK, bh = ah + 2 * BLK, bl = ah + 3 * BLK;
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) {
+              const uint32_t first = (kb | k) ? 1u : 0u;
+              umma_f16(d_corr, ah + 2 * k, bl + 2 * k, IDESC, first);
+              umma_f16(d_corr, al + 2 * k, bh + 2 * k, IDESC, 1u);
+              umma_f16(d_main, ah + 2 * k, bh + 2 * k, IDESC, first);
+            }
+            umma_commit(&empty_bar[slot]);
+            if (++slot == tslots) { slot = 0; ph ^= 1; }
+          }
+          umma_commit(&tmem_full[a]);
+        }
+      } else {
+      mbar_wait(&a_full, 0);                        // A' written by the epilogue warps (generic proxy, fenced)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int n = n_begin; n < n_end; n++) {
         const int i = n - n_begin, a = i & 1;
         mbar_wait(&tmem_empty[a], ((i >> 1) & 1) ^ 1);
@@ -145,6 +190,7 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapB, int tslots, const int 
         umma_commit(&tmem_full[a]);            // both accumulators of this tile complete
         if (++slot == tslots) { slot = 0; ph ^= 1; }
       }
+      }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
@@ -152,7 +198,7 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapB, int tslots, const int 
     const int group = (warp - 4) >> 3;                        // this warp takes the tiles i with (i & 1) == group, accumulator set = group
     const int et = threadIdx.x - 128;                         // 0..511 among the epilogue threads
     // ===== A' = [Ah | Al]: stage, centre, expand, scale, split, store swizzled =====
-    {
+    if (!STREAM) {
       const int64_t valid = nf - m0;                          // frames of this tile that exist
       const int64_t g0 = (f_begin + m0) * (int64_t)D;
       const int total = BM * D;
@@ -335,56 +381,102 @@ static int tc16_tslots(int KB, int D)
   if (fixed >= budget) return 0;
   return (int)std::min<size_t>(tc16::MAX_TSLOTS, (budget - fixed) / ((size_t)KB * tc16::BLOCK_BYTES));
 }
+constexpr int TC16_STREAM_STAGES = 3;      // 3 x 64 KB stages of {Ah, Al, Bh, Bl}
+
+// Expansion width (terms incl. the two constant terms) and whether A' can stay resident in shared memory.
+static void tc16_shape(const HostModel &hm, int &L, int &NCH, bool &stream)
+{
+  const bool full = hm.n_full > 0;
+  L = (full ? hm.D * (hm.D + 3) / 2 : 2 * hm.D) + 2;
+  NCH = (L + 15) / 16;
+  stream = full || NCH > tc16::MAX_NCH || tc16_tslots((2 * NCH + 3) / 4, hm.D) < 2;
+}
 
 bool tc16_supported(const HostModel &hm)
 {
-  if (hm.n_full != 0 || hm.S <= 0 || hm.G <= 0) return false;
+  if (hm.S <= 0 || hm.G <= 0 || (hm.n_full != 0 && hm.n_full != hm.G)) return false;   // all diagonal or all full
   for (int s = 0; s < hm.S; s++)
     if (hm.mix_off[s + 1] - hm.mix_off[s] > tc16::SLOTS_PER_WARP * tc16::GR) return false;
-  const int NCH = (2 * hm.D + 2 + 15) / 16, KB = (2 * NCH + 3) / 4;
-  return NCH <= tc16::MAX_NCH && tc16_tslots(KB, hm.D) >= 2;
+  return true;
 }
 
-// Builds B' = [Bh | Bl] (slot-ordered components x 64*KB fp16), the slot table and the per-term scales.
+// Streaming variant: A' = [Ah | Al] (rows x 2*half fp16) from the features: centre, expand, scale, split.
+// Full covariance: [x ; vec(x x^T)] (lower triangle row-wise, off-diagonals x sqrt 2, aku/LinearAlgebra.cc:220-238);
+// diagonal: [x^2 ; x]; then the two constant terms.
+__global__ void tc16_expand_feats(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int64_t nf, int64_t rows,
+                                  int D, int L, int half, int full, const double *__restrict__ center,
+                                  const float *__restrict__ escale, __half *__restrict__ A, int *__restrict__ ovf_flag)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * half) return;
+  const int64_t fr = i / half;
+  const int l = (int)(i - fr * half);
+  float v = 0.f;
+  if (fr < nf && l < L) {
+    auto x = [&](int d) -> double {
+      const double t = feats_f64 ? reinterpret_cast<const double *>(feats)[(f_begin + fr) * D + d]
+                                 : (double)reinterpret_cast<const float *>(feats)[(f_begin + fr) * D + d];
+      return t - center[d];
+    };
+    const int L0 = L - 2;
+    if (l >= L0) v = 1.f;
+    else if (full) {
+      if (l < D) v = (float)x(l);
+      else {
+        int pos = l - D, r = 0;
+        while ((r + 1) * (r + 2) / 2 <= pos) r++;
+        const int c = pos - r * (r + 1) / 2;
+        const double m = x(r) * x(c);
+        v = (float)((r == c) ? m : sqrt(2.0) * m);
+      }
+    } else {
+      v = (l < D) ? (float)(x(l) * x(l)) : (float)x(l - D);
+    }
+    v *= escale[l];
+    if (!(fabsf(v) <= 65504.f)) atomicOr(ovf_flag, 1);
+  }
+  const __half h = __float2half_rn(v);
+  A[fr * (2 * (int64_t)half) + l] = h;
+  A[fr * (2 * (int64_t)half) + half + l] = __float2half_rn((v - __half2float(h)) * tc16::LO_SCALE);
+}
+
+// Builds B' = [Bh | Bl] (slot-ordered component rows, fp16), the slot table and the per-term scales.
 void model_pack_tc16(akugpu_ctx *ctx)
 {
   const HostModel &hm = ctx->hm;
   PackedTC16 &p = ctx->ptc16;
   p.ready = false;
   if (!tc16_supported(hm)) return;
-  const int S = hm.S, G = hm.G, D = hm.D;
+  const int G = hm.G, D = hm.D;
+  const bool full = hm.n_full > 0;
   p.D = D;
-  p.L = 2 * D + 2;
-  p.NCH = (p.L + 15) / 16;
-  p.KB = (2 * p.NCH + 3) / 4;
-  const int L16 = p.NCH * 16, Kp = p.KB * tc16::BK;
-  std::vector<double> cen(D, 0.0);
-  for (int d = 0; d < D; d++) { double s = 0; for (int g = 0; g < G; g++) s += hm.mean[(size_t)g * D + d]; cen[d] = s / G; }
-  // per-Gaussian expanded parameters for CENTRED features (double): theta[0..D) = -p/2, theta[D..2D) = p m
-  std::vector<double> theta((size_t)G * 2 * D, 0.0), gconst(G, 0.0), tmax(2 * D, 0.0);
-  for (int g = 0; g < G; g++) {
-    double *th = &theta[(size_t)g * 2 * D];
-    double c = 1, q = 0;
-    for (int d = 0; d < D; d++) {
-      const double cv = hm.cov[(size_t)g * D + d], pr = cv > 0 ? 1 / cv : 0, m = hm.mean[(size_t)g * D + d] - cen[d];
-      c *= pr;
-      th[d] = -0.5 * pr;
-      th[D + d] = pr * m;
-      q += pr * m * m;
-    }
-    if (c > 0) c = log(sqrt(c));          // DiagonalGaussian::set_constant, aku/Distributions.cc:1274-1288
-    gconst[g] = c - 0.5 * q;
-    for (int l = 0; l < 2 * D; l++) tmax[l] = std::max(tmax[l], fabs(th[l]));
+  p.full = full;
+  tc16_shape(hm, p.L, p.NCH, p.stream);
+  const int L0 = p.L - 2;                        // data terms; then b_coarse, b_fine
+  if (p.stream) {
+    p.KB = (p.NCH + 3) / 4;                      // k-blocks per half
+    p.half = p.KB * tc16::BK;
+    p.Kp = 2 * p.half;
+  } else {
+    p.KB = (2 * p.NCH + 3) / 4;                  // k-blocks of the whole row
+    p.half = p.NCH * 16;
+    p.Kp = p.KB * tc16::BK;
   }
+  const int half = p.half, Kp = p.Kp;
+  std::vector<double> cen, theta, gconst;
+  tc_expanded_params(hm, full, L0, cen, theta, gconst);
+  std::vector<double> tmax(L0, 0.0);
+  for (int g = 0; g < G; g++)
+    for (int l = 0; l < L0; l++) tmax[l] = std::max(tmax[l], fabs(theta[(size_t)g * L0 + l]));
   // power-of-two scale of every term: max |B'_k| in [2^11, 2^12); the two constant terms stay unscaled
-  std::vector<float> escale(L16, 0.f);
-  std::vector<int> ek(2 * D, 0);
-  for (int l = 0; l < 2 * D; l++) {
+  std::vector<float> escale(half, 0.f);
+  std::vector<int> ek(L0, 0);
+  for (int l = 0; l < L0; l++) {
     if (tmax[l] > 0 && std::isfinite(tmax[l])) ek[l] = ilogb(tmax[l]) - 11;
     ek[l] = std::max(-100, std::min(100, ek[l]));
     escale[l] = (float)ldexp(1.0, ek[l]);
   }
-  escale[2 * D] = escale[2 * D + 1] = 1.f;
+  escale[L0] = escale[L0 + 1] = 1.f;
 
   std::vector<int> slot_state, slot_k0, slot_flags;
   tc_build_slots(hm, tc16::SLOTS_PER_WARP, slot_state, slot_k0, slot_flags);
@@ -395,13 +487,13 @@ void model_pack_tc16(akugpu_ctx *ctx)
   std::vector<int32_t> meta((size_t)p.n_tiles * tc16::SLOTS, -1);
   p.clean.assign(p.n_tiles, 1);
   const uint16_t off_bits = half_bits(tc16::BIAS_OFF);
-  auto put = [&](uint16_t *br, int l, double val) {        // hi at l, lo (scaled by 2^11) at L16 + l
+  auto put = [&](uint16_t *br, int l, double val) {        // hi at l, lo (scaled by 2^11) at half + l
     const float v = (float)val;
     const uint16_t h = half_bits(v);
     br[l] = h;
-    br[L16 + l] = half_bits((float)((val - (double)half_val(h)) * (double)tc16::LO_SCALE));
+    br[half + l] = half_bits((float)((val - (double)half_val(h)) * (double)tc16::LO_SCALE));
   };
-  for (size_t row = 0; row < rows; row++) B[row * Kp + 2 * D] = off_bits;     // absent components: constant = -65504
+  for (size_t row = 0; row < rows; row++) B[row * Kp + L0] = off_bits;     // absent components: constant = -65504
   for (int sl = 0; sl < n_slots; sl++) {
     const int s = slot_state[sl];
     if (s < 0) continue;                                   // padding slot: meta stays -1
@@ -415,11 +507,11 @@ void model_pack_tc16(akugpu_ctx *ctx)
       const double b = log(w) + gconst[g];
       if (!(fabs(b) < 60000.0)) { p.ready = false; return; }   // constant outside the fp16 range: keep the bf16x3 kernel
       uint16_t *br = &B[((size_t)sl * tc16::GR + j) * Kp];
-      for (int l = 0; l < 2 * D; l++) put(br, l, ldexp(theta[(size_t)g * 2 * D + l], -ek[l]));
+      for (int l = 0; l < L0; l++) put(br, l, ldexp(theta[(size_t)g * L0 + l], -ek[l]));
       const uint16_t bc = half_bits((float)b);
-      br[2 * D] = bc;                                      // coarse part, exact in fp16
-      br[L16 + 2 * D] = 0;
-      put(br, 2 * D + 1, b - (double)half_val(bc));        // fine part, hi/lo
+      br[L0] = bc;                                         // coarse part, exact in fp16
+      br[half + L0] = 0;
+      put(br, L0 + 1, b - (double)half_val(bc));           // fine part, hi/lo
     }
   }
   auto up = [&](DevBuf &buf, const void *src, size_t bytes) {
@@ -459,25 +551,42 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   PackedTC16 &p = ctx->ptc16;
   const int64_t nf = f_end - f_begin;
   if (nf <= 0) return false;
-  CUtensorMap mapB;
-  tc_make_map(&mapB, p.B.p, (uint64_t)p.n_tiles * tc16::BN, (uint64_t)p.KB * tc16::BK, true);
+  CUtensorMap mapA, mapB;
+  tc_make_map(&mapB, p.B.p, (uint64_t)p.n_tiles * tc16::BN, (uint64_t)p.Kp, true);
   const int ftiles = (int)((nf + tc16::BM - 1) / tc16::BM);
+  if (p.stream) {      // expansion kernel (accounted to the front-end stage, like the bf16x3 path's)
+    const int64_t rows = (int64_t)ftiles * tc16::BM;
+    ctx->d_fe[4].reserve((size_t)rows * p.Kp * 2);
+    StageScope sc(ctx, 0);
+    const int64_t ne = rows * p.half;
+    tc16_expand_feats<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(feats, feats_f64, f_begin, nf, rows, p.D, p.L, p.half,
+                                                                           p.full ? 1 : 0, p.center.as<double>(), p.escale.as<float>(),
+                                                                           ctx->d_fe[4].as<__half>(), p.flag.as<int>());
+    AKU_CUDA(cudaGetLastError());
+    ctx->launches++;
+    tc_make_map(&mapA, ctx->d_fe[4].p, (uint64_t)rows, (uint64_t)p.Kp, true);
+  } else {
+    mapA = mapB;       // unused by the resident variant
+  }
   int want = 1;
   if (ftiles < ctx->sm_count) want = std::min(p.n_tiles, std::max(1, ctx->sm_count / ftiles));
   int ysplit = 1;
   const int *ranges = tc_tile_ranges(ctx, p.n_tiles, p.clean, p.ranges, want, ysplit);
   if (ysplit != 1) norm = nullptr;        // a frame's states are spread over several CTAs: the LNA kernel does both passes
-  const int tslots = tc16_tslots(p.KB, p.D);
-  const size_t smem = 1024 + (size_t)(1 + tslots) * p.KB * tc16::BLOCK_BYTES + tc16_stage_x_bytes(p.D);
+  const int tslots = p.stream ? TC16_STREAM_STAGES : tc16_tslots(p.KB, p.D);
+  const size_t smem = p.stream ? 1024 + (size_t)tslots * 4 * tc16::BLOCK_BYTES
+                               : 1024 + (size_t)(1 + tslots) * p.KB * tc16::BLOCK_BYTES + tc16_stage_x_bytes(p.D);
   StageScope sc(ctx, 1);
   auto launch = [&](auto kernel) {
-    static size_t attr = 0;     // one per instantiation
-    if (smem > attr) { AKU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-    kernel<<<dim3(ftiles, ysplit), tc16::THREADS, smem, ctx->stream>>>(mapB, tslots, ranges, p.meta.as<int>(), feats, feats_f64, f_begin, nf,
-                                                                     p.D, p.center.as<double>(), p.escale.as<float>(), sll, ldF, norm,
-                                                                     p.flag.as<int>());
+    static std::map<const void *, size_t> attr;     // per instantiation (they all share one function-pointer type)
+    size_t &have = attr[(const void *)kernel];
+    if (smem > have) { AKU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); have = smem; }
+    kernel<<<dim3(ftiles, ysplit), tc16::THREADS, smem, ctx->stream>>>(mapA, mapB, p.KB, tslots, ranges, p.meta.as<int>(), feats, feats_f64,
+                                                                     f_begin, nf, p.D, p.center.as<double>(), p.escale.as<float>(), sll, ldF,
+                                                                     norm, p.flag.as<int>());
   };
-  switch (p.NCH) {
+  if (p.stream) launch(gmm_tc16_kernel<0>);
+  else switch (p.NCH) {
     case 1: launch(gmm_tc16_kernel<1>); break;
     case 2: launch(gmm_tc16_kernel<2>); break;
     case 3: launch(gmm_tc16_kernel<3>); break;

@@ -399,6 +399,14 @@ void model_pack(akugpu_ctx *ctx)
     ctx->ptc.ready = false;
     ctx->ptc16.ready = false;
     if (tc_wanted(ctx)) model_pack_tc(ctx);
+    else if (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) {
+      model_pack_tc16(ctx);              // all-full pools: the streaming fp16x2 kernel
+      if (!ctx->ptc16.ready && hm.n_full == hm.G) {
+        bool ok = true;
+        for (int s = 0; s < hm.S && ok; s++) ok = hm.mix_off[s + 1] - hm.mix_off[s] <= 64;
+        if (ok) model_pack_tc(ctx);
+      }
+    }
     ctx->have_model = true;
     return;
   }
