@@ -59,6 +59,8 @@ SYMBOLS = {
     "akugpu_lna_header": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "akugpu_set_chunk_frames": (C.c_int, [C.c_void_p, C.c_int64]),
     "akugpu_set_scorer_variant": (C.c_int, [C.c_void_p, C.c_int]),
+    "akugpu_model_expanded_form_q": (C.c_double, [C.c_void_p]),
+    "akugpu_scorer_in_use": (C.c_int, [C.c_void_p]),
     "akugpu_pipe_rates": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 

@@ -636,6 +636,21 @@ int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant)
   API_END
 }
 
+double akugpu_model_expanded_form_q(akugpu_ctx *ctx)
+{
+  if (!ctx || !ctx->have_model) return -1.0;
+  return std::max(ctx->ptc16.q_max, ctx->ptc.q_max);
+}
+
+int akugpu_scorer_in_use(akugpu_ctx *ctx)
+{
+  if (!ctx || !ctx->have_model) return AKUGPU_E_STATE;
+  if (ctx->hm.use_clustering && ctx->hm.n_clusters > 0) return 0;
+  if (ctx->ptc16.ready) return ctx->ptc16.stream ? 4 : 3;
+  if (ctx->ptc.ready) return 2;
+  return ctx->hm.n_full > 0 ? 0 : 1;
+}
+
 int akugpu_pipe_rates(akugpu_ctx *ctx, double out[8])
 {
   API_BEGIN

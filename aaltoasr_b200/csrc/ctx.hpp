@@ -127,6 +127,7 @@ struct PackedF64 {
 // tensor-core scorer image (gmm_tc.cu): bf16x3-split expanded parameters, slot-ordered rows
 struct PackedTC {
   bool ready = false, full = false;
+  double q_max = 0;            // conditioning of the expanded form for this model (gmm_tc.cu: tc_expanded_params)
   int L = 0, Lm = 0, Kp = 0, n_tiles = 0;
   DevBuf B, bias, meta, center;
   std::vector<char> clean;
@@ -139,6 +140,7 @@ struct PackedTC16 {
   bool ready = false, full = false, stream = false;   // stream: A' too wide for shared memory (full covariance), streamed like B'
   int D = 0, L = 0, NCH = 0, KB = 0, n_tiles = 0;   // L = terms incl. the 2 constant ones, NCH = K16 chunks per half, KB = 64-wide k-blocks
   int half = 0, Kp = 0;                              // columns of Bh (= offset of Bl) and of a whole row
+  double q_max = 0;                                  // conditioning of the expanded form for this model
   DevBuf B, meta, center, escale, flag;
   std::vector<char> clean;
   std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;

@@ -356,12 +356,33 @@ void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state
 //   diagonal (L = 2D):        theta = [-p/2 ; p m],  gconst = log sqrt(prod p) - 1/2 sum p m^2        (m = mu - c)
 //   full (L = D(D+3)/2):      theta = [P m ; -1/2 vec(P)] (lower triangle, off-diagonals x sqrt 2; the reference's own
 //                             exponential form, aku/Distributions.cc:1530-1547), gconst = log sqrt(det P) - 1/2 m'Pm
-void tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<double> &cen, std::vector<double> &theta,
-                        std::vector<double> &gconst)
+// The feature centre c is chosen per dimension to minimise max_g p_gd (mu_gd - c_d)^2 (ternary search on a convex
+// function; diagonal of the covariance for full Gaussians): the expanded form adds terms of order q_g = 1/2 sum_d
+// p (mu - c)^2 that cancel against the constant, and its fp32 accumulation error is ~4e-7 * q_g (measured,
+// scripts/shape_check.py).  Returns max_g q_g so that the caller can refuse models the form is too ill-conditioned for.
+double tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<double> &cen, std::vector<double> &theta,
+                          std::vector<double> &gconst)
 {
   const int G = hm.G, D = hm.D;
   cen.assign(D, 0.0);
-  for (int d = 0; d < D; d++) { double s = 0; for (int g = 0; g < G; g++) s += hm.mean[(size_t)g * D + d]; cen[d] = G ? s / G : 0; }
+  for (int d = 0; d < D; d++) {
+    double lo = 1e300, hi = -1e300;
+    std::vector<double> mu(G), sp(G);            // mean and sqrt(precision) of this dimension
+    for (int g = 0; g < G; g++) {
+      mu[g] = hm.mean[(size_t)g * D + d];
+      const double cv = full ? hm.full_cov[((size_t)hm.full_index[g] * D + d) * D + d] : hm.cov[(size_t)g * D + d];
+      sp[g] = cv > 0 ? 1 / sqrt(cv) : 0;
+      if (sp[g] > 0) { lo = std::min(lo, mu[g]); hi = std::max(hi, mu[g]); }
+    }
+    if (!(lo <= hi)) { cen[d] = 0; continue; }
+    auto worst = [&](double c) { double w = 0; for (int g = 0; g < G; g++) w = std::max(w, sp[g] * fabs(mu[g] - c)); return w; };
+    for (int it = 0; it < 50 && hi - lo > 1e-9 * (1 + fabs(hi)); it++) {
+      const double a = lo + (hi - lo) / 3, b = hi - (hi - lo) / 3;
+      if (worst(a) < worst(b)) hi = b; else lo = a;
+    }
+    cen[d] = 0.5 * (lo + hi);
+  }
+  double q_max = 0;
   // per-Gaussian expanded parameters for CENTRED features (double)
   theta.assign((size_t)G * L, 0.0);
   gconst.assign(G, 0.0);
@@ -380,6 +401,7 @@ void tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<doubl
       }
       if (c > 0) c = log(sqrt(c));
       gconst[g] = c - 0.5 * q;
+      q_max = std::max(q_max, 0.5 * q);
     } else {
       std::vector<double> cov(hm.full_cov.begin() + (size_t)hm.full_index[g] * D * D,
                               hm.full_cov.begin() + (size_t)(hm.full_index[g] + 1) * D * D);
@@ -397,8 +419,10 @@ void tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<doubl
       for (int i = 0; i < D; i++)
         for (int j = 0; j <= i; j++, pos++) th[pos] = -0.5 * ((i == j) ? P[(size_t)i * D + j] : sqrt(2.0) * P[(size_t)i * D + j]);
       gconst[g] = log(sqrt(det)) - 0.5 * dot;
+      q_max = std::max(q_max, 0.5 * dot);
     }
   }
+  return q_max;
 }
 
 // Builds B' (slot-ordered components x K'), the per-component constants and the slot table.
@@ -413,7 +437,7 @@ void model_pack_tc(akugpu_ctx *ctx)
   p.Lm = (p.L + tc::BK - 1) / tc::BK * tc::BK;                       // leading terms, padded to whole k-blocks
   p.Kp = p.Lm + (5 * p.L + tc::BK - 1) / tc::BK * tc::BK;          // + the five correction products
   std::vector<double> cen, theta, gconst;
-  tc_expanded_params(hm, p.full, p.L, cen, theta, gconst);
+  p.q_max = tc_expanded_params(hm, p.full, p.L, cen, theta, gconst);
   std::vector<int> slot_state, slot_k0, slot_flags;
   tc_build_slots(hm, tc::SLOTS / 2, slot_state, slot_k0, slot_flags);
   const int n_slots = (int)slot_state.size();

@@ -446,6 +446,7 @@ void model_pack_tc16(akugpu_ctx *ctx)
   const HostModel &hm = ctx->hm;
   PackedTC16 &p = ctx->ptc16;
   p.ready = false;
+  p.q_max = 0;
   if (!tc16_supported(hm)) return;
   const int G = hm.G, D = hm.D;
   const bool full = hm.n_full > 0;
@@ -464,7 +465,10 @@ void model_pack_tc16(akugpu_ctx *ctx)
   }
   const int half = p.half, Kp = p.Kp;
   std::vector<double> cen, theta, gconst;
-  tc_expanded_params(hm, full, L0, cen, theta, gconst);
+  p.q_max = tc_expanded_params(hm, full, L0, cen, theta, gconst);
+  // ill-conditioned for the expanded form (sharp Gaussians far from the centre): leave it to the direct-form kernels
+  // unless the tensor-core scorer was asked for explicitly (akugpu_set_scorer_variant(ctx, 3))
+  if (p.q_max > TC_Q_MAX && ctx->scorer_variant != 3) return;
   std::vector<double> tmax(L0, 0.0);
   for (int g = 0; g < G; g++)
     for (int l = 0; l < L0; l++) tmax[l] = std::max(tmax[l], fabs(theta[(size_t)g * L0 + l]));

@@ -10,6 +10,7 @@
 //        product is > 0, otherwise the raw product is kept (DiagonalGaussian::set_constant :1274-1288)
 #include "ctx.hpp"
 #include "kernels.hpp"
+#include "tc_common.cuh"
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -401,7 +402,7 @@ void model_pack(akugpu_ctx *ctx)
     if (tc_wanted(ctx)) model_pack_tc(ctx);
     else if (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) {
       model_pack_tc16(ctx);              // all-full pools: the streaming fp16x2 kernel
-      if (!ctx->ptc16.ready && hm.n_full == hm.G) {
+      if (!ctx->ptc16.ready && hm.n_full == hm.G && ctx->ptc16.q_max <= TC_Q_MAX) {
         bool ok = true;
         for (int s = 0; s < hm.S && ok; s++) ok = hm.mix_off[s + 1] - hm.mix_off[s] <= 64;
         if (ok) model_pack_tc(ctx);
@@ -478,7 +479,8 @@ void model_pack(akugpu_ctx *ctx)
   if (tc_wanted(ctx)) model_pack_tc(ctx);
   else if (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) model_pack_tc16(ctx);
   // packing can decline (a component constant outside the fp16 range): fall back to the bf16x3 image
-  if (!ctx->ptc16.ready && !ctx->ptc.ready && (ctx->scorer_variant == 0 || ctx->scorer_variant == 3)) {
+  if (!ctx->ptc16.ready && !ctx->ptc.ready && (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) &&
+      (ctx->ptc16.q_max <= TC_Q_MAX || ctx->scorer_variant == 3)) {
     const HostModel &h = ctx->hm;
     bool ok = h.S > 0 && h.G > 0;
     for (int s = 0; s < h.S && ok; s++) ok = h.mix_off[s + 1] - h.mix_off[s] <= 64;

@@ -102,6 +102,13 @@ class AkuGpu:
     def set_scorer_variant(self, variant):
         self._ck(self._lib.akugpu_set_scorer_variant(self._h, int(variant)))
 
+    def expanded_form_q(self):
+        return float(self._lib.akugpu_model_expanded_form_q(self._h))
+
+    def scorer_in_use(self):
+        """0 double path, 1 FP32-pipe, 2 bf16x3 tensor-core, 3 fp16x2 tensor-core (resident A'), 4 fp16x2 (streaming A')."""
+        return int(self._lib.akugpu_scorer_in_use(self._h))
+
     def pipe_rates(self):
         out = (C.c_double * 8)()
         self._ck(self._lib.akugpu_pipe_rates(self._h, out))
