@@ -36,6 +36,8 @@ rm -f "$OUT/libaku_ref.a"
 ar rcs "$OUT/libaku_ref.a" $LIBOBJ
 g++ -O2 -o "$OUT/ref_phone_probs" "$OUT/obj/phone_probs.o" "$OUT/libaku_ref.a" -lm
 g++ -O2 -o "$OUT/ref_feacat" "$OUT/obj/feacat.o" "$OUT/libaku_ref.a" -lm
+# The consumer of the LNA stream: the decoder's own reader (decoder/src/LnaReaderCircular.cc, self-contained).
+g++ -O2 -fPIC -w -I"$R/decoder/src" -c "$R/decoder/src/LnaReaderCircular.cc" -o "$OUT/obj/LnaReaderCircular.o"
 # Thin C-callable view of the reference classes for pytest (oracle/ref_capi.cc is ours).
-g++ $CXXFLAGS -shared -o "$OUT/libref_capi.so" "$HERE/ref_capi.cc" "$OUT/libaku_ref.a" -lm
+g++ $CXXFLAGS -I"$R/decoder/src" -shared -o "$OUT/libref_capi.so" "$HERE/ref_capi.cc" "$OUT/obj/LnaReaderCircular.o" "$OUT/libaku_ref.a" -lm
 echo "oracle/_ref built: ref_phone_probs ref_feacat libref_capi.so"

@@ -37,6 +37,8 @@ def lib():
             getattr(_lib, f).argtypes = [C.c_void_p]
         _lib.ref_state_likelihoods.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]
         _lib.ref_gaussian_loglik.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]
+        _lib.ref_lna_read.restype = C.c_long
+        _lib.ref_lna_read.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.c_int]
         _lib.ref_model_read_clustering.argtypes = [C.c_void_p, C.c_char_p]
         _lib.ref_model_set_clustering_min_evals.argtypes = [C.c_void_p, C.c_double, C.c_double]
     return _lib
@@ -114,6 +116,19 @@ class Model:
         if self.h:
             lib().ref_model_close(self.h)
             self.h = None
+
+
+def lna_read(path, buf_frames=64, backwards=True):
+    """The decoder's LnaReaderCircular on an LNA file: float32 log-probs [frames x models] as the decoder sees them."""
+    S = C.c_int(0)
+    n = lib().ref_lna_read(path.encode(), buf_frames, None, 0, C.byref(S), 0)
+    if n < 0:
+        raise _err()
+    out = np.empty((n, S.value), dtype=np.float32)
+    n2 = lib().ref_lna_read(path.encode(), buf_frames, out.ctypes.data, n, C.byref(S), 1 if backwards else 0)
+    if n2 != n:
+        raise _err() if n2 < 0 else RuntimeError("frame count changed between reads")
+    return out
 
 
 def phone_probs(cfg_path, model_base, recipe_path, out_dir, lnabytes=2, extra=(), timeout=3600):

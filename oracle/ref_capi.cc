@@ -11,6 +11,7 @@
 // The LNA byte stream itself is produced by the literal aku/phone_probs.cc,
 // built as oracle/_ref/ref_phone_probs.
 #include <stdio.h>
+#include <algorithm>
 #include <string.h>
 #include <string>
 #include <exception>
@@ -18,6 +19,7 @@
 #include "FeatureGenerator.hh"
 #include "FeatureModules.hh"
 #include "HmmSet.hh"
+#include "LnaReaderCircular.hh"   // decoder/src: the consumer of the LNA stream
 
 using namespace aku;
 
@@ -145,6 +147,33 @@ int ref_gaussian_loglik(void *h, const double *feats, long F, int D, double *out
     return 0;
   } catch (std::string &s) { return fail(s); }
   catch (std::exception &e) { return fail(e.what()); }
+}
+
+// Reads an LNA file with the DECODER's reader (decoder/src/LnaReaderCircular.cc:46-101,130-209): go_to(frame) for
+// frames 0.. until it reports the end, log_prob(model) for every model.  Returns the number of frames; *n_models_out
+// = number of models in the header.  out may be NULL (count only); with `backwards` the frames still inside the
+// reader's circular buffer are revisited in descending order afterwards (the decoder steps back like that), values
+// must agree.
+long ref_lna_read(const char *path, int buf_frames, float *out, long max_frames, int *n_models_out, int backwards)
+{
+  LnaReaderCircular r;
+  r.open_file(path, buf_frames);
+  const int S = r.num_models();
+  if (n_models_out) *n_models_out = S;
+  long n = 0;
+  while (r.go_to((int)n)) {
+    if (out && n < max_frames)
+      for (int s = 0; s < S; s++) out[n * S + s] = r.log_prob(s);
+    n++;
+  }
+  if (backwards && out)
+    for (long f = std::min(n, max_frames) - 1; f >= 0 && f > n - buf_frames; f -= 3) {
+      if (!r.go_to((int)f)) { r.close(); return fail("go_to failed on a backward seek"); }
+      for (int s = 0; s < S; s++)
+        if (out[f * S + s] != r.log_prob(s)) { r.close(); return fail("backward seek returned different values"); }
+    }
+  r.close();
+  return n;
 }
 
 }  // extern "C"

@@ -90,6 +90,13 @@ def test_cpp_tool_matches_python_and_reference(engine, ref_small, tmp_path, lnab
         assert d.max() <= 1 and (d != 0).mean() <= 0.03
     lp, S, nb = formats.read_lna(str(out_cpp / "utt0.lna"))      # decoder-side reader contract
     assert (S, nb) == (g["lik"].shape[1], lnabytes) and lp.shape == g["lik"].shape
+    # ... and the decoder's own reader (decoder/src/LnaReaderCircular.cc, built into oracle/_ref) on our files
+    from oracle import ref
+    assert ref.available(), "oracle/_ref (prebuilt) did not travel to the GPU box"
+    for i in range(len(cuts)):
+        dec = ref.lna_read(str(out_cpp / ("utt%d.lna" % i)))
+        mine, S2, _ = formats.read_lna(str(out_cpp / ("utt%d.lna" % i)))
+        assert dec.shape == (engine.num_frames(cuts[i].size), S) and np.array_equal(dec, np.asarray(mine, dtype=np.float32))
 
 
 def test_cpp_tool_flags(engine, ref_small, tmp_path):

@@ -86,6 +86,29 @@ def test_gaussian_clustering_bit_exact_vs_reference(ref_clust):
     assert not np.array_equal(oracle_np.state_likelihoods(g["model"], g["feats"], clustering=cl), g["lik0"])
 
 
+def test_decoder_reader_consumes_lna(ref_small, tmp_path):
+    """The consumer of the stream: the decoder's own LnaReaderCircular (decoder/src/LnaReaderCircular.cc:46-101,130-209,
+    compiled into oracle/_ref) reads the reference's LNA files; the Python reader the other tests use
+    (aaltoasr_b200.formats.read_lna) returns the same floats, and they are what the oracle encodes."""
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    from aaltoasr_b200 import formats
+    g = ref_small
+    for nb in (2, 4):
+        p = str(tmp_path / ("a%d.lna" % nb))
+        open(p, "wb").write(g["lna%d" % nb].tobytes())
+        lp = ref.lna_read(p)
+        mine, S, b = formats.read_lna(p)
+        assert (S, b) == (g["lik"].shape[1], nb) and lp.shape == g["lik"].shape
+        assert np.array_equal(lp, np.asarray(mine, dtype=np.float32))
+        rec, want = oracle_np.lna_records(g["lik"], nb)
+        if nb == 4:
+            assert np.array_equal(lp, want)
+        else:
+            codes = rec.reshape(-1).view(">u2").astype(np.float64).reshape(lp.shape)
+            assert np.array_equal(lp, (codes / -1820.0).astype(np.float32))
+
+
 @pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
 def test_gmm_lna_bit_exact_vs_reference(case, request):
     """State likelihoods equal the reference's doubles bit for bit; LNA bytes equal the files the
