@@ -53,6 +53,7 @@ SYMBOLS = {
     "akugpu_model_dim": (C.c_int, [C.c_void_p]),
     "akugpu_model_num_gaussians": (C.c_int, [C.c_void_p]),
     "akugpu_gmm_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "akugpu_gmm_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_void_p]),
     "akugpu_gmm_lna": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "akugpu_phone_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),

@@ -527,16 +527,18 @@ int akugpu_model_dim(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->h
 int akugpu_model_num_gaussians(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->hm.G : AKUGPU_E_STATE; }
 
 // ---- scoring -----------------------------------------------------------------------
-int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)
+// Shared body of akugpu_gmm_score / akugpu_gmm_logprobs.  tiny > 0: decoder log-prob mode, out = float [F x S] of
+// (float) log(max(likelihood, tiny)) whatever the precision.
+static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out, double tiny)
 {
-  API_BEGIN
   require_model(ctx);
   if (n_frames < 0 || (n_frames && (!feats || !out))) throw Error(AKUGPU_E_ARG, "bad n_frames / NULL buffers");
   if (precision != AKUGPU_F32 && precision != AKUGPU_F64) throw Error(AKUGPU_E_ARG, "precision must be AKUGPU_F32 or AKUGPU_F64");
   const int S = ctx->hm.S, D = ctx->hm.D;
-  if (n_frames == 0 || S == 0) return AKUGPU_OK;
+  if (n_frames == 0 || S == 0) return;
+  const bool logmode = tiny > 0;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
-  const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
+  const size_t esz = (precision == AKUGPU_F64 && !logmode) ? 8 : 4;        // element size of the result
   const bool odev = is_device_ptr(out);
   uint8_t *d_out = (uint8_t *)out;
   if (!odev) { ctx->d_tmp.reserve((size_t)n_frames * S * esz); d_out = ctx->d_tmp.as<uint8_t>(); }
@@ -544,30 +546,29 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   bool redo = false;
   do {   // a second pass only when the fp16x2 scorer met a feature outside its range (see tc16_needs_redo)
   const int use_tc = tc_mode(ctx, precision);
-  const bool full = (ctx->hm.n_full > 0 && !use_tc) || clustering_on(ctx);    // scored in double whatever was asked
+  const bool dbl = precision == AKUGPU_F64 || (ctx->hm.n_full > 0 && !use_tc) || clustering_on(ctx);   // scored in double
+  const bool want_f32 = esz == 4;
   const int64_t chunk = pick_chunk(ctx, n_frames, use_tc);
-  ctx->d_sll.reserve((size_t)S * chunk * (full ? 8 : esz));
-  if (full && precision == AKUGPU_F32) ctx->d_lna[0].reserve((size_t)S * chunk * 4);
+  ctx->d_sll.reserve((size_t)S * chunk * (dbl ? 8 : 4));
+  if (dbl && want_f32) ctx->d_lna[0].reserve((size_t)S * chunk * 4);
   for (int64_t c0 = 0; c0 < n_frames; c0 += chunk) {
     const int64_t c1 = std::min(n_frames, c0 + chunk);
     StageScope sc(ctx, 1);
-    if (full) {
+    if (dbl) {
       if (ctx->hm.n_full > 0) launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
       else launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
-      if (precision == AKUGPU_F32) {
-        launch_lin_to_log_f32(ctx, ctx->d_sll.as<double>(), (int64_t)S * chunk, ctx->d_lna[0].as<float>());
+      if (want_f32) {
+        launch_lin_to_log_f32(ctx, ctx->d_sll.as<double>(), (int64_t)S * chunk, ctx->d_lna[0].as<float>(), logmode ? tiny : 0.0);
         launch_transpose_f32(ctx, ctx->d_lna[0].as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
       } else {
         launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
       }
-    } else if (precision == AKUGPU_F32) {
+    } else {
       if (use_tc == 2) launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
       else if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
       else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      if (logmode) launch_floor_f32(ctx, ctx->d_sll.as<float>(), (int64_t)S * chunk, (float)log(tiny));
       launch_transpose_f32(ctx, ctx->d_sll.as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
-    } else {
-      launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
-      launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
     }
   }
   redo = !redo && tc16_needs_redo(ctx, use_tc);
@@ -575,6 +576,21 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   } while (redo);
   if (!odev) AKU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_frames * S * esz, cudaMemcpyDeviceToHost, ctx->stream));
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)
+{
+  API_BEGIN
+  gmm_score_impl(ctx, feats, feats_f64, n_frames, precision, out, 0.0);
+  API_END
+}
+
+int akugpu_gmm_logprobs(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, double tiny,
+                        float *out)
+{
+  API_BEGIN
+  if (!(tiny > 0)) throw Error(AKUGPU_E_ARG, "tiny must be > 0 (decode-stream uses 1e-30, phone_probs 1e-50)");
+  gmm_score_impl(ctx, feats, feats_f64, n_frames, precision, out, tiny);
   API_END
 }
 

@@ -127,10 +127,16 @@ __global__ void mixture_f64(const double *__restrict__ lik_g, int64_t ldF, int64
   lin[(int64_t)s * ld_out + f] = l;
 }
 
-__global__ void lin_to_log_f32(const double *__restrict__ lin, int64_t n, float *__restrict__ out)
+// (float) safe_log(x): log(tiny) below tiny (tiny = 0: plain log)
+__global__ void lin_to_log_f32(const double *__restrict__ lin, int64_t n, double tiny, float *__restrict__ out)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)log(lin[i]);
+  if (i < n) { const double x = lin[i]; out[i] = (float)log(x < tiny ? tiny : x); }
+}
+__global__ void floor_f32(float *__restrict__ x, int64_t n, float floor_at)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = fmaxf(x[i], floor_at);          // NaN -> floor
 }
 
 // Frames [f_begin, f_end) -> lin[state][ldF] (linear double likelihoods, floored) for pools with full Gaussians.
@@ -166,9 +172,15 @@ void launch_gmm_full_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int6
   ctx->launches++;
 }
 
-void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float *out)
+void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float *out, double tiny)
 {
-  lin_to_log_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lin, n, out);
+  lin_to_log_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lin, n, tiny, out);
+  AKU_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+void launch_floor_f32(akugpu_ctx *ctx, float *x, int64_t n, float floor_at)
+{
+  floor_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, n, floor_at);
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
 }

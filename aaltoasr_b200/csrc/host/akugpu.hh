@@ -157,6 +157,12 @@ public:
     }
     m_cur = -1;
   }
+  // The in-process decoder feed of decoder/decode-stream.cc:191-207: (float) log(max(likelihood, tiny)) for every state
+  // of the frames [first, first + n) of `feats` (n = 1: the per-frame loop), ready for Toolbox::set_one_frame.
+  void log_probs(const double *feats, int64_t n_frames, std::vector<float> &out, double tiny = 1e-30) {
+    out.resize((size_t)n_frames * m_S);
+    check(m_e.ctx(), akugpu_gmm_logprobs(m_e.ctx(), feats, 1, n_frames, m_prec, tiny, out.data()));
+  }
   void reset_cache() { m_cur = -1; }
   void precompute_likelihoods(int frame) { m_cur = frame; }
   // Linear likelihood floored at 1e-50, as aku::HmmSet::state_likelihood returns (aku/HmmSet.cc:470-481).

@@ -20,7 +20,8 @@ void pipe_rates(akugpu_ctx *ctx, double out[8]);
 // gmm_full.cu
 void launch_gmm_full_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, double *lin,
                          int64_t ldF);
-void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float *out);
+void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float *out, double tiny = 0.0);
+void launch_floor_f32(akugpu_ctx *ctx, float *x, int64_t n, float floor_at);
 
 // gmm_tc.cu (tensor-core scorer, experimental)
 void model_pack_tc(akugpu_ctx *ctx);

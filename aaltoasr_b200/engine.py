@@ -239,6 +239,14 @@ class AkuGpu:
         self._ck(self._lib.akugpu_gmm_score(self._h, _ptr(feats), _is_f64(feats), F, precision, _ptr(out)))
         return out
 
+    def gmm_logprobs(self, feats, precision=F32, tiny=1e-30, out=None):
+        """The in-process decoder feed of decoder/decode-stream.cc: (float) log(max(likelihood, tiny)), un-normalised."""
+        F = int(feats.shape[0])
+        if out is None:
+            out = np.empty((F, self.num_states), dtype=np.float32)
+        self._ck(self._lib.akugpu_gmm_logprobs(self._h, _ptr(feats), _is_f64(feats), F, precision, float(tiny), _ptr(out)))
+        return out
+
     def gmm_lna(self, feats, precision=F32, lnabytes=2, normalize=True, out=None):
         F = int(feats.shape[0])
         if out is None:

@@ -147,6 +147,14 @@ int akugpu_model_num_gaussians(akugpu_ctx *ctx);
 int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames,
                      int precision, void *out);
 
+/* The in-process decoder feed (decoder/decode-stream.cc:59-67,191-207 -> Toolbox::set_one_frame -> OneFrameAcoustics::set,
+ * decoder/src/OneFrameAcoustics.cc:23-30): un-normalised log-probabilities
+ *   out[f][s] = (float) safe_log(state_likelihood(s)),   safe_log(x) = log(max(x, tiny))
+ * for F frames at once (F = 1 serves a per-frame loop: ~40 us per call).  decode-stream uses tiny = 1e-30; the
+ * likelihood itself is floored at 1e-50 by HmmSet as always.  out is float [F x S] for either precision. */
+int akugpu_gmm_logprobs(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, double tiny,
+                        float *out);
+
 /* Scores + the normalise/quantise loop of aku/phone_probs.cc:225-262.
  *   lnabytes 2: big-endian uint16 codes; 4: IEEE float32 little-endian
  *   normalize 0 == phone_probs --no-normalization

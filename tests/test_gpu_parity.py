@@ -308,6 +308,28 @@ def test_throughput_scorers_other_shapes(engine, D, max_mix):
     assert ok.mean() >= 0.999, (D, max_mix, 1 - ok.mean())
 
 
+@pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
+def test_decoder_logprob_feed(engine, case, request):
+    """akugpu_gmm_logprobs = what decoder/decode-stream.cc:191-207 hands to OneFrameAcoustics per frame:
+    (float) log(max(state_likelihood, 1e-30)), un-normalised.  Parity mode equals the oracle up to the float cast of a
+    1-ulp exp difference; throughput mode within the usual bar; one frame at a time gives the same rows."""
+    g = request.getfixturevalue(case)
+    load_model(engine, g["model"])
+    want = np.log(np.maximum(g["lik"], 1e-30)).astype(np.float32)
+    got64 = engine.gmm_logprobs(g["feats"], precision=F64, tiny=1e-30)
+    assert got64.dtype == np.float32 and got64.shape == want.shape
+    assert np.abs(got64.astype(np.float64) - want).max() <= 8e-6 and (got64 != want).mean() < 0.01
+    assert got64.min() >= np.float32(np.log(1e-30))
+    got32 = engine.gmm_logprobs(g["feats"].astype(np.float32), precision=F32, tiny=1e-30)
+    err = np.abs(got32.astype(np.float64) - want) / (1 + np.abs(want) / 40)
+    assert err.max() <= 3e-5, err.max()
+    for f in (0, 17, want.shape[0] - 1):       # the per-frame loop of the decoder
+        row = engine.gmm_logprobs(g["feats"][f:f + 1], precision=F64, tiny=1e-30)
+        assert np.array_equal(row[0], got64[f])
+    with pytest.raises(AkuGpuError, match="tiny must be > 0"):
+        engine.gmm_logprobs(g["feats"], precision=F64, tiny=0.0)
+
+
 def test_fp16_range_fallback(engine, ref_small):
     """A feature far outside the fp16 range of the default scorer's scaled terms makes the call fall back to the
     bf16x3 kernel: results stay finite and the other frames are unchanged."""
