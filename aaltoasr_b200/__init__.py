@@ -8,7 +8,7 @@ CUDA device is missing -- there is no CPU fallback.
 """
 from ._lib import AkuGpuError, load_library, library_path
 from .engine import AkuGpu, F32, F64
-from .hostapi import FeatureGenerator, HmmSet, PhoneProbs
+from .hostapi import FeatureGenerator, HmmSet, PhoneProbs, SpeakerConfig, parse_speaker_file
 
-__all__ = ["AkuGpu", "AkuGpuError", "F32", "F64", "FeatureGenerator", "HmmSet", "PhoneProbs",
+__all__ = ["AkuGpu", "AkuGpuError", "F32", "F64", "FeatureGenerator", "HmmSet", "PhoneProbs", "SpeakerConfig", "parse_speaker_file",
            "load_library", "library_path"]

@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../../include/akugpu.h"
@@ -172,6 +173,140 @@ private:
   Engine &m_e;
   int m_prec, m_S, m_cur;
   std::vector<double> m_lik;
+};
+
+// Speaker / utterance adaptation parameters for FEATURE modules (aku::SpeakerConfig, aku/SpeakerConfig.cc:20-381;
+// phone_probs -S file.spkc, aku/phone_probs.cc:93-94,192-197).  File format:
+//     speaker <id | default>            (or: utterance <id | default>)
+//     {
+//       [feature] <module name>
+//       {
+//         key value ...                 e.g. matrix / bias of a lin_transform (CMLLR), mean / scale of a normalization
+//       }
+//     }
+// set_speaker() / set_utterance() push the stored parameters through FeatureModule::set_parameters
+// (akugpu_frontend_set_parameters).  `model <name>` entries (model-level transformations, aku/ModelModules.hh) select a
+// path outside this library's scope and are refused.
+class SpeakerConfig {
+public:
+  explicit SpeakerConfig(Engine &e) : m_e(e), m_default_speaker_set(false), m_default_utterance_set(false) {}
+  void read_speaker_file(const std::string &path) {
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) throw std::string("could not open speaker configuration ") + path;
+    std::vector<std::string> lines;
+    char buf[1 << 16];
+    std::string cur;
+    while (fgets(buf, sizeof buf, fp)) {
+      cur += buf;
+      if (!cur.empty() && cur[cur.size() - 1] == '\n') { lines.push_back(clean(cur)); cur.clear(); }
+    }
+    if (!cur.empty()) lines.push_back(clean(cur));
+    fclose(fp);
+    size_t i = 0;
+    int lineno = 0;
+    auto next = [&](std::string &out) -> bool {       // next non-empty line
+      while (i < lines.size()) { lineno++; out = lines[i++]; if (!out.empty()) return true; }
+      return false;
+    };
+    std::string line;
+    while (next(line)) {
+      std::vector<std::string> f = split(line, 0);
+      if (f.size() != 2 || (f[0] != "speaker" && f[0] != "utterance")) throw fmt("SpeakerConfig: Syntax error on line %d: ", lineno) + line;
+      const bool is_speaker = f[0] == "speaker", is_default = f[1] == "default";
+      ModuleMap *dst;
+      if (is_speaker) {
+        if (is_default && m_default_speaker_set) throw fmt("SpeakerConfig: Default speaker configuration already defined, redefinition on line %d: ", lineno) + line;
+        if (is_default) { m_default_speaker_set = true; dst = &m_default_speaker; } else dst = &m_speakers[f[1]];
+      } else {
+        if (is_default && m_default_utterance_set) throw fmt("SpeakerConfig: Default utterance configuration already defined, redefinition on line %d: ", lineno) + line;
+        if (is_default) { m_default_utterance_set = true; dst = &m_default_utterance; } else dst = &m_utterances[f[1]];
+      }
+      if (!next(line)) break;
+      if (line != "{") throw std::string("'{' expected in speaker config file: ") + line;
+      while (next(line)) {
+        if (line == "}") break;
+        std::vector<std::string> parts = split(line, 2);
+        std::string ns = "feature", name = line;
+        if (parts.size() == 2) {
+          if (parts[0] != "model" && parts[0] != "feature") throw fmt("SpeakerConfig: Unknown module namespace at line %d", lineno);
+          ns = parts[0]; name = parts[1];
+        }
+        if (ns == "model")
+          throw fmt("SpeakerConfig: error on line %d: ", lineno) + "model transformations are outside the accelerated scope (" + name + ")";
+        // module parameters: a ModuleConfig block (aku/ModuleConfig.cc:166-203)
+        if (!next(line)) throw std::string("SpeakerConfig: Failed reading module parameters around line ") + fmt("%d: ", lineno) + "unexpected end of module config file";
+        if (line != "{") throw std::string("SpeakerConfig: Failed reading module parameters around line ") + fmt("%d: ", lineno) + "'{' expected in module config file: " + line;
+        std::string text;
+        while (true) {
+          if (!next(line)) throw std::string("SpeakerConfig: Failed reading module parameters around line ") + fmt("%d: ", lineno) + "unexpected end of module config file";
+          if (line == "}") break;
+          text += line + "\n";
+        }
+        (*dst)[name] = text;
+      }
+    }
+  }
+  void set_speaker(const std::string &speaker_id) {
+    if (!m_cur_utterance.empty()) set_utterance("");        // the utterance level is reset with the speaker
+    if (speaker_id.empty()) {
+      if (!m_default_speaker_set) throw std::string("SpeakerConfig: No speaker defined, needs a default speaker.");
+      apply(m_default_speaker);
+    } else {
+      std::map<std::string, ModuleMap>::const_iterator it = m_speakers.find(speaker_id);
+      if (it == m_speakers.end()) {
+        if (!m_default_speaker_set) throw std::string("SpeakerConfig: Unknown speaker ") + speaker_id + ", and default speaker settings are missing.";
+        it = m_speakers.insert(std::make_pair(speaker_id, m_default_speaker)).first;
+      }
+      apply(it->second);
+    }
+    m_cur_speaker = speaker_id;
+  }
+  void set_utterance(const std::string &utterance_id) {
+    if (utterance_id.empty()) {
+      if (!m_default_utterance_set) throw std::string("SpeakerConfig: Default utterance is required.");
+      apply(m_default_utterance);
+    } else {
+      std::map<std::string, ModuleMap>::const_iterator it = m_utterances.find(utterance_id);
+      if (it == m_utterances.end()) {
+        if (!m_default_utterance_set) throw std::string("SpeakerConfig: Unknown utterance ") + utterance_id + ", and default utterance settings are missing.";
+        it = m_utterances.insert(std::make_pair(utterance_id, m_default_utterance)).first;
+      }
+      apply(it->second);
+    }
+    m_cur_utterance = utterance_id;
+  }
+  const std::string &get_cur_speaker() const { return m_cur_speaker; }
+  const std::string &get_cur_utterance() const { return m_cur_utterance; }
+private:
+  typedef std::map<std::string, std::string> ModuleMap;     // module name -> `key value` lines
+  void apply(const ModuleMap &m) {
+    for (ModuleMap::const_iterator it = m.begin(); it != m.end(); ++it)
+      check(m_e.ctx(), akugpu_frontend_set_parameters(m_e.ctx(), it->first.c_str(), it->second.c_str()));
+  }
+  static std::string clean(const std::string &s) {
+    size_t b = s.find_first_not_of(" \t\r\n"), e = s.find_last_not_of(" \t\r\n");
+    return b == std::string::npos ? std::string() : s.substr(b, e - b + 1);
+  }
+  static std::vector<std::string> split(const std::string &s, int max_fields) {   // whitespace, at most max_fields (0 = all)
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+      while (i < s.size() && (s[i] == ' ' || s[i] == '\t')) i++;
+      if (i >= s.size()) break;
+      if (max_fields && (int)out.size() == max_fields - 1) { out.push_back(s.substr(i)); break; }
+      size_t j = i;
+      while (j < s.size() && s[j] != ' ' && s[j] != '\t') j++;
+      out.push_back(s.substr(i, j - i));
+      i = j;
+    }
+    return out;
+  }
+  static std::string fmt(const char *f, int v) { char b[256]; snprintf(b, sizeof b, f, v); return b; }
+  Engine &m_e;
+  std::map<std::string, ModuleMap> m_speakers, m_utterances;
+  ModuleMap m_default_speaker, m_default_utterance;
+  bool m_default_speaker_set, m_default_utterance_set;
+  std::string m_cur_speaker, m_cur_utterance;
 };
 
 }  // namespace akugpu

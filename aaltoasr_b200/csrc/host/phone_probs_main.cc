@@ -1,7 +1,7 @@
 // akugpu_phone_probs -- the reference tool aku/phone_probs.cc re-hosted on the GPU library.
 // Same flags (aku/phone_probs.cc:60-81) and the same per-utterance LNA files; utterances of a recipe
 // are batched into GPU calls (-C clusters / --eval-minc / --eval-ming included: the Gaussian-clustering
-// approximation).  -S speakers selects a path outside the accelerated scope and is refused rather than ignored.
+// approximation; -S speakers: per-speaker / per-utterance parameters of feature modules, e.g. a CMLLR lin_transform).
 #include <errno.h>
 #include <math.h>
 #include <stdlib.h>
@@ -11,7 +11,7 @@
 #include <sstream>
 #include "akugpu.hh"
 
-struct Utt { std::string audio, lna; double start_time, end_time; };
+struct Utt { std::string audio, lna, speaker, utterance; double start_time, end_time; };
 
 static bool file_nonempty(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
 
@@ -30,7 +30,7 @@ static std::vector<Utt> read_recipe(const std::string &path, int batch, int bind
     std::string f;
     while (ss >> f) { size_t e = f.find('='); if (e != std::string::npos) kv[f.substr(0, e)] = f.substr(e + 1); }
     Utt u;
-    u.audio = kv["audio"]; u.lna = kv["lna"];
+    u.audio = kv["audio"]; u.lna = kv["lna"]; u.speaker = kv["speaker"]; u.utterance = kv["utterance"];
     u.start_time = kv.count("start-time") ? atof(kv["start-time"].c_str()) : 0;
     u.end_time = kv.count("end-time") ? atof(kv["end-time"].c_str()) : 0;
     all.push_back(u);
@@ -46,7 +46,7 @@ static std::vector<Utt> read_recipe(const std::string &path, int batch, int bind
 
 int main(int argc, char **argv)
 {
-  std::string base, gk, mc, ph, cfg, recipe, outdir, clusters;
+  std::string base, gk, mc, ph, cfg, recipe, outdir, clusters, speakers;
   double eval_minc = 0, eval_ming = 0.1;       // defaults of aku/phone_probs.cc:74-75
   int lnabytes = 2, batch = 0, bindex = 0, info = 0, device = 0, precision = AKUGPU_F32;
   bool raw_input = false, lna_by_audio = false, no_overwrite = false, no_norm = false;
@@ -68,6 +68,7 @@ int main(int argc, char **argv)
                "  -a, --lnabyaudio       name LNA files by the audio file\n  -o, --output-dir=DIR   base path for LNAs\n"
                "  -R, --raw-input        raw audio input\n      --lnabytes=INT     2 (default) or 4\n"
                "  -n, --no-overwrite     skip existing non-empty LNA files\n  -N, --no-normalization\n"
+               "  -S, --speakers=FILE    speaker configuration file (feature-module parameters per speaker / utterance)\n"
                "  -C, --clusters=FILE    Gaussian clustering (.gcl)\n      --eval-minc=FLOAT  minimum ratio of top clusters to evaluate (0)\n"
                "      --eval-ming=FLOAT  minimum ratio of Gaussians to evaluate (0.1)\n"
                "  -B, --batch=INT  -I, --bindex=INT   recipe batching\n  -i, --info=INT\n"
@@ -93,8 +94,7 @@ int main(int argc, char **argv)
       else if (a == "-C" || a == "--clusters") clusters = val();
       else if (a == "--eval-minc") eval_minc = atof(val().c_str());
       else if (a == "--eval-ming") eval_ming = atof(val().c_str());
-      else if (a == "-S" || a == "--speakers")
-        throw std::string("option ") + a + " selects a path outside the accelerated scope (speaker adaptation)";
+      else if (a == "-S" || a == "--speakers") speakers = val();
       else throw std::string("unknown option ") + a;
     }
     if (cfg.empty()) throw std::string("Must give --config");
@@ -109,6 +109,8 @@ int main(int argc, char **argv)
     if (!base.empty()) model.read_all(base);
     else if (!gk.empty() && !mc.empty() && !ph.empty()) model.read_files(gk, mc, ph);
     else throw std::string("Must give either --base or all --gk, --mc and --ph");
+    akugpu::SpeakerConfig speaker_conf(eng);
+    if (!speakers.empty()) speaker_conf.read_speaker_file(speakers);     // aku/phone_probs.cc:93-94,133-134
     if (!clusters.empty()) {          // aku/phone_probs.cc:112-117
       model.read_clustering(clusters);
       model.set_clustering_min_evals(eval_minc, eval_ming);
@@ -141,7 +143,12 @@ int main(int argc, char **argv)
       std::vector<int16_t> pcm;
       std::vector<int64_t> uo(1, 0);
       size_t j = i;
-      while (j < todo.size() && (j == i || (long)pcm.size() < max_batch_samples)) {
+      if (!speakers.empty()) {        // aku/phone_probs.cc:192-197; a GPU call covers utterances that share the parameters
+        speaker_conf.set_speaker(todo[i].speaker);
+        if (!todo[i].utterance.empty()) speaker_conf.set_utterance(todo[i].utterance);
+      }
+      while (j < todo.size() && (j == i || ((long)pcm.size() < max_batch_samples &&
+                                            (speakers.empty() || (todo[j].speaker == todo[i].speaker && todo[j].utterance == todo[i].utterance))))) {
         std::vector<int16_t> one;
         int rate = 0;
         akugpu::read_audio(todo[j].audio, gen.sample_rate(), raw_input, one, rate);

@@ -144,6 +144,99 @@ class HmmSet:
         return float(self._row[state])
 
 
+def parse_speaker_file(text):
+    """The .spkc format of aku::SpeakerConfig::read_speaker_file (aku/SpeakerConfig.cc:20-147):
+    `speaker|utterance <id|default>` / `{` / `[feature] <module>` / `{ key value ... }` / `}`.
+    Returns {"speaker": {id: {module: text}}, "utterance": {...}} with the parameter text as `key value` lines."""
+    lines = [ln.strip() for ln in text.splitlines()]
+    pos = 0
+
+    def nxt():
+        nonlocal pos
+        while pos < len(lines):
+            ln = lines[pos]
+            pos += 1
+            if ln:
+                return ln
+        return None
+
+    out = {"speaker": {}, "utterance": {}}
+    while True:
+        ln = nxt()
+        if ln is None:
+            break
+        f = ln.split()
+        if len(f) != 2 or f[0] not in ("speaker", "utterance"):
+            raise AkuGpuError(-2, "SpeakerConfig: Syntax error on line %d: %s" % (pos, ln))
+        if f[1] in out[f[0]] and f[1] == "default":
+            raise AkuGpuError(-2, "SpeakerConfig: Default %s configuration already defined, redefinition on line %d: %s" % (f[0], pos, ln))
+        mods = out[f[0]].setdefault(f[1], {})
+        if nxt() != "{":
+            raise AkuGpuError(-2, "'{' expected in speaker config file")
+        while True:
+            ln = nxt()
+            if ln is None or ln == "}":
+                break
+            parts = ln.split(None, 1)
+            ns, name = ("feature", ln) if len(parts) < 2 else (parts[0], parts[1])
+            if ns not in ("model", "feature"):
+                raise AkuGpuError(-2, "SpeakerConfig: Unknown module namespace at line %d" % pos)
+            if ns == "model":
+                raise AkuGpuError(-2, "SpeakerConfig: error on line %d: model transformations are outside the accelerated scope (%s)" % (pos, name))
+            if nxt() != "{":
+                raise AkuGpuError(-2, "SpeakerConfig: Failed reading module parameters around line %d: '{' expected in module config file" % pos)
+            body = []
+            while True:
+                ln = nxt()
+                if ln is None:
+                    raise AkuGpuError(-2, "SpeakerConfig: Failed reading module parameters around line %d: unexpected end of module config file" % pos)
+                if ln == "}":
+                    break
+                body.append(ln)
+            mods[name] = "\n".join(body) + ("\n" if body else "")
+    return out
+
+
+class SpeakerConfig:
+    """aku::SpeakerConfig for feature modules (aku/SpeakerConfig.cc:239-336): set_speaker / set_utterance push the stored
+    parameters through FeatureModule::set_parameters (akugpu_frontend_set_parameters)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.conf = {"speaker": {}, "utterance": {}}
+        self.cur_speaker = ""
+        self.cur_utterance = ""
+
+    def read_speaker_file(self, path):
+        self.conf = parse_speaker_file(open(path).read())
+
+    def _apply(self, kind, ident, what):
+        table = self.conf[kind]
+        if not ident:
+            if "default" not in table:
+                raise AkuGpuError(-2, "SpeakerConfig: No speaker defined, needs a default speaker." if kind == "speaker"
+                                  else "SpeakerConfig: Default utterance is required.")
+            mods = table["default"]
+        elif ident in table and ident != "default":
+            mods = table[ident]
+        else:
+            if "default" not in table:
+                raise AkuGpuError(-2, "SpeakerConfig: Unknown %s %s, and default %s settings are missing." % (what, ident, what))
+            mods = table["default"]
+        for name in sorted(mods):
+            self.engine.frontend_set_parameters(name, mods[name])
+
+    def set_speaker(self, speaker_id):
+        if self.cur_utterance:
+            self.set_utterance("")
+        self._apply("speaker", speaker_id, "speaker")
+        self.cur_speaker = speaker_id
+
+    def set_utterance(self, utterance_id):
+        self._apply("utterance", utterance_id, "utterance")
+        self.cur_utterance = utterance_id
+
+
 class PhoneProbs:
     """aku/phone_probs as an object (and the PPToolbox method names)."""
 

@@ -46,6 +46,14 @@ def ref_clust():
 
 
 @pytest.fixture(scope="session")
+def ref_spk():
+    d = load_golden("ref_spk")
+    d["spkc"] = str(d["spkc"])
+    d["speakers"] = [str(s) for s in d["speakers"]]
+    return d
+
+
+@pytest.fixture(scope="session")
 def aku_tests():
     z = np.load(os.path.join(GOLDEN, "aku_tests.npz"))
     return {k: (str(z[k]) if k.endswith("_cfg") else z[k]) for k in z.files}

@@ -16,6 +16,9 @@ Run in the dev container (needs /root/reference and oracle/_ref built by oracle/
   ref_clust.npz   the Gaussian-clustering approximation (phone_probs -C x.gcl --eval-minc/--eval-ming) on the ref_small
                   model: .gcl text (12 clusters, three Gaussians left unlisted), state likelihoods of the reference's
                   HmmSet for three (min_clusters, min_gaussians) settings, and the LNA files of the literal phone_probs.
+  ref_spk.npz     speaker adaptation through feature-module parameters (phone_probs -S x.spkc): a 39x39 lin_transform
+                  ("cmllr") after the MFCC chain, two speakers with their own matrix + bias and a default speaker, a
+                  three-line recipe (speaker A, speaker B, unknown speaker -> default); LNA files of the literal phone_probs.
   ref_edge.npz    the same for a handmade edge-case model (underflow / denormal / floor regimes,
                   zero-variance dimensions, tiny weights).
 """
@@ -189,6 +192,57 @@ def clust_case(pcm, model, tmp):
               100 * (out["lik%d" % k] != exact).mean() for k in range(3)))
 
 
+SPK_TAIL = """
+module
+{
+  name cmllr
+  type lin_transform
+  sources final
+}
+"""
+
+
+def spk_case(pcm, model, tmp):
+    name = "ref_spk"
+    rng = np.random.default_rng(7005)
+    cfg_text = synth.mfcc39_config() + SPK_TAIL
+    cfg = os.path.join(tmp, name + ".cfg"); base = os.path.join(tmp, name)
+    open(cfg, "w").write(cfg_text)
+    formats.write_model(base, **model)
+    D = 39
+    def block(spk):
+        A = np.eye(D) + 0.05 * rng.standard_normal((D, D))
+        b = 0.3 * rng.standard_normal(D)
+        return ("speaker %s\n{\n  cmllr\n  {\n    matrix %s\n    bias %s\n  }\n}\n\n" %
+                (spk, " ".join("%.6g" % v for v in A.reshape(-1)), " ".join("%.6g" % v for v in b)))
+    spkc = "speaker default\n{\n  feature cmllr\n  {\n  }\n}\n\n" + block("alice") + block("bob")
+    spath = os.path.join(tmp, name + ".spkc")
+    open(spath, "w").write(spkc)
+    cuts = [pcm, pcm[:16000], pcm[5000:22000]]
+    lines = []
+    for i, (c, spk) in enumerate(zip(cuts, ["alice", "bob", "carol"])):
+        w = os.path.join(tmp, "spk%d.wav" % i)
+        formats.write_wav(w, c, 16000)
+        lines.append("audio=%s lna=spk%d.lna speaker=%s" % (w, i, spk))
+    rec = os.path.join(tmp, name + ".recipe")
+    open(rec, "w").write("\n".join(lines) + "\n")
+    od = os.path.join(tmp, "spk_out")
+    os.makedirs(od, exist_ok=True)
+    ref.phone_probs(cfg, base, rec, od, 2, extra=["-S", spath])
+    out = dict(cfg=cfg_text, spkc=spkc, pcm=pcm, cut_ranges=np.array([[0, pcm.size], [0, 16000], [5000, 22000]]),
+               speakers=np.array(["alice", "bob", "carol"]), **{"model_" + k: v for k, v in model.items()})
+    for i in range(3):
+        out["lna2_%d" % i] = np.frombuffer(open(os.path.join(od, "spk%d.lna" % i), "rb").read(), dtype=np.uint8)
+    # the same utterances without -S (identity transform) must differ for alice / bob and agree for carol
+    od2 = os.path.join(tmp, "spk_out0")
+    os.makedirs(od2, exist_ok=True)
+    ref.phone_probs(cfg, base, rec, od2, 2)
+    for i in range(3):
+        out["lna2_plain_%d" % i] = np.frombuffer(open(os.path.join(od2, "spk%d.lna" % i), "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "differs from identity:", [float((out["lna2_%d" % i] != out["lna2_plain_%d" % i]).mean()) for i in range(3)])
+
+
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
@@ -201,6 +255,7 @@ def main():
         feats, _, _ = ref.features(cfg, wav)
         run_case("ref_small", pcm, small_model(feats, 7002), tmp)
         clust_case(pcm, small_model(feats, 7002), tmp)
+        spk_case(pcm, small_model(feats, 7002), tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
         run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 

@@ -156,3 +156,43 @@ def test_cpp_tool_gaussian_clustering(engine, ref_clust, tmp_path):
     assert r.returncode == 0
     exact = np.frombuffer(open(str(out2 / "utt0.lna"), "rb").read(), dtype=np.uint8)
     assert (exact != got).mean() > 0.2
+
+
+def test_cpp_tool_speaker_config(engine, ref_spk, tmp_path):
+    """akugpu_phone_probs -S x.spkc (aku/phone_probs.cc:93-94,192-197): per-speaker lin_transform parameters pushed
+    through FeatureModule::set_parameters between GPU calls; LNA files against the literal phone_probs -S output
+    (end to end from WAV: codes within +-1), the Python mirror writes the same bytes, model-level entries are refused."""
+    from aaltoasr_b200 import SpeakerConfig
+    g = ref_spk
+    cfg = str(tmp_path / "spk.cfg"); open(cfg, "w").write(g["cfg"])
+    base = str(tmp_path / "model"); formats.write_model(base, **g["model"])
+    spkc = str(tmp_path / "x.spkc"); open(spkc, "w").write(g["spkc"])
+    lines = []
+    for i, spk in enumerate(g["speakers"]):
+        a, b = g["cut_ranges"][i]
+        w = str(tmp_path / ("spk%d.wav" % i))
+        formats.write_wav(w, g["pcm"][a:b], 16000)
+        lines.append("audio=%s lna=spk%d.lna speaker=%s" % (w, i, spk))
+    rec = str(tmp_path / "recipe"); open(rec, "w").write("\n".join(lines) + "\n")
+    out = tmp_path / "o"; out.mkdir()
+    r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-S", spkc, "--precision=f64"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    engine.frontend_load_config(cfg)
+    engine.model_read(base)
+    sc = SpeakerConfig(engine)
+    sc.read_speaker_file(spkc)
+    for i, spk in enumerate(g["speakers"]):
+        got = np.frombuffer(open(str(out / ("spk%d.lna" % i)), "rb").read(), dtype=np.uint8)
+        want = g["lna2_%d" % i]
+        assert got.size == want.size and bytes(got[:5]) == bytes(want[:5])
+        d = np.abs(got[5:].view(">u2").astype(int) - want[5:].view(">u2").astype(int))
+        assert d.max() <= 1 and (d != 0).mean() <= 0.03, (spk, d.max(), (d != 0).mean())
+        sc.set_speaker(spk)                                  # the Python mirror drives the same library
+        a, b = g["cut_ranges"][i]
+        mine, _, _ = engine.phone_probs(g["pcm"][a:b], precision=F64, lnabytes=2)
+        assert np.array_equal(mine.reshape(-1), got[5:])
+    open(spkc, "w").write("speaker default\n{\n  model mllr\n  {\n  }\n}\n")
+    r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-S", spkc],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode != 0 and b"outside the accelerated scope" in r.stderr

@@ -86,6 +86,27 @@ def test_gaussian_clustering_bit_exact_vs_reference(ref_clust):
     assert not np.array_equal(oracle_np.state_likelihoods(g["model"], g["feats"], clustering=cl), g["lik0"])
 
 
+def test_speaker_config_vs_reference(ref_spk):
+    """phone_probs -S x.spkc: per-speaker parameters of a feature module (a 39x39 lin_transform).  The oracle pipeline
+    with each speaker's block substituted into the module's configuration reproduces the reference's LNA files (codes
+    within +-1: the oracle's FFT rounds differently from KissFFT); an unknown speaker takes the default block."""
+    from aaltoasr_b200 import parse_speaker_file
+    g = ref_spk
+    conf = parse_speaker_file(g["spkc"])["speaker"]
+    assert sorted(conf) == ["alice", "bob", "default"] and conf["default"] == {"cmllr": ""}
+    for i, spk in enumerate(g["speakers"]):
+        params = conf.get(spk, conf["default"])["cmllr"]
+        cfg = g["cfg"].replace("  sources final\n}", "  sources final\n" + "".join("  " + ln + "\n" for ln in params.splitlines()) + "}")
+        a, b = g["cut_ranges"][i]
+        feats = oracle_np.Pipeline(cfg).run(g["pcm"][a:b])
+        rec, _ = oracle_np.lna_records(oracle_np.state_likelihoods(g["model"], feats), 2)
+        want = g["lna2_%d" % i]
+        assert rec.size == want.size - 5
+        d = np.abs(rec.reshape(-1).view(">u2").astype(int) - want[5:].view(">u2").astype(int))
+        assert d.max() <= 1 and (d != 0).mean() <= 0.03, (spk, d.max(), (d != 0).mean())
+    assert np.array_equal(g["lna2_2"], g["lna2_plain_2"]) and not np.array_equal(g["lna2_0"], g["lna2_plain_0"])
+
+
 def test_decoder_reader_consumes_lna(ref_small, tmp_path):
     """The consumer of the stream: the decoder's own LnaReaderCircular (decoder/src/LnaReaderCircular.cc:46-101,130-209,
     compiled into oracle/_ref) reads the reference's LNA files; the Python reader the other tests use
