@@ -34,11 +34,15 @@ SYMBOLS = {
     "akugpu_frontend_dim": (C.c_int, [C.c_void_p]),
     "akugpu_frontend_sample_rate": (C.c_int, [C.c_void_p]),
     "akugpu_frontend_frame_rate": (C.c_float, [C.c_void_p]),
+    "akugpu_frontend_base_is_pre": (C.c_int, [C.c_void_p]),
     "akugpu_frontend_num_frames": (C.c_int64, [C.c_void_p, C.c_int64]),
     "akugpu_frontend_set_parameters": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "akugpu_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "akugpu_features_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_char_p,
                                         C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "akugpu_features_pre": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "akugpu_features_pre_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_char_p,
+                                            C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "akugpu_model_read": (C.c_int, [C.c_void_p, C.c_char_p]),
     "akugpu_model_read_files": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "akugpu_model_load_diag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -327,6 +327,7 @@ int akugpu_frontend_load_config(akugpu_ctx *ctx, const char *cfg_path)
 int akugpu_frontend_dim(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[ctx->fe.last].dim : AKUGPU_E_STATE; }
 int akugpu_frontend_sample_rate(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[0].sample_rate : AKUGPU_E_STATE; }
 float akugpu_frontend_frame_rate(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[0].frame_rate : -1.f; }
+int akugpu_frontend_base_is_pre(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? (ctx->fe.mods[0].type == M_PRE ? 1 : 0) : AKUGPU_E_STATE; }
 int64_t akugpu_frontend_num_frames(akugpu_ctx *ctx, int64_t n_samples)
 {
   if (!ctx || !ctx->fe.configured) return AKUGPU_E_STATE;
@@ -356,11 +357,21 @@ static void frame_offsets_of(akugpu_ctx *ctx, const int64_t *utt_offsets, int n_
   }
 }
 
-int akugpu_features(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts, void *out, int out_f64,
-                    int64_t *frame_offsets)
+// Bytes per input unit (sample or stored row) of the configured base module; want_pre says which entry point was used.
+static size_t base_unit_bytes(akugpu_ctx *ctx, bool want_pre)
 {
-  API_BEGIN
+  const bool pre = ctx->fe.mods[0].type == M_PRE;
+  if (pre != want_pre)
+    throw Error(AKUGPU_E_STATE, pre ? "the configured base module is `pre`: use akugpu_features_pre / akugpu_features_pre_range"
+                                    : "the configured base module is `audiofile`: akugpu_features_pre needs a `pre` base module");
+  return pre ? (size_t)ctx->fe.mods[0].dim * sizeof(float) : sizeof(int16_t);
+}
+
+static void features_impl(akugpu_ctx *ctx, const void *pcm, const int64_t *utt_offsets, int n_utts, void *out, int out_f64,
+                          int64_t *frame_offsets, bool want_pre)
+{
   require_frontend(ctx);
+  const size_t unit = base_unit_bytes(ctx, want_pre);
   std::vector<int64_t> uo, fo;
   frame_offsets_of(ctx, utt_offsets, n_utts, uo, fo);
   if (frame_offsets) memcpy(frame_offsets, fo.data(), fo.size() * sizeof(int64_t));
@@ -368,7 +379,7 @@ int akugpu_features(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offs
     if (!pcm) throw Error(AKUGPU_E_ARG, "pcm is NULL");
     const int dim = ctx->fe.mods[ctx->fe.last].dim;
     const size_t esz = out_f64 ? 8 : 4;
-    const int16_t *d_pcm = (const int16_t *)to_device(ctx, pcm, (size_t)uo[n_utts] * 2, ctx->d_pcm);
+    const void *d_pcm = to_device(ctx, pcm, (size_t)uo[n_utts] * unit, ctx->d_pcm);
     const bool odev = is_device_ptr(out);
     void *d_out = out;
     if (!odev) { ctx->d_feats.reserve((size_t)fo[n_utts] * dim * esz); d_out = ctx->d_feats.p; }
@@ -376,14 +387,29 @@ int akugpu_features(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offs
     if (!odev) AKU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)fo[n_utts] * dim * esz, cudaMemcpyDeviceToHost, ctx->stream));
     AKU_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+}
+
+int akugpu_features(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts, void *out, int out_f64,
+                    int64_t *frame_offsets)
+{
+  API_BEGIN
+  features_impl(ctx, pcm, utt_offsets, n_utts, out, out_f64, frame_offsets, false);
   API_END
 }
 
-int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples, int start_frame, int end_frame,
-                          const char *module_name, void *out, int out_f64, int *dim_out)
+int akugpu_features_pre(akugpu_ctx *ctx, const float *rows, const int64_t *row_offsets, int n_utts, void *out, int out_f64,
+                        int64_t *frame_offsets)
 {
   API_BEGIN
+  features_impl(ctx, rows, row_offsets, n_utts, out, out_f64, frame_offsets, true);
+  API_END
+}
+
+static void features_range_impl(akugpu_ctx *ctx, const void *pcm, int64_t n_samples, int start_frame, int end_frame,
+                                const char *module_name, void *out, int out_f64, int *dim_out, bool want_pre)
+{
   require_frontend(ctx);
+  const size_t unit = base_unit_bytes(ctx, want_pre);
   int target = -1;
   if (module_name && module_name[0]) {
     for (size_t i = 0; i < ctx->fe.mods.size(); i++)
@@ -396,7 +422,7 @@ int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples
     if (!pcm) throw Error(AKUGPU_E_ARG, "pcm is NULL");
     const size_t esz = out_f64 ? 8 : 4;
     const int64_t n = end_frame - start_frame;
-    const int16_t *d_pcm = (const int16_t *)to_device(ctx, pcm, (size_t)n_samples * 2, ctx->d_pcm);
+    const void *d_pcm = to_device(ctx, pcm, (size_t)n_samples * unit, ctx->d_pcm);
     const bool odev = is_device_ptr(out);
     void *d_out = out;
     if (!odev) { ctx->d_feats.reserve((size_t)n * dim * esz); d_out = ctx->d_feats.p; }
@@ -404,6 +430,21 @@ int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples
     if (!odev) AKU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * dim * esz, cudaMemcpyDeviceToHost, ctx->stream));
     AKU_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+}
+
+int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples, int start_frame, int end_frame,
+                          const char *module_name, void *out, int out_f64, int *dim_out)
+{
+  API_BEGIN
+  features_range_impl(ctx, pcm, n_samples, start_frame, end_frame, module_name, out, out_f64, dim_out, false);
+  API_END
+}
+
+int akugpu_features_pre_range(akugpu_ctx *ctx, const float *rows, int64_t n_rows, int start_frame, int end_frame,
+                              const char *module_name, void *out, int out_f64, int *dim_out)
+{
+  API_BEGIN
+  features_range_impl(ctx, rows, n_rows, start_frame, end_frame, module_name, out, out_f64, dim_out, true);
   API_END
 }
 
@@ -611,6 +652,7 @@ int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_o
   API_BEGIN
   require_frontend(ctx);
   require_model(ctx);
+  base_unit_bytes(ctx, false);       // PCM in: needs an audiofile base module
   const int dim = ctx->fe.mods[ctx->fe.last].dim;
   if (dim != ctx->hm.D)
     throw Error(AKUGPU_E_STATE, fmt("Feature dimension (%d) and model dimension (%d) don't agree", dim, ctx->hm.D));

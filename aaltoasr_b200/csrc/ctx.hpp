@@ -149,7 +149,7 @@ struct PackedTC16 {
 // ---------------------------------------------------------------------------------
 // Front-end module graph (parsed from the reference's feature configuration).
 enum ModType { M_AUDIOFILE, M_FFT, M_MEL, M_POWER, M_MEL_POWER, M_DCT, M_DELTA, M_MERGE, M_CONCAT,
-               M_NORMALIZATION, M_LIN_TRANSFORM, M_MEAN_SUBTRACTOR };
+               M_NORMALIZATION, M_LIN_TRANSFORM, M_MEAN_SUBTRACTOR, M_PRE };
 
 struct Module {
   std::string name;

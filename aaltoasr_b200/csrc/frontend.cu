@@ -274,15 +274,17 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
     static const struct { const char *s; ModType t; } types[] = {
         {"audiofile", M_AUDIOFILE}, {"fft", M_FFT}, {"mel", M_MEL}, {"power", M_POWER}, {"mel_power", M_MEL_POWER},
         {"dct", M_DCT}, {"delta", M_DELTA}, {"merge", M_MERGE}, {"concat", M_CONCAT},
-        {"normalization", M_NORMALIZATION}, {"lin_transform", M_LIN_TRANSFORM}, {"mean_subtractor", M_MEAN_SUBTRACTOR}};
+        {"normalization", M_NORMALIZATION}, {"lin_transform", M_LIN_TRANSFORM}, {"mean_subtractor", M_MEAN_SUBTRACTOR},
+        {"pre", M_PRE}};
     bool known = false;
     for (auto &t : types) if (*type == t.s) { m.type = t.t; known = true; }
     if (!known) {
-      if (*type == "pre" || *type == "vtln" || *type == "sr_norm" || *type == "quanteq")
+      if (*type == "vtln" || *type == "sr_norm" || *type == "quanteq")
         throw Error(AKUGPU_E_CONFIG, "module type '" + *type + "' is not supported by the GPU front-end");
       throw Error(AKUGPU_E_CONFIG, "Unknown module type '" + *type + "'");
     }
-    if (fe.mods.empty() && m.type != M_AUDIOFILE) throw Error(AKUGPU_E_CONFIG, "first module should be a base module");
+    if (fe.mods.empty() && m.type != M_AUDIOFILE && m.type != M_PRE) throw Error(AKUGPU_E_CONFIG, "first module should be a base module");
+    if (!fe.mods.empty() && (m.type == M_AUDIOFILE || m.type == M_PRE)) throw Error(AKUGPU_E_CONFIG, "base module must be the first module: " + m.name);
     if (by_name.count(m.name)) throw Error(AKUGPU_E_CONFIG, "multiple definitions of module name: " + m.name);
     const std::string *sources = b.find("sources");
     if (fe.mods.empty() && sources) throw Error(AKUGPU_E_CONFIG, "can not define sources for the first module");
@@ -310,6 +312,16 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
         int raw = 0; get_int(b, "raw", raw);   // container format is the host reader's business
         m.copy_borders = 1; get_int(b, "copy_borders", m.copy_borders);
         if (m.window_width < 2 || m.window_advance <= 0) throw Error(AKUGPU_E_CONFIG, "AudioFileModule: bad window geometry");
+        break;
+      }
+      case M_PRE: {       // PreModule::set_module_config, aku/FeatureModules.cc:671-689: features read from a file
+        m.frame_rate = 125; m.sample_rate = 16000;
+        get_int(b, "sample_rate", m.sample_rate);
+        get_float(b, "frame_rate", m.frame_rate);
+        int legacy = 0; get_int(b, "legacy_file", legacy);   // header layout is the host reader's business
+        if (!get_int(b, "dim", m.dim)) throw Error(AKUGPU_E_CONFIG, "PreModule: Must set dimension");
+        if (m.dim < 1) throw Error(AKUGPU_E_CONFIG, "PreModule: Must set dimension");
+        m.window_advance = m.sample_rate / m.frame_rate;
         break;
       }
       case M_FFT:
@@ -413,6 +425,7 @@ int64_t frontend_num_frames(const Frontend &fe, int64_t n_samples)
   // Sequential generate(0),generate(1),.. reports eof on the first frame whose window
   // [ws, ws+W+1) runs past the file (aku/FeatureModules.cc:399-404), ws = (int)(f*advance).
   const Module &a = fe.mods[0];
+  if (a.type == M_PRE) return n_samples;        // a `pre` base module: one frame per stored row (PreModule::last_frame :651-662)
   if (n_samples < a.window_width + 1) return 0;
   int64_t f = (int64_t)((float)(n_samples - a.window_width - 1) / a.window_advance);
   while (f > 0 && (int64_t)(int)((int)f * a.window_advance) + a.window_width + 1 > n_samples) f--;
@@ -442,6 +455,22 @@ __device__ __forceinline__ void row_to_frame(const int *__restrict__ row_utt, co
 {
   u = row_utt[r];
   t = utts[u].start - H + (int)(r - utts[u].row_off);
+}
+
+// PreModule::generate (aku/FeatureModules.cc:705-755): the base module's rows are stored float32 features; frames before
+// the file repeat the first row, frames after it the last one.  raw: all utterances' rows back to back.
+__global__ void fe_pre_base(const float *__restrict__ raw, int dim, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                            int64_t n_rows, int H, double *__restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  const int64_t r = i / dim;
+  const int c = (int)(i - r * dim);
+  int u, t;
+  row_to_frame(row_utt, utts, r, H, u, t);
+  const UttDesc ud = utts[u];
+  const int tc = min(max(t, 0), ud.n_frames - 1);
+  out[i] = (double)raw[(ud.pcm_off + tc) * dim + c];
 }
 
 // MelModule::generate, aku/FeatureModules.cc:806-849, one bin from the precomputed triangle weights (see
@@ -847,7 +876,7 @@ Plan make_plan(const Frontend &fe, int target)
 }
 
 // Runs the graph for a set of utterance descriptors whose PCM is device resident.
-void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts, int target, void *d_out, int out_f64,
+void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, int target, void *d_out, int out_f64,
                int64_t out_row_base)
 {
   const Frontend &fe = ctx->fe;
@@ -871,6 +900,8 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
   const UttDesc *du = d_utts.as<UttDesc>();
   const int *dr = d_rowutt.as<int>();
 
+  const int16_t *d_pcm = reinterpret_cast<const int16_t *>(d_in);      // audiofile base; a `pre` base reads float rows
+  const bool pre_base = fe.mods[0].type == M_PRE;
   // ---- fusion patterns (the canonical MFCC chain); anything else runs module by module ----
   const int nm = (int)fe.mods.size();
   std::vector<std::vector<int>> cons(nm);
@@ -922,8 +953,18 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
     }
   }
 
-  // one buffer per module that is materialised (the base module is fused into fft and has none)
+  // one buffer per module that is materialised (the audiofile base module is fused into fft and has none)
   std::vector<std::shared_ptr<DevBuf>> buf(fe.mods.size());
+  if (pre_base) {
+    if (ctx->fe_bufs.empty()) ctx->fe_bufs.resize(1);
+    if (!ctx->fe_bufs[0]) ctx->fe_bufs[0] = std::make_shared<DevBuf>();
+    buf[0] = ctx->fe_bufs[0];
+    buf[0]->reserve((size_t)n_rows * base.dim * sizeof(double));
+    fe_pre_base<<<grid1(n_rows * base.dim, 256), 256, 0, st>>>(reinterpret_cast<const float *>(d_in), base.dim, du, dr, n_rows, H,
+                                                              buf[0]->as<double>());
+    AKU_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
   for (int m = 1; m <= target; m++) {
     if (!plan.needed[m]) continue;
     if ((skip[m] && m != f_out) || m == f_fft) continue;
@@ -935,11 +976,11 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
   for (int m = 1; m <= target; m++) {
     if (!plan.needed[m] || skip[m]) continue;
     const Module &mod = fe.mods[m];
-    if (mod.type != M_FFT)
+    if (mod.type != M_FFT && !pre_base)
       for (int sidx : mod.src)
         if (sidx == 0) throw Error(AKUGPU_E_CONFIG, "the audiofile module can only feed an fft module");
     double *o = buf[m] ? buf[m]->as<double>() : nullptr;
-    const double *s0 = mod.src.empty() || mod.src[0] == 0 ? nullptr : (buf[mod.src[0]] ? buf[mod.src[0]]->as<double>() : nullptr);
+    const double *s0 = mod.src.empty() ? nullptr : (buf[mod.src[0]] ? buf[mod.src[0]]->as<double>() : nullptr);
     const int sdim = mod.src.empty() ? 0 : fe.mods[mod.src[0]].dim;
     const int64_t ne = n_rows * mod.dim;
     switch (mod.type) {
@@ -1041,7 +1082,7 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
     AKU_CUDA(cudaGetLastError());
     ctx->launches++;
   }
-  if (target == 0) throw Error(AKUGPU_E_CONFIG, "the raw audiofile module output is not materialised on the GPU");
+  if (target == 0 && !pre_base) throw Error(AKUGPU_E_CONFIG, "the raw audiofile module output is not materialised on the GPU");
   const int dim = fe.mods[target].dim;
   if (g_x >= 0) {
     const Module &D1 = fe.mods[g_d1], &D2 = fe.mods[g_d2];
@@ -1064,7 +1105,7 @@ void run_graph(akugpu_ctx *ctx, const int16_t *d_pcm, std::vector<UttDesc> &utts
 
 }  // namespace
 
-void frontend_run_range(akugpu_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, int start, int end, int target,
+void frontend_run_range(akugpu_ctx *ctx, const void *d_pcm, int64_t n_samples, int start, int end, int target,
                         void *d_out, int out_f64)
 {
   const int64_t nf = frontend_num_frames(ctx->fe, n_samples);
@@ -1076,7 +1117,7 @@ void frontend_run_range(akugpu_ctx *ctx, const int16_t *d_pcm, int64_t n_samples
   run_graph(ctx, d_pcm, utts, target, d_out, out_f64, 0);
 }
 
-void frontend_run_batch(akugpu_ctx *ctx, const int16_t *d_pcm, const std::vector<int64_t> &utt_off,
+void frontend_run_batch(akugpu_ctx *ctx, const void *d_pcm, const std::vector<int64_t> &utt_off,
                         const std::vector<int64_t> &frame_off, void *d_out, int out_f64)
 {
   const int n = (int)utt_off.size() - 1;

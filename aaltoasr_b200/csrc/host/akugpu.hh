@@ -85,7 +85,30 @@ public:
     check(m_e.ctx(), akugpu_frontend_load_config(m_e.ctx(), path.c_str()));
     m_dim = akugpu_frontend_dim(m_e.ctx());
   }
+  // A `pre` base module reads stored features (int32 dim + float32 rows, feacat -H --raw-output) instead of audio.
+  void open_pre(const std::string &filename) {
+    FILE *fp = fopen(filename.c_str(), "rb");
+    if (!fp) throw std::string("could not open file ") + filename;
+    int dim = 0;
+    if (fread(&dim, sizeof(int), 1, fp) < 1) { fclose(fp); throw std::string("PreModule: Could not read the file."); }
+    m_rows.clear();
+    std::vector<float> buf(4096);
+    size_t k;
+    while ((k = fread(buf.data(), sizeof(float), buf.size(), fp)) > 0) m_rows.insert(m_rows.end(), buf.begin(), buf.begin() + k);
+    fclose(fp);
+    if (dim <= 0 || m_rows.size() % (size_t)dim != 0) throw std::string("PreModule: The file has invalid dimension");
+    m_pre_dim = dim;
+    int64_t ro[2] = {0, (int64_t)(m_rows.size() / dim)}, fo[2] = {0, 0};
+    check(m_e.ctx(), akugpu_features_pre(m_e.ctx(), NULL, ro, 1, NULL, 1, fo));
+    m_frames = (int)fo[1];
+    m_feats.resize((size_t)m_frames * m_dim);
+    check(m_e.ctx(), akugpu_features_pre(m_e.ctx(), m_rows.data(), ro, 1, m_feats.data(), 1, fo));
+    m_eof = false;
+    m_pcm.clear();
+  }
   void open(const std::string &filename) {
+    if (akugpu_frontend_base_is_pre(m_e.ctx()) == 1) { open_pre(filename); return; }
+    m_rows.clear();
     int rate = 0;
     read_audio(filename, sample_rate(), false, m_pcm, rate);
     if (rate != sample_rate()) {     // aku/FeatureModules.cc:254-261
@@ -103,8 +126,12 @@ public:
     if (frame >= 0 && frame < m_frames) return &m_feats[(size_t)frame * m_dim];
     m_tmp.resize(m_dim);
     int dim = 0;
-    check(m_e.ctx(), akugpu_features_range(m_e.ctx(), m_pcm.data(), (int64_t)m_pcm.size(), frame, frame + 1, NULL,
-                                           m_tmp.data(), 1, &dim));
+    if (!m_rows.empty())
+      check(m_e.ctx(), akugpu_features_pre_range(m_e.ctx(), m_rows.data(), (int64_t)(m_rows.size() / m_pre_dim), frame, frame + 1,
+                                                 NULL, m_tmp.data(), 1, &dim));
+    else
+      check(m_e.ctx(), akugpu_features_range(m_e.ctx(), m_pcm.data(), (int64_t)m_pcm.size(), frame, frame + 1, NULL,
+                                             m_tmp.data(), 1, &dim));
     return m_tmp.data();
   }
   const std::vector<double> &features() const { return m_feats; }   // all frames, [frames x dim]
@@ -126,6 +153,8 @@ private:
   }
   Engine &m_e;
   std::vector<int16_t> m_pcm;
+  std::vector<float> m_rows;       // stored features of a `pre` base module
+  int m_pre_dim = 0;
   std::vector<double> m_feats, m_tmp;
   int m_frames, m_dim;
   bool m_eof;

@@ -61,10 +61,11 @@ void frontend_set_parameters(akugpu_ctx *ctx, const std::string &module, const s
 int64_t frontend_num_frames(const Frontend &fe, int64_t n_samples);
 // Computes module `target` (or the last module when target<0) for ONE utterance whose PCM is on the
 // device, for frames [start,end) in reference frame numbering; writes [end-start][dim] float or double.
-void frontend_run_range(akugpu_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, int start, int end, int target,
+// d_pcm: int16 samples (audiofile base module) or float32 rows [n x dim] (`pre` base module: n_samples / utt_off count rows)
+void frontend_run_range(akugpu_ctx *ctx, const void *d_pcm, int64_t n_samples, int start, int end, int target,
                         void *d_out, int out_f64);
 // Batch: all utterances, frames 0..n_u-1 each, into d_out [sum n_u][dim].
-void frontend_run_batch(akugpu_ctx *ctx, const int16_t *d_pcm, const std::vector<int64_t> &utt_off,
+void frontend_run_batch(akugpu_ctx *ctx, const void *d_pcm, const std::vector<int64_t> &utt_off,
                         const std::vector<int64_t> &frame_off, void *d_out, int out_f64);
 
 // stage timing (api.cu)

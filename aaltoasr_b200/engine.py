@@ -174,6 +174,28 @@ class AkuGpu:
                                                  C.byref(dim)))
         return out
 
+    def features_pre(self, rows, row_offsets=None, dtype=np.float64, out=None):
+        """A configuration with a `pre` base module: rows = stored float32 features [n x dim] of all utterances."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32) if not _is_torch(rows) else rows
+        n = int(rows.shape[0])
+        ro = np.ascontiguousarray(row_offsets if row_offsets is not None else [0, n], dtype=np.int64)
+        fo = np.zeros(len(ro), dtype=np.int64)
+        self._ck(self._lib.akugpu_features_pre(self._h, None, _ptr(ro), len(ro) - 1, None, 0, _ptr(fo)))
+        if out is None:
+            out = np.empty((int(fo[-1]), self.feature_dim), dtype=dtype)
+        self._ck(self._lib.akugpu_features_pre(self._h, _ptr(rows), _ptr(ro), len(ro) - 1, _ptr(out), _is_f64(out), _ptr(fo)))
+        return out, fo
+
+    def features_pre_range(self, rows, start, end, module=None, dtype=np.float64):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        dim = C.c_int(0)
+        mod = module.encode() if module else None
+        self._ck(self._lib.akugpu_features_pre_range(self._h, None, rows.shape[0], 0, 0, mod, None, 0, C.byref(dim)))
+        out = np.empty((max(0, end - start), dim.value), dtype=dtype)
+        self._ck(self._lib.akugpu_features_pre_range(self._h, _ptr(rows), rows.shape[0], int(start), int(end), mod, _ptr(out),
+                                                     _is_f64(out), C.byref(dim)))
+        return out
+
     # ---- model ----
     def model_read(self, base):
         self._ck(self._lib.akugpu_model_read(self._h, str(base).encode()))

@@ -62,13 +62,14 @@ int         akugpu_stage_times_reset(akugpu_ctx *ctx, int enable);
  * Replaces FeatureGenerator::load_configuration (aku/FeatureGenerator.cc:97-219)
  * and the module classes of aku/FeatureModules.cc.  The text is the reference's
  * own `module { name .. type .. sources .. }` format.  Supported module types:
- * audiofile, fft, mel, power, mel_power, dct, delta, merge, concat, normalization,
- * lin_transform, mean_subtractor.  Others return AKUGPU_E_CONFIG. */
+ * audiofile, pre, fft, mel, power, mel_power, dct, delta, merge, concat, normalization,
+ * lin_transform, mean_subtractor.  Others (vtln, sr_norm, quanteq) return AKUGPU_E_CONFIG. */
 int   akugpu_frontend_load_config(akugpu_ctx *ctx, const char *cfg_path);
 int   akugpu_frontend_load_config_text(akugpu_ctx *ctx, const char *cfg_text);
 int   akugpu_frontend_dim(akugpu_ctx *ctx);            /* FeatureGenerator::dim()         */
 int   akugpu_frontend_sample_rate(akugpu_ctx *ctx);    /* FeatureGenerator::sample_rate() */
 float akugpu_frontend_frame_rate(akugpu_ctx *ctx);     /* FeatureGenerator::frame_rate()  */
+int   akugpu_frontend_base_is_pre(akugpu_ctx *ctx);    /* 1: the base module is `pre` (stored features), 0: audiofile */
 /* Number of frames the reference generates before eof() for an audio file of
  * n_samples samples (aku/FeatureModules.cc:371-424: frame f is valid iff
  * (int)(f*window_advance) + window_width + 1 <= n_samples). */
@@ -95,6 +96,17 @@ int akugpu_features(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offs
 int akugpu_features_range(akugpu_ctx *ctx, const int16_t *pcm, int64_t n_samples,
                           int start_frame, int end_frame, const char *module_name,
                           void *out, int out_f64, int *dim_out);
+
+/* The same two calls for a configuration whose base module is `pre` (PreModule, aku/FeatureModules.cc:603-755: stored
+ * float32 feature rows instead of audio, the format feacat -H --raw-output writes: int32 dim, then rows; the header
+ * is the caller's business).  rows = all utterances' rows back to back, [n x dim] float32 with dim = the `pre`
+ * module's configured dimension; row_offsets / n_rows count rows.  Frames before / after the stored rows repeat the
+ * first / last one (:713-728).  With a `pre` base the int16 entry points (and akugpu_phone_probs) return AKUGPU_E_STATE,
+ * and vice versa. */
+int akugpu_features_pre(akugpu_ctx *ctx, const float *rows, const int64_t *row_offsets, int n_utts,
+                        void *out, int out_f64, int64_t *frame_offsets);
+int akugpu_features_pre_range(akugpu_ctx *ctx, const float *rows, int64_t n_rows, int start_frame, int end_frame,
+                              const char *module_name, void *out, int out_f64, int *dim_out);
 
 /* ---- acoustic model --------------------------------------------------------------
  * Replaces HmmSet::read_all / read_mc / read_ph / read_gk (aku/HmmSet.cc:157-357,

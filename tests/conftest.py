@@ -54,6 +54,11 @@ def ref_spk():
 
 
 @pytest.fixture(scope="session")
+def ref_pre():
+    return load_golden("ref_pre")
+
+
+@pytest.fixture(scope="session")
 def aku_tests():
     z = np.load(os.path.join(GOLDEN, "aku_tests.npz"))
     return {k: (str(z[k]) if k.endswith("_cfg") else z[k]) for k in z.files}

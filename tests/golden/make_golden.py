@@ -19,6 +19,8 @@ Run in the dev container (needs /root/reference and oracle/_ref built by oracle/
   ref_spk.npz     speaker adaptation through feature-module parameters (phone_probs -S x.spkc): a 39x39 lin_transform
                   ("cmllr") after the MFCC chain, two speakers with their own matrix + bias and a default speaker, a
                   three-line recipe (speaker A, speaker B, unknown speaker -> default); LNA files of the literal phone_probs.
+  ref_pre.npz     the `pre` base module (stored float32 features, int32 dim header: feacat -H --raw-output) followed by a
+                  delta module: the reference's output for frames -4 .. n+4 (first / last row replicated outside the file).
   ref_edge.npz    the same for a handmade edge-case model (underflow / denormal / floor regimes,
                   zero-variance dimensions, tiny weights).
 """
@@ -243,6 +245,39 @@ def spk_case(pcm, model, tmp):
     print(name, "differs from identity:", [float((out["lna2_%d" % i] != out["lna2_plain_%d" % i]).mean()) for i in range(3)])
 
 
+PRE_CFG = """module
+{
+  name pre
+  type pre
+  dim 39
+}
+
+module
+{
+  name d
+  type delta
+  sources pre
+  width 2
+}
+"""
+
+
+def pre_case(feats, tmp):
+    rows = feats[:60].astype(np.float32)
+    raw = os.path.join(tmp, "ref_pre.raw")
+    with open(raw, "wb") as f:
+        f.write(np.int32(rows.shape[1]).tobytes())
+        f.write(rows.tobytes())
+    cfg = os.path.join(tmp, "ref_pre.cfg")
+    open(cfg, "w").write(PRE_CFG)
+    out, last, _ = ref.features(cfg, raw)                      # until the reference reports eof
+    ext, _, _ = ref.features(cfg, raw, -4, rows.shape[0] + 4)
+    base = ref.module_output(cfg, raw, "pre", -4, rows.shape[0] + 4)
+    np.savez_compressed(os.path.join(HERE, "ref_pre.npz"), cfg=PRE_CFG, rows=rows, out=out, ext=ext, ext_start=-4, base_ext=base,
+                        last_frame=last)
+    print("ref_pre rows", rows.shape, "frames until eof", out.shape[0], "last_frame", last)
+
+
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
@@ -256,6 +291,7 @@ def main():
         run_case("ref_small", pcm, small_model(feats, 7002), tmp)
         clust_case(pcm, small_model(feats, 7002), tmp)
         spk_case(pcm, small_model(feats, 7002), tmp)
+        pre_case(feats, tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
         run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 

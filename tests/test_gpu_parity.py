@@ -131,6 +131,36 @@ def test_features_sweep_vs_oracle(engine, sr, ww):
     assert np.abs(got - want).max() <= 5e-5, np.abs(got - want).max()
 
 
+def test_pre_base_module(engine, ref_pre, aku_tests):
+    """`pre` base module (stored float32 features, aku/FeatureModules.cc:603-755) followed by a delta module: equal
+    to the reference's doubles, also outside the file (first / last row replicated); and the third aku/tests golden:
+    feacat --raw-output of frames 10..60, read back through pre.feaconf (aku/tests/pre_test.script)."""
+    g = ref_pre
+    engine.frontend_load_config_text(g["cfg"])
+    assert engine.feature_dim == 39 and engine.num_frames(60) == 60
+    out, fo = engine.features_pre(g["rows"])
+    assert list(fo) == [0, 60] and np.array_equal(out, g["out"])
+    n = g["rows"].shape[0]
+    ext = engine.features_pre_range(g["rows"], int(g["ext_start"]), n + 4)
+    assert np.array_equal(ext, g["ext"])
+    base = engine.features_pre_range(g["rows"], -4, n + 4, module="pre")
+    assert np.array_equal(base, g["base_ext"])
+    two, fo = engine.features_pre(np.concatenate([g["rows"], g["rows"][:17]]), [0, n, n + 17])      # batch of two "files"
+    assert list(fo) == [0, n, n + 17] and np.array_equal(two[:n], g["out"])
+    with pytest.raises(AkuGpuError, match="base module is `pre`"):
+        engine.features(np.zeros(4000, np.int16))
+    # aku/tests/pre_test: mfcc_p_dd features of frames 10..60 as raw float32 rows, then the bare `pre` configuration
+    engine.frontend_load_config_text(aku_tests["mfcc_p_dd_cfg"])
+    rows = engine.features_range(aku_tests["short_wav"], 10, 61, dtype=np.float32)
+    engine.frontend_load_config_text(aku_tests["pre_cfg"])
+    back, _ = engine.features_pre(rows)
+    assert np.array_equal(back, rows.astype(np.float64))
+    assert back.shape == aku_tests["pre_test_ref"].shape and np.abs(back - aku_tests["pre_test_ref"]).max() <= 0.0051
+    with pytest.raises(AkuGpuError, match="base module is `audiofile`"):
+        engine.frontend_load_config_text(aku_tests["mfcc_p_dd_cfg"])
+        engine.features_pre(rows)
+
+
 # ------------------------------------------------------------------ GMM + LNA
 @pytest.mark.parametrize("case", ["ref_small", "ref_edge"])
 def test_gmm_lna_parity_mode_bit_exact(engine, case, request):
