@@ -149,7 +149,7 @@ struct PackedTC16 {
 // ---------------------------------------------------------------------------------
 // Front-end module graph (parsed from the reference's feature configuration).
 enum ModType { M_AUDIOFILE, M_FFT, M_MEL, M_POWER, M_MEL_POWER, M_DCT, M_DELTA, M_MERGE, M_CONCAT,
-               M_NORMALIZATION, M_LIN_TRANSFORM, M_MEAN_SUBTRACTOR, M_PRE };
+               M_NORMALIZATION, M_LIN_TRANSFORM, M_MEAN_SUBTRACTOR, M_PRE, M_VTLN };
 
 struct Module {
   std::string name;
@@ -175,6 +175,10 @@ struct Module {
   bool matrix_defined = false, bias_defined = false;
   // mean_subtractor: left/right hold the +1-extended offsets, width = left+right-1
   int ms_width = 0;
+  // vtln (VtlnModule, aku/FeatureModules.cc:1505-1934): warp of the spectrum bins, sinc / linear interpolation
+  int use_pwlin = 0, use_slapt = 0, sinc_rad = 8, lanczos = 1;
+  float pwlin_turn_point = 0.8f, warp_factor = 1.0f;
+  std::vector<float> slapt_params, vtln_bins;
   // device copies of parameters
   std::shared_ptr<DevBuf> d_a, d_b, d_c;
   // extended frame range this module must be evaluated on for an utterance:

@@ -242,6 +242,74 @@ void upload_module_params(akugpu_ctx *ctx, Module &m, const std::vector<Module> 
       m.d_a = upload_vec(tab, st);
       break;
     }
+    case M_VTLN: {
+      // Warped bin positions (float), then the interpolation table, in the reference's mixed float/double arithmetic:
+      // create_blin_bins :1662-1675, create_pwlin_bins :1634-1660, create_slapt_bins :1677-1695, create_sinc_coef_table
+      // :1697-1723 (util::sinc aku/util.hh:151-159).  d_a: float coefficients in tap order; d_b: int {first source bin,
+      // taps, offset} per bin; d_c: float warped positions (linear interpolation when sinc_interpolation_rad == 0).
+      const int dim = m.dim;
+      std::vector<float> &bins = m.vtln_bins;
+      bins.assign(dim, 0.f);
+      int t;
+      if (m.use_slapt) {
+        for (t = 0; t < dim - 1; t++) {
+          double nf = M_PI * (double)t / (dim - 1);
+          bins[t] = t;
+          for (int i = 0; i < (int)m.slapt_params.size(); i++) bins[t] += m.slapt_params[i] * sin((i + 1) * nf) * (dim - 1);
+        }
+        bins[t] = dim - 1;
+      } else if (m.use_pwlin) {
+        float border, slope = 0, point = 0;
+        bool limit = false;
+        border = m.pwlin_turn_point * (float)(dim - 1);
+        for (t = 0; t < dim - 1; t++) {
+          if (!limit) bins[t] = m.warp_factor * (float)t;
+          else bins[t] = slope * (float)t + point;
+          if (!limit && (t >= border || bins[t] >= border)) {
+            slope = ((float)dim - 1 - bins[t]) / ((float)dim - 1 - t);
+            point = (1 - slope) * (float)(dim - 1);
+            limit = true;
+          }
+        }
+        bins[t] = (float)(dim - 1);
+      } else {
+        for (t = 0; t < dim - 1; t++) {
+          double nf = M_PI * (double)t / (dim - 1);
+          bins[t] = t + 2 * atan2((m.warp_factor - 1) * sin(nf), 1 + (1 - m.warp_factor) * cos(nf)) / M_PI * (dim - 1);
+        }
+        bins[t] = dim - 1;
+      }
+      std::vector<float> coef;
+      std::vector<int> desc;
+      if (m.sinc_rad > 0) {
+        auto sinc = [](float x) -> float {
+          const double PI = 3.14159265358979323846;
+          if (fabs(x) < 1e-8) return 1;
+          double y = PI * x;
+          return sin(y) / y;
+        };
+        for (int bi = 0; bi < dim; bi++) {
+          int cent = (int)(bins[bi] + 0.5);
+          int min_i = std::max(cent - m.sinc_rad, 0);
+          int max_i = std::min(cent + m.sinc_rad + 1, dim);
+          desc.push_back(min_i); desc.push_back(std::max(0, max_i - min_i)); desc.push_back((int)coef.size());
+          for (int i = min_i; i < max_i; i++) {
+            float tt = sinc(i - bins[bi]);
+            if (m.lanczos) {
+              if (fabs(i - bins[bi]) < m.sinc_rad) tt *= sinc((i - bins[bi]) / (float)m.sinc_rad);
+              else tt = 0;
+            }
+            coef.push_back(tt);
+          }
+        }
+      }
+      if (coef.empty()) coef.push_back(0.f);
+      if (desc.empty()) desc.assign(3, 0);
+      m.d_a = upload_vec(coef, st);
+      m.d_b = upload_vec(desc, st);
+      m.d_c = upload_vec(bins, st);
+      break;
+    }
     case M_NORMALIZATION:
       m.d_a = upload_vec(m.v_mean, st);
       m.d_b = upload_vec(m.v_scale, st);
@@ -275,11 +343,11 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
         {"audiofile", M_AUDIOFILE}, {"fft", M_FFT}, {"mel", M_MEL}, {"power", M_POWER}, {"mel_power", M_MEL_POWER},
         {"dct", M_DCT}, {"delta", M_DELTA}, {"merge", M_MERGE}, {"concat", M_CONCAT},
         {"normalization", M_NORMALIZATION}, {"lin_transform", M_LIN_TRANSFORM}, {"mean_subtractor", M_MEAN_SUBTRACTOR},
-        {"pre", M_PRE}};
+        {"pre", M_PRE}, {"vtln", M_VTLN}};
     bool known = false;
     for (auto &t : types) if (*type == t.s) { m.type = t.t; known = true; }
     if (!known) {
-      if (*type == "vtln" || *type == "sr_norm" || *type == "quanteq")
+      if (*type == "sr_norm" || *type == "quanteq")
         throw Error(AKUGPU_E_CONFIG, "module type '" + *type + "' is not supported by the GPU front-end");
       throw Error(AKUGPU_E_CONFIG, "Unknown module type '" + *type + "'");
     }
@@ -379,6 +447,21 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
         if (m.dim < 1) throw Error(AKUGPU_E_CONFIG, "LinTransformModule: Dimension must be > 0");
         check_lin_transform(m, sdim);
         break;
+      case M_VTLN: {      // VtlnModule::set_module_config, aku/FeatureModules.cc:1530-1573
+        m.dim = sdim;
+        m.use_pwlin = 0; m.pwlin_turn_point = 0.8f;
+        get_int(b, "pwlin_vtln", m.use_pwlin); get_float(b, "pwlin_turnpoint", m.pwlin_turn_point);
+        m.use_slapt = 0; get_int(b, "slapt", m.use_slapt);
+        if (m.use_pwlin && m.use_slapt) throw Error(AKUGPU_E_CONFIG, "VtlnModule: Can not use both pwlin_vtln and slapt!");
+        m.sinc_rad = 8; get_int(b, "sinc_interpolation_rad", m.sinc_rad);
+        int all_pass = 0; get_int(b, "all-pass", all_pass);
+        if (all_pass) throw Error(AKUGPU_E_CONFIG, "VtlnModule: all-pass transforms are not supported by the GPU front-end");
+        m.lanczos = 1; get_int(b, "lanczos_window", m.lanczos);
+        m.lanczos = m.lanczos > 0 ? 1 : 0;
+        m.warp_factor = 1.0f;
+        m.slapt_params.assign(1, 0.0f);
+        break;
+      }
       case M_MEAN_SUBTRACTOR: {
         m.dim = sdim;
         int l = 75, r = 75;
@@ -410,6 +493,14 @@ void frontend_set_parameters(akugpu_ctx *ctx, const std::string &module, const s
   const Block &b = blocks[0];
   if (m.type == M_NORMALIZATION) {
     read_normalization(m, b);
+  } else if (m.type == M_VTLN) {        // VtlnModule::set_parameters, aku/FeatureModules.cc:1575-1592
+    if (m.use_slapt) {
+      m.slapt_params.assign(1, 0.0f);
+      get_fvec(b, "slapt_coef", m.slapt_params);
+    } else {
+      m.warp_factor = 1.0f;
+      get_float(b, "warp_factor", m.warp_factor);
+    }
   } else if (m.type == M_LIN_TRANSFORM) {
     m.matrix.clear(); m.bias.clear();
     get_fvec(b, "matrix", m.matrix); get_fvec(b, "bias", m.bias);
@@ -782,6 +873,30 @@ __global__ void fe_copy(const double *__restrict__ src, int sdim, int64_t n_rows
   out[r * odim + col0 + c] = src[q * sdim + c];
 }
 
+// VtlnModule::generate (aku/FeatureModules.cc:1906-1934): every output bin is a short dot product of the source spectrum
+// with the Lanczos-windowed sinc taps around its warped position (double accumulator, float coefficients, result clamped
+// at 0 as a float), or a linear interpolation between the two neighbouring bins when sinc_interpolation_rad is 0.
+__global__ void fe_vtln(const double *__restrict__ src, int dim, int64_t n_rows, const float *__restrict__ coef,
+                        const int *__restrict__ desc, const float *__restrict__ bins, int rad, double *__restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  const int64_t r = i / dim;
+  const int b = (int)(i - r * dim);
+  const double *data = src + r * dim;
+  if (rad > 0) {
+    const int di = desc[3 * b], n = desc[3 * b + 1];
+    const float *cf = coef + desc[3 * b + 2];
+    double t = 0;
+    for (int k = 0; k < n; k++) t = __dadd_rn(t, __dmul_rn(data[di + k], (double)cf[k]));
+    out[i] = (double)fmaxf((float)t, 0.0f);
+  } else {
+    const float vb = bins[b];
+    const float p = __fsub_rn(ceilf(vb), vb);
+    out[i] = __dadd_rn(__dmul_rn((double)p, data[(int)floorf(vb)]), __dmul_rn((double)__fsub_rn(1.f, p), data[(int)ceilf(vb)]));
+  }
+}
+
 // NormalizationModule::generate (:1136-1142)
 __global__ void fe_norm(const double *__restrict__ src, int dim, int64_t n_rows, const float *__restrict__ mean,
                         const float *__restrict__ scale, double *__restrict__ out)
@@ -1075,6 +1190,10 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
         break;
       case M_MEAN_SUBTRACTOR:
         fe_meansub<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, dr, du, H, mod.left, mod.right, o);
+        break;
+      case M_VTLN:
+        fe_vtln<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, mod.d_a->as<float>(), mod.d_b->as<int>(), mod.d_c->as<float>(),
+                                                mod.sinc_rad, o);
         break;
       default:
         throw Error(AKUGPU_E_CONFIG, "module '" + mod.name + "' cannot be evaluated here");

@@ -62,8 +62,8 @@ int         akugpu_stage_times_reset(akugpu_ctx *ctx, int enable);
  * Replaces FeatureGenerator::load_configuration (aku/FeatureGenerator.cc:97-219)
  * and the module classes of aku/FeatureModules.cc.  The text is the reference's
  * own `module { name .. type .. sources .. }` format.  Supported module types:
- * audiofile, pre, fft, mel, power, mel_power, dct, delta, merge, concat, normalization,
- * lin_transform, mean_subtractor.  Others (vtln, sr_norm, quanteq) return AKUGPU_E_CONFIG. */
+ * audiofile, pre, fft, vtln (not all-pass), mel, power, mel_power, dct, delta, merge, concat, normalization,
+ * lin_transform, mean_subtractor.  Others (sr_norm, quanteq) return AKUGPU_E_CONFIG. */
 int   akugpu_frontend_load_config(akugpu_ctx *ctx, const char *cfg_path);
 int   akugpu_frontend_load_config_text(akugpu_ctx *ctx, const char *cfg_text);
 int   akugpu_frontend_dim(akugpu_ctx *ctx);            /* FeatureGenerator::dim()         */
@@ -75,7 +75,8 @@ int   akugpu_frontend_base_is_pre(akugpu_ctx *ctx);    /* 1: the base module is 
  * (int)(f*window_advance) + window_width + 1 <= n_samples). */
 int64_t akugpu_frontend_num_frames(akugpu_ctx *ctx, int64_t n_samples);
 /* FeatureModule::set_parameters for a named module (aku/FeatureModule.hh:107):
- * `text` holds `key value...` lines as in a config block (e.g. "matrix ...", "bias ..."). */
+ * `text` holds `key value...` lines as in a config block (lin_transform: "matrix ...", "bias ..."; normalization:
+ * "mean ...", "scale ..."; vtln: "warp_factor w" or "slapt_coef ..."). */
 int   akugpu_frontend_set_parameters(akugpu_ctx *ctx, const char *module_name, const char *text);
 
 /* Batch feature computation: replaces the per-frame FeatureGenerator::generate(f)

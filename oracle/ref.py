@@ -27,6 +27,9 @@ def lib():
         _lib.ref_features.restype = C.c_long
         _lib.ref_features.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_long,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        _lib.ref_features_spk.restype = C.c_long
+        _lib.ref_features_spk.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_long,
+                                          C.POINTER(C.c_int)]
         _lib.ref_module_output.restype = C.c_long
         _lib.ref_module_output.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_long,
                                            C.POINTER(C.c_int)]
@@ -64,6 +67,17 @@ def features(cfg_path, wav_path, start=0, end=-1, max_frames=1 << 20, dim_hint=4
     if n < 0:
         raise _err()
     return buf[:n * dim.value].reshape(n, dim.value).copy(), last.value, fr.value
+
+
+def features_spk(cfg_path, wav_path, spkc_path, speaker, start=0, end=-1, max_frames=1 << 16):
+    """FeatureGenerator::generate with a speaker configuration applied (SpeakerConfig::set_speaker). float64 [F x dim]."""
+    dim = C.c_int(0)
+    buf = np.empty(max_frames * 128, dtype=np.float64)
+    n = lib().ref_features_spk(cfg_path.encode(), wav_path.encode(), spkc_path.encode(), speaker.encode(), start, end,
+                               buf.ctypes.data, max_frames, C.byref(dim))
+    if n < 0:
+        raise _err()
+    return buf[:n * dim.value].reshape(n, dim.value).copy()
 
 
 def module_output(cfg_path, wav_path, module, start, end):

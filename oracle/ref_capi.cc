@@ -19,6 +19,7 @@
 #include "FeatureGenerator.hh"
 #include "FeatureModules.hh"
 #include "HmmSet.hh"
+#include "SpeakerConfig.hh"
 #include "LnaReaderCircular.hh"   // decoder/src: the consumer of the LNA stream
 
 using namespace aku;
@@ -52,6 +53,35 @@ long ref_features(const char *cfg_path, const char *audio_path, int start, int e
       n++;
     }
     if (last_frame_out) *last_frame_out = gen.last_frame();
+    gen.close();
+    return n;
+  } catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
+// The same with a speaker configuration file applied first (aku::SpeakerConfig::read_speaker_file + set_speaker,
+// aku/SpeakerConfig.cc:20-147,239-286; what phone_probs -S does per utterance): run-time module parameters such as a
+// VTLN warp factor or a CMLLR lin_transform.
+long ref_features_spk(const char *cfg_path, const char *audio_path, const char *spkc_path, const char *speaker,
+                      int start, int end, double *out, long max_frames, int *dim_out)
+{
+  try {
+    FeatureGenerator gen;
+    gen.load_configuration(io::Stream(cfg_path));
+    SpeakerConfig sc(gen);
+    sc.read_speaker_file(io::Stream(spkc_path));
+    gen.open(audio_path);
+    sc.set_speaker(speaker);
+    int dim = gen.dim();
+    if (dim_out) *dim_out = dim;
+    long n = 0;
+    for (int f = start; end < 0 || f < end; f++) {
+      const FeatureVec fea = gen.generate(f);
+      if (end < 0 && gen.eof()) break;
+      if (n >= max_frames) break;
+      for (int i = 0; i < dim; i++) out[n * dim + i] = fea[i];
+      n++;
+    }
     gen.close();
     return n;
   } catch (std::string &s) { return fail(s); }

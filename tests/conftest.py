@@ -59,6 +59,12 @@ def ref_pre():
 
 
 @pytest.fixture(scope="session")
+def ref_vtln():
+    z = np.load(os.path.join(GOLDEN, "ref_vtln.npz"))
+    return {k: (str(z[k]) if k.startswith(("cfg_", "spkc_")) else z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="session")
 def aku_tests():
     z = np.load(os.path.join(GOLDEN, "aku_tests.npz"))
     return {k: (str(z[k]) if k.endswith("_cfg") else z[k]) for k in z.files}

@@ -21,6 +21,9 @@ Run in the dev container (needs /root/reference and oracle/_ref built by oracle/
                   three-line recipe (speaker A, speaker B, unknown speaker -> default); LNA files of the literal phone_probs.
   ref_pre.npz     the `pre` base module (stored float32 features, int32 dim header: feacat -H --raw-output) followed by a
                   delta module: the reference's output for frames -4 .. n+4 (first / last row replicated outside the file).
+  ref_vtln.npz    the vtln module (VtlnModule: bilinear / piecewise-linear / SLAPT warps, Lanczos-sinc or linear
+                  interpolation) between fft and mel, warp factors set per speaker through a speaker file: the
+                  reference's 39-dim features for four configurations x three speakers.
   ref_edge.npz    the same for a handmade edge-case model (underflow / denormal / floor regimes,
                   zero-variance dimensions, tiny weights).
 """
@@ -278,6 +281,41 @@ def pre_case(feats, tmp):
     print("ref_pre rows", rows.shape, "frames until eof", out.shape[0], "last_frame", last)
 
 
+def vtln_cfg(extra):
+    base = synth.mfcc39_config()
+    vt = "module\n{\n  name vtln\n  type vtln\n  sources fft\n%s}\n\n" % "".join("  %s\n" % e for e in extra)
+    return base.replace("module\n{\n  name mel\n  type mel\n  sources fft\n}", vt + "module\n{\n  name mel\n  type mel\n  sources vtln\n}")
+
+
+def vtln_case(pcm, tmp):
+    wav = os.path.join(tmp, "vtln.wav")
+    formats.write_wav(wav, pcm[:12000], 16000)
+    variants = {"blin": [], "pwlin": ["pwlin_vtln 1", "pwlin_turnpoint 0.75"], "linear": ["sinc_interpolation_rad 0"],
+                "slapt": ["slapt 1", "sinc_interpolation_rad 4", "lanczos_window 0"]}
+    out = dict(pcm=pcm[:12000])
+    for name, extra in variants.items():
+        cfg_text = vtln_cfg(extra)
+        assert "sources vtln" in cfg_text
+        cfg = os.path.join(tmp, "vtln_%s.cfg" % name)
+        open(cfg, "w").write(cfg_text)
+        if name == "slapt":
+            params = {"s1": "slapt_coef 0.02 -0.01", "s2": "slapt_coef -0.03"}
+        else:
+            params = {"s1": "warp_factor 0.9", "s2": "warp_factor 1.12"}
+        spkc = "speaker default\n{\n  vtln\n  {\n  }\n}\n\n" + "".join(
+            "speaker %s\n{\n  feature vtln\n  {\n    %s\n  }\n}\n\n" % (k, v) for k, v in params.items())
+        sp = os.path.join(tmp, "vtln_%s.spkc" % name)
+        open(sp, "w").write(spkc)
+        out["cfg_" + name] = cfg_text
+        out["spkc_" + name] = spkc
+        for spk in ("s1", "s2", "other"):
+            out["feats_%s_%s" % (name, spk)] = ref.features_spk(cfg, wav, sp, spk)
+        plain, _, _ = ref.features(cfg, wav)
+        assert np.array_equal(plain, out["feats_%s_other" % name])          # default speaker = warp 1
+        print("ref_vtln", name, out["feats_%s_s1" % name].shape, "max |s1 - unwarped| %.3f" % np.abs(out["feats_%s_s1" % name] - plain).max())
+    np.savez_compressed(os.path.join(HERE, "ref_vtln.npz"), **out)
+
+
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
@@ -292,6 +330,7 @@ def main():
         clust_case(pcm, small_model(feats, 7002), tmp)
         spk_case(pcm, small_model(feats, 7002), tmp)
         pre_case(feats, tmp)
+        vtln_case(pcm, tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
         run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 

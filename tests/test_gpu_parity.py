@@ -131,6 +131,31 @@ def test_features_sweep_vs_oracle(engine, sr, ww):
     assert np.abs(got - want).max() <= 5e-5, np.abs(got - want).max()
 
 
+@pytest.mark.parametrize("variant", ["blin", "pwlin", "linear", "slapt"])
+def test_vtln_module(engine, ref_vtln, variant, tmp_path):
+    """vtln module between fft and mel (VtlnModule, aku/FeatureModules.cc:1505-1934): bilinear, piecewise-linear and
+    SLAPT warps, Lanczos-sinc and linear interpolation, the warp set per speaker through a speaker file
+    (SpeakerConfig -> FeatureModule::set_parameters).  Features within the front-end's usual 1e-5 of the reference's."""
+    from aaltoasr_b200 import SpeakerConfig
+    g = ref_vtln
+    engine.frontend_load_config_text(g["cfg_" + variant])
+    spkc = str(tmp_path / "v.spkc")
+    open(spkc, "w").write(g["spkc_" + variant])
+    sc = SpeakerConfig(engine)
+    sc.read_speaker_file(spkc)
+    got = {}
+    for spk in ("s1", "other", "s2"):
+        sc.set_speaker(spk)
+        feats, _ = engine.features(g["pcm"], dtype=np.float64)
+        want = g["feats_%s_%s" % (variant, spk)]
+        assert feats.shape == want.shape
+        assert np.abs(feats - want).max() <= 2e-5, (variant, spk, np.abs(feats - want).max())
+        got[spk] = feats
+    assert np.abs(got["s1"] - got["other"]).max() > 0.1          # the warp does something
+    with pytest.raises(AkuGpuError, match="all-pass"):
+        engine.frontend_load_config_text(g["cfg_blin"].replace("type vtln", "type vtln\n  all-pass 1"))
+
+
 def test_pre_base_module(engine, ref_pre, aku_tests):
     """`pre` base module (stored float32 features, aku/FeatureModules.cc:603-755) followed by a delta module: equal
     to the reference's doubles, also outside the file (first / last row replicated); and the third aku/tests golden:
