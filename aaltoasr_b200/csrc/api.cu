@@ -6,6 +6,7 @@
 #include <string.h>
 #include <fstream>
 #include <sstream>
+#include <mutex>
 
 using namespace akugpu;
 
@@ -26,6 +27,18 @@ static std::string g_create_err;
   }
 
 namespace akugpu {
+
+void ensure_dynamic_smem(akugpu_ctx *ctx, const void *kernel, size_t bytes)
+{
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> have;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &h = have[std::make_pair(ctx->device, kernel)];
+  if (bytes > h) {
+    AKU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    h = bytes;
+  }
+}
 
 StageScope::StageScope(akugpu_ctx *c, int s) : ctx(c), stage(s), l0(c->launches)
 {

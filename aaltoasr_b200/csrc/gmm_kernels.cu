@@ -445,11 +445,7 @@ static void launch_f32_t(akugpu_ctx *ctx, const void *feats, int feats_f64, int6
   const PackedF32 &p = ctx->p32;
   const HostModel &hm = ctx->hm;
   size_t smem = gmm_f32_smem_bytes(p);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    AKU_CUDA(cudaFuncSetAttribute(gmm_diag_f32<F2, DPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  ensure_dynamic_smem(ctx, (const void *)gmm_diag_f32<F2, DPC>, smem);
   int64_t nf = f_end - f_begin;
   int ftiles = (int)((nf + TF - 1) / TF);
   // One wave = sm_count * 2 resident CTAs.  Full chunks are sized to whole waves by the caller
@@ -487,11 +483,7 @@ void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f
   const HostModel &hm = ctx->hm;
   const PackedF64 &p = ctx->p64;
   size_t smem = (size_t)hm.D * 128 * sizeof(double);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    AKU_CUDA(cudaFuncSetAttribute(gmm_diag_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  ensure_dynamic_smem(ctx, (const void *)gmm_diag_f64, smem);
   int64_t nf = f_end - f_begin;
   int ftiles = (int)((nf + 127) / 128);
   const int *g2c = nullptr;
@@ -512,11 +504,7 @@ void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f
                                                               p.c_mix_gauss.as<int>(), p.c_mix_w.as<double>(), C,
                                                               ctx->d_clik.as<double>(), ldF, -1.0, nullptr, nullptr, nullptr);
     AKU_CUDA(cudaGetLastError());
-    static size_t attr_sel = 0;
-    if (sel_smem > attr_sel) {
-      AKU_CUDA(cudaFuncSetAttribute(cluster_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-      attr_sel = sel_smem;
-    }
+    ensure_dynamic_smem(ctx, (const void *)cluster_select, sel_smem);
     cluster_select<<<(unsigned)nf, 256, sel_smem, ctx->stream>>>(ctx->d_clik.as<double>(), ldF, C, Cp, nf, p.c_size.as<int>(),
                                                                  hm.eval_min_clusters, hm.eval_min_gaussians,
                                                                  ctx->d_csel.as<unsigned char>());

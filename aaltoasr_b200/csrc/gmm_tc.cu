@@ -554,14 +554,12 @@ bool launch_gmm_tc(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_
   StageScope sc(ctx, 1);
   if (ares) {
     const size_t smem = (size_t)kblocks * tc::BM * tc::BK * 2 + (size_t)tc::STAGES * tc::BN * tc::BK * 2 + 1024;
-    static size_t attr = 0;
-    if (smem > attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    ensure_dynamic_smem(ctx, (const void *)gmm_tc_kernel<true>, smem);
     gmm_tc_kernel<true><<<grid, 384, smem, ctx->stream>>>(mapA, mapB, kblocks, p.Lm / tc::BK, ranges, p.bias.as<float>(),
                                                           p.meta.as<int>(), sll, ldF, norm);
   } else {
     const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + 1024;
-    static bool attr = false;
-    if (!attr) { AKU_CUDA(cudaFuncSetAttribute(gmm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    ensure_dynamic_smem(ctx, (const void *)gmm_tc_kernel<false>, smem);
     gmm_tc_kernel<false><<<grid, 384, smem, ctx->stream>>>(mapA, mapB, kblocks, p.Lm / tc::BK, ranges, p.bias.as<float>(),
                                                            p.meta.as<int>(), sll, ldF, norm);
   }

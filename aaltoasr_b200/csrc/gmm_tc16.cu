@@ -582,9 +582,7 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
                                : 1024 + (size_t)(1 + tslots) * p.KB * tc16::BLOCK_BYTES + tc16_stage_x_bytes(p.D);
   StageScope sc(ctx, 1);
   auto launch = [&](auto kernel) {
-    static std::map<const void *, size_t> attr;     // per instantiation (they all share one function-pointer type)
-    size_t &have = attr[(const void *)kernel];
-    if (smem > have) { AKU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); have = smem; }
+    ensure_dynamic_smem(ctx, (const void *)kernel, smem);
     kernel<<<dim3(ftiles, ysplit), tc16::THREADS, smem, ctx->stream>>>(mapA, mapB, p.KB, tslots, ranges, p.meta.as<int>(), feats, feats_f64,
                                                                      f_begin, nf, p.D, p.center.as<double>(), p.escale.as<float>(), sll, ldF,
                                                                      norm, p.flag.as<int>());

@@ -68,6 +68,11 @@ void frontend_run_range(akugpu_ctx *ctx, const void *d_pcm, int64_t n_samples, i
 void frontend_run_batch(akugpu_ctx *ctx, const void *d_pcm, const std::vector<int64_t> &utt_off,
                         const std::vector<int64_t> &frame_off, void *d_out, int out_f64);
 
+// Opt-in to `bytes` of dynamic shared memory for `kernel` on the context's device.  The attribute is per device and the
+// cache is shared by every context of the process, so it is keyed by (device, kernel) and guarded by a mutex
+// (one context per host thread, several threads / devices per process).  (api.cu)
+void ensure_dynamic_smem(akugpu_ctx *ctx, const void *kernel, size_t bytes);
+
 // stage timing (api.cu)
 struct StageScope {
   akugpu_ctx *ctx;
