@@ -149,7 +149,7 @@ struct PackedTC16 {
 // ---------------------------------------------------------------------------------
 // Front-end module graph (parsed from the reference's feature configuration).
 enum ModType { M_AUDIOFILE, M_FFT, M_MEL, M_POWER, M_MEL_POWER, M_DCT, M_DELTA, M_MERGE, M_CONCAT,
-               M_NORMALIZATION, M_LIN_TRANSFORM, M_MEAN_SUBTRACTOR, M_PRE, M_VTLN };
+               M_NORMALIZATION, M_LIN_TRANSFORM, M_MEAN_SUBTRACTOR, M_PRE, M_VTLN, M_SR_NORM, M_QUANTEQ };
 
 struct Module {
   std::string name;
@@ -179,6 +179,11 @@ struct Module {
   int use_pwlin = 0, use_slapt = 0, sinc_rad = 8, lanczos = 1;
   float pwlin_turn_point = 0.8f, warp_factor = 1.0f;
   std::vector<float> slapt_params, vtln_bins;
+  // sr_norm (SRNormModule :1936-2069): Lanczos resampling across the stacked frames of a concat module
+  int in_frames = 0, out_frames = 0, frame_dim = 0, lanczos_order = 4;
+  float speech_rate = 1.0f;
+  // quanteq (QuantEqModule :2072-2148): per-channel power-law equalisation, parameters set at run time only
+  std::vector<float> q_alpha, q_gamma, q_max;
   // device copies of parameters
   std::shared_ptr<DevBuf> d_a, d_b, d_c;
   // extended frame range this module must be evaluated on for an utterance:

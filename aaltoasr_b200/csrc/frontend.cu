@@ -310,6 +310,51 @@ void upload_module_params(akugpu_ctx *ctx, Module &m, const std::vector<Module> 
       m.d_c = upload_vec(bins, st);
       break;
     }
+    case M_SR_NORM: {
+      // SRNormModule::set_speech_rate (aku/FeatureModules.cc:2004-2036): Lanczos taps over the input frames for every
+      // output frame, float arithmetic as the reference.  d_a: float taps; d_b: int {first input frame, taps, offset}.
+      const float in_cent = (float)(m.in_frames - 1) / 2, out_cent = (float)(m.out_frames - 1) / 2;
+      auto sinc = [](float x) -> float {
+        const double PI = 3.14159265358979323846;
+        if (fabs(x) < 1e-8) return 1;
+        double y = PI * x;
+        return sin(y) / y;
+      };
+      std::vector<float> coef;
+      std::vector<int> desc;
+      for (int i = 0; i < m.out_frames; i++) {
+        float target_pos = (i - out_cent) / m.speech_rate + in_cent;
+        int cent = (int)roundf(target_pos);
+        int interp_start = std::max(cent - m.lanczos_order, 0);
+        int interp_end = std::min(cent + m.lanczos_order + 1, m.in_frames);
+        desc.push_back(interp_start); desc.push_back(std::max(0, interp_end - interp_start)); desc.push_back((int)coef.size());
+        for (int j = interp_start; j < interp_end; j++) {
+          float t = sinc(j - target_pos);
+          if (fabs(j - target_pos) < m.lanczos_order) t *= sinc((j - target_pos) / (float)m.lanczos_order);
+          else t = 0;
+          coef.push_back(t);
+        }
+      }
+      if (coef.empty()) coef.push_back(0.f);
+      m.d_a = upload_vec(coef, st);
+      m.d_b = upload_vec(desc, st);
+      break;
+    }
+    case M_QUANTEQ: {
+      // active only when alpha, gamma and quant_max are all set (QuantEqModule::generate :2127-2133); d_a = the three
+      // vectors back to back
+      std::vector<float> all;
+      if (!m.q_alpha.empty() && !m.q_gamma.empty() && !m.q_max.empty()) {
+        if ((int)m.q_alpha.size() < m.dim || (int)m.q_gamma.size() < m.dim || (int)m.q_max.size() < m.dim)
+          throw Error(AKUGPU_E_CONFIG, "QuantEqModule: alpha / gamma / quant_max need one value per channel");
+        all.insert(all.end(), m.q_alpha.begin(), m.q_alpha.begin() + m.dim);
+        all.insert(all.end(), m.q_gamma.begin(), m.q_gamma.begin() + m.dim);
+        all.insert(all.end(), m.q_max.begin(), m.q_max.begin() + m.dim);
+      }
+      if (all.empty()) all.push_back(0.f);
+      m.d_a = upload_vec(all, st);
+      break;
+    }
     case M_NORMALIZATION:
       m.d_a = upload_vec(m.v_mean, st);
       m.d_b = upload_vec(m.v_scale, st);
@@ -343,14 +388,10 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
         {"audiofile", M_AUDIOFILE}, {"fft", M_FFT}, {"mel", M_MEL}, {"power", M_POWER}, {"mel_power", M_MEL_POWER},
         {"dct", M_DCT}, {"delta", M_DELTA}, {"merge", M_MERGE}, {"concat", M_CONCAT},
         {"normalization", M_NORMALIZATION}, {"lin_transform", M_LIN_TRANSFORM}, {"mean_subtractor", M_MEAN_SUBTRACTOR},
-        {"pre", M_PRE}, {"vtln", M_VTLN}};
+        {"pre", M_PRE}, {"vtln", M_VTLN}, {"sr_norm", M_SR_NORM}, {"quanteq", M_QUANTEQ}};
     bool known = false;
     for (auto &t : types) if (*type == t.s) { m.type = t.t; known = true; }
-    if (!known) {
-      if (*type == "sr_norm" || *type == "quanteq")
-        throw Error(AKUGPU_E_CONFIG, "module type '" + *type + "' is not supported by the GPU front-end");
-      throw Error(AKUGPU_E_CONFIG, "Unknown module type '" + *type + "'");
-    }
+    if (!known) throw Error(AKUGPU_E_CONFIG, "Unknown module type '" + *type + "'");
     if (fe.mods.empty() && m.type != M_AUDIOFILE && m.type != M_PRE) throw Error(AKUGPU_E_CONFIG, "first module should be a base module");
     if (!fe.mods.empty() && (m.type == M_AUDIOFILE || m.type == M_PRE)) throw Error(AKUGPU_E_CONFIG, "base module must be the first module: " + m.name);
     if (by_name.count(m.name)) throw Error(AKUGPU_E_CONFIG, "multiple definitions of module name: " + m.name);
@@ -462,6 +503,23 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
         m.slapt_params.assign(1, 0.0f);
         break;
       }
+      case M_SR_NORM: {   // SRNormModule::set_module_config, aku/FeatureModules.cc:1954-1989
+        m.in_frames = 0; m.out_frames = 0;
+        get_int(b, "in_frames", m.in_frames); get_int(b, "out_frames", m.out_frames);
+        if (m.in_frames == 0 || m.out_frames == 0) throw Error(AKUGPU_E_CONFIG, "SRNormModule: Must set both in_frames and out_frames.");
+        if (m.in_frames < 0 || m.out_frames < 0 || sdim % m.in_frames != 0)
+          throw Error(AKUGPU_E_CONFIG, "SRNormModule: in_frames does not match with the input dimension");
+        m.frame_dim = sdim / m.in_frames;
+        m.dim = m.out_frames * m.frame_dim;
+        m.lanczos_order = 4; get_int(b, "lanczos_order", m.lanczos_order);
+        if (m.lanczos_order < 1) throw Error(AKUGPU_E_CONFIG, "SRNormModule: lanczos_order must be positive.");
+        m.speech_rate = 1.0f; get_float(b, "speech_rate", m.speech_rate);
+        break;
+      }
+      case M_QUANTEQ:     // QuantEqModule::set_module_config :2086-2093 (quant_train only matters to the trainer)
+        m.dim = sdim;
+        m.q_alpha.clear(); m.q_gamma.clear(); m.q_max.clear();
+        break;
       case M_MEAN_SUBTRACTOR: {
         m.dim = sdim;
         int l = 75, r = 75;
@@ -493,6 +551,12 @@ void frontend_set_parameters(akugpu_ctx *ctx, const std::string &module, const s
   const Block &b = blocks[0];
   if (m.type == M_NORMALIZATION) {
     read_normalization(m, b);
+  } else if (m.type == M_SR_NORM) {     // SRNormModule::set_parameters :1991-1996
+    m.speech_rate = 1.0f;
+    get_float(b, "speech_rate", m.speech_rate);
+  } else if (m.type == M_QUANTEQ) {     // QuantEqModule::set_parameters :2095-2104
+    m.q_alpha.clear(); m.q_gamma.clear(); m.q_max.clear();
+    get_fvec(b, "alpha", m.q_alpha); get_fvec(b, "gamma", m.q_gamma); get_fvec(b, "quant_max", m.q_max);
   } else if (m.type == M_VTLN) {        // VtlnModule::set_parameters, aku/FeatureModules.cc:1575-1592
     if (m.use_slapt) {
       m.slapt_params.assign(1, 0.0f);
@@ -897,6 +961,40 @@ __global__ void fe_vtln(const double *__restrict__ src, int dim, int64_t n_rows,
   }
 }
 
+// SRNormModule::generate (aku/FeatureModules.cc:2039-2061): the input row holds in_frames stacked frames; every output
+// frame is a Lanczos-weighted sum of input frames (float taps, double data and accumulator), clamped at 0 as a float.
+__global__ void fe_srnorm(const double *__restrict__ src, int sdim, int frame_dim, int out_frames, int64_t n_rows,
+                          const float *__restrict__ coef, const int *__restrict__ desc, double *__restrict__ out)
+{
+  const int odim = out_frames * frame_dim;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * odim) return;
+  const int64_t r = i / odim;
+  const int c = (int)(i - r * odim);
+  const int of = c / frame_dim, d = c - of * frame_dim;
+  const double *data = src + r * sdim;
+  const int fi = desc[3 * of], n = desc[3 * of + 1];
+  const float *cf = coef + desc[3 * of + 2];
+  double t = 0;
+  for (int j = 0; j < n; j++) t = __dadd_rn(t, __dmul_rn((double)cf[j], data[(fi + j) * frame_dim + d]));
+  out[i] = (double)fmaxf((float)t, 0.0f);
+}
+
+// QuantEqModule::generate (:2122-2140), operation for operation -- including the reference's parenthesisation, which puts
+// the linear term into the exponent: q * (alpha * pow(x / q, gamma + (1 - alpha) * (x / q))).
+__global__ void fe_quanteq(const double *__restrict__ src, int dim, int64_t n_rows, const float *__restrict__ par, int active,
+                           double *__restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dim) return;
+  if (!active) { out[i] = src[i]; return; }
+  const int k = (int)(i % dim);
+  const float alpha = par[k], gamma = par[dim + k], q = par[2 * dim + k];
+  const double u = __ddiv_rn(src[i], (double)q);
+  const double e = __dadd_rn((double)gamma, __dmul_rn((double)__fsub_rn(1.f, alpha), u));
+  out[i] = __dmul_rn((double)q, __dmul_rn((double)alpha, pow(u, e)));
+}
+
 // NormalizationModule::generate (:1136-1142)
 __global__ void fe_norm(const double *__restrict__ src, int dim, int64_t n_rows, const float *__restrict__ mean,
                         const float *__restrict__ scale, double *__restrict__ out)
@@ -1190,6 +1288,14 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
         break;
       case M_MEAN_SUBTRACTOR:
         fe_meansub<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, dr, du, H, mod.left, mod.right, o);
+        break;
+      case M_SR_NORM:
+        fe_srnorm<<<grid1(ne, 256), 256, 0, st>>>(s0, sdim, mod.frame_dim, mod.out_frames, n_rows, mod.d_a->as<float>(),
+                                                  mod.d_b->as<int>(), o);
+        break;
+      case M_QUANTEQ:
+        fe_quanteq<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, mod.d_a->as<float>(),
+                                                   (!mod.q_alpha.empty() && !mod.q_gamma.empty() && !mod.q_max.empty()) ? 1 : 0, o);
         break;
       case M_VTLN:
         fe_vtln<<<grid1(ne, 256), 256, 0, st>>>(s0, mod.dim, n_rows, mod.d_a->as<float>(), mod.d_b->as<int>(), mod.d_c->as<float>(),

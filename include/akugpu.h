@@ -63,7 +63,7 @@ int         akugpu_stage_times_reset(akugpu_ctx *ctx, int enable);
  * and the module classes of aku/FeatureModules.cc.  The text is the reference's
  * own `module { name .. type .. sources .. }` format.  Supported module types:
  * audiofile, pre, fft, vtln (not all-pass), mel, power, mel_power, dct, delta, merge, concat, normalization,
- * lin_transform, mean_subtractor.  Others (sr_norm, quanteq) return AKUGPU_E_CONFIG. */
+ * lin_transform, mean_subtractor, sr_norm, quanteq -- every module type of aku/FeatureModules.cc. */
 int   akugpu_frontend_load_config(akugpu_ctx *ctx, const char *cfg_path);
 int   akugpu_frontend_load_config_text(akugpu_ctx *ctx, const char *cfg_text);
 int   akugpu_frontend_dim(akugpu_ctx *ctx);            /* FeatureGenerator::dim()         */
@@ -76,7 +76,8 @@ int   akugpu_frontend_base_is_pre(akugpu_ctx *ctx);    /* 1: the base module is 
 int64_t akugpu_frontend_num_frames(akugpu_ctx *ctx, int64_t n_samples);
 /* FeatureModule::set_parameters for a named module (aku/FeatureModule.hh:107):
  * `text` holds `key value...` lines as in a config block (lin_transform: "matrix ...", "bias ..."; normalization:
- * "mean ...", "scale ..."; vtln: "warp_factor w" or "slapt_coef ..."). */
+ * "mean ...", "scale ..."; vtln: "warp_factor w" or "slapt_coef ..."; sr_norm: "speech_rate r"; quanteq: "alpha ...",
+ * "gamma ...", "quant_max ..."). */
 int   akugpu_frontend_set_parameters(akugpu_ctx *ctx, const char *module_name, const char *text);
 
 /* Batch feature computation: replaces the per-frame FeatureGenerator::generate(f)

@@ -65,6 +65,12 @@ def ref_vtln():
 
 
 @pytest.fixture(scope="session")
+def ref_modx():
+    z = np.load(os.path.join(GOLDEN, "ref_modx.npz"))
+    return {k: (str(z[k]) if k.startswith(("cfg_", "spkc_")) else z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="session")
 def aku_tests():
     z = np.load(os.path.join(GOLDEN, "aku_tests.npz"))
     return {k: (str(z[k]) if k.endswith("_cfg") else z[k]) for k in z.files}

@@ -24,6 +24,8 @@ Run in the dev container (needs /root/reference and oracle/_ref built by oracle/
   ref_vtln.npz    the vtln module (VtlnModule: bilinear / piecewise-linear / SLAPT warps, Lanczos-sinc or linear
                   interpolation) between fft and mel, warp factors set per speaker through a speaker file: the
                   reference's 39-dim features for four configurations x three speakers.
+  ref_modx.npz    the two remaining module types: sr_norm (Lanczos resampling over the frames a concat module stacked,
+                  speech rate per speaker) and quanteq (per-channel power-law equalisation, parameters per speaker).
   ref_edge.npz    the same for a handmade edge-case model (underflow / denormal / floor regimes,
                   zero-variance dimensions, tiny weights).
 """
@@ -316,6 +318,87 @@ def vtln_case(pcm, tmp):
     np.savez_compressed(os.path.join(HERE, "ref_vtln.npz"), **out)
 
 
+MODX_HEAD = """module
+{
+  name audiofile
+  type audiofile
+  sample_rate 16000
+}
+
+module
+{
+  name fft
+  type fft
+  sources audiofile
+}
+
+module
+{
+  name mel
+  type mel
+  sources fft
+}
+
+"""
+SRNORM_CFG = MODX_HEAD + """module
+{
+  name stack
+  type concat
+  sources mel
+  left 3
+  right 3
+}
+
+module
+{
+  name srn
+  type sr_norm
+  sources stack
+  in_frames 7
+  out_frames 5
+  lanczos_order 2
+}
+"""
+QUANTEQ_CFG = MODX_HEAD + """module
+{
+  name qe
+  type quanteq
+  sources mel
+}
+
+module
+{
+  name mfcc
+  type dct
+  sources qe
+}
+"""
+
+
+def modx_case(pcm, tmp):
+    rng = np.random.default_rng(7006)
+    wav = os.path.join(tmp, "modx.wav")
+    formats.write_wav(wav, pcm[:12000], 16000)
+    out = dict(pcm=pcm[:12000], cfg_srnorm=SRNORM_CFG, cfg_quanteq=QUANTEQ_CFG)
+    vec = lambda a: " ".join("%.6g" % v for v in a)
+    spk = {"srnorm": {"s1": "speech_rate 0.8", "s2": "speech_rate 1.3"},
+           "quanteq": {"s1": "alpha %s\n    gamma %s\n    quant_max %s" % (vec(rng.uniform(0.3, 0.9, 21)), vec(rng.uniform(0.5, 1.5, 21)), vec(rng.uniform(4, 9, 21))),
+                       "s2": "alpha %s\n    gamma %s\n    quant_max %s" % (vec(rng.uniform(0.3, 0.9, 21)), vec(rng.uniform(0.5, 1.5, 21)), vec(rng.uniform(4, 9, 21)))}}
+    for name, cfg_text, mod in (("srnorm", SRNORM_CFG, "srn"), ("quanteq", QUANTEQ_CFG, "qe")):
+        cfg = os.path.join(tmp, "modx_%s.cfg" % name)
+        open(cfg, "w").write(cfg_text)
+        spkc = "speaker default\n{\n  %s\n  {\n  }\n}\n\n" % mod + "".join(
+            "speaker %s\n{\n  %s\n  {\n    %s\n  }\n}\n\n" % (k, mod, v) for k, v in spk[name].items())
+        sp = os.path.join(tmp, "modx_%s.spkc" % name)
+        open(sp, "w").write(spkc)
+        out["spkc_" + name] = spkc
+        for who in ("s1", "s2", "other"):
+            out["feats_%s_%s" % (name, who)] = ref.features_spk(cfg, wav, sp, who)
+        print("ref_modx", name, out["feats_%s_s1" % name].shape,
+              "max |s1 - default| %.3f" % np.abs(out["feats_%s_s1" % name] - out["feats_%s_other" % name]).max())
+    np.savez_compressed(os.path.join(HERE, "ref_modx.npz"), **out)
+
+
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
@@ -331,6 +414,7 @@ def main():
         spk_case(pcm, small_model(feats, 7002), tmp)
         pre_case(feats, tmp)
         vtln_case(pcm, tmp)
+        modx_case(pcm, tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
         run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 

@@ -156,6 +156,29 @@ def test_vtln_module(engine, ref_vtln, variant, tmp_path):
         engine.frontend_load_config_text(g["cfg_blin"].replace("type vtln", "type vtln\n  all-pass 1"))
 
 
+@pytest.mark.parametrize("which", ["srnorm", "quanteq"])
+def test_sr_norm_and_quanteq_modules(engine, ref_modx, which, tmp_path):
+    """The last two module types of aku/FeatureModules.cc: sr_norm (:1936-2069, Lanczos resampling over the frames a concat
+    module stacked, speech rate per speaker) and quanteq (:2072-2148, per-channel power law, parameters per speaker,
+    identity without them): features within the front-end's usual bar of the reference's for three speakers."""
+    from aaltoasr_b200 import SpeakerConfig
+    g = ref_modx
+    engine.frontend_load_config_text(g["cfg_" + which])
+    spkc = str(tmp_path / "m.spkc")
+    open(spkc, "w").write(g["spkc_" + which])
+    sc = SpeakerConfig(engine)
+    sc.read_speaker_file(spkc)
+    got = {}
+    for spk in ("s1", "other", "s2"):
+        sc.set_speaker(spk)
+        feats, _ = engine.features(g["pcm"], dtype=np.float64)
+        want = g["feats_%s_%s" % (which, spk)]
+        assert feats.shape == want.shape
+        assert np.abs(feats - want).max() <= 3e-5, (which, spk, np.abs(feats - want).max())
+        got[spk] = feats
+    assert np.abs(got["s1"] - got["other"]).max() > 0.1
+
+
 def test_pre_base_module(engine, ref_pre, aku_tests):
     """`pre` base module (stored float32 features, aku/FeatureModules.cc:603-755) followed by a delta module: equal
     to the reference's doubles, also outside the file (first / last row replicated); and the third aku/tests golden:
@@ -561,6 +584,9 @@ def test_full_size_properties(engine, big_case):
 
 # ------------------------------------------------------------------ error behaviour
 def test_errors(engine, ref_small):
+    with pytest.raises(AkuGpuError, match="SRNormModule: Must set both in_frames and out_frames"):
+        engine.frontend_load_config_text("module\n{\n name a\n type audiofile\n sample_rate 16000\n}\nmodule\n{\n name f\n type fft\n sources a\n}\n"
+                                         "module\n{\n name s\n type sr_norm\n sources f\n}\n")
     with pytest.raises(AkuGpuError, match="Unknown module type"):
         engine.frontend_load_config_text("module\n{\n name a\n type nonsense\n}\n")
     with pytest.raises(AkuGpuError, match="first module should be a base module"):
