@@ -110,7 +110,7 @@ lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int norma
         if (k != wstar && sh_M[k][lane] != -INFINITY) Rt += (1.0 + sh_R[k][lane]) * exp((double)(sh_M[k][lane] - gM));
     }
     Mx = gM;
-    lognorm = log1p(Rt);
+    lognorm = (double)(float)log1p(Rt);     // the normaliser is a float everywhere (scorer epilogue, lna_f32_norm)
   }
 
   for (int s_round = 0; s_round < S; s_round += 64) {
@@ -153,6 +153,63 @@ lna_f32(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, int norma
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lna_f32_norm: the first pass of lna_f32 on its own -- per frame the maximum of the float-cast state likelihoods and
+// log1p of the sum of all the others relative to it -- for scorers that do not produce it in their epilogue (FP32-pipe
+// kernel, launches whose component tiles are split over several CTAs).  Same layout of work as lna_f32; the result
+// feeds lna_f32_rows, which then reads the scores once more.
+__global__ void __launch_bounds__(256)
+lna_f32_norm(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, float2 *__restrict__ norm)
+{
+  __shared__ float sh_M[8][32];
+  __shared__ double sh_R[8][32];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int64_t f = (int64_t)blockIdx.x * 32 + lane;
+  const bool fvalid = f < nf;
+  const float *col = sll + (fvalid ? f : 0);
+  float Mx = -INFINITY;
+  double R = 0.0;
+  for (int sb = w * 8; sb < S; sb += 64) {
+    float L[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) L[j] = (sb + j < S) ? __ldg(col + (int64_t)(sb + j) * ldF) : -INFINITY;
+    float bm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { L[j] = log_of_float_cast(L[j]); bm = fmaxf(bm, L[j]); }
+    if (bm == -INFINITY) continue;
+    bool excl = false;
+    if (bm > Mx) {
+      R = (Mx == -INFINITY) ? 0.0 : (R + 1.0) * (double)__expf(Mx - bm);
+      Mx = bm;
+      excl = true;          // the first element equal to the new maximum is the excluded one
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (excl && L[j] == Mx) { excl = false; continue; }
+      if (L[j] != -INFINITY) acc += __expf(L[j] - Mx);
+    }
+    R += (double)acc;
+  }
+  sh_M[w][lane] = Mx;
+  sh_R[w][lane] = R;
+  __syncthreads();
+  if (w != 0 || !fvalid) return;
+  float gM = sh_M[0][lane];
+  int wstar = 0;
+#pragma unroll
+  for (int k = 1; k < 8; ++k)
+    if (sh_M[k][lane] > gM) { gM = sh_M[k][lane]; wstar = k; }
+  double Rt = 0.0;
+  if (gM != -INFINITY) {
+    Rt = sh_R[wstar][lane];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k != wstar && sh_M[k][lane] != -INFINITY) Rt += (1.0 + sh_R[k][lane]) * exp((double)(sh_M[k][lane] - gM));
+  }
+  norm[f] = make_float2(gM, (float)log1p(Rt));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -310,8 +367,16 @@ void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64
 {
   if (nf <= 0) return;
   unsigned grid = (unsigned)((nf + 31) / 32);
-  // row-streaming kernel: needs the scorer's per-frame normaliser (or no normalisation) and 4-byte aligned rows
-  if ((!normalize || norm) && ((size_t)S * lnabytes) % 4 == 0 && ((uintptr_t)out & 3) == 0 && !getenv("AKUGPU_LNA_OLD")) {
+  // row-streaming kernel: needs 4-byte aligned rows; the per-frame normaliser comes from the scorer's epilogue or from
+  // a pass of its own
+  if (((size_t)S * lnabytes) % 4 == 0 && ((uintptr_t)out & 3) == 0 && !getenv("AKUGPU_LNA_OLD")) {
+    if (normalize && !norm) {
+      ctx->d_norm.reserve((size_t)(nf + 31) / 32 * 32 * sizeof(float2));
+      lna_f32_norm<<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, ctx->d_norm.as<float2>());
+      AKU_CUDA(cudaGetLastError());
+      ctx->launches++;
+      norm = ctx->d_norm.as<float2>();
+    }
     if (lnabytes == 2 && normalize) lna_f32_rows<2, true><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
     else if (lnabytes == 2) lna_f32_rows<2, false><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
     else if (normalize) lna_f32_rows<4, true><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
