@@ -15,6 +15,20 @@ struct Utt { std::string audio, lna, speaker, utterance; double start_time, end_
 
 static bool file_nonempty(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
 
+// Output names as io::Stream understands them (aku/io.cc:35-130): "-" = standard output, a leading '|' = pipe to a
+// command, a trailing ".gz" = through gzip; anything else a plain file.
+struct OutStream {
+  FILE *fp; bool is_pipe; bool is_stdout;
+  explicit OutStream(const std::string &name) : fp(NULL), is_pipe(false), is_stdout(false) {
+    if (name == "-") { fp = stdout; is_stdout = true; }
+    else if (!name.empty() && name[0] == '|') { fp = popen(name.c_str() + 1, "w"); is_pipe = true; }
+    else if (name.size() >= 3 && name.compare(name.size() - 3, 3, ".gz") == 0) { fp = popen(("gzip > '" + name + "'").c_str(), "w"); is_pipe = true; }
+    else fp = fopen(name.c_str(), "wb");
+    if (!fp) throw std::string("could not open ") + name + " for writing";
+  }
+  ~OutStream() { if (fp && is_pipe) pclose(fp); else if (fp && !is_stdout) fclose(fp); else if (fp) fflush(fp); }
+};
+
 // Recipe::read (aku/Recipe.cc:24-147): key=value fields; keys persist across lines like the reference's map.
 static std::vector<Utt> read_recipe(const std::string &path, int batch, int bindex)
 {
@@ -174,14 +188,13 @@ int main(int argc, char **argv)
         int64_t s = (int64_t)(u.start_time * fr), e = (int64_t)(u.end_time * fr);   // aku/phone_probs.cc:199-206
         if (e == 0 || e > nf) e = nf;
         if (s > e) s = e;
-        FILE *fp = fopen(u.lna.c_str(), "wb");
-        if (!fp) throw std::string("could not open ") + u.lna + " for writing";
+        OutStream os(u.lna);
+        FILE *fp = os.fp;
         uint8_t hdr[5];
         akugpu_lna_header(S, lnabytes, hdr);
         if (fwrite(hdr, 1, 5, fp) != 5 ||
             fwrite(&rec[(size_t)(fo[k] + s) * S * lnabytes], 1, (size_t)(e - s) * S * lnabytes, fp) != (size_t)(e - s) * S * lnabytes)
           throw std::string("Write error");
-        fclose(fp);
       }
       i = j;
     }

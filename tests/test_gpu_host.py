@@ -121,6 +121,15 @@ def test_cpp_tool_flags(engine, ref_small, tmp_path):
     assert r.returncode != 0 and b"Invalid number of bytes" in r.stderr
     r = run("-g", base + ".gk", "-m", base + ".mc", "-p", base + ".ph", "-c", cfg, "-r", rec, "-o", str(out), "-a")
     assert r.returncode == 0
+    # output names as io::Stream takes them (aku/io.cc:35-130): *.gz through gzip, |command through a pipe
+    import gzip
+    rec2 = str(tmp_path / "recipe_gz")
+    w0 = open(rec).read().split()[0]
+    open(rec2, "w").write("%s lna=%s\n%s lna=|cat>%s\n" % (w0, str(tmp_path / "z.lna.gz"), w0, str(tmp_path / "piped.lna")))
+    assert run("-b", base, "-c", cfg, "-r", rec2).returncode == 0
+    plain = open(str(out / "utt0.lna"), "rb").read()
+    assert gzip.open(str(tmp_path / "z.lna.gz"), "rb").read() == plain
+    assert open(str(tmp_path / "piped.lna"), "rb").read() == plain
 
 
 def test_cpp_tool_gaussian_clustering(engine, ref_clust, tmp_path):
