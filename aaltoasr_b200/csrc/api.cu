@@ -147,10 +147,13 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
       const float2 *norm = nullptr;
       if (use_tc) {   // times its own stages; also yields the per-frame normaliser when it sweeps all states
         ctx->d_norm.reserve((size_t)chunk * sizeof(float2));
+        const bool hybrid = use_tc == 2 && ctx->ptc16.hybrid;    // ill-conditioned states: FP32-pipe kernel, same chunk
         const bool got = use_tc == 2
-                             ? launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, ctx->d_norm.as<float2>())
+                             ? launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk,
+                                               hybrid ? nullptr : ctx->d_norm.as<float2>())
                              : launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, ctx->d_norm.as<float2>());
         if (got) norm = ctx->d_norm.as<float2>();
+        if (hybrid) { StageScope sc(ctx, 1); launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
       } else {
         StageScope sc(ctx, 1);
         launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
@@ -618,7 +621,10 @@ static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, in
         launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
       }
     } else {
-      if (use_tc == 2) launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
+      if (use_tc == 2) {
+        launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
+        if (ctx->ptc16.hybrid) launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      }
       else if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
       else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
       if (logmode) launch_floor_f32(ctx, ctx->d_sll.as<float>(), (int64_t)S * chunk, (float)log(tiny));
@@ -717,7 +723,7 @@ int akugpu_scorer_in_use(akugpu_ctx *ctx)
 {
   if (!ctx || !ctx->have_model) return AKUGPU_E_STATE;
   if (ctx->hm.use_clustering && ctx->hm.n_clusters > 0) return 0;
-  if (ctx->ptc16.ready) return ctx->ptc16.stream ? 4 : 3;
+  if (ctx->ptc16.ready) return ctx->ptc16.hybrid ? 5 : (ctx->ptc16.stream ? 4 : 3);
   if (ctx->ptc.ready) return 2;
   return ctx->hm.n_full > 0 ? 0 : 1;
 }

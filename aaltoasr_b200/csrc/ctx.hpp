@@ -141,6 +141,9 @@ struct PackedTC16 {
   int D = 0, L = 0, NCH = 0, KB = 0, n_tiles = 0;   // L = terms incl. the 2 constant ones, NCH = K16 chunks per half, KB = 64-wide k-blocks
   int half = 0, Kp = 0;                              // columns of Bh (= offset of Bl) and of a whole row
   double q_max = 0;                                  // conditioning of the expanded form for this model
+  bool hybrid = false;                               // states in bad_state are left to the FP32-pipe kernel (packed into p32)
+  std::vector<char> bad_state;                       // [S] 1 = a component of the state is too ill-conditioned for the expanded form
+  int n_bad = 0;
   DevBuf B, meta, center, escale, flag;
   std::vector<char> clean;
   std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;

@@ -339,11 +339,13 @@ static inline float bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float
 
 // Slots (16 component positions of one state) in state order; tiles of 8 slots.  The epilogue warps of a TMEM lane
 // quarter each own `group` consecutive slots of a tile: padding slots (state -1) keep a state from straddling a group.
-void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state, std::vector<int> &slot_k0, std::vector<int> &slot_flags)
+void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state, std::vector<int> &slot_k0, std::vector<int> &slot_flags,
+                    const std::vector<char> *skip_state)
 {
   const int HALF = group;        // slots handled by one epilogue warp: no state straddles such a group
   slot_state.clear(); slot_k0.clear(); slot_flags.clear();
   for (int s = 0; s < hm.S; s++) {
+    if (skip_state && (*skip_state)[s]) continue;
     const int K = hm.mix_off[s + 1] - hm.mix_off[s];
     const int ns = std::max(1, (K + tc::GR - 1) / tc::GR);
     if (ns > HALF) throw Error(AKUGPU_E_MODEL, fmt("the tensor-core scorer handles at most %d components per state (state %d has %d)", HALF * tc::GR, s, K));
@@ -356,33 +358,29 @@ void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state
 //   diagonal (L = 2D):        theta = [-p/2 ; p m],  gconst = log sqrt(prod p) - 1/2 sum p m^2        (m = mu - c)
 //   full (L = D(D+3)/2):      theta = [P m ; -1/2 vec(P)] (lower triangle, off-diagonals x sqrt 2; the reference's own
 //                             exponential form, aku/Distributions.cc:1530-1547), gconst = log sqrt(det P) - 1/2 m'Pm
-// The feature centre c is chosen per dimension to minimise max_g p_gd (mu_gd - c_d)^2 (ternary search on a convex
-// function; diagonal of the covariance for full Gaussians): the expanded form adds terms of order q_g = 1/2 sum_d
-// p (mu - c)^2 that cancel against the constant, and its fp32 accumulation error is ~4e-7 * q_g (measured,
-// scripts/shape_check.py).  Returns max_g q_g so that the caller can refuse models the form is too ill-conditioned for.
+// The expanded form adds terms of order q_g = 1/2 sum_d p_gd (mu_gd - c_d)^2 that cancel against the constant, and its
+// fp32 accumulation error is ~4e-7 * q_g (measured, scripts/shape_check.py).  The feature centre c is the
+// precision-weighted mean of the means per dimension (diagonal of the covariance for full Gaussians): it keeps q small
+// for the bulk of the Gaussians -- the outliers are what the caller hands to the direct-form kernel (a minimax centre
+// lowers the worst q but pushes many more states over the limit).  Returns max_g q_g, and q per Gaussian on request.
 double tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<double> &cen, std::vector<double> &theta,
-                          std::vector<double> &gconst)
+                          std::vector<double> &gconst, std::vector<double> *q_of_gauss)
 {
   const int G = hm.G, D = hm.D;
   cen.assign(D, 0.0);
   for (int d = 0; d < D; d++) {
-    double lo = 1e300, hi = -1e300;
-    std::vector<double> mu(G), sp(G);            // mean and sqrt(precision) of this dimension
+    double sw = 0, swm = 0, sm = 0;
     for (int g = 0; g < G; g++) {
-      mu[g] = hm.mean[(size_t)g * D + d];
       const double cv = full ? hm.full_cov[((size_t)hm.full_index[g] * D + d) * D + d] : hm.cov[(size_t)g * D + d];
-      sp[g] = cv > 0 ? 1 / sqrt(cv) : 0;
-      if (sp[g] > 0) { lo = std::min(lo, mu[g]); hi = std::max(hi, mu[g]); }
+      const double pr = cv > 0 ? 1 / cv : 0;
+      sw += pr;
+      swm += pr * hm.mean[(size_t)g * D + d];
+      sm += hm.mean[(size_t)g * D + d];
     }
-    if (!(lo <= hi)) { cen[d] = 0; continue; }
-    auto worst = [&](double c) { double w = 0; for (int g = 0; g < G; g++) w = std::max(w, sp[g] * fabs(mu[g] - c)); return w; };
-    for (int it = 0; it < 50 && hi - lo > 1e-9 * (1 + fabs(hi)); it++) {
-      const double a = lo + (hi - lo) / 3, b = hi - (hi - lo) / 3;
-      if (worst(a) < worst(b)) hi = b; else lo = a;
-    }
-    cen[d] = 0.5 * (lo + hi);
+    cen[d] = sw > 0 && std::isfinite(swm / sw) ? swm / sw : (G ? sm / G : 0);
   }
   double q_max = 0;
+  if (q_of_gauss) q_of_gauss->assign(G, 0.0);
   // per-Gaussian expanded parameters for CENTRED features (double)
   theta.assign((size_t)G * L, 0.0);
   gconst.assign(G, 0.0);
@@ -402,6 +400,7 @@ double tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<dou
       if (c > 0) c = log(sqrt(c));
       gconst[g] = c - 0.5 * q;
       q_max = std::max(q_max, 0.5 * q);
+      if (q_of_gauss) (*q_of_gauss)[g] = 0.5 * q;
     } else {
       std::vector<double> cov(hm.full_cov.begin() + (size_t)hm.full_index[g] * D * D,
                               hm.full_cov.begin() + (size_t)(hm.full_index[g] + 1) * D * D);
@@ -420,6 +419,7 @@ double tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<dou
         for (int j = 0; j <= i; j++, pos++) th[pos] = -0.5 * ((i == j) ? P[(size_t)i * D + j] : sqrt(2.0) * P[(size_t)i * D + j]);
       gconst[g] = log(sqrt(det)) - 0.5 * dot;
       q_max = std::max(q_max, 0.5 * dot);
+      if (q_of_gauss) (*q_of_gauss)[g] = 0.5 * dot;
     }
   }
   return q_max;
@@ -437,9 +437,9 @@ void model_pack_tc(akugpu_ctx *ctx)
   p.Lm = (p.L + tc::BK - 1) / tc::BK * tc::BK;                       // leading terms, padded to whole k-blocks
   p.Kp = p.Lm + (5 * p.L + tc::BK - 1) / tc::BK * tc::BK;          // + the five correction products
   std::vector<double> cen, theta, gconst;
-  p.q_max = tc_expanded_params(hm, p.full, p.L, cen, theta, gconst);
+  p.q_max = tc_expanded_params(hm, p.full, p.L, cen, theta, gconst, nullptr);
   std::vector<int> slot_state, slot_k0, slot_flags;
-  tc_build_slots(hm, tc::SLOTS / 2, slot_state, slot_k0, slot_flags);
+  tc_build_slots(hm, tc::SLOTS / 2, slot_state, slot_k0, slot_flags, nullptr);
   const int n_slots = (int)slot_state.size();
   p.n_tiles = (n_slots + tc::SLOTS - 1) / tc::SLOTS;
   const size_t rows = (size_t)p.n_tiles * tc::BN;

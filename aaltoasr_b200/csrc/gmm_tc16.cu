@@ -465,10 +465,23 @@ void model_pack_tc16(akugpu_ctx *ctx)
   }
   const int half = p.half, Kp = p.Kp;
   std::vector<double> cen, theta, gconst;
-  p.q_max = tc_expanded_params(hm, full, L0, cen, theta, gconst);
-  // ill-conditioned for the expanded form (sharp Gaussians far from the centre): leave it to the direct-form kernels
-  // unless the tensor-core scorer was asked for explicitly (akugpu_set_scorer_variant(ctx, 3))
-  if (p.q_max > TC_Q_MAX && ctx->scorer_variant != 3) return;
+  std::vector<double> q_of;
+  p.q_max = tc_expanded_params(hm, full, L0, cen, theta, gconst, &q_of);
+  // States with a component that is ill-conditioned for the expanded form (sharp Gaussians far from the centre) are
+  // left to the direct-form FP32-pipe kernel (diagonal pools: model_pack packs exactly those states into the FP32
+  // image and both kernels run per chunk); when half of the states or more are like that, or the pool is full
+  // covariance, the tensor-core scorer is not used at all.  akugpu_set_scorer_variant(ctx, 3) switches the check off.
+  p.hybrid = false;
+  p.n_bad = 0;
+  p.bad_state.assign(hm.S, 0);
+  if (ctx->scorer_variant != 3 && p.q_max > TC_Q_MAX) {
+    for (int st = 0; st < hm.S; st++)
+      for (int k = hm.mix_off[st]; k < hm.mix_off[st + 1]; k++)
+        if (hm.mix_w[k] > 0 && q_of[hm.mix_gauss[k]] > TC_Q_MAX) { p.bad_state[st] = 1; break; }
+    for (int st = 0; st < hm.S; st++) p.n_bad += p.bad_state[st];
+    if (full || 2 * p.n_bad >= hm.S) return;
+    p.hybrid = p.n_bad > 0;
+  }
   std::vector<double> tmax(L0, 0.0);
   for (int g = 0; g < G; g++)
     for (int l = 0; l < L0; l++) tmax[l] = std::max(tmax[l], fabs(theta[(size_t)g * L0 + l]));
@@ -483,7 +496,7 @@ void model_pack_tc16(akugpu_ctx *ctx)
   escale[L0] = escale[L0 + 1] = 1.f;
 
   std::vector<int> slot_state, slot_k0, slot_flags;
-  tc_build_slots(hm, tc16::SLOTS_PER_WARP, slot_state, slot_k0, slot_flags);
+  tc_build_slots(hm, tc16::SLOTS_PER_WARP, slot_state, slot_k0, slot_flags, p.hybrid ? &p.bad_state : nullptr);
   const int n_slots = (int)slot_state.size();
   p.n_tiles = (n_slots + tc16::SLOTS - 1) / tc16::SLOTS;
   const size_t rows = (size_t)p.n_tiles * tc16::BN;

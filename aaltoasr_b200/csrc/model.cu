@@ -411,6 +411,21 @@ void model_pack(akugpu_ctx *ctx)
     ctx->have_model = true;
     return;
   }
+  // ---- tensor-core images first: the fp16x2 packer decides which states (if any) it leaves to the FP32-pipe kernel ----
+  ctx->ptc.ready = false;
+  ctx->ptc16.ready = false;
+  ctx->ptc16.hybrid = false;
+  if (tc_wanted(ctx)) model_pack_tc(ctx);
+  else if (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) model_pack_tc16(ctx);
+  // packing can decline (a component constant outside the fp16 range): fall back to the bf16x3 image
+  if (!ctx->ptc16.ready && !ctx->ptc.ready && (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) &&
+      (ctx->ptc16.q_max <= TC_Q_MAX || ctx->scorer_variant == 3)) {
+    const HostModel &h = ctx->hm;
+    bool ok = h.S > 0 && h.G > 0;
+    for (int s = 0; s < h.S && ok; s++) ok = h.mix_off[s + 1] - h.mix_off[s] <= 64;
+    if (ok) model_pack_tc(ctx);
+  }
+  const bool only_bad = ctx->ptc16.ready && ctx->ptc16.hybrid;       // FP32 image = the states the tensor-core image skips
   // ---- fp32 image: slots of 16 components dealt into 8 warp queues (gmm_kernels.cu) ----
   PackedF32 &p = ctx->p32;
   const int NW = 8, GR = 16, TC = NW * GR, META_INTS = 8;
@@ -430,6 +445,7 @@ void model_pack(akugpu_ctx *ctx)
   struct Slot { int state, k0, first, last; };
   std::vector<std::vector<Slot>> queue(NW);
   for (int s = 0; s < S; s++) {
+    if (only_bad && !ctx->ptc16.bad_state[s]) continue;
     const int K = hm.mix_off[s + 1] - hm.mix_off[s];
     const int ns = std::max(1, (K + GR - 1) / GR);
     int q = 0;
@@ -474,18 +490,6 @@ void model_pack(akugpu_ctx *ctx)
   upload(p.center, cenf, ctx->stream);
   upload(p.center64, cen, ctx->stream);
   AKU_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->ptc.ready = false;
-  ctx->ptc16.ready = false;
-  if (tc_wanted(ctx)) model_pack_tc(ctx);
-  else if (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) model_pack_tc16(ctx);
-  // packing can decline (a component constant outside the fp16 range): fall back to the bf16x3 image
-  if (!ctx->ptc16.ready && !ctx->ptc.ready && (ctx->scorer_variant == 0 || ctx->scorer_variant == 3) &&
-      (ctx->ptc16.q_max <= TC_Q_MAX || ctx->scorer_variant == 3)) {
-    const HostModel &h = ctx->hm;
-    bool ok = h.S > 0 && h.G > 0;
-    for (int s = 0; s < h.S && ok; s++) ok = h.mix_off[s + 1] - h.mix_off[s] <= 64;
-    if (ok) model_pack_tc(ctx);
-  }
   ctx->have_model = true;
 }
 

@@ -79,10 +79,11 @@ __device__ __forceinline__ bool elect_one()
 // host helpers implemented in gmm_tc.cu
 void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16);   // 128 x 64 boxes, SWIZZLE_128B
 double tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<double> &cen, std::vector<double> &theta,
-                          std::vector<double> &gconst);
+                          std::vector<double> &gconst, std::vector<double> *q_of_gauss);
 // Largest cancelling magnitude q the expanded form is trusted with: predicted log-likelihood error 4e-7 * q <= 8e-5.
 constexpr double TC_Q_MAX = 200.0;
-void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state, std::vector<int> &slot_k0, std::vector<int> &slot_flags);
+void tc_build_slots(const HostModel &hm, int group, std::vector<int> &slot_state, std::vector<int> &slot_k0, std::vector<int> &slot_flags,
+                    const std::vector<char> *skip_state);
 const int *tc_tile_ranges(akugpu_ctx *ctx, int n_tiles, const std::vector<char> &clean,
                           std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> &ranges, int want, int &got);
 }  // namespace akugpu

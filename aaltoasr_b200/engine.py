@@ -106,7 +106,8 @@ class AkuGpu:
         return float(self._lib.akugpu_model_expanded_form_q(self._h))
 
     def scorer_in_use(self):
-        """0 double path, 1 FP32-pipe, 2 bf16x3 tensor-core, 3 fp16x2 tensor-core (resident A'), 4 fp16x2 (streaming A')."""
+        """0 double path, 1 FP32-pipe, 2 bf16x3 tensor-core, 3 fp16x2 tensor-core (resident A'), 4 fp16x2 (streaming A'),
+        5 fp16x2 tensor-core + FP32-pipe for the ill-conditioned states."""
         return int(self._lib.akugpu_scorer_in_use(self._h))
 
     def pipe_rates(self):

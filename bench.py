@@ -527,7 +527,8 @@ def main():
                                  "algorithmic_bytes_per_launch": alg_bytes},
                     "fp32_pipe_peak_tflops": 2.0 * rates["tile_ffma2"] / 1e12,
                     "scorer_in_use": {0: "double path", 1: "gmm_diag_f32 (FP32 pipe)", 2: "gmm_tc_kernel (bf16x3)",
-                                      3: "gmm_tc16_kernel (resident A')", 4: "gmm_tc16_kernel<0> (streaming A')"}[eng.scorer_in_use()],
+                                      3: "gmm_tc16_kernel (resident A')", 4: "gmm_tc16_kernel<0> (streaming A')",
+                                      5: "gmm_tc16_kernel + gmm_diag_f32 for ill-conditioned states"}[eng.scorer_in_use()],
                     "expanded_form_q_max": eng.expanded_form_q(),
                     "stage_ms": {"frontend": st["frontend"][0], "gmm": gmm_ms, "lna": st["lna"][0]}}
         if eng.scorer_in_use() != 3:

@@ -198,9 +198,10 @@ int akugpu_set_chunk_frames(akugpu_ctx *ctx, int64_t frames);
  *       pools with <= 64 components per state and dim <= 63, the bf16x3-split kernel for full-covariance pools (and as
  *       the fallback when a feature leaves the fp16 range); otherwise the FP32-pipe kernel (diagonal) or the double
  *       path (mixed pools);
- *       The expanded form is used only for models it is well conditioned for (max over Gaussians of
- *       1/2 sum_d (mu_d - c_d)^2 / var_d <= 200 around the minimax centre c: predicted error <= 8e-5 on a
- *       log-likelihood); sharper models go to the direct-form FP32-pipe kernel (diagonal) or the double path (full);
+ *       The expanded form is used only where it is well conditioned (1/2 sum_d (mu_d - c_d)^2 / var_d <= 200 around the
+ *       minimax centre c: predicted error <= 8e-5 on a log-likelihood): states with a sharper component are scored by
+ *       the direct-form FP32-pipe kernel in the same pass (diagonal pools; all states when they are half the model or
+ *       more), ill-conditioned full-covariance pools by the double path;
  *   1 = FP32-pipe kernel with plain FFMA, 2 = FP32-pipe kernel with packed FFMA2,
  *   3 = the tensor-core scorers as in 0 but without the conditioning check,
  *   4 = force the bf16x3-split tensor-core kernel. */
@@ -210,7 +211,8 @@ int akugpu_set_scorer_variant(akugpu_ctx *ctx, int variant);
 double akugpu_model_expanded_form_q(akugpu_ctx *ctx);
 /* Which kernel serves throughput-mode (F32) requests for the loaded model: 0 = the double path (mixed / ill-conditioned
  * full-covariance pools, Gaussian clustering), 1 = FP32-pipe direct form, 2 = bf16x3 tensor-core, 3 = fp16x2 tensor-core
- * with resident A', 4 = fp16x2 tensor-core streaming A'. */
+ * with resident A', 4 = fp16x2 tensor-core streaming A', 5 = fp16x2 tensor-core for the well-conditioned states + FP32-pipe
+ * kernel for the others. */
 int akugpu_scorer_in_use(akugpu_ctx *ctx);
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
  * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2 with constant

@@ -408,6 +408,44 @@ def test_decoder_logprob_feed(engine, case, request):
         engine.gmm_logprobs(g["feats"], precision=F64, tiny=0.0)
 
 
+def test_hybrid_scoring_of_ill_conditioned_states(engine, ref_edge):
+    """States with a component too sharp / too far from the centre for the expanded (GEMM) form are scored by the
+    direct-form FP32-pipe kernel in the same pass, the rest by the tensor-core kernel: the edge-case model (means up to 9
+    sigma out) in the default mode holds the direct-form bar on every state; a model where every second state is sharp
+    goes to the FP32-pipe kernel entirely."""
+    g = ref_edge
+    load_model(engine, g["model"])
+    assert engine.scorer_in_use() == 5 and engine.expanded_form_q() > 200
+    feats32 = g["feats"].astype(np.float32)
+    l0 = engine.launch_count()
+    ll = engine.gmm_score(feats32, precision=F32).astype(np.float64)
+    assert engine.launch_count() - l0 == 3                    # tensor-core kernel + FP32-pipe kernel + transpose
+    want = np.log(oracle_np.state_likelihoods(g["model"], feats32.astype(np.float64)))
+    live = want > -100
+    err = (np.abs(ll - want) / (1 + np.abs(want) / 40))[live]
+    assert err.max() <= 2e-5, err.max()
+    for nb in (2, 4):                                         # and through the LNA epilogue (normaliser pass + row kernel)
+        got = engine.gmm_lna(feats32, precision=F32, lnabytes=nb)
+        ref = engine.gmm_lna(feats32.astype(np.float64), precision=F64, lnabytes=nb)
+        if nb == 4:
+            a, b = lna4(got).astype(np.float64), lna4(ref).astype(np.float64)
+            ok = (np.abs(a - b) <= REL_TOL * np.abs(b)) | (np.abs(a - b) <= 2e-5)
+            assert ok.mean() >= 0.999
+        else:
+            d = np.abs(codes2(got) - codes2(ref))
+            assert (d <= 1).mean() >= 0.999
+    # half of the states sharp: no tensor-core image at all
+    m = dict(g["model"])
+    covs = m["covs"].copy()
+    off = m["mix_offsets"]
+    for s in range(0, len(off) - 1, 2):
+        covs[m["mix_gauss"][off[s]]] = np.abs(covs[m["mix_gauss"][off[s]]]) * 1e-3 + 1e-6
+    m["covs"] = covs
+    load_model(engine, m)
+    assert engine.scorer_in_use() == 1
+    load_model(engine, g["model"])
+
+
 def test_fp16_range_fallback(engine, ref_small):
     """A feature far outside the fp16 range of the default scorer's scaled terms makes the call fall back to the
     bf16x3 kernel: results stay finite and the other frames are unchanged."""
