@@ -147,8 +147,64 @@ class Pipeline:
             elif t == "mean_subtractor":  # :1385-1405
                 m["dim"] = sdim
                 m["ctx_l"], m["ctx_r"] = int(m.get("left", 75)), int(m.get("right", 75))
+            elif t == "vtln":      # VtlnModule::set_module_config :1530-1573 (all-pass variants not restated)
+                m["dim"] = sdim
+                m["use_pwlin"] = int(m.get("pwlin_vtln", 0))
+                m["turn"] = f32(float(m.get("pwlin_turnpoint", 0.8)))
+                m["use_slapt"] = int(m.get("slapt", 0))
+                m["rad"] = int(m.get("sinc_interpolation_rad", 8))
+                if int(m.get("all-pass", 0)):
+                    raise ValueError("VtlnModule: all-pass transforms are not restated")
+                m["lanczos"] = int(m.get("lanczos_window", 1)) > 0
+                m["warp"] = f32(1.0)
+                m["slapt_params"] = [f32(0.0)]
+                _vtln_tables(m)
+            elif t == "sr_norm":   # SRNormModule::set_module_config :1954-1989
+                m["in_frames"], m["out_frames"] = int(m["in_frames"]), int(m["out_frames"])
+                m["frame_dim"] = sdim // m["in_frames"]
+                m["dim"] = m["out_frames"] * m["frame_dim"]
+                m["order"] = int(m.get("lanczos_order", 4))
+                m["rate"] = f32(float(m.get("speech_rate", 1.0)))
+                _srnorm_tables(m)
+            elif t == "quanteq":   # QuantEqModule::set_module_config :2086-2093
+                m["dim"] = sdim
+                m["alpha"] = m["gamma"] = m["qmax"] = None
             else:
                 raise ValueError("Unknown module type '%s'" % t)
+
+    def set_parameters(self, name, text):
+        """FeatureModule::set_parameters (aku/FeatureModule.hh:107) of one module; text = `key value...` lines."""
+        m = self.mods[self.by_name[name]]
+        kv = {}
+        for ln in text.splitlines():
+            p = ln.split(None, 1)
+            if len(p) == 2:
+                kv[p[0]] = p[1]
+        t = m["type"]
+        if t == "vtln":            # :1575-1592
+            if m["use_slapt"]:
+                m["slapt_params"] = list(_fvec(kv["slapt_coef"])) if "slapt_coef" in kv else [f32(0.0)]
+            else:
+                m["warp"] = f32(float(kv.get("warp_factor", 1.0)))
+            _vtln_tables(m)
+        elif t == "sr_norm":       # :1991-1996
+            m["rate"] = f32(float(kv.get("speech_rate", 1.0)))
+            _srnorm_tables(m)
+        elif t == "quanteq":       # :2095-2104
+            m["alpha"] = _fvec(kv["alpha"]) if "alpha" in kv else None
+            m["gamma"] = _fvec(kv["gamma"]) if "gamma" in kv else None
+            m["qmax"] = _fvec(kv["quant_max"]) if "quant_max" in kv else None
+        elif t == "lin_transform":  # :1187-1195
+            sdim = self.mods[self.by_name[m["sources"][-1]]]["dim"]
+            m["matrix_v"] = _fvec(kv["matrix"]).reshape(m["dim"], sdim) if "matrix" in kv else None
+            m["bias_v"] = _fvec(kv["bias"]) if "bias" in kv else None
+        elif t == "normalization":
+            sdim = m["dim"]
+            m["mean_v"] = _fvec(kv["mean"]) if "mean" in kv else np.zeros(sdim, f32)
+            if "var" in kv:
+                m["scale_v"] = np.array([f32(f32(1) / np.sqrt(v, dtype=f32)) for v in _fvec(kv["var"])], dtype=f32)
+            else:
+                m["scale_v"] = _fvec(kv["scale"]) if "scale" in kv else np.ones(sdim, f32)
 
     @property
     def dim(self):
@@ -248,6 +304,41 @@ class Pipeline:
             if m["bias_v"] is not None:
                 out = out + m["bias_v"].astype(np.float64)
             return out
+        if t == "vtln":            # VtlnModule::generate :1906-1934
+            x = ev(src[0], frames)
+            out = np.zeros_like(x)
+            if m["rad"] > 0:
+                for b in range(m["dim"]):
+                    st, cf = m["sinc_start"][b], m["sinc_coef"][b]
+                    acc = np.zeros(x.shape[0])
+                    for i, c in enumerate(cf):          # double accumulator, float taps
+                        acc = acc + x[:, st + i] * float(c)
+                    out[:, b] = np.maximum(acc.astype(f32), f32(0)).astype(np.float64)
+            else:
+                for b in range(m["dim"]):
+                    vb = m["bins"][b]
+                    p = f32(f32(math.ceil(float(vb))) - vb)
+                    out[:, b] = float(p) * x[:, int(math.floor(float(vb)))] + float(f32(f32(1) - p)) * x[:, int(math.ceil(float(vb)))]
+            return out
+        if t == "sr_norm":         # SRNormModule::generate :2039-2061
+            x = ev(src[0], frames)
+            fd = m["frame_dim"]
+            out = np.zeros((x.shape[0], m["dim"]))
+            for i in range(m["out_frames"]):
+                st, cf = m["start"][i], m["coef"][i]
+                acc = np.zeros((x.shape[0], fd))
+                for j, c in enumerate(cf):
+                    acc = acc + float(c) * x[:, (st + j) * fd:(st + j + 1) * fd]
+                out[:, i * fd:(i + 1) * fd] = np.maximum(acc.astype(f32), f32(0)).astype(np.float64)
+            return out
+        if t == "quanteq":         # QuantEqModule::generate :2122-2140 (the linear term sits in the exponent, as written there)
+            x = ev(src[0], frames)
+            if m["alpha"] is None or m["gamma"] is None or m["qmax"] is None:
+                return x.copy()
+            a, g, q = (m[k][:m["dim"]] for k in ("alpha", "gamma", "qmax"))
+            u = x / q.astype(np.float64)
+            e = g.astype(np.float64) + (f32(1) - a).astype(np.float64) * u
+            return q.astype(np.float64) * (a.astype(np.float64) * np.power(u, e))
         if t == "mean_subtractor":  # :1414-1454 (full-window branch; the recursive branch differs by ~1e-15)
             x = ev(src[0], frames)
             acc = np.zeros_like(x)
@@ -285,6 +376,81 @@ class Pipeline:
                 p = np.log(p, dtype=f32)
             out[i] = p.astype(np.float64)
         return out
+
+
+def _sincf(x):
+    """util::sinc (aku/util.hh:151-159): float in, double arithmetic, float out."""
+    x = f32(x)
+    if abs(float(x)) < 1e-8:
+        return f32(1)
+    y = 3.14159265358979323846 * float(x)
+    return f32(math.sin(y) / y)
+
+
+def _vtln_tables(m):
+    """create_blin_bins :1662-1675 / create_pwlin_bins :1634-1660 / create_slapt_bins :1677-1695 and
+    create_sinc_coef_table :1697-1723: float bins, float taps, the reference's mixed arithmetic."""
+    dim = m["dim"]
+    bins = np.zeros(dim, dtype=f32)
+    if m["use_slapt"]:
+        for t in range(dim - 1):
+            nf = math.pi * float(t) / (dim - 1)
+            v = f32(t)
+            for i, sp in enumerate(m["slapt_params"]):
+                v = f32(float(v) + float(sp) * math.sin((i + 1) * nf) * (dim - 1))
+            bins[t] = v
+    elif m["use_pwlin"]:
+        border = f32(m["turn"] * f32(dim - 1))
+        slope = point = f32(0)
+        limit = False
+        for t in range(dim - 1):
+            bins[t] = f32(m["warp"] * f32(t)) if not limit else f32(f32(slope * f32(t)) + point)
+            if not limit and (t >= border or bins[t] >= border):
+                slope = f32(f32(f32(f32(dim) - f32(1)) - bins[t]) / f32(f32(f32(dim) - f32(1)) - f32(t)))
+                point = f32(f32(f32(1) - slope) * f32(dim - 1))
+                limit = True
+    else:
+        w = m["warp"]
+        for t in range(dim - 1):
+            nf = math.pi * float(t) / (dim - 1)
+            bins[t] = f32(t + 2 * math.atan2(float(f32(w - f32(1))) * math.sin(nf), 1 + float(f32(f32(1) - w)) * math.cos(nf))
+                          / math.pi * (dim - 1))
+    bins[dim - 1] = f32(dim - 1)
+    m["bins"] = bins
+    m["sinc_start"], m["sinc_coef"] = [], []
+    rad = m["rad"]
+    if rad > 0:
+        for b in range(dim):
+            cent = int(float(bins[b]) + 0.5)
+            lo, hi = max(cent - rad, 0), min(cent + rad + 1, dim)
+            cf = []
+            for i in range(lo, hi):
+                d = f32(f32(i) - bins[b])
+                t = _sincf(d)
+                if m["lanczos"]:
+                    t = f32(t * _sincf(f32(d / f32(rad)))) if abs(float(d)) < rad else f32(0)
+                cf.append(t)
+            m["sinc_start"].append(lo)
+            m["sinc_coef"].append(cf)
+
+
+def _srnorm_tables(m):
+    """SRNormModule::set_speech_rate :2004-2036."""
+    in_cent = f32(f32(m["in_frames"] - 1) / f32(2))
+    out_cent = f32(f32(m["out_frames"] - 1) / f32(2))
+    m["start"], m["coef"] = [], []
+    for i in range(m["out_frames"]):
+        pos = f32(f32(f32(f32(i) - out_cent) / m["rate"]) + in_cent)
+        cent = int(math.copysign(math.floor(abs(float(pos)) + 0.5), float(pos)))      # roundf: halves away from zero
+        lo, hi = max(cent - m["order"], 0), min(cent + m["order"] + 1, m["in_frames"])
+        cf = []
+        for j in range(lo, hi):
+            d = f32(f32(j) - pos)
+            t = _sincf(d)
+            t = f32(t * _sincf(f32(d / f32(m["order"])))) if abs(float(d)) < m["order"] else f32(0)
+            cf.append(t)
+        m["start"].append(lo)
+        m["coef"].append(cf)
 
 
 def _fft_float32(x):

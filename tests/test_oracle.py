@@ -5,6 +5,8 @@ Pins the checker before it is trusted: (1) the reference's own aku/tests goldens
 code built from source (tests/golden/ref_small.npz, ref_edge.npz; generator:
 tests/golden/make_golden.py), (3) the live reference library when oracle/_ref is present.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -105,6 +107,34 @@ def test_speaker_config_vs_reference(ref_spk):
         d = np.abs(rec.reshape(-1).view(">u2").astype(int) - want[5:].view(">u2").astype(int))
         assert d.max() <= 1 and (d != 0).mean() <= 0.03, (spk, d.max(), (d != 0).mean())
     assert np.array_equal(g["lna2_2"], g["lna2_plain_2"]) and not np.array_equal(g["lna2_0"], g["lna2_plain_0"])
+
+
+@pytest.mark.parametrize("variant", ["blin", "pwlin", "linear", "slapt"])
+def test_vtln_restatement_vs_reference(variant):
+    """vtln module (warped bins, Lanczos-sinc / linear interpolation) with per-speaker parameters: the restatement
+    against the reference's features (tests/golden/ref_vtln.npz, three speakers per configuration)."""
+    from aaltoasr_b200 import parse_speaker_file
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vtln.npz"))
+    conf = parse_speaker_file(str(z["spkc_" + variant]))["speaker"]
+    P = oracle_np.Pipeline(str(z["cfg_" + variant]))
+    for spk in ("s1", "s2", "other"):
+        P.set_parameters("vtln", conf.get(spk, conf["default"])["vtln"])
+        got = P.run(z["pcm"])
+        want = z["feats_%s_%s" % (variant, spk)]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 2e-5, (variant, spk, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("which,mod", [("srnorm", "srn"), ("quanteq", "qe")])
+def test_sr_norm_quanteq_restatement_vs_reference(which, mod):
+    from aaltoasr_b200 import parse_speaker_file
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_modx.npz"))
+    conf = parse_speaker_file(str(z["spkc_" + which]))["speaker"]
+    P = oracle_np.Pipeline(str(z["cfg_" + which]))
+    for spk in ("s1", "s2", "other"):
+        P.set_parameters(mod, conf.get(spk, conf["default"])[mod])
+        got = P.run(z["pcm"])
+        want = z["feats_%s_%s" % (which, spk)]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 3e-5, (which, spk, np.abs(got - want).max())
 
 
 def test_decoder_reader_consumes_lna(ref_small, tmp_path):
