@@ -82,7 +82,11 @@ class Pipeline:
             src = [self.mods[self.by_name[s]] for s in m["sources"]]
             sdim = src[-1]["dim"] if src else 0
             m["ctx_l"] = m["ctx_r"] = 0
-            if t == "audiofile":   # aku/FeatureModules.cc:328-360
+            if t == "pre":         # PreModule::set_module_config :671-689: stored float32 feature rows instead of audio
+                m["dim"] = int(m["dim"])
+                m["sr"] = int(m.get("sample_rate", 16000))
+                m["frate"] = f32(float(m.get("frame_rate", 125)))
+            elif t == "audiofile":   # aku/FeatureModules.cc:328-360
                 sr = int(m["sample_rate"])
                 m["sr"] = sr
                 m["emph"] = f32(float(m.get("pre_emph_coef", 0.97)))
@@ -246,6 +250,32 @@ class Pipeline:
             if mi in need and self.mods[mi]["type"] != "audiofile":
                 lo, hi = need[mi]
                 cache[mi] = (lo, self._eval(mi, np.arange(lo, hi), pcm, n, cache))
+        lo, arr = cache[tgt]
+        return arr[start - lo:end - lo]
+
+    def run_pre(self, rows, start=0, end=None, module=None):
+        """The same for a configuration whose base module is `pre` (PreModule::generate :705-755): rows = the stored
+        float32 features [n x dim]; frames before / after the file repeat the first / last row."""
+        rows = np.asarray(rows, dtype=np.float32)
+        n = rows.shape[0]
+        if end is None:
+            end = n
+        tgt = self.by_name[module] if module else len(self.mods) - 1
+        need = {tgt: [start, end]}
+        for mi in range(tgt, -1, -1):
+            if mi not in need:
+                continue
+            m = self.mods[mi]
+            for sname in m["sources"]:
+                si = self.by_name[sname]
+                lo, hi = need[mi][0] - m["ctx_l"], need[mi][1] + m["ctx_r"]
+                need[si] = [min(need[si][0], lo), max(need[si][1], hi)] if si in need else [lo, hi]
+        lo, hi = need[0]
+        cache = {0: (lo, rows[np.clip(np.arange(lo, hi), 0, n - 1)].astype(np.float64))}
+        for mi in range(1, tgt + 1):
+            if mi in need:
+                lo, hi = need[mi]
+                cache[mi] = (lo, self._eval(mi, np.arange(lo, hi), None, n, cache))
         lo, arr = cache[tgt]
         return arr[start - lo:end - lo]
 

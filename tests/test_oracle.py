@@ -137,6 +137,16 @@ def test_sr_norm_quanteq_restatement_vs_reference(which, mod):
         assert got.shape == want.shape and np.abs(got - want).max() <= 3e-5, (which, spk, np.abs(got - want).max())
 
 
+def test_pre_module_restatement_vs_reference():
+    """`pre` base module + delta: the restatement equals the reference's doubles, also outside the stored rows."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pre.npz"))
+    P = oracle_np.Pipeline(str(z["cfg"]))
+    n = z["rows"].shape[0]
+    assert np.array_equal(P.run_pre(z["rows"]), z["out"])
+    assert np.array_equal(P.run_pre(z["rows"], int(z["ext_start"]), n + 4), z["ext"])
+    assert np.array_equal(P.run_pre(z["rows"], -4, n + 4, module="pre"), z["base_ext"])
+
+
 def test_decoder_reader_consumes_lna(ref_small, tmp_path):
     """The consumer of the stream: the decoder's own LnaReaderCircular (decoder/src/LnaReaderCircular.cc:46-101,130-209,
     compiled into oracle/_ref) reads the reference's LNA files; the Python reader the other tests use
