@@ -418,7 +418,9 @@ def main():
     keep_out = F * rec <= 60e9
     out_d = torch.empty((F, rec), dtype=torch.uint8, device="cuda") if keep_out else None
     # e2e buffers: pinned PCM; LNA drained through one pinned buffer per sub-batch (a writer would stream it out)
-    sub = min(n_utts, int(os.environ.get("AKUGPU_BENCH_SUB", "250")))
+    # utterances per e2e call: 250 on one GPU; fewer per rank when several ranks share the host (pinned memory per rank
+    # = one sub-batch of LNA: 3.1 GB at 250 utterances)
+    sub = min(n_utts, int(os.environ.get("AKUGPU_BENCH_SUB", str(max(50, 250 // max(1, world // 2))))))
     pcm_p = torch.from_numpy(pcm).pin_memory()
     out_p = torch.empty((int(fo[sub]), rec), dtype=torch.uint8).pin_memory()
 
