@@ -385,6 +385,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the accelerated path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner / debug lines to stdout; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     global N_STATES, N_MIX, WORKLOAD
     if args.config in (3, 5):
