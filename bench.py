@@ -215,6 +215,38 @@ def reference_arm(args):
         "gpu_launches": 0}))
 
 
+def bind_to_gpu_numa(torch, local):
+    """Several ranks on one host: keep this rank's threads (and with them its pinned host buffers, first touch) on the
+    CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI device).  Best effort: any failure leaves the affinity alone."""
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+        out = subprocess.run(["nvidia-smi", "--query-gpu=uuid,pci.bus_id", "--format=csv,noheader"], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+        bus = None
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) == 2 and f[0] == uuid:
+                bus = f[1]
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/local_cpulist" % (dom[-4:].lower(), rest.lower())
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, z = part.split("-")
+                cpus.update(range(int(a), int(z) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------
 def _event_time(torch, stream, fn, reps):
     torch.cuda.synchronize()
@@ -384,6 +416,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the accelerated path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa(torch, local) if world > 1 else None
     if world > 1:
         # NCCL prints its version banner / debug lines to stdout; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -566,7 +599,8 @@ def main():
                     "d2h_bytes_per_step": int(F * rec), "ms_per_step": ms_e2e / args.steps,
                     "d2h_GBps": F * rec / (ms_e2e / args.steps * 1e-3) / 1e9, "pcie_d2h_peak_GBps": d2h_gbs,
                     "pcie_frac": (F * rec / (ms_e2e / args.steps * 1e-3) / 1e9) / d2h_gbs,
-                    "note": "LNA records leave the device at the PCIe rate; %d-utterance calls" % sub},
+                    "note": "LNA records leave the device at the PCIe rate; %d-utterance calls%s" % (
+                        sub, "; rank bound to the %d CPUs next to its GPU" % numa_cpus if numa_cpus else "")},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
