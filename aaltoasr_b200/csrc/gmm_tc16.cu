@@ -1,5 +1,8 @@
-// gmm_tc16.cu -- default throughput scorer for diagonal pools: fp16 hi/lo-split tensor-core GEMM (tcgen05 + TMEM + TMA)
-// with the frame tile's expanded features built in the kernel and resident in shared memory.
+// gmm_tc16.cu -- default throughput scorer: fp16 hi/lo-split tensor-core GEMM (tcgen05 + TMEM + TMA).  Diagonal pools:
+// the frame tile's expanded features are built in the kernel and stay resident in shared memory (gmm_tc16_kernel<NCH>);
+// full-covariance pools (K = D(D+3)/2 + 2 terms): the same kernel streaming A' next to B' (gmm_tc16_kernel<0>).
+// Which states it serves is decided at pack time from the conditioning of the expanded form (model_pack_tc16): states with
+// a component too sharp / too far from the feature centre go to the direct-form FP32-pipe kernel in the same pass.
 //
 // Reference arithmetic (aku/Distributions.cc:1041-1062, 2079-2086): for every Gaussian of the pool
 //     ll = -1/2 sum_d p_d (f_d - mu_d)^2 + log sqrt(prod p_d),        state likelihood = sum_k w_k exp(ll_k).
