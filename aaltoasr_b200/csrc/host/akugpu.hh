@@ -15,9 +15,11 @@
 #ifndef AKUGPU_HOST_HH
 #define AKUGPU_HOST_HH
 
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -44,13 +46,13 @@ private:
 // RIFF/WAVE PCM16 mono or headerless RAW PCM16, what aku::AudioReader accepts (aku/AudioReader.cc:86-155).
 inline void read_audio(const std::string &path, int config_rate, bool force_raw, std::vector<int16_t> &pcm, int &rate)
 {
-  FILE *fp = fopen(path.c_str(), "rb");
+  FILE *fp = path == "-" ? stdin : fopen(path.c_str(), "rb");    // "-" = standard input, like io::Stream (aku/io.cc:52-60)
   if (!fp) throw std::string("AudioReader::open(): could not open file:") + path;
   std::vector<unsigned char> b;
   unsigned char buf[65536];
   size_t k;
   while ((k = fread(buf, 1, sizeof buf, fp)) > 0) b.insert(b.end(), buf, buf + k);
-  fclose(fp);
+  if (fp != stdin) fclose(fp);
   size_t off = 0, len = b.size();
   rate = config_rate;
   if (!force_raw && b.size() >= 12 && !memcmp(&b[0], "RIFF", 4) && !memcmp(&b[8], "WAVE", 4)) {
@@ -87,15 +89,15 @@ public:
   }
   // A `pre` base module reads stored features (int32 dim + float32 rows, feacat -H --raw-output) instead of audio.
   void open_pre(const std::string &filename) {
-    FILE *fp = fopen(filename.c_str(), "rb");
+    FILE *fp = filename == "-" ? stdin : fopen(filename.c_str(), "rb");
     if (!fp) throw std::string("could not open file ") + filename;
     int dim = 0;
-    if (fread(&dim, sizeof(int), 1, fp) < 1) { fclose(fp); throw std::string("PreModule: Could not read the file."); }
+    if (fread(&dim, sizeof(int), 1, fp) < 1) { if (fp != stdin) fclose(fp); throw std::string("PreModule: Could not read the file."); }
     m_rows.clear();
     std::vector<float> buf(4096);
     size_t k;
     while ((k = fread(buf.data(), sizeof(float), buf.size(), fp)) > 0) m_rows.insert(m_rows.end(), buf.begin(), buf.begin() + k);
-    fclose(fp);
+    if (fp != stdin) fclose(fp);
     if (dim <= 0 || m_rows.size() % (size_t)dim != 0) throw std::string("PreModule: The file has invalid dimension");
     m_pre_dim = dim;
     int64_t ro[2] = {0, (int64_t)(m_rows.size() / dim)}, fo[2] = {0, 0};
@@ -133,6 +135,19 @@ public:
       check(m_e.ctx(), akugpu_features_range(m_e.ctx(), m_pcm.data(), (int64_t)m_pcm.size(), frame, frame + 1, NULL,
                                              m_tmp.data(), 1, &dim));
     return m_tmp.data();
+  }
+  // Frames [start, end) in one GPU call, frames outside the file as the reference's border handling gives them
+  // (feacat --start-frame / --end-frame, aku/feacat.cc:96-121).  Re-run after SpeakerConfig changes parameters.
+  void generate_range(int start, int end, std::vector<double> &out) {
+    int dim = 0;
+    out.resize((size_t)std::max(0, end - start) * m_dim);
+    if (end <= start) return;
+    if (!m_rows.empty())
+      check(m_e.ctx(), akugpu_features_pre_range(m_e.ctx(), m_rows.data(), (int64_t)(m_rows.size() / m_pre_dim), start, end,
+                                                 NULL, out.data(), 1, &dim));
+    else
+      check(m_e.ctx(), akugpu_features_range(m_e.ctx(), m_pcm.data(), (int64_t)m_pcm.size(), start, end, NULL,
+                                             out.data(), 1, &dim));
   }
   const std::vector<double> &features() const { return m_feats; }   // all frames, [frames x dim]
   bool eof() const { return m_eof; }

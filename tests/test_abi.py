@@ -50,6 +50,23 @@ def test_create_fails_loudly_without_cuda():
         aaltoasr_b200.AkuGpu(0)
 
 
+@pytest.mark.parametrize("tool", ["akugpu_phone_probs", "akugpu_feacat"])
+def test_host_tools_build_and_fail_loudly_without_cuda(tool, tmp_path):
+    """The C++ tools over the ABI (aku/phone_probs.cc, aku/feacat.cc re-hosted) are built by build(), print their
+    usage without a device, and exit non-zero with the library's message when there is none."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "aaltoasr_b200", tool)
+    assert os.access(exe, os.X_OK), exe + " missing: run __graft_entry__.build()"
+    r = subprocess.run([exe, "--help"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode == 0 and b"usage: " + tool.encode() in r.stdout and b"--config" in r.stdout
+    if torch.cuda.is_available():
+        return
+    args = ["-c", str(tmp_path / "x.cfg")] + (["-r", str(tmp_path / "x.recipe"), "-b", "m"] if tool.endswith("probs") else ["x.wav"])
+    r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode != 0 and b"no CPU fallback" in r.stderr
+
+
 def test_formats_roundtrip(tmp_path):
     pcm = synth.synth_audio(5, 4000)
     formats.write_wav(str(tmp_path / "a.wav"), pcm, 16000)

@@ -205,3 +205,82 @@ def test_cpp_tool_speaker_config(engine, ref_spk, tmp_path):
     r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-S", spkc],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert r.returncode != 0 and b"outside the accelerated scope" in r.stderr
+
+
+FEACAT = os.path.join(ROOT, "aaltoasr_b200", "akugpu_feacat")
+
+
+def _ascii_rows(b):
+    return np.array([[float(x) for x in l.split()] for l in b.decode().splitlines() if l.strip()])
+
+
+def test_feacat_tool_aku_scripts(engine, aku_tests, ref_vtln, tmp_path):
+    """akugpu_feacat run the way the reference's own regression scripts run feacat
+    (aku/tests/mfcc_p_dd.script, mfcc_cms_norm.script, pre_test.script), against their .ref outputs;
+    the bar is theirs: equal at the 4 printed decimals up to the reference's float-buffer rounding (5.1e-3)."""
+    wav = str(tmp_path / "short.wav")
+    formats.write_wav(wav, aku_tests["short_wav"], int(aku_tests["sample_rate"]))
+    cfgs = {}
+    for k in ("mfcc_p_dd", "mfcc_cms_norm", "pre"):
+        cfgs[k] = str(tmp_path / (k + ".feaconf"))
+        open(cfgs[k], "w").write(aku_tests[k + "_cfg"])
+    run = lambda *a, **kw: subprocess.run([FEACAT] + list(a), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, **kw)
+    # mfcc_p_dd.script: audio on standard input, negative start, --write-config and a second run on the written copy
+    tmpcfg = str(tmp_path / "mfcc_p_dd.feaconf.tmp")
+    audio = open(wav, "rb").read()
+    r1 = run("--start-frame", "-10", "--end-frame", "80", "--write-config", tmpcfg, "-c", cfgs["mfcc_p_dd"], "-", input=audio)
+    assert r1.returncode == 0, r1.stderr.decode()
+    r2 = run("--start-frame", "-10", "--end-frame", "80", "-c", tmpcfg, "-", input=audio)
+    assert r2.returncode == 0, r2.stderr.decode()
+    got = _ascii_rows(r1.stdout + r2.stdout)
+    gold = aku_tests["mfcc_p_dd_ref"]
+    assert got.shape == gold.shape and np.abs(got - gold).max() <= 0.0051
+    assert r1.stdout == r2.stdout
+    # every row is "%8.4f " per component
+    line = r1.stdout.decode().splitlines()[0]
+    assert len(line) == 9 * gold.shape[1] and line.endswith(" ")
+    # mfcc_cms_norm.script: short options, frames past both ends
+    r = run("-c", cfgs["mfcc_cms_norm"], "-s", "-15", "-e", "90", "-", input=audio)
+    assert r.returncode == 0, r.stderr.decode()
+    got = _ascii_rows(r.stdout)
+    assert got.shape == aku_tests["mfcc_cms_norm_ref"].shape and np.abs(got - aku_tests["mfcc_cms_norm_ref"]).max() <= 0.0051
+    # pre_test.script: raw output with header, read back through a `pre` configuration
+    r = run("--start-frame", "10", "--end-frame", "60", "-c", cfgs["mfcc_p_dd"], "-H", "--raw-output", wav)
+    assert r.returncode == 0, r.stderr.decode()
+    dim = int(np.frombuffer(r.stdout[:4], "<i4")[0])
+    assert dim == 39 and len(r.stdout) == 4 + 51 * 39 * 4
+    pre = str(tmp_path / "pre_test.tmp")
+    open(pre, "wb").write(r.stdout)
+    r = run("-c", cfgs["pre"], pre)
+    assert r.returncode == 0, r.stderr.decode()
+    got = _ascii_rows(r.stdout)
+    assert got.shape == aku_tests["pre_test_ref"].shape and np.abs(got - aku_tests["pre_test_ref"]).max() <= 0.0051
+    # whole file (open end), a descending range, and the library's own matrix behind the same rows
+    engine.frontend_load_config_text(aku_tests["mfcc_p_dd_cfg"])
+    full, _ = engine.features(aku_tests["short_wav"], dtype=np.float64)
+    r = run("-c", cfgs["mfcc_p_dd"], "--raw-output", wav)
+    assert r.returncode == 0, r.stderr.decode()
+    raw = np.frombuffer(r.stdout, "<f4").reshape(-1, 39)
+    assert raw.shape == full.shape and np.array_equal(raw, full.astype(np.float32))
+    r = run("-c", cfgs["mfcc_p_dd"], "--raw-output", "-s", "5", "-e", "-3", wav)
+    assert r.returncode == 0, r.stderr.decode()
+    desc = np.frombuffer(r.stdout, "<f4").reshape(-1, 39)
+    want = engine.features_range(aku_tests["short_wav"], -3, 6, dtype=np.float64)[::-1]
+    assert np.array_equal(desc, want.astype(np.float32))
+    # -S / -d: a speaker's feature-module parameters (the vtln warp) reach the front-end; goldens = the reference's
+    cfg = str(tmp_path / "vtln.cfg")
+    open(cfg, "w").write(ref_vtln["cfg_blin"])
+    spkc = str(tmp_path / "v.spkc")
+    open(spkc, "w").write(ref_vtln["spkc_blin"])
+    w2 = str(tmp_path / "v.wav")
+    formats.write_wav(w2, ref_vtln["pcm"], 16000)
+    for spk in ("s1", "other", "s2"):
+        r = run("-c", cfg, "-S", spkc, "-d", spk, "--raw-output", w2)
+        assert r.returncode == 0, r.stderr.decode()
+        gold = ref_vtln["feats_blin_" + spk]
+        got = np.frombuffer(r.stdout, "<f4").reshape(-1, gold.shape[1])
+        assert got.shape == gold.shape and np.abs(got - gold).max() <= 2e-5 + 1e-6 * np.abs(gold).max()
+    # errors: -G refused, bad config reported like the reference ("exception: ...", non-zero exit)
+    assert run("-c", cfgs["mfcc_p_dd"], "-G", "0.1", wav).returncode != 0
+    r = run("-c", str(tmp_path / "missing.cfg"), wav)
+    assert r.returncode != 0 and b"exception:" in r.stderr
