@@ -205,6 +205,17 @@ static const void *to_device(akugpu_ctx *ctx, const void *src, size_t bytes, Dev
   return scratch.p;
 }
 
+// With a global model-level CMLLR set (akugpu_model_set_cmllr) the scorers see A f + b instead of f.
+static const void *adapt_feats(akugpu_ctx *ctx, const void *d_feats, int feats_f64, int64_t F)
+{
+  if (!ctx->hm.cmllr_on || F <= 0) return d_feats;
+  const int D = ctx->hm.D;
+  ctx->d_adapt.reserve((size_t)F * D * (feats_f64 ? 8 : 4));
+  StageScope sc(ctx, 1);
+  launch_affine_rows(ctx, d_feats, feats_f64, F, D, ctx->d_cmllr.as<double>(), ctx->d_adapt.p);
+  return ctx->d_adapt.p;
+}
+
 extern "C" {
 
 akugpu_ctx *akugpu_create(int device)
@@ -514,6 +525,7 @@ int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim, 
   hm.cov.assign(covs, covs + (size_t)n_gauss * dim);
   hm.full_index.clear(); hm.full_cov.clear(); hm.n_full = 0;
   hm.clear_clustering();
+  hm.clear_cmllr();
   model_pack(ctx);
   API_END
 }
@@ -579,6 +591,48 @@ int akugpu_model_use_clustering(akugpu_ctx *ctx, int on)
   API_END
 }
 
+// ---- model-level CMLLR, global transform (phone_probs -S with a `model cmllr` entry, unitmode UNIT_NO) ----
+int akugpu_model_set_cmllr(akugpu_ctx *ctx, const double *W)
+{
+  API_BEGIN
+  require_model(ctx);
+  HostModel &hm = ctx->hm;
+  const int D = hm.D;
+  if (!W && !hm.cmllr_on) return AKUGPU_OK;
+  double factor = 1.0;
+  if (W) {
+    // AdaptedGaussian::compute_likelihood multiplies by AdaptedFeatureVector::determinant_A =
+    // |LinearAlgebra::full_matrix_determinant(A)| (aku/ModelModules.hh:141,170).  That routine LU-factorises a copy but
+    // multiplies the diagonal of A itself (aku/LinearAlgebra.cc:74-86), so the factor is |prod_i A(i,i)|, not |det A|;
+    // the reference's numbers are the contract, hence the same factor here.
+    for (int i = 0; i < D; i++) factor *= W[(size_t)i * (D + 1) + 1 + i];
+    factor = fabs(factor);
+    if (!(factor > 0) || std::isinf(factor)) throw Error(AKUGPU_E_ARG, "CMLLR: the diagonal of A must be finite and non-zero");
+    for (size_t i = 0; i < (size_t)D * (D + 1); i++)
+      if (!std::isfinite(W[i])) throw Error(AKUGPU_E_ARG, "CMLLR: W has a non-finite element");
+  }
+  if (hm.mix_w_base.empty()) hm.mix_w_base = hm.mix_w;
+  ctx->have_model = false;
+  if (W) {
+    hm.cmllr_W.assign(W, W + (size_t)D * (D + 1));
+    std::vector<double> Ab((size_t)D * D + D);
+    for (int i = 0; i < D; i++) {
+      for (int j = 0; j < D; j++) Ab[(size_t)i * D + j] = W[(size_t)i * (D + 1) + 1 + j];
+      Ab[(size_t)D * D + i] = W[(size_t)i * (D + 1)];
+    }
+    ctx->d_cmllr.reserve(Ab.size() * sizeof(double));
+    AKU_CUDA(cudaMemcpyAsync(ctx->d_cmllr.p, Ab.data(), Ab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < hm.mix_w.size(); k++) hm.mix_w[k] = hm.mix_w_base[k] * factor;
+    hm.cmllr_on = true;
+  } else {
+    hm.mix_w = hm.mix_w_base;
+    hm.clear_cmllr();
+  }
+  model_pack(ctx);          // every scorer image carries the weights
+  API_END
+}
+
 int akugpu_model_num_states(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->hm.S : AKUGPU_E_STATE; }
 int akugpu_model_dim(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->hm.D : AKUGPU_E_STATE; }
 int akugpu_model_num_gaussians(akugpu_ctx *ctx) { return (ctx && ctx->have_model) ? ctx->hm.G : AKUGPU_E_STATE; }
@@ -595,6 +649,7 @@ static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, in
   if (n_frames == 0 || S == 0) return;
   const bool logmode = tiny > 0;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
+  d_feats = adapt_feats(ctx, d_feats, feats_f64, n_frames);
   const size_t esz = (precision == AKUGPU_F64 && !logmode) ? 8 : 4;        // element size of the result
   const bool odev = is_device_ptr(out);
   uint8_t *d_out = (uint8_t *)out;
@@ -661,6 +716,7 @@ int akugpu_gmm_lna(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_
   require_model(ctx);
   if (n_frames < 0 || (n_frames && !feats)) throw Error(AKUGPU_E_ARG, "bad n_frames / NULL feats");
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * ctx->hm.D * (feats_f64 ? 8 : 4), ctx->d_feats);
+  d_feats = adapt_feats(ctx, d_feats, feats_f64, n_frames);
   score_to_lna(ctx, d_feats, feats_f64, n_frames, precision, lnabytes, normalize, out, nullptr);
   API_END
 }
@@ -684,7 +740,8 @@ int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_o
   const int16_t *d_pcm = (const int16_t *)to_device(ctx, pcm, (size_t)uo[n_utts] * 2, ctx->d_pcm);
   ctx->d_feats.reserve((size_t)fo[n_utts] * dim * (feats_f64 ? 8 : 4));
   { StageScope sc(ctx, 0); frontend_run_batch(ctx, d_pcm, uo, fo, ctx->d_feats.p, feats_f64); }
-  score_to_lna(ctx, ctx->d_feats.p, feats_f64, fo[n_utts], precision, lnabytes, normalize, out, checksum_out);
+  const void *d_feats = adapt_feats(ctx, ctx->d_feats.p, feats_f64, fo[n_utts]);
+  score_to_lna(ctx, d_feats, feats_f64, fo[n_utts], precision, lnabytes, normalize, out, checksum_out);
   API_END
 }
 

@@ -94,6 +94,13 @@ struct HostModel {
     n_clusters = 0; cluster_gauss.clear(); gauss_cluster.clear(); c_mean.clear(); c_cov.clear();
     use_clustering = false; eval_min_clusters = eval_min_gaussians = 1;
   }
+  // Global model-level constrained MLLR (ConstrainedMllr with unitmode UNIT_NO, aku/ModelModules.cc:172-236): every
+  // Gaussian is evaluated at A f + b and its likelihood multiplied by the module's "determinant" (see api.cu).  The
+  // factor is folded into the mixture weights (mix_w = mix_w_base * factor) so that every scorer image carries it.
+  bool cmllr_on = false;
+  std::vector<double> cmllr_W;      // [D x (D+1)] row-major as given: column 0 = b, columns 1..D = A
+  std::vector<double> mix_w_base;   // the normalised weights while cmllr_on
+  void clear_cmllr() { cmllr_on = false; cmllr_W.clear(); mix_w_base.clear(); }
 };
 
 // fp32 scorer image: tiles of 8 slots x 16 components, see gmm_kernels.cu.
@@ -238,6 +245,7 @@ struct akugpu_ctx {
 
   // scratch
   akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk, d_norm, d_clik, d_csel;
+  akugpu::DevBuf d_cmllr, d_adapt;     // double [D*D + D] (A row-major, then b); adapted features of the current call
   akugpu::DevBuf d_fe[8];
   std::vector<std::shared_ptr<akugpu::DevBuf>> fe_bufs;   // per-module output matrices (grow-only)
   akugpu::PinnedBuf h_in[2], h_out[2];

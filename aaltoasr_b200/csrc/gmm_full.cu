@@ -139,6 +139,21 @@ __global__ void floor_f32(float *__restrict__ x, int64_t n, float floor_at)
   if (i < n) x[i] = fmaxf(x[i], floor_at);          // NaN -> floor
 }
 
+// ConstrainedMllr::AdaptedFeatureVector::calculate_new_ada_vector (aku/ModelModules.hh:208-212): o = b + A f, in double.
+template <class T>
+__global__ void affine_rows(const T *__restrict__ in, int64_t F, int D, const double *__restrict__ Ab, T *__restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F * D) return;
+  const int64_t r = i / D;
+  const int c = (int)(i - r * D);
+  const T *x = in + r * D;
+  const double *a = Ab + (size_t)c * D;
+  double acc = 0;                      // row sum in index order, then + b: separate multiplies and adds like the CPU code
+  for (int j = 0; j < D; j++) acc = __dadd_rn(acc, __dmul_rn(a[j], (double)x[j]));
+  out[i] = (T)__dadd_rn(acc, Ab[(size_t)D * D + c]);
+}
+
 // Frames [f_begin, f_end) -> lin[state][ldF] (linear double likelihoods, floored) for pools with full Gaussians.
 void launch_gmm_full_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f_begin, int64_t f_end, double *lin,
                          int64_t ldF)
@@ -175,6 +190,15 @@ void launch_gmm_full_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int6
 void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float *out, double tiny)
 {
   lin_to_log_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(lin, n, tiny, out);
+  AKU_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+void launch_affine_rows(akugpu_ctx *ctx, const void *in, int is_f64, int64_t F, int D, const double *Ab, void *out)
+{
+  if (F <= 0) return;
+  const unsigned blocks = (unsigned)((F * D + 255) / 256);
+  if (is_f64) affine_rows<double><<<blocks, 256, 0, ctx->stream>>>((const double *)in, F, D, Ab, (double *)out);
+  else affine_rows<float><<<blocks, 256, 0, ctx->stream>>>((const float *)in, F, D, Ab, (float *)out);
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
 }

@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -229,8 +230,9 @@ private:
 //       }
 //     }
 // set_speaker() / set_utterance() push the stored parameters through FeatureModule::set_parameters
-// (akugpu_frontend_set_parameters).  `model <name>` entries (model-level transformations, aku/ModelModules.hh) select a
-// path outside this library's scope and are refused.
+// (akugpu_frontend_set_parameters).  A speaker's `model cmllr` entry (model-level constrained MLLR, aku/ModelModules.hh)
+// is applied through akugpu_model_set_cmllr when it is the global transform (unitmode UNIT_NO); regression-class
+// transforms are refused.  As in the reference, a speaker without the entry keeps the previous speaker's transform.
 class SpeakerConfig {
 public:
   explicit SpeakerConfig(Engine &e) : m_e(e), m_default_speaker_set(false), m_default_utterance_set(false) {}
@@ -275,8 +277,12 @@ public:
           if (parts[0] != "model" && parts[0] != "feature") throw fmt("SpeakerConfig: Unknown module namespace at line %d", lineno);
           ns = parts[0]; name = parts[1];
         }
-        if (ns == "model")
-          throw fmt("SpeakerConfig: error on line %d: ", lineno) + "model transformations are outside the accelerated scope (" + name + ")";
+        if (ns == "model") {
+          // ModelTransformer::get_new_module knows one module (aku/ModelModules.cc:12-18); it is loaded per speaker
+          if (name != "cmllr") throw fmt("SpeakerConfig: error on line %d: ", lineno) + "unknown model module requested: " + name;
+          if (!is_speaker)
+            throw fmt("SpeakerConfig: error on line %d: ", lineno) + "model modules are loaded per speaker; an utterance-level entry is not supported";
+        }
         // module parameters: a ModuleConfig block (aku/ModuleConfig.cc:166-203)
         if (!next(line)) throw std::string("SpeakerConfig: Failed reading module parameters around line ") + fmt("%d: ", lineno) + "unexpected end of module config file";
         if (line != "{") throw std::string("SpeakerConfig: Failed reading module parameters around line ") + fmt("%d: ", lineno) + "'{' expected in module config file: " + line;
@@ -286,7 +292,7 @@ public:
           if (line == "}") break;
           text += line + "\n";
         }
-        (*dst)[name] = text;
+        (*dst)[ns == "model" ? "model " + name : name] = text;
       }
     }
   }
@@ -324,8 +330,48 @@ public:
 private:
   typedef std::map<std::string, std::string> ModuleMap;     // module name -> `key value` lines
   void apply(const ModuleMap &m) {
-    for (ModuleMap::const_iterator it = m.begin(); it != m.end(); ++it)
-      check(m_e.ctx(), akugpu_frontend_set_parameters(m_e.ctx(), it->first.c_str(), it->second.c_str()));
+    for (ModuleMap::const_iterator it = m.begin(); it != m.end(); ++it) {
+      if (it->first == "model cmllr") apply_cmllr(it->second);
+      else check(m_e.ctx(), akugpu_frontend_set_parameters(m_e.ctx(), it->first.c_str(), it->second.c_str()));
+    }
+  }
+  // ConstrainedMllr::set_parameters (aku/ModelModules.cc:62-95) for the global transform (unitmode UNIT_NO): one `w1` of
+  // dim*(dim+1) numbers, row-major [dim x (dim+1)], column 0 = bias; no `w` entry = no transform.
+  void apply_cmllr(const std::string &text) {
+    const int dim = akugpu_model_dim(m_e.ctx());
+    if (dim <= 0) throw std::string("cmllr: a model must be loaded before the speaker configuration is applied");
+    std::map<std::string, std::vector<std::string> > params;
+    size_t pos = 0;
+    while (pos < text.size()) {
+      size_t e = text.find('\n', pos);
+      if (e == std::string::npos) e = text.size();
+      std::vector<std::string> f = split(text.substr(pos, e - pos), 0);
+      if (!f.empty()) params[f[0]] = std::vector<std::string>(f.begin() + 1, f.end());
+      pos = e + 1;
+    }
+    if (params.count("unitmode") && !params["unitmode"].empty()) {
+      const std::string &um = params["unitmode"][0];
+      if (um == "UNIT_GAUSSIAN" || um == "UNIT_MIX" || um == "UNIT_PHONE")
+        throw std::string("cmllr: regression-class transforms (unitmode ") + um + ") are not provided, only the global transform (UNIT_NO)";
+    }
+    const size_t n = (size_t)dim * (dim + 1);
+    std::map<std::vector<std::string>, std::vector<double> > found;
+    for (int i = 1;; i++) {
+      std::map<std::string, std::vector<std::string> >::const_iterator it = params.find(fmt("w%d", i));
+      if (it == params.end()) break;
+      const std::vector<std::string> &parts = it->second;
+      if (parts.size() < n) throw std::string("ERROR: not enough elements for matrix ") + fmt("w%d", i);
+      std::vector<double> w(n);
+      for (size_t k = 0; k < n; k++) {
+        const std::string &t = parts[parts.size() - n + k];
+        char *end = NULL;
+        w[k] = (double)(float)strtod(t.c_str(), &end);       // str::str2float returns through a float (aku/str.cc:261-282)
+        if (end == t.c_str() || *end) throw std::string("invalid value: ") + t;
+      }
+      found[std::vector<std::string>(parts.begin(), parts.end() - n)] = w;
+    }
+    if (found.size() > 1) throw std::string("ERROR: speaker can only contain one transform when UNIT_NO (global transform) is set");
+    check(m_e.ctx(), akugpu_model_set_cmllr(m_e.ctx(), found.empty() ? NULL : found.begin()->second.data()));
   }
   static std::string clean(const std::string &s) {
     size_t b = s.find_first_not_of(" \t\r\n"), e = s.find_last_not_of(" \t\r\n");

@@ -1,7 +1,8 @@
 // akugpu_phone_probs -- the reference tool aku/phone_probs.cc re-hosted on the GPU library.
 // Same flags (aku/phone_probs.cc:60-81) and the same per-utterance LNA files; utterances of a recipe
 // are batched into GPU calls (-C clusters / --eval-minc / --eval-ming included: the Gaussian-clustering
-// approximation; -S speakers: per-speaker / per-utterance parameters of feature modules, e.g. a CMLLR lin_transform).
+// approximation; -S speakers: per-speaker / per-utterance parameters of feature modules, e.g. a CMLLR lin_transform,
+// and a speaker's global model-level `model cmllr` transform).
 #include <errno.h>
 #include <math.h>
 #include <stdlib.h>
@@ -82,7 +83,8 @@ int main(int argc, char **argv)
                "  -a, --lnabyaudio       name LNA files by the audio file\n  -o, --output-dir=DIR   base path for LNAs\n"
                "  -R, --raw-input        raw audio input\n      --lnabytes=INT     2 (default) or 4\n"
                "  -n, --no-overwrite     skip existing non-empty LNA files\n  -N, --no-normalization\n"
-               "  -S, --speakers=FILE    speaker configuration file (feature-module parameters per speaker / utterance)\n"
+               "  -S, --speakers=FILE    speaker configuration file (feature-module parameters per speaker / utterance,\n"
+               "                         global `model cmllr` transforms per speaker)\n"
                "  -C, --clusters=FILE    Gaussian clustering (.gcl)\n      --eval-minc=FLOAT  minimum ratio of top clusters to evaluate (0)\n"
                "      --eval-ming=FLOAT  minimum ratio of Gaussians to evaluate (0.1)\n"
                "  -B, --batch=INT  -I, --bindex=INT   recipe batching\n  -i, --info=INT\n"

@@ -22,6 +22,8 @@ void launch_gmm_full_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int6
                          int64_t ldF);
 void launch_lin_to_log_f32(akugpu_ctx *ctx, const double *lin, int64_t n, float *out, double tiny = 0.0);
 void launch_floor_f32(akugpu_ctx *ctx, float *x, int64_t n, float floor_at);
+// out[f] = A in[f] + b for F feature rows (float or double, accumulated in double); Ab = A [D x D] row-major, then b [D]
+void launch_affine_rows(akugpu_ctx *ctx, const void *in, int is_f64, int64_t F, int D, const double *Ab, void *out);
 
 // gmm_tc.cu (tensor-core scorer, experimental)
 void model_pack_tc(akugpu_ctx *ctx);

@@ -134,6 +134,7 @@ void model_read_clustering(const std::string &gcl_path, HostModel &hm)
 void model_read_files(const std::string &gk_path, const std::string &mc_path, const std::string &ph_path, HostModel &hm)
 {
   hm.clear_clustering();
+  hm.clear_cmllr();
   // --- .mc ---
   std::vector<std::vector<int32_t>> mc_idx;
   std::vector<std::vector<double>> mc_w;

@@ -242,6 +242,18 @@ class AkuGpu:
     def use_clustering(self, on=True):
         self._ck(self._lib.akugpu_model_use_clustering(self._h, 1 if on else 0))
 
+    def model_set_cmllr(self, W):
+        """Global model-level CMLLR: W = [dim x (dim+1)] (column 0 = bias, the rest = A), None removes it
+        (ConstrainedMllr with unitmode UNIT_NO, aku/ModelModules.cc:172-236)."""
+        if W is None:
+            self._ck(self._lib.akugpu_model_set_cmllr(self._h, None))
+            return
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        D = self.model_dim
+        if W.shape != (D, D + 1):
+            raise ValueError("W must be [%d x %d]" % (D, D + 1))
+        self._ck(self._lib.akugpu_model_set_cmllr(self._h, _ptr(W)))
+
     @property
     def num_states(self):
         return self._lib.akugpu_model_num_states(self._h)

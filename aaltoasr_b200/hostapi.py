@@ -182,7 +182,12 @@ def parse_speaker_file(text):
             if ns not in ("model", "feature"):
                 raise AkuGpuError(-2, "SpeakerConfig: Unknown module namespace at line %d" % pos)
             if ns == "model":
-                raise AkuGpuError(-2, "SpeakerConfig: error on line %d: model transformations are outside the accelerated scope (%s)" % (pos, name))
+                # ModelTransformer::get_new_module knows one module (aku/ModelModules.cc:12-18)
+                if name != "cmllr":
+                    raise AkuGpuError(-2, "SpeakerConfig: error on line %d: unknown model module requested: %s" % (pos, name))
+                if f[0] == "utterance":
+                    raise AkuGpuError(-2, "SpeakerConfig: error on line %d: model modules are loaded per speaker "
+                                      "(aku/SpeakerConfig.cc:248-284); an utterance-level entry is not supported" % pos)
             if nxt() != "{":
                 raise AkuGpuError(-2, "SpeakerConfig: Failed reading module parameters around line %d: '{' expected in module config file" % pos)
             body = []
@@ -193,13 +198,47 @@ def parse_speaker_file(text):
                 if ln == "}":
                     break
                 body.append(ln)
-            mods[name] = "\n".join(body) + ("\n" if body else "")
+            mods[name if ns == "feature" else "model " + name] = "\n".join(body) + ("\n" if body else "")
     return out
 
 
+def parse_cmllr_parameters(text, dim):
+    """ConstrainedMllr::set_parameters (aku/ModelModules.cc:62-95) for the global transform: `unitmode UNIT_NO` and one
+    `w1` of dim*(dim+1) numbers, row-major [dim x (dim+1)], column 0 = bias.  Returns W or None (no transform given)."""
+    params = {}
+    for ln in text.splitlines():
+        f = ln.split()
+        if f:
+            params[f[0]] = f[1:]
+    um = params.get("unitmode", ["UNIT_NO"])
+    um = um[0] if um else "UNIT_NO"
+    if um in ("UNIT_GAUSSIAN", "UNIT_MIX", "UNIT_PHONE"):
+        raise AkuGpuError(-2, "cmllr: regression-class transforms (unitmode %s) are not provided, only the global "
+                          "transform (UNIT_NO)" % um)
+    n = dim * (dim + 1)
+    found = {}
+    i = 1
+    while "w%d" % i in params:
+        parts = params["w%d" % i]
+        if len(parts) < n:
+            raise AkuGpuError(-2, "ERROR: not enough elements for matrix w%d" % i)
+        vals = []
+        for t in parts[len(parts) - n:]:
+            try:
+                vals.append(float(np.float32(float(t))))      # str::str2float returns through a float (aku/str.cc:261-282)
+            except ValueError:
+                raise AkuGpuError(-2, "invalid value: " + t)
+        found[tuple(parts[:len(parts) - n])] = np.array(vals, dtype=np.float64).reshape(dim, dim + 1)
+        i += 1
+    if len(found) > 1:
+        raise AkuGpuError(-2, "ERROR: speaker can only contain one transform when UNIT_NO (global transform) is set")
+    return next(iter(found.values())) if found else None
+
+
 class SpeakerConfig:
-    """aku::SpeakerConfig for feature modules (aku/SpeakerConfig.cc:239-336): set_speaker / set_utterance push the stored
-    parameters through FeatureModule::set_parameters (akugpu_frontend_set_parameters)."""
+    """aku::SpeakerConfig (aku/SpeakerConfig.cc:239-336): set_speaker / set_utterance push the stored parameters of
+    feature modules through FeatureModule::set_parameters (akugpu_frontend_set_parameters) and a speaker's global
+    `model cmllr` transform through akugpu_model_set_cmllr (the model must be loaded first, as in the reference)."""
 
     def __init__(self, engine):
         self.engine = engine
@@ -224,7 +263,10 @@ class SpeakerConfig:
                 raise AkuGpuError(-2, "SpeakerConfig: Unknown %s %s, and default %s settings are missing." % (what, ident, what))
             mods = table["default"]
         for name in sorted(mods):
-            self.engine.frontend_set_parameters(name, mods[name])
+            if name == "model cmllr":     # model namespace: ModelTransformer (aku/SpeakerConfig.cc:248-284)
+                self.engine.model_set_cmllr(parse_cmllr_parameters(mods[name], self.engine.model_dim))
+            else:
+                self.engine.frontend_set_parameters(name, mods[name])
 
     def set_speaker(self, speaker_id):
         if self.cur_utterance:

@@ -148,6 +148,15 @@ int akugpu_model_set_clustering(akugpu_ctx *ctx, int n_clusters, const int32_t *
                                 const int32_t *cluster_index, int64_t n_pairs);
 int akugpu_model_set_clustering_min_evals(akugpu_ctx *ctx, double min_clusters, double min_gaussians);
 int akugpu_model_use_clustering(akugpu_ctx *ctx, int on);
+/* Model-level constrained MLLR with ONE global transform: the `model cmllr` entry of a speaker file with
+ * `unitmode UNIT_NO` (ConstrainedMllr::set_parameters / load_transform, aku/ModelModules.cc:62-95,172-236;
+ * phone_probs -S, aku/SpeakerConfig.cc:236-285).  W = [dim x (dim+1)] doubles, row-major, exactly the `w1` value:
+ * column 0 is the bias b, columns 1..dim the matrix A.  Every Gaussian (and cluster centre) is then evaluated at
+ * A f + b and its likelihood multiplied by the reference's factor |prod_i A(i,i)| (AdaptedGaussian, aku/ModelModules.hh:
+ * 161-171; its "determinant" is the product of A's own diagonal, aku/LinearAlgebra.cc:74-86 -- reproduced as it is).
+ * W = NULL removes the transform (ModelTransformer::reset_transforms); loading a model clears it.  Regression-class
+ * transforms (unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN, aku/RegClassTree.cc) are not provided. */
+int akugpu_model_set_cmllr(akugpu_ctx *ctx, const double *W);
 int akugpu_model_num_states(akugpu_ctx *ctx);   /* HmmSet::num_states()  */
 int akugpu_model_dim(akugpu_ctx *ctx);          /* HmmSet::dim()         */
 int akugpu_model_num_gaussians(akugpu_ctx *ctx);

@@ -695,7 +695,27 @@ def _diag_loglik(x, mu, prec, cst):
     return ll
 
 
-def state_likelihoods(model, feats, block=256, clustering=None):
+def cmllr_adapt(W, feats):
+    """Global model-level CMLLR (ConstrainedMllr with unitmode UNIT_NO, aku/ModelModules.cc:172-236): W is the `w1`
+    matrix [D x (D+1)], column 0 = b, columns 1..D = A (:208-211).  Returns (A f + b for every frame, factor):
+    AdaptedFeatureVector::calculate_new_ada_vector (aku/ModelModules.hh:208-212) copies b and adds A f; the factor that
+    AdaptedGaussian::compute_likelihood (:170) multiplies every likelihood with is
+    |LinearAlgebra::full_matrix_determinant(A)| (:141), and that routine multiplies the diagonal of A ITSELF, not of
+    its LU factors (aku/LinearAlgebra.cc:74-86) -- restated as it is."""
+    W = np.asarray(W, dtype=np.float64)
+    D = W.shape[0]
+    A, b = W[:, 1:], W[:, 0]
+    feats = np.asarray(feats, dtype=np.float64)
+    acc = np.zeros(feats.shape)
+    for j in range(D):                        # row sums in index order
+        acc += feats[:, j:j + 1] * A[None, :, j]
+    det = 1.0
+    for i in range(D):
+        det *= A[i, i]
+    return acc + b[None, :], abs(det)
+
+
+def state_likelihoods(model, feats, block=256, clustering=None, cmllr=None):
     """HmmSet::precompute_likelihoods (aku/HmmSet.cc:485-501) for every frame: linear state
     likelihoods floored at 1e-50.  Sums run in the reference's order (dims then components).
     clustering = dict(n_clusters, gauss, cluster, min_clusters, min_gaussians) (the two ratios of
@@ -704,8 +724,12 @@ def state_likelihoods(model, feats, block=256, clustering=None):
     std::priority_queue; ties here go to the lower index), members of the leading clusters evaluated exactly while
     (clusters < min) or (Gaussians < min), the rest take the centre's likelihood -- and, because
     PDFPool::compute_likelihood (:2637-2644) only trusts cached values > 0, a centre likelihood of 0 means the Gaussian is
-    evaluated exactly after all."""
+    evaluated exactly after all.
+    cmllr = W [D x (D+1)]: every Gaussian and cluster centre is wrapped in an AdaptedGaussian (see cmllr_adapt)."""
     feats = np.asarray(feats, dtype=np.float64)
+    factor = None
+    if cmllr is not None:
+        feats, factor = cmllr_adapt(cmllr, feats)
     mu = np.asarray(model["means"], dtype=np.float64)
     prec, cst = gaussian_params(mu, model["covs"])
     off, mg = model["mix_offsets"], model["mix_gauss"]
@@ -747,8 +771,12 @@ def state_likelihoods(model, feats, block=256, clustering=None):
                     dot += phi[:, l] * th[l]
                 ll[:, g] = (dot + nrm) + c
         lik = _exp(ll).astype(np.float64)   # DiagonalGaussian::compute_likelihood (:1036)
+        if factor is not None:
+            lik = lik * factor              # AdaptedGaussian::compute_likelihood
         if clustering is not None:
             clik = _exp(_diag_loglik(x, cm, cprec, ccst)).astype(np.float64)
+            if factor is not None:
+                clik = clik * factor
             for t in range(x.shape[0]):
                 order = sorted(range(C), key=lambda c: (-clik[t, c], c))
                 sel = np.zeros(C, dtype=bool)

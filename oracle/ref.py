@@ -44,6 +44,7 @@ def lib():
         _lib.ref_lna_read.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.c_int]
         _lib.ref_model_read_clustering.argtypes = [C.c_void_p, C.c_char_p]
         _lib.ref_model_set_clustering_min_evals.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        _lib.ref_model_set_speaker.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     return _lib
 
 
@@ -117,6 +118,12 @@ class Model:
 
     def set_clustering_min_evals(self, min_clusters, min_gaussians):
         if lib().ref_model_set_clustering_min_evals(self.h, float(min_clusters), float(min_gaussians)):
+            raise _err()
+
+    def set_speaker(self, spkc_path, speaker):
+        """aku::SpeakerConfig(gen, &model).set_speaker: loads the speaker's `model` transformations (the file is read
+        on the first call)."""
+        if lib().ref_model_set_speaker(self.h, spkc_path.encode(), speaker.encode()):
             raise _err()
 
     def gaussian_loglik(self, feats):

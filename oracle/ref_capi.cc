@@ -111,7 +111,13 @@ long ref_module_output(const char *cfg_path, const char *audio_path, const char 
   catch (std::exception &e) { return fail(e.what()); }
 }
 
-struct RefModel { HmmSet model; };
+struct RefModel {
+  HmmSet model;
+  FeatureGenerator gen;          // no configuration: only `model` entries of a speaker file are used through it
+  SpeakerConfig *spk;
+  RefModel() : spk(NULL) {}
+  ~RefModel() { delete spk; }    // resets the model transformations before the model goes
+};
 
 void *ref_model_open(const char *base)
 {
@@ -138,6 +144,22 @@ int ref_model_set_clustering_min_evals(void *h, double min_clusters, double min_
 {
   try { ((RefModel *)h)->model.set_clustering_min_evals(min_clusters, min_gaussians); return 0; }
   catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
+// aku::SpeakerConfig(gen, &model): read_speaker_file once, then set_speaker -- loads the speaker's model
+// transformations (`model cmllr` entries; ModelTransformer, aku/SpeakerConfig.cc:236-285) into the HmmSet.
+int ref_model_set_speaker(void *h, const char *spkc_path, const char *speaker)
+{
+  try {
+    RefModel *m = (RefModel *)h;
+    if (!m->spk) {
+      m->spk = new SpeakerConfig(m->gen, &m->model);
+      m->spk->read_speaker_file(io::Stream(spkc_path));
+    }
+    m->spk->set_speaker(speaker);
+    return 0;
+  } catch (std::string &s) { return fail(s); }
   catch (std::exception &e) { return fail(e.what()); }
 }
 

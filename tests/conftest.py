@@ -54,6 +54,15 @@ def ref_spk():
 
 
 @pytest.fixture(scope="session")
+def ref_cmllr():
+    d = load_golden("ref_cmllr")
+    d["spkc"] = str(d["spkc"])
+    d["gcl"] = str(d["gcl"])
+    d["speakers"] = [str(s) for s in d["speakers"]]
+    return d
+
+
+@pytest.fixture(scope="session")
 def ref_pre():
     return load_golden("ref_pre")
 

@@ -399,9 +399,92 @@ def modx_case(pcm, tmp):
     np.savez_compressed(os.path.join(HERE, "ref_modx.npz"), **out)
 
 
+def cmllr_case(pcm, model, tmp):
+    """Model-level CMLLR, global transform (`model cmllr`, unitmode UNIT_NO): state likelihoods of aku::HmmSet after
+    aku::SpeakerConfig::set_speaker (plain and with Gaussian clustering), and the LNA files of the literal phone_probs
+    -S for three speakers (the third falls back to the default speaker = no transform)."""
+    name = "ref_cmllr"
+    rng = np.random.default_rng(7010)
+    cfg_text = synth.mfcc39_config()
+    wav = os.path.join(tmp, name + ".wav"); cfg = os.path.join(tmp, name + ".cfg"); base = os.path.join(tmp, name)
+    formats.write_wav(wav, pcm, 16000)
+    open(cfg, "w").write(cfg_text)
+    formats.write_model(base, **model)
+    feats, _, _ = ref.features(cfg, wav)
+    D = 39
+    Ws = {}
+    sd = feats.std(axis=0)
+    def block(spk, flip):
+        A = np.eye(D) + 0.03 * rng.standard_normal((D, D)) * (sd[:, None] / sd[None, :])
+        if flip:
+            A[3, 3] = -A[3, 3]              # the likelihood factor is |prod diag(A)|
+        b = 0.15 * sd * rng.standard_normal(D)
+        W = np.concatenate([b[:, None], A], axis=1)
+        text = " ".join("%g" % v for v in W.reshape(-1))      # what the reference's own writer emits (ModelModules.cc:143)
+        Ws[spk] = np.array([float(t) for t in text.split()]).reshape(D, D + 1)
+        return "speaker %s\n{\n  model cmllr\n  {\n    unitmode UNIT_NO\n    w1 %s\n  }\n}\n\n" % (spk, text)
+    spkc = "speaker default\n{\n  model cmllr\n  {\n    unitmode UNIT_NO\n  }\n}\n\n" + block("alice", False) + block("bob", True)
+    spath = os.path.join(tmp, name + ".spkc")
+    open(spath, "w").write(spkc)
+    out = dict(cfg=cfg_text, spkc=spkc, pcm=pcm, feats=feats, W_alice=Ws["alice"], W_bob=Ws["bob"],
+               **{"model_" + k: v for k, v in model.items()})
+    M = ref.Model(base)
+    plain = M.state_likelihoods(feats)
+    for spk in ("alice", "bob", "carol", "alice"):        # back to alice: the transform is reloaded
+        M.set_speaker(spath, spk)
+        lik = M.state_likelihoods(feats)
+        if "lik_" + spk in out:
+            assert np.array_equal(out["lik_" + spk], lik)
+        out["lik_" + spk] = lik
+    M.close()
+    assert np.array_equal(out["lik_carol"], plain)
+    # with the Gaussian-clustering approximation on (cluster centres are wrapped too)
+    z = np.load(os.path.join(HERE, "ref_clust.npz"))
+    gpath = os.path.join(tmp, name + ".gcl")
+    open(gpath, "w").write(str(z["gcl"]))
+    out["gcl"] = str(z["gcl"])
+    M = ref.Model(base)
+    M.read_clustering(gpath)
+    M.set_clustering_min_evals(0.0, 0.25)
+    M.set_speaker(spath, "bob")
+    out["lik_clust_bob"] = M.state_likelihoods(feats)
+    M.close()
+    # the literal tool
+    cuts = [pcm, pcm[:16000], pcm[5000:22000]]
+    lines = []
+    for i, (c, spk) in enumerate(zip(cuts, ["alice", "bob", "carol"])):
+        w = os.path.join(tmp, "cm%d.wav" % i)
+        formats.write_wav(w, c, 16000)
+        lines.append("audio=%s lna=cm%d.lna speaker=%s" % (w, i, spk))
+    rec = os.path.join(tmp, name + ".recipe")
+    open(rec, "w").write("\n".join(lines) + "\n")
+    for tag, extra in (("", []), ("raw", ["-N"])):
+        for nb in (2, 4):
+            od = os.path.join(tmp, "cm_out%s%d" % (tag, nb))
+            os.makedirs(od, exist_ok=True)
+            ref.phone_probs(cfg, base, rec, od, nb, extra=["-S", spath] + extra)
+            for i in range(3):
+                out["lna%d%s_%d" % (nb, tag, i)] = np.frombuffer(open(os.path.join(od, "cm%d.lna" % i), "rb").read(), dtype=np.uint8)
+    out["cut_ranges"] = np.array([[0, pcm.size], [0, 16000], [5000, 22000]])
+    out["speakers"] = np.array(["alice", "bob", "carol"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "log-lik shift alice/bob vs plain (median):",
+          float(np.median(np.log(out["lik_alice"]) - np.log(plain))), float(np.median(np.log(out["lik_bob"]) - np.log(plain))),
+          "clustered differs from exact on %.1f%%" % (100 * (out["lik_clust_bob"] != out["lik_bob"]).mean()))
+
+
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
+    if sys.argv[1:] == ["cmllr"]:             # only the newest fixture (the others are unchanged)
+        with tempfile.TemporaryDirectory() as tmp:
+            pcm = synth.synth_audio(7001, 24000)
+            wav = os.path.join(tmp, "probe.wav"); cfg = os.path.join(tmp, "probe.cfg")
+            formats.write_wav(wav, pcm, 16000)
+            open(cfg, "w").write(synth.mfcc39_config())
+            feats, _, _ = ref.features(cfg, wav)
+            cmllr_case(pcm, small_model(feats, 7002), tmp)
+        return
     aku_tests()
     with tempfile.TemporaryDirectory() as tmp:
         pcm = synth.synth_audio(7001, 24000)
@@ -415,6 +498,7 @@ def main():
         pre_case(feats, tmp)
         vtln_case(pcm, tmp)
         modx_case(pcm, tmp)
+        cmllr_case(pcm, small_model(feats, 7002), tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
         run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 

@@ -67,6 +67,66 @@ def test_host_tools_build_and_fail_loudly_without_cuda(tool, tmp_path):
     assert r.returncode != 0 and b"no CPU fallback" in r.stderr
 
 
+def test_cpp_speaker_config_matches_python_mirror(tmp_path):
+    """akugpu::SpeakerConfig (the C++ adapter, csrc/host/akugpu.hh) compiled against stubs of the C-ABI calls it makes:
+    for the speaker files of the goldens it issues the same frontend_set_parameters / model_set_cmllr calls, with the
+    same values, as the Python mirror -- feature modules, `model cmllr` (floats through str2float), default speaker,
+    sticky parameters, and the reference's error messages."""
+    import subprocess
+    from conftest import load_golden
+    from aaltoasr_b200 import parse_speaker_file
+    from aaltoasr_b200.hostapi import parse_cmllr_parameters
+    exe = str(tmp_path / "spk_harness")
+    subprocess.run(["g++", "-O1", "-std=c++11", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "spk_harness.cc")],
+                   check=True, timeout=300)
+
+    def calls(spkc_text, dim, speakers):
+        path = str(tmp_path / "x.spkc")
+        open(path, "w").write(spkc_text)
+        r = subprocess.run([exe, path, str(dim)] + list(speakers), stdout=subprocess.PIPE, timeout=60)
+        return r.returncode, r.stdout.decode()
+
+    # model-level CMLLR fixture
+    g = load_golden("ref_cmllr")
+    spkc = str(g["spkc"])
+    rc, out = calls(spkc, 39, ["alice", "bob", "carol", "alice"])
+    assert rc == 0, out
+    conf = parse_speaker_file(spkc)["speaker"]
+    blocks = out.split("speaker ")[1:]
+    assert [b.split("\n", 1)[0] for b in blocks] == ["alice", "bob", "carol", "alice"]
+    for b in blocks:
+        spk, rest = b.split("\n", 1)
+        W = parse_cmllr_parameters(conf.get(spk, conf["default"])["model cmllr"], 39)
+        if W is None:
+            assert rest.strip() == "cmllr none"
+        else:
+            vals = np.array([float(t) for t in rest.split()[1:]])
+            assert rest.startswith("cmllr ") and np.array_equal(vals, W.reshape(-1))
+    # feature-module fixture: the parameter text reaches akugpu_frontend_set_parameters unchanged
+    g = load_golden("ref_spk")
+    spkc = str(g["spkc"])
+    rc, out = calls(spkc, 39, ["alice", "carol"])
+    assert rc == 0, out
+    conf = parse_speaker_file(spkc)["speaker"]
+    assert out == "speaker alice\nfeature cmllr\n%s.\nspeaker carol\nfeature cmllr\n%s.\n" % (conf["alice"]["cmllr"], conf["default"]["cmllr"])
+    # errors, worded like the reference
+    head = "speaker a\n{\n  model cmllr\n  {\n"
+    for body, msg in (("    unitmode UNIT_PHONE\n    w1 x 1 0 0 1 0 0\n", "regression-class"),
+                      ("    w1 1 2 3\n", "not enough elements for matrix w1"),
+                      ("    w1 0 1 zz 0 0 1\n", "invalid value: zz"),
+                      ("    w1 p 0 1 0 0 0 1\n    w2 q 0 1 0 0 0 1\n", "only contain one transform")):
+        rc, out = calls(head + body + "  }\n}\n", 2, ["a"])
+        assert rc == 1 and msg in out, (body, out)
+    rc, out = calls(head + "    w1 0.5 1 0 -0.5 0 1\n  }\n}\n", 2, ["a"])
+    assert rc == 0 and out == "speaker a\ncmllr 0.5 1 0 -0.5 0 1\n"
+    rc, out = calls("speaker a\n{\n  model mllr\n  {\n  }\n}\n", 2, ["a"])
+    assert rc == 1 and "SpeakerConfig: error on line 3: unknown model module requested: mllr" in out
+    rc, out = calls("utterance u\n{\n  model cmllr\n  {\n  }\n}\n", 2, [])
+    assert rc == 1 and "utterance-level" in out
+    rc, out = calls("speaker a\n{\n}\n", 2, ["b"])
+    assert rc == 1 and "Unknown speaker b, and default speaker settings are missing." in out
+
+
 def test_formats_roundtrip(tmp_path):
     pcm = synth.synth_audio(5, 4000)
     formats.write_wav(str(tmp_path / "a.wav"), pcm, 16000)

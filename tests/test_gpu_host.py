@@ -204,7 +204,58 @@ def test_cpp_tool_speaker_config(engine, ref_spk, tmp_path):
     open(spkc, "w").write("speaker default\n{\n  model mllr\n  {\n  }\n}\n")
     r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-S", spkc],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
-    assert r.returncode != 0 and b"outside the accelerated scope" in r.stderr
+    assert r.returncode != 0 and b"unknown model module requested: mllr" in r.stderr
+
+
+def test_cpp_tool_model_cmllr(engine, ref_cmllr, tmp_path):
+    """akugpu_phone_probs -S x.spkc with `model cmllr` entries (global model-level CMLLR, aku/ModelModules.cc): LNA files
+    for three speakers against the literal phone_probs -S output (2- and 4-byte, normalised and -N: the factor
+    |prod diag(A)| shows only without normalisation); the Python mirror writes the same bytes; regression-class unit modes
+    are refused."""
+    from aaltoasr_b200 import SpeakerConfig
+    g = ref_cmllr
+    cfg = str(tmp_path / "c.cfg"); open(cfg, "w").write(g["cfg"])
+    base = str(tmp_path / "model"); formats.write_model(base, **g["model"])
+    spkc = str(tmp_path / "x.spkc"); open(spkc, "w").write(g["spkc"])
+    lines = []
+    for i, spk in enumerate(g["speakers"]):
+        a, b = g["cut_ranges"][i]
+        w = str(tmp_path / ("cm%d.wav" % i))
+        formats.write_wav(w, g["pcm"][a:b], 16000)
+        lines.append("audio=%s lna=cm%d.lna speaker=%s" % (w, i, spk))
+    rec = str(tmp_path / "recipe"); open(rec, "w").write("\n".join(lines) + "\n")
+    engine.frontend_load_config(cfg)
+    engine.model_read(base)
+    sc = SpeakerConfig(engine)
+    sc.read_speaker_file(spkc)
+    for nb, tag, extra in ((2, "", []), (4, "", []), (2, "raw", ["-N"]), (4, "raw", ["-N"])):
+        out = tmp_path / ("o%d%s" % (nb, tag)); out.mkdir()
+        r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-S", spkc, "--precision=f64",
+                            "--lnabytes=%d" % nb] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()
+        for i, spk in enumerate(g["speakers"]):
+            got = np.frombuffer(open(str(out / ("cm%d.lna" % i)), "rb").read(), dtype=np.uint8)
+            want = g["lna%d%s_%d" % (nb, tag, i)]
+            assert got.size == want.size and bytes(got[:5]) == bytes(want[:5])
+            if nb == 2:      # end to end from WAV: codes within +-1 (the FFT rounds differently from KissFFT)
+                d = np.abs(got[5:].view(">u2").astype(int) - want[5:].view(">u2").astype(int))
+                assert d.max() <= 1 and (d != 0).mean() <= 0.03, (spk, tag, d.max(), (d != 0).mean())
+            else:
+                assert np.abs(got[5:].view("<f4") - want[5:].view("<f4")).max() <= 2e-3, (spk, tag)
+            sc.set_speaker(spk)                                  # the Python mirror drives the same library
+            a, b = g["cut_ranges"][i]
+            mine, _, _ = engine.phone_probs(g["pcm"][a:b], precision=F64, lnabytes=nb, normalize=not extra)
+            assert np.array_equal(mine.reshape(-1), got[5:])
+    engine.model_set_cmllr(None)
+    # alice and bob differ from the untransformed model, carol (default speaker: no `w`) does not
+    plain = [engine.phone_probs(g["pcm"][a:b], precision=F64, lnabytes=2)[0].reshape(-1) for a, b in g["cut_ranges"]]
+    assert not np.array_equal(plain[0], g["lna2_0"][5:]) and not np.array_equal(plain[1], g["lna2_1"][5:])
+    d = np.abs(plain[2].view(">u2").astype(int) - g["lna2_2"][5:].view(">u2").astype(int))
+    assert d.max() <= 1
+    open(spkc, "w").write(g["spkc"].replace("unitmode UNIT_NO", "unitmode UNIT_MIX"))
+    r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(tmp_path / "o2"), "-S", spkc],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode != 0 and b"regression-class" in r.stderr
 
 
 FEACAT = os.path.join(ROOT, "aaltoasr_b200", "akugpu_feacat")

@@ -346,6 +346,67 @@ def test_gaussian_clustering_parity(engine, ref_clust, tmp_path):
     assert (np.abs(engine.gmm_score(g["feats"], precision=F64) - g["lik_exact"]) / g["lik_exact"]).max() <= 4.5e-16
 
 
+def test_model_cmllr_parity(engine, ref_cmllr, tmp_path):
+    """Global model-level CMLLR (`model cmllr`, unitmode UNIT_NO; ConstrainedMllr / AdaptedGaussian, aku/ModelModules.cc):
+    state likelihoods within CUDA-exp ulps of the reference's HmmSet after SpeakerConfig::set_speaker -- two speakers
+    (one with a negative diagonal element: the factor is |prod diag(A)|), the default speaker (no transform), a
+    revisit, and with Gaussian clustering on; every throughput scorer holds its usual bar on the adapted model."""
+    from aaltoasr_b200 import SpeakerConfig
+    g = ref_cmllr
+    load_model(engine, g["model"])
+    spkc = str(tmp_path / "m.spkc")
+    open(spkc, "w").write(g["spkc"])
+    sc = SpeakerConfig(engine)
+    sc.read_speaker_file(spkc)
+    for spk in ("alice", "bob", "carol", "alice"):
+        sc.set_speaker(spk)
+        lik = engine.gmm_score(g["feats"], precision=F64)
+        want = g["lik_" + spk]
+        rel = np.abs(lik - want) / want
+        assert rel.max() <= 2e-15, (spk, rel.max())
+    assert not np.array_equal(g["lik_alice"], g["lik_carol"])
+    # direct call; every throughput scorer on the adapted model
+    engine.model_set_cmllr(g["W_bob"].astype(np.float32).astype(np.float64))
+    feats32 = g["feats"].astype(np.float32)
+    Wb = g["W_bob"].astype(np.float32).astype(np.float64)
+    # what the scorers are handed: float32 features, adapted in double, stored as float32 again
+    adapted, factor = oracle_np.cmllr_adapt(Wb, feats32.astype(np.float64))
+    want_ll = np.log(oracle_np.state_likelihoods(g["model"], adapted.astype(np.float32).astype(np.float64)) * factor)
+    assert np.abs(want_ll - np.log(g["lik_bob"])).max() <= 1e-5
+    for variant in (0, 1, 2, 3, 4):
+        engine.set_scorer_variant(variant)
+        try:
+            ll = engine.gmm_score(feats32, precision=F32).astype(np.float64)
+            err = np.abs(ll - want_ll) / (1 + np.abs(want_ll) / 40)
+            assert err.max() <= 3e-5, (variant, err.max())
+            raw4 = lna4(engine.gmm_lna(feats32, precision=F32, lnabytes=4, normalize=False)).reshape(ll.shape)
+            assert np.abs(raw4 - want_ll).max() <= 2e-4 < 0.07 < abs(np.log(factor)), variant    # the factor reaches the un-normalised stream
+        finally:
+            engine.set_scorer_variant(0)
+    lp = engine.gmm_logprobs(g["feats"], tiny=1e-30)
+    assert np.abs(lp - np.log(np.maximum(g["lik_bob"], 1e-30))).max() <= 2e-4
+    # Gaussian clustering on top (centres are wrapped as well)
+    gpath = str(tmp_path / "c.gcl")
+    open(gpath, "w").write(g["gcl"])
+    engine.read_clustering(gpath)
+    engine.set_clustering_min_evals(0.0, 0.25)
+    lik = engine.gmm_score(g["feats"], precision=F64)
+    assert (np.abs(lik - g["lik_clust_bob"]) / g["lik_clust_bob"]).max() <= 2e-15
+    engine.use_clustering(False)
+    # removal, errors, and a model load clears it
+    engine.model_set_cmllr(None)
+    assert (np.abs(engine.gmm_score(g["feats"], precision=F64) - g["lik_carol"]) / g["lik_carol"]).max() <= 4.5e-16
+    W = g["W_alice"].copy()
+    W[5, 6] = 0.0
+    with pytest.raises(AkuGpuError, match="diagonal of A"):
+        engine.model_set_cmllr(W)
+    with pytest.raises(ValueError):
+        engine.model_set_cmllr(np.zeros((39, 39)))
+    engine.model_set_cmllr(g["W_alice"])
+    load_model(engine, g["model"])
+    assert (np.abs(engine.gmm_score(g["feats"], precision=F64) - g["lik_carol"]) / g["lik_carol"]).max() <= 4.5e-16
+
+
 @pytest.mark.parametrize("D,max_mix", [(5, 3), (13, 16), (26, 40), (39, 64), (47, 9), (63, 20), (70, 12), (39, 90)])
 def test_throughput_scorers_other_shapes(engine, D, max_mix):
     """Every instantiation of the default scorer (K16 chunk counts 1-8 = feature dims up to 63, the streaming variant

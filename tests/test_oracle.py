@@ -109,6 +109,61 @@ def test_speaker_config_vs_reference(ref_spk):
     assert np.array_equal(g["lna2_2"], g["lna2_plain_2"]) and not np.array_equal(g["lna2_0"], g["lna2_plain_0"])
 
 
+def test_model_cmllr_bit_exact_vs_reference(ref_cmllr):
+    """phone_probs -S with `model cmllr` entries (global transform, unitmode UNIT_NO): the restatement of
+    ConstrainedMllr / AdaptedGaussian equals the reference's HmmSet after SpeakerConfig::set_speaker bit for bit, for a
+    plain speaker, one whose A has a negative diagonal element (the factor is |prod diag(A)|, not |det A|), the default
+    speaker (no transform) and with Gaussian clustering on (centres are wrapped too)."""
+    from aaltoasr_b200 import parse_speaker_file
+    from aaltoasr_b200.hostapi import parse_cmllr_parameters
+    g = ref_cmllr
+    conf = parse_speaker_file(g["spkc"])["speaker"]
+    assert sorted(conf) == ["alice", "bob", "default"] and list(conf["alice"]) == ["model cmllr"]
+    W = {spk: parse_cmllr_parameters(conf[spk]["model cmllr"], 39) for spk in conf}
+    # the values pass through str::str2float, i.e. a float (aku/str.cc:261-282)
+    assert W["default"] is None
+    assert np.array_equal(W["alice"], g["W_alice"].astype(np.float32)) and np.array_equal(W["bob"], g["W_bob"].astype(np.float32))
+    assert W["bob"][3, 4] < 0
+    A = W["bob"][:, 1:]
+    adapted, factor = oracle_np.cmllr_adapt(W["bob"], g["feats"])
+    assert factor == abs(np.prod(np.diag(A))) and abs(factor / abs(np.linalg.det(A)) - 1) > 1e-6     # not the determinant
+    assert np.allclose(adapted, g["feats"] @ A.T + W["bob"][:, 0], rtol=0, atol=1e-12)
+    for spk in ("alice", "bob"):
+        lik = oracle_np.state_likelihoods(g["model"], g["feats"], cmllr=W[spk])
+        assert np.array_equal(lik, g["lik_" + spk]), spk
+    plain = oracle_np.state_likelihoods(g["model"], g["feats"])
+    assert np.array_equal(plain, g["lik_carol"]) and not np.array_equal(plain, g["lik_alice"])
+    n, gi, ci = oracle_np.parse_clustering(g["gcl"])
+    cl = dict(n_clusters=n, gauss=gi, cluster=ci, min_clusters=0.0, min_gaussians=0.25)
+    assert np.array_equal(oracle_np.state_likelihoods(g["model"], g["feats"], clustering=cl, cmllr=W["bob"]), g["lik_clust_bob"])
+    # the literal tool: per-utterance files, speakers alice / bob / carol(default)
+    for i, spk in enumerate(g["speakers"]):
+        a, b = g["cut_ranges"][i]
+        feats = oracle_np.Pipeline(g["cfg"]).run(g["pcm"][a:b])
+        lik = oracle_np.state_likelihoods(g["model"], feats, cmllr=W.get(spk))
+        for nb, tag, norm in ((2, "", True), (4, "", True), (2, "raw", False), (4, "raw", False)):
+            want = g["lna%d%s_%d" % (nb, tag, i)]
+            rec, _ = oracle_np.lna_records(lik, nb, normalize=norm)
+            assert rec.size == want.size - 5
+            if nb == 2:          # codes within +-1: the oracle's FFT rounds differently from KissFFT
+                d = np.abs(rec.reshape(-1).view(">u2").astype(int) - want[5:].view(">u2").astype(int))
+                assert d.max() <= 1 and (d != 0).mean() <= 0.03, (spk, tag, d.max(), (d != 0).mean())
+            else:
+                got, ref_lp = rec.reshape(-1).view("<f4"), want[5:].view("<f4")
+                assert np.abs(got - ref_lp).max() <= 2e-3, (spk, tag)
+    # parameter errors of ConstrainedMllr::set_parameters
+    from aaltoasr_b200 import AkuGpuError
+    with pytest.raises(AkuGpuError, match="not enough elements"):
+        parse_cmllr_parameters("unitmode UNIT_NO\nw1 1 2 3\n", 39)
+    with pytest.raises(AkuGpuError, match="regression-class"):
+        parse_cmllr_parameters("unitmode UNIT_PHONE\nw1 a 1 0 0 1 0 0\n", 2)
+    with pytest.raises(AkuGpuError, match="invalid value"):
+        parse_cmllr_parameters("w1 0 1 x 0 0 1\n", 2)
+    assert np.array_equal(parse_cmllr_parameters("w1 0.5 1 0 -0.5 0 1\n", 2), [[0.5, 1, 0], [-0.5, 0, 1]])
+    with pytest.raises(AkuGpuError, match="unknown model module"):
+        parse_speaker_file("speaker a\n{\n  model mllr\n  {\n  }\n}\n")
+
+
 @pytest.mark.parametrize("variant", ["blin", "pwlin", "linear", "slapt"])
 def test_vtln_restatement_vs_reference(variant):
     """vtln module (warped bins, Lanczos-sinc / linear interpolation) with per-speaker parameters: the restatement
