@@ -15,11 +15,14 @@
 #ifndef AKUGPU_HOST_HH
 #define AKUGPU_HOST_HH
 
+#include <errno.h>
+#include <fcntl.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <algorithm>
 #include <map>
 #include <string>
@@ -45,15 +48,9 @@ private:
 };
 
 // RIFF/WAVE PCM16 mono or headerless RAW PCM16, what aku::AudioReader accepts (aku/AudioReader.cc:86-155).
-inline void read_audio(const std::string &path, int config_rate, bool force_raw, std::vector<int16_t> &pcm, int &rate)
+inline void parse_audio(const std::vector<unsigned char> &b, const std::string &path, int config_rate, bool force_raw,
+                        std::vector<int16_t> &pcm, int &rate)
 {
-  FILE *fp = path == "-" ? stdin : fopen(path.c_str(), "rb");    // "-" = standard input, like io::Stream (aku/io.cc:52-60)
-  if (!fp) throw std::string("AudioReader::open(): could not open file:") + path;
-  std::vector<unsigned char> b;
-  unsigned char buf[65536];
-  size_t k;
-  while ((k = fread(buf, 1, sizeof buf, fp)) > 0) b.insert(b.end(), buf, buf + k);
-  if (fp != stdin) fclose(fp);
   size_t off = 0, len = b.size();
   rate = config_rate;
   if (!force_raw && b.size() >= 12 && !memcmp(&b[0], "RIFF", 4) && !memcmp(&b[8], "WAVE", 4)) {
@@ -79,6 +76,17 @@ inline void read_audio(const std::string &path, int config_rate, bool force_raw,
   }
   pcm.resize(len / 2);
   for (size_t i = 0; i < pcm.size(); i++) pcm[i] = (int16_t)(b[off + 2 * i] | (b[off + 2 * i + 1] << 8));
+}
+inline void read_audio(const std::string &path, int config_rate, bool force_raw, std::vector<int16_t> &pcm, int &rate)
+{
+  FILE *fp = path == "-" ? stdin : fopen(path.c_str(), "rb");    // "-" = standard input, like io::Stream (aku/io.cc:52-60)
+  if (!fp) throw std::string("AudioReader::open(): could not open file:") + path;
+  std::vector<unsigned char> b;
+  unsigned char buf[65536];
+  size_t k;
+  while ((k = fread(buf, 1, sizeof buf, fp)) > 0) b.insert(b.end(), buf, buf + k);
+  if (fp != stdin) fclose(fp);
+  parse_audio(b, path, config_rate, force_raw, pcm, rate);
 }
 
 class FeatureGenerator {
@@ -397,6 +405,83 @@ private:
   ModuleMap m_default_speaker, m_default_utterance;
   bool m_default_speaker_set, m_default_utterance_set;
   std::string m_cur_speaker, m_cur_utterance;
+};
+
+// aku::PPToolbox (aku/PhoneProbsToolbox.hh:13-31, the class behind aku/swig/PPToolbox.i): one utterance in, one LNA
+// stream out (5-byte header, 2-byte normalised codes -- lnabytes is fixed to 2 there, aku/PhoneProbsToolbox.cc:57,138),
+// whole utterance per GPU call instead of the per-frame loop (:83-131,156-207).
+class PPToolbox {
+public:
+  explicit PPToolbox(int device = 0, int precision = AKUGPU_F32) : m_e(device), m_gen(m_e), m_model(m_e), m_prec(precision) {}
+  void read_models(const std::string &base) { m_model.read_all(base); }
+  void read_configuration(const std::string &cfgname) { m_gen.load_configuration(cfgname); }
+  void set_clustering(const std::string &clfile_name, double eval_minc, double eval_ming) {
+    m_model.read_clustering(clfile_name);
+    m_model.set_clustering_min_evals(eval_minc, eval_ming);
+  }
+  // Audio from an open descriptor (read to its end; raw_flag: headerless PCM16), LNA stream to out_fd.  Neither
+  // descriptor is closed.
+  void generate_to_fd(int in_fd, int out_fd, bool raw_flag) {
+    check_dims();
+    std::vector<unsigned char> b;
+    unsigned char buf[65536];
+    for (;;) {
+      ssize_t k = read(in_fd, buf, sizeof buf);
+      if (k < 0) { if (errno == EINTR) continue; throw std::string("could not read fd: ") + strerror(errno); }
+      if (k == 0) break;
+      b.insert(b.end(), buf, buf + k);
+    }
+    std::vector<int16_t> pcm;
+    int rate = 0;
+    parse_audio(b, "<fd>", m_gen.sample_rate(), raw_flag, pcm, rate);
+    emit(pcm, rate, out_fd);
+  }
+  void generate_from_file_to_fd(const std::string &input_name, int out_fd, bool /*raw_flag: unused by the reference too*/) {
+    check_dims();
+    std::vector<int16_t> pcm;
+    int rate = 0;
+    read_audio(input_name, m_gen.sample_rate(), false, pcm, rate);
+    emit(pcm, rate, out_fd);
+  }
+  void generate(const std::string &input_name, const std::string &output_name, bool raw_flag) {
+    int out = open(output_name.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0664);
+    if (out < 0) throw std::string("could not open ") + output_name + ": " + strerror(errno);
+    try { generate_from_file_to_fd(input_name, out, raw_flag); }
+    catch (...) { close(out); throw; }
+    close(out);
+  }
+private:
+  void check_dims() {
+    if (m_model.dim() != m_gen.dim()) {     // aku/PhoneProbsToolbox.cc:65-70
+      char msg[256];
+      snprintf(msg, sizeof msg, "Gaussian dimension is %d but feature dimension is %d.", m_model.dim(), m_gen.dim());
+      throw std::string(msg);
+    }
+  }
+  void emit(const std::vector<int16_t> &pcm, int rate, int out_fd) {
+    if (rate != m_gen.sample_rate()) {      // aku/FeatureModules.cc:254-261
+      char msg[256];
+      snprintf(msg, sizeof msg, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree.", rate, m_gen.sample_rate());
+      throw std::string(msg);
+    }
+    const int S = m_model.num_states();
+    int64_t uo[2] = {0, (int64_t)pcm.size()}, fo[2] = {0, 0};
+    check(m_e.ctx(), akugpu_features(m_e.ctx(), NULL, uo, 1, NULL, 0, fo));     // frame count only
+    std::vector<uint8_t> rec(5 + (size_t)fo[1] * S * 2);
+    check(m_e.ctx(), akugpu_lna_header(S, 2, rec.data()));
+    if (fo[1] > 0)
+      check(m_e.ctx(), akugpu_phone_probs(m_e.ctx(), pcm.data(), uo, 1, m_prec, 2, 1, rec.data() + 5, fo, NULL));
+    size_t done = 0;
+    while (done < rec.size()) {
+      ssize_t k = write(out_fd, rec.data() + done, rec.size() - done);
+      if (k < 0) { if (errno == EINTR) continue; throw std::string("Write error"); }
+      done += (size_t)k;
+    }
+  }
+  Engine m_e;
+  FeatureGenerator m_gen;
+  HmmSet m_model;
+  int m_prec;
 };
 
 }  // namespace akugpu

@@ -67,6 +67,28 @@ def test_host_tools_build_and_fail_loudly_without_cuda(tool, tmp_path):
     assert r.returncode != 0 and b"no CPU fallback" in r.stderr
 
 
+def build_pptoolbox_driver(tmp_path):
+    """g++ build of tests/cpp/pptoolbox_main.cc (akugpu::PPToolbox, header-only) against the in-tree libakugpu.so."""
+    import subprocess
+    exe = str(tmp_path / "pptoolbox_main")
+    libdir = os.path.join(ROOT, "aaltoasr_b200")
+    subprocess.run(["g++", "-O1", "-std=c++11", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "pptoolbox_main.cc"),
+                    "-L" + libdir, "-lakugpu", "-Wl,-rpath," + libdir], check=True, timeout=300)
+    return exe
+
+
+def test_cpp_pptoolbox_builds_and_fails_loudly_without_cuda(tmp_path):
+    """akugpu::PPToolbox (C++ mirror of aku::PPToolbox, aku/PhoneProbsToolbox.hh) compiles warning-free against the C ABI
+    and reports the missing device instead of falling back."""
+    import subprocess
+    import torch
+    exe = build_pptoolbox_driver(tmp_path)
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([exe, "x.cfg", "model", "in.wav", str(tmp_path / "out.lna")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode == 1 and b"no CPU fallback" in r.stderr and not os.path.exists(str(tmp_path / "out.lna"))
+
+
 def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     """akugpu::SpeakerConfig (the C++ adapter, csrc/host/akugpu.hh) compiled against stubs of the C-ABI calls it makes:
     for the speaker files of the goldens it issues the same frontend_set_parameters / model_set_cmllr calls, with the

@@ -258,6 +258,58 @@ def test_cpp_tool_model_cmllr(engine, ref_cmllr, tmp_path):
     assert r.returncode != 0 and b"regression-class" in r.stderr
 
 
+def test_cpp_pptoolbox_mirror(engine, ref_small, ref_clust, tmp_path):
+    """akugpu::PPToolbox (C++, aku/PhoneProbsToolbox.hh:13-31 / aku/swig/PPToolbox.i:59-66): generate() from a file,
+    generate_to_fd() from open descriptors (WAV and headerless raw PCM), set_clustering(); the LNA stream (5-byte
+    header + 2-byte normalised codes) is byte-identical to the library's own phone_probs output and within +-1 code of
+    the literal reference tool's file."""
+    from test_abi import build_pptoolbox_driver
+    exe = build_pptoolbox_driver(tmp_path)
+    g = ref_small
+    cfg, base, rec, cuts = write_case(tmp_path, g, n=1)
+    wav = str(tmp_path / "utt0.wav")
+    raw = str(tmp_path / "utt0.raw")
+    g["pcm"].astype("<i2").tofile(raw)
+    engine.frontend_load_config(cfg)
+    engine.model_read(base)
+    S = engine.num_states
+    run = lambda *a: subprocess.run([exe] + list(a), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    for prec_name, prec in (("f32", F32), ("f64", F64)):
+        want, _, _ = engine.phone_probs(g["pcm"], precision=prec, lnabytes=2)
+        for mode, src in (("file", wav), ("fd", wav), ("rawfd", raw)):
+            out = str(tmp_path / ("o_%s_%s.lna" % (prec_name, mode)))
+            r = run(cfg, base, src, out, prec_name, mode)
+            assert r.returncode == 0, r.stderr.decode()
+            got = np.frombuffer(open(out, "rb").read(), dtype=np.uint8)
+            assert bytes(got[:5]) == S.to_bytes(4, "big") + b"\x02" == bytes(g["lna2"][:5])
+            assert np.array_equal(got[5:], want.reshape(-1)), (prec_name, mode)
+        d = np.abs(got[5:].view(">u2").astype(int) - g["lna2"][5:].view(">u2").astype(int))
+        assert d.max() <= 1 and (d != 0).mean() <= 0.03, (prec_name, d.max(), (d != 0).mean())
+    # set_clustering: the approximation of phone_probs -C x.gcl --eval-ming=0.25 (fixture of the literal tool)
+    gc = ref_clust
+    gcl = str(tmp_path / "c.gcl")
+    open(gcl, "w").write(gc["gcl"])
+    out = str(tmp_path / "o_clust.lna")
+    r = run(cfg, base, wav, out, "f32", "file", gcl, "0.0", "0.25")
+    assert r.returncode == 0, r.stderr.decode()
+    got = np.frombuffer(open(out, "rb").read(), dtype=np.uint8)
+    d = np.abs(got[5:].view(">u2").astype(int) - gc["lna2"][5:].view(">u2").astype(int))
+    assert got.size == gc["lna2"].size and d.max() <= 1 and (d != 0).mean() <= 0.03
+    engine.read_clustering(gcl)
+    engine.set_clustering_min_evals(0.0, 0.25)
+    want, _, _ = engine.phone_probs(g["pcm"], precision=F32, lnabytes=2)
+    engine.use_clustering(False)
+    assert np.array_equal(got[5:], want.reshape(-1))
+    # errors: a model of another dimension, a missing input
+    bad = str(tmp_path / "bad")
+    m = g["model"]
+    formats.write_model(bad, m["mix_offsets"], m["mix_gauss"], m["mix_weight"], m["means"][:, :13], m["covs"][:, :13])
+    r = run(cfg, bad, wav, out)
+    assert r.returncode == 1 and b"Gaussian dimension is 13 but feature dimension is 39." in r.stderr
+    r = run(cfg, base, str(tmp_path / "missing.wav"), out)
+    assert r.returncode == 1 and b"could not open file" in r.stderr
+
+
 FEACAT = os.path.join(ROOT, "aaltoasr_b200", "akugpu_feacat")
 
 
