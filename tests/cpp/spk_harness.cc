@@ -1,5 +1,5 @@
 // CPU harness for the header-only C++ adapters (aaltoasr_b200/csrc/host/akugpu.hh): akugpu::SpeakerConfig driven
-// against STUBS of the few C-ABI calls it makes, which print what they receive.  tests/test_abi.py compiles this with
+// against STUBS of the few C-ABI calls it makes, which print what they receive; and akugpu::read_audio (mode `audio`).  tests/test_abi.py compiles this with
 // g++ and compares the calls with the Python mirror's parse of the same speaker file.  No GPU, no libakugpu.so.
 #include "../../aaltoasr_b200/csrc/host/akugpu.hh"
 
@@ -28,6 +28,20 @@ int akugpu_model_set_cmllr(akugpu_ctx *, const double *W)
 int main(int argc, char **argv)
 {
   if (argc < 3) return 2;
+  if (std::string(argv[1]) == "audio") {       // spk_harness audio PATH CONFIG_RATE RAW(0|1): akugpu::read_audio
+    try {
+      std::vector<int16_t> pcm;
+      int rate = 0;
+      akugpu::read_audio(argv[2], atoi(argv[3]), atoi(argv[4]) != 0, pcm, rate);
+      long long sum = 0;
+      for (size_t i = 0; i < pcm.size(); i++) sum += (long long)pcm[i] * (long long)(i % 97 + 1);
+      printf("%zu %d %lld\n", pcm.size(), rate, sum);
+    } catch (std::string &s) {
+      printf("exception: %s\n", s.c_str());
+      return 1;
+    }
+    return 0;
+  }
   g_dim = atoi(argv[2]);
   try {
     akugpu::Engine eng(0);

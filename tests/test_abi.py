@@ -93,7 +93,7 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     """akugpu::SpeakerConfig (the C++ adapter, csrc/host/akugpu.hh) compiled against stubs of the C-ABI calls it makes:
     for the speaker files of the goldens it issues the same frontend_set_parameters / model_set_cmllr calls, with the
     same values, as the Python mirror -- feature modules, `model cmllr` (floats through str2float), default speaker,
-    sticky parameters, and the reference's error messages."""
+    sticky parameters, and the reference's error messages.  Also akugpu::read_audio (WAV / raw PCM16, as AudioReader)."""
     import subprocess
     from conftest import load_golden
     from aaltoasr_b200 import parse_speaker_file
@@ -107,6 +107,28 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
         open(path, "w").write(spkc_text)
         r = subprocess.run([exe, path, str(dim)] + list(speakers), stdout=subprocess.PIPE, timeout=60)
         return r.returncode, r.stdout.decode()
+
+    # akugpu::read_audio: RIFF/WAVE PCM16 (with an odd-sized extra chunk before `data`), headerless raw, errors
+    pcm = synth.synth_audio(11, 4001)
+    w = str(tmp_path / "a.wav")
+    formats.write_wav(w, pcm, 8000)
+    blob = open(w, "rb").read()
+    i = blob.index(b"data")
+    extra = blob[:i] + b"LIST" + (3).to_bytes(4, "little") + b"abc\x00" + blob[i:]
+    extra = extra[:4] + (len(extra) - 8).to_bytes(4, "little") + extra[8:]
+    open(str(tmp_path / "b.wav"), "wb").write(extra)
+    pcm.astype("<i2").tofile(str(tmp_path / "a.raw"))
+    want_sum = int((pcm.astype(np.int64) * (np.arange(pcm.size) % 97 + 1)).sum())
+    for path, cfg_rate, raw, rate in (("a.wav", 16000, 0, 8000), ("b.wav", 16000, 0, 8000), ("a.raw", 16000, 1, 16000)):
+        r = subprocess.run([exe, "audio", str(tmp_path / path), str(cfg_rate), str(raw)], stdout=subprocess.PIPE, timeout=60)
+        assert r.returncode == 0 and r.stdout.decode().split() == [str(pcm.size), str(rate), str(want_sum)], (path, r.stdout)
+    r = subprocess.run([exe, "audio", str(tmp_path / "nope.wav"), "16000", "0"], stdout=subprocess.PIPE, timeout=60)
+    assert r.returncode == 1 and b"could not open file" in r.stdout
+    stereo = bytearray(blob)
+    stereo[22] = 2
+    open(str(tmp_path / "s.wav"), "wb").write(bytes(stereo))
+    r = subprocess.run([exe, "audio", str(tmp_path / "s.wav"), "16000", "0"], stdout=subprocess.PIPE, timeout=60)
+    assert r.returncode == 1 and b"multiple channels not supported" in r.stdout
 
     # model-level CMLLR fixture
     g = load_golden("ref_cmllr")
