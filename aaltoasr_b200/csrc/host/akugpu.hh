@@ -202,13 +202,7 @@ public:
   // Scores every frame of an utterance at once; the per-frame calls below index into the result.
   void set_utterance(const double *feats, int64_t n_frames) {
     m_lik.resize((size_t)n_frames * m_S);
-    if (m_prec == AKUGPU_F64) {
-      check(m_e.ctx(), akugpu_gmm_score(m_e.ctx(), feats, 1, n_frames, AKUGPU_F64, m_lik.data()));
-    } else {
-      std::vector<float> ll((size_t)n_frames * m_S);
-      check(m_e.ctx(), akugpu_gmm_score(m_e.ctx(), feats, 1, n_frames, AKUGPU_F32, ll.data()));
-      for (size_t i = 0; i < ll.size(); i++) { double v = exp((double)ll[i]); m_lik[i] = v < 1e-50 ? 1e-50 : v; }
-    }
+    score(feats, n_frames, m_lik.data());
     m_cur = -1;
   }
   // The in-process decoder feed of decoder/decode-stream.cc:191-207: (float) log(max(likelihood, tiny)) for every state
@@ -217,15 +211,38 @@ public:
     out.resize((size_t)n_frames * m_S);
     check(m_e.ctx(), akugpu_gmm_logprobs(m_e.ctx(), feats, 1, n_frames, m_prec, tiny, out.data()));
   }
-  void reset_cache() { m_cur = -1; }
+  void reset_cache() { m_cur = -1; m_one_valid = false; }
   void precompute_likelihoods(int frame) { m_cur = frame; }
   // Linear likelihood floored at 1e-50, as aku::HmmSet::state_likelihood returns (aku/HmmSet.cc:470-481).
   double state_likelihood(int state) const { return m_lik[(size_t)m_cur * m_S + state]; }
   double state_likelihood(int state, int frame) const { return m_lik[(size_t)frame * m_S + state]; }
+  // The reference's own signatures for callers that hand in one feature vector at a time (aku/HmmSet.hh:309-321):
+  // precompute_likelihoods(f) scores every state for `fea` in one GPU call (F = 1); state_likelihood(s, f) returns the
+  // cached value and, like pdf_likelihood (aku/HmmSet.cc:470-481), fills the cache first when reset_cache() emptied it
+  // -- the cache is keyed by reset_cache(), not by the vector, exactly as there.
+  void precompute_likelihoods(const double *fea) {
+    m_one.resize(m_S);
+    score(fea, 1, m_one.data());
+    m_one_valid = true;
+  }
+  double state_likelihood(int state, const double *fea) {
+    if (!m_one_valid) precompute_likelihoods(fea);
+    return m_one[state];
+  }
 private:
+  void score(const double *feats, int64_t n_frames, double *lik) {
+    if (m_prec == AKUGPU_F64) {
+      check(m_e.ctx(), akugpu_gmm_score(m_e.ctx(), feats, 1, n_frames, AKUGPU_F64, lik));
+    } else {
+      std::vector<float> ll((size_t)n_frames * m_S);
+      check(m_e.ctx(), akugpu_gmm_score(m_e.ctx(), feats, 1, n_frames, AKUGPU_F32, ll.data()));
+      for (size_t i = 0; i < ll.size(); i++) { double v = exp((double)ll[i]); lik[i] = v < 1e-50 ? 1e-50 : v; }
+    }
+  }
   Engine &m_e;
   int m_prec, m_S, m_cur;
-  std::vector<double> m_lik;
+  bool m_one_valid = false;
+  std::vector<double> m_lik, m_one;
 };
 
 // Speaker / utterance adaptation parameters for FEATURE modules (aku::SpeakerConfig, aku/SpeakerConfig.cc:20-381;

@@ -15,6 +15,25 @@ int akugpu_frontend_set_parameters(akugpu_ctx *, const char *module, const char 
   printf("feature %s\n%s.\n", module, text);
   return 0;
 }
+// scoring stub: S = 3 states; linear likelihood (F64) or log-likelihood (F32) of state s for a frame = f(frame sum, s)
+static int g_score_calls = 0;
+int akugpu_model_num_states(akugpu_ctx *) { return 3; }
+int akugpu_model_read(akugpu_ctx *, const char *) { return 0; }
+int akugpu_gmm_score(akugpu_ctx *, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)
+{
+  g_score_calls++;
+  if (!feats_f64) return -1;
+  const double *x = (const double *)feats;
+  for (int64_t f = 0; f < n_frames; f++) {
+    const double sum = x[f * g_dim] + x[f * g_dim + 1];
+    for (int s = 0; s < 3; s++) {
+      const double lik = (s == 2 && sum > 100) ? 1e-60 : (sum + 1) * (s + 1);
+      if (precision == AKUGPU_F64) ((double *)out)[f * 3 + s] = lik < 1e-50 ? 1e-50 : lik;
+      else ((float *)out)[f * 3 + s] = (float)log(lik);
+    }
+  }
+  return 0;
+}
 int akugpu_model_set_cmllr(akugpu_ctx *, const double *W)
 {
   if (!W) { printf("cmllr none\n"); return 0; }
@@ -40,6 +59,31 @@ int main(int argc, char **argv)
       printf("exception: %s\n", s.c_str());
       return 1;
     }
+    return 0;
+  }
+  if (std::string(argv[1]) == "hmm") {         // spk_harness hmm f32|f64: the akugpu::HmmSet cache protocol
+    g_dim = 2;
+    akugpu::Engine eng(0);
+    akugpu::HmmSet model(eng, std::string(argv[2]) == "f64" ? AKUGPU_F64 : AKUGPU_F32);
+    model.read_all("stub");
+    const double a[2] = {1, 2}, b[2] = {5, 6}, c[2] = {100, 1}, utt[6] = {1, 2, 5, 6, 100, 1};
+    double v0, v1;                                 // (values first: argument evaluation order is unspecified)
+    model.reset_cache();
+    model.precompute_likelihoods(a);
+    v0 = model.state_likelihood(0, a); v1 = model.state_likelihood(2, a);
+    printf("%.6g %.6g calls=%d\n", v0, v1, g_score_calls);
+    v0 = model.state_likelihood(1, b);             // cache keyed by reset_cache(), not by the vector
+    printf("%.6g calls=%d\n", v0, g_score_calls);
+    model.reset_cache();
+    v0 = model.state_likelihood(1, b); v1 = model.state_likelihood(0, b);     // filled on demand
+    printf("%.6g %.6g calls=%d\n", v0, v1, g_score_calls);
+    model.reset_cache();
+    v0 = model.state_likelihood(2, c);             // floored at 1e-50
+    printf("%.6g calls=%d\n", v0, g_score_calls);
+    model.set_utterance(utt, 3);
+    model.precompute_likelihoods(1);
+    v0 = model.state_likelihood(2); v1 = model.state_likelihood(0, 2);
+    printf("%.6g %.6g calls=%d\n", v0, v1, g_score_calls);
     return 0;
   }
   g_dim = atoi(argv[2]);

@@ -130,6 +130,12 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     r = subprocess.run([exe, "audio", str(tmp_path / "s.wav"), "16000", "0"], stdout=subprocess.PIPE, timeout=60)
     assert r.returncode == 1 and b"multiple channels not supported" in r.stdout
 
+    # akugpu::HmmSet: the reference's per-vector signatures over one GPU call per reset_cache() (stubbed scorer, 3 states)
+    for prec in ("f64", "f32"):
+        r = subprocess.run([exe, "hmm", prec], stdout=subprocess.PIPE, timeout=60)
+        assert r.returncode == 0
+        assert r.stdout.decode().splitlines() == ["4 12 calls=1", "8 calls=1", "24 12 calls=2", "1e-50 calls=3", "36 102 calls=4"], (prec, r.stdout)
+
     # model-level CMLLR fixture
     g = load_golden("ref_cmllr")
     spkc = str(g["spkc"])
