@@ -280,3 +280,28 @@ def test_live_reference_matches_golden(ref_small, tmp_path):
     M = ref.Model(str(tmp_path / "m"))
     assert np.array_equal(M.state_likelihoods(feats), ref_small["lik"])
     M.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("sr,ww", [(8000, None), (16000, 512), (32000, None), (16000, 2048), (48000, None), (16000, 400),
+                                   (24000, None), (16000, 1536), (12000, None)])
+def test_oracle_feature_sweep_vs_live_reference(sr, ww, tmp_path):
+    """BASELINE config 3 (other sample rates / window widths): the restatement against the compiled reference on the very
+    configurations tests/test_gpu_parity.py::test_features_sweep_vs_oracle holds the GPU front-end to -- frame counts
+    identical, features within the 1e-5 of the 16 kHz fixtures (KissFFT float vs the oracle's FFT)."""
+    from aaltoasr_b200 import formats, synth
+    cfg_text = synth.mfcc39_config(sr)
+    if ww:
+        cfg_text = cfg_text.replace("sample_rate %d" % sr, "sample_rate %d\n  window_width %d" % (sr, ww))
+    pcm = synth.synth_audio(3000 + sr // 1000, sr // 2, sr)
+    wav, cfg = str(tmp_path / "a.wav"), str(tmp_path / "a.cfg")
+    formats.write_wav(wav, pcm, sr)
+    open(cfg, "w").write(cfg_text)
+    want, last, rate = ref.features(cfg, wav)
+    P = oracle_np.Pipeline(cfg_text)
+    assert P.num_frames(pcm.size) == want.shape[0] == last + 1
+    got = P.run(pcm)
+    assert np.abs(got - want).max() <= 1e-5, np.abs(got - want).max()
+    ext = P.run(pcm, -4, want.shape[0] + 5)                  # border frames on both sides
+    want_ext, _, _ = ref.features(cfg, wav, -4, want.shape[0] + 5)
+    assert np.abs(ext - want_ext).max() <= 1e-5
