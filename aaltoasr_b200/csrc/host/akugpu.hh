@@ -424,6 +424,76 @@ private:
   std::string m_cur_speaker, m_cur_utterance;
 };
 
+// aku::Recipe (aku/Recipe.hh:15-118, aku/Recipe.cc:24-147): one utterance per line of key=value fields.  A key missing on
+// a later line keeps the value of the line before (the reference never clears its map), also across batch borders;
+// with num_batches > 1 the non-empty, non-comment lines are cut into contiguous parts, the first (lines % batches) of
+// them one line longer (cluster_speakers = false, as phone_probs calls it, aku/phone_probs.cc:137-139).
+class Recipe {
+public:
+  struct Info {
+    std::string audio_path, lna_path, speaker_id, utterance_id;
+    double start_time, end_time;
+    Info() : start_time(0), end_time(0) {}
+    bool operator<(const Info &i) const { return speaker_id < i.speaker_id; }      // aku/Recipe.hh:89-91
+  };
+  std::vector<Info> infos;
+  void clear() { infos.clear(); }
+  void read(const std::string &path, int num_batches = 0, int batch_index = 0) {
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) throw std::string("could not open file ") + path + ": " + strerror(errno);
+    std::vector<std::string> lines;
+    std::string cur;
+    char buf[4096];
+    while (fgets(buf, sizeof buf, fp)) {
+      cur += buf;
+      if (!cur.empty() && cur[cur.size() - 1] == '\n') { push_line(lines, cur); cur.clear(); }
+    }
+    if (!cur.empty()) push_line(lines, cur);
+    fclose(fp);
+    if (num_batches > 1 && (batch_index < 1 || batch_index > num_batches)) throw std::string("Invalid batch index");
+    const size_t n = lines.size();
+    size_t first = 0, last = n;
+    if (num_batches > 1) {
+      const size_t per = n / num_batches, rem = n % num_batches, b = (size_t)batch_index - 1;
+      first = b * per + std::min(b, rem);
+      last = first + per + (b < rem ? 1 : 0);
+    }
+    std::map<std::string, std::string> kv;
+    for (size_t i = 0; i < std::min(last, n); i++) {
+      size_t p = 0;
+      const std::string &line = lines[i];
+      while (p < line.size()) {
+        while (p < line.size() && (line[p] == ' ' || line[p] == '\t')) p++;
+        size_t q = p;
+        while (q < line.size() && line[q] != ' ' && line[q] != '\t') q++;
+        if (q > p) {
+          const std::string f = line.substr(p, q - p);
+          const size_t e = f.find('=');
+          // str::split(field, "=", false): exactly two parts, i.e. one '=' that is not the last character
+          if (e == std::string::npos || e + 1 == f.size() || f.find('=', e + 1) != std::string::npos)
+            throw std::string("Invalid recipe line: ") + line;
+          kv[f.substr(0, e)] = f.substr(e + 1);
+        }
+        p = q;
+      }
+      if (i < first) continue;
+      Info info;
+      info.audio_path = kv["audio"]; info.lna_path = kv["lna"]; info.speaker_id = kv["speaker"]; info.utterance_id = kv["utterance"];
+      if (kv.count("start-time")) info.start_time = atof(kv["start-time"].c_str());
+      if (kv.count("end-time")) info.end_time = atof(kv["end-time"].c_str());
+      infos.push_back(info);
+    }
+  }
+  void sort_infos() { std::stable_sort(infos.begin(), infos.end()); }               // aku/Recipe.hh:115-117
+private:
+  static void push_line(std::vector<std::string> &lines, const std::string &raw) {   // str::clean(&line, "\n\t ")
+    size_t b = raw.find_first_not_of("\n\t \r"), e = raw.find_last_not_of("\n\t \r");
+    if (b == std::string::npos) return;
+    if (raw[b] == '#') return;
+    lines.push_back(raw.substr(b, e - b + 1));
+  }
+};
+
 // aku::PPToolbox (aku/PhoneProbsToolbox.hh:13-31, the class behind aku/swig/PPToolbox.i): one utterance in, one LNA
 // stream out (5-byte header, 2-byte normalised codes -- lnabytes is fixed to 2 there, aku/PhoneProbsToolbox.cc:57,138),
 // whole utterance per GPU call instead of the per-frame loop (:83-131,156-207).

@@ -30,41 +30,12 @@ struct OutStream {
   ~OutStream() { if (fp && is_pipe) pclose(fp); else if (fp && !is_stdout) fclose(fp); else if (fp) fflush(fp); }
 };
 
-// Recipe::read (aku/Recipe.cc:24-147): key=value fields; keys persist across lines like the reference's map.
-static std::vector<Utt> read_recipe(const std::string &path, int batch, int bindex)
-{
-  std::ifstream in(path.c_str());
-  if (!in) throw std::string("could not open recipe ") + path;
-  std::vector<Utt> all;
-  std::map<std::string, std::string> kv;
-  std::string line;
-  while (std::getline(in, line)) {
-    size_t b = line.find_first_not_of(" \t\r");
-    if (b == std::string::npos || line[b] == '#') continue;
-    std::istringstream ss(line);
-    std::string f;
-    while (ss >> f) { size_t e = f.find('='); if (e != std::string::npos) kv[f.substr(0, e)] = f.substr(e + 1); }
-    Utt u;
-    u.audio = kv["audio"]; u.lna = kv["lna"]; u.speaker = kv["speaker"]; u.utterance = kv["utterance"];
-    u.start_time = kv.count("start-time") ? atof(kv["start-time"].c_str()) : 0;
-    u.end_time = kv.count("end-time") ? atof(kv["end-time"].c_str()) : 0;
-    all.push_back(u);
-  }
-  if (batch <= 1) return all;
-  if (bindex < 1 || bindex > batch) throw std::string("Invalid batch index");
-  // contiguous split (aku/Recipe.cc:63-115, no speaker clustering)
-  size_t n = all.size(), per = n / batch, rem = n % batch;
-  size_t start = (bindex - 1) * per + std::min<size_t>(bindex - 1, rem);
-  size_t cnt = per + ((size_t)(bindex - 1) < rem ? 1 : 0);
-  return std::vector<Utt>(all.begin() + start, all.begin() + start + cnt);
-}
-
 int main(int argc, char **argv)
 {
   std::string base, gk, mc, ph, cfg, recipe, outdir, clusters, speakers;
   double eval_minc = 0, eval_ming = 0.1;       // defaults of aku/phone_probs.cc:74-75
   int lnabytes = 2, batch = 0, bindex = 0, info = 0, device = 0, precision = AKUGPU_F32;
-  bool raw_input = false, lna_by_audio = false, no_overwrite = false, no_norm = false;
+  bool raw_input = false, lna_by_audio = false, no_overwrite = false, no_norm = false, sort_recipe = false;
   long max_batch_samples = 64L << 20;
   try {
     for (int i = 1; i < argc; i++) {
@@ -80,7 +51,7 @@ int main(int argc, char **argv)
         printf("usage: akugpu_phone_probs [OPTION...]\n"
                "  -b, --base=BASENAME    base filename for model files\n  -g, --gk=FILE  -m, --mc=FILE  -p, --ph=FILE\n"
                "  -c, --config=FILE      feature configuration\n  -r, --recipe=FILE      recipe file\n"
-               "  -a, --lnabyaudio       name LNA files by the audio file\n  -o, --output-dir=DIR   base path for LNAs\n"
+               "  -a, --afname           name LNA files by the audio file\n      --sort-recipe      sort recipe lines by speaker, useful with adaptation\n  -o, --output-dir=DIR   base path for LNAs\n"
                "  -R, --raw-input        raw audio input\n      --lnabytes=INT     2 (default) or 4\n"
                "  -n, --no-overwrite     skip existing non-empty LNA files\n  -N, --no-normalization\n"
                "  -S, --speakers=FILE    speaker configuration file (feature-module parameters per speaker / utterance,\n"
@@ -97,7 +68,8 @@ int main(int argc, char **argv)
       else if (a == "-c" || a == "--config") cfg = val();
       else if (a == "-r" || a == "--recipe") recipe = val();
       else if (a == "-o" || a == "--output-dir") outdir = val();
-      else if (a == "-a" || a == "--lnabyaudio") lna_by_audio = true;
+      else if (a == "-a" || a == "--afname" || a == "--lnabyaudio") lna_by_audio = true;
+      else if (a == "--sort-recipe") sort_recipe = true;
       else if (a == "-R" || a == "--raw-input") raw_input = true;
       else if (a == "--lnabytes") lnabytes = atoi(val().c_str());
       else if (a == "-n" || a == "--no-overwrite") no_overwrite = true;
@@ -137,7 +109,18 @@ int main(int argc, char **argv)
       throw std::string(msg);
     }
     const int S = model.num_states();
-    std::vector<Utt> utts = read_recipe(recipe, batch, bindex);
+    if ((batch != 0) != (bindex != 0)) throw std::string("Must give both --batch and --bindex");   // aku/phone_probs.cc:135-136
+    akugpu::Recipe rcp;
+    rcp.read(recipe, batch, bindex);
+    if (sort_recipe) rcp.sort_infos();                                                                // aku/phone_probs.cc:141-142
+    std::vector<Utt> utts;
+    for (size_t k = 0; k < rcp.infos.size(); k++) {
+      const akugpu::Recipe::Info &r = rcp.infos[k];
+      Utt u;
+      u.audio = r.audio_path; u.lna = r.lna_path; u.speaker = r.speaker_id; u.utterance = r.utterance_id;
+      u.start_time = r.start_time; u.end_time = r.end_time;
+      utts.push_back(u);
+    }
     // output names (aku/phone_probs.cc:155-176) and --no-overwrite (:180-190)
     std::vector<Utt> todo;
     for (size_t k = 0; k < utts.size(); k++) {

@@ -77,20 +77,40 @@ def write_model(base, mix_offsets, mix_gauss, mix_weight, means, covs=None, full
             f.write("%d 3 p%d\n-1 -2 %d\n0 1 2 1\n1 0\n2 2 2 0.8 1 0.2\n" % (s + 1, s, s))
 
 
-def read_recipe(path):
-    """One utterance per line of key=value fields; a key missing on a later line inherits the
-    previous line's value (the reference never clears its map, aku/Recipe.cc:29,82-90)."""
-    infos, cur = [], {}
+def read_recipe(path, num_batches=0, batch_index=0):
+    """aku::Recipe::read (aku/Recipe.cc:24-147): one utterance per line of key=value fields; a key missing on a later
+    line inherits the previous line's value (the reference never clears its map, :29,82-90), also across batch borders.
+    num_batches > 1: the contiguous part `batch_index` (1-based) of the non-empty, non-comment lines, the first
+    (lines % batches) parts one line longer (:63-115 with cluster_speakers = false, as phone_probs calls it)."""
+    lines = []
     for line in open(path):
-        line = line.strip()
-        if not line or line.startswith("#"):
-            continue
-        for field in line.split():
-            if "=" in field:
-                k, v = field.split("=", 1)
-                cur[k] = v
-        infos.append(dict(cur))
+        line = line.strip("\n\t \r")
+        if line and not line.startswith("#"):
+            lines.append(line)
+    if num_batches > 1 and not 1 <= batch_index <= num_batches:
+        raise ValueError("Invalid batch index")
+    first, last = 0, len(lines)
+    if num_batches > 1:
+        per, rem = divmod(len(lines), num_batches)
+        first = (batch_index - 1) * per + min(batch_index - 1, rem)
+        last = first + per + (1 if batch_index - 1 < rem else 0)
+    infos, cur = [], {}
+    for i, line in enumerate(lines[:last]):
+        for field in line.replace("\t", " ").split(" "):
+            if not field:
+                continue
+            kv = field.split("=")
+            if len(kv) != 2 or field.endswith("="):          # str::split(field, "=", false) must give two parts
+                raise ValueError("Invalid recipe line: " + line)
+            cur[kv[0]] = kv[1]
+        if i >= first:
+            infos.append(dict(cur))
     return infos
+
+
+def sort_recipe(infos):
+    """Recipe::sort_infos (aku/Recipe.hh:89-91,115-117; phone_probs --sort-recipe): stable sort by speaker."""
+    return sorted(infos, key=lambda d: d.get("speaker", ""))
 
 
 def lna_header(num_states, lnabytes):

@@ -306,15 +306,12 @@ class PhoneProbs:
         return rec.shape[0]
 
     def run_recipe(self, recipe_path, out_dir="", batch=1, bindex=1, no_overwrite=False, audio_ext_lna=False,
-                   max_batch_samples=64 << 20):
+                   max_batch_samples=64 << 20, sort_recipe=False):
         """The tool's recipe loop (aku/phone_probs.cc:135-267): utterances of this batch share GPU
         launches; output files are per utterance like the reference's."""
-        infos = formats.read_recipe(recipe_path)
-        if batch > 1:   # contiguous split like Recipe::read (aku/Recipe.cc:63-115)
-            n = len(infos)
-            per, rem = divmod(n, batch)
-            start = (bindex - 1) * per + min(bindex - 1, rem)
-            infos = infos[start:start + per + (1 if bindex - 1 < rem else 0)]
+        infos = formats.read_recipe(recipe_path, batch, bindex)
+        if sort_recipe:     # --sort-recipe (aku/phone_probs.cc:141-142)
+            infos = formats.sort_recipe(infos)
         todo = []
         for info in infos:
             if audio_ext_lna or "lna" not in info:

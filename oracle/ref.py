@@ -45,6 +45,8 @@ def lib():
         _lib.ref_model_read_clustering.argtypes = [C.c_void_p, C.c_char_p]
         _lib.ref_model_set_clustering_min_evals.argtypes = [C.c_void_p, C.c_double, C.c_double]
         _lib.ref_model_set_speaker.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        _lib.ref_recipe_read.restype = C.c_long
+        _lib.ref_recipe_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_long]
     return _lib
 
 
@@ -137,6 +139,17 @@ class Model:
         if self.h:
             lib().ref_model_close(self.h)
             self.h = None
+
+
+def recipe_read(path, num_batches=0, batch_index=0, sort=False):
+    """aku::Recipe::read as phone_probs calls it (+ sort_infos): list of (audio, lna, speaker, utterance, start, end)."""
+    buf = C.create_string_buffer(1 << 20)
+    n = lib().ref_recipe_read(path.encode(), num_batches, batch_index, 1 if sort else 0, buf, len(buf))
+    if n < 0:
+        raise _err()
+    rows = [ln.split("|") for ln in buf.value.decode().splitlines()]
+    assert len(rows) == n
+    return [(r[0], r[1], r[2], r[3], float(r[4]), float(r[5])) for r in rows]
 
 
 def lna_read(path, buf_frames=64, backwards=True):

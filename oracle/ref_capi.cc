@@ -20,6 +20,7 @@
 #include "FeatureModules.hh"
 #include "HmmSet.hh"
 #include "SpeakerConfig.hh"
+#include "Recipe.hh"
 #include "LnaReaderCircular.hh"   // decoder/src: the consumer of the LNA stream
 
 using namespace aku;
@@ -197,6 +198,29 @@ int ref_gaussian_loglik(void *h, const double *feats, long F, int D, double *out
       for (int g = 0; g < G; g++) out[f * G + g] = pool->get_pdf(g)->compute_log_likelihood(v);
     }
     return 0;
+  } catch (std::string &s) { return fail(s); }
+  catch (std::exception &e) { return fail(e.what()); }
+}
+
+// aku::Recipe::read(file, num_batches, batch_index, cluster_speakers = false) as phone_probs calls it
+// (aku/phone_probs.cc:137-142), optionally followed by sort_infos().  Writes one line per Info:
+// audio|lna|speaker|utterance|start|end.  Returns the number of infos, -1 on error, -2 if `cap` is too small.
+long ref_recipe_read(const char *path, int num_batches, int batch_index, int sort, char *out, long cap)
+{
+  try {
+    Recipe recipe;
+    recipe.read(io::Stream(path), num_batches, batch_index, false);
+    if (sort) recipe.sort_infos();
+    std::string text;
+    for (size_t i = 0; i < recipe.infos.size(); i++) {
+      const Recipe::Info &r = recipe.infos[i];
+      char t[64];
+      snprintf(t, sizeof t, "|%g|%g\n", (double)r.start_time, (double)r.end_time);
+      text += r.audio_path + "|" + r.lna_path + "|" + r.speaker_id + "|" + r.utterance_id + t;
+    }
+    if ((long)text.size() + 1 > cap) return -2;
+    memcpy(out, text.c_str(), text.size() + 1);
+    return (long)recipe.infos.size();
   } catch (std::string &s) { return fail(s); }
   catch (std::exception &e) { return fail(e.what()); }
 }

@@ -61,6 +61,20 @@ int main(int argc, char **argv)
     }
     return 0;
   }
+  if (std::string(argv[1]) == "recipe") {      // spk_harness recipe PATH BATCHES INDEX SORT: akugpu::Recipe
+    try {
+      akugpu::Recipe r;
+      r.read(argv[2], atoi(argv[3]), atoi(argv[4]));
+      if (atoi(argv[5])) r.sort_infos();
+      for (size_t i = 0; i < r.infos.size(); i++)
+        printf("%s|%s|%s|%s|%g|%g\n", r.infos[i].audio_path.c_str(), r.infos[i].lna_path.c_str(), r.infos[i].speaker_id.c_str(),
+               r.infos[i].utterance_id.c_str(), r.infos[i].start_time, r.infos[i].end_time);
+    } catch (std::string &s) {
+      printf("exception: %s\n", s.c_str());
+      return 1;
+    }
+    return 0;
+  }
   if (std::string(argv[1]) == "hmm") {         // spk_harness hmm f32|f64: the akugpu::HmmSet cache protocol
     g_dim = 2;
     akugpu::Engine eng(0);

@@ -177,6 +177,80 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     assert rc == 1 and "Unknown speaker b, and default speaker settings are missing." in out
 
 
+def test_recipe_reader_three_ways(tmp_path):
+    """aku::Recipe::read + sort_infos as phone_probs uses them (-B / -I / --sort-recipe, aku/phone_probs.cc:137-142): the
+    C++ adapter (akugpu::Recipe), the Python mirror (formats.read_recipe / sort_recipe) and -- when oracle/_ref is built --
+    the reference's own class give the same utterance lists for every batch of several recipes: inherited keys (also
+    across batch borders), comments, blank lines, tabs, fewer lines than batches, and the reference's errors."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import ref
+    exe = str(tmp_path / "spk_harness")
+    subprocess.run(["g++", "-O1", "-std=c++11", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "spk_harness.cc")],
+                   check=True, timeout=300)
+    rng = np.random.default_rng(5)
+    recipes = []
+    lines = []
+    for i in range(23):
+        f = ["audio=/d/a%d.wav" % i]
+        if i % 3 != 1:
+            f.append("lna=a%d.lna" % i)
+        if i % 4 == 0:
+            f.append("speaker=spk%d" % rng.integers(0, 4))
+        if i % 5 == 2:
+            f.append("utterance=u%d" % i)
+        if i % 6 == 3:
+            f += ["start-time=%.2f" % (0.1 * i), "end-time=%.2f" % (0.1 * i + 1)]
+        lines.append((" " if i % 2 else "\t").join(f))
+        if i % 7 == 0:
+            lines.append("# a comment")
+        if i % 8 == 0:
+            lines.append("   ")
+    recipes.append("\n".join(lines) + "\n")
+    recipes.append("audio=x.wav speaker=b\naudio=y.wav speaker=a\naudio=z.wav\n  audio=w.wav speaker=b transcript=t.phn")   # no final newline
+    recipes.append("")
+
+    def fmt(rows):
+        return ["%s|%s|%s|%s|%g|%g" % r for r in rows]
+
+    for k, text in enumerate(recipes):
+        path = str(tmp_path / ("r%d.recipe" % k))
+        open(path, "w").write(text)
+        for B, I in [(0, 0), (1, 1), (2, 1), (2, 2), (3, 2), (5, 1), (5, 5), (7, 4), (30, 3), (30, 29)]:
+            for srt in (0, 1):
+                r = subprocess.run([exe, "recipe", path, str(B), str(I), str(srt)], stdout=subprocess.PIPE, timeout=60)
+                assert r.returncode == 0, r.stdout
+                cpp = r.stdout.decode().splitlines()
+                infos = formats.read_recipe(path, B, I)
+                if srt:
+                    infos = formats.sort_recipe(infos)
+                py = fmt([(d.get("audio", ""), d.get("lna", ""), d.get("speaker", ""), d.get("utterance", ""),
+                           float(d.get("start-time", 0)), float(d.get("end-time", 0))) for d in infos])
+                assert cpp == py, (k, B, I, srt)
+                if ref.available():
+                    assert cpp == fmt(ref.recipe_read(path, B, I, bool(srt))), (k, B, I, srt)
+        # all batches together = the whole recipe, in order
+        whole = formats.read_recipe(path)
+        for B in (2, 3, 7):
+            assert sum((formats.read_recipe(path, B, i) for i in range(1, B + 1)), []) == whole
+    bad = str(tmp_path / "bad.recipe")
+    for text in ("audio=a.wav lna\n", "audio=a.wav lna=\n", "audio=a.wav x=1=2\n"):
+        open(bad, "w").write(text)
+        r = subprocess.run([exe, "recipe", bad, "0", "0", "0"], stdout=subprocess.PIPE, timeout=60)
+        assert r.returncode == 1 and b"Invalid recipe line: audio=a.wav" in r.stdout
+        with pytest.raises(ValueError, match="Invalid recipe line"):
+            formats.read_recipe(bad)
+        if ref.available():
+            with pytest.raises(RuntimeError, match="Invalid recipe line"):
+                ref.recipe_read(bad)
+    open(bad, "w").write("audio=a.wav\n")
+    r = subprocess.run([exe, "recipe", bad, "3", "4", "0"], stdout=subprocess.PIPE, timeout=60)
+    assert r.returncode == 1 and b"Invalid batch index" in r.stdout
+    with pytest.raises(ValueError, match="Invalid batch index"):
+        formats.read_recipe(bad, 3, 4)
+
+
 def test_formats_roundtrip(tmp_path):
     pcm = synth.synth_audio(5, 4000)
     formats.write_wav(str(tmp_path / "a.wav"), pcm, 16000)

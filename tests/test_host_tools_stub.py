@@ -1,0 +1,263 @@
+"""CPU tests of the host tools' OWN logic -- aaltoasr_b200/csrc/host/phone_probs_main.cc and feacat_main.cc linked
+against a FAKE of the C ABI (tests/cpp/stub_akugpu.cc: closed-form "features" and "LNA bytes", every call logged).
+What is checked here is what the tools add above the library: the recipe loop of aku/phone_probs.cc:135-267 (output
+names, -o / -a / -n, start-time / end-time cropping, -B / -I, --sort-recipe, one GPU call per run of utterances that
+share a speaker, speaker files incl. sticky `model cmllr`), the frame ranges and output formats of aku/feacat.cc, and
+the error paths.  The real library behind the same tools is covered by tests/test_gpu_host.py on the GPU."""
+import gzip
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from aaltoasr_b200 import formats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "aaltoasr_b200", "csrc", "host")
+STUB = os.path.join(ROOT, "tests", "cpp", "stub_akugpu.cc")
+S = 4
+
+
+@pytest.fixture(scope="module")
+def tools(tmp_path_factory):
+    d = tmp_path_factory.mktemp("stubtools")
+    out = {}
+    for name in ("phone_probs", "feacat"):
+        exe = str(d / name)
+        subprocess.run(["g++", "-O1", "-std=c++11", "-Wall", "-Werror", "-o", exe, os.path.join(HOST, name + "_main.cc"), STUB],
+                       check=True, timeout=300)
+        out[name] = exe
+    return out
+
+
+def lna_file(frames, lnabytes=2, normalize=1, cmllr=0, shift=0):
+    """What the stub's akugpu_phone_probs writes for the utterance-local frames `frames`, behind the 5-byte header."""
+    body = bytes((7 * f + 3 * s + b + 100 * normalize + 50 * cmllr + shift) & 255
+                 for f in frames for s in range(S) for b in range(lnabytes))
+    return struct.pack(">I", S) + bytes([lnabytes]) + body
+
+
+SPKC = """speaker default
+{
+  shift
+  {
+    value 0
+  }
+}
+speaker s1
+{
+  feature shift
+  {
+    value 1
+  }
+}
+speaker s2
+{
+  shift
+  {
+    value 2
+  }
+  model cmllr
+  {
+    unitmode UNIT_NO
+    w1 0.5 1 0 0 -0.5 0 1 0 0.25 0 0 1
+  }
+}
+utterance default
+{
+  shift
+  {
+    value 0
+  }
+}
+utterance u1
+{
+  shift
+  {
+    value 7
+  }
+}
+"""
+
+
+@pytest.fixture()
+def case(tmp_path):
+    n_samples = [1280, 2560, 640, 1920, 1300]          # 10, 20, 5, 15, 10 frames
+    for i, n in enumerate(n_samples):
+        formats.write_wav(str(tmp_path / ("a%d.wav" % i)), (np.arange(n) % 100).astype(np.int16), 16000)
+    rec = str(tmp_path / "r.recipe")
+    open(rec, "w").write(
+        "audio=%(d)s/a0.wav lna=x0.lna speaker=s1\n"
+        "# the speaker carries over\n"
+        "audio=%(d)s/a1.wav lna=x1.lna\n"
+        "\n"
+        "audio=%(d)s/a2.wav speaker=s2 lna=x2.lna start-time=0.02 end-time=0.036\n"
+        "audio=%(d)s/a3.wav lna=x3.lna speaker=s1 start-time=0 end-time=0\n"
+        "audio=%(d)s/a4.wav speaker=s3 lna=x4.lna\n" % {"d": str(tmp_path)})
+    cfg = str(tmp_path / "f.cfg")
+    open(cfg, "w").write("module\n{\n  name shift\n  type stub\n}\n")
+    spkc = str(tmp_path / "x.spkc")
+    open(spkc, "w").write(SPKC)
+    return dict(dir=tmp_path, recipe=rec, cfg=cfg, spkc=spkc, frames=[n // 128 for n in n_samples])
+
+
+def run(exe, args, log=None, env=None, **kw):
+    e = dict(os.environ)
+    e.pop("AKUGPU_STUB_LOG", None)
+    if log:
+        e["AKUGPU_STUB_LOG"] = log
+    if env:
+        e.update(env)
+    return subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120, env=e, **kw)
+
+
+def calls(log, what):
+    return [ln for ln in open(log).read().splitlines() if ln.startswith(what)]
+
+
+def test_phone_probs_recipe_loop(tools, case):
+    c, exe = case, tools["phone_probs"]
+    out = c["dir"] / "o"
+    out.mkdir()
+    log = str(c["dir"] / "log1")
+    r = run(exe, ["-b", "mdl", "-c", c["cfg"], "-r", c["recipe"], "-o", str(out), "-i", "1"], log)
+    assert r.returncode == 0, r.stderr.decode()
+    fr = c["frames"]
+    for i in (0, 1, 3, 4):
+        assert open(str(out / ("x%d.lna" % i)), "rb").read() == lna_file(range(fr[i])), i
+    assert open(str(out / "x2.lna"), "rb").read() == lna_file(range(2, 4))            # start-time / end-time in frames
+    # one library call per utterance without -S (no reason to split) -- all five in one
+    assert calls(log, "phone_probs") == ["phone_probs n_utts=5 samples=7700 precision=0 lnabytes=2 normalize=1"]
+    assert calls(log, "model_read") == ["model_read mdl"] and calls(log, "load_config") == ["load_config " + c["cfg"]]
+    assert r.stdout.decode().count("Processing file: ") == 5
+
+    # -S: utterances that share a speaker share a call; `model cmllr` stays loaded for speakers without the entry
+    log = str(c["dir"] / "log2")
+    r = run(exe, ["-b", "mdl", "-c", c["cfg"], "-r", c["recipe"], "-o", str(out), "-S", c["spkc"], "--lnabytes=4", "-N"], log)
+    assert r.returncode == 0, r.stderr.decode()
+    assert [ln.split()[1] for ln in calls(log, "phone_probs")] == ["n_utts=2", "n_utts=1", "n_utts=1", "n_utts=1"]
+    seq = [ln for ln in open(log).read().splitlines() if ln.split()[0] in ("set_parameters", "set_cmllr", "phone_probs")]
+    assert seq[:2] == ["set_parameters shift value 1;", "phone_probs n_utts=2 samples=3840 precision=0 lnabytes=4 normalize=0"]
+    assert "set_cmllr 0.5 1" in seq and seq.index("set_cmllr 0.5 1") < seq.index("phone_probs n_utts=1 samples=640 precision=0 lnabytes=4 normalize=0")
+    assert open(str(out / "x0.lna"), "rb").read() == lna_file(range(fr[0]), 4, 0, 0, 1)
+    assert open(str(out / "x2.lna"), "rb").read() == lna_file(range(2, 4), 4, 0, 1, 2)
+    assert open(str(out / "x3.lna"), "rb").read() == lna_file(range(fr[3]), 4, 0, 1, 1)      # s1 again: cmllr still on
+    assert open(str(out / "x4.lna"), "rb").read() == lna_file(range(fr[4]), 4, 0, 1, 0)      # unknown speaker: default block
+
+    # --sort-recipe groups the speakers (stable): s1 x 3 in one call, then s2, s3
+    log = str(c["dir"] / "log3")
+    r = run(exe, ["-b", "mdl", "-c", c["cfg"], "-r", c["recipe"], "-o", str(out), "-S", c["spkc"], "--sort-recipe"], log)
+    assert r.returncode == 0, r.stderr.decode()
+    assert [ln.split()[1] for ln in calls(log, "phone_probs")] == ["n_utts=3", "n_utts=1", "n_utts=1"]
+    assert open(str(out / "x3.lna"), "rb").read() == lna_file(range(fr[3]), 2, 1, 0, 1)      # before s2 now: no cmllr yet
+
+
+def test_phone_probs_flags(tools, case):
+    c, exe = case, tools["phone_probs"]
+    out = c["dir"] / "o"
+    out.mkdir()
+    fr = c["frames"]
+    base = ["-c", c["cfg"], "-r", c["recipe"], "-o", str(out)]
+    # -a / --afname: named by the audio file; -g -m -p instead of -b; clustering flags reach the library
+    log = str(c["dir"] / "log")
+    r = run(exe, base + ["-g", "m.gk", "-m", "m.mc", "-p", "m.ph", "--afname", "-C", "c.gcl", "--eval-minc", "0.1", "--eval-ming=0.2"], log)
+    assert r.returncode == 0, r.stderr.decode()
+    assert sorted(os.listdir(str(out))) == ["a%d.lna" % i for i in range(5)]
+    assert calls(log, "model_read") == ["model_read_files m.gk m.mc m.ph"]
+    assert calls(log, "read_clustering") == ["read_clustering c.gcl"] and calls(log, "min_evals") == ["min_evals 0.1 0.2"]
+    # -n: existing non-empty files are skipped, empty ones are not
+    for f in os.listdir(str(out)):
+        os.remove(str(out / f))
+    open(str(out / "x0.lna"), "wb").write(b"keep")
+    open(str(out / "x1.lna"), "wb").close()
+    log = str(c["dir"] / "logn")
+    r = run(exe, base + ["-b", "mdl", "-n"], log)
+    assert r.returncode == 0, r.stderr.decode()
+    assert open(str(out / "x0.lna"), "rb").read() == b"keep" and open(str(out / "x1.lna"), "rb").read() == lna_file(range(fr[1]))
+    assert calls(log, "phone_probs")[0].split()[1] == "n_utts=4"
+    # -B / -I: the second of two batches is lines 4-5 (3 + 2); both flags are needed
+    for f in os.listdir(str(out)):
+        os.remove(str(out / f))
+    r = run(exe, base + ["-b", "mdl", "-B", "2", "-I", "2"])
+    assert r.returncode == 0 and sorted(os.listdir(str(out))) == ["x3.lna", "x4.lna"]
+    r = run(exe, base + ["-b", "mdl", "-B", "2"])
+    assert r.returncode == 1 and b"Must give both --batch and --bindex" in r.stderr
+    r = run(exe, base + ["-b", "mdl", "-B", "2", "-I", "3"])
+    assert r.returncode == 1 and b"Invalid batch index" in r.stderr
+    # io::Stream output names: a trailing .gz goes through gzip
+    rec = str(c["dir"] / "gz.recipe")
+    open(rec, "w").write("audio=%s/a2.wav lna=z.lna.gz\n" % c["dir"])
+    r = run(exe, ["-b", "mdl", "-c", c["cfg"], "-r", rec, "-o", str(out)])
+    assert r.returncode == 0, r.stderr.decode()
+    assert gzip.open(str(out / "z.lna.gz")).read() == lna_file(range(fr[2]))
+    # errors worded like the reference's
+    for args, msg in ((["-r", c["recipe"], "-b", "m"], b"Must give --config"),
+                      (["-c", c["cfg"], "-b", "m"], b"Must give --recipe"),
+                      (base, b"Must give either --base or all --gk, --mc and --ph"),
+                      (base + ["-b", "m", "--lnabytes=3"], b"Invalid number of bytes for probabilities in LNA file"),
+                      (base + ["-b", "m", "--frobnicate"], b"unknown option --frobnicate"),
+                      (["-c", str(c["dir"] / "none.cfg"), "-r", c["recipe"], "-b", "m"], b"could not open file")):
+        r = run(exe, args)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+    r = run(exe, base + ["-b", "m"], env={"AKUGPU_STUB_MODEL_DIM": "5"})
+    assert r.returncode == 1 and b"Feature dimension (3) and model dimension (5) don't agree" in r.stderr
+    formats.write_wav(str(c["dir"] / "a2.wav"), np.zeros(640, np.int16), 8000)
+    r = run(exe, base + ["-b", "m"])
+    assert r.returncode == 1 and b"Audio file sample rate (8000 Hz) and model configuration (16000 Hz) don't agree." in r.stderr
+
+
+def rows_of(frames, shift=0.0):
+    return np.array([[f + 0.25 * d + shift for d in range(3)] for f in frames])
+
+
+def test_feacat_ranges_and_formats(tools, case):
+    c, exe = case, tools["feacat"]
+    wav = str(c["dir"] / "a1.wav")                      # 20 frames
+    r = run(exe, ["-c", c["cfg"], wav])
+    assert r.returncode == 0, r.stderr.decode()
+    lines = r.stdout.decode().splitlines()
+    assert len(lines) == 20 and lines[3] == "  3.0000   3.2500   3.5000 "            # "%8.4f " per component
+    # frames outside the file: the library's border handling, one call for the whole range; end frame inclusive
+    log = str(c["dir"] / "log")
+    r = run(exe, ["-c", c["cfg"], "-s", "-2", "-e", "3", wav], log)
+    got = np.array([[float(x) for x in ln.split()] for ln in r.stdout.decode().splitlines()])
+    assert np.array_equal(got, rows_of([0, 0, 0, 1, 2, 3])) and calls(log, "features_range") == ["features_range -2 4"]
+    r = run(exe, ["-c", c["cfg"], "--start-frame=18", wav])                          # open end: to the end of the file
+    assert len(r.stdout.decode().splitlines()) == 2
+    r = run(exe, ["-c", c["cfg"], "--start-frame", "25", wav])
+    assert r.returncode == 0 and r.stdout == b""
+    # raw output with the int32 dimension header; descending range
+    r = run(exe, ["-c", c["cfg"], "--raw-output", "-H", "-s", "5", "-e", "2", wav])
+    assert r.stdout[:4] == struct.pack("<i", 3)
+    assert np.array_equal(np.frombuffer(r.stdout[4:], "<f4").reshape(-1, 3), rows_of([5, 4, 3, 2]).astype(np.float32))
+    r = run(exe, ["-c", c["cfg"], "-H", "-s", "1", "-e", "1", wav])
+    assert b"Warning: header is only written in raw output mode" in r.stderr and len(r.stdout.decode().splitlines()) == 1
+    # audio on standard input; --write-config
+    wcfg = str(c["dir"] / "w.cfg")
+    r = run(exe, ["-c", c["cfg"], "-w", wcfg, "-e", "1", "-"], input=open(wav, "rb").read())
+    assert r.returncode == 0 and len(r.stdout.decode().splitlines()) == 2 and open(wcfg).read() == open(c["cfg"]).read()
+    # -S / -d / -u: speaker, then utterance parameters
+    r = run(exe, ["-c", c["cfg"], "-S", c["spkc"], "-d", "s2", "-e", "0", wav])
+    assert [float(x) for x in r.stdout.decode().split()] == [2.0, 2.25, 2.5]
+    r = run(exe, ["-c", c["cfg"], "-S", c["spkc"], "-d", "s1", "-u", "u1", "-e", "0", wav])
+    assert [float(x) for x in r.stdout.decode().split()] == [7.0, 7.25, 7.5]
+    r = run(exe, ["-c", c["cfg"], "-S", c["spkc"], "-d", "nobody", "-e", "0", wav])     # default speaker block
+    assert [float(x) for x in r.stdout.decode().split()] == [0.0, 0.25, 0.5]
+    # a `pre` configuration reads the raw file feacat -H --raw-output wrote
+    pre_cfg = str(c["dir"] / "pre.cfg")
+    open(pre_cfg, "w").write("module\n{\n  name pre\n  type pre\n  dim 3\n}\n")
+    raw = str(c["dir"] / "f.raw")
+    open(raw, "wb").write(run(exe, ["-c", c["cfg"], "--raw-output", "-H", "-s", "4", "-e", "9", wav]).stdout)
+    r = run(exe, ["-c", pre_cfg, "-s", "-1", "-e", "6", raw])
+    got = np.array([[float(x) for x in ln.split()] for ln in r.stdout.decode().splitlines()])
+    assert np.array_equal(got, rows_of([4, 4, 5, 6, 7, 8, 9, 9]))
+    # errors
+    assert run(exe, ["-c", c["cfg"]]).returncode == 1 and run(exe, ["-c", c["cfg"], wav, wav]).returncode == 1
+    r = run(exe, [wav])
+    assert r.returncode == 1 and b"Must give --config" in r.stderr
+    r = run(exe, ["-c", c["cfg"], "-G", "0.1", wav])
+    assert r.returncode == 1 and b"not supported" in r.stderr
+    r = run(exe, ["-c", c["cfg"], str(c["dir"] / "none.wav")])
+    assert r.returncode == 1 and b"exception: AudioReader::open(): could not open file" in r.stderr
