@@ -261,3 +261,39 @@ def test_feacat_ranges_and_formats(tools, case):
     assert r.returncode == 1 and b"not supported" in r.stderr
     r = run(exe, ["-c", c["cfg"], str(c["dir"] / "none.wav")])
     assert r.returncode == 1 and b"exception: AudioReader::open(): could not open file" in r.stderr
+
+
+class FakeEngine:
+    """The stub's formulas behind the Python engine surface PhoneProbs.run_recipe uses."""
+    sample_rate, frame_rate, num_states = 16000, 125.0, S
+
+    def phone_probs(self, pcm, uo, precision=0, lnabytes=2, normalize=True):
+        fo = np.concatenate([[0], np.cumsum(np.diff(uo) // 128)]).astype(np.int64)
+        rec = np.concatenate([np.frombuffer(lna_file(range(int(fo[k + 1] - fo[k])), lnabytes, 1 if normalize else 0)[5:], np.uint8)
+                              for k in range(len(uo) - 1)]).reshape(int(fo[-1]), S * lnabytes)
+        return rec, fo, None
+
+
+def test_python_run_recipe_matches_the_cpp_tool(tools, case):
+    """hostapi.PhoneProbs.run_recipe (the Python mirror used by the GPU tests) and the C++ tool write the same files for
+    the same recipe: names, cropping, batches, --sort-recipe, --no-overwrite."""
+    from aaltoasr_b200 import PhoneProbs
+    c = case
+    for k, (flags, kw) in enumerate(((["-B", "2", "-I", "1"], dict(batch=2, bindex=1)),
+                                     ([], {}),
+                                     (["--sort-recipe", "--lnabytes=4", "-N"], dict(sort_recipe=True)),
+                                     (["-a", "-n"], dict(audio_ext_lna=True, no_overwrite=True)))):
+        o_cpp, o_py = c["dir"] / ("cpp%d" % k), c["dir"] / ("py%d" % k)
+        o_cpp.mkdir(); o_py.mkdir()
+        if "-n" in flags:
+            for o in (o_cpp, o_py):
+                open(str(o / "a1.lna"), "wb").write(b"old")
+        r = run(tools["phone_probs"], ["-b", "m", "-c", c["cfg"], "-r", c["recipe"], "-o", str(o_cpp)] + flags)
+        assert r.returncode == 0, r.stderr.decode()
+        four = "--lnabytes=4" in flags
+        pp = PhoneProbs(engine=FakeEngine(), lnabytes=4 if four else 2, normalize=not four)
+        n = pp.run_recipe(c["recipe"], str(o_py), **kw)
+        names = sorted(os.listdir(str(o_cpp)))
+        assert names == sorted(os.listdir(str(o_py))) and n == len(names) - (1 if "-n" in flags else 0)
+        for f in names:
+            assert open(str(o_cpp / f), "rb").read() == open(str(o_py / f), "rb").read(), (flags, f)
