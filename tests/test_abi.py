@@ -177,6 +177,49 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     assert rc == 1 and "Unknown speaker b, and default speaker settings are missing." in out
 
 
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/aku") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libaku_ref.a"))),
+                    reason="needs the reference's headers and oracle/_ref/libaku_ref.a")
+def test_reference_side_plugin_compiles_and_serves_reference_modules(tmp_path):
+    """integration/GpuFrontendModule.hh -- the aku::BaseFeaModule subclass a maintainer adds to the reference -- builds
+    against the reference's own headers and library, and behaves as FeatureGenerator expects of a base module: dim /
+    rates / config round trip, eof and last_frame, at() forward, past both ends and backward, set_file on a stream, a second
+    file after reset, speaker parameters addressed to a module of the GPU chain -- with the reference's own DeltaModule computing from it (fake ABI: feature(f, d) = clamp(f) + 0.25 d)."""
+    import subprocess
+    R = "/root/reference"
+    exe = str(tmp_path / "plugin_harness")
+    subprocess.run(["g++", "-O1", "-std=gnu++11", "-DKISS_FFT", "-DDLLIMPORT=", "-fpermissive", "-w",
+                    "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + R + "/aku", "-I" + R + "/vendor/kiss_fft",
+                    "-I" + os.path.join(ROOT, "integration"), "-I" + os.path.join(ROOT, "aaltoasr_b200", "csrc", "host"),
+                    "-o", exe, os.path.join(ROOT, "tests", "cpp", "plugin_harness.cc"), os.path.join(ROOT, "tests", "cpp", "stub_akugpu.cc"),
+                    os.path.join(ROOT, "oracle", "_ref", "libaku_ref.a"), "-lm"], check=True, timeout=600)
+    cfg = str(tmp_path / "f.cfg")
+    open(cfg, "w").write("x")
+    formats.write_wav(str(tmp_path / "a.wav"), np.zeros(1280, np.int16), 16000)      # 10 frames
+    formats.write_wav(str(tmp_path / "b.wav"), np.zeros(2560, np.int16), 16000)      # 20 frames
+    r = subprocess.run([exe, cfg, str(tmp_path / "a.wav"), str(tmp_path / "b.wav"), "-"], stdout=subprocess.PIPE,
+                       input=open(str(tmp_path / "a.wav"), "rb").read(), timeout=60)
+    assert r.returncode == 0, r.stdout
+    out = r.stdout.decode().splitlines()
+    assert out[:2] == ["type gpu_frontend dim 3 rate 16000 fr 125", "config roundtrip"]
+
+    def block(n):
+        last = n - 1
+        rows = ["file last_frame %d eof(last) 0 eof(last+1) 1" % last]
+        for f in (0, 1, 5, last, last + 3, -2, 3):
+            c = min(max(f, 0), last)
+            rows.append("base %d: %g %g %g" % (f, c, c + 0.25, c + 0.5))
+        for f, d in ((-1, 0.2), (0, 0.5), (1, 0.8), (2, 1)):      # DeltaModule width 2 over clamp(f): sum k (x[t+k] - x[t-k]) / 10
+            rows.append("delta %d: %g %g %g" % (f, d, d, d))
+        return rows
+
+    extra = ["shifted 4: 6 6.25 6.5", "refused: GpuFrontendModule: parameter keys are <module>.<parameter>: value 1"]
+    assert out[2:] == block(10) + extra + block(20) + block(10)
+    bad = str(tmp_path / "c.wav")
+    formats.write_wav(bad, np.zeros(1280, np.int16), 8000)
+    r = subprocess.run([exe, cfg, bad], stdout=subprocess.PIPE, timeout=60)
+    assert r.returncode == 1 and b"Audio file sample rate (8000 Hz) and model configuration (16000 Hz) don't agree." in r.stdout
+
+
 def test_recipe_reader_three_ways(tmp_path):
     """aku::Recipe::read + sort_infos as phone_probs uses them (-B / -I / --sort-recipe, aku/phone_probs.cc:137-142): the
     C++ adapter (akugpu::Recipe), the Python mirror (formats.read_recipe / sort_recipe) and -- when oracle/_ref is built --
