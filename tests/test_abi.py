@@ -183,7 +183,8 @@ def test_reference_side_plugin_compiles_and_serves_reference_modules(tmp_path):
     """integration/GpuFrontendModule.hh -- the aku::BaseFeaModule subclass a maintainer adds to the reference -- builds
     against the reference's own headers and library, and behaves as FeatureGenerator expects of a base module: dim /
     rates / config round trip, eof and last_frame, at() forward, past both ends and backward, set_file on a stream, a second
-    file after reset, speaker parameters addressed to a module of the GPU chain -- with the reference's own DeltaModule computing from it (fake ABI: feature(f, d) = clamp(f) + 0.25 d)."""
+    file after reset, speaker parameters addressed to a module of the GPU chain, and finally the reference's literal
+    feacat on a FeatureGenerator with the one-line registration -- with the reference's own DeltaModule computing from it (fake ABI: feature(f, d) = clamp(f) + 0.25 d)."""
     import subprocess
     R = "/root/reference"
     exe = str(tmp_path / "plugin_harness")
@@ -218,6 +219,35 @@ def test_reference_side_plugin_compiles_and_serves_reference_modules(tmp_path):
     formats.write_wav(bad, np.zeros(1280, np.int16), 8000)
     r = subprocess.run([exe, cfg, bad], stdout=subprocess.PIPE, timeout=60)
     assert r.returncode == 1 and b"Audio file sample rate (8000 Hz) and model configuration (16000 Hz) don't agree." in r.stdout
+
+    # The one-line registration, applied to a scratch copy of aku/FeatureGenerator.cc (never stored in the repository),
+    # and the reference's LITERAL feacat tool on top: a reference configuration whose base module is the GPU chain and
+    # whose delta / merge modules are the reference's own.
+    src = open(R + "/aku/FeatureGenerator.cc").read()
+    marker = "    else\n      throw std::string(\"Unknown module type '\")"
+    assert src.count(marker) == 1 and src.count('#include "FeatureModules.hh"\n') == 1
+    src = src.replace('#include "FeatureModules.hh"\n', '#include "FeatureModules.hh"\n#include "GpuFrontendModule.hh"\n')
+    src = src.replace(marker, "    else if (type == GpuFrontendModule::type_str())\n      module = new GpuFrontendModule();\n" + marker)
+    patched = str(tmp_path / "FeatureGenerator_registered.cc")
+    open(patched, "w").write(src)
+    flags = ["-O1", "-std=gnu++11", "-DKISS_FFT", "-DDLLIMPORT=", "-fpermissive", "-w",
+             "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + R + "/aku", "-I" + R + "/vendor/kiss_fft",
+             "-I" + os.path.join(ROOT, "integration"), "-I" + os.path.join(ROOT, "aaltoasr_b200", "csrc", "host")]
+    feacat = str(tmp_path / "ref_feacat_with_plugin")
+    subprocess.run(["g++"] + flags + ["-o", feacat, R + "/aku/feacat.cc", patched, os.path.join(ROOT, "tests", "cpp", "stub_akugpu.cc"),
+                                      os.path.join(ROOT, "oracle", "_ref", "libaku_ref.a"), "-lm"], check=True, timeout=600)
+    ref_cfg = str(tmp_path / "ref.feaconf")
+    open(ref_cfg, "w").write("module\n{\n  name gpu\n  type gpu_frontend\n  config %s\n}\n"
+                             "module\n{\n  name d\n  type delta\n  sources gpu\n  width 2\n}\n"
+                             "module\n{\n  name m\n  type merge\n  sources gpu d\n}\n" % cfg)
+    r = subprocess.run([feacat, "-c", ref_cfg, "-s", "-1", "-e", "3", str(tmp_path / "a.wav")], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode == 0, r.stderr
+    got = np.array([[float(x) for x in ln.split()] for ln in r.stdout.decode().splitlines()])
+    want = np.array([[c, c + 0.25, c + 0.5, d, d, d] for c, d in ((0, 0.2), (0, 0.5), (1, 0.8), (2, 1.0), (3, 1.0))])
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-4
+    r = subprocess.run([feacat, "-c", ref_cfg, str(tmp_path / "b.wav")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode == 0 and len(r.stdout.decode().splitlines()) == 20          # to the end of the file: eof from the plugin
 
 
 def test_recipe_reader_three_ways(tmp_path):
