@@ -5,6 +5,7 @@
 //   frames(n_samples) = n_samples / 128         dim = 3        states = 4        16 kHz, 125 frames/s
 //   feature(f, d)     = clamp(f, 0, n-1) + 0.25 d + shift      (shift: set_parameters("shift", "value X"))
 //   lna byte(f, s, b) = (7 f + 3 s + b + 100 normalize + 50 cmllr + (int)shift) & 255     (f = frame within the utterance)
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -135,6 +136,23 @@ int akugpu_model_set_cmllr(akugpu_ctx *, const double *W)
 {
   g_cmllr = W ? 1 : 0;
   if (W) logf("set_cmllr %g %g\n", W[0], W[1]); else logf("set_cmllr none\n");
+  return 0;
+}
+
+// F64: linear likelihood of state s for a frame = (1 + x0 + x1) (s + 1) / 1000 (the test features are >= 0), floored at 1e-50;
+// F32: its logarithm.  Logged once per call.
+int akugpu_gmm_score(akugpu_ctx *, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)
+{
+  logf("gmm_score frames=%lld precision=%d\n", (long long)n_frames, precision);
+  if (!feats_f64) { g_err = "stub: double features only"; return AKUGPU_E_ARG; }
+  const int D = akugpu_model_dim(NULL);
+  const double *x = (const double *)feats;
+  for (int64_t f = 0; f < n_frames; f++)
+    for (int s = 0; s < 4; s++) {
+      double lik = (1 + x[f * D] + x[f * D + 1]) * (s + 1) / 1000.0;
+      if (lik < 1e-50) lik = 1e-50;
+      if (precision == AKUGPU_F64) ((double *)out)[f * 4 + s] = lik; else ((float *)out)[f * 4 + s] = (float)log(lik);
+    }
   return 0;
 }
 

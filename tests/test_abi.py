@@ -250,6 +250,79 @@ def test_reference_side_plugin_compiles_and_serves_reference_modules(tmp_path):
     assert r.returncode == 0 and len(r.stdout.decode().splitlines()) == 20          # to the end of the file: eof from the plugin
 
 
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/aku") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libaku_ref.a"))),
+                    reason="needs the reference's sources and oracle/_ref/libaku_ref.a")
+def test_reference_phone_probs_runs_unmodified_on_plugin_and_hook(tmp_path):
+    """The reference's LITERAL phone_probs main, linked with scratch copies of aku/FeatureGenerator.cc (+ the one-line
+    registration of integration/GpuFrontendModule.hh) and aku/HmmSet.cc (+ the two hook lines of
+    integration/GpuHmmSetHook.hh): with AKUGPU_HOOK=1 every frame's features and state likelihoods come from the C ABI
+    (here its fake: closed forms), the reference's own loop normalises and quantises them, and the LNA file equals the
+    oracle's encoding of those likelihoods; without the variable the same binary is the CPU tool."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import oracle_np
+    R = "/root/reference"
+    fg = open(R + "/aku/FeatureGenerator.cc").read()
+    marker = "    else\n      throw std::string(\"Unknown module type '\")"
+    fg = fg.replace('#include "FeatureModules.hh"\n', '#include "FeatureModules.hh"\n#include "GpuFrontendModule.hh"\n')
+    fg = fg.replace(marker, "    else if (type == GpuFrontendModule::type_str())\n      module = new GpuFrontendModule();\n" + marker)
+    hs = open(R + "/aku/HmmSet.cc").read()
+    a = '  read_gk(base + ".gk");\n}\n'
+    b = "  // Precompute base distribution likelihoods\n  m_pool.precompute_likelihoods(*f.get_vector());\n"
+    assert hs.count(a) == 1 and hs.count(b) == 1
+    hs = hs.replace('#include "HmmSet.hh"\n', '#include "HmmSet.hh"\n#include "GpuHmmSetHook.hh"\n')
+    hs = hs.replace(a, '  read_gk(base + ".gk");\n  akugpu_hook::attach(this, base);\n}\n')
+    hs = hs.replace(b, "  if (akugpu_hook::score(this, *f.get_vector(), m_pdf_likelihoods, m_valid_pdf_likelihoods)) return;\n" + b)
+    open(str(tmp_path / "FeatureGenerator_registered.cc"), "w").write(fg)
+    open(str(tmp_path / "HmmSet_hooked.cc"), "w").write(hs)
+    flags = ["-O1", "-std=gnu++11", "-DKISS_FFT", "-DDLLIMPORT=", "-fpermissive", "-w",
+             "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + R + "/aku", "-I" + R + "/vendor/kiss_fft",
+             "-I" + os.path.join(ROOT, "integration"), "-I" + os.path.join(ROOT, "aaltoasr_b200", "csrc", "host")]
+    exe = str(tmp_path / "ref_phone_probs_gpu")
+    subprocess.run(["g++"] + flags + ["-o", exe, R + "/aku/phone_probs.cc", str(tmp_path / "FeatureGenerator_registered.cc"),
+                                      str(tmp_path / "HmmSet_hooked.cc"), os.path.join(ROOT, "tests", "cpp", "stub_akugpu.cc"),
+                                      os.path.join(ROOT, "oracle", "_ref", "libaku_ref.a"), "-lm"], check=True, timeout=900)
+    inner = str(tmp_path / "inner.cfg")
+    open(inner, "w").write("x")
+    cfg = str(tmp_path / "ref.feaconf")
+    open(cfg, "w").write("module\n{\n  name gpu\n  type gpu_frontend\n  config %s\n}\n" % inner)
+    rng = np.random.default_rng(3)
+    base = str(tmp_path / "m")
+    model = dict(mix_offsets=np.arange(5, dtype=np.int32), mix_gauss=np.arange(4, dtype=np.int32), mix_weight=np.ones(4),
+                 means=rng.standard_normal((4, 3)) + 3, covs=rng.uniform(0.5, 2, (4, 3)))
+    formats.write_model(base, **model)
+    wav = str(tmp_path / "a.wav")
+    formats.write_wav(wav, np.zeros(1280, np.int16), 16000)           # 10 frames
+    rec = str(tmp_path / "r")
+    open(rec, "w").write("audio=%s lna=a.lna\n" % wav)
+    env = dict(os.environ)
+    out = {}
+    for hook in ("1", ""):
+        log = str(tmp_path / ("log" + hook))
+        od = tmp_path / ("o" + hook)
+        od.mkdir()
+        env["AKUGPU_STUB_LOG"] = log
+        env["AKUGPU_HOOK"] = hook
+        r = subprocess.run([exe, "-b", base, "-c", cfg, "-r", rec, "-o", str(od)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           env=env, timeout=120)
+        assert r.returncode == 0, r.stderr
+        out[hook] = (open(str(od / "a.lna"), "rb").read(), open(log).read().splitlines())
+    blob, log = out["1"]
+    assert log.count("gmm_score frames=1 precision=1") == 10 and "model_read " + base in log        # one call per frame, F64
+    f = np.arange(10, dtype=np.float64)
+    lik = ((1 + f + (f + 0.25))[:, None] * (np.arange(4) + 1)[None, :]) / 1000.0
+    want, _ = oracle_np.lna_records(lik, 2)
+    assert blob[:5] == b"\x00\x00\x00\x04\x02" and blob[5:] == want.tobytes()
+    blob0, log0 = out[""]
+    assert not any(ln.startswith("gmm_score") or ln.startswith("model_read") for ln in log0)        # CPU tool: the library is not asked
+    assert len(blob0) == len(blob) and blob0 != blob
+    # the CPU path of the same binary is the reference's arithmetic: the oracle on the plugin's features
+    feats = np.stack([f, f + 0.25, f + 0.5], axis=1)
+    want0, _ = oracle_np.lna_records(oracle_np.state_likelihoods(model, feats), 2)
+    assert blob0[5:] == want0.tobytes()
+
+
 def test_recipe_reader_three_ways(tmp_path):
     """aku::Recipe::read + sort_infos as phone_probs uses them (-B / -I / --sort-recipe, aku/phone_probs.cc:137-142): the
     C++ adapter (akugpu::Recipe), the Python mirror (formats.read_recipe / sort_recipe) and -- when oracle/_ref is built --
