@@ -23,6 +23,7 @@
 #include "BaseFeaModule.hh"
 #include "ModuleConfig.hh"
 #include "akugpu.hh"        // aaltoasr_b200/csrc/host: read_audio, check, the C ABI
+#include "GpuHmmSetHook.hh" // publish_utterance: lets the HmmSet hook score the whole utterance in one call
 
 namespace aku {
 
@@ -47,7 +48,8 @@ public:
     akugpu::parse_audio(bytes, "<stream>", sample_rate(), false, m_pcm, rate);
     open_pcm(rate);
   }
-  virtual void discard_file(void) { m_pcm.clear(); m_feats.clear(); m_frames = 0; }
+  virtual void discard_file(void) { m_pcm.clear(); m_feats.clear(); m_frames = 0; akugpu_hook::publish_utterance(NULL, 0, 0); }
+  virtual ~GpuFrontendModule() { if (akugpu_hook::current_utterance().feats == m_feats.data()) akugpu_hook::publish_utterance(NULL, 0, 0); }
   virtual bool eof(int frame) { return frame >= m_frames; }
   virtual int sample_rate(void) { return akugpu_frontend_sample_rate(m_engine.ctx()); }
   virtual float frame_rate(void) { return akugpu_frontend_frame_rate(m_engine.ctx()); }
@@ -123,6 +125,7 @@ private:
     m_frames = (int)fo[1];
     m_feats.resize((size_t)m_frames * m_dim);
     if (m_frames > 0) akugpu::check(m_engine.ctx(), akugpu_features(m_engine.ctx(), m_pcm.data(), uo, 1, m_feats.data(), 1, fo));
+    akugpu_hook::publish_utterance(m_feats.data(), m_frames, m_dim);
     reset();                           // the ring buffer of at() holds frames of the previous file / parameters
   }
 

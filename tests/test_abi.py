@@ -296,30 +296,39 @@ def test_reference_phone_probs_runs_unmodified_on_plugin_and_hook(tmp_path):
     formats.write_wav(wav, np.zeros(1280, np.int16), 16000)           # 10 frames
     rec = str(tmp_path / "r")
     open(rec, "w").write("audio=%s lna=a.lna\n" % wav)
+    cfg_t = str(tmp_path / "ref_t.feaconf")          # a CPU-side reference module after the GPU module
+    open(cfg_t, "w").write(open(cfg).read() + "module\n{\n  name t\n  type lin_transform\n  sources gpu\n  bias 1 0 0\n}\n")
     env = dict(os.environ)
     out = {}
-    for hook in ("1", ""):
-        log = str(tmp_path / ("log" + hook))
-        od = tmp_path / ("o" + hook)
+    for tag, hook, c in (("gpu", "1", cfg), ("cpu", "", cfg), ("gpu_t", "1", cfg_t)):
+        log = str(tmp_path / ("log_" + tag))
+        od = tmp_path / ("o_" + tag)
         od.mkdir()
         env["AKUGPU_STUB_LOG"] = log
         env["AKUGPU_HOOK"] = hook
-        r = subprocess.run([exe, "-b", base, "-c", cfg, "-r", rec, "-o", str(od)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                           env=env, timeout=120)
+        r = subprocess.run([exe, "-b", base, "-c", c, "-r", rec, "-o", str(od), "-N"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           env=env, timeout=120)          # -N: the fake's likelihoods differ between frames only before normalisation
         assert r.returncode == 0, r.stderr
-        out[hook] = (open(str(od / "a.lna"), "rb").read(), open(log).read().splitlines())
-    blob, log = out["1"]
-    assert log.count("gmm_score frames=1 precision=1") == 10 and "model_read " + base in log        # one call per frame, F64
+        out[tag] = (open(str(od / "a.lna"), "rb").read(), open(log).read().splitlines())
     f = np.arange(10, dtype=np.float64)
+    # vectors straight from the GPU module: the hook scores the whole utterance in ONE call, then serves the frames
+    blob, log = out["gpu"]
+    assert [ln for ln in log if ln.startswith("gmm_score")] == ["gmm_score frames=10 precision=1"] and "model_read " + base in log
     lik = ((1 + f + (f + 0.25))[:, None] * (np.arange(4) + 1)[None, :]) / 1000.0
-    want, _ = oracle_np.lna_records(lik, 2)
+    want, _ = oracle_np.lna_records(lik, 2, normalize=False)
     assert blob[:5] == b"\x00\x00\x00\x04\x02" and blob[5:] == want.tobytes()
-    blob0, log0 = out[""]
+    # vectors changed by a CPU module downstream: the single-frame path, one call per frame
+    blob_t, log_t = out["gpu_t"]
+    assert [ln for ln in log_t if ln.startswith("gmm_score")] == ["gmm_score frames=1 precision=1"] * 10
+    lik_t = ((1 + (f + 1) + (f + 0.25))[:, None] * (np.arange(4) + 1)[None, :]) / 1000.0
+    want_t, _ = oracle_np.lna_records(lik_t, 2, normalize=False)
+    assert blob_t[5:] == want_t.tobytes() and blob_t != blob
+    blob0, log0 = out["cpu"]
     assert not any(ln.startswith("gmm_score") or ln.startswith("model_read") for ln in log0)        # CPU tool: the library is not asked
     assert len(blob0) == len(blob) and blob0 != blob
     # the CPU path of the same binary is the reference's arithmetic: the oracle on the plugin's features
     feats = np.stack([f, f + 0.25, f + 0.5], axis=1)
-    want0, _ = oracle_np.lna_records(oracle_np.state_likelihoods(model, feats), 2)
+    want0, _ = oracle_np.lna_records(oracle_np.state_likelihoods(model, feats), 2, normalize=False)
     assert blob0[5:] == want0.tobytes()
 
 
