@@ -40,4 +40,38 @@ g++ -O2 -o "$OUT/ref_feacat" "$OUT/obj/feacat.o" "$OUT/libaku_ref.a" -lm
 g++ -O2 -fPIC -w -I"$R/decoder/src" -c "$R/decoder/src/LnaReaderCircular.cc" -o "$OUT/obj/LnaReaderCircular.o"
 # Thin C-callable view of the reference classes for pytest (oracle/ref_capi.cc is ours).
 g++ $CXXFLAGS -I"$R/decoder/src" -shared -o "$OUT/libref_capi.so" "$HERE/ref_capi.cc" "$OUT/obj/LnaReaderCircular.o" "$OUT/libaku_ref.a" -lm
-echo "oracle/_ref built: ref_phone_probs ref_feacat libref_capi.so"
+# The reference's LITERAL tools on the GPU library: scratch copies of aku/FeatureGenerator.cc (+ the one-line registration
+# of integration/GpuFrontendModule.hh) and aku/HmmSet.cc (+ the two hook lines of integration/GpuHmmSetHook.hh), written
+# to oracle/_ref/obj only, linked with the unmodified phone_probs.o / feacat.o and the in-tree libakugpu.so.  They run
+# as the CPU tools unless a configuration uses `type gpu_frontend` / the environment has AKUGPU_HOOK=1.
+LIBAKU="$HERE/../aaltoasr_b200/libakugpu.so"
+if [ -f "$LIBAKU" ]; then
+  python3 - "$R" "$OUT/obj" <<'PY'
+import sys
+R, obj = sys.argv[1], sys.argv[2]
+fg = open(R + "/aku/FeatureGenerator.cc").read()
+marker = "    else\n      throw std::string(\"Unknown module type '\")"
+assert fg.count(marker) == 1
+fg = fg.replace('#include "FeatureModules.hh"\n', '#include "FeatureModules.hh"\n#include "GpuFrontendModule.hh"\n', 1)
+fg = fg.replace(marker, "    else if (type == GpuFrontendModule::type_str())\n      module = new GpuFrontendModule();\n" + marker)
+hs = open(R + "/aku/HmmSet.cc").read()
+a = '  read_gk(base + ".gk");\n}\n'
+b = "  // Precompute base distribution likelihoods\n  m_pool.precompute_likelihoods(*f.get_vector());\n"
+assert hs.count(a) == 1 and hs.count(b) == 1
+hs = hs.replace('#include "HmmSet.hh"\n', '#include "HmmSet.hh"\n#include "GpuHmmSetHook.hh"\n', 1)
+hs = hs.replace(a, '  read_gk(base + ".gk");\n  akugpu_hook::attach(this, base);\n}\n')
+hs = hs.replace(b, "  if (akugpu_hook::score(this, *f.get_vector(), m_pdf_likelihoods, m_valid_pdf_likelihoods)) return;\n" + b)
+open(obj + "/FeatureGenerator_registered.cc", "w").write(fg)
+open(obj + "/HmmSet_hooked.cc", "w").write(hs)
+PY
+  GPUFLAGS="$CXXFLAGS -I$HERE/../integration -I$HERE/../aaltoasr_b200/csrc/host"
+  g++ $GPUFLAGS -c "$OUT/obj/FeatureGenerator_registered.cc" -o "$OUT/obj/FeatureGenerator_registered.o" &
+  g++ $GPUFLAGS -c "$OUT/obj/HmmSet_hooked.cc" -o "$OUT/obj/HmmSet_hooked.o" &
+  wait
+  rm -f "$OUT/obj/FeatureGenerator_registered.cc" "$OUT/obj/HmmSet_hooked.cc"
+  for t in phone_probs feacat; do
+    g++ -O2 -o "$OUT/ref_${t}_gpu" "$OUT/obj/$t.o" "$OUT/obj/FeatureGenerator_registered.o" "$OUT/obj/HmmSet_hooked.o" \
+        "$OUT/libaku_ref.a" -L"$HERE/../aaltoasr_b200" -lakugpu -Wl,-rpath,'$ORIGIN/../../aaltoasr_b200' -lm
+  done
+fi
+echo "oracle/_ref built: ref_phone_probs ref_feacat libref_capi.so$([ -f "$OUT/ref_phone_probs_gpu" ] && echo ' ref_phone_probs_gpu ref_feacat_gpu')"

@@ -332,6 +332,29 @@ def test_reference_phone_probs_runs_unmodified_on_plugin_and_hook(tmp_path):
     assert blob0[5:] == want0.tobytes()
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_feacat_gpu")), reason="oracle/_ref not built")
+def test_prebuilt_reference_tools_on_the_library(aku_tests, tmp_path):
+    """oracle/_ref/ref_feacat_gpu / ref_phone_probs_gpu = the reference's literal tools with the plugin registered and the
+    hook in place, linked against the real libakugpu.so (oracle/build_ref.sh).  Without a `gpu_frontend` module they ARE
+    the CPU tools (same bytes as ref_feacat); with one they need the device and say so."""
+    import subprocess
+    import torch
+    wav = str(tmp_path / "short.wav")
+    formats.write_wav(wav, aku_tests["short_wav"], int(aku_tests["sample_rate"]))
+    cfg = str(tmp_path / "mfcc_p_dd.feaconf")
+    open(cfg, "w").write(aku_tests["mfcc_p_dd_cfg"])
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    outs = [subprocess.run([os.path.join(ref_dir, exe), "-c", cfg, "-s", "-10", "-e", "80", wav], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, timeout=120) for exe in ("ref_feacat", "ref_feacat_gpu")]
+    assert outs[0].returncode == 0 and outs[1].returncode == 0 and outs[0].stdout == outs[1].stdout and len(outs[0].stdout) > 1000
+    if torch.cuda.is_available():
+        return
+    gcfg = str(tmp_path / "gpu.feaconf")
+    open(gcfg, "w").write("module\n{\n  name gpu\n  type gpu_frontend\n  config %s\n}\n" % cfg)
+    r = subprocess.run([os.path.join(ref_dir, "ref_feacat_gpu"), "-c", gcfg, wav], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"no CPU fallback" in r.stderr
+
+
 def test_recipe_reader_three_ways(tmp_path):
     """aku::Recipe::read + sort_infos as phone_probs uses them (-B / -I / --sort-recipe, aku/phone_probs.cc:137-142): the
     C++ adapter (akugpu::Recipe), the Python mirror (formats.read_recipe / sort_recipe) and -- when oracle/_ref is built --
