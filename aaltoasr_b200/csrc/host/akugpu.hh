@@ -129,6 +129,29 @@ public:
     }
     open_pcm();
   }
+  // FeatureGenerator::open(FILE*, dont_fclose, stream) / open_fd (aku/FeatureGenerator.cc:55-83): the stream is read
+  // to its end here (the library computes whole utterances); open_fd ignores its raw flag like the reference's does.
+  void open(FILE *file, bool dont_fclose = false, bool /*stream*/ = false) {
+    std::vector<unsigned char> b;
+    unsigned char buf[65536];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof buf, file)) > 0) b.insert(b.end(), buf, buf + k);
+    if (!dont_fclose) fclose(file);
+    m_rows.clear();
+    int rate = 0;
+    parse_audio(b, "<stream>", sample_rate(), false, m_pcm, rate);
+    if (rate != sample_rate()) {
+      char msg[256];
+      snprintf(msg, sizeof msg, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree.", rate, sample_rate());
+      throw std::string(msg);
+    }
+    open_pcm();
+  }
+  void open_fd(int fd, bool /*raw_audio*/ = false) {
+    FILE *file = fdopen(fd, "rb");
+    if (file == NULL) throw std::string("could not open fd ") + ": " + strerror(errno);
+    open(file, false, false);
+  }
   void open_pcm(const std::vector<int16_t> &pcm) { m_pcm = pcm; open_pcm(); }
   void close() { m_pcm.clear(); m_feats.clear(); m_frames = 0; }
   // Feature vector of `frame` (doubles, like aku::FeatureVec); valid until the next generate().

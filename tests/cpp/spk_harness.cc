@@ -15,6 +15,31 @@ int akugpu_frontend_set_parameters(akugpu_ctx *, const char *module, const char 
   printf("feature %s\n%s.\n", module, text);
   return 0;
 }
+// feature stub for the FeatureGenerator adapter: frames = samples / 128, feature(f, d) = clamp(f) + 0.25 d
+int akugpu_frontend_load_config(akugpu_ctx *, const char *) { return 0; }
+int akugpu_frontend_dim(akugpu_ctx *) { return 3; }
+int akugpu_frontend_sample_rate(akugpu_ctx *) { return 16000; }
+int akugpu_frontend_base_is_pre(akugpu_ctx *) { return 0; }
+int akugpu_features(akugpu_ctx *, const int16_t *, const int64_t *uo, int n_utts, void *out, int f64, int64_t *fo)
+{
+  fo[0] = 0;
+  for (int u = 0; u < n_utts; u++) fo[u + 1] = fo[u] + (uo[u + 1] - uo[u]) / 128;
+  if (out && f64)
+    for (int64_t f = 0; f < fo[n_utts]; f++) for (int d = 0; d < 3; d++) ((double *)out)[f * 3 + d] = f + 0.25 * d;
+  return 0;
+}
+int akugpu_features_range(akugpu_ctx *, const int16_t *, int64_t n_samples, int start, int end, const char *, void *out, int,
+                          int *dim_out)
+{
+  if (dim_out) *dim_out = 3;
+  const int64_t n = n_samples / 128;
+  for (int f = start; out && f < end; f++)
+    for (int d = 0; d < 3; d++) ((double *)out)[(size_t)(f - start) * 3 + d] = (f < 0 ? 0 : (f >= n ? n - 1 : f)) + 0.25 * d;
+  return 0;
+}
+int akugpu_features_pre(akugpu_ctx *, const float *, const int64_t *, int, void *, int, int64_t *) { return -1; }
+int akugpu_features_pre_range(akugpu_ctx *, const float *, int64_t, int, int, const char *, void *, int, int *) { return -1; }
+
 // scoring stub: S = 3 states; linear likelihood (F64) or log-likelihood (F32) of state s for a frame = f(frame sum, s)
 static int g_score_calls = 0;
 int akugpu_model_num_states(akugpu_ctx *) { return 3; }
@@ -55,6 +80,28 @@ int main(int argc, char **argv)
       long long sum = 0;
       for (size_t i = 0; i < pcm.size(); i++) sum += (long long)pcm[i] * (long long)(i % 97 + 1);
       printf("%zu %d %lld\n", pcm.size(), rate, sum);
+    } catch (std::string &s) {
+      printf("exception: %s\n", s.c_str());
+      return 1;
+    }
+    return 0;
+  }
+  if (std::string(argv[1]) == "fgopen") {      // spk_harness fgopen PATH: akugpu::FeatureGenerator::open(FILE*) / open_fd / open
+    try {
+      g_dim = 3;
+      akugpu::Engine eng(0);
+      akugpu::FeatureGenerator gen(eng);
+      gen.load_configuration("stub.cfg");
+      FILE *fp = fopen(argv[2], "rb");
+      gen.open(fp, true);
+      printf("FILE* %d frames, f(3,1)=%g\n", gen.num_frames(), gen.generate(3)[1]);
+      fclose(fp);                              // dont_fclose: still ours
+      gen.open_fd(open(argv[2], O_RDONLY));
+      printf("fd %d frames, eof(last)=%d", gen.num_frames(), (gen.generate(gen.last_frame()), (int)gen.eof()));
+      gen.generate(gen.last_frame() + 1);
+      printf(" eof(last+1)=%d\n", (int)gen.eof());
+      gen.open(argv[2]);
+      printf("path %d frames\n", gen.num_frames());
     } catch (std::string &s) {
       printf("exception: %s\n", s.c_str());
       return 1;

@@ -130,6 +130,17 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     r = subprocess.run([exe, "audio", str(tmp_path / "s.wav"), "16000", "0"], stdout=subprocess.PIPE, timeout=60)
     assert r.returncode == 1 and b"multiple channels not supported" in r.stdout
 
+    # akugpu::FeatureGenerator: open(FILE*, dont_fclose) / open_fd / open(path) on the same file
+    w16 = str(tmp_path / "a16.wav")
+    formats.write_wav(w16, pcm, 16000)
+    r = subprocess.run([exe, "fgopen", w], stdout=subprocess.PIPE, timeout=60)           # the 8 kHz file: refused like the reference does
+    assert r.returncode == 1 and b"Audio file sample rate (8000 Hz) and model configuration (16000 Hz) don't agree." in r.stdout
+    r = subprocess.run([exe, "fgopen", w16], stdout=subprocess.PIPE, timeout=60)
+    assert r.returncode == 0 and r.stdout.decode().splitlines() == ["FILE* 31 frames, f(3,1)=3.25", "fd 31 frames, eof(last)=0 eof(last+1)=1",
+                                                                    "path 31 frames"], r.stdout
+    r = subprocess.run([exe, "fgopen", str(tmp_path / "a.raw")], stdout=subprocess.PIPE, timeout=60)      # headerless: read as raw PCM16
+    assert r.returncode == 0 and r.stdout.decode().splitlines()[0].startswith("FILE* 31 frames")
+
     # akugpu::HmmSet: the reference's per-vector signatures over one GPU call per reset_cache() (stubbed scorer, 3 states)
     for prec in ("f64", "f32"):
         r = subprocess.run([exe, "hmm", prec], stdout=subprocess.PIPE, timeout=60)
