@@ -366,6 +366,202 @@ def test_prebuilt_reference_tools_on_the_library(aku_tests, tmp_path):
     assert r.returncode != 0 and b"no CPU fallback" in r.stderr
 
 
+def test_library_model_readers_on_the_cpu(ref_small, ref_edge, ref_full, ref_clust, tmp_path):
+    """The library's own .gk / .mc / .ph and .gcl readers (csrc/model.cu, pure host code exported from libakugpu.so) run
+    without a device: what they read equals the arrays the files were written from (weights normalised like
+    Mixture::normalize_weights, full covariances, the .gcl reader's repeated last pair and the moment-matched centres
+    of the oracle), the sizes agree with the reference's HmmSet on the same files, and malformed files end in an error
+    that names the problem -- never in a crash."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import oracle_np, ref
+    exe = str(tmp_path / "model_harness")
+    libdir = os.path.join(ROOT, "aaltoasr_b200")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-I/usr/local/cuda/include", "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "model_harness.cc"), "-L" + libdir, "-lakugpu", "-Wl,-rpath," + libdir],
+                   check=True, timeout=300)
+
+    def load(path, dtypes):
+        b, pos, out = open(path, "rb").read(), 0, []
+        for dt in dtypes:
+            n = int(np.frombuffer(b, "<i8", 1, pos)[0])
+            pos += 8
+            out.append(np.frombuffer(b, dt, n, pos))
+            pos += n * np.dtype(dt).itemsize
+        assert pos == len(b)
+        return out
+
+    for k, g in enumerate((ref_small, ref_edge, ref_full)):
+        m = g["model"]
+        base = str(tmp_path / ("m%d" % k))
+        formats.write_model(base, **m)
+        r = subprocess.run([exe, "read", base, base + ".bin"], stdout=subprocess.PIPE, timeout=60)
+        assert r.returncode == 0, r.stdout
+        hdr, off, idx, w, mean, cov, fidx, fcov = load(base + ".bin", ["<i4", "<i4", "<i4", "<f8", "<f8", "<f8", "<i4", "<f8"])
+        G, D = m["means"].shape
+        S = len(m["mix_offsets"]) - 1
+        full = np.asarray(m["full_mask"], dtype=bool) if "full_mask" in m else np.zeros(G, dtype=bool)
+        assert list(hdr) == [S, G, D, int(full.sum())]
+        assert np.array_equal(off, m["mix_offsets"]) and np.array_equal(idx, m["mix_gauss"])
+        want_w = np.asarray(m["mix_weight"], dtype=np.float64).copy()
+        for s_ in range(S):
+            a, b = m["mix_offsets"][s_], m["mix_offsets"][s_ + 1]
+            tot = 0.0
+            for v in want_w[a:b]:
+                tot += v
+            want_w[a:b] /= tot
+        assert np.array_equal(w, want_w)
+        assert np.array_equal(mean.reshape(G, D), m["means"])
+        if "covs" in m:
+            assert np.array_equal(cov.reshape(G, D)[~full], np.asarray(m["covs"])[~full])
+        if full.any():
+            assert np.array_equal(fidx >= 0, full)
+            assert np.array_equal(fcov.reshape(-1, D, D), np.asarray(m["full_covs"])[full])
+        if ref.available():
+            M = ref.Model(base)
+            assert (M.S, M.G, M.D) == (S, G, D)
+            M.close()
+    # clustering file: pairs as the reference's loop reads them, centres as the oracle merges them
+    m = ref_clust["model"]
+    base = str(tmp_path / "mc")
+    formats.write_model(base, **m)
+    gcl = str(tmp_path / "c.gcl")
+    open(gcl, "w").write(ref_clust["gcl"])
+    r = subprocess.run([exe, "gcl", base, gcl, base + ".bin"], stdout=subprocess.PIPE, timeout=60)
+    assert r.returncode == 0, r.stdout
+    hdr, g2c, sizes, cmean, ccov = load(base + ".bin", ["<i4", "<i4", "<i4", "<f8", "<f8"])
+    n, gi, ci = oracle_np.parse_clustering(ref_clust["gcl"])
+    cm, cc, members = oracle_np.cluster_centers(m, n, gi, ci)
+    assert hdr[0] == n == 12 and list(sizes) == [len(L) for L in members] and sum(sizes) == len(gi)      # incl. the repeated last pair
+    want_g2c = np.full(m["means"].shape[0], -1)
+    for c, L in enumerate(members):
+        want_g2c[L] = c
+    assert np.array_equal(g2c, want_g2c) and (g2c < 0).sum() == 3
+    assert np.allclose(cmean.reshape(n, -1), cm, rtol=1e-14, atol=0) and np.allclose(ccov.reshape(n, -1), cc, rtol=1e-13, atol=0)
+    # malformed files
+    base = str(tmp_path / "bad")
+    formats.write_model(base, **ref_small["model"])
+    orig = {e: open(base + e).read() for e in (".gk", ".mc", ".ph")}
+    gk, mc = orig[".gk"].splitlines(), orig[".mc"].splitlines()
+    cases = [(".gk", "\n".join(gk[:5]) + "\n", "unexpected end of file"),
+             (".gk", "\n".join(gk[:3] + [" ".join(gk[3].split()[:20])] + gk[4:]) + "\n", "expected number"),
+             (".gk", "\n".join([gk[0], gk[1].replace("diag", "foo")] + gk[2:]) + "\n", "Unknown model type"),
+             (".gk", "x y z\n" + "\n".join(gk[1:]) + "\n", "expected integer"),
+             (".gk", "", "expected integer"),
+             (".mc", "\n".join([mc[0], "1 99999 1.0"] + mc[2:]) + "\n", "refers to Gaussian 99999 of 96"),
+             (".mc", "\n".join(mc[:3]) + "\n", "expected integer"),
+             (".ph", None, "could not open"),
+             (".ph", "HELLO\n" + "\n".join(orig[".ph"].splitlines()[1:]) + "\n", "first token is not PHONE")]
+    for ext, text, msg in cases:
+        for e in orig:
+            open(base + e, "w").write(orig[e])
+        if text is None:
+            os.remove(base + ext)
+        else:
+            open(base + ext, "w").write(text)
+        r = subprocess.run([exe, "read", base, base + ".bin"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+        assert r.returncode == 1 and r.stdout.startswith(b"error -") and msg.encode() in r.stdout, (ext, msg, r.returncode, r.stdout)
+    for e in orig:
+        open(base + e, "w").write(orig[e])
+    for text, msg in (("99\n0 0\n", "seems insensible"), ("2\n0 0\n5000 1\n", "Gauss index out of bounds"), ("2\n0 7\n", "out of bounds")):
+        open(gcl, "w").write(text)
+        r = subprocess.run([exe, "gcl", base, gcl, base + ".bin"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+        assert r.returncode == 1 and msg.encode() in r.stdout, (text, r.returncode, r.stdout)
+
+
+def test_library_expanded_form_and_slot_tables_on_the_cpu(ref_small, ref_edge, ref_full, tmp_path):
+    """Host mathematics of the tensor-core packers, run on the CPU from libakugpu.so: tc_expanded_params (csrc/gmm_tc.cu)
+    -- <expand(x - c), theta_g> + gconst_g reproduces every Gaussian's log-likelihood (diagonal: the oracle's; full: the
+    reference's exponential form) and q_g is the cancelling magnitude the conditioning guard is built on -- and
+    tc_build_slots: every component in exactly one slot, states contiguous, never across a warp's group of slots."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import oracle_np
+    exe = str(tmp_path / "model_harness")
+    libdir = os.path.join(ROOT, "aaltoasr_b200")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-I/usr/local/cuda/include", "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "model_harness.cc"), "-L" + libdir, "-lakugpu", "-Wl,-rpath," + libdir],
+                   check=True, timeout=300)
+
+    def load(path, dtypes):
+        b, pos, out = open(path, "rb").read(), 0, []
+        for dt in dtypes:
+            n = int(np.frombuffer(b, "<i8", 1, pos)[0])
+            pos += 8
+            out.append(np.frombuffer(b, dt, n, pos))
+            pos += n * np.dtype(dt).itemsize
+        assert pos == len(b)
+        return out
+
+    # diagonal pools
+    for k, g in enumerate((ref_small, ref_edge)):
+        m = g["model"]
+        base = str(tmp_path / ("d%d" % k))
+        formats.write_model(base, **m)
+        assert subprocess.run([exe, "expand", base, base + ".bin"], timeout=60).returncode == 0
+        cen, theta, gconst, q, qmax = load(base + ".bin", ["<f8"] * 5)
+        G, D = m["means"].shape
+        theta = theta.reshape(G, 2 * D)
+        prec, cst = oracle_np.gaussian_params(m["means"], m["covs"])
+        mc = m["means"] - cen[None, :]
+        assert np.allclose(q, 0.5 * (prec * mc * mc).sum(axis=1), rtol=1e-12) and qmax[0] == q.max()
+        x = g["feats"][::7]
+        y = x - cen[None, :]
+        ll = np.concatenate([y * y, y], axis=1) @ theta.T + gconst[None, :]
+        want = oracle_np._diag_loglik(x, m["means"], prec, cst)
+        ok = np.isfinite(want) & (np.abs(want) < 1e6)
+        assert ok.mean() > 0.9
+        assert (np.abs(ll - want)[ok] <= 1e-9 * (1 + np.abs(want[ok]) + q[None, :].repeat(x.shape[0], 0)[ok])).all()
+        if k == 0:
+            assert qmax[0] < 200          # the synthetic "realistic" model is well inside the guard (TC_Q_MAX)
+        else:
+            assert qmax[0] > 200          # the edge model is what the hybrid split exists for
+    # an all-full pool: the reference's exponential form around the centre
+    m = ref_full["model"]
+    idx = np.nonzero(m["full_mask"])[0]
+    base = str(tmp_path / "f")
+    off = np.arange(0, len(idx) + 1, 3, dtype=np.int32)
+    formats.write_model(base, off, np.arange(len(idx), dtype=np.int32), np.ones(len(idx)), m["means"][idx],
+                        full_covs=np.asarray(m["full_covs"])[idx])
+    assert subprocess.run([exe, "expand", base, base + ".bin"], timeout=60).returncode == 0
+    cen, theta, gconst, q, qmax = load(base + ".bin", ["<f8"] * 5)
+    D = m["means"].shape[1]
+    L = D * (D + 3) // 2
+    theta = theta.reshape(len(idx), L)
+    x = ref_full["feats"][::9]
+    phi = oracle_np.exponential_feature(x - cen[None, :])
+    ll = phi @ theta.T + gconst[None, :]
+    for j, gi in enumerate(idx[:12]):
+        cov = np.asarray(m["full_covs"][gi], dtype=np.float64)
+        P = np.linalg.inv(cov)
+        d = x - m["means"][gi][None, :]
+        want = -0.5 * np.einsum("fi,ij,fj->f", d, P, d) + 0.5 * np.linalg.slogdet(P)[1]
+        assert np.abs(ll[:, j] - want).max() <= 1e-7 * (1 + np.abs(want).max() + q[j])
+    # slot tables (16 components per slot; a warp owns `group` consecutive slots of a tile)
+    m = ref_edge["model"]
+    base = str(tmp_path / "d1")
+    S = len(m["mix_offsets"]) - 1
+    for group in (4, 8):
+        assert subprocess.run([exe, "slots", base, str(group), base + ".slots"], timeout=60).returncode == 0
+        t = load(base + ".slots", ["<i4"] * 6)
+        for (st, k0, fl), skipped in ((t[:3], set()), (t[3:], set(range(0, S, 5)))):
+            seen = {}
+            for i, s_ in enumerate(st):
+                if s_ < 0:
+                    assert fl[i] == 3
+                    continue
+                seen.setdefault(int(s_), []).append(i)
+            assert set(seen) == set(range(S)) - skipped
+            for s_, slots in seen.items():
+                K = m["mix_offsets"][s_ + 1] - m["mix_offsets"][s_]
+                assert slots == list(range(slots[0], slots[0] + len(slots))) and len(slots) == max(1, -(-K // 16))
+                assert slots[0] // group == slots[-1] // group                      # no state straddles a warp's group
+                assert [int(k0[i]) for i in slots] == [16 * j for j in range(len(slots))]
+                assert [int(fl[i]) for i in slots] == [((j == 0) << 1) | (j == len(slots) - 1) for j in range(len(slots))]
+
+
 def test_recipe_reader_three_ways(tmp_path):
     """aku::Recipe::read + sort_infos as phone_probs uses them (-B / -I / --sort-recipe, aku/phone_probs.cc:137-142): the
     C++ adapter (akugpu::Recipe), the Python mirror (formats.read_recipe / sort_recipe) and -- when oracle/_ref is built --
