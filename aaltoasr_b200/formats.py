@@ -25,7 +25,11 @@ def write_wav(path, pcm, sample_rate):
 
 def read_wav(path):
     """Returns (int16 samples, sample_rate).  PCM16 mono only, like the reference."""
-    b = open(path, "rb").read()
+    return parse_wav(open(path, "rb").read(), path)
+
+
+def parse_wav(b, path="<bytes>"):
+    """read_wav on the bytes of a RIFF/WAVE file."""
     if b[:4] != b"RIFF" or b[8:12] != b"WAVE":
         raise ValueError("%s: not a RIFF/WAVE file" % path)
     p, sr, ch, bits, fmt = 12, None, None, None, None

@@ -295,14 +295,46 @@ class PhoneProbs:
     def read_models(self, base):
         self.engine.model_read(base)
 
-    def generate(self, audio_path, lna_path):
-        pcm, sr = formats.read_wav(audio_path)
+    def set_clustering(self, clfile_name, eval_minc, eval_ming):
+        """PPToolbox::set_clustering (aku/PhoneProbsToolbox.cc:50-53)."""
+        self.engine.read_clustering(clfile_name)
+        self.engine.set_clustering_min_evals(eval_minc, eval_ming)
+
+    def _pcm_of(self, blob, raw_flag, what):
+        if not raw_flag and blob[:4] == b"RIFF" and blob[8:12] == b"WAVE":
+            pcm, sr = formats.parse_wav(blob, what)
+        else:                                   # headerless PCM16 at the configured rate, like AudioReader's fallback
+            pcm, sr = np.frombuffer(blob[:len(blob) // 2 * 2], dtype="<i2").copy(), self.engine.sample_rate
         if sr != self.engine.sample_rate:
             raise AkuGpuError(-2, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree."
                               % (sr, self.engine.sample_rate))
+        return pcm
+
+    def _stream(self, pcm):
         rec, _, _ = self.engine.phone_probs(pcm, precision=self.precision, lnabytes=self.lnabytes,
                                             normalize=self.normalize)
+        return rec
+
+    def generate(self, audio_path, lna_path, raw_flag=False):
+        """PPToolbox::generate(input_name, output_name, raw_flag) (aku/PhoneProbsToolbox.cc:211-222)."""
+        rec = self._stream(self._pcm_of(open(audio_path, "rb").read(), raw_flag, audio_path))
         formats.write_lna(lna_path, rec, self.engine.num_states, self.lnabytes)
+        return rec.shape[0]
+
+    def generate_to_fd(self, in_fd, out_fd, raw_flag=False):
+        """PPToolbox::generate_to_fd (aku/PhoneProbsToolbox.cc:55-133): audio from an open descriptor (read to its end),
+        header + records to out_fd; neither descriptor is closed."""
+        chunks = []
+        while True:
+            b = os.read(in_fd, 1 << 20)
+            if not b:
+                break
+            chunks.append(b)
+        rec = self._stream(self._pcm_of(b"".join(chunks), raw_flag, "<fd>"))
+        data = formats.lna_header(self.engine.num_states, self.lnabytes) + np.ascontiguousarray(rec, dtype=np.uint8).tobytes()
+        done = 0
+        while done < len(data):
+            done += os.write(out_fd, data[done:])
         return rec.shape[0]
 
     def run_recipe(self, recipe_path, out_dir="", batch=1, bindex=1, no_overwrite=False, audio_ext_lna=False,

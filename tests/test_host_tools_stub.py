@@ -267,7 +267,8 @@ class FakeEngine:
     """The stub's formulas behind the Python engine surface PhoneProbs.run_recipe uses."""
     sample_rate, frame_rate, num_states = 16000, 125.0, S
 
-    def phone_probs(self, pcm, uo, precision=0, lnabytes=2, normalize=True):
+    def phone_probs(self, pcm, uo=None, precision=0, lnabytes=2, normalize=True):
+        uo = np.array([0, pcm.size]) if uo is None else uo
         fo = np.concatenate([[0], np.cumsum(np.diff(uo) // 128)]).astype(np.int64)
         rec = np.concatenate([np.frombuffer(lna_file(range(int(fo[k + 1] - fo[k])), lnabytes, 1 if normalize else 0)[5:], np.uint8)
                               for k in range(len(uo) - 1)]).reshape(int(fo[-1]), S * lnabytes)
@@ -297,3 +298,38 @@ def test_python_run_recipe_matches_the_cpp_tool(tools, case):
         assert names == sorted(os.listdir(str(o_py))) and n == len(names) - (1 if "-n" in flags else 0)
         for f in names:
             assert open(str(o_cpp / f), "rb").read() == open(str(o_py / f), "rb").read(), (flags, f)
+
+
+def test_python_pptoolbox_surface(case):
+    """aaltoasr_b200.PPToolbox (= PhoneProbs): the method names and arguments of the reference's SWIG class
+    (aku/swig/PPToolbox.i:59-66) -- generate(in, out, raw_flag), generate_to_fd, set_clustering -- over the engine."""
+    import aaltoasr_b200
+    c = case
+
+    class Eng(FakeEngine):
+        log = []
+
+        def read_clustering(self, path):
+            self.log.append(("read_clustering", path))
+
+        def set_clustering_min_evals(self, a, b):
+            self.log.append(("min_evals", a, b))
+
+    eng = Eng()
+    pp = aaltoasr_b200.PPToolbox(engine=eng)
+    pp.set_clustering("c.gcl", 0.1, 0.2)
+    assert eng.log == [("read_clustering", "c.gcl"), ("min_evals", 0.1, 0.2)]
+    wav = str(c["dir"] / "a1.wav")
+    out = str(c["dir"] / "py.lna")
+    assert pp.generate(wav, out, False) == 20 and open(out, "rb").read() == lna_file(range(20))
+    raw = str(c["dir"] / "a1.raw")
+    formats.read_wav(wav)[0].astype("<i2").tofile(raw)
+    assert pp.generate(raw, out, True) == 20 and open(out, "rb").read() == lna_file(range(20))
+    fin, fout = os.open(wav, os.O_RDONLY), os.open(str(c["dir"] / "fd.lna"), os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o664)
+    assert pp.generate_to_fd(fin, fout, False) == 20
+    os.close(fin)
+    os.close(fout)
+    assert open(str(c["dir"] / "fd.lna"), "rb").read() == lna_file(range(20))
+    formats.write_wav(str(c["dir"] / "k8.wav"), np.zeros(640, np.int16), 8000)
+    with pytest.raises(aaltoasr_b200.AkuGpuError, match="don't agree"):
+        pp.generate(str(c["dir"] / "k8.wav"), out)
