@@ -64,6 +64,8 @@ inline void parse_audio(const std::vector<unsigned char> &b, const std::string &
         ch = b[p + 10] | (b[p + 11] << 8);
         rate = b[p + 12] | (b[p + 13] << 8) | (b[p + 14] << 16) | ((uint32_t)b[p + 15] << 24);
         bits = b[p + 22] | (b[p + 23] << 8);
+        // WAVE_FORMAT_EXTENSIBLE: the sample format is the first field of the SubFormat GUID (libsndfile reads these too)
+        if (fmt == 0xFFFE && n >= 40 && p + 8 + 26 <= b.size()) fmt = b[p + 8 + 24] | (b[p + 8 + 25] << 8);
       } else if (!memcmp(&b[p], "data", 4)) {
         off = p + 8; len = n; if (off + len > b.size()) len = b.size() - off;
         found = true;

@@ -38,6 +38,8 @@ def parse_wav(b, path="<bytes>"):
         if cid == b"fmt ":
             fmt, ch, sr = struct.unpack("<HHI", b[p + 8:p + 16])
             bits = struct.unpack("<H", b[p + 22:p + 24])[0]
+            if fmt == 0xFFFE and ln >= 40:      # WAVE_FORMAT_EXTENSIBLE: format tag = first field of the SubFormat GUID
+                fmt = struct.unpack("<H", b[p + 32:p + 34])[0]
         elif cid == b"data":
             if fmt != 1 or bits != 16:
                 raise ValueError("%s: sample format not PCM16" % path)

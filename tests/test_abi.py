@@ -119,7 +119,17 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     open(str(tmp_path / "b.wav"), "wb").write(extra)
     pcm.astype("<i2").tofile(str(tmp_path / "a.raw"))
     want_sum = int((pcm.astype(np.int64) * (np.arange(pcm.size) % 97 + 1)).sum())
-    for path, cfg_rate, raw, rate in (("a.wav", 16000, 0, 8000), ("b.wav", 16000, 0, 8000), ("a.raw", 16000, 1, 16000)):
+    # WAVE_FORMAT_EXTENSIBLE with a PCM SubFormat (what many recorders write; libsndfile reads it as PCM16)
+    fmt_at = blob.index(b"fmt ")
+    body = blob[fmt_at + 8:fmt_at + 24]
+    ext = (b"\xfe\xff" + body[2:] + (22).to_bytes(2, "little") + (16).to_bytes(2, "little") + (4).to_bytes(4, "little") +
+           b"\x01\x00\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71")
+    extw = blob[:fmt_at] + b"fmt " + (40).to_bytes(4, "little") + ext + blob[fmt_at + 24:]
+    extw = extw[:4] + (len(extw) - 8).to_bytes(4, "little") + extw[8:]
+    open(str(tmp_path / "e.wav"), "wb").write(extw)
+    got_pcm, got_sr = formats.read_wav(str(tmp_path / "e.wav"))
+    assert got_sr == 8000 and np.array_equal(got_pcm, pcm)
+    for path, cfg_rate, raw, rate in (("a.wav", 16000, 0, 8000), ("b.wav", 16000, 0, 8000), ("e.wav", 16000, 0, 8000), ("a.raw", 16000, 1, 16000)):
         r = subprocess.run([exe, "audio", str(tmp_path / path), str(cfg_rate), str(raw)], stdout=subprocess.PIPE, timeout=60)
         assert r.returncode == 0 and r.stdout.decode().split() == [str(pcm.size), str(rate), str(want_sum)], (path, r.stdout)
     r = subprocess.run([exe, "audio", str(tmp_path / "nope.wav"), "16000", "0"], stdout=subprocess.PIPE, timeout=60)
