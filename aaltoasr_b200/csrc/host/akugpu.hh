@@ -48,12 +48,15 @@ private:
 };
 
 // RIFF/WAVE PCM16 mono or headerless RAW PCM16, what aku::AudioReader accepts (aku/AudioReader.cc:86-155).
+// Headerless data is little-endian unless the audiofile module's configuration says `endian big` (aku/AudioReader.cc:94-108).
 inline void parse_audio(const std::vector<unsigned char> &b, const std::string &path, int config_rate, bool force_raw,
-                        std::vector<int16_t> &pcm, int &rate)
+                        std::vector<int16_t> &pcm, int &rate, bool raw_big_endian = false)
 {
+  bool is_raw = true;
   size_t off = 0, len = b.size();
   rate = config_rate;
   if (!force_raw && b.size() >= 12 && !memcmp(&b[0], "RIFF", 4) && !memcmp(&b[8], "WAVE", 4)) {
+    is_raw = false;
     size_t p = 12;
     int fmt = -1, ch = 0, bits = 0;
     bool found = false;
@@ -77,9 +80,11 @@ inline void parse_audio(const std::vector<unsigned char> &b, const std::string &
     if (ch != 1) throw std::string("AudioReader: sorry, audio files with multiple channels not supported");
   }
   pcm.resize(len / 2);
-  for (size_t i = 0; i < pcm.size(); i++) pcm[i] = (int16_t)(b[off + 2 * i] | (b[off + 2 * i + 1] << 8));
+  const int lo = (is_raw && raw_big_endian) ? 1 : 0;
+  for (size_t i = 0; i < pcm.size(); i++) pcm[i] = (int16_t)(b[off + 2 * i + lo] | (b[off + 2 * i + 1 - lo] << 8));
 }
-inline void read_audio(const std::string &path, int config_rate, bool force_raw, std::vector<int16_t> &pcm, int &rate)
+inline void read_audio(const std::string &path, int config_rate, bool force_raw, std::vector<int16_t> &pcm, int &rate,
+                       bool raw_big_endian = false)
 {
   FILE *fp = path == "-" ? stdin : fopen(path.c_str(), "rb");    // "-" = standard input, like io::Stream (aku/io.cc:52-60)
   if (!fp) throw std::string("AudioReader::open(): could not open file:") + path;
@@ -88,7 +93,32 @@ inline void read_audio(const std::string &path, int config_rate, bool force_raw,
   size_t k;
   while ((k = fread(buf, 1, sizeof buf, fp)) > 0) b.insert(b.end(), buf, buf + k);
   if (fp != stdin) fclose(fp);
-  parse_audio(b, path, config_rate, force_raw, pcm, rate);
+  parse_audio(b, path, config_rate, force_raw, pcm, rate, raw_big_endian);
+}
+
+// The two keys of the audiofile module that concern the FILE rather than the signal processing (AudioFileModule::
+// set_module_config, aku/FeatureModules.cc:345-356): `raw 1` = never look for a header, `endian big|little` = byte
+// order of headerless data.  The library parses the rest of the configuration; the container is the host's business.
+inline void config_audio_format(const std::string &cfg_path, bool &raw, bool &big_endian)
+{
+  raw = false; big_endian = false;
+  FILE *fp = fopen(cfg_path.c_str(), "r");
+  if (!fp) return;                     // the library reports the missing file
+  char line[4096];
+  int depth = 0, module = 0;
+  while (fgets(line, sizeof line, fp)) {
+    char key[64] = "", val[64] = "";
+    const int n = sscanf(line, " %63s %63s", key, val);
+    if (n < 1) continue;
+    if (!strcmp(key, "{")) { depth++; continue; }
+    if (!strcmp(key, "}")) { depth--; if (depth == 0 && module == 1) break; continue; }      // first module only: the base module
+    if (depth == 0 && !strcmp(key, "module")) { module++; continue; }
+    if (depth == 1 && module == 1 && n == 2) {
+      if (!strcmp(key, "raw")) raw = atoi(val) != 0;
+      if (!strcmp(key, "endian")) big_endian = !strcmp(val, "big");
+    }
+  }
+  fclose(fp);
 }
 
 class FeatureGenerator {
@@ -97,7 +127,10 @@ public:
   void load_configuration(const std::string &path) {
     check(m_e.ctx(), akugpu_frontend_load_config(m_e.ctx(), path.c_str()));
     m_dim = akugpu_frontend_dim(m_e.ctx());
+    config_audio_format(path, m_cfg_raw, m_cfg_big_endian);
   }
+  bool config_raw() const { return m_cfg_raw; }                   // `raw 1` / `endian big` of the audiofile module
+  bool config_big_endian() const { return m_cfg_big_endian; }
   // A `pre` base module reads stored features (int32 dim + float32 rows, feacat -H --raw-output) instead of audio.
   void open_pre(const std::string &filename) {
     FILE *fp = filename == "-" ? stdin : fopen(filename.c_str(), "rb");
@@ -123,7 +156,7 @@ public:
     if (akugpu_frontend_base_is_pre(m_e.ctx()) == 1) { open_pre(filename); return; }
     m_rows.clear();
     int rate = 0;
-    read_audio(filename, sample_rate(), false, m_pcm, rate);
+    read_audio(filename, sample_rate(), m_cfg_raw, m_pcm, rate, m_cfg_big_endian);
     if (rate != sample_rate()) {     // aku/FeatureModules.cc:254-261
       char msg[256];
       snprintf(msg, sizeof msg, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree.", rate, sample_rate());
@@ -141,7 +174,7 @@ public:
     if (!dont_fclose) fclose(file);
     m_rows.clear();
     int rate = 0;
-    parse_audio(b, "<stream>", sample_rate(), false, m_pcm, rate);
+    parse_audio(b, "<stream>", sample_rate(), m_cfg_raw, m_pcm, rate, m_cfg_big_endian);
     if (rate != sample_rate()) {
       char msg[256];
       snprintf(msg, sizeof msg, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree.", rate, sample_rate());
@@ -207,6 +240,7 @@ private:
   std::vector<double> m_feats, m_tmp;
   int m_frames, m_dim;
   bool m_eof;
+  bool m_cfg_raw = false, m_cfg_big_endian = false;
 };
 
 class HmmSet {
@@ -545,14 +579,14 @@ public:
     }
     std::vector<int16_t> pcm;
     int rate = 0;
-    parse_audio(b, "<fd>", m_gen.sample_rate(), raw_flag, pcm, rate);
+    parse_audio(b, "<fd>", m_gen.sample_rate(), raw_flag || m_gen.config_raw(), pcm, rate, m_gen.config_big_endian());
     emit(pcm, rate, out_fd);
   }
   void generate_from_file_to_fd(const std::string &input_name, int out_fd, bool /*raw_flag: unused by the reference too*/) {
     check_dims();
     std::vector<int16_t> pcm;
     int rate = 0;
-    read_audio(input_name, m_gen.sample_rate(), false, pcm, rate);
+    read_audio(input_name, m_gen.sample_rate(), m_gen.config_raw(), pcm, rate, m_gen.config_big_endian());
     emit(pcm, rate, out_fd);
   }
   void generate(const std::string &input_name, const std::string &output_name, bool raw_flag) {

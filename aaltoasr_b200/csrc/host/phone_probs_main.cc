@@ -150,7 +150,7 @@ int main(int argc, char **argv)
                                             (speakers.empty() || (todo[j].speaker == todo[i].speaker && todo[j].utterance == todo[i].utterance))))) {
         std::vector<int16_t> one;
         int rate = 0;
-        akugpu::read_audio(todo[j].audio, gen.sample_rate(), raw_input, one, rate);
+        akugpu::read_audio(todo[j].audio, gen.sample_rate(), raw_input || gen.config_raw(), one, rate, gen.config_big_endian());
         if (rate != gen.sample_rate()) {
           char msg[256];
           snprintf(msg, sizeof msg, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree.", rate, gen.sample_rate());

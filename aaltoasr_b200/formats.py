@@ -83,6 +83,30 @@ def write_model(base, mix_offsets, mix_gauss, mix_weight, means, covs=None, full
             f.write("%d 3 p%d\n-1 -2 %d\n0 1 2 1\n1 0\n2 2 2 0.8 1 0.2\n" % (s + 1, s, s))
 
 
+def config_audio_format(cfg_text):
+    """(raw, big_endian) from the `raw` / `endian` keys of the FIRST module of a feature configuration -- the audiofile
+    module's keys that concern the file, not the signal processing (aku/FeatureModules.cc:345-356)."""
+    raw, big, depth, module = False, False, 0, 0
+    for line in cfg_text.splitlines():
+        f = line.split()
+        if not f:
+            continue
+        if f[0] == "{":
+            depth += 1
+        elif f[0] == "}":
+            depth -= 1
+            if depth == 0 and module == 1:
+                break
+        elif depth == 0 and f[0] == "module":
+            module += 1
+        elif depth == 1 and module == 1 and len(f) >= 2:
+            if f[0] == "raw":
+                raw = int(f[1]) != 0
+            if f[0] == "endian":
+                big = f[1] == "big"
+    return raw, big
+
+
 def read_recipe(path, num_batches=0, batch_index=0):
     """aku::Recipe::read (aku/Recipe.cc:24-147): one utterance per line of key=value fields; a key missing on a later
     line inherits the previous line's value (the reference never clears its map, :29,82-90), also across batch borders.

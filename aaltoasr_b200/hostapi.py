@@ -291,6 +291,7 @@ class PhoneProbs:
     # PPToolbox names (aku/swig/PPToolbox.i:59-66)
     def read_configuration(self, cfg):
         self.engine.frontend_load_config(cfg)
+        self._cfg_raw, self._cfg_big_endian = formats.config_audio_format(open(cfg).read())
 
     def read_models(self, base):
         self.engine.model_read(base)
@@ -301,10 +302,12 @@ class PhoneProbs:
         self.engine.set_clustering_min_evals(eval_minc, eval_ming)
 
     def _pcm_of(self, blob, raw_flag, what):
+        raw_flag = raw_flag or getattr(self, "_cfg_raw", False)
         if not raw_flag and blob[:4] == b"RIFF" and blob[8:12] == b"WAVE":
             pcm, sr = formats.parse_wav(blob, what)
         else:                                   # headerless PCM16 at the configured rate, like AudioReader's fallback
-            pcm, sr = np.frombuffer(blob[:len(blob) // 2 * 2], dtype="<i2").copy(), self.engine.sample_rate
+            dt = ">i2" if getattr(self, "_cfg_big_endian", False) else "<i2"
+            pcm, sr = np.frombuffer(blob[:len(blob) // 2 * 2], dtype=dt).astype(np.int16), self.engine.sample_rate
         if sr != self.engine.sample_rate:
             raise AkuGpuError(-2, "Audio file sample rate (%d Hz) and model configuration (%d Hz) don't agree."
                               % (sr, self.engine.sample_rate))

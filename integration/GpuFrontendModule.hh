@@ -35,7 +35,7 @@ public:
   // FeatureGenerator::open(filename) (aku/FeatureGenerator.cc:31-52): the whole utterance is computed here.
   virtual void set_fname(const char *fname) {
     int rate = 0;
-    akugpu::read_audio(fname, sample_rate(), false, m_pcm, rate);
+    akugpu::read_audio(fname, sample_rate(), m_raw, m_pcm, rate, m_big_endian);
     open_pcm(rate);
   }
   // FeatureGenerator::open(FILE*) / open_fd (aku/FeatureGenerator.cc:55-83): the stream is read to its end.
@@ -45,7 +45,7 @@ public:
     size_t k;
     while ((k = fread(buf, 1, sizeof buf, fp)) > 0) bytes.insert(bytes.end(), buf, buf + k);
     int rate = 0;
-    akugpu::parse_audio(bytes, "<stream>", sample_rate(), false, m_pcm, rate);
+    akugpu::parse_audio(bytes, "<stream>", sample_rate(), m_raw, m_pcm, rate, m_big_endian);
     open_pcm(rate);
   }
   virtual void discard_file(void) { m_pcm.clear(); m_feats.clear(); m_frames = 0; akugpu_hook::publish_utterance(NULL, 0, 0); }
@@ -91,6 +91,7 @@ private:
     if (!config.get("config", m_config_path)) throw std::string("GpuFrontendModule: Must set config (a feature configuration file)");
     akugpu::check(m_engine.ctx(), akugpu_frontend_load_config(m_engine.ctx(), m_config_path.c_str()));
     m_dim = akugpu_frontend_dim(m_engine.ctx());
+    akugpu::config_audio_format(m_config_path, m_raw, m_big_endian);      // `raw` / `endian` of the GPU chain's audiofile module
     m_own_offset_left = 0;
     m_own_offset_right = 0;
   }
@@ -134,6 +135,7 @@ private:
   std::vector<int16_t> m_pcm;
   std::vector<double> m_feats;
   int m_frames;
+  bool m_raw = false, m_big_endian = false;
 };
 
 }  // namespace aku

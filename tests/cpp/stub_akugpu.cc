@@ -32,6 +32,12 @@ static void logf(const char *fmt, ...)
   fclose(fp);
 }
 static int64_t frames_of(int64_t n_samples) { return n_samples / 128; }
+static void log_pcm(const int16_t *pcm, int64_t n)
+{
+  long long w = 0;
+  for (int64_t i = 0; i < n; i++) w += (long long)pcm[i] * (long long)(i % 97 + 1);
+  logf("pcm n=%lld wsum=%lld\n", (long long)n, w);
+}
 
 extern "C" {
 
@@ -85,6 +91,7 @@ int akugpu_features(akugpu_ctx *, const int16_t *pcm, const int64_t *uo, int n_u
   if (!out) return 0;
   if (!pcm) { g_err = "pcm is NULL"; return AKUGPU_E_ARG; }
   logf("features n_utts=%d samples=%lld\n", n_utts, (long long)uo[n_utts]);
+  log_pcm(pcm, uo[n_utts]);
   for (int u = 0; u < n_utts; u++)
     fill_features(fo[u + 1] - fo[u], 0, (int)(fo[u + 1] - fo[u]), (char *)out + (size_t)fo[u] * 3 * (f64 ? 8 : 4), f64);
   return 0;
@@ -170,6 +177,7 @@ int akugpu_phone_probs(akugpu_ctx *, const int16_t *pcm, const int64_t *uo, int 
   if (n_utts && !pcm) { g_err = "pcm is NULL"; return AKUGPU_E_ARG; }
   logf("phone_probs n_utts=%d samples=%lld precision=%d lnabytes=%d normalize=%d\n", n_utts, (long long)uo[n_utts], precision,
        lnabytes, normalize);
+  if (n_utts) log_pcm(pcm, uo[n_utts]);
   if (!out) return 0;
   for (int u = 0; u < n_utts; u++)
     for (int64_t f = 0; f < fo[u + 1] - fo[u]; f++)

@@ -333,3 +333,49 @@ def test_python_pptoolbox_surface(case):
     formats.write_wav(str(c["dir"] / "k8.wav"), np.zeros(640, np.int16), 8000)
     with pytest.raises(aaltoasr_b200.AkuGpuError, match="don't agree"):
         pp.generate(str(c["dir"] / "k8.wav"), out)
+
+
+def test_raw_and_endian_keys_of_the_audiofile_module(tools, case):
+    """`raw 1` and `endian big` of the audiofile module (AudioFileModule::set_module_config, aku/FeatureModules.cc:345-356;
+    AudioReader::open, aku/AudioReader.cc:94-108) are the host reader's business: headerless big-endian PCM reaches the
+    library as the same samples as the WAV file, through both tools; without the keys the bytes are taken little-endian;
+    `raw 1` also stops a RIFF header from being interpreted."""
+    c = case
+    pcm, _ = formats.read_wav(str(c["dir"] / "a1.wav"))
+    wsum = int((pcm.astype(np.int64) * (np.arange(pcm.size) % 97 + 1)).sum())
+    be = str(c["dir"] / "be.raw")
+    pcm.astype(">i2").tofile(be)
+    le = str(c["dir"] / "le.raw")
+    pcm.astype("<i2").tofile(le)
+    cfg_be = str(c["dir"] / "be.cfg")
+    open(cfg_be, "w").write("module\n{\n  name audiofile\n  type audiofile\n  sample_rate 16000\n  endian big\n  raw 1\n}\n"
+                            "module\n{\n  name x\n  type stub\n  endian little\n  sources audiofile\n}\n")     # only the base module counts
+    want = "pcm n=%d wsum=%d" % (pcm.size, wsum)
+    swapped = pcm.astype("<i2").view(">i2").astype(np.int64)
+    want_swapped = "pcm n=%d wsum=%d" % (pcm.size, int((swapped * (np.arange(pcm.size) % 97 + 1)).sum()))
+    for exe, args in ((tools["feacat"], ["-e", "0"]), ):
+        for cfg, path, expect in ((c["cfg"], str(c["dir"] / "a1.wav"), want), (c["cfg"], le, want), (cfg_be, be, want),
+                                  (c["cfg"], be, want_swapped)):
+            log = str(c["dir"] / "log_fc")
+            if os.path.exists(log):
+                os.remove(log)
+            r = run(exe, ["-c", cfg] + args + [path], log)
+            assert r.returncode == 0, r.stderr.decode()
+            assert calls(log, "pcm") == [expect], (cfg, path)
+    assert formats.config_audio_format(open(cfg_be).read()) == (True, True) and formats.config_audio_format(open(c["cfg"]).read()) == (False, False)
+    # `raw 1`: the 44 header bytes of a WAV file are samples too
+    log = str(c["dir"] / "log_rawwav")
+    r = run(tools["feacat"], ["-c", cfg_be, "-e", "0", str(c["dir"] / "a1.wav")], log)
+    assert r.returncode == 0 and calls(log, "pcm")[0].startswith("pcm n=%d " % (pcm.size + 22))
+    # the recipe tool: configuration keys, and -R on top of a plain configuration
+    rec = str(c["dir"] / "raw.recipe")
+    out = c["dir"] / "oraw"
+    out.mkdir()
+    open(rec, "w").write("audio=%s lna=be.lna\n" % be)
+    log = str(c["dir"] / "log_pp")
+    r = run(tools["phone_probs"], ["-b", "m", "-c", cfg_be, "-r", rec, "-o", str(out)], log)
+    assert r.returncode == 0 and calls(log, "pcm") == [want]
+    open(rec, "w").write("audio=%s lna=le.lna\n" % le)
+    log = str(c["dir"] / "log_pp2")
+    r = run(tools["phone_probs"], ["-b", "m", "-c", c["cfg"], "-r", rec, "-o", str(out), "-R"], log)
+    assert r.returncode == 0 and calls(log, "pcm") == [want]
