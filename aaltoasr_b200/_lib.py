@@ -35,6 +35,8 @@ SYMBOLS = {
     "akugpu_frontend_sample_rate": (C.c_int, [C.c_void_p]),
     "akugpu_frontend_frame_rate": (C.c_float, [C.c_void_p]),
     "akugpu_frontend_base_is_pre": (C.c_int, [C.c_void_p]),
+    "akugpu_frontend_base_dim": (C.c_int, [C.c_void_p]),
+    "akugpu_frontend_pre_legacy": (C.c_int, [C.c_void_p]),
     "akugpu_frontend_num_frames": (C.c_int64, [C.c_void_p, C.c_int64]),
     "akugpu_frontend_set_parameters": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "akugpu_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

@@ -133,6 +133,8 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
   const size_t rec = (size_t)S * lnabytes;
   const bool out_dev = out && is_device_ptr(out);
   const bool out_host = out && !out_dev;
+  if (out_dev && ((uintptr_t)out & 3))      // the LNA kernels store 32-bit words (16-bit when S * lnabytes is odd-sized)
+    throw Error(AKUGPU_E_ARG, "a device `out` buffer must be 4-byte aligned");
   const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
   ctx->d_sll.reserve((size_t)S * chunk * esz);
   if (!out_dev) { ctx->d_lna[0].reserve(chunk * rec); if (out_host) ctx->d_lna[1].reserve(chunk * rec); }
@@ -147,11 +149,13 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
       const float2 *norm = nullptr;
       if (use_tc) {   // times its own stages; also yields the per-frame normaliser when it sweeps all states
         ctx->d_norm.reserve((size_t)chunk * sizeof(float2));
-        const bool hybrid = use_tc == 2 && ctx->ptc16.hybrid;    // ill-conditioned states: FP32-pipe kernel, same chunk
-        const bool got = use_tc == 2
-                             ? launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk,
-                                               hybrid ? nullptr : ctx->d_norm.as<float2>())
-                             : launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, ctx->d_norm.as<float2>());
+        // ill-conditioned states: FP32-pipe kernel, same chunk -- also when the call is being redone with the bf16x3
+        // kernel after an fp16 range overflow (that image holds every state in the expanded form; the FP32 image
+        // holds exactly the states the expanded form is not trusted with and overwrites their rows)
+        const bool hybrid = ctx->ptc16.ready && ctx->ptc16.hybrid;
+        float2 *const nrm = hybrid ? nullptr : ctx->d_norm.as<float2>();
+        const bool got = use_tc == 2 ? launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nrm)
+                                     : launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nrm);
         if (got) norm = ctx->d_norm.as<float2>();
         if (hybrid) { StageScope sc(ctx, 1); launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
       } else {
@@ -355,6 +359,8 @@ int akugpu_frontend_dim(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? 
 int akugpu_frontend_sample_rate(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[0].sample_rate : AKUGPU_E_STATE; }
 float akugpu_frontend_frame_rate(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[0].frame_rate : -1.f; }
 int akugpu_frontend_base_is_pre(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? (ctx->fe.mods[0].type == M_PRE ? 1 : 0) : AKUGPU_E_STATE; }
+int akugpu_frontend_base_dim(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? ctx->fe.mods[0].dim : AKUGPU_E_STATE; }
+int akugpu_frontend_pre_legacy(akugpu_ctx *ctx) { return (ctx && ctx->fe.configured) ? (ctx->fe.mods[0].type == M_PRE && ctx->fe.mods[0].legacy_file ? 1 : 0) : AKUGPU_E_STATE; }
 int64_t akugpu_frontend_num_frames(akugpu_ctx *ctx, int64_t n_samples)
 {
   if (!ctx || !ctx->fe.configured) return AKUGPU_E_STATE;
@@ -676,12 +682,10 @@ static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, in
         launch_transpose_f64(ctx, ctx->d_sll.as<double>(), chunk, S, c1 - c0, (double *)(d_out + (size_t)c0 * S * 8));
       }
     } else {
-      if (use_tc == 2) {
-        launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
-        if (ctx->ptc16.hybrid) launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
-      }
+      if (use_tc == 2) launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
       else if (use_tc) launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nullptr);
-      else launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+      if (!use_tc || (ctx->ptc16.ready && ctx->ptc16.hybrid))     // whole model, or the states left out of the expanded form
+        launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
       if (logmode) launch_floor_f32(ctx, ctx->d_sll.as<float>(), (int64_t)S * chunk, (float)log(tiny));
       launch_transpose_f32(ctx, ctx->d_sll.as<float>(), chunk, S, c1 - c0, (float *)(d_out + (size_t)c0 * S * 4));
     }
@@ -730,7 +734,7 @@ int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_o
   base_unit_bytes(ctx, false);       // PCM in: needs an audiofile base module
   const int dim = ctx->fe.mods[ctx->fe.last].dim;
   if (dim != ctx->hm.D)
-    throw Error(AKUGPU_E_STATE, fmt("Feature dimension (%d) and model dimension (%d) don't agree", dim, ctx->hm.D));
+    throw Error(AKUGPU_E_STATE, fmt("Gaussian dimension is %d but feature dimension is %d.", ctx->hm.D, dim));
   std::vector<int64_t> uo, fo;
   frame_offsets_of(ctx, utt_offsets, n_utts, uo, fo);
   if (frame_offsets) memcpy(frame_offsets, fo.data(), fo.size() * sizeof(int64_t));

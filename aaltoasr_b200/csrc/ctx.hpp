@@ -169,6 +169,7 @@ struct Module {
   int left = 0, right = 0;  // own context (frames)
   // audiofile
   int sample_rate = 0, window_width = 0, copy_borders = 1;
+  int legacy_file = 0;      // pre: 1-byte dimension header (PreModule::set_file, aku/FeatureModules.cc:608-615)
   float frame_rate = 125.f, window_advance = 0.f, emph = 0.97f;
   // fft
   int magnitude = 1, log = 0;

@@ -427,7 +427,7 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
         m.frame_rate = 125; m.sample_rate = 16000;
         get_int(b, "sample_rate", m.sample_rate);
         get_float(b, "frame_rate", m.frame_rate);
-        int legacy = 0; get_int(b, "legacy_file", legacy);   // header layout is the host reader's business
+        m.legacy_file = 0; get_int(b, "legacy_file", m.legacy_file);   // 1-byte header (akugpu_frontend_pre_legacy): the host reader's business
         if (!get_int(b, "dim", m.dim)) throw Error(AKUGPU_E_CONFIG, "PreModule: Must set dimension");
         if (m.dim < 1) throw Error(AKUGPU_E_CONFIG, "PreModule: Must set dimension");
         m.window_advance = m.sample_rate / m.frame_rate;

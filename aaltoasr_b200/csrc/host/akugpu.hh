@@ -135,14 +135,20 @@ public:
   void open_pre(const std::string &filename) {
     FILE *fp = filename == "-" ? stdin : fopen(filename.c_str(), "rb");
     if (!fp) throw std::string("could not open file ") + filename;
+    // PreModule::set_file (aku/FeatureModules.cc:602-627): a `legacy_file 1` configuration stores the dimension in ONE
+    // byte, otherwise it is an int; either way it must equal the configured `dim` of the module
     int dim = 0;
-    if (fread(&dim, sizeof(int), 1, fp) < 1) { if (fp != stdin) fclose(fp); throw std::string("PreModule: Could not read the file."); }
+    bool got;
+    if (akugpu_frontend_pre_legacy(m_e.ctx()) == 1) { char d = 0; got = fread(&d, 1, 1, fp) == 1; dim = d; }
+    else got = fread(&dim, sizeof(int), 1, fp) == 1;
+    if (!got) { if (fp != stdin) fclose(fp); throw std::string("PreModule: Could not read the file."); }
+    if (dim != akugpu_frontend_base_dim(m_e.ctx())) { if (fp != stdin) fclose(fp); throw std::string("PreModule: The file has invalid dimension"); }
     m_rows.clear();
     std::vector<float> buf(4096);
     size_t k;
     while ((k = fread(buf.data(), sizeof(float), buf.size(), fp)) > 0) m_rows.insert(m_rows.end(), buf.begin(), buf.begin() + k);
     if (fp != stdin) fclose(fp);
-    if (dim <= 0 || m_rows.size() % (size_t)dim != 0) throw std::string("PreModule: The file has invalid dimension");
+    m_rows.resize(m_rows.size() / (size_t)dim * (size_t)dim);      // a trailing partial row is never read (PreModule::generate :733-745)
     m_pre_dim = dim;
     int64_t ro[2] = {0, (int64_t)(m_rows.size() / dim)}, fo[2] = {0, 0};
     check(m_e.ctx(), akugpu_features_pre(m_e.ctx(), NULL, ro, 1, NULL, 1, fo));

@@ -14,7 +14,15 @@
 
 struct Utt { std::string audio, lna, speaker, utterance; double start_time, end_time; };
 
-static bool file_nonempty(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && st.st_size > 0; }
+// stat() == 0 is the reference's test for "exists" (aku/phone_probs.cc:180-190): an empty file is skipped too
+static bool file_exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+// a file name inside single quotes of a /bin/sh command line: ' -> '\''
+static std::string sh_quote(const std::string &s)
+{
+  std::string q = "'";
+  for (size_t i = 0; i < s.size(); i++) { if (s[i] == '\'') q += "'\\''"; else q += s[i]; }
+  return q + "'";
+}
 
 // Output names as io::Stream understands them (aku/io.cc:35-130): "-" = standard output, a leading '|' = pipe to a
 // command, a trailing ".gz" = through gzip; anything else a plain file.
@@ -23,7 +31,7 @@ struct OutStream {
   explicit OutStream(const std::string &name) : fp(NULL), is_pipe(false), is_stdout(false) {
     if (name == "-") { fp = stdout; is_stdout = true; }
     else if (!name.empty() && name[0] == '|') { fp = popen(name.c_str() + 1, "w"); is_pipe = true; }
-    else if (name.size() >= 3 && name.compare(name.size() - 3, 3, ".gz") == 0) { fp = popen(("gzip > '" + name + "'").c_str(), "w"); is_pipe = true; }
+    else if (name.size() >= 3 && name.compare(name.size() - 3, 3, ".gz") == 0) { fp = popen(("gzip > " + sh_quote(name)).c_str(), "w"); is_pipe = true; }
     else fp = fopen(name.c_str(), "wb");
     if (!fp) throw std::string("could not open ") + name + " for writing";
   }
@@ -53,7 +61,7 @@ int main(int argc, char **argv)
                "  -c, --config=FILE      feature configuration\n  -r, --recipe=FILE      recipe file\n"
                "  -a, --afname           name LNA files by the audio file\n      --sort-recipe      sort recipe lines by speaker, useful with adaptation\n  -o, --output-dir=DIR   base path for LNAs\n"
                "  -R, --raw-input        raw audio input\n      --lnabytes=INT     2 (default) or 4\n"
-               "  -n, --no-overwrite     skip existing non-empty LNA files\n  -N, --no-normalization\n"
+               "  -n, --no-overwrite     prevent overwriting existing files\n  -N, --no-normalization\n"
                "  -S, --speakers=FILE    speaker configuration file (feature-module parameters per speaker / utterance,\n"
                "                         global `model cmllr` transforms per speaker)\n"
                "  -C, --clusters=FILE    Gaussian clustering (.gcl)\n      --eval-minc=FLOAT  minimum ratio of top clusters to evaluate (0)\n"
@@ -87,7 +95,7 @@ int main(int argc, char **argv)
     }
     if (cfg.empty()) throw std::string("Must give --config");
     if (recipe.empty()) throw std::string("Must give --recipe");
-    if (lnabytes != 2 && lnabytes != 4) throw std::string("Invalid number of bytes for probabilities in LNA file");   // aku/phone_probs.cc:121
+    if (lnabytes != 2 && lnabytes != 4) throw std::string("Invalid number of LNA bytes");   // aku/phone_probs.cc:88-90
     if (!outdir.empty() && outdir[outdir.size() - 1] != '/') outdir += "/";
 
     akugpu::Engine eng(device);
@@ -103,9 +111,9 @@ int main(int argc, char **argv)
       model.read_clustering(clusters);
       model.set_clustering_min_evals(eval_minc, eval_ming);
     }
-    if (gen.dim() != model.dim()) {   // aku/phone_probs.cc:125-131
-      char msg[200];
-      snprintf(msg, sizeof msg, "Feature dimension (%d) and model dimension (%d) don't agree", gen.dim(), model.dim());
+    if (model.dim() != gen.dim()) {   // aku/phone_probs.cc:119-124
+      char msg[256];
+      snprintf(msg, sizeof msg, "Gaussian dimension is %d but feature dimension is %d.", model.dim(), gen.dim());
       throw std::string(msg);
     }
     const int S = model.num_states();
@@ -125,14 +133,17 @@ int main(int argc, char **argv)
     std::vector<Utt> todo;
     for (size_t k = 0; k < utts.size(); k++) {
       Utt u = utts[k];
-      if (lna_by_audio || u.lna.empty()) {
+      if (lna_by_audio) {               // aku/phone_probs.cc:158-176
         std::string f = u.audio;
-        size_t sl = f.rfind('/'); if (sl != std::string::npos) f = f.substr(sl + 1);
-        size_t dot = f.rfind('.'); if (dot != std::string::npos) f = f.substr(0, dot);
+        size_t sl = f.rfind('/'); if (sl != std::string::npos && sl + 1 < f.size()) f = f.substr(sl + 1);   // a trailing '/' keeps the path
+        size_t dot = f.rfind('.'); if (dot != std::string::npos && dot > 0) f.erase(dot);                    // ".hidden" keeps its name
         u.lna = f + ".lna";
       }
-      u.lna = outdir + u.lna;
-      if (no_overwrite && file_nonempty(u.lna)) continue;
+      u.lna = outdir + u.lna;            // an empty lna= is an open error later, as in the reference (no silent fallback)
+      if (no_overwrite && file_exists(u.lna)) {
+        fprintf(stderr, "WARNING: skipping existing lna file %s\n", u.lna.c_str());
+        continue;
+      }
       todo.push_back(u);
     }
     const float fr = gen.frame_rate();
@@ -169,16 +180,31 @@ int main(int argc, char **argv)
       for (int k = 0; k < n; k++) {
         const Utt &u = todo[i + k];
         if (info > 0) printf("Processing file: %s\n", u.audio.c_str());
-        int64_t nf = fo[k + 1] - fo[k];
-        int64_t s = (int64_t)(u.start_time * fr), e = (int64_t)(u.end_time * fr);   // aku/phone_probs.cc:199-206
-        if (e == 0 || e > nf) e = nf;
+        const int64_t nf = fo[k + 1] - fo[k];
+        int64_t s = (int64_t)(int)(u.start_time * fr), e = (int64_t)(int)(u.end_time * fr);   // aku/phone_probs.cc:199-206
+        if (e == 0 || e > nf) e = nf;          // the reference's loop breaks at eof
         if (s > e) s = e;
         OutStream os(u.lna);
         FILE *fp = os.fp;
         uint8_t hdr[5];
         akugpu_lna_header(S, lnabytes, hdr);
-        if (fwrite(hdr, 1, 5, fp) != 5 ||
-            fwrite(&rec[(size_t)(fo[k] + s) * S * lnabytes], 1, (size_t)(e - s) * S * lnabytes, fp) != (size_t)(e - s) * S * lnabytes)
+        if (fwrite(hdr, 1, 5, fp) != 5) throw std::string("Write error");
+        if (s < 0) {
+          // frames before the file: the reference's loop starts at a negative frame and every module sees the
+          // border-replicated first window there (aku/FeatureModules.cc:381-422); generated on their own
+          const int64_t nneg = std::min<int64_t>(e, 0) - s;
+          const int dim = gen.dim();
+          std::vector<double> fneg((size_t)nneg * dim);
+          int d_out = 0;
+          akugpu::check(eng.ctx(), akugpu_features_range(eng.ctx(), pcm.data() + uo[k], uo[k + 1] - uo[k], (int)s, (int)(s + nneg), NULL,
+                                                         fneg.data(), 1, &d_out));
+          std::vector<uint8_t> rneg((size_t)nneg * S * lnabytes);
+          akugpu::check(eng.ctx(), akugpu_gmm_lna(eng.ctx(), fneg.data(), 1, nneg, precision, lnabytes, no_norm ? 0 : 1, rneg.data()));
+          if (fwrite(rneg.data(), 1, rneg.size(), fp) != rneg.size()) throw std::string("Write error");
+          s = std::min<int64_t>(e, 0);
+        }
+        const size_t nbytes = (size_t)(e - s) * S * lnabytes;
+        if (nbytes && fwrite(rec.data() + (size_t)(fo[k] + s) * S * lnabytes, 1, nbytes, fp) != nbytes)
           throw std::string("Write error");
       }
       i = j;

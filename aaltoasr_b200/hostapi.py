@@ -349,12 +349,19 @@ class PhoneProbs:
             infos = formats.sort_recipe(infos)
         todo = []
         for info in infos:
-            if audio_ext_lna or "lna" not in info:
-                name = os.path.splitext(os.path.basename(info["audio"]))[0] + ".lna"
+            if audio_ext_lna:           # aku/phone_probs.cc:158-176: extension stripped only at a dot past position 0
+                name = info["audio"]
+                cut = name.rfind("/")
+                if 0 <= cut < len(name) - 1:
+                    name = name[cut + 1:]
+                dot = name.rfind(".")
+                name = (name[:dot] if dot > 0 else name) + ".lna"
             else:
-                name = info["lna"]
+                name = info.get("lna", "")
             path = os.path.join(out_dir, name) if out_dir else name
-            if no_overwrite and os.path.exists(path) and os.path.getsize(path) > 0:
+            if no_overwrite and os.path.exists(path):      # stat() == 0, empty files included (aku/phone_probs.cc:180-190)
+                import sys
+                sys.stderr.write("WARNING: skipping existing lna file %s\n" % path)
                 continue
             todo.append((info, path))
         written = 0
@@ -379,9 +386,15 @@ class PhoneProbs:
                 a, b = int(fo[k]), int(fo[k + 1])
                 s = int(float(info.get("start-time", 0) or 0) * fr)          # aku/phone_probs.cc:199-206
                 e = int(float(info.get("end-time", 0) or 0) * fr)
-                if e == 0:
+                if e == 0 or e > b - a:
                     e = b - a
-                formats.write_lna(path, rec[a + min(s, b - a):a + min(e, b - a)], self.engine.num_states, self.lnabytes)
+                s = min(s, e)
+                part = rec[a + max(s, 0):a + max(e, 0)]
+                if s < 0:       # frames before the file: the reference's loop generates them (first window replicated)
+                    fneg = self.engine.features_range(pcms[k], s, min(e, 0), dtype=np.float64)
+                    rneg = self.engine.gmm_lna(fneg, precision=self.precision, lnabytes=self.lnabytes, normalize=self.normalize)
+                    part = np.concatenate([rneg.reshape(-1, rec.shape[1]), part])
+                formats.write_lna(path, part, self.engine.num_states, self.lnabytes)
                 written += 1
             i = j
         return written

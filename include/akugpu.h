@@ -70,6 +70,12 @@ int   akugpu_frontend_dim(akugpu_ctx *ctx);            /* FeatureGenerator::dim(
 int   akugpu_frontend_sample_rate(akugpu_ctx *ctx);    /* FeatureGenerator::sample_rate() */
 float akugpu_frontend_frame_rate(akugpu_ctx *ctx);     /* FeatureGenerator::frame_rate()  */
 int   akugpu_frontend_base_is_pre(akugpu_ctx *ctx);    /* 1: the base module is `pre` (stored features), 0: audiofile */
+/* Output dimension of the base module: window_width for audiofile, the configured `dim` for pre -- the value
+ * PreModule::set_file compares with the file header ("The file has invalid dimension", aku/FeatureModules.cc:622-626). */
+int   akugpu_frontend_base_dim(akugpu_ctx *ctx);
+/* 1: the `pre` base module was configured with `legacy_file 1`: the stored-feature file starts with a ONE-byte
+ * dimension instead of an int32 (aku/FeatureModules.cc:608-615).  Reading the header is the host reader's business. */
+int   akugpu_frontend_pre_legacy(akugpu_ctx *ctx);
 /* Number of frames the reference generates before eof() for an audio file of
  * n_samples samples (aku/FeatureModules.cc:371-424: frame f is valid iff
  * (int)(f*window_advance) + window_width + 1 <= n_samples). */
@@ -127,8 +133,9 @@ int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim,
                            const double *mix_weight, const double *means, const double *covs);
 /* All-full-covariance pool (FullCovarianceGaussian, aku/Distributions.cc:1467-1488,1560-1586):
  * full_covs is [G x D x D] row-major.  Pools mixing `diag` and `full` lines come through
- * akugpu_model_read.  Full-covariance models are scored in double (exponential form,
- * aku/Distributions.cc:1437-1446) whatever precision is requested. */
+ * akugpu_model_read.  Precision F64 scores them in double (the reference's exponential form,
+ * aku/Distributions.cc:1437-1446); F32 uses the fp16 hi/lo-split tensor-core kernel on the same expanded form
+ * (gmm_tc16_kernel<0>) when the pool is all-full-covariance and well conditioned, the double path otherwise. */
 int akugpu_model_load_full(akugpu_ctx *ctx, int n_states, int n_gauss, int dim,
                            const int32_t *mix_offsets, const int32_t *mix_gauss,
                            const double *mix_weight, const double *means, const double *full_covs);
@@ -181,7 +188,8 @@ int akugpu_gmm_logprobs(akugpu_ctx *ctx, const void *feats, int feats_f64, int64
 /* Scores + the normalise/quantise loop of aku/phone_probs.cc:225-262.
  *   lnabytes 2: big-endian uint16 codes; 4: IEEE float32 little-endian
  *   normalize 0 == phone_probs --no-normalization
- *   out       [n_frames x S x lnabytes] bytes, no header.  */
+ *   out       [n_frames x S x lnabytes] bytes, no header; a DEVICE buffer must be 4-byte aligned (AKUGPU_E_ARG
+ *             otherwise), host buffers may have any alignment.  */
 int akugpu_gmm_lna(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames,
                    int precision, int lnabytes, int normalize, uint8_t *out);
 

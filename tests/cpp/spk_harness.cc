@@ -20,6 +20,8 @@ int akugpu_frontend_load_config(akugpu_ctx *, const char *) { return 0; }
 int akugpu_frontend_dim(akugpu_ctx *) { return 3; }
 int akugpu_frontend_sample_rate(akugpu_ctx *) { return 16000; }
 int akugpu_frontend_base_is_pre(akugpu_ctx *) { return 0; }
+int akugpu_frontend_base_dim(akugpu_ctx *) { return 0; }
+int akugpu_frontend_pre_legacy(akugpu_ctx *) { return 0; }
 int akugpu_features(akugpu_ctx *, const int16_t *, const int64_t *uo, int n_utts, void *out, int f64, int64_t *fo)
 {
   fo[0] = 0;

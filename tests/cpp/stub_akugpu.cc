@@ -16,7 +16,7 @@
 struct akugpu_ctx { int dummy; };
 static akugpu_ctx g_ctx;
 static double g_shift = 0;
-static int g_cmllr = 0, g_pre = 0;
+static int g_cmllr = 0, g_pre = 0, g_legacy = 0;
 static std::string g_err = "stub";
 
 static void logf(const char *fmt, ...)
@@ -52,6 +52,7 @@ int akugpu_frontend_load_config(akugpu_ctx *, const char *cfg_path)
   fclose(fp);
   const size_t n = strlen(cfg_path);
   g_pre = n >= 7 && !strcmp(cfg_path + n - 7, "pre.cfg");
+  g_legacy = n >= 14 && !strcmp(cfg_path + n - 14, "legacy_pre.cfg");
   logf("load_config %s\n", cfg_path);
   return 0;
 }
@@ -59,6 +60,8 @@ int akugpu_frontend_dim(akugpu_ctx *) { return 3; }
 int akugpu_frontend_sample_rate(akugpu_ctx *) { return 16000; }
 float akugpu_frontend_frame_rate(akugpu_ctx *) { return 125.0f; }
 int akugpu_frontend_base_is_pre(akugpu_ctx *) { return g_pre; }
+int akugpu_frontend_base_dim(akugpu_ctx *) { return 3; }
+int akugpu_frontend_pre_legacy(akugpu_ctx *) { return g_legacy; }
 int akugpu_frontend_set_parameters(akugpu_ctx *, const char *module, const char *text)
 {
   std::string t(text);
@@ -160,6 +163,20 @@ int akugpu_gmm_score(akugpu_ctx *, const void *feats, int feats_f64, int64_t n_f
       if (lik < 1e-50) lik = 1e-50;
       if (precision == AKUGPU_F64) ((double *)out)[f * 4 + s] = lik; else ((float *)out)[f * 4 + s] = (float)log(lik);
     }
+  return 0;
+}
+
+// records of explicit feature rows: byte = (200 + 7 row + 3 s + b + 100 normalize + (int)x[row][0]) & 255
+int akugpu_gmm_lna(akugpu_ctx *, const void *feats, int feats_f64, int64_t n_frames, int precision, int lnabytes, int normalize,
+                   uint8_t *out)
+{
+  logf("gmm_lna frames=%lld precision=%d lnabytes=%d normalize=%d\n", (long long)n_frames, precision, lnabytes, normalize);
+  if (!feats_f64) { g_err = "stub: double features only"; return AKUGPU_E_ARG; }
+  const double *x = (const double *)feats;
+  for (int64_t f = 0; f < n_frames; f++)
+    for (int s = 0; s < 4; s++)
+      for (int b = 0; b < lnabytes; b++)
+        out[((size_t)f * 4 + s) * lnabytes + b] = (uint8_t)((200 + 7 * f + 3 * s + b + 100 * normalize + (int)x[f * 3]) & 255);
   return 0;
 }
 

@@ -2,8 +2,7 @@
 are aku/feacat.cc / aku/phone_probs.cc linked with integration/GpuFrontendModule.hh registered in FeatureGenerator and
 integration/GpuHmmSetHook.hh hooked into HmmSet (three added lines, oracle/build_ref.sh), against the real libakugpu.so.
 
-NOT YET RUN ON A GPU: the binaries were added when this round's GPU budget was spent (the same chain passes on the CPU
-against the fake ABI, tests/test_abi.py).  They are therefore opt-in -- AKUGPU_TEST_REFBIN=1 -- until their first GPU run."""
+The same chain also runs on the CPU against the fake ABI (tests/test_abi.py)."""
 import os
 import subprocess
 
@@ -15,8 +14,6 @@ from aaltoasr_b200 import formats
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AKUGPU_TEST_REFBIN") != "1",
-                                 reason="opt-in (AKUGPU_TEST_REFBIN=1): not yet run on a GPU, see the module docstring"),
               pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_feacat_gpu")), reason="oracle/_ref not built")]
 
 

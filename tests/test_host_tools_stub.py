@@ -167,7 +167,7 @@ def test_phone_probs_flags(tools, case):
     assert sorted(os.listdir(str(out))) == ["a%d.lna" % i for i in range(5)]
     assert calls(log, "model_read") == ["model_read_files m.gk m.mc m.ph"]
     assert calls(log, "read_clustering") == ["read_clustering c.gcl"] and calls(log, "min_evals") == ["min_evals 0.1 0.2"]
-    # -n: existing non-empty files are skipped, empty ones are not
+    # -n: any existing file is skipped with the reference's warning (stat() == 0, aku/phone_probs.cc:180-190), empty or not
     for f in os.listdir(str(out)):
         os.remove(str(out / f))
     open(str(out / "x0.lna"), "wb").write(b"keep")
@@ -175,8 +175,31 @@ def test_phone_probs_flags(tools, case):
     log = str(c["dir"] / "logn")
     r = run(exe, base + ["-b", "mdl", "-n"], log)
     assert r.returncode == 0, r.stderr.decode()
-    assert open(str(out / "x0.lna"), "rb").read() == b"keep" and open(str(out / "x1.lna"), "rb").read() == lna_file(range(fr[1]))
-    assert calls(log, "phone_probs")[0].split()[1] == "n_utts=4"
+    assert open(str(out / "x0.lna"), "rb").read() == b"keep" and open(str(out / "x1.lna"), "rb").read() == b""
+    assert r.stderr.decode().count("WARNING: skipping existing lna file ") == 2
+    assert ("WARNING: skipping existing lna file %s\n" % (out / "x1.lna")) in r.stderr.decode()
+    assert calls(log, "phone_probs")[0].split()[1] == "n_utts=3"
+    # -a keeps a leading dot (the reference strips the extension only at position > 0); a quote in a .gz name is no shell escape
+    formats.write_wav(str(c["dir"] / ".hid"), (np.arange(640) % 100).astype(np.int16), 16000)
+    rec = str(c["dir"] / "dot.recipe")
+    open(rec, "w").write("audio=%s/.hid lna=unused.lna\naudio=%s/a2.wav lna=it's.lna.gz\n" % (c["dir"], c["dir"]))
+    r = run(exe, ["-b", "mdl", "-c", c["cfg"], "-r", rec, "-o", str(out), "-a"])
+    assert r.returncode == 0 and os.path.exists(str(out / ".hid.lna")), r.stderr.decode()
+    r = run(exe, ["-b", "mdl", "-c", c["cfg"], "-r", rec, "-o", str(out)])
+    assert r.returncode == 0 and gzip.open(str(out / "it's.lna.gz")).read() == lna_file(range(fr[2])), r.stderr.decode()
+    # a negative start-time: frames before the file are generated through features_range + gmm_lna (the reference's loop
+    # starts at the negative frame, border-replicated windows), then the file's own records follow; start == end == file
+    # end writes a header-only file (used to index one past the buffer)
+    rec = str(c["dir"] / "neg.recipe")
+    open(rec, "w").write("audio=%s/a0.wav lna=n0.lna start-time=-0.024 end-time=0.016\n"
+                         "audio=%s/a2.wav lna=n2.lna start-time=0.04 end-time=0.04\n" % (c["dir"], c["dir"]))
+    log = str(c["dir"] / "logneg")
+    r = run(exe, ["-b", "mdl", "-c", c["cfg"], "-r", rec, "-o", str(out)], log)
+    assert r.returncode == 0, r.stderr.decode()
+    assert calls(log, "features_range") == ["features_range -3 0"] and calls(log, "gmm_lna") == ["gmm_lna frames=3 precision=0 lnabytes=2 normalize=1"]
+    neg = bytes((200 + 7 * f + 3 * s + b + 100) & 255 for f in range(3) for s in range(S) for b in range(2))
+    assert open(str(out / "n0.lna"), "rb").read() == lna_file([])[:5] + neg + lna_file(range(2))[5:]
+    assert open(str(out / "n2.lna"), "rb").read() == lna_file([])[:5]
     # -B / -I: the second of two batches is lines 4-5 (3 + 2); both flags are needed
     for f in os.listdir(str(out)):
         os.remove(str(out / f))
@@ -196,13 +219,13 @@ def test_phone_probs_flags(tools, case):
     for args, msg in ((["-r", c["recipe"], "-b", "m"], b"Must give --config"),
                       (["-c", c["cfg"], "-b", "m"], b"Must give --recipe"),
                       (base, b"Must give either --base or all --gk, --mc and --ph"),
-                      (base + ["-b", "m", "--lnabytes=3"], b"Invalid number of bytes for probabilities in LNA file"),
+                      (base + ["-b", "m", "--lnabytes=3"], b"Invalid number of LNA bytes"),
                       (base + ["-b", "m", "--frobnicate"], b"unknown option --frobnicate"),
                       (["-c", str(c["dir"] / "none.cfg"), "-r", c["recipe"], "-b", "m"], b"could not open file")):
         r = run(exe, args)
         assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
     r = run(exe, base + ["-b", "m"], env={"AKUGPU_STUB_MODEL_DIM": "5"})
-    assert r.returncode == 1 and b"Feature dimension (3) and model dimension (5) don't agree" in r.stderr
+    assert r.returncode == 1 and b"Gaussian dimension is 5 but feature dimension is 3." in r.stderr
     formats.write_wav(str(c["dir"] / "a2.wav"), np.zeros(640, np.int16), 8000)
     r = run(exe, base + ["-b", "m"])
     assert r.returncode == 1 and b"Audio file sample rate (8000 Hz) and model configuration (16000 Hz) don't agree." in r.stderr
@@ -253,6 +276,22 @@ def test_feacat_ranges_and_formats(tools, case):
     r = run(exe, ["-c", pre_cfg, "-s", "-1", "-e", "6", raw])
     got = np.array([[float(x) for x in ln.split()] for ln in r.stdout.decode().splitlines()])
     assert np.array_equal(got, rows_of([4, 4, 5, 6, 7, 8, 9, 9]))
+    # PreModule::set_file (aku/FeatureModules.cc:602-627): a header dimension other than the configured one is refused
+    # (it used to be trusted: rows mis-strided, host buffer over-read), and `legacy_file 1` = a ONE-byte header
+    body = open(raw, "rb").read()[4:]
+    bad = str(c["dir"] / "bad.raw")
+    open(bad, "wb").write(struct.pack("<i", 2) + body)
+    r = run(exe, ["-c", pre_cfg, bad])
+    assert r.returncode == 1 and b"PreModule: The file has invalid dimension" in r.stderr
+    legacy_cfg = str(c["dir"] / "legacy_pre.cfg")
+    open(legacy_cfg, "w").write("module\n{\n  name pre\n  type pre\n  dim 3\n  legacy_file 1\n}\n")
+    leg = str(c["dir"] / "leg.raw")
+    open(leg, "wb").write(bytes([3]) + body + b"\x00\x00")        # + a trailing partial row, never read
+    r = run(exe, ["-c", legacy_cfg, "-s", "0", "-e", "1", leg])
+    got = np.array([[float(x) for x in ln.split()] for ln in r.stdout.decode().splitlines()])
+    assert np.array_equal(got, rows_of([4, 5]))
+    r = run(exe, ["-c", legacy_cfg, raw])                              # int32 header read as one byte + misaligned rows
+    assert r.returncode == 0 or b"PreModule" in r.stderr
     # errors
     assert run(exe, ["-c", c["cfg"]]).returncode == 1 and run(exe, ["-c", c["cfg"], wav, wav]).returncode == 1
     r = run(exe, [wav])
