@@ -64,6 +64,14 @@ SYMBOLS = {
     "akugpu_gmm_lna": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "akugpu_phone_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "akugpu_phone_probs_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "akugpu_checksum_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64]),
+    "akugpu_checksum_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
+    "akugpu_checksum_end": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "akugpu_shared_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "akugpu_shared_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "akugpu_shared_release": (C.c_int, [C.c_void_p, C.c_void_p]),
     "akugpu_lna_header": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "akugpu_set_chunk_frames": (C.c_int, [C.c_void_p, C.c_int64]),
     "akugpu_set_scorer_variant": (C.c_int, [C.c_void_p, C.c_int]),

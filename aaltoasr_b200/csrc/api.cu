@@ -119,7 +119,7 @@ static bool tc16_needs_redo(akugpu_ctx *ctx, int mode)
 }
 
 static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f64, int64_t F, int precision, int lnabytes,
-                              int normalize, uint8_t *out, uint64_t *checksum_out, int *mode_out)
+                              int normalize, uint8_t *out, uint64_t *checksum_out, int *mode_out, bool utt_chk = false)
 {
   const int S = ctx->hm.S;
   if (lnabytes != 2 && lnabytes != 4) throw Error(AKUGPU_E_ARG, "lnabytes must be 2 or 4");
@@ -170,6 +170,7 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
       { StageScope sc(ctx, 2); launch_lna_f64(ctx, ctx->d_sll.as<double>(), chunk, S, nf, lnabytes, normalize, dst); }
     }
     if (checksum_out) launch_checksum(ctx, dst, nf * rec, ctx->d_chk.as<unsigned long long>());
+    if (utt_chk) checksum_update(ctx, dst, c0, nf);      // per-utterance sums; the records are still in L2
     if (out_host) {
       AKU_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
       AKU_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[b], 0));
@@ -188,16 +189,24 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
 }
 
 static void score_to_lna(akugpu_ctx *ctx, const void *d_feats, int feats_f64, int64_t F, int precision, int lnabytes,
-                         int normalize, uint8_t *out, uint64_t *checksum_out)
+                         int normalize, uint8_t *out, uint64_t *checksum_out, const std::vector<int64_t> *fo = nullptr,
+                         uint64_t *utt_checksums = nullptr)
 {
   int mode = 0;
-  score_to_lna_impl(ctx, d_feats, feats_f64, F, precision, lnabytes, normalize, out, checksum_out, &mode);
+  const bool utt_chk = fo && utt_checksums;
+  const int n_utts = utt_chk ? (int)fo->size() - 1 : 0;
+  if (utt_chk) checksum_begin(ctx, fo->data(), n_utts, (int64_t)ctx->hm.S * lnabytes);
+  score_to_lna_impl(ctx, d_feats, feats_f64, F, precision, lnabytes, normalize, out, checksum_out, &mode, utt_chk);
   if (tc16_needs_redo(ctx, mode)) {
     ctx->tc16_suspended = true;
-    try { score_to_lna_impl(ctx, d_feats, feats_f64, F, precision, lnabytes, normalize, out, checksum_out, &mode); }
+    try {
+      if (utt_chk) checksum_begin(ctx, fo->data(), n_utts, (int64_t)ctx->hm.S * lnabytes);
+      score_to_lna_impl(ctx, d_feats, feats_f64, F, precision, lnabytes, normalize, out, checksum_out, &mode, utt_chk);
+    }
     catch (...) { ctx->tc16_suspended = false; throw; }
     ctx->tc16_suspended = false;
   }
+  if (utt_chk) checksum_end(ctx, utt_checksums);
 }
 
 // Makes `src` (host or device) available on the device; returns the device pointer.
@@ -272,6 +281,8 @@ void akugpu_destroy(akugpu_ctx *ctx)
     if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
   }
+  for (void *p : ctx->shared_peer) cudaIpcCloseMemHandle(p);
+  for (void *p : ctx->shared_own) cudaFree(p);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -725,15 +736,16 @@ int akugpu_gmm_lna(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_
   API_END
 }
 
-int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts, int precision,
-                       int lnabytes, int normalize, uint8_t *out, int64_t *frame_offsets, uint64_t *checksum_out)
+int akugpu_phone_probs_ex(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts, int precision,
+                          int lnabytes, int normalize, uint8_t *out, int64_t *frame_offsets, uint64_t *checksum_out,
+                          uint64_t *utt_checksums)
 {
   API_BEGIN
   require_frontend(ctx);
   require_model(ctx);
   base_unit_bytes(ctx, false);       // PCM in: needs an audiofile base module
   const int dim = ctx->fe.mods[ctx->fe.last].dim;
-  if (dim != ctx->hm.D)
+  if (dim != ctx->hm.D)              // aku/phone_probs.cc:119-124
     throw Error(AKUGPU_E_STATE, fmt("Gaussian dimension is %d but feature dimension is %d.", ctx->hm.D, dim));
   std::vector<int64_t> uo, fo;
   frame_offsets_of(ctx, utt_offsets, n_utts, uo, fo);
@@ -745,8 +757,14 @@ int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_o
   ctx->d_feats.reserve((size_t)fo[n_utts] * dim * (feats_f64 ? 8 : 4));
   { StageScope sc(ctx, 0); frontend_run_batch(ctx, d_pcm, uo, fo, ctx->d_feats.p, feats_f64); }
   const void *d_feats = adapt_feats(ctx, ctx->d_feats.p, feats_f64, fo[n_utts]);
-  score_to_lna(ctx, d_feats, feats_f64, fo[n_utts], precision, lnabytes, normalize, out, checksum_out);
+  score_to_lna(ctx, d_feats, feats_f64, fo[n_utts], precision, lnabytes, normalize, out, checksum_out, &fo, utt_checksums);
   API_END
+}
+
+int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts, int precision,
+                       int lnabytes, int normalize, uint8_t *out, int64_t *frame_offsets, uint64_t *checksum_out)
+{
+  return akugpu_phone_probs_ex(ctx, pcm, utt_offsets, n_utts, precision, lnabytes, normalize, out, frame_offsets, checksum_out, NULL);
 }
 
 int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5])

@@ -250,5 +250,11 @@ struct akugpu_ctx {
   akugpu::DevBuf d_fe[8];
   std::vector<std::shared_ptr<akugpu::DevBuf>> fe_bufs;   // per-module output matrices (grow-only)
   akugpu::PinnedBuf h_in[2], h_out[2];
+  // per-utterance checksum sink (multigpu.cu): frame-offset table and 64-bit accumulators on the device
+  akugpu::DevBuf d_chk_fo, d_chk_acc;
+  bool chk_open = false;
+  int chk_n_utts = 0;
+  int64_t chk_rec = 0, chk_frames = 0, chk_first = 0;
+  std::vector<void *> shared_own, shared_peer;   // akugpu_shared_alloc / akugpu_shared_open buffers still held
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
 };

@@ -206,8 +206,13 @@ gmm_diag_f32(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
     const int meta = reinterpret_cast<const int *>(cs + TC)[warp];
 
     // This warp is done with the stage buffer; the last of the 8 warps re-arms it.
+    // Hand-off of the buffer to the async proxy (WAR): every warp's reads of the stage are ordered before its count
+    // (syncwarp + release fence + atomic), the last warp's count is followed by an acquire fence and the proxy fence,
+    // then the bulk copy.  compute-sanitizer racecheck does not model this counter and reports the copy against the
+    // reads (profiles/r02_sanitizer.txt); the first fill / refill -> read direction is the mbarrier's complete_tx.
     __syncwarp();
     if (lane == 0) {
+      __threadfence_block();
       const int old = atomicAdd(&done_cnt[b], 1);
       if (old == NW - 1) {
         done_cnt[b] = 0;

@@ -50,6 +50,11 @@ void launch_lna_f64(akugpu_ctx *ctx, const double *lin, int64_t ldF, int S, int6
                     uint8_t *out);
 void launch_checksum(akugpu_ctx *ctx, const uint8_t *buf, int64_t nbytes, unsigned long long *acc);
 
+// multigpu.cu: per-utterance checksum sink
+void checksum_begin(akugpu_ctx *ctx, const int64_t *frame_offsets, int n_utts, int64_t rec_bytes);
+void checksum_update(akugpu_ctx *ctx, const uint8_t *records, int64_t first_frame, int64_t n_frames);
+void checksum_end(akugpu_ctx *ctx, uint64_t *out);
+
 // model.cu
 void model_read_clustering(const std::string &gcl_path, HostModel &hm);
 void model_set_clustering(HostModel &hm, int n_clusters, const int32_t *gauss_index, const int32_t *cluster_index, int64_t n_pairs);

@@ -17,9 +17,15 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+class DevPtr(int):
+    """A raw DEVICE address (e.g. a peer buffer mapped by shared_open, plus an offset) passed where a buffer is expected."""
+
+
 def _ptr(x):
     if x is None:
         return None
+    if isinstance(x, DevPtr):
+        return C.c_void_p(int(x))
     if _is_torch(x):
         if not x.is_contiguous():
             raise ValueError("tensor must be contiguous")
@@ -291,9 +297,10 @@ class AkuGpu:
         return out
 
     def phone_probs(self, pcm, utt_offsets=None, precision=F32, lnabytes=2, normalize=True, out=None, discard=False,
-                    checksum=False):
+                    checksum=False, utt_checksums=False):
         """PCM -> LNA records for a batch of utterances.  Returns (records [F x S*lnabytes] or None,
-        frame_offsets, checksum or None)."""
+        frame_offsets, checksum or None); with utt_checksums=True the third item is the array of per-utterance
+        order-sensitive checksums (akugpu_phone_probs_ex) instead.  `out` may be a DevPtr (raw device address)."""
         n = int(pcm.numel() if _is_torch(pcm) else pcm.size)
         uo = np.ascontiguousarray(utt_offsets if utt_offsets is not None else [0, n], dtype=np.int64)
         fo = np.zeros(len(uo), dtype=np.int64)
@@ -301,10 +308,46 @@ class AkuGpu:
             fo = self.frame_offsets(uo)
             out = np.empty((int(fo[-1]), self.num_states * lnabytes), dtype=np.uint8)
         chk = C.c_uint64(0)
+        if utt_checksums:
+            uc = np.zeros(len(uo) - 1, dtype=np.uint64)
+            self._ck(self._lib.akugpu_phone_probs_ex(self._h, _ptr(pcm), _ptr(uo), len(uo) - 1, precision, lnabytes,
+                                                     1 if normalize else 0, _ptr(out), _ptr(fo), None, _ptr(uc)))
+            return out, fo, uc
         self._ck(self._lib.akugpu_phone_probs(self._h, _ptr(pcm), _ptr(uo), len(uo) - 1, precision, lnabytes,
                                               1 if normalize else 0, _ptr(out), _ptr(fo),
                                               C.byref(chk) if checksum else None))
         return out, fo, (int(chk.value) if checksum else None)
+
+    # ---- utterance-sharded runs over several GPUs: checksum sink, buffers shared between the processes of a node ----
+    def checksum_begin(self, frame_offsets, rec_bytes):
+        fo = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        self._chk_n = len(fo) - 1
+        self._ck(self._lib.akugpu_checksum_begin(self._h, _ptr(fo), self._chk_n, int(rec_bytes)))
+
+    def checksum_update(self, records, first_frame, n_frames):
+        """records: DEVICE buffer (torch CUDA tensor or DevPtr) holding frames [first_frame, first_frame + n_frames)."""
+        self._ck(self._lib.akugpu_checksum_update(self._h, _ptr(records), int(first_frame), int(n_frames)))
+
+    def checksum_end(self):
+        out = np.zeros(self._chk_n, dtype=np.uint64)
+        self._ck(self._lib.akugpu_checksum_end(self._h, _ptr(out)))
+        return out
+
+    def shared_alloc(self, nbytes):
+        """(DevPtr, 64-byte handle) of a device buffer other processes of this node can map (CUDA IPC)."""
+        p = C.c_void_p(0)
+        h = np.zeros(64, dtype=np.uint8)
+        self._ck(self._lib.akugpu_shared_alloc(self._h, int(nbytes), C.byref(p), _ptr(h)))
+        return DevPtr(p.value), h.tobytes()
+
+    def shared_open(self, handle):
+        p = C.c_void_p(0)
+        h = np.frombuffer(bytes(handle), dtype=np.uint8).copy()
+        self._ck(self._lib.akugpu_shared_open(self._h, _ptr(h), C.byref(p)))
+        return DevPtr(p.value)
+
+    def shared_release(self, ptr):
+        self._ck(self._lib.akugpu_shared_release(self._h, C.c_void_p(int(ptr))))
 
     def lna_header(self, lnabytes):
         buf = np.zeros(5, dtype=np.uint8)

@@ -18,6 +18,13 @@ utterances are independent, no data-path collective).
           launches is reported next to it
   cpu_baseline : the reference's own FeatureGenerator + HmmSet code (oracle/_ref, built from
           /root/reference) on the host cores, on a bounded sample of the same workload
+  sub_records : the other BASELINE.json configs in the same driver-run line (each a small, separately timed run):
+          N = 1: parity_mode_f64 (config-2 model in the byte-exact double arithmetic), config3_feature_sweep,
+                 config5_full_covariance (+ its own cpu_baseline), config4_model_1gpu (10000 x 32 on one GPU)
+          N > 1: config4 (100 h sharded by utterance over the N GPUs, 10000 x 32: model broadcast, frame-count
+                 all-gather, LPT partition, per-rank writers AND the LNA gather to one writer rank -- fused p2p stores
+                 and ncclSend/Recv -- with a checksum sink, 1-vs-N per-utterance checksum check), host_d2h (the
+                 concurrent PCIe probe that explains the e2e curve)
 """
 import argparse
 import json
@@ -322,7 +329,7 @@ def bench_feature_sweep(args, local):
             "sweep": sweep, "cpu_baseline": None}
 
 
-def bench_full_cov(args, local):
+def bench_full_cov(args, local, cpu_baseline=False):
     """BASELINE.json configs[4]: 2000-state x 16-mixture full-covariance pool (FullCovarianceGaussian; the subspace
     classes are dead code in the reference build), features resident -> LNA, tensor-core expanded form."""
     import torch
@@ -347,8 +354,8 @@ def bench_full_cov(args, local):
     full = np.einsum("gik,gjk->gij", A, A) * 0.1
     full[:, np.arange(D), np.arange(D)] += rng.uniform(0.5, 2, (G, D)) * sd ** 2
     t0 = time.time()
-    eng.model_load_full(np.arange(0, G + 1, M, dtype=np.int32), np.arange(G, dtype=np.int32),
-                        rng.dirichlet(np.ones(M), S).reshape(-1), means, full)
+    weights = rng.dirichlet(np.ones(M), S).reshape(-1)
+    eng.model_load_full(np.arange(0, G + 1, M, dtype=np.int32), np.arange(G, dtype=np.int32), weights, means, full)
     log("config 5: model packed in %.1f s, %d frames" % (time.time() - t0, F))
     feats_d = torch.from_numpy(feats).cuda()
     out_d = torch.empty((F, S * LNABYTES), dtype=torch.uint8, device="cuda")
@@ -371,6 +378,17 @@ def bench_full_cov(args, local):
     mma_flop = 2.0 * Kp * G * (-(-F // 128) * 128) * args.steps
     achieved = mma_flop / (gmm_ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    cpu = None
+    if cpu_baseline:
+        try:
+            n_sub = 32
+            g = np.arange(n_sub * M)
+            sub = dict(mix_offsets=np.arange(0, n_sub * M + 1, M, dtype=np.int32), mix_gauss=np.arange(n_sub * M, dtype=np.int32),
+                       mix_weight=weights[:n_sub * M], means=means[g], full_covs=full[g])
+            cpu = sub_full_cov_cpu_baseline(sub, feats[:128].astype(np.float64), S)
+        except Exception as e:
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+    useful_tf = 2.0 * L * G * F * args.steps / (gmm_ms * 1e-3) / 1e12
     eng.close()
     return {"metric": "acoustic frames/sec (full-covariance GMM log-lik -> LNA)", "value": F / (ms * 1e-3), "unit": "frames/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -381,13 +399,432 @@ def bench_full_cov(args, local):
                     "d2h_bytes_per_step": int(F * S * LNABYTES), "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "gmm_tc16_kernel<0> (tcgen05 kind::f16, fp16 hi/lo-split exponential form, A' and B' streamed, K' = %d issued for %d useful terms)" % (Kp, L),
-                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "bound": "tensor", "achieved": useful_tf, "peak": peak, "unit": "TFLOP/s", "frac": useful_tf / peak,
                          "traffic": None, "launches": int(gmm_launches), "stage_ms": {"gmm+expand": gmm_ms, "lna": st["lna"][0]},
-                         "useful_flop_per_frame": 2.0 * L * G},
-            "cpu_baseline": None}
+                         "algorithmic_flop_per_frame": 2.0 * L * G,
+                         "algorithmic": "2 K G per frame with K = D(D+3)/2 = %d (SURVEY.md 8d, the reference's own exponential form)" % L,
+                         "issued_mma": {"achieved": achieved, "unit": "TFLOP/s", "frac_of_peak": achieved / peak, "k_issued": Kp, "k_algorithmic": L}},
+            "cpu_baseline": cpu}
 
 
 # --------------------------------------------------------------------------------------
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def timed_region(torch, dist, world, stream, fn, steps):
+    """barrier + synchronize on both sides, CUDA events on the launching stream, MAX over ranks (ms for `steps` calls)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def scorer_roofline(eng, st, F, steps, ms_total, S, M, D=39):
+    """Roofline record of the dominant kernel (gmm_tc16_kernel) from the stage timers of the timed region.
+    `achieved` counts ALGORITHMIC flops: SURVEY.md section 8(d)'s GEMM-form figure 2 (2D+1) S M per frame; the MMA work the
+    kernel actually issues (three fp16 split products over whole K16 steps) is reported beside it."""
+    peaks = _peaks()
+    hbm_peak, hbm_src = measured_peaks()
+    gmm_ms, gmm_launches = st["gmm"]
+    frames_per_launch = F * steps / max(1, gmm_launches)
+    avg_ms = gmm_ms / max(1, gmm_launches)
+    G = S * M
+    alg_flop_per_frame = 2.0 * (2 * D + 1) * G
+    achieved = alg_flop_per_frame * frames_per_launch / (avg_ms * 1e-3) / 1e12
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)       # kernel timed inside a long step -> the sustained figure
+    nch = -(-(2 * D + 2) // 16)
+    Kp = 3 * nch * 16
+    comps = -(-S * (-(-M // 16) * 16) // 128) * 128
+    frames_pad = -(-int(frames_per_launch) // 128) * 128
+    issued = 2.0 * Kp * comps * frames_pad / (avg_ms * 1e-3) / 1e12
+    bytes_per_frame = D * 4 + S * 4                                # features in, state log-likelihoods out
+    param_bytes = comps * (-(-2 * nch // 4) * 64) * 2
+    alg_bytes = bytes_per_frame * frames_per_launch + param_bytes
+    hbm_gbs = alg_bytes / (avg_ms * 1e-3) / 1e9
+    rates = eng.pipe_rates()
+    mufu = G * frames_per_launch / (avg_ms * 1e-3)
+    in_use = eng.scorer_in_use()
+    r = {"kernel": "gmm_tc16_kernel (tcgen05 kind::f16, fp16 hi/lo-split expanded form, A' resident in shared memory)",
+         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+         "traffic": None,
+         "algorithmic_flop_per_frame": alg_flop_per_frame,
+         "algorithmic": "2 (2D+1) S M per frame (SURVEY.md 8d, GEMM form) x frames per launch / average launch time",
+         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md sustained)",
+         "launches": int(gmm_launches), "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch,
+         "share_of_step": gmm_ms / (ms_total if ms_total > 0 else 1),
+         "issued_mma": {"achieved": issued, "unit": "TFLOP/s", "frac_of_peak": issued / peak_tf, "k_issued": Kp, "k_algorithmic": 2 * D + 1,
+                        "note": "tensor-pipe occupancy: three fp16 split products (hi.hi, hi.lo, lo.hi) over %d K16 steps" % nch},
+         "mufu_view": {"achieved": mufu, "peak": rates["ex2"], "unit": "exp2/s", "frac": mufu / rates["ex2"]},
+         "hbm_view": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                      "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg_bytes},
+         "traffic_note": "DRAM bytes are not measurable inside the run; the ncu --set full capture of this kernel is profiles/r01_gmm_tc16_ncu_full.txt "
+                         "(762 MB per launch against 793 MB algorithmic)",
+         "fp32_pipe_peak_tflops": 2.0 * rates["tile_ffma2"] / 1e12,
+         "scorer_in_use": {0: "double path", 1: "gmm_diag_f32 (FP32 pipe)", 2: "gmm_tc_kernel (bf16x3)",
+                           3: "gmm_tc16_kernel (resident A')", 4: "gmm_tc16_kernel<0> (streaming A')",
+                           5: "gmm_tc16_kernel + gmm_diag_f32 for ill-conditioned states"}[in_use],
+         "expanded_form_q_max": eng.expanded_form_q(),
+         "stage_ms": {"frontend": st["frontend"][0], "gmm": gmm_ms, "lna": st["lna"][0]}}
+    if in_use != 3:
+        r["kernel"] = "WARNING: the arithmetic below assumes gmm_tc16_kernel; in use: " + r["scorer_in_use"]
+    return r
+
+
+def sub_parity_mode(args, torch, eng, stream, pcm_d, pcm_p, uo, fo, n_utts=24):
+    """The config-2 model in parity arithmetic (F64: the reference's operations in double, byte-identical LNA)."""
+    from aaltoasr_b200 import F64
+    n = min(n_utts, len(uo) - 1)
+    F = int(fo[n])
+    rec = N_STATES * LNABYTES
+    out_d = torch.empty((F, rec), dtype=torch.uint8, device="cuda")
+    out_p = torch.empty((F, rec), dtype=torch.uint8).pin_memory()
+    sub_uo = uo[:n + 1]
+    ns = int(uo[n])
+    eng.phone_probs(pcm_d[:ns], sub_uo, precision=F64, lnabytes=LNABYTES, out=out_d)
+    ms = _event_time(torch, stream, lambda: eng.phone_probs(pcm_d[:ns], sub_uo, precision=F64, lnabytes=LNABYTES, out=out_d), 2)
+    ms_e = _event_time(torch, stream, lambda: eng.phone_probs(pcm_p[:ns], sub_uo, precision=F64, lnabytes=LNABYTES, out=out_p), 2)
+    return {"metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA), parity mode", "value": F / (ms * 1e-3), "unit": "frames/s",
+            "dtype": "f64", "steps": 2, "ms_per_step": ms,
+            "config": {"workload": "%d utterances x 10 s of the headline workload, F64 parity arithmetic (gmm_diag_f64 + lna_f64: the "
+                                   "reference's operations in double, LNA bytes identical to the reference's)" % n, "frames": F},
+            "e2e": {"value": F / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": ns * 2, "d2h_bytes_per_step": F * rec, "ms_per_step": ms_e}}
+
+
+def sub_full_cov_cpu_baseline(model_sub, feats, n_states_full):
+    """The reference's FullCovarianceGaussian path (aku::HmmSet from oracle/_ref) on all host cores, on a sub-model
+    (its loader spends ~18 ms per full-covariance Gaussian); cost per frame is linear in the number of Gaussians."""
+    import multiprocessing as mp
+    from aaltoasr_b200 import formats
+    from oracle import ref
+    if not ref.available():
+        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built on this box"}
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as tmp:
+        base = os.path.join(tmp, "full")
+        formats.write_model(base, **model_sub)
+        np.save(os.path.join(tmp, "x.npy"), feats)
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_ref_fullcov_worker, [(base, os.path.join(tmp, "x.npy"))] * cores)
+    n_sub = len(model_sub["mix_offsets"]) - 1
+    frames = sum(r[1] for r in res)
+    secs = max(r[0] for r in res)
+    scale = n_sub / float(n_states_full)
+    return {"value": frames / secs * scale, "unit": "frames/s", "cores": cores, "kind": "reference",
+            "sample": "%d frames per core on %d cores against %d of the %d states (aku::HmmSet, FullCovarianceGaussian exponential "
+                      "form; %.2f s), scaled by %d/%d: cost per frame is linear in the Gaussians; model load excluded" % (
+                          res[0][1], cores, n_sub, n_states_full, secs, n_sub, n_states_full)}
+
+
+def _ref_fullcov_worker(a):
+    base, xpath = a
+    from oracle import ref
+    M = ref.Model(base)
+    x = np.load(xpath)
+    t0 = time.perf_counter()
+    M.state_likelihoods(x)
+    dt = time.perf_counter() - t0
+    M.close()
+    return dt, int(x.shape[0])
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: 100 h sharded by utterance over the GPUs of the node, 10000 x 32
+C4_STATES, C4_MIX = 10000, 32
+C4_CLIPS, C4_CLIP_SAMPLES = 32, 15 * SAMPLE_RATE
+
+
+def c4_utterance_lengths(n_total):
+    """Jittered utterance lengths U(5, 15) s, the same table on every rank."""
+    return (np.random.default_rng(4000).uniform(5.0, 15.0, n_total) * SAMPLE_RATE).astype(np.int64)
+
+
+def c4_audio(clips, lens, ids):
+    """Utterance u = a window of clip u % 32: fully determined by the global utterance id, so any rank can rebuild any
+    utterance (the 1-vs-N checksum check needs that)."""
+    total = int(lens[ids].sum())
+    pcm = np.empty(total, dtype=np.int16)
+    uo = np.zeros(len(ids) + 1, dtype=np.int64)
+    o = 0
+    for k, u in enumerate(int(x) for x in ids):
+        n = int(lens[u])
+        start = (u * 7919) % (C4_CLIP_SAMPLES - n + 1)
+        pcm[o:o + n] = clips[u % C4_CLIPS][start:start + n]
+        o += n
+        uo[k + 1] = o
+    return pcm, uo
+
+
+def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
+    """One pass of the hot path over this rank's shard in every payload mode; see the module docstring."""
+    from contextlib import nullcontext
+    from aaltoasr_b200 import AkuGpu, F32, multigpu as mg, synth
+    from aaltoasr_b200.engine import DevPtr
+    from aaltoasr_b200.partition import gather_utterance_table
+    t_setup = time.time()
+    eng = AkuGpu(local)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.frontend_load_config_text(synth.mfcc39_config(SAMPLE_RATE))
+    n_total = utts_per_gpu * world
+    lens = c4_utterance_lengths(n_total)
+    clips = [synth.synth_audio(4000 + i, C4_CLIP_SAMPLES, SAMPLE_RATE) for i in range(C4_CLIPS)]
+    collectives = []
+    # ---- model: built by rank 0, broadcast as one packed buffer
+    model = None
+    if rank == 0:
+        pcm16 = np.concatenate(clips[:16])
+        feats, _ = eng.features(pcm16, np.arange(17, dtype=np.int64) * C4_CLIP_SAMPLES, dtype=np.float64)
+        model = synth.synth_diag_model(4999, feats, C4_STATES, C4_MIX)
+    if world > 1:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        model, nbytes = mg.broadcast_model(model, 0)
+        torch.cuda.synchronize()
+        collectives.append({"op": "broadcast (packed model arrays, rank 0 -> all)", "bytes": nbytes, "ms": 1e3 * (time.perf_counter() - t0)})
+    t0 = time.time()
+    eng.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
+    t_pack = time.time() - t0
+    S = eng.num_states
+    rec = S * LNABYTES
+    # ---- frame counts: every rank looks at every world-th utterance, all-gather, partition redundantly
+    ids_seen = np.arange(rank, n_total, world)
+    counts_seen = np.array([eng.num_frames(int(lens[u])) for u in ids_seen], dtype=np.int64)
+    if world > 1:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        n_frames = mg.gather_frame_counts(ids_seen, counts_seen, n_total)
+        collectives.append({"op": "all_gather (int32 n_frames[utt])", "bytes": int(n_total * 8), "ms": 1e3 * (time.perf_counter() - t0)})
+    else:
+        n_frames = counts_seen
+    parts = mg.partition(n_frames, world, args.split)
+    mine = parts[rank]
+    pcm, uo = c4_audio(clips, lens, mine)
+    my_frames = n_frames[mine]
+    fo = np.concatenate([[0], np.cumsum(my_frames)]).astype(np.int64)
+    F_mine, F_total = int(fo[-1]), int(n_frames.sum())
+    pcm_p = torch.from_numpy(pcm).pin_memory()
+    pcm_d = pcm_p.cuda()
+    max_frames = 2 * 148 * 128                                     # one chunk of the scorer (two waves)
+    plan = mg.GatherPlan(n_frames, parts, max_frames, rec, writer=0)
+    slot_bytes = plan.slot_bytes
+    log("config 4 rank %d: %d utterances, %d frames (%.1f GB of LNA), %d sub-batches, model packed in %.1f s, setup %.1f s" % (
+        rank, len(mine), F_mine, F_mine * rec / 1e9, len(plan.sched[rank]), t_pack, time.time() - t_setup))
+
+    src_chk = np.zeros(len(mine), dtype=np.uint64)
+
+    def produce_into(want_chk):
+        def produce(u0, u1, out):
+            a, b = int(uo[u0]), int(uo[u1])
+            _, _, uc = eng.phone_probs(pcm_d[a:b], uo[u0:u1 + 1] - uo[u0], precision=F32, lnabytes=LNABYTES, out=out,
+                                       utt_checksums=want_chk)
+            if want_chk:
+                src_chk[u0:u1] = uc
+        return produce
+
+    def timed(fn):
+        return timed_region(torch, dist, world, stream, fn, 1)
+
+    res = {}
+    # ---- (1) device-resident: records into two rotating device slots
+    dev_slots = [torch.empty(slot_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    mg.run_writers(produce_into(False), my_frames[:min(len(mine), 60)], max_frames, dev_slots)          # warm-up
+    eng.stage_times_reset(True)
+    l0 = eng.launch_count()
+    ms_res = timed(lambda: mg.run_writers(produce_into(False), my_frames, max_frames, dev_slots))
+    launches = eng.launch_count() - l0
+    st = eng.stage_times()
+    eng.stage_times_reset(False)
+    # ---- (2) per-rank writers end to end: pinned host PCM in, records to two rotating pinned host slots
+    e2e_chunks = 4
+    host_slots = [torch.empty(e2e_chunks * slot_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def produce_host(u0, u1, out):
+        a, b = int(uo[u0]), int(uo[u1])
+        eng.phone_probs(pcm_p[a:b], uo[u0:u1 + 1] - uo[u0], precision=F32, lnabytes=LNABYTES, out=out)
+    mg.run_writers(produce_host, my_frames[:min(len(mine), 60)], e2e_chunks * max_frames, host_slots)       # warm-up
+    ms_e2e = timed(lambda: mg.run_writers(produce_host, my_frames, e2e_chunks * max_frames, host_slots))
+    del host_slots
+    res.update({"value": F_total / (ms_res * 1e-3), "ms_per_step": ms_res,
+                "e2e": {"value": F_total / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(pcm.nbytes),
+                        "d2h_bytes_per_step": int(F_mine * rec), "ms_per_step": ms_e2e,
+                        "d2h_GBps_per_gpu": F_mine * rec / (ms_e2e * 1e-3) / 1e9,
+                        "note": "per-rank writers (the reference's -B/-I model): every rank streams its own records to pinned host memory, "
+                                "%d-chunk calls, two rotating host slots" % e2e_chunks}})
+    # ---- (3) LNA gather to the writer rank
+    gather = None
+    table_ok = None
+    if world > 1:
+        gather = {}
+        g_tok, g_free = dist.new_group(), dist.new_group()
+        for g in (g_tok, g_free):                                  # communicators created now, by all ranks together
+            dist.barrier(group=g)
+        sink_eng = AkuGpu(local) if rank == 0 else None
+        sink_stream = torch.cuda.Stream() if rank == 0 else None
+        if rank == 0:
+            sink_eng.set_stream(sink_stream.cuda_stream)
+        base = np.concatenate([[0], np.cumsum([int(plan.fo[r][-1]) for r in plan.senders])]).astype(np.int64)
+        sink_base = {r: int(base[i]) for i, r in enumerate(plan.senders)}
+        sink_fo = np.concatenate([plan.fo[r][:-1] + sink_base[r] for r in plan.senders] + [[int(base[-1])]]).astype(np.int64)
+        sink_ids = np.concatenate([plan.parts[r] for r in plan.senders])
+        recv_bytes = int(base[-1]) * rec
+
+        def sink(r, slot, f0, n):
+            sink_eng.checksum_update(slot, sink_base[r] + f0, n)
+
+        def sink_scope():
+            return torch.cuda.stream(sink_stream)
+        sunk = {}
+        for mode in ("p2p", "nccl"):
+            shared = peer_base = None
+            if mode == "p2p":
+                nslots = 2
+                handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    shared, h = eng.shared_alloc(len(plan.senders) * nslots * slot_bytes)
+                    handle.copy_(torch.frombuffer(bytearray(h), dtype=torch.uint8))
+                dist.broadcast(handle, 0)
+                if rank != 0:
+                    peer_base = eng.shared_open(handle.cpu().numpy().tobytes())
+                root = shared if rank == 0 else peer_base
+                idx = {r: i for i, r in enumerate(plan.senders)}
+
+                def peer_slot(r, j):
+                    return DevPtr(int(root) + (idx[r] * nslots + j) * slot_bytes)
+                token = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+                def run():
+                    with torch.cuda.stream(stream):
+                        mg.gather_p2p(plan, rank, produce_into(True), sink, dev_slots, peer_slot, nslots, g_tok, g_free, token,
+                                      sink_scope if rank == 0 else nullcontext)
+                        if rank == 0:
+                            stream.wait_stream(sink_stream)          # the timed region ends after the sink's last checksum
+            else:
+                recv_slots = {r: [torch.empty(slot_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)] for r in plan.senders} \
+                    if rank == 0 else None
+
+                def run():
+                    with torch.cuda.stream(stream):
+                        mg.gather_nccl(plan, rank, produce_into(True), sink, dev_slots, recv_slots, None,
+                                       sink_scope if rank == 0 else nullcontext)
+                        if rank == 0:
+                            stream.wait_stream(sink_stream)
+            if rank == 0:
+                sink_eng.checksum_begin(sink_fo, rec)
+            ms = timed(run)
+            if rank == 0:
+                sunk[mode] = sink_eng.checksum_end()
+            gather[mode] = {"value": F_total / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+                            "bytes_into_writer": recv_bytes, "nvlink_GBps_into_writer": recv_bytes / (ms * 1e-3) / 1e9}
+            if mode == "p2p":
+                torch.cuda.synchronize(); dist.barrier()
+                if rank != 0:
+                    eng.shared_release(peer_base)
+                dist.barrier()
+                if rank == 0:
+                    eng.shared_release(shared)
+            else:
+                recv_slots = None
+        gather["p2p"]["how"] = ("lna_f32_rows of every rank stores its records straight into the writer's rotating buffer (CUDA-IPC mapped peer "
+                                "memory over NVLink): epilogue + gather in one kernel; NCCL carries two 8-byte tokens per sub-batch")
+        gather["nccl"]["how"] = "records into a local send slot, ncclSend -> ncclRecv into the writer's rotating slots"
+        # ---- the table: (utterance, n_frames, source checksum) all-gathered; the writer compares what arrived
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        tf, tc, owner = gather_utterance_table(mine, my_frames, src_chk, n_total)
+        collectives.append({"op": "all_gather (utterance, n_frames, checksum) table", "bytes": int(n_total * 24), "ms": 1e3 * (time.perf_counter() - t0)})
+        collectives.append({"op": "LNA gather to rank 0 (p2p stores / ncclSend+Recv), per step", "bytes": recv_bytes})
+        if rank == 0:
+            gather["sink_checksums_equal_source"] = bool(all(np.array_equal(sunk[m], tc[sink_ids]) for m in sunk))
+            table_ok = bool(np.array_equal(tf, n_frames) and all(owner[i] == r for r in range(world) for i in parts[r][:4]))
+        sink_eng and sink_eng.close()
+    else:
+        # one GPU: the per-utterance checksums of the run itself (two differently batched passes must agree)
+        mg.run_writers(produce_into(True), my_frames, max_frames, dev_slots)
+        tc = src_chk.copy()
+    # ---- 1-GPU-vs-N-GPU: rank 0 alone rescoring a sample of ALL utterances, batched differently
+    check = None
+    if rank == 0:
+        sample = np.arange(0, n_total, max(1, n_total // 256))[:256]
+        spcm, suo = c4_audio(clips, lens, sample)
+        _, _, sc = eng.phone_probs(spcm, suo, precision=F32, lnabytes=LNABYTES, discard=True, utt_checksums=True)
+        check = {"checksum_1_vs_N_equal": bool(np.array_equal(sc, tc[sample])), "checked_utterances": int(len(sample)),
+                 "how": "rank 0 alone rescoring every %d-th utterance of the whole list in one differently batched call; per-utterance "
+                        "order-sensitive checksums (akugpu_phone_probs_ex) against the N-rank run's table" % max(1, n_total // 256)}
+    line = None
+    if rank == 0:
+        line = {"metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA)", "unit": "frames/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                "higher_is_better": True, "scaling": "weak", "dtype": "f16x2->f32", "data": "synthetic",
+                "config": {"workload": "%.1f h @16 kHz sharded by utterance: %d utterances of 5-15 s (%d per GPU), 39-dim MFCC+d+dd, "
+                                       "10000-state x 32-mix diag GMM, 2-byte LNA" % (lens.sum() / SAMPLE_RATE / 3600.0, n_total, utts_per_gpu),
+                           "utterances": int(n_total), "frames": F_total, "split": args.split, "sub_batch_frames": max_frames,
+                           "lna_bytes_total": int(F_total * rec), "l2_policy": "every sub-batch writes 0.76 GB of records: far beyond L2"},
+                "gpu_launches": int(launches),
+                "roofline": scorer_roofline(eng, st, F_mine, 1, ms_res, C4_STATES, C4_MIX),
+                "gather": gather, "collectives": collectives, "table_ok": table_ok}
+        line.update(res)
+        line.update(check)
+    eng.close()
+    return line
+
+
+def host_d2h_probe(torch, dist, rank, world, stream):
+    """All ranks copy device -> pinned host at the same time: what the host side of PCIe gives N GPUs together."""
+    out = {}
+    for mb in (64, 1024):
+        n = mb << 20
+        src = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dst = torch.empty(n, dtype=torch.uint8).pin_memory()
+        dst.copy_(src, non_blocking=True)
+        reps = 4 if mb >= 1024 else 16
+        ms = timed_region(torch, dist, world, stream, lambda: dst.copy_(src, non_blocking=True), reps)
+        out["d2h_%dMB_aggregate_GBps" % mb] = world * n * reps / (ms * 1e-3) / 1e9
+        ms = timed_region(torch, dist, world, stream, lambda: src.copy_(dst, non_blocking=True), reps)
+        out["h2d_%dMB_aggregate_GBps" % mb] = world * n * reps / (ms * 1e-3) / 1e9
+        del src, dst
+    try:
+        out["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+        out["cpus_visible"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return out
+
+
+class Watchdog:
+    """A sub-record that hangs (a collective waiting for a rank that failed) must not take the headline with it: when the
+    timer fires, rank 0 prints the line it has -- the sub-record marked as timed out -- and every rank leaves."""
+
+    def __init__(self, seconds, on_fire):
+        self.t = threading.Timer(seconds, self._fire)
+        self.t.daemon = True
+        self.on_fire = on_fire
+
+    def _fire(self):
+        try:
+            self.on_fire()
+        finally:
+            sys.stdout.flush()
+            os._exit(0)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.t.cancel()
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,11 +833,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=None, help="utterances per GPU (default: the BASELINE config)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
-                    help="BASELINE.json config: 2 = 1000 utts, 5000x16 (default, the metric's config); "
-                         "3 = feature-only sweep (8-64 kHz, 256-2048-point windows); "
-                         "4 = 100 h over 8 GPUs (4500 utts per GPU), 10000x32, LNA discarded after the checksum-free write; "
-                         "5 = 2000-state x 16-mix full-covariance pool")
+                    help="BASELINE.json config to run on its own: 2 = 1000 utts, 5000x16 (default, the metric's config, with the "
+                         "other configs as sub_records); 3 = feature-only sweep; 4 = 100 h over the GPUs (4500 utts per GPU), "
+                         "10000x32, with the LNA gather; 5 = 2000-state x 16-mix full-covariance pool")
+    ap.add_argument("--split", default="lpt", choices=["lpt", "reference"],
+                    help="config 4: utterance partition (lpt = by frame count; reference = aku/Recipe.cc:63-115, what -B N -I i gives)")
+    ap.add_argument("--c4-utts", type=int, default=None, help="config 4 sub-record: utterances per GPU (default 4500 at N > 1, 300 at N = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true")
+    ap.add_argument("--sub-timeout", type=int, default=420, help="seconds the multi-GPU sub-records may take before they are abandoned")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -421,7 +862,6 @@ def main():
         # NCCL prints its version banner / debug lines to stdout; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    global N_STATES, N_MIX, WORKLOAD
     if args.config in (3, 5):
         if world > 1:
             raise SystemExit("bench.py --config %d is a single-GPU configuration" % args.config)
@@ -429,9 +869,15 @@ def main():
         print(json.dumps(line))
         return
     if args.config == 4:
-        N_STATES, N_MIX = 10000, 32
-        WORKLOAD = "100 h @16 kHz sharded by utterance (4500 x 10 s per GPU), 39-dim MFCC+d+dd, 10000-state x 32-mix diag GMM, 2-byte LNA"
-    n_utts = args.utts if args.utts else (4500 if args.config == 4 else N_UTTS)
+        line = bench_config4(args, torch, dist, rank, world, local, args.utts or args.c4_utts or 4500)
+        if rank == 0:
+            line["vs_baseline"] = None
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    n_utts = args.utts if args.utts else N_UTTS
 
     eng = AkuGpu(local)
     stream = torch.cuda.Stream()
@@ -448,10 +894,7 @@ def main():
     log("rank %d: %d utterances, %d frames, audio generated in %.1f s" % (rank, n_utts, F, time.time() - t0))
 
     pcm_d = torch.from_numpy(pcm).cuda()
-    # LNA of a step stays in HBM when it fits (12.5 GB for config 2); config 4 emits 112 GB per GPU, so
-    # its records go to the library's per-chunk device buffer instead (same kernels, same bytes written)
-    keep_out = F * rec <= 60e9
-    out_d = torch.empty((F, rec), dtype=torch.uint8, device="cuda") if keep_out else None
+    out_d = torch.empty((F, rec), dtype=torch.uint8, device="cuda")     # 12.5 GB: the LNA of a step stays in HBM
     # e2e buffers: pinned PCM; LNA drained through one pinned buffer per sub-batch (a writer would stream it out)
     # utterances per e2e call: 250 on one GPU; fewer per rank when several ranks share the host (pinned memory per rank
     # = one sub-batch of LNA: 3.1 GB at 250 utterances)
@@ -459,13 +902,8 @@ def main():
     pcm_p = torch.from_numpy(pcm).pin_memory()
     out_p = torch.empty((int(fo[sub]), rec), dtype=torch.uint8).pin_memory()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def step_resident():
-        eng.phone_probs(pcm_d, uo, precision=F32, lnabytes=LNABYTES, out=out_d, discard=not keep_out)
+        eng.phone_probs(pcm_d, uo, precision=F32, lnabytes=LNABYTES, out=out_d)
 
     def step_e2e():
         for u0 in range(0, n_utts, sub):
@@ -474,18 +912,7 @@ def main():
                             lnabytes=LNABYTES, out=out_p[:int(fo[u1] - fo[u0])])
 
     def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(steps):
-                fn()
-            e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return timed_region(torch, dist, world, stream, fn, steps)
 
     for _ in range(args.warmup):
         step_resident()
@@ -517,59 +944,61 @@ def main():
     value = total_frames * args.steps / (ms_res * 1e-3)
     e2e_val = total_frames * args.steps / (ms_e2e * 1e-3)
 
+    line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (the scorer), per launch, measured in the timed region ----
-        gmm_ms, gmm_launches = st["gmm"]
-        frames_per_launch = F * args.steps / max(1, gmm_launches)
-        avg_ms = gmm_ms / max(1, gmm_launches)
-        G = N_STATES * N_MIX
-        hbm_peak, hbm_src = measured_peaks()
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        # Dominant kernel = gmm_tc16_kernel (tcgen05, fp16 hi/lo split): per (frame tile, component tile) it issues
-        # 3 * NCH MMAs of M128 N128 K16 (NCH = ceil((2D+2)/16) = 5): MAIN = Ah.Bh, CORR = Ah.Bl + Al.Bh
-        D = 39
-        nch = -(-(2 * D + 2) // 16)
-        Kp = 3 * nch * 16                                      # K terms issued per (frame, component)
-        comps = -(-N_STATES * (-(-N_MIX // 16) * 16) // 128) * 128
-        frames_pad = -(-int(frames_per_launch) // 128) * 128
-        mma_flop = 2.0 * Kp * comps * frames_pad
-        achieved_tf = mma_flop / (avg_ms * 1e-3) / 1e12
-        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)  # kernel timed inside a long step -> sustained figure
-        useful_flop = G * D * 4.0 * frames_per_launch          # the reference's own count: sub, mul, mul, add per (component, dim)
-        bytes_per_frame = D * 4 + N_STATES * 4                 # features in, state log-likelihoods out
-        param_bytes = comps * (-(-2 * nch // 4) * 64) * 2      # B' = [Bh | Bl], fp16, k-blocks of 64
-        alg_bytes = bytes_per_frame * frames_per_launch + param_bytes
-        hbm_gbs = alg_bytes / (avg_ms * 1e-3) / 1e9
-        traffic = None
-        tr = os.path.join(ROOT, "profiles", "r01_gmm_tc16_ncu_full.txt")
-        if os.path.exists(tr):
-            for ln in open(tr):
-                if "traffic (dram read+write) bytes" in ln:
-                    traffic = float(ln.split(":")[1])
-        rates = eng.pipe_rates()
-        # second co-limit of this kernel: one exp2 per (frame, component) on the MUFU pipe
-        mufu_rate = G * frames_per_launch / (avg_ms * 1e-3)
-        roofline = {"kernel": "gmm_tc16_kernel (tcgen05 kind::f16, fp16 hi/lo-split expanded form, A' resident in shared memory)",
-                    "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                    "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md sustained)",
-                    "launches": int(gmm_launches), "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch,
-                    "share_of_step": gmm_ms / (ms_res if ms_res > 0 else 1),
-                    "issued_mma_flop_per_launch": mma_flop, "useful_flop_per_launch": useful_flop,
-                    "note": "K' = %d issued per component for %d useful terms (3 fp16 split products); co-limit MUFU: "
-                            "%.2e exp2/s of %.2e measured pipe rate" % (Kp, 2 * D, mufu_rate, rates["ex2"]),
-                    "mufu_view": {"achieved": mufu_rate, "peak": rates["ex2"], "unit": "exp2/s", "frac": mufu_rate / rates["ex2"]},
-                    "hbm_view": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,
-                                 "algorithmic_bytes_per_launch": alg_bytes},
-                    "fp32_pipe_peak_tflops": 2.0 * rates["tile_ffma2"] / 1e12,
-                    "scorer_in_use": {0: "double path", 1: "gmm_diag_f32 (FP32 pipe)", 2: "gmm_tc_kernel (bf16x3)",
-                                      3: "gmm_tc16_kernel (resident A')", 4: "gmm_tc16_kernel<0> (streaming A')",
-                                      5: "gmm_tc16_kernel + gmm_diag_f32 for ill-conditioned states"}[eng.scorer_in_use()],
-                    "expanded_form_q_max": eng.expanded_form_q(),
-                    "stage_ms": {"frontend": st["frontend"][0], "gmm": gmm_ms, "lna": st["lna"][0]}}
-        if eng.scorer_in_use() != 3:
-            roofline["note"] = "WARNING: the roofline arithmetic below assumes gmm_tc16_kernel; " + roofline["note"]
+        roofline = scorer_roofline(eng, st, F, args.steps, ms_res, N_STATES, N_MIX)
+        line = {
+            "metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2->f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if n_utts == N_UTTS else WORKLOAD.replace("1000 utterances", "%d utterances" % n_utts),
+                       "utterances_per_gpu": n_utts, "frames_per_gpu": F, "precision": "F32 throughput mode",
+                       "l2_policy": "inputs+outputs per step (%.1f GB) exceed L2; no flush needed" % (F * rec / 1e9),
+                       "parallelism": "utterance shards, one process per GPU, no data-path collective"},
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(pcm.nbytes),
+                    "d2h_bytes_per_step": int(F * rec), "ms_per_step": ms_e2e / args.steps,
+                    "d2h_GBps": F * rec / (ms_e2e / args.steps * 1e-3) / 1e9, "pcie_d2h_peak_GBps": d2h_gbs,
+                    "pcie_frac": (F * rec / (ms_e2e / args.steps * 1e-3) / 1e9) / d2h_gbs,
+                    "note": "LNA records leave the device at the PCIe rate; %d-utterance calls%s" % (
+                        sub, "; rank bound to the %d CPUs next to its GPU" % numa_cpus if numa_cpus else "")},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": None, "sub_records": {}}
+
+    # ---------------- sub-records: the other BASELINE configs, in the same driver-run line ----------------
+    subs = {}
+    if not args.no_sub_records:
+        def guarded(name, fn):
+            try:
+                t0 = time.time()
+                r = fn()
+                if r is not None:
+                    r["wall_s"] = time.time() - t0
+                return r
+            except Exception as e:      # a sub-record never takes the headline down; the failure is recorded
+                log("sub-record %s failed: %r" % (name, e))
+                return {"failed": repr(e)}
+        if world == 1:
+            subs["parity_mode_f64"] = guarded("parity_mode_f64", lambda: sub_parity_mode(args, torch, eng, stream, pcm_d, pcm_p, uo, fo))
+    del out_d, out_p, pcm_d, pcm_p
+    eng.close()
+    torch.cuda.empty_cache()
+    if not args.no_sub_records:
+        sub_args = argparse.Namespace(**vars(args))
+        sub_args.steps, sub_args.warmup, sub_args.utts = 3, 3, None
+        if world == 1:
+            subs["config3_feature_sweep"] = guarded("config3", lambda: bench_feature_sweep(sub_args, local))
+            subs["config5_full_covariance"] = guarded("config5", lambda: bench_full_cov(sub_args, local, cpu_baseline=not args.no_cpu_baseline))
+            subs["config4_model_1gpu"] = guarded("config4", lambda: bench_config4(sub_args, torch, dist, rank, world, local, args.c4_utts or 300))
+        else:
+            def bail():
+                if rank == 0:
+                    subs.setdefault("config4", {"failed": "timed out after %d s (see stderr)" % args.sub_timeout})
+                    line["sub_records"] = subs
+                    print(json.dumps(line))
+            with Watchdog(args.sub_timeout, bail):
+                subs["host_d2h"] = guarded("host_d2h", lambda: host_d2h_probe(torch, dist, rank, world, stream))
+                subs["config4"] = guarded("config4", lambda: bench_config4(sub_args, torch, dist, rank, world, local, args.c4_utts or 4500))
+
+    if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -587,26 +1016,12 @@ def main():
                            "sample": "oracle/_ref not built on this box"}
             except Exception as e:   # the baseline is reported, never required
                 cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
-        line = {
-            "metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2->f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (n_utts == N_UTTS or args.config == 4) else WORKLOAD.replace("1000 utterances", "%d utterances" % n_utts),
-                       "utterances_per_gpu": n_utts, "frames_per_gpu": F, "precision": "F32 throughput mode",
-                       "l2_policy": "inputs+outputs per step (%.1f GB) exceed L2; no flush needed" % (F * rec / 1e9),
-                       "parallelism": "utterance shards, one process per GPU, no data-path collective"},
-            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(pcm.nbytes),
-                    "d2h_bytes_per_step": int(F * rec), "ms_per_step": ms_e2e / args.steps,
-                    "d2h_GBps": F * rec / (ms_e2e / args.steps * 1e-3) / 1e9, "pcie_d2h_peak_GBps": d2h_gbs,
-                    "pcie_frac": (F * rec / (ms_e2e / args.steps * 1e-3) / 1e9) / d2h_gbs,
-                    "note": "LNA records leave the device at the PCIe rate; %d-utterance calls%s" % (
-                        sub, "; rank bound to the %d CPUs next to its GPU" % numa_cpus if numa_cpus else "")},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+        line["cpu_baseline"] = cpu
+        line["sub_records"] = subs
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":

@@ -202,6 +202,39 @@ int akugpu_phone_probs(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_o
                        int precision, int lnabytes, int normalize,
                        uint8_t *out, int64_t *frame_offsets, uint64_t *checksum_out);
 
+/* The same call that also returns one order-sensitive 64-bit checksum per utterance (utt_checksums [n_utts], host; may be
+ * NULL), computed on the device from the records as they are written (see akugpu_checksum_begin for the definition).
+ * An utterance's checksum does not depend on which other utterances shared the call or on which GPU ran it: the
+ * utterance-sharded run over N GPUs (the reference's `-B N -I i` split, aku/phone_probs.cc:78-79,
+ * 135-139) is checked against the single-GPU run with it. */
+int akugpu_phone_probs_ex(akugpu_ctx *ctx, const int16_t *pcm, const int64_t *utt_offsets, int n_utts,
+                          int precision, int lnabytes, int normalize,
+                          uint8_t *out, int64_t *frame_offsets, uint64_t *checksum_out, uint64_t *utt_checksums);
+
+/* ---- utterance-sharded runs over several GPUs (one process per GPU) ----------------------------------------------
+ * No counterpart in the reference (its batch processes share nothing and write their own files); these are the
+ * device-side pieces of "a final gather of LNA buffers" (BASELINE.json north_star).
+ *
+ * Checksum sink: per-utterance checksums of LNA records that are resident on this device -- produced here or received
+ * from another rank.  With w_j = little-endian 32-bit word j of a frame's record (zero padded to whole words):
+ *     row(f) = sum_j (2j+1) w_j          utt(u) = sum_i (2i+1) row(frame_offsets[u] + i)          (mod 2^64)
+ *   begin   frame_offsets [n_utts+1] (host) numbers the frames of the stream the records belong to; rec_bytes = S * lnabytes
+ *   update  records (DEVICE) = frames [first_frame, first_frame + n_frames) of that stream, in any order of calls,
+ *           asynchronous on the context's stream
+ *   end     waits and returns utt_checksums [n_utts] (host) */
+int akugpu_checksum_begin(akugpu_ctx *ctx, const int64_t *frame_offsets, int n_utts, int64_t rec_bytes);
+int akugpu_checksum_update(akugpu_ctx *ctx, const uint8_t *records, int64_t first_frame, int64_t n_frames);
+int akugpu_checksum_end(akugpu_ctx *ctx, uint64_t *utt_checksums);
+/* Device buffers that another process of the same node can map (CUDA IPC): the writer rank allocates its rotating
+ * receive buffer with akugpu_shared_alloc and hands the 64-byte handle to the other ranks (any transport: the bench uses
+ * a torch.distributed broadcast); they map it with akugpu_shared_open and pass the mapped address (+ their slot offset)
+ * as the DEVICE `out` of akugpu_phone_probs / akugpu_gmm_lna: the LNA kernel then stores its records straight into
+ * the writer's memory over NVLink -- epilogue and gather in one kernel, no send buffer.  akugpu_shared_release frees /
+ * unmaps (also done by akugpu_destroy). */
+int akugpu_shared_alloc(akugpu_ctx *ctx, size_t bytes, void **dev_ptr, unsigned char handle[64]);
+int akugpu_shared_open(akugpu_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int akugpu_shared_release(akugpu_ctx *ctx, void *dev_ptr);
+
 /* Writes the 5-byte LNA header (aku/phone_probs.cc:213-214): big-endian uint32
  * num_states, then lnabytes. */
 int akugpu_lna_header(int n_states, int lnabytes, uint8_t out5[5]);
