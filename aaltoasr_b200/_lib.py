@@ -72,11 +72,14 @@ SYMBOLS = {
     "akugpu_shared_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "akugpu_shared_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "akugpu_shared_release": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "akugpu_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "akugpu_lna_header": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "akugpu_set_chunk_frames": (C.c_int, [C.c_void_p, C.c_int64]),
     "akugpu_set_scorer_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "akugpu_model_expanded_form_q": (C.c_double, [C.c_void_p]),
     "akugpu_scorer_in_use": (C.c_int, [C.c_void_p]),
+    "akugpu_set_streaming": (C.c_int, [C.c_void_p, C.c_int]),
+    "akugpu_stream_probe": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "akugpu_pipe_rates": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 

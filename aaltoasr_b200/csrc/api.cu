@@ -281,6 +281,7 @@ void akugpu_destroy(akugpu_ctx *ctx)
     if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
   }
+  if (ctx->stream_state.host) cudaFreeHost(ctx->stream_state.host);
   for (void *p : ctx->shared_peer) cudaIpcCloseMemHandle(p);
   for (void *p : ctx->shared_own) cudaFree(p);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -665,6 +666,12 @@ static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, in
   const int S = ctx->hm.S, D = ctx->hm.D;
   if (n_frames == 0 || S == 0) return;
   const bool logmode = tiny > 0;
+  // streaming regime (the decoder's per-frame feed): one launch, features in the parameter block, results and the
+  // completion flag straight into mapped host memory.  false = a feature left the fp16 range: the general path below
+  // redoes the call (and finds the same overflow itself)
+  if (stream_applicable(ctx, precision, n_frames) &&
+      stream_score(ctx, feats, feats_f64, n_frames, (float *)out, logmode ? 1 : 0, logmode ? (float)log(tiny) : 0.f))
+    return;
   const void *d_feats = to_device(ctx, feats, (size_t)n_frames * D * (feats_f64 ? 8 : 4), ctx->d_feats);
   d_feats = adapt_feats(ctx, d_feats, feats_f64, n_frames);
   const size_t esz = (precision == AKUGPU_F64 && !logmode) ? 8 : 4;        // element size of the result
@@ -805,6 +812,22 @@ int akugpu_scorer_in_use(akugpu_ctx *ctx)
   if (ctx->ptc16.ready) return ctx->ptc16.hybrid ? 5 : (ctx->ptc16.stream ? 4 : 3);
   if (ctx->ptc.ready) return 2;
   return ctx->hm.n_full > 0 ? 0 : 1;
+}
+
+int akugpu_set_streaming(akugpu_ctx *ctx, int enable)
+{
+  API_BEGIN
+  ctx->streaming_enabled = enable != 0;
+  API_END
+}
+
+int akugpu_stream_probe(akugpu_ctx *ctx, double out[8])
+{
+  API_BEGIN
+  require_model(ctx);
+  if (!out) throw Error(AKUGPU_E_ARG, "out is NULL");
+  stream_probe(ctx, out);
+  API_END
 }
 
 int akugpu_pipe_rates(akugpu_ctx *ctx, double out[8])

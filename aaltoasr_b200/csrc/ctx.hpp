@@ -39,10 +39,13 @@ struct DevBuf {
   size_t cap = 0;
   void reserve(size_t bytes) {
     if (bytes <= cap) return;
+    // a buffer that has to grow again gets 1/8 of headroom: batches of slightly different sizes (utterances of
+    // jittered length) must not pay a cudaFree + cudaMalloc -- hundreds of ms for GB-sized buffers -- every few calls
+    const size_t want = p ? bytes + bytes / 8 : bytes;
     if (p) AKU_CUDA(cudaFree(p));
     p = nullptr; cap = 0;
-    AKU_CUDA(cudaMalloc(&p, bytes));
-    cap = bytes;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; AKU_CUDA(cudaMalloc(&p, bytes)); cap = bytes; return; }
+    cap = want;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T *as() const { return (T *)p; }
@@ -154,6 +157,18 @@ struct PackedTC16 {
   DevBuf B, meta, center, escale, flag;
   std::vector<char> clean;
   std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;
+  std::vector<double> h_center;                      // host copy of the feature centre (the streaming scorer centres on the host)
+  alignas(64) unsigned char map_b[128];              // CUtensorMap of B', encoded once per model (streaming scorer)
+  bool map_ready = false;
+};
+
+// streaming-regime scorer (gmm_stream.cu): pinned, mapped host block {flags | centred features | results}, CTA counter
+constexpr int STREAM_MAX_FRAMES = 32;
+struct StreamState {
+  void *host = nullptr, *dev_view = nullptr;
+  size_t bytes = 0;
+  DevBuf cnt;
+  unsigned int seq = 0;
 };
 
 // ---------------------------------------------------------------------------------
@@ -232,6 +247,8 @@ struct akugpu_ctx {
   int64_t chunk_frames = 0;   // 0 = auto: one full wave of the scorer per chunk
   int scorer_variant = 0;
   bool tc16_suspended = false;   // set while a call is redone with the bf16x3 kernel after an fp16 range overflow
+  bool streaming_enabled = true; // small calls (<= STREAM_MAX_FRAMES frames) of the decoder feed take gmm_stream_kernel
+  akugpu::StreamState stream_state;
 
   akugpu::HostModel hm;
   bool have_model = false;

@@ -66,6 +66,63 @@ constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 constexpr float BIAS_OFF = -65504.f;               // bias of absent components: exp() underflows to exactly 0
 }  // namespace tc16
 
+// One step of the fused first pass of the LNA normalisation (aku/phone_probs.cc:227-232): running maximum nMx of the
+// float-cast state log-likelihoods of a frame and nR = sum of all the other terms relative to it.  Explicit roundings:
+// gmm_tc16_kernel's epilogue and tc16_norm_replay must produce the same bits.
+__device__ __forceinline__ void norm_update(float res, float &nMx, float &nR)
+{
+  const float Lc = log_of_float_cast(res);
+  if (Lc > nMx) {
+    nR = (nMx == -INFINITY) ? 0.f : __fmul_rn(__fadd_rn(nR, 1.f), tc::ex2f(__fmul_rn(__fsub_rn(nMx, Lc), tc::LOG2E)));
+    nMx = Lc;
+  } else {
+    nR = __fadd_rn(nR, tc::ex2f(__fmul_rn(__fsub_rn(Lc, nMx), tc::LOG2E)));      // exp2(-inf) = 0 covers flushed states
+  }
+}
+// Merge of the four partial (maximum, sum) pairs of a frame, in the epilogue's order.
+__device__ __forceinline__ float2 norm_merge(const float (&M)[4], const double (&R)[4])
+{
+  float gM = M[0];
+  double Rt = R[0];
+  for (int o = 1; o < 4; o++) {
+    const float oM = M[o];
+    const double oR = R[o];
+    if (oM > gM) { Rt = oR + ((gM == -INFINITY) ? 0.0 : (1.0 + Rt) * exp((double)(gM - oM))); gM = oM; }
+    else if (oM != -INFINITY) Rt += (1.0 + oR) * exp((double)(oM - gM));
+  }
+  return make_float2(gM, (float)log1p(Rt));
+}
+
+// The normaliser of a frame must not depend on how the call was cut into launches: when the component tiles of a
+// (short) launch are spread over grid.y the epilogue cannot produce it, and this kernel REPLAYS the epilogue's
+// accumulation from the stored scores -- the same four partial streams (tiles of one parity x slots of one half tile, in
+// tile and slot order), the same operations, the same merge -- so a frame's LNA bytes are identical whichever launch
+// shape scored it (per-utterance checksums of differently batched runs are compared, multigpu.cu).
+__global__ void __launch_bounds__(128)
+tc16_norm_replay(const float *__restrict__ sll, int64_t ldF, int64_t nf, const int *__restrict__ meta, int n_tiles,
+                 float2 *__restrict__ norm)
+{
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  float M[4];
+  double R[4];
+  // partial o as the epilogue merges them: o = 0 (group 0, half 0), 1 (group 0, half 1), 2 (group 1, half 0), 3 (group 1, half 1)
+  for (int o = 0; o < 4; o++) {
+    const int group = o >> 1, half = o & 1;
+    float nMx = -INFINITY, nR = 0.f;
+    for (int n = group; n < n_tiles; n += 2) {
+      const int4 mt = __ldg(reinterpret_cast<const int4 *>(meta) + (size_t)n * 2 + half);
+      const int m4[4] = {mt.x, mt.y, mt.z, mt.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (m4[k] >= 0 && (m4[k] & 1)) norm_update(__ldg(sll + (int64_t)(m4[k] >> 2) * ldF + f), nMx, nR);
+    }
+    M[o] = nMx;
+    R[o] = (double)nR;
+  }
+  norm[f] = norm_merge(M, R);
+}
+
 // NCH > 0: A' resident (built in the kernel), B' streamed one component tile per ring slot.
 // NCH == 0: streaming variant for wide expansions (full covariance: K = D(D+3)/2 + 2 = 821): A' = [Ah | Al] comes
 //           from an expansion kernel through TMA like B' = [Bh | Bl]; a ring stage = the same 64-wide k-block of the
@@ -292,15 +349,7 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (last && mt >= 0) {
         const float res = fmaf(lg2f(sum), LN2, mx);
         sll_f[(int64_t)(mt >> 2) * ldF] = res;
-        if (norm) {
-          const float Lc = log_of_float_cast(res);
-          if (Lc > nMx) {
-            nR = (nMx == -INFINITY) ? 0.f : (nR + 1.f) * ex2f((nMx - Lc) * LOG2E);
-            nMx = Lc;
-          } else {
-            nR += ex2f((Lc - nMx) * LOG2E);      // exp2(-inf) = 0 covers flushed states
-          }
-        }
+        if (norm) norm_update(res, nMx, nR);
       }
     };
     static_assert(SLOTS_PER_WARP == 4 && EPI_GROUPS == 2, "the epilogue below handles four slots per warp and tile, two warp groups");
@@ -339,15 +388,12 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       sR[warp - 4][lane] = (double)nR;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       if (warp - 4 < 4) {
-        float gM = nMx;
-        double Rt = (double)nR;
-        for (int o = 1; o < EPI_WARPS / 4; o++) {
-          const float oM = sM[q + 4 * o][lane];
-          const double oR = sR[q + 4 * o][lane];
-          if (oM > gM) { Rt = oR + ((gM == -INFINITY) ? 0.0 : (1.0 + Rt) * exp((double)(gM - oM))); gM = oM; }
-          else if (oM != -INFINITY) Rt += (1.0 + oR) * exp((double)(oM - gM));
-        }
-        norm[frame] = make_float2(gM, (float)log1p(Rt));
+        static_assert(EPI_WARPS == 16, "four partial streams per frame: (group, half)");
+        float M[4];
+        double R[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++) { M[o] = sM[q + 4 * o][lane]; R[o] = sR[q + 4 * o][lane]; }
+        norm[frame] = norm_merge(M, R);
       }
     }
   }
@@ -541,6 +587,8 @@ void model_pack_tc16(akugpu_ctx *ctx)
   up(p.B, B.data(), B.size() * 2);
   up(p.meta, meta.data(), meta.size() * 4);
   up(p.center, cen.data(), cen.size() * 8);
+  p.h_center = cen;
+  p.map_ready = false;
   up(p.escale, escale.data(), escale.size() * 4);
   p.flag.reserve(16);
   AKU_CUDA(cudaMemsetAsync(p.flag.p, 0, 16, ctx->stream));
@@ -592,7 +640,8 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   if (ftiles < ctx->sm_count) want = std::min(p.n_tiles, std::max(1, ctx->sm_count / ftiles));
   int ysplit = 1;
   const int *ranges = tc_tile_ranges(ctx, p.n_tiles, p.clean, p.ranges, want, ysplit);
-  if (ysplit != 1) norm = nullptr;        // a frame's states are spread over several CTAs: the LNA kernel does both passes
+  float2 *replay_norm = nullptr;          // a frame's states are spread over several CTAs: the normaliser is replayed afterwards
+  if (ysplit != 1) { replay_norm = norm; norm = nullptr; }
   const int tslots = p.stream ? TC16_STREAM_STAGES : tc16_tslots(p.KB, p.D);
   const size_t smem = p.stream ? 1024 + (size_t)tslots * 4 * tc16::BLOCK_BYTES
                                : 1024 + (size_t)(1 + tslots) * p.KB * tc16::BLOCK_BYTES + tc16_stage_x_bytes(p.D);
@@ -617,6 +666,12 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   }
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
+  if (replay_norm) {
+    tc16_norm_replay<<<(unsigned)((nf + 127) / 128), 128, 0, ctx->stream>>>(sll, ldF, nf, p.meta.as<int>(), p.n_tiles, replay_norm);
+    AKU_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return true;
+  }
   return norm != nullptr;
 }
 

@@ -43,6 +43,11 @@ bool gmm_tc16_overflowed(akugpu_ctx *ctx);
 bool host_cholesky(const std::vector<double> &A, int n, std::vector<double> &Lw);
 void host_lu_inverse(const std::vector<double> &M, int n, std::vector<double> &inv);
 
+// gmm_stream.cu (streaming-regime scorer: <= STREAM_MAX_FRAMES frames against the whole model in one launch)
+bool stream_applicable(akugpu_ctx *ctx, int precision, int64_t n_frames);
+bool stream_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, float *out, int use_floor, float floor_at);
+void stream_probe(akugpu_ctx *ctx, double out[8]);
+
 // lna_kernels.cu
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
                     const float2 *norm, uint8_t *out);

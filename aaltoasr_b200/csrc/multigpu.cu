@@ -160,6 +160,16 @@ int akugpu_shared_open(akugpu_ctx *ctx, const unsigned char handle[64], void **d
   API_END
 }
 
+// Asynchronous device-to-device copy on the context's stream (local slot -> the writer's mapped buffer: a copy engine
+// moves the records over NVLink while the SMs score the next sub-batch).
+int akugpu_copy_async(akugpu_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+  API_BEGIN
+  if (bytes && (!dst || !src)) throw Error(AKUGPU_E_ARG, "copy_async: NULL pointer");
+  if (bytes) AKU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+  API_END
+}
+
 int akugpu_shared_release(akugpu_ctx *ctx, void *dev_ptr)
 {
   API_BEGIN

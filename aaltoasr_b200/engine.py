@@ -116,6 +116,20 @@ class AkuGpu:
         5 fp16x2 tensor-core + FP32-pipe for the ill-conditioned states."""
         return int(self._lib.akugpu_scorer_in_use(self._h))
 
+    def set_streaming(self, enable=True):
+        self._ck(self._lib.akugpu_set_streaming(self._h, 1 if enable else 0))
+
+    def stream_probe(self):
+        """Streaming-regime rates for the loaded model (akugpu_stream_probe)."""
+        out = (C.c_double * 8)()
+        self._ck(self._lib.akugpu_stream_probe(self._h, out))
+        b = out[0]
+        return {"image_bytes": b, "kernel_s_l2": out[1], "kernel_s_hbm": out[2], "probe_s_l2": out[3], "probe_s_hbm": out[4],
+                "kernel_GBps_l2": b / out[1] / 1e9, "kernel_GBps_hbm": b / out[2] / 1e9,
+                "probe_GBps_l2": b / out[3] / 1e9, "probe_GBps_hbm": b / out[4] / 1e9,
+                "sm_mhz_isolated": out[5], "kernel_s_train": out[6], "kernel_GBps_train": b / out[6] / 1e9 if out[6] > 0 else None,
+                "sm_mhz_train": out[7]}
+
     def pipe_rates(self):
         out = (C.c_double * 8)()
         self._ck(self._lib.akugpu_pipe_rates(self._h, out))
@@ -345,6 +359,10 @@ class AkuGpu:
         h = np.frombuffer(bytes(handle), dtype=np.uint8).copy()
         self._ck(self._lib.akugpu_shared_open(self._h, _ptr(h), C.byref(p)))
         return DevPtr(p.value)
+
+    def copy_async(self, dst, src, nbytes):
+        """cudaMemcpyAsync between device buffers (tensors or DevPtr, local or mapped peer memory) on this context's stream."""
+        self._ck(self._lib.akugpu_copy_async(self._h, _ptr(dst), _ptr(src), int(nbytes)))
 
     def shared_release(self, ptr):
         self._ck(self._lib.akugpu_shared_release(self._h, C.c_void_p(int(ptr))))

@@ -214,13 +214,16 @@ def gather_nccl(plan, rank, produce, sink, send_slots, recv_slots, group=None, s
                 sink(r, recv_slots[r][k & 1], f0, n)
 
 
-def gather_p2p(plan, rank, produce, sink, own_slots, peer_slot, nslots, g_tok, g_free, token, sink_scope=_NoScope):
+def gather_p2p(plan, rank, produce, sink, own_slots, peer_slot, nslots, g_tok, g_free, token, sink_scope=_NoScope,
+               tok_scope=_NoScope):
     """The LNA kernel stores into the writer's memory: produce(u0, u1, out) is handed the mapped peer slot.
     peer_slot(r, j)  -> what `produce` / `sink` take for slot j of sender r (a DevPtr into the shared buffer)
     own_slots        the writer's buffers for its own records
     g_tok / g_free   two process groups carrying the 8-byte "slot filled" (sender -> writer) and "slot free"
                      (writer -> sender) tokens: separate communicators, so neither direction can block the other
-    token            a small tensor on the right device."""
+    token            a small tensor on the right device
+    tok_scope        context manager factory entered around a sender's "slot filled" token (copy-engine variant: the
+                     stream the asynchronous copy was issued on, so that the token follows the copy, not the scoring)."""
     import torch.distributed as dist
     mine = plan.sched[rank]
     # Tokens are sent asynchronously and collected at the end: with blocking sends the two directions wait for each
@@ -231,8 +234,9 @@ def gather_p2p(plan, rank, produce, sink, own_slots, peer_slot, nslots, g_tok, g
         for k, (u0, u1, f0, n) in enumerate(mine):
             if k >= nslots:
                 dist.recv(tok_in, plan.writer, group=g_free)      # the writer has consumed sub-batch k - nslots
-            produce(u0, u1, peer_slot(rank, k % nslots))       # returns when the records are in the writer's memory
-            works.append(dist.isend(token, plan.writer, group=g_tok))
+            produce(u0, u1, peer_slot(rank, k % nslots))       # returns when the records are in / on their way to the writer's memory
+            with tok_scope():
+                works.append(dist.isend(token, plan.writer, group=g_tok))
     else:
         for k in range(plan.rounds()):
             if k < len(mine):

@@ -624,11 +624,16 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
 
     src_chk = np.zeros(len(mine), dtype=np.uint64)
 
+    trace = os.environ.get("AKUGPU_BENCH_TRACE")
+
     def produce_into(want_chk):
         def produce(u0, u1, out):
             a, b = int(uo[u0]), int(uo[u1])
+            t0 = time.perf_counter()
             _, _, uc = eng.phone_probs(pcm_d[a:b], uo[u0:u1 + 1] - uo[u0], precision=F32, lnabytes=LNABYTES, out=out,
                                        utt_checksums=want_chk)
+            if trace:
+                log("rank %d produce utts [%d, %d) %d frames: %.2f ms" % (rank, u0, u1, int(fo[u1] - fo[u0]), 1e3 * (time.perf_counter() - t0)))
             if want_chk:
                 src_chk[u0:u1] = uc
         return produce
@@ -639,7 +644,11 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
     res = {}
     # ---- (1) device-resident: records into two rotating device slots
     dev_slots = [torch.empty(slot_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
-    mg.run_writers(produce_into(False), my_frames[:min(len(mine), 60)], max_frames, dev_slots)          # warm-up
+    # warm-up: the largest sub-batch first (every scratch buffer of the library reaches its final size), then two more
+    sched = plan.sched[rank]
+    big = max(range(len(sched)), key=lambda k: sched[k][3])
+    for k in [big] + list(range(min(2, len(sched)))):
+        produce_into(False)(sched[k][0], sched[k][1], dev_slots[k & 1])
     eng.stage_times_reset(True)
     l0 = eng.launch_count()
     ms_res = timed(lambda: mg.run_writers(produce_into(False), my_frames, max_frames, dev_slots))
@@ -653,7 +662,9 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
     def produce_host(u0, u1, out):
         a, b = int(uo[u0]), int(uo[u1])
         eng.phone_probs(pcm_p[a:b], uo[u0:u1 + 1] - uo[u0], precision=F32, lnabytes=LNABYTES, out=out)
-    mg.run_writers(produce_host, my_frames[:min(len(mine), 60)], e2e_chunks * max_frames, host_slots)       # warm-up
+    sched_e = mg.sub_batches(my_frames, e2e_chunks * max_frames)
+    big = max(range(len(sched_e)), key=lambda k: sched_e[k][3])
+    produce_host(sched_e[big][0], sched_e[big][1], host_slots[0])                                        # warm-up
     ms_e2e = timed(lambda: mg.run_writers(produce_host, my_frames, e2e_chunks * max_frames, host_slots))
     del host_slots
     res.update({"value": F_total / (ms_res * 1e-3), "ms_per_step": ms_res,
@@ -686,10 +697,16 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
         def sink_scope():
             return torch.cuda.stream(sink_stream)
         sunk = {}
-        for mode in ("p2p", "nccl"):
-            shared = peer_base = None
-            if mode == "p2p":
-                nslots = 2
+        copy_eng, copy_stream, copy_ev = None, None, [None, None]
+        if rank != 0:
+            copy_eng = AkuGpu(local)
+            copy_stream = torch.cuda.Stream()
+            copy_eng.set_stream(copy_stream.cuda_stream)
+        idx = {r: i for i, r in enumerate(plan.senders)}
+        nslots = 2
+        for mode in ("p2p_store", "p2p_copy", "nccl"):
+            shared = peer_base = recv_slots = None
+            if mode != "nccl":
                 handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
                 if rank == 0:
                     shared, h = eng.shared_alloc(len(plan.senders) * nslots * slot_bytes)
@@ -698,25 +715,45 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
                 if rank != 0:
                     peer_base = eng.shared_open(handle.cpu().numpy().tobytes())
                 root = shared if rank == 0 else peer_base
-                idx = {r: i for i, r in enumerate(plan.senders)}
 
-                def peer_slot(r, j):
+                def peer_slot(r, j, root=root):
                     return DevPtr(int(root) + (idx[r] * nslots + j) * slot_bytes)
                 token = torch.zeros(1, dtype=torch.int64, device="cuda")
+                if mode == "p2p_store":
+                    prod, tok_scope = produce_into(False), nullcontext
+                else:
+                    kcount = [0]
 
-                def run():
+                    def prod(u0, u1, peer_out):
+                        # records into a local slot (scored on the compute stream), then a copy engine carries them over
+                        # NVLink on its own stream while the next sub-batch is scored; the token follows the copy
+                        k = kcount[0]
+                        kcount[0] += 1
+                        if copy_ev[k & 1] is not None:
+                            stream.wait_event(copy_ev[k & 1])          # the slot's previous copy has left
+                        produce_into(False)(u0, u1, dev_slots[k & 1])
+                        copy_eng.copy_async(peer_out, dev_slots[k & 1], int(fo[u1] - fo[u0]) * rec)
+                        copy_ev[k & 1] = torch.cuda.Event()
+                        copy_ev[k & 1].record(copy_stream)
+
+                    def tok_scope():
+                        return torch.cuda.stream(copy_stream)
+
+                def run(prod=prod, tok_scope=tok_scope, peer_slot=peer_slot, token=token):
                     with torch.cuda.stream(stream):
-                        mg.gather_p2p(plan, rank, produce_into(True), sink, dev_slots, peer_slot, nslots, g_tok, g_free, token,
-                                      sink_scope if rank == 0 else nullcontext)
+                        mg.gather_p2p(plan, rank, produce_into(False) if rank == 0 else prod, sink, dev_slots, peer_slot, nslots, g_tok, g_free,
+                                      token, sink_scope if rank == 0 else nullcontext, nullcontext if rank == 0 else tok_scope)
                         if rank == 0:
                             stream.wait_stream(sink_stream)          # the timed region ends after the sink's last checksum
+                        elif copy_stream is not None:
+                            stream.wait_stream(copy_stream)
             else:
                 recv_slots = {r: [torch.empty(slot_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)] for r in plan.senders} \
                     if rank == 0 else None
 
-                def run():
+                def run(recv_slots=recv_slots):
                     with torch.cuda.stream(stream):
-                        mg.gather_nccl(plan, rank, produce_into(True), sink, dev_slots, recv_slots, None,
+                        mg.gather_nccl(plan, rank, produce_into(False), sink, dev_slots, recv_slots, None,
                                        sink_scope if rank == 0 else nullcontext)
                         if rank == 0:
                             stream.wait_stream(sink_stream)
@@ -726,19 +763,26 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
             if rank == 0:
                 sunk[mode] = sink_eng.checksum_end()
             gather[mode] = {"value": F_total / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
-                            "bytes_into_writer": recv_bytes, "nvlink_GBps_into_writer": recv_bytes / (ms * 1e-3) / 1e9}
-            if mode == "p2p":
+                            "bytes_into_writer": recv_bytes, "payload_GBps_into_writer": recv_bytes / (ms * 1e-3) / 1e9}
+            if mode != "nccl":
                 torch.cuda.synchronize(); dist.barrier()
                 if rank != 0:
                     eng.shared_release(peer_base)
                 dist.barrier()
                 if rank == 0:
                     eng.shared_release(shared)
-            else:
-                recv_slots = None
-        gather["p2p"]["how"] = ("lna_f32_rows of every rank stores its records straight into the writer's rotating buffer (CUDA-IPC mapped peer "
-                                "memory over NVLink): epilogue + gather in one kernel; NCCL carries two 8-byte tokens per sub-batch")
+            recv_slots = None
+        if copy_eng:
+            copy_eng.close()
+        gather["p2p_store"]["how"] = ("lna_f32_rows of every rank stores its records straight into the writer's rotating buffer (CUDA-IPC mapped "
+                                      "peer memory over NVLink): epilogue + gather in one kernel; NCCL carries two 8-byte tokens per sub-batch")
+        gather["p2p_copy"]["how"] = ("records into a local slot, then one asynchronous copy-engine transfer into the writer's mapped rotating buffer "
+                                     "while the SMs score the next sub-batch; same tokens")
         gather["nccl"]["how"] = "records into a local send slot, ncclSend -> ncclRecv into the writer's rotating slots"
+        gather["note"] = ("payload_GBps_into_writer = bytes / step time: it is bounded by the rate at which the senders PRODUCE records "
+                          "(10000 states x 2 bytes per frame), not by NVLink, unless the writer's ingest saturates")
+        # ---- source checksums: one more (untimed) local pass with the per-utterance checksums switched on
+        mg.run_writers(produce_into(True), my_frames, max_frames, dev_slots)
         # ---- the table: (utterance, n_frames, source checksum) all-gathered; the writer compares what arrived
         torch.cuda.synchronize(); t0 = time.perf_counter()
         tf, tc, owner = gather_utterance_table(mine, my_frames, src_chk, n_total)

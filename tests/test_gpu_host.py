@@ -118,7 +118,7 @@ def test_cpp_tool_flags(engine, ref_small, tmp_path):
     r = run("-c", cfg, "-r", rec)
     assert r.returncode != 0 and b"Must give either --base or all --gk, --mc and --ph" in r.stderr
     r = run("-b", base, "-c", cfg, "-r", rec, "--lnabytes=3")
-    assert r.returncode != 0 and b"Invalid number of bytes" in r.stderr
+    assert r.returncode != 0 and b"Invalid number of LNA bytes" in r.stderr
     r = run("-g", base + ".gk", "-m", base + ".mc", "-p", base + ".ph", "-c", cfg, "-r", rec, "-o", str(out), "-a")
     assert r.returncode == 0
     # output names as io::Stream takes them (aku/io.cc:35-130): *.gz through gzip, |command through a pipe

@@ -1,0 +1,152 @@
+"""GPU tests of the streaming-regime scorer (gmm_stream_kernel): the decoder's per-frame feed
+(decoder/decode-stream.cc:191-207 -> OneFrameAcoustics::set) -- a few frames against the whole model in one launch."""
+import time
+
+import numpy as np
+import pytest
+
+from aaltoasr_b200 import F32, F64, synth
+from oracle import oracle_np
+
+pytestmark = pytest.mark.gpu
+
+
+def load_model(engine, m):
+    engine.model_load_diag(m["mix_offsets"], m["mix_gauss"], m["mix_weight"], m["means"], m["covs"])
+
+
+def both_paths(engine, fn):
+    engine.set_streaming(True)
+    l0 = engine.launch_count()
+    a = fn()
+    n_stream = engine.launch_count() - l0
+    engine.set_streaming(False)
+    try:
+        l0 = engine.launch_count()
+        b = fn()
+        n_batch = engine.launch_count() - l0
+    finally:
+        engine.set_streaming(True)
+    return a, b, n_stream, n_batch
+
+
+@pytest.mark.parametrize("F", [1, 2, 7, 16, 17, 32])
+def test_streaming_scorer_equals_batch_path_small_model(engine, ref_small, F):
+    g = ref_small
+    load_model(engine, g["model"])
+    assert engine.scorer_in_use() == 3
+    x = g["feats"][3:3 + F].astype(np.float32)
+    a, b, ns, nb = both_paths(engine, lambda: engine.gmm_score(x, precision=F32))
+    assert ns == 1 and nb >= 2                                   # ONE launch against scorer + transpose
+    assert np.abs(a.astype(np.float64) - b).max() <= 2e-6        # same products, another summation order in the epilogue
+    assert np.abs(a - np.log(g["lik"][3:3 + F])).max() <= 3e-5   # the reference's likelihoods
+    # the decoder feed: (float) log(max(l, 1e-30)), floats and doubles in
+    a, b, ns, nb = both_paths(engine, lambda: engine.gmm_logprobs(g["feats"][3:3 + F], precision=F32, tiny=1e-30))
+    assert ns == 1 and np.abs(a.astype(np.float64) - b).max() <= 2e-6
+    want = np.log(np.maximum(g["lik"][3:3 + F], 1e-30))
+    assert np.abs(a - want).max() <= 3e-5
+
+
+def test_streaming_scorer_floor_and_edge_model(engine, ref_edge):
+    """The edge-case model is hybrid (ill-conditioned states): the streaming scorer declines, results are the general
+    path's.  A plain model with frames far from every Gaussian: the floor of the decoder feed applies."""
+    g = ref_edge
+    load_model(engine, g["model"])
+    assert engine.scorer_in_use() == 5
+    x = g["feats"][:4].astype(np.float32)
+    a, b, ns, nb = both_paths(engine, lambda: engine.gmm_logprobs(x, precision=F32, tiny=1e-30))
+    assert ns == nb and np.array_equal(a, b)
+
+
+def test_streaming_scorer_floor(engine, ref_small):
+    g = ref_small
+    load_model(engine, g["model"])
+    x = g["feats"][:5].astype(np.float32).copy()
+    x[2] += 40.0                                                  # far from everything: likelihood below 1e-30
+    a, b, ns, nb = both_paths(engine, lambda: engine.gmm_logprobs(x, precision=F32, tiny=1e-30))
+    assert ns == 1
+    floor = np.float32(np.log(1e-30))
+    assert (a[2] == floor).all() and (b[2] == floor).all()
+    assert np.abs(a.astype(np.float64) - b).max() <= 2e-6
+    raw, rawb, _, _ = both_paths(engine, lambda: engine.gmm_score(x, precision=F32))       # no floor in the plain score
+    assert (raw[2] < floor).all() and (np.abs(raw[2].astype(np.float64) - rawb[2]) <= 2e-6 * np.abs(rawb[2]) + 2e-6).all()
+
+
+def test_streaming_scorer_device_buffers_and_overflow(engine, ref_small):
+    import torch
+    g = ref_small
+    load_model(engine, g["model"])
+    x = g["feats"][10:13].astype(np.float32)
+    host = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)
+    xd = torch.from_numpy(x).cuda()
+    od = torch.empty((3, engine.num_states), dtype=torch.float32, device="cuda")
+    l0 = engine.launch_count()
+    engine.gmm_logprobs(xd, precision=F32, tiny=1e-30, out=od)
+    assert engine.launch_count() - l0 == 1
+    assert np.array_equal(od.cpu().numpy(), host)                 # device features are centred in the kernel: same arithmetic
+    x64d = torch.from_numpy(g["feats"][10:13]).cuda()
+    engine.gmm_logprobs(x64d, precision=F32, tiny=1e-30, out=od)       # the unrounded doubles: differs by the feature rounding only
+    assert np.abs(od.cpu().numpy() - host).max() <= 1e-5
+    # a feature outside the fp16 range of the scaled terms: the call falls through to the general path (bf16x3 redo)
+    bad = x.copy()
+    bad[1, 3] = 3.0e4
+    l0 = engine.launch_count()
+    got = engine.gmm_score(bad, precision=F32)
+    assert engine.launch_count() - l0 >= 4
+    assert np.isfinite(got).all() and got[1].max() < -1e5
+    assert np.abs(got[[0, 2]] - engine.gmm_score(x, precision=F32)[[0, 2]]).max() <= 3e-5
+    again = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)     # and the fast path is back, flag cleared
+    assert np.array_equal(again, host)
+
+
+@pytest.fixture(scope="module")
+def feats20s(engine):
+    engine.frontend_load_config_text(synth.mfcc39_config())
+    pcm = np.concatenate([synth.synth_audio(2000 + i, 160000) for i in range(2)])
+    feats, _ = engine.features(pcm, np.array([0, 160000, 320000]), dtype=np.float64)
+    return feats
+
+
+@pytest.mark.parametrize("S,K,seed", [(5000, 16, 2999), (10000, 32, 4999)])
+def test_streaming_scorer_full_size_models(engine, feats20s, S, K, seed):
+    """Config-2 and config-4 models: every frame of a per-frame loop equals the batch path; latency per call reported."""
+    model = synth.synth_diag_model(seed, feats20s, S, K)
+    load_model(engine, model)
+    assert engine.scorer_in_use() == 3
+    idx = np.arange(0, 2496, 96)
+    x = feats20s[idx].astype(np.float32)
+    engine.set_streaming(False)
+    try:
+        batch = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)
+    finally:
+        engine.set_streaming(True)
+    rows = np.stack([engine.gmm_logprobs(x[i:i + 1], precision=F32, tiny=1e-30)[0] for i in range(len(idx))])
+    assert np.abs(rows.astype(np.float64) - batch).max() <= 4e-6
+    blk = engine.gmm_logprobs(x[:16], precision=F32, tiny=1e-30)
+    assert np.abs(blk.astype(np.float64) - batch[:16]).max() <= 4e-6
+    blk = engine.gmm_logprobs(x[:26], precision=F32, tiny=1e-30)             # N = 32 variant, ragged
+    assert np.abs(blk.astype(np.float64) - batch).max() <= 4e-6
+    want = np.log(np.maximum(oracle_np.state_likelihoods(model, x[:2].astype(np.float64)), 1e-30))
+    assert np.abs(rows[:2] - want).max() <= 4e-5
+    p = engine.stream_probe()
+    print("stream probe %d x %d: image %.1f MB; kernel %.2f us (L2-resident, %.0f GB/s) / %.2f us (after L2 flush, %.0f GB/s); "
+          "plain read sweep %.0f GB/s (L2) / %.0f GB/s (HBM)" % (S, K, p["image_bytes"] / 1e6, 1e6 * p["kernel_s_l2"], p["kernel_GBps_l2"],
+                                                                 1e6 * p["kernel_s_hbm"], p["kernel_GBps_hbm"], p["probe_GBps_l2"], p["probe_GBps_hbm"]))
+    print("stream probe %d x %d: SM clock after isolated launches %.0f MHz; train of 200 launches: %.2f us per launch (%.0f GB/s), SM clock %.0f MHz"
+          % (S, K, p["sm_mhz_isolated"], 1e6 * p["kernel_s_train"], p["kernel_GBps_train"], p["sm_mhz_train"]))
+    import ctypes as C
+    lib, h = engine._lib, engine._h
+    for F in (1, 8, 16, 32):
+        xb = np.ascontiguousarray(x[:F] if F <= len(x) else np.vstack([x, x])[:F])
+        ob = np.empty((F, S), dtype=np.float32)
+        px, po = C.c_void_p(xb.ctypes.data), C.c_void_p(ob.ctypes.data)
+        call = lambda: lib.akugpu_gmm_logprobs(h, px, 0, F, 0, C.c_double(1e-30), po)
+        for _ in range(50):
+            assert call() == 0
+        t0 = time.perf_counter()
+        n = 1000
+        for _ in range(n):
+            call()
+        us = 1e6 * (time.perf_counter() - t0) / n
+        print("streaming scorer %d x %d, F = %d: %.1f us per akugpu_gmm_logprobs call (host buffers, ctypes loop)" % (S, K, F, us))
+        assert us < 1000.0
