@@ -656,7 +656,7 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
     st = eng.stage_times()
     eng.stage_times_reset(False)
     # ---- (2) per-rank writers end to end: pinned host PCM in, records to two rotating pinned host slots
-    e2e_chunks = 4
+    e2e_chunks = 4 if world <= 2 else 2            # pinned host memory per rank: two slots of e2e_chunks x 0.76 GB
     host_slots = [torch.empty(e2e_chunks * slot_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
 
     def produce_host(u0, u1, out):
@@ -697,7 +697,7 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
         def sink_scope():
             return torch.cuda.stream(sink_stream)
         sunk = {}
-        copy_eng, copy_stream, copy_ev = None, None, [None, None]
+        copy_eng, copy_stream, copy_ev, copy_log = None, None, [None, None], []
         if rank != 0:
             copy_eng = AkuGpu(local)
             copy_stream = torch.cuda.Stream()
@@ -732,9 +732,13 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
                         if copy_ev[k & 1] is not None:
                             stream.wait_event(copy_ev[k & 1])          # the slot's previous copy has left
                         produce_into(False)(u0, u1, dev_slots[k & 1])
-                        copy_eng.copy_async(peer_out, dev_slots[k & 1], int(fo[u1] - fo[u0]) * rec)
-                        copy_ev[k & 1] = torch.cuda.Event()
+                        nb = int(fo[u1] - fo[u0]) * rec
+                        t0e = torch.cuda.Event(enable_timing=True)
+                        t0e.record(copy_stream)
+                        copy_eng.copy_async(peer_out, dev_slots[k & 1], nb)
+                        copy_ev[k & 1] = torch.cuda.Event(enable_timing=True)
                         copy_ev[k & 1].record(copy_stream)
+                        copy_log.append((nb, t0e, copy_ev[k & 1]))
 
                     def tok_scope():
                         return torch.cuda.stream(copy_stream)
@@ -772,6 +776,14 @@ def bench_config4(args, torch, dist, rank, world, local, utts_per_gpu):
                 if rank == 0:
                     eng.shared_release(shared)
             recv_slots = None
+        # NVLink rate of the copy-engine transfers themselves (sender side, events around every copy), all ranks' medians
+        torch.cuda.synchronize()
+        rates = sorted(nb / (a.elapsed_time(b) * 1e-3) / 1e9 for nb, a, b in copy_log if nb > (64 << 20))
+        med = torch.tensor([rates[len(rates) // 2] if rates else 0.0], device="cuda")
+        allmed = [torch.zeros_like(med) for _ in range(world)]
+        dist.all_gather(allmed, med)
+        gather["p2p_copy"]["copy_GBps_per_sender_median"] = [float(x.item()) for x in allmed[1:]]
+        gather["p2p_copy"]["copy_GBps_sum_over_senders"] = float(sum(x.item() for x in allmed[1:]))
         if copy_eng:
             copy_eng.close()
         gather["p2p_store"]["how"] = ("lna_f32_rows of every rank stores its records straight into the writer's rotating buffer (CUDA-IPC mapped "
