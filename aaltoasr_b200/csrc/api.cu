@@ -50,12 +50,13 @@ StageScope::StageScope(akugpu_ctx *c, int s) : ctx(c), stage(s), l0(c->launches)
     return e;
   };
   e0 = get(); e1 = get();
-  AKU_CUDA(cudaEventRecord(e0, ctx->stream));
+  st = ctx->stream;
+  AKU_CUDA(cudaEventRecord(e0, st));
 }
 StageScope::~StageScope()
 {
   if (!ctx->timer.enabled || !e0) return;
-  cudaEventRecord(e1, ctx->stream);
+  cudaEventRecord(e1, st);
   ctx->timer.pending.push_back(std::make_pair(stage, std::make_pair(e0, e1)));
   ctx->timer.launches[stage] += ctx->launches - l0;
 }
@@ -136,38 +137,64 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
   if (out_dev && ((uintptr_t)out & 3))      // the LNA kernels store 32-bit words (16-bit when S * lnabytes is odd-sized)
     throw Error(AKUGPU_E_ARG, "a device `out` buffer must be 4-byte aligned");
   const size_t esz = precision == AKUGPU_F64 ? 8 : 4;
+  // Throughput mode with more than one chunk: the LNA epilogue of chunk k (HBM bound, 33 KB of shared memory per CTA)
+  // runs on a second stream next to the scorer of chunk k+1 (compute bound; its ring is one slot shorter so that
+  // both fit an SM): scores and normalisers are double buffered.
+  const bool overlap = precision == AKUGPU_F32 && ctx->overlap_lna && F > chunk;
   ctx->d_sll.reserve((size_t)S * chunk * esz);
+  if (overlap) ctx->d_sll2.reserve((size_t)S * chunk * esz);
   if (!out_dev) { ctx->d_lna[0].reserve(chunk * rec); if (out_host) ctx->d_lna[1].reserve(chunk * rec); }
   if (checksum_out) { ctx->d_chk.reserve(8); AKU_CUDA(cudaMemsetAsync(ctx->d_chk.p, 0, 8, ctx->stream)); }
+  cudaStream_t const main_stream = ctx->stream;
+  struct Restore { akugpu_ctx *c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, main_stream};
+  if (overlap) {   // what the LNA stream touches first must be ordered after what the main stream did before this call
+    AKU_CUDA(cudaEventRecord(ctx->ev_sc[0], main_stream));
+    AKU_CUDA(cudaStreamWaitEvent(ctx->lna_stream, ctx->ev_sc[0], 0));
+  }
   int c = 0;
   for (int64_t c0 = 0; c0 < F; c0 += chunk, ++c) {
     const int64_t c1 = std::min(F, c0 + chunk), nf = c1 - c0;
     const int b = out_host ? (c & 1) : 0;
+    const int b2 = overlap ? (c & 1) : 0;
+    DevBuf &sllb = b2 ? ctx->d_sll2 : ctx->d_sll;
+    DevBuf &normb = b2 ? ctx->d_norm2 : ctx->d_norm;
     uint8_t *dst = out_dev ? out + c0 * rec : ctx->d_lna[b].as<uint8_t>();
-    if (out_host && c >= 2) AKU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));
+    if (overlap && c >= 2) AKU_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_ln[b2], 0));      // the LNA kernel of chunk c-2 has read this buffer
+    const float2 *norm = nullptr;
     if (precision == AKUGPU_F32) {
-      const float2 *norm = nullptr;
       if (use_tc) {   // times its own stages; also yields the per-frame normaliser when it sweeps all states
-        ctx->d_norm.reserve((size_t)chunk * sizeof(float2));
+        normb.reserve((size_t)chunk * sizeof(float2));
         // ill-conditioned states: FP32-pipe kernel, same chunk -- also when the call is being redone with the bf16x3
         // kernel after an fp16 range overflow (that image holds every state in the expanded form; the FP32 image
         // holds exactly the states the expanded form is not trusted with and overwrites their rows)
         const bool hybrid = ctx->ptc16.ready && ctx->ptc16.hybrid;
-        float2 *const nrm = hybrid ? nullptr : ctx->d_norm.as<float2>();
-        const bool got = use_tc == 2 ? launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nrm)
-                                     : launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk, nrm);
-        if (got) norm = ctx->d_norm.as<float2>();
-        if (hybrid) { StageScope sc(ctx, 1); launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk); }
+        float2 *const nrm = hybrid ? nullptr : normb.as<float2>();
+        const bool got = use_tc == 2 ? launch_gmm_tc16(ctx, d_feats, feats_f64, c0, c1, sllb.as<float>(), chunk, nrm)
+                                     : launch_gmm_tc(ctx, d_feats, feats_f64, c0, c1, sllb.as<float>(), chunk, nrm);
+        if (got) norm = normb.as<float2>();
+        if (hybrid) { StageScope sc(ctx, 1); launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, sllb.as<float>(), chunk); }
       } else {
         StageScope sc(ctx, 1);
-        launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<float>(), chunk);
+        launch_gmm_f32(ctx, d_feats, feats_f64, c0, c1, sllb.as<float>(), chunk);
       }
-      { StageScope sc(ctx, 2); launch_lna_f32(ctx, ctx->d_sll.as<float>(), chunk, S, nf, lnabytes, normalize, norm, dst); }
     } else {
-      { StageScope sc(ctx, 1);
-        if (ctx->hm.n_full > 0) launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk);
-        else launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, ctx->d_sll.as<double>(), chunk); }
-      { StageScope sc(ctx, 2); launch_lna_f64(ctx, ctx->d_sll.as<double>(), chunk, S, nf, lnabytes, normalize, dst); }
+      StageScope sc(ctx, 1);
+      if (ctx->hm.n_full > 0) launch_gmm_full_f64(ctx, d_feats, feats_f64, c0, c1, sllb.as<double>(), chunk);
+      else launch_gmm_f64(ctx, d_feats, feats_f64, c0, c1, sllb.as<double>(), chunk);
+    }
+    if (overlap) {   // everything from here to the end of the iteration is issued on the LNA stream
+      AKU_CUDA(cudaEventRecord(ctx->ev_sc[b2], main_stream));
+      ctx->stream = ctx->lna_stream;
+      AKU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sc[b2], 0));
+    }
+    if (out_host && c >= 2) AKU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));       // the ring buffer has left the device
+    if (precision == AKUGPU_F32) {
+      if (normalize && !norm && overlap) normb.reserve((size_t)(chunk + 31) / 32 * 32 * sizeof(float2));
+      StageScope sc(ctx, 2);
+      launch_lna_f32(ctx, sllb.as<float>(), chunk, S, nf, lnabytes, normalize, norm, dst, overlap ? normb.as<float2>() : nullptr);
+    } else {
+      StageScope sc(ctx, 2);
+      launch_lna_f64(ctx, sllb.as<double>(), chunk, S, nf, lnabytes, normalize, dst);
     }
     if (checksum_out) launch_checksum(ctx, dst, nf * rec, ctx->d_chk.as<unsigned long long>());
     if (utt_chk) checksum_update(ctx, dst, c0, nf);      // per-utterance sums; the records are still in L2
@@ -177,6 +204,14 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
       AKU_CUDA(cudaMemcpyAsync(out + c0 * rec, dst, nf * rec, cudaMemcpyDeviceToHost, ctx->copy_out));
       AKU_CUDA(cudaEventRecord(ctx->ev_out[b], ctx->copy_out));
     }
+    if (overlap) {
+      AKU_CUDA(cudaEventRecord(ctx->ev_ln[b2], ctx->stream));
+      ctx->stream = main_stream;
+    }
+  }
+  if (overlap) {   // the caller's stream sees the whole call: it waits for the LNA stream's last event
+    AKU_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_ln[(c - 1) & 1], 0));
+    if (c >= 2) AKU_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_ln[c & 1], 0));
   }
   if (checksum_out) {
     unsigned long long h = 0;
@@ -257,7 +292,12 @@ akugpu_ctx *akugpu_create(int device)
     AKU_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     AKU_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     AKU_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    AKU_CUDA(cudaStreamCreateWithFlags(&ctx->lna_stream, cudaStreamNonBlocking));
+    if (getenv("AKUGPU_OVERLAP")) ctx->overlap_lna = atoi(getenv("AKUGPU_OVERLAP")) != 0;
+    if (getenv("AKUGPU_CHUNK_FRAMES")) ctx->chunk_frames = atoll(getenv("AKUGPU_CHUNK_FRAMES"));
     for (int i = 0; i < 2; i++) {
+      AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_sc[i], cudaEventDisableTiming));
+      AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_ln[i], cudaEventDisableTiming));
       AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
       AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
       AKU_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
@@ -280,7 +320,10 @@ void akugpu_destroy(akugpu_ctx *ctx)
     if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
     if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+    if (ctx->ev_sc[i]) cudaEventDestroy(ctx->ev_sc[i]);
+    if (ctx->ev_ln[i]) cudaEventDestroy(ctx->ev_ln[i]);
   }
+  if (ctx->lna_stream) cudaStreamDestroy(ctx->lna_stream);
   if (ctx->stream_state.host) cudaFreeHost(ctx->stream_state.host);
   for (void *p : ctx->shared_peer) cudaIpcCloseMemHandle(p);
   for (void *p : ctx->shared_own) cudaFree(p);

@@ -212,6 +212,8 @@ struct Module {
   std::vector<float> q_alpha, q_gamma, q_max;
   // device copies of parameters
   std::shared_ptr<DevBuf> d_a, d_b, d_c;
+  std::shared_ptr<DevBuf> d_d;   // double copy of a float table (mel triangle weights, dct basis): the warp-per-frame front-end kernel
+                                 // reads the widened values instead of converting them term by term
   // extended frame range this module must be evaluated on for an utterance:
   // [-ext_left, n_frames-1+ext_right]
   int ext_left = 0, ext_right = 0;
@@ -241,6 +243,10 @@ struct akugpu_ctx {
   cudaStream_t stream = nullptr;       // compute stream
   bool own_stream = true;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  // second compute stream: the LNA epilogue of chunk k runs here next to the scorer of chunk k+1 (api.cu, score_to_lna_impl)
+  cudaStream_t lna_stream = nullptr;
+  cudaEvent_t ev_sc[2] = {nullptr, nullptr}, ev_ln[2] = {nullptr, nullptr};
+  bool overlap_lna = false;      // measured (profiles/r02_overlap_experiment.txt): no gain, the step is power-capped; AKUGPU_OVERLAP=1 switches it on
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
@@ -263,6 +269,7 @@ struct akugpu_ctx {
 
   // scratch
   akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk, d_norm, d_clik, d_csel;
+  akugpu::DevBuf d_sll2, d_norm2;      // second score / normaliser buffers of the overlapped pipeline
   akugpu::DevBuf d_cmllr, d_adapt;     // double [D*D + D] (A row-major, then b); adapted features of the current call
   akugpu::DevBuf d_fe[8];
   std::vector<std::shared_ptr<akugpu::DevBuf>> fe_bufs;   // per-module output matrices (grow-only)

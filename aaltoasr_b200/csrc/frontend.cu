@@ -231,6 +231,7 @@ void upload_module_params(akugpu_ctx *ctx, Module &m, const std::vector<Module> 
       m.d_a = upload_vec(scales, st);
       m.d_b = upload_vec(desc, st);
       m.d_c = upload_vec(sums, st);
+      m.d_d = upload_vec(std::vector<double>(scales.begin(), scales.end()), st);
       break;
     }
     case M_DCT: {
@@ -240,6 +241,7 @@ void upload_module_params(akugpu_ctx *ctx, Module &m, const std::vector<Module> 
       for (int i = 0; i < m.dim - bias; i++)
         for (int b = 0; b < sd; b++) tab[(size_t)(i + bias) * sd + b] = cosf((i + 1) * (b + 0.5) * M_PI / sd);   // :977
       m.d_a = upload_vec(tab, st);
+      m.d_d = upload_vec(std::vector<double>(tab.begin(), tab.end()), st);
       break;
     }
     case M_VTLN: {
@@ -612,6 +614,16 @@ __device__ __forceinline__ void row_to_frame(const int *__restrict__ row_utt, co
   t = utts[u].start - H + (int)(r - utts[u].row_off);
 }
 
+// row r of the module buffers belongs to the utterance whose [row_off, next row_off) holds it: binary search.
+__global__ void fe_build_row_utt(const UttDesc *__restrict__ utts, int n_utts, int64_t n_rows, int *__restrict__ row_utt)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int lo = 0, hi = n_utts;                      // largest u with utts[u].row_off <= r
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (utts[mid].row_off <= r) lo = mid; else hi = mid; }
+  row_utt[r] = lo;
+}
+
 // PreModule::generate (aku/FeatureModules.cc:705-755): the base module's rows are stored float32 features; frames before
 // the file repeat the first row, frames after it the last one.  raw: all utterances' rows back to back.
 __global__ void fe_pre_base(const float *__restrict__ raw, int dim, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
@@ -652,6 +664,7 @@ struct FuseStatic {
   MelTable mel = {nullptr, nullptr, nullptr};
   int dct_dim = 0, dct_col = 0;
   const float *dct_table = nullptr;
+  const double *mel_scale_d = nullptr, *dct_table_d = nullptr;   // the same tables widened to double
   int pow_col = -1;            // -1: no power module
   int odim = 0;
   double *out = nullptr;       // [rows][odim]
@@ -779,6 +792,140 @@ fe_spectrum_fft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utt
     for (int b = 0; b < fuse.mel_dim; b++) acc = __dadd_rn(acc, __dmul_rn(melv[fl][b], (double)tb[b]));
     fuse.out[r * fuse.odim + fuse.dct_col + tl] = acc;
   }
+}
+
+// audiofile + fft with ONE WARP PER FRAME for power-of-two windows (128 ... 2048 samples): the N/2-point complex FFT lives
+// in registers -- lane l holds the elements l, l + 32, ... -- the radix-2 DIT stages whose partners sit in another lane
+// exchange them with shuffles (both lanes form the same twiddle product: same operations, same bits as a shared-memory
+// butterfly), the later stages are register-to-register; no CTA barrier anywhere.  The real-FFT split goes once through
+// a per-warp shared-memory row (conjugate-symmetric gather), and the fused epilogue (mel bins on 21 lanes, the sequential
+// float power sum on the last lane, the dct on 12 lanes) is warp-local as well.  Float / double placement as in
+// fe_spectrum_fft; the mel and dct tables are read widened to double, the spectrum is kept widened next to its floats
+// (two conversions per mel tap instead of four, none in the dct).
+template <int N>
+__global__ void __launch_bounds__(256)
+fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                 int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
+                 const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out, const FuseStatic fuse)
+{
+  constexpr int M = N / 2, NR = M / 32, LOGM = fe_log2(M);
+  constexpr int WPB = 8;                                        // frames (warps) per CTA
+  static_assert((M & (M - 1)) == 0 && M >= 32 && M <= 256, "window must be a power of two, 64 ... 512 samples");
+  __shared__ float2 zs[WPB][M];
+  __shared__ __align__(16) float pwf[WPB][M + 4];
+  __shared__ double pwd[WPB][M + 2];
+  __shared__ double melv[WPB][FUSE_MAX_MEL];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * WPB + w;
+  const bool valid = r < n_rows;
+  int u = 0, t = 0;
+  if (valid) row_to_frame(row_utt, utts, r, H, u, t);
+  const UttDesc ud = utts[u];
+  int tc = t;
+  if (copy_borders) tc = min(max(t, 0), ud.n_frames - 1);
+  const int ws = (int)(tc * adv);                              // window start: AudioFileModule::generate, aku/FeatureModules.cc:378-397
+  const int16_t *x = pcm + ud.pcm_off;
+  float2 z[NR];
+#pragma unroll
+  for (int rr = 0; rr < NR; rr++) {
+    const int pos = rr * 32 + lane;                            // position after the bit reversal of the decimation in time
+    const int k = (int)(__brev((unsigned)pos) >> (32 - LOGM));
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = 2 * k + e;
+      const int64_t p0 = (int64_t)ws + i, p1 = p0 + 1;
+      const float s0 = (valid && p0 >= 0 && p0 < ud.n_samples) ? (float)x[p0] : 0.f;
+      const float s1 = (valid && p1 >= 0 && p1 < ud.n_samples) ? (float)x[p1] : 0.f;
+      const float pe = __fsub_rn(s1, __fmul_rn(emph, s0));                  // float pre-emphasis (:429)
+      // float window * double sample -> float (:531): the double product of two floats is exact, so its rounding to
+      // float is the fp32 product
+      v[e] = __fmul_rn(__ldg(window + i), pe);
+    }
+    z[rr] = make_float2(v[0], v[1]);
+  }
+  // stages whose partner is in another lane: half = 1 .. 16
+#pragma unroll
+  for (int half = 1; half < 32; half <<= 1) {
+    const float2 wv = __ldg(tw + (lane & (half - 1)) * (N / (2 * half)));   // twiddle e^{-2 pi i j / len} = tw[j * N / len]
+    const bool hi = (lane & half) != 0;
+#pragma unroll
+    for (int rr = 0; rr < NR; rr++) {
+      const float2 mine = z[rr];
+      const float2 other = make_float2(__shfl_xor_sync(0xffffffffu, mine.x, half), __shfl_xor_sync(0xffffffffu, mine.y, half));
+      const float2 a = hi ? other : mine, c = hi ? mine : other;
+      const float2 wc = make_float2(c.x * wv.x - c.y * wv.y, c.x * wv.y + c.y * wv.x);
+      z[rr] = hi ? make_float2(a.x - wc.x, a.y - wc.y) : make_float2(a.x + wc.x, a.y + wc.y);
+    }
+  }
+  // stages inside the lane: half = 32 .. M / 2, register distance half / 32
+#pragma unroll
+  for (int hr = 1; hr < NR; hr <<= 1) {
+    const int half = hr * 32;
+#pragma unroll
+    for (int rr = 0; rr < NR; rr++) {
+      if (rr & hr) continue;
+      const int j = ((rr & (hr - 1)) << 5) | lane;
+      const float2 wv = __ldg(tw + j * (N / (2 * half)));
+      const float2 a = z[rr], c = z[rr + hr];
+      const float2 wc = make_float2(c.x * wv.x - c.y * wv.y, c.x * wv.y + c.y * wv.x);
+      z[rr] = make_float2(a.x + wc.x, a.y + wc.y);
+      z[rr + hr] = make_float2(a.x - wc.x, a.y - wc.y);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < NR; rr++) zs[w][rr * 32 + lane] = z[rr];
+  __syncwarp();
+  // split: X[k] = (Z[k]+conj(Z[M-k]))/2 - i e^{-2 pi i k/N} (Z[k]-conj(Z[M-k]))/2 ,  k = 0..M
+  {
+    double *o = out + r * (M + 1);
+    for (int k = lane; k <= M; k += 32) {
+      const float2 a = zs[w][k == M ? 0 : k], b = zs[w][k == 0 ? 0 : M - k];
+      const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+      const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
+      const float2 wv = (k == M) ? make_float2(-1.f, 0.f) : __ldg(tw + k);
+      const float2 wd = make_float2(wv.x * d.x - wv.y * d.y, wv.x * d.y + wv.y * d.x);      // -i * w * d below
+      const float re = e.x + wd.y, im = e.y - wd.x;
+      float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));       // float power (:534-537)
+      if (magnitude) p = sqrtf(p);
+      if (do_log) p = logf(p);
+      if (fuse.on) { pwf[w][k] = p; pwd[w][k] = (double)p; }
+      else if (valid) o[k] = (double)p;
+    }
+  }
+  if (!fuse.on) return;
+  __syncwarp();
+  // mel bins: MelModule::generate (:806-849) from the precomputed triangle weights; float accumulator fed through a
+  // double product, as the reference's `val += scale * data`
+  for (int b = lane; b < fuse.mel_dim; b += 32) {
+    const int t0 = fuse.mel.desc[3 * b], n = fuse.mel.desc[3 * b + 1];
+    const double *sc = fuse.mel_scale_d + fuse.mel.desc[3 * b + 2];
+    float val = 0;
+    for (int i = 0; i < n; i++) val = (float)__dadd_rn((double)val, __dmul_rn(sc[i], pwd[w][min(t0 + i, M)]));
+    const float sum = fuse.mel.sum[b];
+    melv[w][b] = fuse.mel_root ? pow((double)__fdiv_rn(val, sum), 0.1) : (double)logf(__fadd_rn(__fdiv_rn(val, sum), 1.f));
+  }
+  // power: the float accumulator of PowerModule (:875-885) is a chain of FADDs (see fe_spectrum_fft); the last lane has
+  // no mel bin to compute in the usual configurations
+  if (fuse.pow_col >= 0 && lane == 31) {
+    float power = 0;
+    const float4 *p4 = reinterpret_cast<const float4 *>(pwf[w]);
+#pragma unroll 4
+    for (int i = 0; i < M / 4; i++) {
+      const float4 q = p4[i];
+      power = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(power, q.x), q.y), q.z), q.w);
+    }
+    power = __fadd_rn(power, pwf[w][M]);
+    if (valid) fuse.out[r * fuse.odim + fuse.pow_col] = log(__dadd_rn((double)power, 1e-10));
+  }
+  __syncwarp();
+  if (valid)
+    for (int c = lane; c < fuse.dct_dim; c += 32) {          // DCTModule::generate (:956-979)
+      const double *tb = fuse.dct_table_d + (size_t)c * fuse.mel_dim;
+      double acc = 0.0;
+      for (int b = 0; b < fuse.mel_dim; b++) acc = __dadd_rn(acc, __dmul_rn(melv[w][b], tb[b]));
+      fuse.out[r * fuse.odim + fuse.dct_col + c] = acc;
+    }
 }
 
 // Fused tail  X -> delta -> delta -> merge(X, d1, d2) -> output rows without the halo (DeltaModule::generate :1019-1037
@@ -1099,18 +1246,19 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
   int64_t n_rows = 0;
   for (auto &u : utts) { u.row_off = n_rows; n_rows += (int64_t)u.n_rows_out + 2 * H; }
   if (n_rows == 0) return;
-  std::vector<int> row_utt((size_t)n_rows);
-  for (size_t u = 0; u < utts.size(); u++)
-    for (int64_t r = utts[u].row_off; r < utts[u].row_off + utts[u].n_rows_out + 2 * H; r++) row_utt[(size_t)r] = (int)u;
   cudaStream_t st = ctx->stream;
   DevBuf &d_utts = ctx->d_fe[0], &d_rowutt = ctx->d_fe[1];
   d_utts.reserve(utts.size() * sizeof(UttDesc));
-  d_rowutt.reserve(row_utt.size() * sizeof(int));
+  d_rowutt.reserve((size_t)n_rows * sizeof(int));
   AKU_CUDA(cudaMemcpyAsync(d_utts.p, utts.data(), utts.size() * sizeof(UttDesc), cudaMemcpyHostToDevice, st));
-  AKU_CUDA(cudaMemcpyAsync(d_rowutt.p, row_utt.data(), row_utt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  // the pageable sources above must stay alive until the copies are done
+  // the pageable source above must stay alive until the copy is done
   AKU_CUDA(cudaStreamSynchronize(st));
   const UttDesc *du = d_utts.as<UttDesc>();
+  // row -> utterance table, built on the device (a million-entry host loop + copy per call used to be a third of the
+  // front-end stage of a config-2 step)
+  fe_build_row_utt<<<grid1(n_rows, 256), 256, 0, st>>>(du, (int)utts.size(), n_rows, d_rowutt.as<int>());
+  AKU_CUDA(cudaGetLastError());
+  ctx->launches++;
   const int *dr = d_rowutt.as<int>();
 
   const int16_t *d_pcm = reinterpret_cast<const int16_t *>(d_in);      // audiofile base; a `pre` base reads float rows
@@ -1208,6 +1356,7 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
           fuse.mel_dim = mel.dim; fuse.mel_root = mel.root;
           fuse.mel = MelTable{mel.d_a->as<float>(), mel.d_b->as<int>(), mel.d_c->as<float>()};
           fuse.dct_dim = dct.dim; fuse.dct_table = dct.d_a->as<float>();
+          fuse.mel_scale_d = mel.d_d->as<double>(); fuse.dct_table_d = dct.d_d->as<double>();
           fuse.odim = fe.mods[f_out].dim;
           fuse.out = buf[f_out]->as<double>();
           if (f_pow >= 0) {   // column order of the merge
@@ -1224,10 +1373,28 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
                                                              mod.log, o, fuse);                                     \
     break;                                                                                                          \
   }
-        switch (N) {
-          SPEC_FFT(128)
-          SPEC_FFT(256)
-          SPEC_FFT(512)
+#define SPEC_WFFT(NN)                                                                                               \
+  case NN: {                                                                                                        \
+    constexpr int WPB_ = 8;                                                                                         \
+    fe_spectrum_wfft<NN><<<grid1(n_rows, WPB_), WPB_ * 32, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,  \
+                                                                   base.emph, base.copy_borders, win, tw,           \
+                                                                   mod.magnitude, mod.log, o, fuse);                \
+    break;                                                                                                          \
+  }
+        const char *old_fft = getenv("AKUGPU_FE_OLDFFT");             // the shared-memory kernel, for comparisons
+        if (old_fft && (N & (N - 1)) == 0) {
+          switch (N) {
+            SPEC_FFT(128)
+            SPEC_FFT(256)
+            SPEC_FFT(512)
+            SPEC_FFT(1024)
+            SPEC_FFT(2048)
+          }
+        } else
+        switch (N) {       // measured (profiles/r02_config3_frontend.txt): one warp per frame wins up to 512 samples
+          SPEC_WFFT(128)
+          SPEC_WFFT(256)
+          SPEC_WFFT(512)
           SPEC_FFT(1024)
           SPEC_FFT(2048)
           SPEC_FFT(192)
@@ -1240,6 +1407,7 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
                                                                              mod.magnitude, mod.log, o);
         }
 #undef SPEC_FFT
+#undef SPEC_WFFT
         break;
       }
       case M_MEL:

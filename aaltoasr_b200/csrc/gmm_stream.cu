@@ -62,6 +62,7 @@ gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
   __shared__ uint64_t full_bar[MAX_TSLOTS], empty_bar[MAX_TSLOTS], tmem_full[2], tmem_empty[2], a_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float2 part[2][2][SLOTS][NF];                    // [group][tile parity][slot][frame] = {max, sum of exp}
+  __shared__ int pmeta[2][2][SLOTS];                          // the tile's slot table, fetched while its MMAs run
   unsigned char *ring = smem + KB * A_BLOCK;
   float *stage_x = reinterpret_cast<float *>(ring + (size_t)tslots * SLOT_BYTES);
 
@@ -188,10 +189,12 @@ gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     const int bar_id = 2 + group;
     for (int n = n_begin + group; n < n_end; n += 2) {
       const int use = (n - n_begin) >> 1;
+      if (tg < SLOTS) pmeta[group][use & 1][tg] = __ldg(meta + (size_t)n * SLOTS + tg);     // off the critical path
       mbar_wait(&tmem_full[group], use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + group * 2 * NF;
       float2(*pt)[NF] = part[group][use & 1];
+      const int *pm = pmeta[group][use & 1];
 #pragma unroll
       for (int h = 0; h < NF / 16; h++) {
         uint32_t rm[16], rc[16];
@@ -223,7 +226,7 @@ gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
       // states = one 32-byte store per frame
       for (int e = tg; e < NF * SLOTS; e += GROUP_THREADS) {
         const int f = e >> 3, k = e & 7;
-        const int mt = __ldg(meta + (size_t)n * SLOTS + k);
+        const int mt = pm[k];
         if (f < nf && mt >= 0 && (mt & 1)) {
           float2 a = pt[k][f];
           if (!(mt & 2)) {
@@ -232,7 +235,7 @@ gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
               const float M = fmaxf(a.x, b.x);
               a.y = a.y * ex2f((a.x - M) * LOG2E) + b.y * ex2f((b.x - M) * LOG2E);
               a.x = M;
-              if (__ldg(meta + (size_t)n * SLOTS + j) & 2) break;
+              if (pm[j] & 2) break;
             }
           }
           float res = fmaf(lg2f(a.y), LN2, a.x);
@@ -242,7 +245,6 @@ gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
       }
       // the table of the other parity is written next; this one again only after the next barrier
     }
-    __threadfence_system();                                    // results (possibly in mapped host memory) before the counter
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -251,6 +253,8 @@ gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(4 * NF) : "memory");
   }
   if (threadIdx.x == 0) {
+    // ONE system-scope fence per CTA: the barrier above orders every thread's result stores (possibly into mapped host
+    // memory) before it, and the fence is cumulative (a fence per writing thread cost more than the whole sweep)
     __threadfence_system();
     const unsigned int old = atomicAdd(cnt, 1u);
     if (old == gridDim.x * gridDim.y - 1) {                    // last CTA: re-arm the counter, publish the sequence number

@@ -98,29 +98,40 @@ __device__ __forceinline__ float2 norm_merge(const float (&M)[4], const double (
 // accumulation from the stored scores -- the same four partial streams (tiles of one parity x slots of one half tile, in
 // tile and slot order), the same operations, the same merge -- so a frame's LNA bytes are identical whichever launch
 // shape scored it (per-utterance checksums of differently batched runs are compared, multigpu.cu).
-__global__ void __launch_bounds__(128)
+// Four threads per frame, one per partial stream; two tiles (up to eight scores) are loaded before their updates run.
+__global__ void __launch_bounds__(256)
 tc16_norm_replay(const float *__restrict__ sll, int64_t ldF, int64_t nf, const int *__restrict__ meta, int n_tiles,
                  float2 *__restrict__ norm)
 {
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= nf) return;
+  const int o = threadIdx.x & 3;                                   // partial o as the epilogue merges them:
+  const int group = o >> 1, half = o & 1;                          // 0 (group 0, half 0), 1 (0, 1), 2 (1, 0), 3 (1, 1)
+  const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+  const bool valid = f < nf;
+  const float *col = sll + (valid ? f : 0);
+  float nMx = -INFINITY, nR = 0.f;
+  const int4 *meta4 = reinterpret_cast<const int4 *>(meta);
+  for (int n = group; n < n_tiles; n += 4) {
+    const int4 ma = __ldg(meta4 + (size_t)n * 2 + half);
+    const bool second = n + 2 < n_tiles;
+    const int4 mb = second ? __ldg(meta4 + (size_t)(n + 2) * 2 + half) : make_int4(-1, -1, -1, -1);
+    const int m8[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (m8[k] >= 0 && (m8[k] & 1)) ? __ldg(col + (int64_t)(m8[k] >> 2) * ldF) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (m8[k] >= 0 && (m8[k] & 1)) norm_update(v[k], nMx, nR);
+  }
+  // the four partials of a frame sit in neighbouring lanes
   float M[4];
   double R[4];
-  // partial o as the epilogue merges them: o = 0 (group 0, half 0), 1 (group 0, half 1), 2 (group 1, half 0), 3 (group 1, half 1)
-  for (int o = 0; o < 4; o++) {
-    const int group = o >> 1, half = o & 1;
-    float nMx = -INFINITY, nR = 0.f;
-    for (int n = group; n < n_tiles; n += 2) {
-      const int4 mt = __ldg(reinterpret_cast<const int4 *>(meta) + (size_t)n * 2 + half);
-      const int m4[4] = {mt.x, mt.y, mt.z, mt.w};
+  const int base = (threadIdx.x & 31) & ~3;
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (m4[k] >= 0 && (m4[k] & 1)) norm_update(__ldg(sll + (int64_t)(m4[k] >> 2) * ldF + f), nMx, nR);
-    }
-    M[o] = nMx;
-    R[o] = (double)nR;
+  for (int k = 0; k < 4; k++) {
+    M[k] = __shfl_sync(0xffffffffu, nMx, base + k);
+    R[k] = (double)__shfl_sync(0xffffffffu, nR, base + k);
   }
-  norm[f] = norm_merge(M, R);
+  if (valid && o == 0) norm[f] = norm_merge(M, R);
 }
 
 // NCH > 0: A' resident (built in the kernel), B' streamed one component tile per ring slot.
@@ -423,12 +434,18 @@ static inline float half_val(uint16_t b)
 
 static size_t tc16_stage_x_bytes(int D) { return ((size_t)tc16::BM * D * sizeof(float) + 1023) / 1024 * 1024; }
 // ring slots (one component tile of B' each) that fit beside A' and the feature staging area
-static int tc16_tslots(int KB, int D)
+static int tc16_tslots(int KB, int D, bool leave_room = false)
 {
   const size_t budget = 227 * 1024 - 8192 /* static shared memory */ - 1024 /* alignment */;
   const size_t fixed = (size_t)KB * tc16::BLOCK_BYTES + tc16_stage_x_bytes(D);
   if (fixed >= budget) return 0;
-  return (int)std::min<size_t>(tc16::MAX_TSLOTS, (budget - fixed) / ((size_t)KB * tc16::BLOCK_BYTES));
+  int n = (int)std::min<size_t>(tc16::MAX_TSLOTS, (budget - fixed) / ((size_t)KB * tc16::BLOCK_BYTES));
+  // leave_room: the LNA epilogue of the previous chunk shares the SM (33 KB of shared memory per CTA, api.cu); two ring
+  // slots cover the L2 latency of a 48 KB tile at the ~1 us a tile takes
+  if (leave_room) while (n > 2 && fixed + (size_t)n * KB * tc16::BLOCK_BYTES + 40 * 1024 > budget) n--;
+  static const char *force = getenv("AKUGPU_TC16_SLOTS");
+  if (force && atoi(force) >= 2) n = std::min(n, atoi(force));
+  return n;
 }
 constexpr int TC16_STREAM_STAGES = 3;      // 3 x 64 KB stages of {Ah, Al, Bh, Bl}
 
@@ -642,7 +659,7 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   const int *ranges = tc_tile_ranges(ctx, p.n_tiles, p.clean, p.ranges, want, ysplit);
   float2 *replay_norm = nullptr;          // a frame's states are spread over several CTAs: the normaliser is replayed afterwards
   if (ysplit != 1) { replay_norm = norm; norm = nullptr; }
-  const int tslots = p.stream ? TC16_STREAM_STAGES : tc16_tslots(p.KB, p.D);
+  const int tslots = p.stream ? TC16_STREAM_STAGES : tc16_tslots(p.KB, p.D, ctx->overlap_lna);
   const size_t smem = p.stream ? 1024 + (size_t)tslots * 4 * tc16::BLOCK_BYTES
                                : 1024 + (size_t)(1 + tslots) * p.KB * tc16::BLOCK_BYTES + tc16_stage_x_bytes(p.D);
   StageScope sc(ctx, 1);
@@ -667,7 +684,7 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
   if (replay_norm) {
-    tc16_norm_replay<<<(unsigned)((nf + 127) / 128), 128, 0, ctx->stream>>>(sll, ldF, nf, p.meta.as<int>(), p.n_tiles, replay_norm);
+    tc16_norm_replay<<<(unsigned)((nf + 63) / 64), 256, 0, ctx->stream>>>(sll, ldF, nf, p.meta.as<int>(), p.n_tiles, replay_norm);
     AKU_CUDA(cudaGetLastError());
     ctx->launches++;
     return true;

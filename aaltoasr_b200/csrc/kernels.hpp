@@ -49,8 +49,9 @@ bool stream_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_f
 void stream_probe(akugpu_ctx *ctx, double out[8]);
 
 // lna_kernels.cu
+// norm_scratch: where a normaliser pass of its own writes (default: ctx->d_norm)
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
-                    const float2 *norm, uint8_t *out);
+                    const float2 *norm, uint8_t *out, float2 *norm_scratch = nullptr);
 void launch_lna_f64(akugpu_ctx *ctx, const double *lin, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
                     uint8_t *out);
 void launch_checksum(akugpu_ctx *ctx, const uint8_t *buf, int64_t nbytes, unsigned long long *acc);
@@ -90,6 +91,7 @@ struct StageScope {
   akugpu_ctx *ctx;
   int stage;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st = nullptr;
   int64_t l0;
   StageScope(akugpu_ctx *c, int s);
   ~StageScope();

@@ -363,7 +363,7 @@ __global__ void checksum_kernel(const uint8_t *__restrict__ buf, int64_t nbytes,
 }
 
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
-                    const float2 *norm, uint8_t *out)
+                    const float2 *norm, uint8_t *out, float2 *norm_scratch)
 {
   if (nf <= 0) return;
   unsigned grid = (unsigned)((nf + 31) / 32);
@@ -371,11 +371,11 @@ void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64
   // a pass of its own
   if (((size_t)S * lnabytes) % 4 == 0 && ((uintptr_t)out & 3) == 0 && !getenv("AKUGPU_LNA_OLD")) {
     if (normalize && !norm) {
-      ctx->d_norm.reserve((size_t)(nf + 31) / 32 * 32 * sizeof(float2));
-      lna_f32_norm<<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, ctx->d_norm.as<float2>());
+      if (!norm_scratch) { ctx->d_norm.reserve((size_t)(nf + 31) / 32 * 32 * sizeof(float2)); norm_scratch = ctx->d_norm.as<float2>(); }
+      lna_f32_norm<<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm_scratch);
       AKU_CUDA(cudaGetLastError());
       ctx->launches++;
-      norm = ctx->d_norm.as<float2>();
+      norm = norm_scratch;
     }
     if (lnabytes == 2 && normalize) lna_f32_rows<2, true><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
     else if (lnabytes == 2) lna_f32_rows<2, false><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);

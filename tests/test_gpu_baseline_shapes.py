@@ -310,3 +310,27 @@ def test_lna_bytes_do_not_depend_on_the_launch_shape(engine, gpu_feats):
     finally:
         engine.set_chunk_frames(0)
     assert np.array_equal(c[:300], a) and np.array_equal(c[-300:], a)
+
+
+def test_overlapped_lna_pipeline_writes_the_same_bytes(engine, gpu_feats, monkeypatch):
+    """The LNA epilogue of chunk k runs on a second stream next to the scorer of chunk k+1 (double-buffered scores): same
+    bytes as the serial pipeline (AKUGPU_OVERLAP=0), device and host outputs, checksums, several chunks + a ragged tail."""
+    import torch
+    from aaltoasr_b200 import AkuGpu
+    model = synth.synth_diag_model(2999, gpu_feats, 5000, 16)
+    pcm = np.concatenate([synth.synth_audio(2000 + i, 160000) for i in range(70)])       # 87 360 frames: 3 chunks, the last one ragged
+    uo = np.arange(71, dtype=np.int64) * 160000
+    res = {}
+    for tag, env in (("overlap", "1"), ("serial", "0")):
+        monkeypatch.setenv("AKUGPU_OVERLAP", env)
+        with AkuGpu(0) as eng:
+            eng.frontend_load_config_text(synth.mfcc39_config(16000))
+            load_model(eng, model)
+            host, fo, chk = eng.phone_probs(pcm, uo, lnabytes=2, utt_checksums=True)
+            dev = torch.empty(host.shape, dtype=torch.uint8, device="cuda")
+            _, _, tot = eng.phone_probs(torch.from_numpy(pcm).cuda(), uo, lnabytes=2, out=dev, checksum=True)
+            f4 = eng.gmm_lna(gpu_feats[:2000].astype(np.float32), lnabytes=4, normalize=False)
+            res[tag] = (host, chk, dev.cpu().numpy(), tot, f4)
+    a, b = res["overlap"], res["serial"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    assert np.array_equal(a[0], a[2]) and a[3] == int(a[0].astype(np.uint64).sum()) and np.array_equal(a[4], b[4])

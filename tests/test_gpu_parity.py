@@ -110,7 +110,30 @@ def test_fused_frontend_identical_to_module_by_module(engine, sr, monkeypatch):
         n_plain = engine.launch_count() - l0
         monkeypatch.delenv("AKUGPU_FE_NOFUSE")
         assert np.array_equal(fused, plain)
-        assert n_fused == 2 and n_plain >= 10, (n_fused, n_plain)
+        assert n_fused == 3 and n_plain >= 10, (n_fused, n_plain)      # row table + fused spectrum kernel + fused delta kernel
+
+
+@pytest.mark.parametrize("sr,ww", [(8000, None), (16000, None), (16000, 512), (16000, 1024), (16000, 2048), (32000, None)])
+def test_warp_fft_kernel_against_the_shared_memory_kernel(engine, sr, ww, monkeypatch):
+    """Power-of-two windows run one warp per frame with the FFT in registers (fe_spectrum_wfft); the butterflies, twiddles
+    and roundings are those of the shared-memory kernel (fe_spectrum_fft, AKUGPU_FE_OLDFFT=1): spectra and features agree
+    up to the compiler's choice of which multiply-adds it contracts (a few 1e-6 relative on a spectrum bin)."""
+    from aaltoasr_b200 import synth
+    cfg = synth.mfcc39_config(sr)
+    if ww:
+        cfg = cfg.replace("sample_rate %d" % sr, "sample_rate %d\n  window_width %d" % (sr, ww))
+    engine.frontend_load_config_text(cfg)
+    pcm = synth.synth_audio(3200 + sr // 1000, sr, sr)
+    new = engine.features(pcm, dtype=np.float64)[0]
+    new_fft = engine.features_range(pcm, -2, 9, module="fft")
+    monkeypatch.setenv("AKUGPU_FE_OLDFFT", "1")
+    old = engine.features(pcm, dtype=np.float64)[0]
+    old_fft = engine.features_range(pcm, -2, 9, module="fft")
+    monkeypatch.delenv("AKUGPU_FE_OLDFFT")
+    print("sr %d window %s: max |feature diff| %.3g, max relative spectrum diff %.3g, identical: %s" % (
+        sr, ww, np.abs(new - old).max(), (np.abs(new_fft - old_fft) / np.maximum(np.abs(old_fft), 1e-30)).max(), np.array_equal(new, old)))
+    assert np.abs(new - old).max() <= 3e-6
+    assert (np.abs(new_fft - old_fft) <= 5e-6 * np.abs(old_fft) + 1e-3).all()
 
 
 @pytest.mark.parametrize("sr,ww", [(8000, None), (16000, 512), (32000, None), (16000, 2048), (48000, None), (16000, 400),
