@@ -20,7 +20,8 @@ utterances are independent, no data-path collective).
           /root/reference) on the host cores, on a bounded sample of the same workload
   sub_records : the other BASELINE.json configs in the same driver-run line (each a small, separately timed run):
           N = 1: parity_mode_f64 (config-2 model in the byte-exact double arithmetic), config3_feature_sweep,
-                 config5_full_covariance (+ its own cpu_baseline), config4_model_1gpu (10000 x 32 on one GPU)
+                 config5_full_covariance (+ its own cpu_baseline), config4_model_1gpu (10000 x 32 on one GPU),
+                 streaming (the decoder's per-frame feed: microseconds per call, sweep rate against L2 / HBM)
           N > 1: config4 (100 h sharded by utterance over the N GPUs, 10000 x 32: model broadcast, frame-count
                  all-gather, LPT partition, per-rank writers AND the LNA gather to one writer rank -- fused p2p stores
                  and ncclSend/Recv -- with a checksum sink, 1-vs-N per-utterance checksum check), host_d2h (the
@@ -301,6 +302,7 @@ def bench_feature_sweep(args, local):
         l0 = eng.launch_count()
         ms = _event_time(torch, stream, lambda: eng.features(pcm_d, uo, out=out_d), reps)
         launches = eng.launch_count() - l0
+        eng.features(pcm_p, uo, out=out_p)            # warm-up of the host-buffer path (staging buffers grow on first use)
         ms_e2e = _event_time(torch, stream, lambda: eng.features(pcm_p, uo, out=out_p), reps)
         hop = sr / 125.0
         alg = (2 * hop + 4 * dim) * F
@@ -321,11 +323,13 @@ def bench_feature_sweep(args, local):
             "e2e": {"value": head["e2e_frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": head["h2d"],
                     "d2h_bytes_per_step": head["d2h"], "ms_per_step": head["ms_e2e"]},
             "gpu_launches": int(head["launches"]),
-            "roofline": {"kernel": "front-end module kernels (fe_spectrum_pow2 dominant)", "bound": "hbm",
-                         "achieved": head["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
+            "roofline": {"kernel": "fe_spectrum_wfft<256> (one warp per frame, FFT in registers, fused mel + power + dct + merge) + fe_delta2_merge",
+                         "bound": "hbm", "achieved": head["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
                          "traffic": None, "peak_source": hbm_src,
-                         "note": "module outputs are separate double matrices: actual traffic is ~10x the algorithmic 412 B/frame; "
-                                 "the FFT stage is FP32/shared-memory bound (DESIGN.md 4.4)"},
+                         "algorithmic": "2 * hop + 4 * dim = 412 B per frame (SURVEY.md 8d) x frames / time of a whole akugpu_features call",
+                         "note": "the stage is issue / latency bound, not bandwidth bound: ncu (profiles/r02_fe_spectrum_wfft_ncu_full.txt) shows "
+                                 "1761 warp instructions per frame at 79 % issue-slot utilisation, DRAM traffic 260 B per frame at 1.5 % of "
+                                 "DRAM throughput; the operations are the reference's float / double sequence, reproduced exactly"},
             "sweep": sweep, "cpu_baseline": None}
 
 
@@ -502,6 +506,66 @@ def sub_parity_mode(args, torch, eng, stream, pcm_d, pcm_p, uo, fo, n_utts=24):
             "config": {"workload": "%d utterances x 10 s of the headline workload, F64 parity arithmetic (gmm_diag_f64 + lna_f64: the "
                                    "reference's operations in double, LNA bytes identical to the reference's)" % n, "frames": F},
             "e2e": {"value": F / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": ns * 2, "d2h_bytes_per_step": F * rec, "ms_per_step": ms_e}}
+
+
+def sub_streaming(args, local, model2):
+    """Streaming regime: the decoder's per-frame feed -- a call of akugpu_gmm_logprobs on F <= 32 frames
+    sweeps the whole parameter image.  Latency per call through the C ABI with HOST buffers, the kernel's sweep rate, and
+    the L2 / HBM read rates of that very buffer it is measured against."""
+    import ctypes as C
+    from aaltoasr_b200 import AkuGpu, synth
+    hbm_peak, hbm_src = measured_peaks()
+    out = {"metric": "microseconds per akugpu_gmm_logprobs call (host features in, host log-probs out)", "unit": "us", "higher_is_better": False,
+           "kernel": "gmm_stream_kernel (tcgen05, GEMM turned around: components x frames; one launch over all SMs; results and the "
+                     "completion flag written into mapped host memory)", "models": {}}
+    eng = AkuGpu(local)
+    eng.frontend_load_config_text(synth.mfcc39_config(SAMPLE_RATE))
+    pcm = np.concatenate([synth.synth_audio(2000 + i, UTT_SAMPLES, SAMPLE_RATE) for i in range(2)])
+    feats, _ = eng.features(pcm, np.arange(3, dtype=np.int64) * UTT_SAMPLES, dtype=np.float32)
+    lib, h = eng._lib, eng._h
+    for name, model in (("5000x16", model2), ("10000x32", synth.synth_diag_model(4999, feats.astype(np.float64), C4_STATES, C4_MIX))):
+        eng.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
+        S = eng.num_states
+        rec = {}
+        for F in (1, 8, 16, 32):
+            x = np.ascontiguousarray(feats[100:100 + F])
+            ob = np.empty((F, S), dtype=np.float32)
+            px, po = C.c_void_p(x.ctypes.data), C.c_void_p(ob.ctypes.data)
+            tiny = C.c_double(1e-30)
+            for _ in range(100):
+                lib.akugpu_gmm_logprobs(h, px, 0, F, 0, tiny, po)
+            n = 2000 if F <= 8 else 500
+            t0 = time.perf_counter()
+            for _ in range(n):
+                lib.akugpu_gmm_logprobs(h, px, 0, F, 0, tiny, po)
+            rec["F=%d" % F] = 1e6 * (time.perf_counter() - t0) / n
+        eng.set_streaming(False)
+        x = np.ascontiguousarray(feats[100:101])
+        ob = np.empty((1, S), dtype=np.float32)
+        for _ in range(20):
+            eng.gmm_logprobs(x, tiny=1e-30, out=ob)
+        t0 = time.perf_counter()
+        for _ in range(300):
+            eng.gmm_logprobs(x, tiny=1e-30, out=ob)
+        general = 1e6 * (time.perf_counter() - t0) / 300
+        eng.set_streaming(True)
+        p = eng.stream_probe()
+        out["models"][name] = {
+            "us_per_call": rec, "us_per_call_general_path_F=1": general, "calls_per_s_F=1": 1e6 / rec["F=1"],
+            "x_realtime_per_frame_loop": 1e6 / rec["F=1"] / 125.0,
+            "image_bytes": p["image_bytes"],
+            "kernel_us_isolated_launch": 1e6 * p["kernel_s_l2"], "kernel_us_after_l2_flush": 1e6 * p["kernel_s_hbm"],
+            "kernel_us_in_launch_train": 1e6 * p["kernel_s_train"],
+            "sweep_GBps_in_launch_train": p["kernel_GBps_train"], "sweep_GBps_after_l2_flush": p["kernel_GBps_hbm"],
+            "l2_read_probe_GBps": p["probe_GBps_l2"], "hbm_read_probe_GBps_same_buffer": p["probe_GBps_hbm"],
+            "sweep_frac_of_l2_probe": p["kernel_GBps_train"] / p["probe_GBps_l2"],
+            "sweep_frac_of_hbm_peak_cold": p["kernel_GBps_hbm"] / hbm_peak, "hbm_peak_GBps": hbm_peak, "hbm_peak_source": hbm_src,
+            "sm_mhz": p["sm_mhz_train"],
+            "regime": "the image is L2-resident from the second call on (126 MB L2): the launch-train figure is an L2 sweep; the "
+                      "after-flush figure is the cold (HBM) sweep of a single launch, launch latency included"}
+    out["value"] = out["models"]["5000x16"]["us_per_call"]["F=1"]
+    eng.close()
+    return out
 
 
 def sub_full_cov_cpu_baseline(model_sub, feats, n_states_full):
@@ -1044,6 +1108,7 @@ def main():
             subs["config3_feature_sweep"] = guarded("config3", lambda: bench_feature_sweep(sub_args, local))
             subs["config5_full_covariance"] = guarded("config5", lambda: bench_full_cov(sub_args, local, cpu_baseline=not args.no_cpu_baseline))
             subs["config4_model_1gpu"] = guarded("config4", lambda: bench_config4(sub_args, torch, dist, rank, world, local, args.c4_utts or 300))
+            subs["streaming"] = guarded("streaming", lambda: sub_streaming(sub_args, local, model))
         else:
             def bail():
                 if rank == 0:
