@@ -163,7 +163,7 @@ struct PackedTC16 {
 };
 
 // streaming-regime scorer (gmm_stream.cu): pinned, mapped host block {flags | centred features | results}, CTA counter
-constexpr int STREAM_MAX_FRAMES = 32;
+constexpr int STREAM_MAX_FRAMES = 16;     // measured (tests/test_gpu_stream.py): beyond 16 frames (8 at 1250 tiles) the general path is as fast
 struct StreamState {
   void *host = nullptr, *dev_view = nullptr;
   size_t bytes = 0;

@@ -8,7 +8,7 @@
 // several launches, an fp16-overflow flag read-back and two copies: 41 us whatever F <= 128.
 //
 // Here: ONE kernel, the component tiles spread over all SMs (grid.y), and the GEMM turned around --
-//     D[component (M = 128), frame (N = 16 or 32)] = B'[128 x K] . A'[frames x K]^T
+//     D[component (M = 128), frame (N = 16)] = B'[128 x K] . A'[frames x K]^T
 // so the tensor-core time per tile is an eighth of the batch kernel's M = 128 frames (a tile then costs what its 48 KB
 // of parameters cost to fetch).  The epilogue reads TMEM with component = lane: the mixture log-sum-exp of a slot is a
 // 16-lane shuffle reduction; multi-slot states are merged through a tiny shared-memory table; the floor of the decoder
@@ -36,16 +36,16 @@ constexpr int THREADS = 384;                       // warp 0 TMA, warp 1 MMA, wa
 constexpr int EPI_THREADS = 256, GROUP_THREADS = 128;
 constexpr int MAX_TSLOTS = 4;
 constexpr float LO_INV = 1.f / 2048.f, LO_SCALE = 2048.f;
-constexpr int XS_MAX = 640;                        // centred features carried as kernel parameters (floats)
+constexpr int XS_DIM = 40;                         // centred features of up to NF frames x 40 dims travel as kernel parameters
 }  // namespace tcs
 
-struct StreamX { float v[tcs::XS_MAX]; };
+template <int NF> struct StreamX { float v[NF * tcs::XS_DIM]; };      // 2.5 KB (NF = 16) / 5 KB (NF = 32: large-parameter launch)
 
 // feats == nullptr: the frames are xs.v (already centred, [nf][D]); otherwise raw features in global / mapped memory,
 // centred here (center != nullptr) or taken as they are (center == nullptr: centred by the host into mapped memory).
 template <int NCH, int NF>
 __global__ void __launch_bounds__(tcs::THREADS, 1)
-gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ StreamX xs, int tslots,
+gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ StreamX<NF> xs, int tslots,
                   const int *__restrict__ range_begin, const int *__restrict__ meta, const void *__restrict__ feats, int feats_f64,
                   int nf, int D, int S, const double *__restrict__ center, const float *__restrict__ escale,
                   float *__restrict__ out, int use_floor, float floor_at, unsigned int *__restrict__ cnt,
@@ -322,11 +322,12 @@ bool stream_applicable(akugpu_ctx *ctx, int precision, int64_t n_frames)
   if (!p.ready || p.stream || p.hybrid || ctx->tc16_suspended || ctx->hm.cmllr_on) return false;
   if (ctx->hm.use_clustering && ctx->hm.n_clusters > 0) return false;
   if (p.NCH < 1 || p.NCH > 8 || p.D > 63) return false;
-  return stream_tslots(p.KB, n_frames <= 16 ? 16 : 32, p.D) >= 1;
+  if (n_frames > 8 && p.n_tiles > 800) return false;      // the result stores (32 bytes per tile and frame over PCIe) outweigh the sweep
+  return stream_tslots(p.KB, 16, p.D) >= 1;
 }
 
 template <int NF>
-static void stream_launch(akugpu_ctx *ctx, const StreamX &xs, const void *feats, int feats_f64, int nf, const double *center, float *out,
+static void stream_launch(akugpu_ctx *ctx, const StreamX<NF> &xs, const void *feats, int feats_f64, int nf, const double *center, float *out,
                           int use_floor, float floor_at, unsigned int seq, const int *ranges, int ysplit, int tslots)
 {
   PackedTC16 &p = ctx->ptc16;
@@ -377,7 +378,7 @@ static bool stream_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64,
   }
   int ysplit = 1;
   const int *ranges = tc_tile_ranges(ctx, p.n_tiles, p.clean, p.ranges, std::min(p.n_tiles, ctx->sm_count), ysplit);
-  const int NF = nf <= 16 ? 16 : 32;
+  constexpr int NF = 16;
   const int tslots = stream_tslots(p.KB, NF, D);
   unsigned char *hb = reinterpret_cast<unsigned char *>(st.host), *db = reinterpret_cast<unsigned char *>(st.dev_view);
   volatile unsigned int *hflags = reinterpret_cast<volatile unsigned int *>(hb);
@@ -386,25 +387,25 @@ static bool stream_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64,
   float *d_out = reinterpret_cast<float *>(db + 256) + STREAM_MAX_FRAMES * 64;
 
   const bool feats_dev = is_device_ptr(feats), out_dev = is_device_ptr(out);
-  StreamX xs;
+  StreamX<16> xs16;
+  float *xs_v = xs16.v;
   const void *k_feats = nullptr;
   int k_f64 = 0;
   const double *k_center = nullptr;
   if (feats_dev) { k_feats = feats; k_f64 = feats_f64; k_center = p.center.as<double>(); }
   else {
     // centre on the host exactly as the kernels do: (float)((double) f - c)
-    float *dst = (nf * D <= tcs::XS_MAX) ? xs.v : h_x;
+    float *dst = (D <= tcs::XS_DIM) ? xs_v : h_x;
     const double *c = p.h_center.data();
     if (feats_f64) { const double *f = (const double *)feats; for (int i = 0; i < nf; i++) for (int d = 0; d < D; d++) dst[i * D + d] = (float)(f[i * D + d] - c[d]); }
     else { const float *f = (const float *)feats; for (int i = 0; i < nf; i++) for (int d = 0; d < D; d++) dst[i * D + d] = (float)((double)f[i * D + d] - c[d]); }
-    if (dst == h_x) k_feats = d_x;      // too large for the parameter block: the kernel reads the mapped staging area
+    if (dst == h_x) k_feats = d_x;      // too wide for the parameter block: the kernel reads the mapped staging area
   }
   float *k_out = out_dev ? out : d_out;
   const unsigned int seq = ++st.seq ? st.seq : ++st.seq;      // never 0
   {
     StageScope sc(ctx, 1);
-    if (NF == 16) stream_launch<16>(ctx, xs, k_feats, k_f64, nf, k_center, k_out, use_floor, floor_at, seq, ranges, ysplit, tslots);
-    else stream_launch<32>(ctx, xs, k_feats, k_f64, nf, k_center, k_out, use_floor, floor_at, seq, ranges, ysplit, tslots);
+    stream_launch<16>(ctx, xs16, k_feats, k_f64, nf, k_center, k_out, use_floor, floor_at, seq, ranges, ysplit, tslots);
   }
   if (!wait) return true;                      // (probe: a train of launches, completion by event)
   // completion: the last CTA stores seq into mapped host memory after every result is visible

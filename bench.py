@@ -509,7 +509,7 @@ def sub_parity_mode(args, torch, eng, stream, pcm_d, pcm_p, uo, fo, n_utts=24):
 
 
 def sub_streaming(args, local, model2):
-    """Streaming regime: the decoder's per-frame feed -- a call of akugpu_gmm_logprobs on F <= 32 frames
+    """Streaming regime: the decoder's per-frame feed -- a call of akugpu_gmm_logprobs on F <= 16 frames
     sweeps the whole parameter image.  Latency per call through the C ABI with HOST buffers, the kernel's sweep rate, and
     the L2 / HBM read rates of that very buffer it is measured against."""
     import ctypes as C
@@ -527,7 +527,7 @@ def sub_streaming(args, local, model2):
         eng.model_load_diag(model["mix_offsets"], model["mix_gauss"], model["mix_weight"], model["means"], model["covs"])
         S = eng.num_states
         rec = {}
-        for F in (1, 8, 16, 32):
+        for F in (1, 4, 8, 16):
             x = np.ascontiguousarray(feats[100:100 + F])
             ob = np.empty((F, S), dtype=np.float32)
             px, po = C.c_void_p(x.ctypes.data), C.c_void_p(ob.ctypes.data)

@@ -267,7 +267,8 @@ double akugpu_model_expanded_form_q(akugpu_ctx *ctx);
  * with resident A', 4 = fp16x2 tensor-core streaming A', 5 = fp16x2 tensor-core for the well-conditioned states + FP32-pipe
  * kernel for the others. */
 int akugpu_scorer_in_use(akugpu_ctx *ctx);
-/* Streaming-regime scorer.  Calls of akugpu_gmm_score (precision F32) / akugpu_gmm_logprobs with at most 32 frames --
+/* Streaming-regime scorer.  Calls of akugpu_gmm_score (precision F32) / akugpu_gmm_logprobs with at most 16 frames (8 for models of more
+ * than 800 component tiles) --
  * the decoder's per-frame loop, decoder/decode-stream.cc:191-207 -- are served by ONE launch that spreads the component
  * tiles of the whole model over all SMs (gmm_stream_kernel); host features travel in the kernel's parameter block,
  * results and the completion flag are written straight into pinned, mapped host memory.  Diagonal pools served by the

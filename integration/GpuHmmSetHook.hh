@@ -1,7 +1,7 @@
 // integration/GpuHmmSetHook.hh -- lets the reference's own aku::HmmSet (a concrete class, aku/HmmSet.hh:94) score on the
 // GPU library without changing any caller: HmmSet::precompute_likelihoods(const FeatureVec&) asks this hook for the
 // likelihoods of all emission pdfs of the frame and only runs its CPU loop (aku/HmmSet.cc:485-501) when no GPU model is
-// attached.  Two edits in aku/HmmSet.cc:
+// attached.  Three edits in aku/HmmSet.cc:
 //
 //     void HmmSet::read_all(const std::string &base) {
 //       read_mc(base + ".mc"); read_ph(base + ".ph"); read_gk(base + ".gk");
@@ -11,6 +11,12 @@
 //       reset_cache();
 //       if (akugpu_hook::score(this, *f.get_vector(), m_pdf_likelihoods, m_valid_pdf_likelihoods)) return;   // +
 //       ...                                                               // the CPU loop, unchanged
+//     double HmmSet::pdf_likelihood(const int p, const FeatureVec &feature) {
+//       if (m_pdf_likelihoods[p] > 0) return m_pdf_likelihoods[p];
+//       if (akugpu_hook::score(this, *feature.get_vector(), m_pdf_likelihoods, m_valid_pdf_likelihoods))   // + lazy callers
+//         return m_pdf_likelihoods[p];                                    //   (Viterbi.cc:249,369, HmmNetBaumWelch.cc:1930):
+//       ...                                                               //   the first miss after reset_cache() scores the
+//                                                                         //   frame's every state, the rest are cache hits
 //
 // phone_probs, the aligner and every other caller of precompute_likelihoods / state_likelihood run unmodified.  When the
 // feature vector handed in is a frame of the utterance that integration/GpuFrontendModule.hh has just computed (the

@@ -275,7 +275,7 @@ def test_reference_side_plugin_compiles_and_serves_reference_modules(tmp_path):
                     reason="needs the reference's sources and oracle/_ref/libaku_ref.a")
 def test_reference_phone_probs_runs_unmodified_on_plugin_and_hook(tmp_path):
     """The reference's LITERAL phone_probs main, linked with scratch copies of aku/FeatureGenerator.cc (+ the one-line
-    registration of integration/GpuFrontendModule.hh) and aku/HmmSet.cc (+ the two hook lines of
+    registration of integration/GpuFrontendModule.hh) and aku/HmmSet.cc (+ the three hook lines of
     integration/GpuHmmSetHook.hh): with AKUGPU_HOOK=1 every frame's features and state likelihoods come from the C ABI
     (here its fake: closed forms), the reference's own loop normalises and quantises them, and the LNA file equals the
     oracle's encoding of those likelihoods; without the variable the same binary is the CPU tool."""
@@ -291,8 +291,11 @@ def test_reference_phone_probs_runs_unmodified_on_plugin_and_hook(tmp_path):
     hs = open(R + "/aku/HmmSet.cc").read()
     a = '  read_gk(base + ".gk");\n}\n'
     b = "  // Precompute base distribution likelihoods\n  m_pool.precompute_likelihoods(*f.get_vector());\n"
-    assert hs.count(a) == 1 and hs.count(b) == 1
+    c = "    return m_pdf_likelihoods[p];\n\n  m_pdf_likelihoods[p] = m_emission_pdfs[p]->compute_likelihood(*feature.get_vector());\n"
+    assert hs.count(a) == 1 and hs.count(b) == 1 and hs.count(c) == 1
     hs = hs.replace('#include "HmmSet.hh"\n', '#include "HmmSet.hh"\n#include "GpuHmmSetHook.hh"\n')
+    hs = hs.replace(c, "    return m_pdf_likelihoods[p];\n  if (akugpu_hook::score(this, *feature.get_vector(), m_pdf_likelihoods, m_valid_pdf_likelihoods))\n"
+                       "    return m_pdf_likelihoods[p];\n\n  m_pdf_likelihoods[p] = m_emission_pdfs[p]->compute_likelihood(*feature.get_vector());\n")
     hs = hs.replace(a, '  read_gk(base + ".gk");\n  akugpu_hook::attach(this, base);\n}\n')
     hs = hs.replace(b, "  if (akugpu_hook::score(this, *f.get_vector(), m_pdf_likelihoods, m_valid_pdf_likelihoods)) return;\n" + b)
     open(str(tmp_path / "FeatureGenerator_registered.cc"), "w").write(fg)

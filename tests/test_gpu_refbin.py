@@ -74,3 +74,50 @@ def test_reference_phone_probs_on_module_and_hook(ref_small, tmp_path):
     r = subprocess.run([os.path.join(REF, "ref_phone_probs_gpu"), "-b", base, "-c", plain, "-r", rec, "-o", str(out)],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert r.returncode == 0 and open(str(out / "a.lna"), "rb").read() == bytes(g["lna2"])
+
+
+def test_reference_aligner_on_the_hook(ref_small, tmp_path):
+    """The reference's Viterbi aligner (aku/align.cc -> Viterbi.cc:249,369: reset_cache() + state_likelihood(s, f) for the
+    ACTIVE states only) on the HmmSet hook: the first miss of a frame scores every state on the GPU, the frame's other
+    requests are cache hits.  Same segmentation as the CPU tool, with the reference's own features (one library call
+    per frame) and with the GPU module as the base module (the whole utterance scored in one call)."""
+    g = ref_small
+    base = str(tmp_path / "model")
+    formats.write_model(base, **g["model"])
+    S = len(g["model"]["mix_offsets"]) - 1
+    P = S // 3
+    with open(base + ".ph", "w") as f:          # three-state left-to-right phones over the fixture's 24 states
+        f.write("PHONE\n%d\n" % P)
+        for p in range(P):
+            f.write("%d 5 p%d\n-1 -2 %d %d %d\n0 1 2 1\n1 0\n2 2 2 0.8 3 0.2\n3 2 3 0.8 4 0.2\n4 2 4 0.8 1 0.2\n" % (p + 1, p, 3 * p, 3 * p + 1, 3 * p + 2))
+    wav = str(tmp_path / "a.wav")
+    formats.write_wav(wav, g["pcm"], 16000)
+    plain = str(tmp_path / "plain.feaconf")
+    open(plain, "w").write(g["cfg"])
+    gpucfg = gpu_config(tmp_path, g["cfg"])
+    phn = str(tmp_path / "a.phn")
+    open(phn, "w").write("\n".join("p%d" % p for p in [0, 3, 1, 5, 2, 7, 4, 6, 0, 2]) + "\n")
+
+    def align(exe, cfg, tag, hook):
+        out = str(tmp_path / (tag + ".phn"))
+        rec = str(tmp_path / (tag + ".recipe"))
+        open(rec, "w").write("audio=%s transcript=%s alignment=%s\n" % (wav, phn, out))
+        env = dict(os.environ, AKUGPU_HOOK="1" if hook else "")
+        r = subprocess.run([os.path.join(REF, exe), "-b", base, "-c", cfg, "-r", rec, "-i", "2"], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()
+        ll = [float(ln.split(":")[1]) for ln in r.stderr.decode().splitlines() if ln.startswith("File log likelihood")]
+        return open(out).read(), ll[0]
+
+    cpu, ll_cpu = align("ref_align", plain, "cpu", False)
+    assert len(cpu.splitlines()) == 30 and cpu.splitlines()[0].split()[2] == "p0.0"
+    hooked, ll_h = align("ref_align_gpu", plain, "hook", True)              # reference features, GPU likelihoods per frame
+    assert hooked == cpu and abs(ll_h - ll_cpu) <= 1e-6 * abs(ll_cpu)
+    full, ll_f = align("ref_align_gpu", gpucfg, "gpu", True)                # GPU features + whole utterance scored at once
+    assert abs(ll_f - ll_cpu) <= 1e-4 * abs(ll_cpu)
+    a = [ln.split() for ln in full.splitlines()]
+    b = [ln.split() for ln in cpu.splitlines()]
+    assert [x[2] for x in a] == [x[2] for x in b]
+    assert max(abs(int(x[0]) - int(y[0])) for x, y in zip(a, b)) <= 128      # boundaries within a frame (features differ by 1e-5)
+    off, ll_o = align("ref_align_gpu", plain, "off", False)                 # hook off: the binary is the CPU tool
+    assert off == cpu and ll_o == ll_cpu

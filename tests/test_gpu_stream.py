@@ -30,7 +30,7 @@ def both_paths(engine, fn):
     return a, b, n_stream, n_batch
 
 
-@pytest.mark.parametrize("F", [1, 2, 7, 16, 17, 32])
+@pytest.mark.parametrize("F", [1, 2, 7, 9, 16])
 def test_streaming_scorer_equals_batch_path_small_model(engine, ref_small, F):
     g = ref_small
     load_model(engine, g["model"])
@@ -124,8 +124,8 @@ def test_streaming_scorer_full_size_models(engine, feats20s, S, K, seed):
     assert np.abs(rows.astype(np.float64) - batch).max() <= 4e-6
     blk = engine.gmm_logprobs(x[:16], precision=F32, tiny=1e-30)
     assert np.abs(blk.astype(np.float64) - batch[:16]).max() <= 4e-6
-    blk = engine.gmm_logprobs(x[:26], precision=F32, tiny=1e-30)             # N = 32 variant, ragged
-    assert np.abs(blk.astype(np.float64) - batch).max() <= 4e-6
+    blk = engine.gmm_logprobs(x[:7], precision=F32, tiny=1e-30)              # ragged
+    assert np.abs(blk.astype(np.float64) - batch[:7]).max() <= 4e-6
     want = np.log(np.maximum(oracle_np.state_likelihoods(model, x[:2].astype(np.float64)), 1e-30))
     assert np.abs(rows[:2] - want).max() <= 4e-5
     p = engine.stream_probe()
@@ -136,8 +136,8 @@ def test_streaming_scorer_full_size_models(engine, feats20s, S, K, seed):
           % (S, K, p["sm_mhz_isolated"], 1e6 * p["kernel_s_train"], p["kernel_GBps_train"], p["sm_mhz_train"]))
     import ctypes as C
     lib, h = engine._lib, engine._h
-    for F in (1, 8, 16, 32):
-        xb = np.ascontiguousarray(x[:F] if F <= len(x) else np.vstack([x, x])[:F])
+    for F in (1, 4, 8, 16):
+        xb = np.ascontiguousarray(x[:F])
         ob = np.empty((F, S), dtype=np.float32)
         px, po = C.c_void_p(xb.ctypes.data), C.c_void_p(ob.ctypes.data)
         call = lambda: lib.akugpu_gmm_logprobs(h, px, 0, F, 0, C.c_double(1e-30), po)
@@ -148,5 +148,16 @@ def test_streaming_scorer_full_size_models(engine, feats20s, S, K, seed):
         for _ in range(n):
             call()
         us = 1e6 * (time.perf_counter() - t0) / n
-        print("streaming scorer %d x %d, F = %d: %.1f us per akugpu_gmm_logprobs call (host buffers, ctypes loop)" % (S, K, F, us))
+        engine.set_streaming(False)
+        try:
+            for _ in range(20):
+                call()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                call()
+            us_general = 1e6 * (time.perf_counter() - t0) / 200
+        finally:
+            engine.set_streaming(True)
+        print("streaming scorer %d x %d, F = %d: %.1f us per akugpu_gmm_logprobs call (host buffers, ctypes loop); general path %.1f us"
+              % (S, K, F, us, us_general))
         assert us < 1000.0
