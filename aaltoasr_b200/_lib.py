@@ -56,6 +56,7 @@ SYMBOLS = {
     "akugpu_model_set_clustering_min_evals": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "akugpu_model_use_clustering": (C.c_int, [C.c_void_p, C.c_int]),
     "akugpu_model_set_cmllr": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "akugpu_model_set_cmllr_units": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_void_p]),
     "akugpu_model_num_states": (C.c_int, [C.c_void_p]),
     "akugpu_model_dim": (C.c_int, [C.c_void_p]),
     "akugpu_model_num_gaussians": (C.c_int, [C.c_void_p]),

@@ -4,6 +4,7 @@
 #include "ctx.hpp"
 #include "kernels.hpp"
 #include <string.h>
+#include <algorithm>
 #include <fstream>
 #include <sstream>
 #include <mutex>
@@ -106,6 +107,7 @@ static int tc_mode(akugpu_ctx *ctx, int precision)
 {
   if (precision != AKUGPU_F32) return 0;
   if (clustering_on(ctx)) return 0;      // the clustering approximation is evaluated in double (reference semantics)
+  if (ctx->hm.n_tr > 0) return 0;        // regression-class CMLLR: one feature row per class, served by the double path
   if (ctx->ptc16.ready && !ctx->tc16_suspended) return 2;
   return ctx->ptc.ready ? 1 : 0;
 }
@@ -129,7 +131,7 @@ static void score_to_lna_impl(akugpu_ctx *ctx, const void *d_feats, int feats_f6
   const int use_tc = tc_mode(ctx, precision);
   *mode_out = use_tc;
   if (ctx->hm.n_full > 0 && !use_tc) precision = AKUGPU_F64;   // full-covariance pools are scored in double
-  if (clustering_on(ctx)) precision = AKUGPU_F64;
+  if (clustering_on(ctx) || ctx->hm.n_tr > 0) precision = AKUGPU_F64;
   const int64_t chunk = pick_chunk(ctx, F, use_tc);
   const size_t rec = (size_t)S * lnabytes;
   const bool out_dev = out && is_device_ptr(out);
@@ -258,6 +260,18 @@ static const void *adapt_feats(akugpu_ctx *ctx, const void *d_feats, int feats_f
 {
   if (!ctx->hm.cmllr_on || F <= 0) return d_feats;
   const int D = ctx->hm.D;
+  if (ctx->hm.n_tr > 0) {
+    // regression classes: one adapted copy of the rows per transform next to the unadapted rows; the double scorer
+    // picks a Gaussian's row by its class (gmm_diag_f64)
+    const size_t esz = feats_f64 ? 8 : 4;
+    ctx->d_adapt.reserve((size_t)ctx->hm.n_tr * F * D * esz);
+    ctx->adapt_stride = F * D;
+    StageScope sc(ctx, 1);
+    for (int t = 0; t < ctx->hm.n_tr; t++)
+      launch_affine_rows(ctx, d_feats, feats_f64, F, D, ctx->d_cmllr.as<double>() + (size_t)t * (D * D + D),
+                         (char *)ctx->d_adapt.p + (size_t)t * F * D * esz);
+    return d_feats;
+  }
   ctx->d_adapt.reserve((size_t)F * D * (feats_f64 ? 8 : 4));
   StageScope sc(ctx, 1);
   launch_affine_rows(ctx, d_feats, feats_f64, F, D, ctx->d_cmllr.as<double>(), ctx->d_adapt.p);
@@ -587,6 +601,8 @@ int akugpu_model_load_diag(akugpu_ctx *ctx, int n_states, int n_gauss, int dim, 
   hm.full_index.clear(); hm.full_cov.clear(); hm.n_full = 0;
   hm.clear_clustering();
   hm.clear_cmllr();
+  hm.ph_label.clear();
+  hm.ph_states.clear();
   model_pack(ctx);
   API_END
 }
@@ -674,6 +690,7 @@ int akugpu_model_set_cmllr(akugpu_ctx *ctx, const double *W)
   }
   if (hm.mix_w_base.empty()) hm.mix_w_base = hm.mix_w;
   ctx->have_model = false;
+  hm.n_tr = 0; hm.g_tr.clear(); hm.tr_Ab.clear();        // a global transform replaces regression-class ones
   if (W) {
     hm.cmllr_W.assign(W, W + (size_t)D * (D + 1));
     std::vector<double> Ab((size_t)D * D + D);
@@ -691,6 +708,113 @@ int akugpu_model_set_cmllr(akugpu_ctx *ctx, const double *W)
     hm.clear_cmllr();
   }
   model_pack(ctx);          // every scorer image carries the weights
+  API_END
+}
+
+// ---- model-level CMLLR with regression classes (unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN) ----
+static std::string center_phone(const std::string &label)      // Hmm::get_center_phone, aku/HmmSet.cc:22-40
+{
+  const size_t p1 = label.find_last_of('-'), p2 = label.find_first_of('+');
+  std::string t;
+  if (p1 != std::string::npos && p2 != std::string::npos) { if (p2 > p1 + 1) t = label.substr(p1 + 1, p2 - p1 - 1); }
+  else if (p1 != std::string::npos) t = label.substr(p1 + 1);
+  else if (p2 != std::string::npos) t = label.substr(0, p2);
+  else t = label;
+  if (t.empty()) throw Error(AKUGPU_E_MODEL, "Invalid phone label " + label);
+  return t;
+}
+
+int akugpu_model_set_cmllr_units(akugpu_ctx *ctx, const char *unitmode, int n_transforms, const char *const *units, const double *W)
+{
+  API_BEGIN
+  require_model(ctx);
+  if (!unitmode) throw Error(AKUGPU_E_ARG, "unitmode is NULL");
+  const std::string um(unitmode);
+  if (um == "UNIT_NO") {
+    if (n_transforms > 1) throw Error(AKUGPU_E_ARG, "ERROR: speaker can only contain one transform when UNIT_NO (global transform) is set");
+    return akugpu_model_set_cmllr(ctx, n_transforms == 1 ? W : NULL);
+  }
+  if (um != "UNIT_PHONE" && um != "UNIT_MIX" && um != "UNIT_GAUSSIAN") throw Error(AKUGPU_E_ARG, "unknown unitmode " + um);
+  if (n_transforms == 0) return akugpu_model_set_cmllr(ctx, NULL);
+  if (n_transforms < 0 || !units || !W) throw Error(AKUGPU_E_ARG, "bad n_transforms / NULL arrays");
+  HostModel &hm = ctx->hm;
+  if (hm.n_full > 0) throw Error(AKUGPU_E_MODEL, "CMLLR regression classes are provided for diagonal pools only");
+  if (clustering_on(ctx) || hm.n_clusters > 0)
+    throw Error(AKUGPU_E_STATE, "CMLLR regression classes together with Gaussian clustering are not provided");
+  const int D = hm.D, G = hm.G;
+  if (um == "UNIT_PHONE" && hm.ph_label.empty())
+    throw Error(AKUGPU_E_STATE, "UNIT_PHONE transforms need the phone table of a model read from files (akugpu_model_read)");
+  // ConstrainedMllr::load_transform (aku/ModelModules.cc:172-236) visits the transforms in the order of their std::map
+  // key -- the vector of unit strings -- and wraps every Gaussian of a transform anew: the last claimant wins
+  std::vector<std::vector<std::string>> keys(n_transforms);
+  for (int t = 0; t < n_transforms; t++) {
+    if (!units[t]) throw Error(AKUGPU_E_ARG, "units[t] is NULL");
+    std::istringstream is(units[t]);
+    std::string u;
+    while (is >> u) keys[t].push_back(u);
+    if (keys[t].empty()) throw Error(AKUGPU_E_ARG, "a regression-class transform needs at least one unit");
+    for (size_t i = 0; i < (size_t)D * (D + 1); i++)
+      if (!std::isfinite(W[(size_t)t * D * (D + 1) + i])) throw Error(AKUGPU_E_ARG, "CMLLR: W has a non-finite element");
+  }
+  std::vector<int> order(n_transforms);
+  for (int t = 0; t < n_transforms; t++) order[t] = t;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+  for (int t = 1; t < n_transforms; t++)
+    if (keys[order[t]] == keys[order[t - 1]]) throw Error(AKUGPU_E_ARG, "two transforms list the same units");   // one map entry in the reference
+  std::vector<int32_t> g_tr(G, -1);
+  std::vector<double> Ab((size_t)n_transforms * (D * D + D)), factor(n_transforms, 1.0);
+  auto mixture_gaussians = [&](long m, std::vector<int> &out) {
+    if (m < 0 || m >= hm.S) throw Error(AKUGPU_E_ARG, fmt("CMLLR: mixture %ld out of range", m));
+    for (int k = hm.mix_off[m]; k < hm.mix_off[m + 1]; k++) out.push_back(hm.mix_gauss[k]);
+  };
+  for (int r = 0; r < n_transforms; r++) {
+    const int t = order[r];
+    const double *Wt = W + (size_t)t * D * (D + 1);
+    double f = 1.0;
+    for (int i = 0; i < D; i++) {
+      for (int j = 0; j < D; j++) Ab[(size_t)r * (D * D + D) + (size_t)i * D + j] = Wt[(size_t)i * (D + 1) + 1 + j];
+      Ab[(size_t)r * (D * D + D) + (size_t)D * D + i] = Wt[(size_t)i * (D + 1)];
+      f *= Wt[(size_t)i * (D + 1) + 1 + i];          // the reference's "determinant": see akugpu_model_set_cmllr
+    }
+    factor[r] = fabs(f);
+    if (!(factor[r] > 0) || std::isinf(factor[r])) throw Error(AKUGPU_E_ARG, "CMLLR: the diagonal of A must be finite and non-zero");
+    std::vector<int> gs;
+    if (um == "UNIT_PHONE") {          // RegClassTree::UnitPhoneme::get_gaussians, aku/RegClassTree.cc:302-322
+      for (size_t h = 0; h < hm.ph_label.size(); h++) {
+        if (std::find(keys[t].begin(), keys[t].end(), center_phone(hm.ph_label[h])) == keys[t].end()) continue;
+        for (int32_t st : hm.ph_states[h]) mixture_gaussians(st, gs);
+      }
+    } else if (um == "UNIT_MIX") {     // UnitMixture::get_gaussians :368-385: units that are not numbers are skipped
+      for (const std::string &u : keys[t]) {
+        char *end = nullptr;
+        const long m = strtol(u.c_str(), &end, 10);
+        if (end == u.c_str() || *end) continue;
+        mixture_gaussians(m, gs);
+      }
+    } else {                           // UnitGaussian::get_gaussians :444-454
+      for (const std::string &u : keys[t]) {
+        const long g = strtol(u.c_str(), nullptr, 10);
+        if (g < 0 || g >= G) throw Error(AKUGPU_E_ARG, fmt("CMLLR: Gaussian %ld out of range", g));
+        gs.push_back((int)g);
+      }
+    }
+    for (int g : gs) g_tr[g] = r;
+  }
+  if (hm.mix_w_base.empty()) hm.mix_w_base = hm.mix_w;
+  ctx->have_model = false;
+  hm.cmllr_W.clear();
+  hm.n_tr = n_transforms;
+  hm.g_tr = g_tr;
+  hm.tr_Ab = Ab;
+  ctx->d_cmllr.reserve(Ab.size() * sizeof(double));
+  AKU_CUDA(cudaMemcpyAsync(ctx->d_cmllr.p, Ab.data(), Ab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  AKU_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (size_t k = 0; k < hm.mix_w.size(); k++) {
+    const int tr = g_tr[hm.mix_gauss[k]];
+    hm.mix_w[k] = tr >= 0 ? hm.mix_w_base[k] * factor[tr] : hm.mix_w_base[k];
+  }
+  hm.cmllr_on = true;
+  model_pack(ctx);
   API_END
 }
 
@@ -725,7 +849,7 @@ static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, in
   bool redo = false;
   do {   // a second pass only when the fp16x2 scorer met a feature outside its range (see tc16_needs_redo)
   const int use_tc = tc_mode(ctx, precision);
-  const bool dbl = precision == AKUGPU_F64 || (ctx->hm.n_full > 0 && !use_tc) || clustering_on(ctx);   // scored in double
+  const bool dbl = precision == AKUGPU_F64 || (ctx->hm.n_full > 0 && !use_tc) || clustering_on(ctx) || ctx->hm.n_tr > 0;   // scored in double
   const bool want_f32 = esz == 4;
   const int64_t chunk = pick_chunk(ctx, n_frames, use_tc);
   ctx->d_sll.reserve((size_t)S * chunk * (dbl ? 8 : 4));

@@ -103,7 +103,16 @@ struct HostModel {
   bool cmllr_on = false;
   std::vector<double> cmllr_W;      // [D x (D+1)] row-major as given: column 0 = b, columns 1..D = A
   std::vector<double> mix_w_base;   // the normalised weights while cmllr_on
-  void clear_cmllr() { cmllr_on = false; cmllr_W.clear(); mix_w_base.clear(); }
+  // Regression-class transforms (unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN, aku/ModelModules.cc:62-95,172-236):
+  // Gaussian g with g_tr[g] = t >= 0 is evaluated at A_t f + b_t and multiplied by transform t's factor.  cmllr_on is set
+  // too; the throughput scorers do not serve such a model (one feature row per class), the double path does.
+  int n_tr = 0;
+  std::vector<int32_t> g_tr;        // [G]
+  std::vector<double> tr_Ab;        // [n_tr][D*D + D]: A row-major, then b
+  void clear_cmllr() { cmllr_on = false; cmllr_W.clear(); mix_w_base.clear(); n_tr = 0; g_tr.clear(); tr_Ab.clear(); }
+  // phones of the .ph file (label, states) -- what UNIT_PHONE transforms are resolved with; empty for direct loads
+  std::vector<std::string> ph_label;
+  std::vector<std::vector<int32_t>> ph_states;
 };
 
 // fp32 scorer image: tiles of 8 slots x 16 components, see gmm_kernels.cu.
@@ -132,6 +141,7 @@ struct PackedF64 {
   DevBuf diag_gauss;           // int32  [G - n_full]  pool indices of the diagonal Gaussians
   // Gaussian clustering: centres as a pool of C one-component "states", cluster of each Gaussian, member counts
   DevBuf c_mean, c_prec, c_cst, c_mix_off, c_mix_gauss, c_mix_w, g2c, c_size;
+  DevBuf g_tr;                 // int32 [G] transform of each Gaussian (regression-class CMLLR), -1 = none
 };
 
 // tensor-core scorer image (gmm_tc.cu): bf16x3-split expanded parameters, slot-ordered rows
@@ -269,8 +279,10 @@ struct akugpu_ctx {
 
   // scratch
   akugpu::DevBuf d_feats, d_sll, d_lna[2], d_pcm, d_tmp, d_chk, d_norm, d_clik, d_csel;
+  int64_t adapt_stride = 0;            // elements between the adapted feature arrays of two transforms (F * D of the current call)
   akugpu::DevBuf d_sll2, d_norm2;      // second score / normaliser buffers of the overlapped pipeline
-  akugpu::DevBuf d_cmllr, d_adapt;     // double [D*D + D] (A row-major, then b); adapted features of the current call
+  akugpu::DevBuf d_cmllr, d_adapt;     // double [n][D*D + D] (A row-major, then b) per transform; adapted features of the current call
+                                       // (global transform: [F][D]; regression classes: [n_tr][F][D])
   akugpu::DevBuf d_fe[8];
   std::vector<std::shared_ptr<akugpu::DevBuf>> fe_bufs;   // per-module output matrices (grow-only)
   akugpu::PinnedBuf h_in[2], h_out[2];

@@ -279,7 +279,8 @@ gmm_diag_f64(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
              const double *__restrict__ mean, const double *__restrict__ prec, const double *__restrict__ cst,
              const int *__restrict__ mix_off, const int *__restrict__ mix_gauss, const double *__restrict__ mix_w,
              int S, double *__restrict__ lin, int64_t ldF, double floor_at, const int *__restrict__ g2c,
-             const unsigned char *__restrict__ csel, const double *__restrict__ clik)
+             const unsigned char *__restrict__ csel, const double *__restrict__ clik,
+             const int *__restrict__ g_tr = nullptr, const void *__restrict__ tfeats = nullptr, int64_t t_stride = 0)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *xs = reinterpret_cast<double *>(smem_raw);   // [D][128]
@@ -303,12 +304,30 @@ gmm_diag_f64(const void *__restrict__ feats, int feats_f64, int64_t f_begin, int
       const double *mu = mean + (size_t)g * D;
       const double *pr = prec + (size_t)g * D;
       double ll[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int d = 0; d < D; ++d) {
-        const double m = mu[d], p = pr[d];
+      // regression-class CMLLR (AdaptedGaussian, aku/ModelModules.hh:161-171): this Gaussian sees its class's A f + b
+      const int tr = g_tr ? g_tr[g] : -1;
+      if (tr < 0) {
+        for (int d = 0; d < D; ++d) {
+          const double m = mu[d], p = pr[d];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          double dd = __dsub_rn(xs[d * 128 + lane + 32 * i], m);
-          ll[i] = __dadd_rn(ll[i], __dmul_rn(__dmul_rn(dd, dd), p));
+          for (int i = 0; i < 4; ++i) {
+            double dd = __dsub_rn(xs[d * 128 + lane + 32 * i], m);
+            ll[i] = __dadd_rn(ll[i], __dmul_rn(__dmul_rn(dd, dd), p));
+          }
+        }
+      } else {
+        for (int d = 0; d < D; ++d) {
+          const double m = mu[d], p = pr[d];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int64_t gf = f0 + lane + 32 * i;
+            double xv = 0.0;
+            if (gf < f_end)
+              xv = feats_f64 ? reinterpret_cast<const double *>(tfeats)[(int64_t)tr * t_stride + gf * D + d]
+                             : (double)reinterpret_cast<const float *>(tfeats)[(int64_t)tr * t_stride + gf * D + d];
+            double dd = __dsub_rn(xv, m);
+            ll[i] = __dadd_rn(ll[i], __dmul_rn(__dmul_rn(dd, dd), p));
+          }
         }
       }
       const double c = cst[g];
@@ -523,7 +542,8 @@ void launch_gmm_f64(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t f
   dim3 grid(ftiles, ysplit);
   gmm_diag_f64<<<grid, 256, smem, ctx->stream>>>(feats, feats_f64, f_begin, f_end, hm.D, p.mean.as<double>(),
                                                  p.prec.as<double>(), p.cst.as<double>(), p.mix_off.as<int>(),
-                                                 p.mix_gauss.as<int>(), p.mix_w.as<double>(), hm.S, lin, ldF, 1e-50, g2c, csel, clik);
+                                                 p.mix_gauss.as<int>(), p.mix_w.as<double>(), hm.S, lin, ldF, 1e-50, g2c, csel, clik,
+                                                 hm.n_tr > 0 ? p.g_tr.as<int>() : nullptr, ctx->d_adapt.p, ctx->adapt_stride);
   AKU_CUDA(cudaGetLastError());
   ctx->launches++;
 }

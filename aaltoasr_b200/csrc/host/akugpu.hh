@@ -321,8 +321,8 @@ private:
 //     }
 // set_speaker() / set_utterance() push the stored parameters through FeatureModule::set_parameters
 // (akugpu_frontend_set_parameters).  A speaker's `model cmllr` entry (model-level constrained MLLR, aku/ModelModules.hh)
-// is applied through akugpu_model_set_cmllr when it is the global transform (unitmode UNIT_NO); regression-class
-// transforms are refused.  As in the reference, a speaker without the entry keeps the previous speaker's transform.
+// is applied through akugpu_model_set_cmllr when it is the global transform (unitmode UNIT_NO) and through
+// akugpu_model_set_cmllr_units for the regression-class modes (UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN).  As in the reference, a speaker without the entry keeps the previous speaker's transform.
 class SpeakerConfig {
 public:
   explicit SpeakerConfig(Engine &e) : m_e(e), m_default_speaker_set(false), m_default_utterance_set(false) {}
@@ -425,8 +425,8 @@ private:
       else check(m_e.ctx(), akugpu_frontend_set_parameters(m_e.ctx(), it->first.c_str(), it->second.c_str()));
     }
   }
-  // ConstrainedMllr::set_parameters (aku/ModelModules.cc:62-95) for the global transform (unitmode UNIT_NO): one `w1` of
-  // dim*(dim+1) numbers, row-major [dim x (dim+1)], column 0 = bias; no `w` entry = no transform.
+  // ConstrainedMllr::set_parameters (aku/ModelModules.cc:62-95): `unitmode` and entries `w<i> [units...] <dim*(dim+1)
+  // numbers>`, row-major [dim x (dim+1)], column 0 = bias; no `w` entry = no transform.
   void apply_cmllr(const std::string &text) {
     const int dim = akugpu_model_dim(m_e.ctx());
     if (dim <= 0) throw std::string("cmllr: a model must be loaded before the speaker configuration is applied");
@@ -439,18 +439,16 @@ private:
       if (!f.empty()) params[f[0]] = std::vector<std::string>(f.begin() + 1, f.end());
       pos = e + 1;
     }
-    if (params.count("unitmode") && !params["unitmode"].empty()) {
-      const std::string &um = params["unitmode"][0];
-      if (um == "UNIT_GAUSSIAN" || um == "UNIT_MIX" || um == "UNIT_PHONE")
-        throw std::string("cmllr: regression-class transforms (unitmode ") + um + ") are not provided, only the global transform (UNIT_NO)";
-    }
+    std::string um = "UNIT_NO";
+    if (params.count("unitmode") && !params["unitmode"].empty()) um = params["unitmode"][0];
     const size_t n = (size_t)dim * (dim + 1);
+    const size_t need = um == "UNIT_NO" ? n : n + 1;         // regression-class entries list their units in front of the matrix
     std::map<std::vector<std::string>, std::vector<double> > found;
     for (int i = 1;; i++) {
       std::map<std::string, std::vector<std::string> >::const_iterator it = params.find(fmt("w%d", i));
       if (it == params.end()) break;
       const std::vector<std::string> &parts = it->second;
-      if (parts.size() < n) throw std::string("ERROR: not enough elements for matrix ") + fmt("w%d", i);
+      if (parts.size() < need) throw std::string("ERROR: not enough elements for matrix ") + fmt("w%d", i);
       std::vector<double> w(n);
       for (size_t k = 0; k < n; k++) {
         const std::string &t = parts[parts.size() - n + k];
@@ -460,8 +458,25 @@ private:
       }
       found[std::vector<std::string>(parts.begin(), parts.end() - n)] = w;
     }
-    if (found.size() > 1) throw std::string("ERROR: speaker can only contain one transform when UNIT_NO (global transform) is set");
-    check(m_e.ctx(), akugpu_model_set_cmllr(m_e.ctx(), found.empty() ? NULL : found.begin()->second.data()));
+    if (um == "UNIT_NO") {
+      if (found.size() > 1) throw std::string("ERROR: speaker can only contain one transform when UNIT_NO (global transform) is set");
+      check(m_e.ctx(), akugpu_model_set_cmllr(m_e.ctx(), found.empty() ? NULL : found.begin()->second.data()));
+      return;
+    }
+    // UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN: the library resolves the units to Gaussians (it has the model's phones and
+    // mixtures) and applies the transforms in the reference's std::map order
+    std::vector<std::string> units;
+    std::vector<const char *> unit_ptrs;
+    std::vector<double> W;
+    for (std::map<std::vector<std::string>, std::vector<double> >::const_iterator it = found.begin(); it != found.end(); ++it) {
+      std::string u;
+      for (size_t k = 0; k < it->first.size(); k++) u += (k ? " " : "") + it->first[k];
+      units.push_back(u);
+      W.insert(W.end(), it->second.begin(), it->second.end());
+    }
+    for (size_t k = 0; k < units.size(); k++) unit_ptrs.push_back(units[k].c_str());
+    check(m_e.ctx(), akugpu_model_set_cmllr_units(m_e.ctx(), um.c_str(), (int)units.size(), unit_ptrs.empty() ? NULL : unit_ptrs.data(),
+                                                  W.empty() ? NULL : W.data()));
   }
   static std::string clean(const std::string &s) {
     size_t b = s.find_first_not_of(" \t\r\n"), e = s.find_last_not_of(" \t\r\n");

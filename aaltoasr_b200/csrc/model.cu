@@ -158,14 +158,18 @@ void model_read_files(const std::string &gk_path, const std::string &mc_path, co
     Tokens t(ph_path);
     if (t.word() != "PHONE") throw Error(AKUGPU_E_MODEL, ph_path + ": first token is not PHONE");
     long phones = t.integer();
+    hm.ph_label.clear();
+    hm.ph_states.clear();
     for (long h = 0; h < phones; h++) {
       t.integer();                 // index
       long states = t.integer() - 2;
-      t.word();                    // label
+      hm.ph_label.push_back(t.word());     // label (UNIT_PHONE transforms of a speaker file are resolved with it)
+      hm.ph_states.push_back(std::vector<int32_t>());
       t.integer(); t.integer();    // -1 -2
       for (long s = 0; s < states; s++) {
         long pdf = t.integer();
         if (pdf + 1 > n_states) n_states = (int)pdf + 1;
+        hm.ph_states.back().push_back((int32_t)pdf);
       }
       for (long s = -2; s < states; s++) {
         t.integer();               // source
@@ -352,6 +356,7 @@ void model_pack(akugpu_ctx *ctx)
     upload(p.mix_off, hm.mix_off, ctx->stream);
     upload(p.mix_gauss, hm.mix_gauss, ctx->stream);
     upload(p.mix_w, hm.mix_w, ctx->stream);
+    if (hm.n_tr > 0) upload(p.g_tr, hm.g_tr, ctx->stream);
     // full-covariance Gaussians: exponential parameters (recompute_exponential_parameters, :1530-1547)
     p.n_full = hm.n_full;
     p.L = D * (D + 3) / 2;

@@ -274,6 +274,17 @@ class AkuGpu:
             raise ValueError("W must be [%d x %d]" % (D, D + 1))
         self._ck(self._lib.akugpu_model_set_cmllr(self._h, _ptr(W)))
 
+    def model_set_cmllr_units(self, unitmode, transforms):
+        """Regression-class model-level CMLLR: transforms = [(units: list of str, W [dim x (dim+1)]), ...]
+        (unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN of aku/ModelModules.cc; [] removes them)."""
+        n = len(transforms)
+        D = self.model_dim
+        arr = (C.c_char_p * max(1, n))(*[(" ".join(u)).encode() for u, _ in transforms])
+        W = np.ascontiguousarray(np.stack([np.asarray(w, dtype=np.float64) for _, w in transforms]) if n else np.zeros((0, D, D + 1)))
+        if n and W.shape != (n, D, D + 1):
+            raise ValueError("every W must be [%d x %d]" % (D, D + 1))
+        self._ck(self._lib.akugpu_model_set_cmllr_units(self._h, unitmode.encode(), n, arr, _ptr(W) if n else None))
+
     @property
     def num_states(self):
         return self._lib.akugpu_model_num_states(self._h)

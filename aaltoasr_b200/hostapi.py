@@ -203,8 +203,17 @@ def parse_speaker_file(text):
 
 
 def parse_cmllr_parameters(text, dim):
-    """ConstrainedMllr::set_parameters (aku/ModelModules.cc:62-95) for the global transform: `unitmode UNIT_NO` and one
-    `w1` of dim*(dim+1) numbers, row-major [dim x (dim+1)], column 0 = bias.  Returns W or None (no transform given)."""
+    """The global transform of a `model cmllr` entry (unitmode UNIT_NO): W [dim x (dim+1)] or None (no `w` entry)."""
+    um, trs = parse_cmllr_transforms(text, dim)
+    if um != "UNIT_NO":
+        raise AkuGpuError(-2, "cmllr: unitmode %s holds regression-class transforms: parse_cmllr_transforms" % um)
+    return trs[0][1] if trs else None
+
+
+def parse_cmllr_transforms(text, dim):
+    """ConstrainedMllr::set_parameters (aku/ModelModules.cc:62-95): `unitmode UNIT_NO | UNIT_PHONE | UNIT_MIX | UNIT_GAUSSIAN`
+    and entries `w<i> [units...] <dim*(dim+1) numbers>` (row-major [dim x (dim+1)], column 0 = bias; regression-class
+    modes need at least one unit in front of the matrix).  Returns (unitmode, [(units, W), ...]) in the order w1, w2, ..."""
     params = {}
     for ln in text.splitlines():
         f = ln.split()
@@ -212,15 +221,13 @@ def parse_cmllr_parameters(text, dim):
             params[f[0]] = f[1:]
     um = params.get("unitmode", ["UNIT_NO"])
     um = um[0] if um else "UNIT_NO"
-    if um in ("UNIT_GAUSSIAN", "UNIT_MIX", "UNIT_PHONE"):
-        raise AkuGpuError(-2, "cmllr: regression-class transforms (unitmode %s) are not provided, only the global "
-                          "transform (UNIT_NO)" % um)
     n = dim * (dim + 1)
+    need = n if um == "UNIT_NO" else n + 1
     found = {}
     i = 1
     while "w%d" % i in params:
         parts = params["w%d" % i]
-        if len(parts) < n:
+        if len(parts) < need:
             raise AkuGpuError(-2, "ERROR: not enough elements for matrix w%d" % i)
         vals = []
         for t in parts[len(parts) - n:]:
@@ -228,11 +235,11 @@ def parse_cmllr_parameters(text, dim):
                 vals.append(float(np.float32(float(t))))      # str::str2float returns through a float (aku/str.cc:261-282)
             except ValueError:
                 raise AkuGpuError(-2, "invalid value: " + t)
-        found[tuple(parts[:len(parts) - n])] = np.array(vals, dtype=np.float64).reshape(dim, dim + 1)
+        found[tuple(parts[:len(parts) - n])] = np.array(vals, dtype=np.float64).reshape(dim, dim + 1)     # same units: one map entry
         i += 1
-    if len(found) > 1:
+    if um == "UNIT_NO" and len(found) > 1:
         raise AkuGpuError(-2, "ERROR: speaker can only contain one transform when UNIT_NO (global transform) is set")
-    return next(iter(found.values())) if found else None
+    return um, [(list(k), w) for k, w in found.items()]
 
 
 class SpeakerConfig:
@@ -264,7 +271,11 @@ class SpeakerConfig:
             mods = table["default"]
         for name in sorted(mods):
             if name == "model cmllr":     # model namespace: ModelTransformer (aku/SpeakerConfig.cc:248-284)
-                self.engine.model_set_cmllr(parse_cmllr_parameters(mods[name], self.engine.model_dim))
+                um, trs = parse_cmllr_transforms(mods[name], self.engine.model_dim)
+                if um == "UNIT_NO":
+                    self.engine.model_set_cmllr(trs[0][1] if trs else None)
+                else:                     # regression classes: phones / mixtures / Gaussians listed in front of each matrix
+                    self.engine.model_set_cmllr_units(um, trs)
             else:
                 self.engine.frontend_set_parameters(name, mods[name])
 

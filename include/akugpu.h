@@ -162,8 +162,18 @@ int akugpu_model_use_clustering(akugpu_ctx *ctx, int on);
  * A f + b and its likelihood multiplied by the reference's factor |prod_i A(i,i)| (AdaptedGaussian, aku/ModelModules.hh:
  * 161-171; its "determinant" is the product of A's own diagonal, aku/LinearAlgebra.cc:74-86 -- reproduced as it is).
  * W = NULL removes the transform (ModelTransformer::reset_transforms); loading a model clears it.  Regression-class
- * transforms (unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN, aku/RegClassTree.cc) are not provided. */
+ * transforms (unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN): akugpu_model_set_cmllr_units. */
 int akugpu_model_set_cmllr(akugpu_ctx *ctx, const double *W);
+/* The same module with regression classes: `unitmode UNIT_PHONE | UNIT_MIX | UNIT_GAUSSIAN` and entries `w<i> <units...>
+ * <D x (D+1) numbers>` (ConstrainedMllr::set_parameters / load_transform, aku/ModelModules.cc:62-95,172-236).  units[t] =
+ * the unit strings of transform t separated by blanks: centre-phone labels (Hmm::get_center_phone, aku/HmmSet.cc:22-40;
+ * needs a model read from files), mixture indices, or Gaussian indices (RegClassTree::Unit*::get_gaussians,
+ * aku/RegClassTree.cc:302-322,368-385,444-454); W = [n_transforms x D x (D+1)].  A Gaussian claimed by several
+ * transforms takes the last one in the order of the reference's std::map (unit lists compared lexicographically); a
+ * Gaussian no transform claims is left alone.  unitmode "UNIT_NO" = akugpu_model_set_cmllr; n_transforms = 0 removes the
+ * transforms.  While regression-class transforms are loaded every request is served by the double path (each class has its
+ * own feature row; diagonal pools, no Gaussian clustering). */
+int akugpu_model_set_cmllr_units(akugpu_ctx *ctx, const char *unitmode, int n_transforms, const char *const *units, const double *W);
 int akugpu_model_num_states(akugpu_ctx *ctx);   /* HmmSet::num_states()  */
 int akugpu_model_dim(akugpu_ctx *ctx);          /* HmmSet::dim()         */
 int akugpu_model_num_gaussians(akugpu_ctx *ctx);

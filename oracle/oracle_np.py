@@ -717,7 +717,65 @@ def cmllr_adapt(W, feats):
     return acc + b[None, :], abs(det)
 
 
-def state_likelihoods(model, feats, block=256, clustering=None, cmllr=None):
+def center_phone(label):
+    """Hmm::get_center_phone (aku/HmmSet.cc:22-40): the b of a-b+c, a-b, b+c or b."""
+    p1, p2 = label.rfind("-"), label.find("+")
+    if p1 >= 0 and p2 >= 0:
+        t = label[p1 + 1:p2] if p2 > p1 + 1 else ""
+    elif p1 >= 0:
+        t = label[p1 + 1:]
+    elif p2 >= 0:
+        t = label[:p2]
+    else:
+        t = label
+    if not t:
+        raise ValueError("Invalid phone label " + label)
+    return t
+
+
+def cmllr_unit_gaussians(unitmode, units, model, phones=None):
+    """The Gaussians a regression-class transform applies to (RegClassTree::Unit*::get_gaussians, aku/RegClassTree.cc:
+    302-322, 368-385, 444-454).  units: the strings in front of the matrix in a `w<i>` entry.  phones (UNIT_PHONE): list of
+    (label, [state, ...]) from the .ph file; a state's emission pdf is the mixture of the same index."""
+    off, mg = model["mix_offsets"], model["mix_gauss"]
+    out = set()
+    if unitmode == "UNIT_PHONE":
+        for label, states in phones:
+            if center_phone(label) in units:
+                for st in states:
+                    out.update(int(g) for g in mg[off[st]:off[st + 1]])
+    elif unitmode == "UNIT_MIX":
+        for u in units:
+            try:
+                m = int(u)
+            except ValueError:
+                continue                       # str2long failed: skipped (:378)
+            out.update(int(g) for g in mg[off[m]:off[m + 1]])
+    elif unitmode == "UNIT_GAUSSIAN":
+        for u in units:
+            try:
+                out.add(int(u))
+            except ValueError:
+                out.add(0)                     # str2long leaves 0 and the result is used regardless (:451)
+    else:
+        raise ValueError("unitmode")
+    return sorted(out)
+
+
+def cmllr_unit_assignment(unitmode, transforms, model, phones=None):
+    """ConstrainedMllr::load_transform (aku/ModelModules.cc:172-236): the transforms are visited in the order of their
+    std::map key -- the vector of unit strings, compared lexicographically -- and every Gaussian of a transform is wrapped
+    anew, so a Gaussian that several transforms claim ends up with the LAST one.  transforms: list of (units, W).
+    Returns (gauss -> transform index or -1, transforms in visiting order)."""
+    order = sorted(range(len(transforms)), key=lambda i: list(transforms[i][0]))
+    g2t = np.full(np.asarray(model["means"]).shape[0], -1, dtype=np.int32)
+    for rank, i in enumerate(order):
+        for g in cmllr_unit_gaussians(unitmode, transforms[i][0], model, phones):
+            g2t[g] = rank
+    return g2t, [transforms[i] for i in order]
+
+
+def state_likelihoods(model, feats, block=256, clustering=None, cmllr=None, cmllr_units=None):
     """HmmSet::precompute_likelihoods (aku/HmmSet.cc:485-501) for every frame: linear state
     likelihoods floored at 1e-50.  Sums run in the reference's order (dims then components).
     clustering = dict(n_clusters, gauss, cluster, min_clusters, min_gaussians) (the two ratios of
@@ -727,7 +785,9 @@ def state_likelihoods(model, feats, block=256, clustering=None, cmllr=None):
     (clusters < min) or (Gaussians < min), the rest take the centre's likelihood -- and, because
     PDFPool::compute_likelihood (:2637-2644) only trusts cached values > 0, a centre likelihood of 0 means the Gaussian is
     evaluated exactly after all.
-    cmllr = W [D x (D+1)]: every Gaussian and cluster centre is wrapped in an AdaptedGaussian (see cmllr_adapt)."""
+    cmllr = W [D x (D+1)]: every Gaussian and cluster centre is wrapped in an AdaptedGaussian (see cmllr_adapt).
+    cmllr_units = (g2t, [W_0, W_1, ...]): regression-class transforms (see cmllr_unit_assignment): Gaussian g with
+    g2t[g] = t >= 0 is evaluated at A_t f + b_t and multiplied by transform t's factor, the others are left alone."""
     feats = np.asarray(feats, dtype=np.float64)
     factor = None
     if cmllr is not None:
@@ -775,6 +835,14 @@ def state_likelihoods(model, feats, block=256, clustering=None, cmllr=None):
         lik = _exp(ll).astype(np.float64)   # DiagonalGaussian::compute_likelihood (:1036)
         if factor is not None:
             lik = lik * factor              # AdaptedGaussian::compute_likelihood
+        if cmllr_units is not None:
+            g2t, Ws = cmllr_units
+            for t, W in enumerate(Ws):
+                gs = np.nonzero(np.asarray(g2t) == t)[0]
+                if len(gs) == 0:
+                    continue
+                xa, fac = cmllr_adapt(W, x)
+                lik[:, gs] = _exp(_diag_loglik(xa, mu[gs], prec[gs], cst[gs])).astype(np.float64) * fac
         if clustering is not None:
             clik = _exp(_diag_loglik(x, cm, cprec, ccst)).astype(np.float64)
             if factor is not None:

@@ -63,6 +63,16 @@ def ref_cmllr():
 
 
 @pytest.fixture(scope="session")
+def ref_cmllr_units():
+    z = np.load(os.path.join(GOLDEN, "ref_cmllr_units.npz"))
+    d = {k: z[k] for k in z.files}
+    for k in ("cfg", "spkc", "ph", "unitmode_phone", "unitmode_mix", "unitmode_gauss"):
+        d[k] = str(d[k])
+    d["model"] = {k[6:]: d[k] for k in list(d) if k.startswith("model_")}
+    return d
+
+
+@pytest.fixture(scope="session")
 def ref_pre():
     return load_golden("ref_pre")
 

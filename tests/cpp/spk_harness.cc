@@ -39,6 +39,13 @@ int akugpu_features_range(akugpu_ctx *, const int16_t *, int64_t n_samples, int 
     for (int d = 0; d < 3; d++) ((double *)out)[(size_t)(f - start) * 3 + d] = (f < 0 ? 0 : (f >= n ? n - 1 : f)) + 0.25 * d;
   return 0;
 }
+int akugpu_model_set_cmllr_units(akugpu_ctx *, const char *unitmode, int n, const char *const *units, const double *W)
+{
+  printf("cmllr_units %s", unitmode);
+  for (int t = 0; t < n; t++) printf(" [%s] %g %g", units[t], W[(size_t)t * 6], W[(size_t)t * 6 + 5]);
+  printf("\n");
+  return 0;
+}
 int akugpu_features_pre(akugpu_ctx *, const float *, const int64_t *, int, void *, int, int64_t *) { return -1; }
 int akugpu_features_pre_range(akugpu_ctx *, const float *, int64_t, int, int, const char *, void *, int, int *) { return -1; }
 

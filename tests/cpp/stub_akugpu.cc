@@ -149,6 +149,15 @@ int akugpu_model_set_cmllr(akugpu_ctx *, const double *W)
   return 0;
 }
 
+int akugpu_model_set_cmllr_units(akugpu_ctx *, const char *unitmode, int n, const char *const *units, const double *W)
+{
+  g_cmllr = n > 0 ? 1 : 0;
+  logf("set_cmllr_units %s n=%d", unitmode, n);
+  for (int t = 0; t < n; t++) logf(" [%s] %g", units[t], W[(size_t)t * 12]);
+  logf("\n");
+  return 0;
+}
+
 // F64: linear likelihood of state s for a frame = (1 + x0 + x1) (s + 1) / 1000 (the test features are >= 0), floored at 1e-50;
 // F32: its logarithm.  Logged once per call.
 int akugpu_gmm_score(akugpu_ctx *, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)

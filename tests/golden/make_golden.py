@@ -38,7 +38,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from aaltoasr_b200 import formats, synth   # noqa: E402
-from oracle import ref                     # noqa: E402
+from oracle import oracle_np, ref          # noqa: E402
 
 REF = os.environ.get("AKU_REF", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -473,9 +473,99 @@ def cmllr_case(pcm, model, tmp):
           "clustered differs from exact on %.1f%%" % (100 * (out["lik_clust_bob"] != out["lik_bob"]).mean()))
 
 
+def cmllr_units_case(pcm, model, tmp):
+    """Model-level CMLLR with regression classes (`model cmllr`, unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN,
+    aku/ModelModules.cc:62-95,172-236): state likelihoods of aku::HmmSet after SpeakerConfig::set_speaker for one speaker
+    per unit mode (two transforms each, claiming overlapping Gaussians through the model's shared components), and the
+    LNA file of the literal phone_probs -S for each."""
+    name = "ref_cmllr_units"
+    rng = np.random.default_rng(7020)
+    cfg_text = synth.mfcc39_config()
+    wav = os.path.join(tmp, name + ".wav"); cfg = os.path.join(tmp, name + ".cfg"); base = os.path.join(tmp, name)
+    formats.write_wav(wav, pcm, 16000)
+    open(cfg, "w").write(cfg_text)
+    formats.write_model(base, **model)
+    # eight three-state phones over the 24 states; context-dependent labels exercise Hmm::get_center_phone
+    labels = ["a", "x-b+y", "c+z", "q-d", "e", "a-f+a", "g", "x-a+y"]
+    phones = [(labels[p], [3 * p, 3 * p + 1, 3 * p + 2]) for p in range(8)]
+    ph_text = "PHONE\n8\n" + "".join("%d 5 %s\n-1 -2 %d %d %d\n0 1 2 1\n1 0\n2 2 2 0.8 3 0.2\n3 2 3 0.8 4 0.2\n4 2 4 0.8 1 0.2\n"
+                                      % (p + 1, labels[p], 3 * p, 3 * p + 1, 3 * p + 2) for p in range(8))
+    open(base + ".ph", "w").write(ph_text)
+    feats, _, _ = ref.features(cfg, wav)
+    D = 39
+    sd = feats.std(axis=0)
+    def matrix(flip=False):
+        A = np.eye(D) + 0.03 * rng.standard_normal((D, D)) * (sd[:, None] / sd[None, :])
+        if flip:
+            A[5, 5] = -A[5, 5]
+        b = 0.15 * sd * rng.standard_normal(D)
+        W = np.concatenate([b[:, None], A], axis=1)
+        text = " ".join("%g" % v for v in W.reshape(-1))
+        # the reference parses the values with str::str2float (aku/str.cc:261-282): they pass through a float
+        return text, np.array([np.float32(float(t)) for t in text.split()], dtype=np.float64).reshape(D, D + 1)
+    cases = {"phone": ("UNIT_PHONE", [["a", "d"], ["b", "g", "nosuch"]]),          # "a" = phones 0 and 7 (x-a+y)
+             "mix": ("UNIT_MIX", [["7", "2", "19"], ["0", "1", "2", "3", "23"]]),      # mixture 2 in both: map order decides
+             "gauss": ("UNIT_GAUSSIAN", [["5", "40", "41", "90"], ["0", "1", "2", "40", "17"]])}
+    spkc = "speaker default\n{\n}\n\n"
+    out = dict(cfg=cfg_text, pcm=pcm, feats=feats, ph=ph_text, **{"model_" + k: v for k, v in model.items()})
+    for spk, (um, unit_lists) in cases.items():
+        lines = ["    unitmode " + um]
+        for i, units in enumerate(unit_lists):
+            text, W = matrix(flip=(i == 1))
+            lines.append("    w%d %s %s" % (i + 1, " ".join(units), text))
+            out["W_%s_%d" % (spk, i)] = W
+            out["units_%s_%d" % (spk, i)] = np.array(units)
+        spkc += "speaker %s\n{\n  model cmllr\n  {\n%s\n  }\n}\n\n" % (spk, "\n".join(lines))
+        out["unitmode_" + spk] = um
+    spath = os.path.join(tmp, name + ".spkc")
+    open(spath, "w").write(spkc)
+    out["spkc"] = spkc
+    M = ref.Model(base)
+    plain = M.state_likelihoods(feats)
+    out["lik_plain"] = plain
+    for spk, (um, unit_lists) in cases.items():
+        M.set_speaker(spath, spk)
+        lik = M.state_likelihoods(feats)
+        out["lik_" + spk] = lik
+        trs = [(unit_lists[i], out["W_%s_%d" % (spk, i)]) for i in range(len(unit_lists))]
+        g2t, ordered = oracle_np.cmllr_unit_assignment(um, trs, model, phones)
+        mine = oracle_np.state_likelihoods(model, feats, cmllr_units=(g2t, [w for _, w in ordered]))
+        rel = np.abs(mine - lik) / lik
+        print(name, spk, um, "adapted Gaussians per transform:", [int((g2t == t).sum()) for t in range(len(trs))],
+              "states changed: %d / 24" % int((np.abs(lik - plain).max(axis=0) > 0).sum()), "oracle max rel diff %.3g" % rel.max(),
+              "bit-identical" if np.array_equal(mine, lik) else "")
+        out["g2t_" + spk] = g2t
+    # a speaker without a `model cmllr` entry leaves the previous speaker's transforms loaded (set_modules only touches
+    # listed modules, aku/SpeakerConfig.cc:365-380)
+    M.set_speaker(spath, "nobody")
+    assert np.array_equal(M.state_likelihoods(feats), out["lik_gauss"])
+    M.close()
+    lines = []
+    for i, spk in enumerate(cases):
+        lines.append("audio=%s lna=cu%d.lna speaker=%s" % (wav, i, spk))
+    rec = os.path.join(tmp, name + ".recipe")
+    open(rec, "w").write("\n".join(lines) + "\n")
+    for nb in (2, 4):
+        od = os.path.join(tmp, "cu_out%d" % nb)
+        os.makedirs(od, exist_ok=True)
+        ref.phone_probs(cfg, base, rec, od, nb, extra=["-S", spath])
+        for i, spk in enumerate(cases):
+            out["lna%d_%s" % (nb, spk)] = np.frombuffer(open(os.path.join(od, "cu%d.lna" % i), "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
+    if sys.argv[1:] == ["cmllr_units"]:
+        with tempfile.TemporaryDirectory() as tmp:
+            pcm = synth.synth_audio(7001, 24000)
+            wav = os.path.join(tmp, "probe.wav"); cfg = os.path.join(tmp, "probe.cfg")
+            formats.write_wav(wav, pcm, 16000)
+            open(cfg, "w").write(synth.mfcc39_config())
+            feats, _, _ = ref.features(cfg, wav)
+            cmllr_units_case(pcm, small_model(feats, 7002), tmp)
+        return
     if sys.argv[1:] == ["cmllr"]:             # only the newest fixture (the others are unchanged)
         with tempfile.TemporaryDirectory() as tmp:
             pcm = synth.synth_audio(7001, 24000)
@@ -499,6 +589,7 @@ def main():
         vtln_case(pcm, tmp)
         modx_case(pcm, tmp)
         cmllr_case(pcm, small_model(feats, 7002), tmp)
+        cmllr_units_case(pcm, small_model(feats, 7002), tmp)
         run_case("ref_edge", pcm, edge_model(feats, 7003), tmp)
         run_case("ref_full", pcm, full_model(feats, 5999), tmp)
 

@@ -182,7 +182,7 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
     assert out == "speaker alice\nfeature cmllr\n%s.\nspeaker carol\nfeature cmllr\n%s.\n" % (conf["alice"]["cmllr"], conf["default"]["cmllr"])
     # errors, worded like the reference
     head = "speaker a\n{\n  model cmllr\n  {\n"
-    for body, msg in (("    unitmode UNIT_PHONE\n    w1 x 1 0 0 1 0 0\n", "regression-class"),
+    for body, msg in (("    unitmode UNIT_PHONE\n    w1 1 0 0 1 0 0\n", "not enough elements for matrix w1"),      # no unit in front of the matrix
                       ("    w1 1 2 3\n", "not enough elements for matrix w1"),
                       ("    w1 0 1 zz 0 0 1\n", "invalid value: zz"),
                       ("    w1 p 0 1 0 0 0 1\n    w2 q 0 1 0 0 0 1\n", "only contain one transform")):
@@ -190,6 +190,9 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
         assert rc == 1 and msg in out, (body, out)
     rc, out = calls(head + "    w1 0.5 1 0 -0.5 0 1\n  }\n}\n", 2, ["a"])
     assert rc == 0 and out == "speaker a\ncmllr 0.5 1 0 -0.5 0 1\n"
+    # regression classes: units in front of each matrix, handed to the library in the reference's std::map order
+    rc, out = calls(head + "    unitmode UNIT_PHONE\n    w1 u a 0.5 1 0 -0.5 0 1\n    w2 b 0.25 1 0 0 0 2\n  }\n}\n", 2, ["a"])
+    assert rc == 0 and out == "speaker a\ncmllr_units UNIT_PHONE [b] 0.25 2 [u a] 0.5 1\n", out
     rc, out = calls("speaker a\n{\n  model mllr\n  {\n  }\n}\n", 2, ["a"])
     assert rc == 1 and "SpeakerConfig: error on line 3: unknown model module requested: mllr" in out
     rc, out = calls("utterance u\n{\n  model cmllr\n  {\n  }\n}\n", 2, [])

@@ -255,7 +255,7 @@ def test_cpp_tool_model_cmllr(engine, ref_cmllr, tmp_path):
     open(spkc, "w").write(g["spkc"].replace("unitmode UNIT_NO", "unitmode UNIT_MIX"))
     r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(tmp_path / "o2"), "-S", spkc],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
-    assert r.returncode != 0 and b"regression-class" in r.stderr
+    assert r.returncode != 0 and b"not enough elements for matrix w1" in r.stderr        # a regression-class entry needs its units
 
 
 def test_cpp_pptoolbox_mirror(engine, ref_small, ref_clust, tmp_path):
@@ -387,3 +387,29 @@ def test_feacat_tool_aku_scripts(engine, aku_tests, ref_vtln, tmp_path):
     assert run("-c", cfgs["mfcc_p_dd"], "-G", "0.1", wav).returncode != 0
     r = run("-c", str(tmp_path / "missing.cfg"), wav)
     assert r.returncode != 0 and b"exception:" in r.stderr
+
+
+def test_cpp_tool_regression_class_cmllr(ref_cmllr_units, tmp_path):
+    """akugpu_phone_probs -S with `model cmllr` entries in the regression-class unit modes (UNIT_PHONE / UNIT_MIX /
+    UNIT_GAUSSIAN): the C++ SpeakerConfig hands units + matrices to akugpu_model_set_cmllr_units; files within +-1 code of
+    the literal phone_probs -S output (features from the WAV differ in the last bits)."""
+    g = ref_cmllr_units
+    base = str(tmp_path / "m")
+    formats.write_model(base, **g["model"])
+    open(base + ".ph", "w").write(g["ph"])
+    cfg = str(tmp_path / "c.cfg"); open(cfg, "w").write(g["cfg"])
+    spkc = str(tmp_path / "x.spkc"); open(spkc, "w").write(g["spkc"])
+    wav = str(tmp_path / "a.wav"); formats.write_wav(wav, g["pcm"], 16000)
+    rec = str(tmp_path / "r")
+    open(rec, "w").write("".join("audio=%s lna=%s.lna speaker=%s\n" % (wav, spk, spk) for spk in ("phone", "mix", "gauss")))
+    for prec in ("f64", "f32"):
+        out = tmp_path / ("o_" + prec); out.mkdir()
+        r = subprocess.run([TOOL, "-b", base, "-c", cfg, "-r", rec, "-o", str(out), "-S", spkc, "--precision=" + prec],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()
+        for spk in ("phone", "mix", "gauss"):
+            got = np.frombuffer(open(str(out / (spk + ".lna")), "rb").read(), dtype=np.uint8)
+            want = g["lna2_" + spk]
+            assert got.size == want.size and bytes(got[:5]) == bytes(want[:5])
+            d = np.abs(got[5:].view(">u2").astype(int) - want[5:].view(">u2").astype(int))
+            assert d.max() <= 1 and (d != 0).mean() <= 0.03, (prec, spk, d.max(), (d != 0).mean())

@@ -728,3 +728,54 @@ def test_errors(engine, ref_small):
         engine.phone_probs(ref_small["pcm"])
     with pytest.raises(AkuGpuError, match="could not open"):
         engine.model_read("/nonexistent/model")
+
+
+def test_cmllr_regression_classes(engine, ref_cmllr_units, tmp_path):
+    """Regression-class model-level CMLLR (unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN) on the GPU double path: every
+    Gaussian sees its class's A f + b (gmm_diag_f64 picks the row by class) and its class's factor; likelihoods equal the
+    reference's aku::HmmSet after SpeakerConfig::set_speaker, LNA bytes the literal phone_probs -S files; throughput-mode
+    requests are served by the same path; removing the transforms restores the plain model."""
+    from aaltoasr_b200 import SpeakerConfig, formats
+    g = ref_cmllr_units
+    base = str(tmp_path / "m")
+    formats.write_model(base, **g["model"])
+    open(base + ".ph", "w").write(g["ph"])
+    engine.frontend_load_config_text(g["cfg"])
+    engine.model_read(base)                                   # UNIT_PHONE needs the phone table of the files
+    plain = engine.gmm_score(g["feats"], precision=F64)
+    assert (np.abs(plain - g["lik_plain"]) / g["lik_plain"]).max() <= 1e-12
+    spkc = str(tmp_path / "x.spkc")
+    open(spkc, "w").write(g["spkc"])
+    sc = SpeakerConfig(engine)
+    sc.read_speaker_file(spkc)
+    for spk in ("phone", "mix", "gauss"):
+        sc.set_speaker(spk)
+        assert engine.scorer_in_use() in (0, 3)              # whatever the image, requests go to the double path
+        lik = engine.gmm_score(g["feats"], precision=F64)
+        rel = np.abs(lik - g["lik_" + spk]) / g["lik_" + spk]
+        assert rel.max() <= 1e-12, (spk, rel.max())
+        for nb in (2, 4):
+            want = g["lna%d_%s" % (nb, spk)][5:]
+            assert np.array_equal(engine.gmm_lna(g["feats"], precision=F64, lnabytes=nb).reshape(-1), want), (spk, nb)
+            # F32 requests and float features: same path, features rounded to float
+            got = engine.gmm_lna(g["feats"].astype(np.float32), precision=F32, lnabytes=nb).reshape(-1)
+            if nb == 2:
+                d = np.abs(got.view(">u2").astype(int) - want.view(">u2").astype(int))
+                assert d.max() <= 1 and (d != 0).mean() <= 0.02
+        ll32 = engine.gmm_score(g["feats"].astype(np.float32), precision=F32)
+        assert np.abs(ll32 - np.log(g["lik_" + spk])).max() <= 2e-4
+        row = engine.gmm_logprobs(g["feats"][5:6], precision=F32, tiny=1e-30)          # the small-call path declines, general path serves
+        assert np.abs(row[0] - np.log(g["lik_" + spk][5])).max() <= 2e-4
+    # direct API: Gaussian units on a model loaded from memory; phones are not available there
+    load_model(engine, g["model"])
+    trs = [([str(u) for u in g["units_gauss_%d" % i]], g["W_gauss_%d" % i]) for i in range(2)]
+    engine.model_set_cmllr_units("UNIT_GAUSSIAN", trs)
+    lik = engine.gmm_score(g["feats"], precision=F64)
+    assert (np.abs(lik - g["lik_gauss"]) / g["lik_gauss"]).max() <= 1e-12
+    with pytest.raises(AkuGpuError, match="phone table"):
+        engine.model_set_cmllr_units("UNIT_PHONE", [(["a"], g["W_phone_0"])])
+    with pytest.raises(AkuGpuError, match="out of range"):
+        engine.model_set_cmllr_units("UNIT_MIX", [(["24"], g["W_mix_0"])])
+    engine.model_set_cmllr_units("UNIT_GAUSSIAN", [])
+    assert (np.abs(engine.gmm_score(g["feats"], precision=F64) - g["lik_plain"]) / g["lik_plain"]).max() <= 1e-12
+    assert engine.scorer_in_use() == 3

@@ -157,6 +157,11 @@ def test_model_cmllr_bit_exact_vs_reference(ref_cmllr):
         parse_cmllr_parameters("unitmode UNIT_NO\nw1 1 2 3\n", 39)
     with pytest.raises(AkuGpuError, match="regression-class"):
         parse_cmllr_parameters("unitmode UNIT_PHONE\nw1 a 1 0 0 1 0 0\n", 2)
+    from aaltoasr_b200.hostapi import parse_cmllr_transforms
+    um, trs = parse_cmllr_transforms("unitmode UNIT_PHONE\nw1 a b 1 0 0 1 0 0\nw2 c 0 1 0 0 0 1\n", 2)
+    assert um == "UNIT_PHONE" and [u for u, _ in trs] == [["a", "b"], ["c"]] and np.array_equal(trs[1][1], [[0, 1, 0], [0, 0, 1]])
+    with pytest.raises(AkuGpuError, match="not enough elements"):
+        parse_cmllr_transforms("unitmode UNIT_MIX\nw1 1 0 0 1 0 0\n", 2)
     with pytest.raises(AkuGpuError, match="invalid value"):
         parse_cmllr_parameters("w1 0 1 x 0 0 1\n", 2)
     assert np.array_equal(parse_cmllr_parameters("w1 0.5 1 0 -0.5 0 1\n", 2), [[0.5, 1, 0], [-0.5, 0, 1]])
@@ -305,3 +310,35 @@ def test_oracle_feature_sweep_vs_live_reference(sr, ww, tmp_path):
     ext = P.run(pcm, -4, want.shape[0] + 5)                  # border frames on both sides
     want_ext, _, _ = ref.features(cfg, wav, -4, want.shape[0] + 5)
     assert np.abs(ext - want_ext).max() <= 1e-5
+
+
+def test_cmllr_regression_classes_against_reference(ref_cmllr_units):
+    """`model cmllr` with unitmode UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN (aku/ModelModules.cc:62-95,172-236): the restatement --
+    units resolved to Gaussians (centre phones, mixtures, Gaussian indices), transforms visited in the reference's std::map
+    order so that the last claimant of a shared Gaussian wins, values through str2float's float -- equals aku::HmmSet after
+    SpeakerConfig::set_speaker bit for bit, and the host parsers agree with the fixture."""
+    from aaltoasr_b200 import parse_speaker_file
+    from aaltoasr_b200.hostapi import parse_cmllr_transforms
+    g = ref_cmllr_units
+    phones = []
+    tok = g["ph"].split()
+    assert tok[0] == "PHONE"
+    lines = g["ph"].splitlines()[2:]
+    for p in range(8):
+        label = lines[7 * p].split()[2]
+        phones.append((label, [int(x) for x in lines[7 * p + 1].split()[2:]]))
+    assert oracle_np.center_phone("x-b+y") == "b" and oracle_np.center_phone("c+z") == "c" and oracle_np.center_phone("q-d") == "d"
+    conf = parse_speaker_file(g["spkc"])["speaker"]
+    for spk in ("phone", "mix", "gauss"):
+        um, trs = parse_cmllr_transforms(conf[spk]["model cmllr"], 39)
+        assert um == g["unitmode_" + spk] and len(trs) == 2
+        for i, (units, W) in enumerate(trs):
+            assert units == [str(u) for u in g["units_%s_%d" % (spk, i)]] and np.array_equal(W, g["W_%s_%d" % (spk, i)])
+        g2t, ordered = oracle_np.cmllr_unit_assignment(um, trs, g["model"], phones)
+        assert np.array_equal(g2t, g["g2t_" + spk])
+        lik = oracle_np.state_likelihoods(g["model"], g["feats"], cmllr_units=(g2t, [w for _, w in ordered]))
+        assert np.array_equal(lik, g["lik_" + spk])
+        assert not np.array_equal(lik, g["lik_plain"])
+        for nb in (2, 4):
+            rec, _ = oracle_np.lna_records(lik, nb)
+            assert np.array_equal(rec.reshape(-1), g["lna%d_%s" % (nb, spk)][5:])       # the literal phone_probs -S on the same features
