@@ -212,7 +212,7 @@ struct Module {
   // mean_subtractor: left/right hold the +1-extended offsets, width = left+right-1
   int ms_width = 0;
   // vtln (VtlnModule, aku/FeatureModules.cc:1505-1934): warp of the spectrum bins, sinc / linear interpolation
-  int use_pwlin = 0, use_slapt = 0, sinc_rad = 8, lanczos = 1;
+  int use_pwlin = 0, use_slapt = 0, sinc_rad = 8, lanczos = 1, all_pass = 0;
   float pwlin_turn_point = 0.8f, warp_factor = 1.0f;
   std::vector<float> slapt_params, vtln_bins;
   // sr_norm (SRNormModule :1936-2069): Lanczos resampling across the stacked frames of a concat module

@@ -283,7 +283,87 @@ void upload_module_params(akugpu_ctx *ctx, Module &m, const std::vector<Module> 
       }
       std::vector<float> coef;
       std::vector<int> desc;
-      if (m.sinc_rad > 0) {
+      if (m.all_pass) {
+        // All-pass VTLN: the warp as a matrix T on the cepstrum of the spectrum, final = IDCT * (T * DCT), applied as full
+        // rows of coefficients (create_all_pass_blin_transform :1717-1757, create_all_pass_slapt_transform :1759-1868,
+        // set_all_pass_transform :1870-1904).  Everything in double; sums over the inner index in ascending order.
+        auto conv = [](const std::vector<double> &a, const std::vector<double> &bb) {      // (a * b)[j] = sum_{p+q=j} a[p] b[q]
+          std::vector<double> out(a.size() + bb.size() - 1, 0.0);
+          for (size_t j = 0; j < out.size(); j++) {
+            const size_t lo = j >= bb.size() - 1 ? j - (bb.size() - 1) : 0, hi = std::min(j, a.size() - 1);
+            double tt = 0;
+            for (size_t p = lo; p <= hi; p++) tt += a[p] * bb[j - p];
+            out[j] = tt;
+          }
+          return out;
+        };
+        std::vector<double> T((size_t)dim * dim, 0.0);
+        T[0] = 1.0;
+        if (!m.use_slapt) {
+          const double alpha = (double)(float)(m.warp_factor - 1);
+          std::vector<double> q1(dim), q(dim, 0.0), qn(dim);
+          q1[0] = -alpha;
+          double temp = 1 - alpha * alpha;
+          for (int i = 1; i < dim; i++) { q1[i] = temp; temp *= alpha; }
+          q[0] = 1;
+          for (int i = 1; i < dim; i++) {      // column i: the i-th convolution power of q1, truncated to dim terms
+            for (int j = 0; j < dim; j++) {
+              double tt = 0;
+              for (int k = 0; k <= j; k++) tt += q[k] * q1[j - k];
+              qn[j] = tt;
+            }
+            q = qn;
+            T[(size_t)0 * dim + i] = 2 * q[0];
+            for (int j = 1; j < dim; j++) T[(size_t)j * dim + i] = q[j];
+          }
+        } else {
+          const int P = (int)m.slapt_params.size();
+          std::vector<double> f1(2 * P + 1, 0.0);
+          for (int i = 0; i < P; i++) {
+            f1[i] = -m.slapt_params[P - i - 1] * M_PI / 2;
+            f1[i + P + 1] = m.slapt_params[i] * M_PI / 2;
+          }
+          std::vector<double> q(2 * dim + 1, 0.0), cur_f(1, 1.0);
+          int center = 0;
+          double cur_m = 1;
+          for (int i = 0; i <= 10; i++) {        // exp of the sequence: sum over i of f1^(*i) / i!
+            if (i > 0) cur_m = cur_m / (double)i;
+            for (int j = std::max(0, dim - center); j < std::min(2 * dim + 1, dim + center + 1); j++) q[j] = q[j] + cur_m * cur_f[j - dim + center];
+            cur_f = conv(cur_f, f1);
+            center = ((int)cur_f.size() - 1) / 2;
+          }
+          q.pop_back(); q.pop_back();
+          const std::vector<double> q1 = q;
+          for (int i = 1; i < dim; i++) {
+            T[(size_t)0 * dim + i] = 2 * q[dim - 1];
+            for (int j = 1; j < dim; j++) T[(size_t)j * dim + i] = q[dim + j - 1] + q[dim - j - 1];
+            const std::vector<double> full = conv(q, q1);
+            q.assign(full.begin() + (dim - 1), full.begin() + (3 * dim - 2));
+          }
+        }
+        std::vector<double> dct((size_t)dim * dim), idct((size_t)dim * dim), tmp((size_t)dim * dim), fin((size_t)dim * dim);
+        for (int i = 0; i < dim; i++)
+          for (int j = 0; j < dim; j++) {
+            dct[(size_t)i * dim + j] = cos(i * (j + 0.5) * M_PI / dim);
+            idct[(size_t)i * dim + j] = j == 0 ? 1.0 / dim : cos((i + 0.5) * j * M_PI / dim) * 2 / dim;
+          }
+        for (int i = 0; i < dim; i++)
+          for (int j = 0; j < dim; j++) {
+            double acc = 0;
+            for (int p2 = 0; p2 < dim; p2++) acc += T[(size_t)i * dim + p2] * dct[(size_t)p2 * dim + j];
+            tmp[(size_t)i * dim + j] = acc;
+          }
+        for (int i = 0; i < dim; i++)
+          for (int j = 0; j < dim; j++) {
+            double acc = 0;
+            for (int p2 = 0; p2 < dim; p2++) acc += idct[(size_t)i * dim + p2] * tmp[(size_t)p2 * dim + j];
+            fin[(size_t)i * dim + j] = acc;
+          }
+        for (int bi = 0; bi < dim; bi++) {
+          desc.push_back(0); desc.push_back(dim); desc.push_back((int)coef.size());
+          for (int j = 0; j < dim; j++) coef.push_back((float)fin[(size_t)bi * dim + j]);
+        }
+      } else if (m.sinc_rad > 0) {
         auto sinc = [](float x) -> float {
           const double PI = 3.14159265358979323846;
           if (fabs(x) < 1e-8) return 1;
@@ -497,10 +577,13 @@ void frontend_parse(akugpu_ctx *ctx, const std::string &text)
         m.use_slapt = 0; get_int(b, "slapt", m.use_slapt);
         if (m.use_pwlin && m.use_slapt) throw Error(AKUGPU_E_CONFIG, "VtlnModule: Can not use both pwlin_vtln and slapt!");
         m.sinc_rad = 8; get_int(b, "sinc_interpolation_rad", m.sinc_rad);
-        int all_pass = 0; get_int(b, "all-pass", all_pass);
-        if (all_pass) throw Error(AKUGPU_E_CONFIG, "VtlnModule: all-pass transforms are not supported by the GPU front-end");
-        m.lanczos = 1; get_int(b, "lanczos_window", m.lanczos);
+        m.all_pass = 0; get_int(b, "all-pass", m.all_pass);
+        if (m.use_pwlin && m.all_pass) throw Error(AKUGPU_E_CONFIG, "VtlnModule: Can not use both pwlin_vtln and all-pass!");
+        m.lanczos = m.all_pass ? 0 : 1; get_int(b, "lanczos_window", m.lanczos);
         m.lanczos = m.lanczos > 0 ? 1 : 0;
+        if (m.lanczos && m.all_pass) throw Error(AKUGPU_E_CONFIG, "VtlnModule: Can not use both lanczos_window and all-pass!");
+        if (m.all_pass && m.sinc_rad <= 0)     // the reference would then interpolate with warped bins it never computed
+          throw Error(AKUGPU_E_CONFIG, "VtlnModule: all-pass needs sinc_interpolation_rad > 0");
         m.warp_factor = 1.0f;
         m.slapt_params.assign(1, 0.0f);
         break;

@@ -62,7 +62,7 @@ int         akugpu_stage_times_reset(akugpu_ctx *ctx, int enable);
  * Replaces FeatureGenerator::load_configuration (aku/FeatureGenerator.cc:97-219)
  * and the module classes of aku/FeatureModules.cc.  The text is the reference's
  * own `module { name .. type .. sources .. }` format.  Supported module types:
- * audiofile, pre, fft, vtln (not all-pass), mel, power, mel_power, dct, delta, merge, concat, normalization,
+ * audiofile, pre, fft, vtln (incl. all-pass), mel, power, mel_power, dct, delta, merge, concat, normalization,
  * lin_transform, mean_subtractor, sr_norm, quanteq -- every module type of aku/FeatureModules.cc. */
 int   akugpu_frontend_load_config(akugpu_ctx *ctx, const char *cfg_path);
 int   akugpu_frontend_load_config_text(akugpu_ctx *ctx, const char *cfg_text);

@@ -151,15 +151,18 @@ class Pipeline:
             elif t == "mean_subtractor":  # :1385-1405
                 m["dim"] = sdim
                 m["ctx_l"], m["ctx_r"] = int(m.get("left", 75)), int(m.get("right", 75))
-            elif t == "vtln":      # VtlnModule::set_module_config :1530-1573 (all-pass variants not restated)
+            elif t == "vtln":      # VtlnModule::set_module_config :1530-1573
                 m["dim"] = sdim
                 m["use_pwlin"] = int(m.get("pwlin_vtln", 0))
                 m["turn"] = f32(float(m.get("pwlin_turnpoint", 0.8)))
                 m["use_slapt"] = int(m.get("slapt", 0))
                 m["rad"] = int(m.get("sinc_interpolation_rad", 8))
-                if int(m.get("all-pass", 0)):
-                    raise ValueError("VtlnModule: all-pass transforms are not restated")
-                m["lanczos"] = int(m.get("lanczos_window", 1)) > 0
+                m["all_pass"] = int(m.get("all-pass", 0))
+                if m["use_pwlin"] and m["all_pass"]:
+                    raise ValueError("VtlnModule: Can not use both pwlin_vtln and all-pass!")
+                m["lanczos"] = int(m.get("lanczos_window", 0 if m["all_pass"] else 1)) > 0
+                if m["lanczos"] and m["all_pass"]:
+                    raise ValueError("VtlnModule: Can not use both lanczos_window and all-pass!")
                 m["warp"] = f32(1.0)
                 m["slapt_params"] = [f32(0.0)]
                 _vtln_tables(m)
@@ -417,9 +420,91 @@ def _sincf(x):
     return f32(math.sin(y) / y)
 
 
+def _full_conv(a, b):
+    """Linear convolution (a * b)[j] = sum_{p+q=j} a[p] b[q], p ascending (the index bookkeeping of
+    aku/FeatureModules.cc:1793-1815,1836-1862 spells out exactly this sum)."""
+    out = [0.0] * (len(a) + len(b) - 1)
+    for j in range(len(out)):
+        lo = max(0, j - (len(b) - 1))
+        hi = min(j, len(a) - 1)
+        t = 0.0
+        for p in range(lo, hi + 1):
+            t += a[p] * b[j - p]
+        out[j] = t
+    return out
+
+
+def _vtln_allpass_tables(m):
+    """All-pass VTLN: the warp as a matrix on the cepstrum of the spectrum, wrapped in a DCT / inverse DCT and applied as
+    full rows of `sinc` coefficients (create_all_pass_blin_transform :1717-1757, create_all_pass_slapt_transform
+    :1759-1868, set_all_pass_transform :1870-1904)."""
+    dim = m["dim"]
+    T = np.zeros((dim, dim))
+    T[0, 0] = 1.0
+    if not m["use_slapt"]:
+        alpha = float(f32(m["warp"] - f32(1)))               # double alpha = m_warp_factor - 1 (a float expression)
+        q1 = [0.0] * dim
+        q1[0] = -alpha
+        temp = 1 - alpha * alpha
+        for i in range(1, dim):
+            q1[i] = temp
+            temp *= alpha
+        q = [0.0] * dim
+        q[0] = 1.0
+        for i in range(1, dim):                                # column i: the i-th convolution power of q1, truncated
+            qn = [0.0] * dim
+            for j in range(dim):
+                t = 0.0
+                for k in range(j + 1):
+                    t += q[k] * q1[j - k]
+                qn[j] = t
+            q = qn
+            T[0, i] = 2 * q[0]
+            for j in range(1, dim):
+                T[j, i] = q[j]
+    else:
+        sp = [float(x) for x in m["slapt_params"]]
+        P = len(sp)
+        f1 = [0.0] * (2 * P + 1)
+        for i in range(P):
+            f1[i] = -sp[P - i - 1] * math.pi / 2
+            f1[i + P + 1] = sp[i] * math.pi / 2
+        q = [0.0] * (2 * dim + 1)
+        cur_f, center, cur_m = [1.0], 0, 1.0
+        for i in range(11):                                    # exp of the sequence: sum over i of f1^(*i) / i!
+            if i > 0:
+                cur_m = cur_m / float(i)
+            for j in range(max(0, dim - center), min(2 * dim + 1, dim + center + 1)):
+                q[j] = q[j] + cur_m * cur_f[j - dim + center]
+            cur_f = _full_conv(cur_f, f1)
+            center = (len(cur_f) - 1) // 2
+        q = q[:-2]                                             # "make the initial sequence symmetric"
+        q1 = list(q)
+        for i in range(1, dim):
+            T[0, i] = 2 * q[dim - 1]
+            for j in range(1, dim):
+                T[j, i] = q[dim + j - 1] + q[dim - j - 1]
+            full = _full_conv(q, q1)
+            q = full[dim - 1:3 * dim - 2]
+    # set_all_pass_transform: final = idct * (T * dct), sums over the inner index in ascending order
+    dct = np.array([[math.cos(i * (j + 0.5) * math.pi / dim) for j in range(dim)] for i in range(dim)])
+    idct = np.array([[(1.0 / dim) if j == 0 else math.cos((i + 0.5) * j * math.pi / dim) * 2 / dim for j in range(dim)] for i in range(dim)])
+    tmp = np.zeros((dim, dim))
+    for p in range(dim):
+        tmp += T[:, p:p + 1] * dct[p:p + 1, :]
+    fin = np.zeros((dim, dim))
+    for p in range(dim):
+        fin += idct[:, p:p + 1] * tmp[p:p + 1, :]
+    m["bins"] = np.zeros(dim, dtype=f32)
+    m["sinc_start"] = [0] * dim
+    m["sinc_coef"] = [[f32(v) for v in fin[i]] for i in range(dim)]
+
+
 def _vtln_tables(m):
     """create_blin_bins :1662-1675 / create_pwlin_bins :1634-1660 / create_slapt_bins :1677-1695 and
     create_sinc_coef_table :1697-1723: float bins, float taps, the reference's mixed arithmetic."""
+    if m.get("all_pass"):
+        return _vtln_allpass_tables(m)
     dim = m["dim"]
     bins = np.zeros(dim, dtype=f32)
     if m["use_slapt"]:

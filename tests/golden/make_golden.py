@@ -318,6 +318,47 @@ def vtln_case(pcm, tmp):
     np.savez_compressed(os.path.join(HERE, "ref_vtln.npz"), **out)
 
 
+def vtln_allpass_case(pcm, tmp):
+    """VtlnModule with `all-pass 1` (aku/FeatureModules.cc:1717-1904): bilinear and SLAPT warps as cepstral matrices."""
+    wav = os.path.join(tmp, "vtlnap.wav")
+    formats.write_wav(wav, pcm[:8000], 16000)
+    variants = {"blin": ["all-pass 1"], "slapt": ["all-pass 1", "slapt 1"]}
+    out = dict(pcm=pcm[:8000])
+    for name, extra in variants.items():
+        cfg_text = vtln_cfg(extra)
+        cfg = os.path.join(tmp, "vtlnap_%s.cfg" % name)
+        open(cfg, "w").write(cfg_text)
+        params = {"s1": "slapt_coef 0.02 -0.01", "s2": "slapt_coef -0.03"} if name == "slapt" else {"s1": "warp_factor 0.93", "s2": "warp_factor 1.08"}
+        spkc = "speaker default\n{\n  vtln\n  {\n  }\n}\n\n" + "".join(
+            "speaker %s\n{\n  feature vtln\n  {\n    %s\n  }\n}\n\n" % (k, v) for k, v in params.items())
+        sp = os.path.join(tmp, "vtlnap_%s.spkc" % name)
+        open(sp, "w").write(spkc)
+        out["cfg_" + name] = cfg_text
+        out["spkc_" + name] = spkc
+        for spk in ("s1", "s2", "other"):
+            out["feats_%s_%s" % (name, spk)] = ref.features_spk(cfg, wav, sp, spk)
+        plain, _, _ = ref.features(vtln_cfg_path(tmp), wav)
+        print("ref_vtln_allpass", name, out["feats_%s_s1" % name].shape,
+              "max |s1 - no vtln| %.3f, |default - no vtln| %.3g" % (np.abs(out["feats_%s_s1" % name] - plain).max(),
+                                                                     np.abs(out["feats_%s_other" % name] - plain).max()))
+        P = oracle_np.Pipeline(cfg_text)
+        for spk, prm in list(params.items()) + [("other", None)]:
+            if prm:
+                P.set_parameters("vtln", prm)
+            else:
+                P.set_parameters("vtln", "")
+            mine = P.run(pcm[:8000])
+            print("   oracle vs reference, speaker %s: max abs diff %.3g" % (spk, np.abs(mine - out["feats_%s_%s" % (name, spk)]).max()))
+    np.savez_compressed(os.path.join(HERE, "ref_vtln_allpass.npz"), **out)
+
+
+def vtln_cfg_path(tmp):
+    """The same chain with a pass-through vtln module (warp 1, linear interpolation): the unwarped features."""
+    p = os.path.join(tmp, "vtln_plain.cfg")
+    open(p, "w").write(vtln_cfg(["sinc_interpolation_rad 0"]))
+    return p
+
+
 MODX_HEAD = """module
 {
   name audiofile
@@ -557,6 +598,10 @@ def cmllr_units_case(pcm, model, tmp):
 def main():
     if not ref.available():
         raise SystemExit("oracle/_ref is not built: run oracle/build_ref.sh first")
+    if sys.argv[1:] == ["vtln_allpass"]:
+        with tempfile.TemporaryDirectory() as tmp:
+            vtln_allpass_case(synth.synth_audio(7001, 24000), tmp)
+        return
     if sys.argv[1:] == ["cmllr_units"]:
         with tempfile.TemporaryDirectory() as tmp:
             pcm = synth.synth_audio(7001, 24000)
@@ -587,6 +632,7 @@ def main():
         spk_case(pcm, small_model(feats, 7002), tmp)
         pre_case(feats, tmp)
         vtln_case(pcm, tmp)
+        vtln_allpass_case(pcm, tmp)
         modx_case(pcm, tmp)
         cmllr_case(pcm, small_model(feats, 7002), tmp)
         cmllr_units_case(pcm, small_model(feats, 7002), tmp)

@@ -7,6 +7,8 @@ Bars (BASELINE.json north_star):
   * GMM + LNA, parity mode (F64) on the reference's float64 features: LNA bytes identical
   * throughput mode (F32): float log-probs within 1e-4 relative; 2-byte codes within +-1
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -175,8 +177,31 @@ def test_vtln_module(engine, ref_vtln, variant, tmp_path):
         assert np.abs(feats - want).max() <= 2e-5, (variant, spk, np.abs(feats - want).max())
         got[spk] = feats
     assert np.abs(got["s1"] - got["other"]).max() > 0.1          # the warp does something
-    with pytest.raises(AkuGpuError, match="all-pass"):
-        engine.frontend_load_config_text(g["cfg_blin"].replace("type vtln", "type vtln\n  all-pass 1"))
+    with pytest.raises(AkuGpuError, match="lanczos_window and all-pass"):
+        engine.frontend_load_config_text(g["cfg_blin"].replace("type vtln", "type vtln\n  all-pass 1\n  lanczos_window 1"))
+
+
+@pytest.mark.parametrize("variant", ["blin", "slapt"])
+def test_vtln_all_pass(engine, variant, tmp_path):
+    """vtln with `all-pass 1` (VtlnModule::create_all_pass_blin_transform / _slapt_transform / set_all_pass_transform,
+    aku/FeatureModules.cc:1717-1904): the cepstral warp matrix is built on the host in double and applied by fe_vtln as
+    full coefficient rows; features within the front-end's usual bar of the reference's, warp per speaker."""
+    from aaltoasr_b200 import SpeakerConfig
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vtln_allpass.npz"))
+    engine.frontend_load_config_text(str(z["cfg_" + variant]))
+    spkc = str(tmp_path / "v.spkc")
+    open(spkc, "w").write(str(z["spkc_" + variant]))
+    sc = SpeakerConfig(engine)
+    sc.read_speaker_file(spkc)
+    got = {}
+    for spk in ("s1", "other", "s2", "s1"):
+        sc.set_speaker(spk)
+        feats, _ = engine.features(z["pcm"], dtype=np.float64)
+        want = z["feats_%s_%s" % (variant, spk)]
+        assert feats.shape == want.shape
+        assert np.abs(feats - want).max() <= 2e-5, (variant, spk, np.abs(feats - want).max())
+        got[spk] = feats
+    assert np.abs(got["s1"] - got["other"]).max() > 0.1
 
 
 @pytest.mark.parametrize("which", ["srnorm", "quanteq"])

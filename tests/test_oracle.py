@@ -184,6 +184,25 @@ def test_vtln_restatement_vs_reference(variant):
         assert got.shape == want.shape and np.abs(got - want).max() <= 2e-5, (variant, spk, np.abs(got - want).max())
 
 
+@pytest.mark.parametrize("variant", ["blin", "slapt"])
+def test_vtln_all_pass_restatement_vs_reference(variant):
+    """vtln with `all-pass 1` (aku/FeatureModules.cc:1717-1904): the warp as a matrix on the cepstrum of the spectrum (bilinear:
+    convolution powers of the all-pass series; SLAPT: the truncated exponential series of the parameter sequence), wrapped
+    in DCT / inverse DCT and applied as full coefficient rows -- against the reference's features for three speakers."""
+    from aaltoasr_b200 import parse_speaker_file
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vtln_allpass.npz"))
+    conf = parse_speaker_file(str(z["spkc_" + variant]))["speaker"]
+    P = oracle_np.Pipeline(str(z["cfg_" + variant]))
+    for spk in ("s1", "s2", "other"):
+        P.set_parameters("vtln", conf.get(spk, conf["default"])["vtln"])
+        got = P.run(z["pcm"])
+        want = z["feats_%s_%s" % (variant, spk)]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 2e-5, (variant, spk, np.abs(got - want).max())
+    assert np.abs(z["feats_%s_s1" % variant] - z["feats_%s_other" % variant]).max() > 0.1
+    with pytest.raises(ValueError, match="lanczos_window and all-pass"):
+        oracle_np.Pipeline(str(z["cfg_blin"]).replace("all-pass 1", "all-pass 1\n  lanczos_window 1"))
+
+
 @pytest.mark.parametrize("which,mod", [("srnorm", "srn"), ("quanteq", "qe")])
 def test_sr_norm_quanteq_restatement_vs_reference(which, mod):
     from aaltoasr_b200 import parse_speaker_file
