@@ -138,7 +138,7 @@ tc16_norm_replay(const float *__restrict__ sll, int64_t ldF, int64_t nf, const i
 // NCH == 0: streaming variant for wide expansions (full covariance: K = D(D+3)/2 + 2 = 821): A' = [Ah | Al] comes
 //           from an expansion kernel through TMA like B' = [Bh | Bl]; a ring stage = the same 64-wide k-block of the
 //           four halves (64 KB); `nkb` k-blocks per half, `tslots` stages.
-template <int NCH>
+template <int NCH, bool PAIR = true>
 __global__ void __launch_bounds__(tc16::THREADS, 1)
 gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int nkb, int tslots,
                 const int *__restrict__ range_begin,
@@ -363,6 +363,64 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (norm) norm_update(res, nMx, nR);
       }
     };
+    // Two slots at once: the same arithmetic in the same order as two process() calls, but both slots' maxima and
+    // arguments come first and the 32 exp2 are issued in ONE burst before either slot's tail (sum, carry, log, store,
+    // normaliser -- the branchy part).  process() leaves 16-wide bursts separated by ~200 instructions of tail and
+    // prologue; with four epilogue warps per scheduler that kept the XU pipe 67 % busy (profiles/r02_gmm_tc16_ncu_full.txt).
+    auto tail = [&](const float2 (&x)[8], float mx, float nml, bool first, bool last, int mt) {
+      float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        s0 = __fadd2_rn(s0, x[c]);
+        s1 = __fadd2_rn(s1, x[c + 1]);
+      }
+      float sum = (s0.x + s0.y) + (s1.x + s1.y);
+      if (!first) sum = fmaf(run_s, ex2f(fmaf(run_a, LOG2E, nml)), sum);
+      run_a = mx;
+      run_s = sum;
+      if (last && mt >= 0) {
+        const float res = fmaf(lg2f(sum), LN2, mx);
+        sll_f[(int64_t)(mt >> 2) * ldF] = res;
+        if (norm) norm_update(res, nMx, nR);
+      }
+    };
+    auto process2 = [&](const uint32_t (&rmA)[16], const uint32_t (&rcA)[16], int mtA, const uint32_t (&rmB)[16],
+                        const uint32_t (&rcB)[16], int mtB) {
+      float2 vA[8], vB[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        vA[c] = __ffma2_rn(make_float2(__uint_as_float(rcA[2 * c]), __uint_as_float(rcA[2 * c + 1])), make_float2(LO_INV, LO_INV),
+                           make_float2(__uint_as_float(rmA[2 * c]), __uint_as_float(rmA[2 * c + 1])));
+        vB[c] = __ffma2_rn(make_float2(__uint_as_float(rcB[2 * c]), __uint_as_float(rcB[2 * c + 1])), make_float2(LO_INV, LO_INV),
+                           make_float2(__uint_as_float(rmB[2 * c]), __uint_as_float(rmB[2 * c + 1])));
+      }
+      const bool firstA = (mtA & 2) != 0, lastA = (mtA & 1) != 0, firstB = (mtB & 2) != 0, lastB = (mtB & 1) != 0;
+      auto max16 = [](const float2 (&v)[8]) {
+        float m8[8], m4[4];
+#pragma unroll
+        for (int c = 0; c < 8; c++) m8[c] = fmaxf(v[c].x, v[c].y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) m4[c] = fmaxf(m8[c], m8[c + 4]);
+        return fmaxf(fmaxf(m4[0], m4[2]), fmaxf(m4[1], m4[3]));
+      };
+      float mxA = max16(vA), mxB = max16(vB);
+      if (!firstA) mxA = fmaxf(mxA, run_a);
+      if (!firstB) mxB = fmaxf(mxB, mxA);                       // what run_a is once slot A is done
+      const float nmlA = -mxA * LOG2E, nmlB = -mxB * LOG2E;
+      float2 xA[8], xB[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        xA[c] = __ffma2_rn(vA[c], make_float2(LOG2E, LOG2E), make_float2(nmlA, nmlA));
+        xB[c] = __ffma2_rn(vB[c], make_float2(LOG2E, LOG2E), make_float2(nmlB, nmlB));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        xA[c] = make_float2(ex2f(xA[c].x), ex2f(xA[c].y));
+        xB[c] = make_float2(ex2f(xB[c].x), ex2f(xB[c].y));
+      }
+      tail(xA, mxA, nmlA, firstA, lastA, mtA);
+      tail(xB, mxB, nmlB, firstB, lastB, mtB);
+    };
     static_assert(SLOTS_PER_WARP == 4 && EPI_GROUPS == 2, "the epilogue below handles four slots per warp and tile, two warp groups");
     // The two warp groups work on alternate tiles: while one group waits for its accumulators and loads them, the
     // other one keeps the MUFU / FMA pipes busy (all 16 warps on one tile left those pipes idle during every
@@ -380,8 +438,8 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       AKU_TMEM_LD16(r1, taddr + GR);
       AKU_TMEM_LD16(c1, taddr + GR + BN);
       AKU_TMEM_LD_WAIT();
-      process(r0, c0, mt.x);
-      process(r1, c1, mt.y);
+      if (PAIR) process2(r0, c0, mt.x, r1, c1, mt.y);
+      else { process(r0, c0, mt.x); process(r1, c1, mt.y); }
       AKU_TMEM_LD16(r0, taddr + 2 * GR);
       AKU_TMEM_LD16(c0, taddr + 2 * GR + BN);
       AKU_TMEM_LD16(r1, taddr + 3 * GR);
@@ -391,8 +449,8 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[group]);
-      process(r0, c0, mt.z);
-      process(r1, c1, mt.w);
+      if (PAIR) process2(r0, c0, mt.z, r1, c1, mt.w);
+      else { process(r0, c0, mt.z); process(r1, c1, mt.w); }
     }
     if (norm) {   // the four warps of a lane quarter merge their parts; one float2 per frame
       sM[warp - 4][lane] = nMx;
@@ -675,7 +733,7 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
     case 2: launch(gmm_tc16_kernel<2>); break;
     case 3: launch(gmm_tc16_kernel<3>); break;
     case 4: launch(gmm_tc16_kernel<4>); break;
-    case 5: launch(gmm_tc16_kernel<5>); break;
+    case 5: if (getenv("AKUGPU_TC16_EPI_OLD")) launch(gmm_tc16_kernel<5, false>); else launch(gmm_tc16_kernel<5>); break;
     case 6: launch(gmm_tc16_kernel<6>); break;
     case 7: launch(gmm_tc16_kernel<7>); break;
     case 8: launch(gmm_tc16_kernel<8>); break;
