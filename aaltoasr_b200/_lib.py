@@ -81,6 +81,10 @@ SYMBOLS = {
     "akugpu_scorer_in_use": (C.c_int, [C.c_void_p]),
     "akugpu_set_streaming": (C.c_int, [C.c_void_p, C.c_int]),
     "akugpu_stream_probe": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "akugpu_stream_open": (C.c_int, [C.c_void_p, C.c_double]),
+    "akugpu_stream_close": (C.c_int, [C.c_void_p]),
+    "akugpu_stream_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.POINTER(C.c_float))]),
+    "akugpu_stream_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "akugpu_pipe_rates": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 

@@ -13,10 +13,15 @@ using namespace akugpu;
 
 static std::string g_create_err;
 
-#define API_BEGIN                                             \
+// API_BEGIN_KEEP: entry points that may be served by the resident scorer (gmm_resident.cu); every other entry point
+// ends a running resident kernel first, so that the device is whole before anything else is launched or allocated.
+#define API_BEGIN_KEEP                                        \
   if (!ctx) return AKUGPU_E_ARG;                              \
   try {                                                       \
     AKU_CUDA(cudaSetDevice(ctx->device));
+#define API_BEGIN                                             \
+  API_BEGIN_KEEP                                              \
+    session_quiesce(ctx);
 #define API_END                                               \
     return AKUGPU_OK;                                         \
   } catch (const Error &e) {                                  \
@@ -327,6 +332,7 @@ void akugpu_destroy(akugpu_ctx *ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  session_destroy(ctx);       // a resident kernel would hold the device synchronisation until its idle timer
   cudaDeviceSynchronize();
   for (auto &p : ctx->timer.pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
   for (auto e : ctx->timer.pool) cudaEventDestroy(e);
@@ -836,6 +842,10 @@ static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, in
   // streaming regime (the decoder's per-frame feed): one launch, features in the parameter block, results and the
   // completion flag straight into mapped host memory.  false = a feature left the fp16 range: the general path below
   // redoes the call (and finds the same overflow itself)
+  if (session_applicable(ctx, precision, n_frames, feats, out) &&
+      session_score(ctx, feats, feats_f64, n_frames, (float *)out, logmode ? 1 : 0, logmode ? (float)log(tiny) : 0.f))
+    return;
+  session_quiesce(ctx);
   if (stream_applicable(ctx, precision, n_frames) &&
       stream_score(ctx, feats, feats_f64, n_frames, (float *)out, logmode ? 1 : 0, logmode ? (float)log(tiny) : 0.f))
     return;
@@ -884,7 +894,7 @@ static void gmm_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64, in
 
 int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)
 {
-  API_BEGIN
+  API_BEGIN_KEEP
   gmm_score_impl(ctx, feats, feats_f64, n_frames, precision, out, 0.0);
   API_END
 }
@@ -892,7 +902,7 @@ int akugpu_gmm_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
 int akugpu_gmm_logprobs(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, int precision, double tiny,
                         float *out)
 {
-  API_BEGIN
+  API_BEGIN_KEEP
   if (!(tiny > 0)) throw Error(AKUGPU_E_ARG, "tiny must be > 0 (decode-stream uses 1e-30, phone_probs 1e-50)");
   gmm_score_impl(ctx, feats, feats_f64, n_frames, precision, out, tiny);
   API_END
@@ -986,6 +996,65 @@ int akugpu_set_streaming(akugpu_ctx *ctx, int enable)
   API_BEGIN
   ctx->streaming_enabled = enable != 0;
   API_END
+}
+
+int akugpu_stream_open(akugpu_ctx *ctx, double idle_ms)
+{
+  API_BEGIN
+  require_model(ctx);
+  if (!(idle_ms > 0)) idle_ms = 100.0;
+  StreamState &st = ctx->stream_state;
+  st.session_idle_ms = idle_ms;
+  st.session_want = true;
+  if (!session_applicable(ctx, AKUGPU_F32, 1, nullptr, nullptr)) {
+    st.session_want = false;
+    throw Error(AKUGPU_E_STATE, "the resident scorer serves diagonal models of the fp16x2 tensor-core scorer (no clustering, no model-level CMLLR, no hybrid split)");
+  }
+  session_launch(ctx);
+  API_END
+}
+
+int akugpu_stream_logprobs(akugpu_ctx *ctx, const float *feats, int n_frames, double tiny, const float **rows)
+{
+  API_BEGIN_KEEP
+  require_model(ctx);
+  if (!feats || !rows || n_frames < 1 || n_frames > STREAM_MAX_FRAMES) throw Error(AKUGPU_E_ARG, "akugpu_stream_logprobs: 1..16 frames of host float features, rows != NULL");
+  if (!ctx->stream_state.session_want) throw Error(AKUGPU_E_STATE, "akugpu_stream_logprobs: no session (akugpu_stream_open)");
+  const bool logmode = tiny > 0;
+  const float floor_at = logmode ? (float)log(tiny) : 0.f;
+  if (stream_applicable(ctx, AKUGPU_F32, n_frames) && session_score(ctx, feats, 0, n_frames, nullptr, logmode ? 1 : 0, floor_at)) {
+    *rows = session_rows(ctx);
+  } else {
+    // more frames than the model allows per message, or a feature outside the fp16 range: the general path, into a
+    // buffer of the context
+    ctx->stream_fallback.resize((size_t)n_frames * ctx->hm.S);
+    gmm_score_impl(ctx, feats, 0, n_frames, AKUGPU_F32, ctx->stream_fallback.data(), logmode ? tiny : 0.0);
+    *rows = ctx->stream_fallback.data();
+  }
+  API_END
+}
+
+int akugpu_stream_close(akugpu_ctx *ctx)
+{
+  API_BEGIN          /* ends the kernel */
+  ctx->stream_state.session_want = false;
+  API_END
+}
+
+int akugpu_stream_stats(akugpu_ctx *ctx, int64_t out[8])
+{
+  if (!ctx || !out) return AKUGPU_E_ARG;
+  const StreamState &st = ctx->stream_state;
+  out[0] = st.session_want ? 1 : 0;
+  out[1] = st.session_live ? 1 : 0;
+  out[2] = st.session_launches;
+  out[3] = st.session_calls;
+  const volatile unsigned int *f = reinterpret_cast<const volatile unsigned int *>(st.host);
+  out[4] = f ? f[4] : 0;
+  out[5] = f ? f[5] : 0;
+  out[6] = f ? f[6] : 0;
+  out[7] = f ? f[7] : 0;
+  return AKUGPU_OK;
 }
 
 int akugpu_stream_probe(akugpu_ctx *ctx, double out[8])

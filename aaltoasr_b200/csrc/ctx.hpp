@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <chrono>
 #include <memory>
 #include "../../include/akugpu.h"
 
@@ -169,6 +170,7 @@ struct PackedTC16 {
   std::map<int, std::pair<int, std::shared_ptr<DevBuf>>> ranges;
   std::vector<double> h_center;                      // host copy of the feature centre (the streaming scorer centres on the host)
   alignas(64) unsigned char map_b[128];              // CUtensorMap of B', encoded once per model (streaming scorer)
+  alignas(64) unsigned char map_b64[128];            // the same rows as 32-column boxes with SWIZZLE_64B (resident scorer)
   bool map_ready = false;
 };
 
@@ -177,8 +179,16 @@ constexpr int STREAM_MAX_FRAMES = 16;     // measured (tests/test_gpu_stream.py)
 struct StreamState {
   void *host = nullptr, *dev_view = nullptr;
   size_t bytes = 0;
-  DevBuf cnt;
+  DevBuf cnt, relay;          // relay: {command word (16 B) | pad | features of the call} the polling CTA hands to the others
   unsigned int seq = 0;
+  // resident scorer (gmm_resident.cu): a kernel that stays on the device between calls, parameter image in shared memory
+  bool session_want = false, session_live = false;
+  double session_idle_ms = 100.0;
+  cudaStream_t session_stream = nullptr;
+  void *pkt_host = nullptr, *pkt_dev = nullptr;      // one 512-byte command packet per CTA, pinned + mapped
+  int session_grid = 0;
+  int64_t session_launches = 0, session_calls = 0;
+  std::chrono::steady_clock::time_point session_last;
 };
 
 // ---------------------------------------------------------------------------------
@@ -265,6 +275,7 @@ struct akugpu_ctx {
   bool tc16_suspended = false;   // set while a call is redone with the bf16x3 kernel after an fp16 range overflow
   bool streaming_enabled = true; // small calls (<= STREAM_MAX_FRAMES frames) of the decoder feed take gmm_stream_kernel
   akugpu::StreamState stream_state;
+  std::vector<float> stream_fallback;   // akugpu_stream_logprobs: rows of a call the resident scorer could not serve
 
   akugpu::HostModel hm;
   bool have_model = false;

@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
+#include "stream_common.cuh"
 #include <math.h>
 #include <string.h>
 #if defined(__x86_64__)
@@ -29,15 +30,6 @@
 
 namespace akugpu {
 
-namespace tcs {
-constexpr int BM = 128, BK = 64, GR = 16, SLOTS = BM / GR;
-constexpr uint32_t B_BLOCK = BM * BK * 2;          // 16 KB: one k-block of a component tile of B'
-constexpr int THREADS = 384;                       // warp 0 TMA, warp 1 MMA, warps 4-11 epilogue (two groups of four)
-constexpr int EPI_THREADS = 256, GROUP_THREADS = 128;
-constexpr int MAX_TSLOTS = 4;
-constexpr float LO_INV = 1.f / 2048.f, LO_SCALE = 2048.f;
-constexpr int XS_DIM = 40;                         // centred features of up to NF frames x 40 dims travel as kernel parameters
-}  // namespace tcs
 
 template <int NF> struct StreamX { float v[NF * tcs::XS_DIM]; };      // 2.5 KB (NF = 16) / 5 KB (NF = 32: large-parameter launch)
 
@@ -261,6 +253,7 @@ gmm_stream_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
       *cnt = 0u;
       __threadfence_system();
       flags[0] = seq;
+      __threadfence_system();
     }
   }
 }
@@ -302,7 +295,7 @@ static int stream_tslots(int KB, int NF, int D)
   return (int)std::min<size_t>(tcs::MAX_TSLOTS, (budget - fixed) / slot);
 }
 
-static void stream_buffers(akugpu_ctx *ctx, int S)
+void stream_buffers(akugpu_ctx *ctx, int S)
 {
   StreamState &st = ctx->stream_state;
   const size_t need = 256 + (size_t)STREAM_MAX_FRAMES * 64 * sizeof(float) + (size_t)STREAM_MAX_FRAMES * S * sizeof(float);
@@ -313,6 +306,16 @@ static void stream_buffers(akugpu_ctx *ctx, int S)
   AKU_CUDA(cudaHostGetDevicePointer(&st.dev_view, st.host, 0));
   st.bytes = need;
   if (!st.cnt.p) { st.cnt.reserve(16); AKU_CUDA(cudaMemsetAsync(st.cnt.p, 0, 16, ctx->stream)); AKU_CUDA(cudaStreamSynchronize(ctx->stream)); }
+}
+
+void stream_map_ready(akugpu_ctx *ctx)
+{
+  PackedTC16 &p = ctx->ptc16;
+  if (p.map_ready) return;
+  tc_make_map(reinterpret_cast<CUtensorMap *>(p.map_b), p.B.p, (uint64_t)p.n_tiles * tcs::BM, (uint64_t)p.Kp, true);
+  // the last, half-filled k-block of a row (NCH odd) as a 32-column box with the 64-byte swizzle (gmm_resident.cu)
+  tc_make_map(reinterpret_cast<CUtensorMap *>(p.map_b64), p.B.p, (uint64_t)p.n_tiles * tcs::BM, (uint64_t)p.Kp, true, 32);
+  p.map_ready = true;
 }
 
 bool stream_applicable(akugpu_ctx *ctx, int precision, int64_t n_frames)
@@ -372,10 +375,7 @@ static bool stream_score_impl(akugpu_ctx *ctx, const void *feats, int feats_f64,
   StreamState &st = ctx->stream_state;
   const int S = ctx->hm.S, D = p.D, nf = (int)n_frames;
   stream_buffers(ctx, S);
-  if (!p.map_ready) {
-    tc_make_map(reinterpret_cast<CUtensorMap *>(p.map_b), p.B.p, (uint64_t)p.n_tiles * tcs::BM, (uint64_t)p.Kp, true);
-    p.map_ready = true;
-  }
+  stream_map_ready(ctx);
   int ysplit = 1;
   const int *ranges = tc_tile_ranges(ctx, p.n_tiles, p.clean, p.ranges, std::min(p.n_tiles, ctx->sm_count), ysplit);
   constexpr int NF = 16;

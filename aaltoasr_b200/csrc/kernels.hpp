@@ -47,6 +47,13 @@ void host_lu_inverse(const std::vector<double> &M, int n, std::vector<double> &i
 bool stream_applicable(akugpu_ctx *ctx, int precision, int64_t n_frames);
 bool stream_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, float *out, int use_floor, float floor_at);
 void stream_probe(akugpu_ctx *ctx, double out[8]);
+// gmm_resident.cu (resident scorer: a kernel that stays on the device between calls, parameter image in shared memory)
+bool session_applicable(akugpu_ctx *ctx, int precision, int64_t n_frames, const void *feats, const void *out);
+bool session_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_frames, float *out, int use_floor, float floor_at);
+void session_launch(akugpu_ctx *ctx);
+void session_quiesce(akugpu_ctx *ctx);
+void session_destroy(akugpu_ctx *ctx);
+const float *session_rows(akugpu_ctx *ctx);      // the pinned result rows of the last session call
 
 // lna_kernels.cu
 // norm_scratch: where a normaliser pass of its own writes (default: ctx->d_norm)

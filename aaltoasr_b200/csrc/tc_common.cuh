@@ -39,6 +39,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// The same for SWIZZLE_64B: rows of 64 B (32 fp16), SBO = 512 B (8 rows x 64 B) >> 4, layout type 4.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A/B format at bits 7/10 (0 = F16, 1 = BF16),
 // K-major both, N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t umma_idesc(int m, int n, bool bf16) {
@@ -77,7 +81,8 @@ __device__ __forceinline__ bool elect_one()
 }  // namespace tc
 
 // host helpers implemented in gmm_tc.cu
-void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16);   // 128 x 64 boxes, SWIZZLE_128B
+// boxes of 128 rows x 64 columns with SWIZZLE_128B (default) or 128 x 32 with SWIZZLE_64B
+void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16, int box_cols = 64);
 double tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<double> &cen, std::vector<double> &theta,
                           std::vector<double> &gconst, std::vector<double> *q_of_gauss);
 // Largest cancelling magnitude q the expanded form is trusted with: predicted log-likelihood error 4e-7 * q <= 8e-5.

@@ -119,6 +119,29 @@ class AkuGpu:
     def set_streaming(self, enable=True):
         self._ck(self._lib.akugpu_set_streaming(self._h, 1 if enable else 0))
 
+    def stream_open(self, idle_ms=100.0):
+        """Starts the resident scorer (akugpu_stream_open): small host-buffer calls of gmm_score / gmm_logprobs become
+        messages to a kernel that keeps the parameter image in shared memory; any other call ends it."""
+        self._ck(self._lib.akugpu_stream_open(self._h, float(idle_ms)))
+
+    def stream_logprobs(self, feats, tiny=1e-30):
+        """akugpu_stream_logprobs: 1..16 rows of host float32 features -> a VIEW of the pinned result rows [F x S]
+        (valid until the next call on this context)."""
+        x = np.ascontiguousarray(feats, dtype=np.float32)
+        rows = C.POINTER(C.c_float)()
+        self._ck(self._lib.akugpu_stream_logprobs(self._h, C.c_void_p(x.ctypes.data), int(x.shape[0]), float(tiny), C.byref(rows)))
+        return np.ctypeslib.as_array(rows, shape=(int(x.shape[0]), self.num_states))
+
+    def stream_close(self):
+        self._ck(self._lib.akugpu_stream_close(self._h))
+
+    def stream_stats(self):
+        out = (C.c_int64 * 8)()
+        self._ck(self._lib.akugpu_stream_stats(self._h, out))
+        return {"want": bool(out[0]), "live": bool(out[1]), "launches": int(out[2]), "calls": int(out[3]),
+                "device_ns_features": int(out[4]), "device_ns_call": int(out[5]),
+                "device_ns_stored": int(out[6]), "device_ns_fenced": int(out[7])}
+
     def stream_probe(self):
         """Streaming-regime rates for the loaded model (akugpu_stream_probe)."""
         out = (C.c_double * 8)()

@@ -293,6 +293,29 @@ int akugpu_set_streaming(akugpu_ctx *ctx, int enable);
  * out[5] = SM clock (MHz) right after the isolated launches (an idle GPU clocks down between them); out[6] = seconds per
  * launch in a train of 200 back-to-back launches (GPU busy, image L2-resident); out[7] = SM clock (MHz) after the train. */
 int akugpu_stream_probe(akugpu_ctx *ctx, double out[8]);
+/* Resident scorer for a stream decoder's session (decoder/decode-stream.cc:150-207: one Toolbox + one acoustic model
+ * for the life of the stream, one scoring call per frame).  akugpu_stream_open starts ONE kernel that stays on the
+ * device: each of its CTAs keeps its share of the parameter image in shared memory (the config-2 model, 5000 x 16 =
+ * 30.7 MB, fits the 148 SMs whole; of a larger model the tiles that do not fit are streamed from L2 per call).  While
+ * it runs, calls of akugpu_gmm_score (F32) / akugpu_gmm_logprobs with host buffers and at most 16 frames are MESSAGES to
+ * that kernel through pinned, mapped memory -- no launch and no CUDA call on the path of a frame -- and return the
+ * bits the launch-per-call scorer returns.  The kernel ends when it is told to (akugpu_stream_close, and ANY other
+ * entry point of this context sends that message first: nothing of the library runs beside it) or by itself after
+ * idle_ms without a call (<= 0: 100 ms); the next eligible call starts it again.  Other CUDA work of the process on
+ * the same device waits for that moment too: open a session on a GPU the decoder owns.  Models the streaming scorer
+ * does not serve (akugpu_set_streaming) are refused with AKUGPU_E_STATE.
+ * akugpu_stream_stats: out[0] = session requested, out[1] = kernel believed to be running, out[2] = kernel launches,
+ * out[3] = calls served by it; out[4] / out[5] = the last call as the last CTA to finish saw it, in nanoseconds of the
+ * device's timer: command seen -> A' built, command seen -> every CTA done (host-side latency minus out[5] is PCIe and
+ * polling); out[6] / out[7] = command seen -> that CTA's results stored / fenced. */
+int akugpu_stream_open(akugpu_ctx *ctx, double idle_ms);
+/* The per-frame call of an open session without a copy and without pointer queries: feats = n_frames (1..16) rows of
+ * HOST float features, *rows = [n_frames][n_states] floats of (float) log(max(likelihood, tiny)) (tiny <= 0: the plain
+ * log-likelihoods) in pinned memory of the context, valid until its next call -- what decoder/decode-stream.cc:191-207
+ * computes into its vector before Toolbox::set_one_frame.  AKUGPU_E_STATE without akugpu_stream_open. */
+int akugpu_stream_logprobs(akugpu_ctx *ctx, const float *feats, int n_frames, double tiny, const float **rows);
+int akugpu_stream_close(akugpu_ctx *ctx);
+int akugpu_stream_stats(akugpu_ctx *ctx, int64_t out[8]);
 
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):
  * out[0] FFMA, out[1] FFMA2 (counted as 2 lane-ops), out[2] DFMA, out[3] MUFU.EX2 with constant

@@ -161,3 +161,149 @@ def test_streaming_scorer_full_size_models(engine, feats20s, S, K, seed):
         print("streaming scorer %d x %d, F = %d: %.1f us per akugpu_gmm_logprobs call (host buffers, ctypes loop); general path %.1f us"
               % (S, K, F, us, us_general))
         assert us < 1000.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# resident scorer (gmm_resident_kernel): the parameter image stays in shared memory, a call is a message
+def _session_pair(engine, fn):
+    """fn() through one launch per call, then through the resident kernel: (launch result, session result, launches
+    during the session call)."""
+    engine.stream_close()
+    a = fn()
+    engine.stream_open(200.0)
+    try:
+        fn()                                   # the first message of a session
+        l0 = engine.launch_count()
+        b = fn()
+        n = engine.launch_count() - l0
+    finally:
+        engine.stream_close()
+    return a, b, n
+
+
+@pytest.mark.parametrize("F", [1, 2, 7, 9, 16])
+def test_resident_scorer_returns_the_bits_of_the_launch_path_small_model(engine, ref_small, F):
+    g = ref_small
+    load_model(engine, g["model"])
+    assert engine.scorer_in_use() == 3
+    x = g["feats"][3:3 + F].astype(np.float32)
+    a, b, n = _session_pair(engine, lambda: engine.gmm_score(x, precision=F32))
+    assert n == 0                                                 # no launch on the path of a call
+    assert np.array_equal(a, b)
+    assert np.abs(b - np.log(g["lik"][3:3 + F])).max() <= 3e-5    # the reference's likelihoods
+    a, b, n = _session_pair(engine, lambda: engine.gmm_logprobs(g["feats"][3:3 + F], precision=F32, tiny=1e-30))    # doubles in
+    assert n == 0 and np.array_equal(a, b)
+
+
+def test_resident_scorer_lifecycle(engine, ref_small):
+    """Another entry point ends the kernel and the next small call starts it again; the idle timer ends it too; a
+    feature outside the fp16 range sends the call down the general path; device buffers are not served by it."""
+    import torch
+    g = ref_small
+    load_model(engine, g["model"])
+    x = g["feats"][:5].astype(np.float32).copy()
+    x[2] += 40.0                                                  # below the floor of the decoder feed
+    engine.stream_close()
+    want = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)
+    s0 = engine.stream_stats()
+    engine.stream_open(30.0)
+    try:
+        st = engine.stream_stats()
+        assert st["want"] and st["live"] and st["launches"] == s0["launches"] + 1
+        got = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)
+        assert np.array_equal(got, want) and (got[2] == np.float32(np.log(1e-30))).all()
+        assert engine.stream_stats()["calls"] == s0["calls"] + 1
+        # any other entry point: the kernel is told to end first, the device is whole
+        rec = engine.gmm_lna(g["feats"], precision=F64, lnabytes=2)
+        assert np.array_equal(rec.reshape(-1), g["lna2"][5:])
+        assert not engine.stream_stats()["live"]
+        got = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)   # started again by the call
+        st = engine.stream_stats()
+        assert np.array_equal(got, want) and st["live"] and st["launches"] == s0["launches"] + 2
+        # idle timer (30 ms): the kernel is gone, the call notices and starts another
+        time.sleep(0.3)
+        got = engine.gmm_logprobs(x[:1], precision=F32, tiny=1e-30)
+        assert np.array_equal(got, want[:1]) and engine.stream_stats()["launches"] == s0["launches"] + 3
+        for i in range(200):                                      # a per-frame loop, every answer checked
+            r = engine.gmm_logprobs(x[i % 5:i % 5 + 1], precision=F32, tiny=1e-30)
+            assert np.array_equal(r[0], want[i % 5])
+        assert engine.stream_stats()["launches"] == s0["launches"] + 3
+        # out of the fp16 range: general path (bf16x3 redo), then the session again
+        bad = x.copy()
+        bad[1, 3] = 3.0e4
+        r = engine.gmm_score(bad, precision=F32)
+        assert np.isfinite(r).all() and r[1].max() < -1e5
+        assert np.array_equal(engine.gmm_logprobs(x, precision=F32, tiny=1e-30), want)
+        # device buffers: one launch per call beside a closed kernel
+        xd = torch.from_numpy(x).cuda()
+        od = torch.empty((5, engine.num_states), dtype=torch.float32, device="cuda")
+        engine.gmm_logprobs(xd, precision=F32, tiny=1e-30, out=od)
+        assert np.array_equal(od.cpu().numpy(), want) and not engine.stream_stats()["live"]
+    finally:
+        engine.stream_close()
+    assert not engine.stream_stats()["want"] and not engine.stream_stats()["live"]
+
+
+def test_resident_scorer_refuses_models_it_does_not_serve(engine, ref_edge):
+    load_model(engine, ref_edge["model"])                         # hybrid: ill-conditioned states on the FP32 pipe
+    with pytest.raises(Exception):
+        engine.stream_open(50.0)
+    assert not engine.stream_stats()["want"]
+
+
+@pytest.mark.parametrize("S,K,seed", [(5000, 16, 2999), (10000, 32, 4999)])
+def test_resident_scorer_full_size_models(engine, feats20s, S, K, seed):
+    """Config-2 model: the whole image is resident (5 tiles per CTA); config-4 model: 3 resident tiles + a ring for the
+    other 14.  Every frame of a per-frame loop carries the bits of the launch path; latency per call reported."""
+    model = synth.synth_diag_model(seed, feats20s, S, K)
+    load_model(engine, model)
+    assert engine.scorer_in_use() == 3
+    idx = np.arange(0, 2496, 48)
+    x = feats20s[idx].astype(np.float32)
+    engine.stream_close()
+    rows = np.stack([engine.gmm_logprobs(x[i:i + 1], precision=F32, tiny=1e-30)[0] for i in range(len(idx))])
+    blk = engine.gmm_logprobs(x[:7], precision=F32, tiny=1e-30)
+    want = np.log(np.maximum(oracle_np.state_likelihoods(model, x[:2].astype(np.float64)), 1e-30))
+    assert np.abs(rows[:2] - want).max() <= 4e-5
+    engine.stream_open(200.0)
+    try:
+        l0 = engine.launch_count()
+        got = np.stack([engine.gmm_logprobs(x[i:i + 1], precision=F32, tiny=1e-30)[0] for i in range(len(idx))])
+        assert np.array_equal(got, rows)
+        if K == 16:
+            assert np.array_equal(engine.gmm_logprobs(x[:7], precision=F32, tiny=1e-30), blk)
+        assert engine.launch_count() == l0
+        import ctypes as C
+        lib, h = engine._lib, engine._h
+        for F in ((1, 4, 8, 16) if K == 16 else (1, 4, 8)):
+            xb = np.ascontiguousarray(x[:F])
+            ob = np.empty((F, S), dtype=np.float32)
+            px, po = C.c_void_p(xb.ctypes.data), C.c_void_p(ob.ctypes.data)
+            call = lambda: lib.akugpu_gmm_logprobs(h, px, 0, F, 0, C.c_double(1e-30), po)
+            for _ in range(200):
+                assert call() == 0
+            t0 = time.perf_counter()
+            n = 5000
+            for _ in range(n):
+                call()
+            us = 1e6 * (time.perf_counter() - t0) / n
+            # the zero-copy entry point: a view of the pinned rows
+            view = engine.stream_logprobs(xb, tiny=1e-30)
+            assert np.array_equal(view, ob)
+            rows_p = C.POINTER(C.c_float)()
+            vcall = lambda: lib.akugpu_stream_logprobs(h, px, F, C.c_double(1e-30), C.byref(rows_p))
+            for _ in range(200):
+                assert vcall() == 0
+            t0 = time.perf_counter()
+            for _ in range(n):
+                vcall()
+            us_view = 1e6 * (time.perf_counter() - t0) / n
+            print("resident scorer %d x %d, F = %d: %.2f us per akugpu_stream_logprobs call (pinned rows returned, ctypes loop)" % (S, K, F, us_view))
+            st = engine.stream_stats()
+            print("resident scorer %d x %d, F = %d: %.2f us per akugpu_gmm_logprobs call (host buffers, ctypes loop); on the device: "
+                  "%.2f us command -> A', %.2f -> this CTA's results stored, %.2f -> every CTA's, %.2f us command -> rows in host memory"
+                  % (S, K, F, us, st["device_ns_features"] / 1e3, st["device_ns_stored"] / 1e3, st["device_ns_fenced"] / 1e3, st["device_ns_call"] / 1e3))
+            assert us < 500.0
+        assert engine.launch_count() == l0
+    finally:
+        engine.stream_close()
