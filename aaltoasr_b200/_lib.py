@@ -83,6 +83,7 @@ SYMBOLS = {
     "akugpu_stream_probe": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "akugpu_stream_open": (C.c_int, [C.c_void_p, C.c_double]),
     "akugpu_stream_close": (C.c_int, [C.c_void_p]),
+    "akugpu_stream_latency": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "akugpu_stream_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.POINTER(C.c_float))]),
     "akugpu_stream_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "akugpu_pipe_rates": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

@@ -8,6 +8,7 @@
 #include <fstream>
 #include <sstream>
 #include <mutex>
+#include <chrono>
 
 using namespace akugpu;
 
@@ -1031,6 +1032,33 @@ int akugpu_stream_logprobs(akugpu_ctx *ctx, const float *feats, int n_frames, do
     gmm_score_impl(ctx, feats, 0, n_frames, AKUGPU_F32, ctx->stream_fallback.data(), logmode ? tiny : 0.0);
     *rows = ctx->stream_fallback.data();
   }
+  API_END
+}
+
+int akugpu_stream_latency(akugpu_ctx *ctx, const float *feats, int n_frames, double tiny, int n_calls, double out_us[4])
+{
+  API_BEGIN_KEEP
+  require_model(ctx);
+  if (!feats || !out_us || n_frames < 1 || n_calls < 1) throw Error(AKUGPU_E_ARG, "akugpu_stream_latency: bad arguments");
+  std::vector<double> us((size_t)n_calls);
+  std::vector<float> scratch((size_t)n_frames * ctx->hm.S);
+  const bool logmode = tiny > 0;
+  const float floor_at = logmode ? (float)log(tiny) : 0.f;
+  for (int i = 0; i < n_calls; i++) {
+    const auto t0 = std::chrono::steady_clock::now();
+    // what akugpu_stream_logprobs does inside an open session; one launch per call (akugpu_gmm_logprobs) otherwise
+    if (!(ctx->stream_state.session_want && n_frames <= STREAM_MAX_FRAMES && stream_applicable(ctx, AKUGPU_F32, n_frames) &&
+          session_score(ctx, feats, 0, n_frames, nullptr, logmode ? 1 : 0, floor_at)))
+      gmm_score_impl(ctx, feats, 0, n_frames, AKUGPU_F32, scratch.data(), logmode ? tiny : 0.0);
+    us[(size_t)i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  }
+  double sum = 0;
+  for (double v : us) sum += v;
+  std::sort(us.begin(), us.end());
+  out_us[0] = sum / n_calls;
+  out_us[1] = us[(size_t)(n_calls / 2)];
+  out_us[2] = us[(size_t)std::min<int64_t>(n_calls - 1, (int64_t)(0.99 * n_calls))];
+  out_us[3] = us.back();
   API_END
 }
 

@@ -132,6 +132,13 @@ class AkuGpu:
         self._ck(self._lib.akugpu_stream_logprobs(self._h, C.c_void_p(x.ctypes.data), int(x.shape[0]), float(tiny), C.byref(rows)))
         return np.ctypeslib.as_array(rows, shape=(int(x.shape[0]), self.num_states))
 
+    def stream_latency(self, feats, tiny=1e-30, n_calls=2000):
+        """akugpu_stream_latency: microseconds per per-frame-loop call, timed inside the library."""
+        x = np.ascontiguousarray(feats, dtype=np.float32)
+        out = (C.c_double * 4)()
+        self._ck(self._lib.akugpu_stream_latency(self._h, C.c_void_p(x.ctypes.data), int(x.shape[0]), float(tiny), int(n_calls), out))
+        return {"mean_us": out[0], "median_us": out[1], "p99_us": out[2], "max_us": out[3]}
+
     def stream_close(self):
         self._ck(self._lib.akugpu_stream_close(self._h))
 

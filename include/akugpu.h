@@ -315,6 +315,11 @@ int akugpu_stream_open(akugpu_ctx *ctx, double idle_ms);
  * computes into its vector before Toolbox::set_one_frame.  AKUGPU_E_STATE without akugpu_stream_open. */
 int akugpu_stream_logprobs(akugpu_ctx *ctx, const float *feats, int n_frames, double tiny, const float **rows);
 int akugpu_stream_close(akugpu_ctx *ctx);
+/* Measurement aid: n_calls per-frame-loop calls on the same n_frames rows of host float features, each timed on the host
+ * (steady clock) inside the library, i.e. without the caller's own call overhead: out_us = {mean, median, 99th
+ * percentile, maximum} microseconds per call.  Inside an open session a call is what akugpu_stream_logprobs does;
+ * otherwise what akugpu_gmm_logprobs (tiny > 0) / akugpu_gmm_score does with host buffers. */
+int akugpu_stream_latency(akugpu_ctx *ctx, const float *feats, int n_frames, double tiny, int n_calls, double out_us[4]);
 int akugpu_stream_stats(akugpu_ctx *ctx, int64_t out[8]);
 
 /* Micro-benchmarks of the issue pipes the scorer depends on (lane-ops per second):

@@ -13,7 +13,7 @@
 constexpr int PKT = 256;   // bytes of a CTA's packet: 8 sectors of {7 floats, tag}
 
 __global__ void mailbox2_kernel(const unsigned *pk, float *out, float *gres, volatile unsigned *done, unsigned *cnt, int own_line,
-                                int completion, int nres, unsigned n_calls)
+                                int completion, int nres, unsigned n_calls, unsigned *errs)
 {
   __shared__ unsigned s_seq;
   __shared__ float s_x[64];
@@ -33,6 +33,11 @@ __global__ void mailbox2_kernel(const unsigned *pk, float *out, float *gres, vol
         if (ok) { if (lane == 0) s_seq = t0; break; }
       }
       if (lane < 12) { s_x[lane * 4] = __uint_as_float(v.x); s_x[lane * 4 + 1] = __uint_as_float(v.y); s_x[lane * 4 + 2] = __uint_as_float(v.z); }
+      if (lane < 12) {   // payload word j of a sector must be (float)(tag + j)
+        const int j0 = (lane & 1) ? 4 : 0;
+        const float want = (float)(s_seq + j0);
+        if (__uint_as_float(v.x) != want || __uint_as_float(v.y) != want + 1.f || __uint_as_float(v.z) != want + 2.f) atomicAdd(errs, 1u);
+      }
     }
     __syncthreads();
     last = s_seq;
@@ -74,6 +79,8 @@ int main()
   unsigned *cnt;
   float *gres;
   cudaMalloc(&cnt, 16);
+  unsigned *errs;
+  cudaMalloc(&errs, 16);
   cudaMalloc(&gres, 1 << 20);
   cudaStream_t st;
   cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
@@ -82,26 +89,38 @@ int main()
   const unsigned N = 3000;
   for (int grid : {1, 16, 148})
     for (int own = 0; own < 2; own++)
-      for (int completion = 0; completion < 3; completion++) {
-        if (grid == 148 && !own) continue;       // known: 400 us
+      for (int wmode = 0; wmode < 3; wmode++) {
+        const int completion = 1;
+        if (!own) continue;
         const int nres = 36;                     // 148 x 36 floats ~ 21 KB of results
         memset(h, 0, 4096 + 148 * PKT);
         cudaMemset(cnt, 0, 16);
+        cudaMemset(errs, 0, 16);
         cudaDeviceSynchronize();
-        mailbox2_kernel<<<grid, 128, 0, st>>>((const unsigned *)(d + 4096), (float *)(d + (1 << 20)), gres, (volatile unsigned *)d, cnt, own, completion, nres, N);
+        mailbox2_kernel<<<grid, 128, 0, st>>>((const unsigned *)(d + 4096), (float *)(d + (1 << 20)), gres, (volatile unsigned *)d, cnt, own, completion, nres, N, errs);
         bool ok = true;
         double worst = 0, host_write = 0;
         auto t0 = std::chrono::steady_clock::now();
         for (unsigned c = 1; c <= N && ok; c++) {
           auto a = std::chrono::steady_clock::now();
           const int npk = own ? grid : 1;
+          alignas(64) unsigned tmpl[64];
+          for (int s = 0; s < 6; s++) { for (int k = 0; k < 7; k++) { float f = (float)(c + k); memcpy(&tmpl[s * 8 + k], &f, 4); } tmpl[s * 8 + 7] = c; }
           for (int b = 0; b < npk; b++) {
             unsigned *p = h_pk + (size_t)b * (PKT / 4);
-            for (int s = 0; s < 6; s++) {
-              for (int k = 0; k < 7; k++) { float f = (float)(c + k); memcpy(&p[s * 8 + k], &f, 4); }
-              p[s * 8 + 7] = c;                  // the sector's tag, after its payload (x86: stores stay in order)
+            if (wmode == 0) {
+              for (int s = 0; s < 6; s++) {
+                memcpy(p + s * 8, tmpl + s * 8, 28);
+                __asm__ __volatile__("" ::: "memory");
+                ((volatile unsigned *)p)[s * 8 + 7] = c;                  // the sector's tag, after its payload (x86: stores stay in order)
+              }
+            } else if (wmode == 1) {   // two 16-byte stores per sector, the tag in the second
+              for (int s = 0; s < 12; s++) _mm_store_si128((__m128i *)(p + s * 4), _mm_load_si128((const __m128i *)(tmpl + s * 4)));
+            } else {                   // non-temporal: full 64-byte lines through the write-combining buffers
+              for (int s = 0; s < 12; s++) _mm_stream_si128((__m128i *)(p + s * 4), _mm_load_si128((const __m128i *)(tmpl + s * 4)));
             }
           }
+          if (wmode == 2) _mm_sfence();
           auto w = std::chrono::steady_clock::now();
           uint64_t spins = 0;
           while (h_done[0] != c) { _mm_pause(); if (++spins > 200000000ull) { ok = false; break; } }
@@ -113,6 +132,9 @@ int main()
         double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / N;
         if (!ok) { for (int b = 0; b < 148; b++) for (int s = 0; s < 6; s++) h_pk[(size_t)b * (PKT / 4) + s * 8 + 7] = 0xffffffffu; }
         cudaError_t e = cudaStreamSynchronize(st);
+        unsigned herr = 0;
+        cudaMemcpy(&herr, errs, 4, cudaMemcpyDeviceToHost);
+        printf("write mode %d (0 scalar + tag, 1 SSE 16 B, 2 non-temporal) payload errors %u | ", wmode, herr);
         printf("grid %3d %s completion %d: %7.2f us per round trip (host packet writes %.2f us, worst %.1f)%s %s\n", grid, own ? "own packet per CTA" : "one shared packet  ",
                completion, us, host_write / N, worst, ok ? "" : "  TIMED OUT", e == cudaSuccess ? "" : cudaGetErrorString(e));
         fflush(stdout);

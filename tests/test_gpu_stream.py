@@ -299,6 +299,9 @@ def test_resident_scorer_full_size_models(engine, feats20s, S, K, seed):
                 vcall()
             us_view = 1e6 * (time.perf_counter() - t0) / n
             print("resident scorer %d x %d, F = %d: %.2f us per akugpu_stream_logprobs call (pinned rows returned, ctypes loop)" % (S, K, F, us_view))
+            nat = engine.stream_latency(xb, n_calls=5000)
+            print("resident scorer %d x %d, F = %d: timed inside the library: mean %.2f us, median %.2f, p99 %.2f, max %.1f"
+                  % (S, K, F, nat["mean_us"], nat["median_us"], nat["p99_us"], nat["max_us"]))
             st = engine.stream_stats()
             print("resident scorer %d x %d, F = %d: %.2f us per akugpu_gmm_logprobs call (host buffers, ctypes loop); on the device: "
                   "%.2f us command -> A', %.2f -> this CTA's results stored, %.2f -> every CTA's, %.2f us command -> rows in host memory"
