@@ -908,37 +908,44 @@ fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
   if (copy_borders) tc = min(max(t, 0), ud.n_frames - 1);
   const int ws = (int)(tc * adv);                              // window start: AudioFileModule::generate, aku/FeatureModules.cc:378-397
   const int16_t *x = pcm + ud.pcm_off;
+  // frames that lie inside the audio (all but the first / last of an utterance) need no range test per sample
+  const bool inside = valid && ws >= 0 && (int64_t)ws + N < ud.n_samples;
+  const int16_t *xw = x + ws;
   float2 z[NR];
 #pragma unroll
   for (int rr = 0; rr < NR; rr++) {
     const int pos = rr * 32 + lane;                            // position after the bit reversal of the decimation in time
     const int k = (int)(__brev((unsigned)pos) >> (32 - LOGM));
-    float v[2];
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const int i = 2 * k + e;
-      const int64_t p0 = (int64_t)ws + i, p1 = p0 + 1;
-      const float s0 = (valid && p0 >= 0 && p0 < ud.n_samples) ? (float)x[p0] : 0.f;
-      const float s1 = (valid && p1 >= 0 && p1 < ud.n_samples) ? (float)x[p1] : 0.f;
-      const float pe = __fsub_rn(s1, __fmul_rn(emph, s0));                  // float pre-emphasis (:429)
-      // float window * double sample -> float (:531): the double product of two floats is exact, so its rounding to
-      // float is the fp32 product
-      v[e] = __fmul_rn(__ldg(window + i), pe);
+    float s0, s1, s2;
+    if (inside) {
+      s0 = (float)xw[2 * k]; s1 = (float)xw[2 * k + 1]; s2 = (float)xw[2 * k + 2];
+    } else {
+      const int64_t p0 = (int64_t)ws + 2 * k;
+      s0 = (valid && p0 >= 0 && p0 < ud.n_samples) ? (float)x[p0] : 0.f;
+      s1 = (valid && p0 + 1 >= 0 && p0 + 1 < ud.n_samples) ? (float)x[p0 + 1] : 0.f;
+      s2 = (valid && p0 + 2 >= 0 && p0 + 2 < ud.n_samples) ? (float)x[p0 + 2] : 0.f;
     }
-    z[rr] = make_float2(v[0], v[1]);
+    const float2 wn = __ldg(reinterpret_cast<const float2 *>(window) + k);
+    // float pre-emphasis (:429); float window * double sample -> float (:531): the double product of two floats is
+    // exact, so its rounding to float is the fp32 product
+    z[rr] = make_float2(__fmul_rn(wn.x, __fsub_rn(s1, __fmul_rn(emph, s0))), __fmul_rn(wn.y, __fsub_rn(s2, __fmul_rn(emph, s1))));
   }
-  // stages whose partner is in another lane: half = 1 .. 16
+  // stages whose partner is in another lane: half = 1 .. 16.  The upper lane of a pair multiplies its element by the
+  // twiddle, the lower one by (1, 0) -- exact --, both send the product: lower = own + received, upper = received - own
+  // (one fused multiply-add by +-1: the rounding of the sum / difference).  Same operations, same bits as a butterfly
+  // that computes the twiddle product on both sides.
 #pragma unroll
   for (int half = 1; half < 32; half <<= 1) {
-    const float2 wv = __ldg(tw + (lane & (half - 1)) * (N / (2 * half)));   // twiddle e^{-2 pi i j / len} = tw[j * N / len]
     const bool hi = (lane & half) != 0;
+    float2 wv = __ldg(tw + (lane & (half - 1)) * (N / (2 * half)));         // twiddle e^{-2 pi i j / len} = tw[j * N / len]
+    if (!hi) wv = make_float2(1.f, 0.f);
+    const float sg = hi ? -1.f : 1.f;
 #pragma unroll
     for (int rr = 0; rr < NR; rr++) {
-      const float2 mine = z[rr];
-      const float2 other = make_float2(__shfl_xor_sync(0xffffffffu, mine.x, half), __shfl_xor_sync(0xffffffffu, mine.y, half));
-      const float2 a = hi ? other : mine, c = hi ? mine : other;
-      const float2 wc = make_float2(c.x * wv.x - c.y * wv.y, c.x * wv.y + c.y * wv.x);
-      z[rr] = hi ? make_float2(a.x - wc.x, a.y - wc.y) : make_float2(a.x + wc.x, a.y + wc.y);
+      const float2 c = z[rr];
+      const float2 t = make_float2(c.x * wv.x - c.y * wv.y, c.x * wv.y + c.y * wv.x);
+      const float2 o = make_float2(__shfl_xor_sync(0xffffffffu, t.x, half), __shfl_xor_sync(0xffffffffu, t.y, half));
+      z[rr] = make_float2(__fmaf_rn(t.x, sg, o.x), __fmaf_rn(t.y, sg, o.y));
     }
   }
   // stages inside the lane: half = 32 .. M / 2, register distance half / 32
@@ -983,8 +990,14 @@ fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
   for (int b = lane; b < fuse.mel_dim; b += 32) {
     const int t0 = fuse.mel.desc[3 * b], n = fuse.mel.desc[3 * b + 1];
     const double *sc = fuse.mel_scale_d + fuse.mel.desc[3 * b + 2];
+    const double *pw = pwd[w] + t0;
+    const int n_in = min(n, M + 1 - t0);                       // taps inside the spectrum; the others read its last bin
     float val = 0;
-    for (int i = 0; i < n; i++) val = (float)__dadd_rn((double)val, __dmul_rn(sc[i], pwd[w][min(t0 + i, M)]));
+    int i = 0;
+#pragma unroll 4
+    for (; i < n_in; i++) val = (float)__dadd_rn((double)val, __dmul_rn(sc[i], pw[i]));
+    const double last = pwd[w][M];
+    for (i = max(i, 0); i < n; i++) val = (float)__dadd_rn((double)val, __dmul_rn(sc[i], last));
     const float sum = fuse.mel.sum[b];
     melv[w][b] = fuse.mel_root ? pow((double)__fdiv_rn(val, sum), 0.1) : (double)logf(__fadd_rn(__fdiv_rn(val, sum), 1.f));
   }
