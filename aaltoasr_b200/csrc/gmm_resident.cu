@@ -99,7 +99,8 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
   const int n_begin = range_begin[blockIdx.y], n_end = range_begin[blockIdx.y + 1];
   const int T = n_end - n_begin;
   // resident tiles: the first R of the range, one slot each, loaded once; the other T - R tiles pass through NR ring slots
-  const int NR = T <= nslots ? 0 : (nslots >= 4 ? 2 : 1);
+  // (ring depth: a slot is ~1 us in flight, 40 KB; three of them keep the SM's ~120 GB/s L2 port busy)
+  const int NR = T <= nslots ? 0 : (nslots >= 5 ? 3 : nslots >= 3 ? 2 : 1);
   const int R = T <= nslots ? T : nslots - NR;
 
   if (threadIdx.x == 0) {

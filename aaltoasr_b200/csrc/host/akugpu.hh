@@ -323,6 +323,37 @@ private:
 // (akugpu_frontend_set_parameters).  A speaker's `model cmllr` entry (model-level constrained MLLR, aku/ModelModules.hh)
 // is applied through akugpu_model_set_cmllr when it is the global transform (unitmode UNIT_NO) and through
 // akugpu_model_set_cmllr_units for the regression-class modes (UNIT_PHONE / UNIT_MIX / UNIT_GAUSSIAN).  As in the reference, a speaker without the entry keeps the previous speaker's transform.
+// The stream decoder's session (decoder/decode-stream.cc:150-207: one acoustic model for the life of the stream, one
+// scoring call per frame -> Toolbox::set_one_frame).  While an object lives, the model sits in the shared memory of the
+// SMs (akugpu_stream_open) and log_probs() is a message to the resident kernel: no launch, no copy -- the returned rows
+// are the context's pinned memory, valid until its next call.  Any other call on the engine ends the kernel; the next
+// log_probs() starts it again.
+class StreamSession {
+public:
+  explicit StreamSession(Engine &e, double tiny = 1e-30, double idle_ms = 100.0) : m_e(e), m_tiny(tiny), m_S(akugpu_model_num_states(e.ctx())) {
+    check(m_e.ctx(), akugpu_stream_open(m_e.ctx(), idle_ms));
+  }
+  ~StreamSession() { akugpu_stream_close(m_e.ctx()); }
+  int num_states() const { return m_S; }
+  // (float) log(max(likelihood, tiny)) of every state for n_frames (1..16) rows of host float features
+  const float *log_probs(const float *feats, int n_frames = 1) {
+    const float *rows = 0;
+    check(m_e.ctx(), akugpu_stream_logprobs(m_e.ctx(), feats, n_frames, m_tiny, &rows));
+    return rows;
+  }
+  // the reference's vector form: what decode-stream.cc hands to Toolbox::set_one_frame
+  void log_probs(const std::vector<float> &fea, std::vector<float> &out) {
+    const float *rows = log_probs(fea.data(), 1);
+    out.assign(rows, rows + m_S);
+  }
+private:
+  StreamSession(const StreamSession &);
+  StreamSession &operator=(const StreamSession &);
+  Engine &m_e;
+  double m_tiny;
+  int m_S;
+};
+
 class SpeakerConfig {
 public:
   explicit SpeakerConfig(Engine &e) : m_e(e), m_default_speaker_set(false), m_default_utterance_set(false) {}

@@ -51,6 +51,23 @@ int akugpu_features_pre_range(akugpu_ctx *, const float *, int64_t, int, int, co
 
 // scoring stub: S = 3 states; linear likelihood (F64) or log-likelihood (F32) of state s for a frame = f(frame sum, s)
 static int g_score_calls = 0;
+// resident scorer, stubbed: log((1 + x0 + x1) (s + 1) / 1000) floored at log(tiny), rows in a static buffer
+static int g_session_open = 0, g_session_calls = 0;
+static float g_session_rows[16 * 3];
+int akugpu_stream_open(akugpu_ctx *, double idle_ms) { g_session_open = idle_ms > 0 ? 1 : -1; return 0; }
+int akugpu_stream_close(akugpu_ctx *) { g_session_open = 0; return 0; }
+int akugpu_stream_logprobs(akugpu_ctx *, const float *feats, int n_frames, double tiny, const float **rows)
+{
+  if (!g_session_open || n_frames < 1 || n_frames > 16) return -1;
+  g_session_calls++;
+  for (int f = 0; f < n_frames; f++)
+    for (int s = 0; s < 3; s++) {
+      double lik = (1 + feats[f * g_dim] + feats[f * g_dim + 1]) * (s + 1) / 1000.0;
+      g_session_rows[f * 3 + s] = (float)log(lik < tiny ? tiny : lik);
+    }
+  *rows = g_session_rows;
+  return 0;
+}
 int akugpu_model_num_states(akugpu_ctx *) { return 3; }
 int akugpu_model_read(akugpu_ctx *, const char *) { return 0; }
 int akugpu_gmm_score(akugpu_ctx *, const void *feats, int feats_f64, int64_t n_frames, int precision, void *out)
@@ -129,6 +146,21 @@ int main(int argc, char **argv)
       printf("exception: %s\n", s.c_str());
       return 1;
     }
+    return 0;
+  }
+  if (std::string(argv[1]) == "session") {     // spk_harness session: akugpu::StreamSession over the stubbed entry points
+    g_dim = 2;
+    akugpu::Engine eng(0);
+    {
+      akugpu::StreamSession ses(eng, 1e-30, 50.0);
+      const float x[4] = {1, 2, 5, 6};
+      const float *r = ses.log_probs(x, 2);
+      printf("%d states, open=%d, rows %.6g %.6g %.6g | %.6g\n", ses.num_states(), g_session_open, r[0], r[1], r[2], r[3]);
+      std::vector<float> fea(x + 2, x + 4), out;
+      ses.log_probs(fea, out);
+      printf("%d values, %.6g, calls=%d\n", (int)out.size(), out[2], g_session_calls);
+    }
+    printf("open=%d\n", g_session_open);
     return 0;
   }
   if (std::string(argv[1]) == "hmm") {         // spk_harness hmm f32|f64: the akugpu::HmmSet cache protocol

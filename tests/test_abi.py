@@ -157,6 +157,13 @@ def test_cpp_speaker_config_matches_python_mirror(tmp_path):
         assert r.returncode == 0
         assert r.stdout.decode().splitlines() == ["4 12 calls=1", "8 calls=1", "24 12 calls=2", "1e-50 calls=3", "36 102 calls=4"], (prec, r.stdout)
 
+    # akugpu::StreamSession: open on construction, rows of the context returned without a copy, closed on destruction
+    r = subprocess.run([exe, "session", "x"], stdout=subprocess.PIPE, timeout=60)
+    assert r.returncode == 0
+    want = [np.float32(np.log((1 + 1 + 2) * (s + 1) / 1000.0)) for s in range(3)] + [np.float32(np.log((1 + 5 + 6) / 1000.0))]
+    assert r.stdout.decode().splitlines() == ["3 states, open=1, rows %.6g %.6g %.6g | %.6g" % tuple(want),
+                                              "3 values, %.6g, calls=2" % np.float32(np.log(12 * 3 / 1000.0)), "open=0"], r.stdout
+
     # model-level CMLLR fixture
     g = load_golden("ref_cmllr")
     spkc = str(g["spkc"])
