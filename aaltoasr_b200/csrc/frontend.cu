@@ -885,22 +885,15 @@ fe_spectrum_fft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utt
 // float power sum on the last lane, the dct on 12 lanes) is warp-local as well.  Float / double placement as in
 // fe_spectrum_fft; the mel and dct tables are read widened to double, the spectrum is kept widened next to its floats
 // (two conversions per mel tap instead of four, none in the dct).
+// One frame's spectrum by one warp: window, pre-emphasis, N/2-point complex FFT in registers, real-FFT split.  The
+// values go to the warp's shared-memory row(s) (fused paths) or, widened, to row r of `out`.
 template <int N>
-__global__ void __launch_bounds__(256)
-fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
-                 int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
-                 const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out, const FuseStatic fuse)
+__device__ __forceinline__ void wfft_frame(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                                           int64_t r, bool valid, int H, float adv, float emph, int copy_borders,
+                                           const float *__restrict__ window, const float2 *__restrict__ tw, int magnitude, int do_log,
+                                           double *__restrict__ out, float2 *zsw, float *pwf_row, double *pwd_row, int lane)
 {
   constexpr int M = N / 2, NR = M / 32, LOGM = fe_log2(M);
-  constexpr int WPB = 8;                                        // frames (warps) per CTA
-  static_assert((M & (M - 1)) == 0 && M >= 32 && M <= 256, "window must be a power of two, 64 ... 512 samples");
-  __shared__ float2 zs[WPB][M];
-  __shared__ __align__(16) float pwf[WPB][M + 4];
-  __shared__ double pwd[WPB][M + 2];
-  __shared__ double melv[WPB][FUSE_MAX_MEL];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * WPB + w;
-  const bool valid = r < n_rows;
   int u = 0, t = 0;
   if (valid) row_to_frame(row_utt, utts, r, H, u, t);
   const UttDesc ud = utts[u];
@@ -964,13 +957,13 @@ fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
     }
   }
 #pragma unroll
-  for (int rr = 0; rr < NR; rr++) zs[w][rr * 32 + lane] = z[rr];
+  for (int rr = 0; rr < NR; rr++) zsw[rr * 32 + lane] = z[rr];
   __syncwarp();
   // split: X[k] = (Z[k]+conj(Z[M-k]))/2 - i e^{-2 pi i k/N} (Z[k]-conj(Z[M-k]))/2 ,  k = 0..M
   {
     double *o = out + r * (M + 1);
     for (int k = lane; k <= M; k += 32) {
-      const float2 a = zs[w][k == M ? 0 : k], b = zs[w][k == 0 ? 0 : M - k];
+      const float2 a = zsw[k == M ? 0 : k], b = zsw[k == 0 ? 0 : M - k];
       const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
       const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
       const float2 wv = (k == M) ? make_float2(-1.f, 0.f) : __ldg(tw + k);
@@ -979,10 +972,30 @@ fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
       float p = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));       // float power (:534-537)
       if (magnitude) p = sqrtf(p);
       if (do_log) p = logf(p);
-      if (fuse.on) { pwf[w][k] = p; pwd[w][k] = (double)p; }
+      if (pwf_row) { pwf_row[k] = p; if (pwd_row) pwd_row[k] = (double)p; }
       else if (valid) o[k] = (double)p;
     }
   }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                 int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
+                 const float2 *__restrict__ tw, int magnitude, int do_log, double *__restrict__ out, const FuseStatic fuse)
+{
+  constexpr int M = N / 2;
+  constexpr int WPB = 8;                                        // frames (warps) per CTA
+  static_assert((M & (M - 1)) == 0 && M >= 32 && M <= 256, "window must be a power of two, 64 ... 512 samples");
+  __shared__ float2 zs[WPB][M];
+  __shared__ __align__(16) float pwf[WPB][M + 4];
+  __shared__ double pwd[WPB][M + 2];
+  __shared__ double melv[WPB][FUSE_MAX_MEL];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * WPB + w;
+  const bool valid = r < n_rows;
+  wfft_frame<N>(pcm, utts, row_utt, r, valid, H, adv, emph, copy_borders, window, tw, magnitude, do_log, out, zs[w],
+                fuse.on ? pwf[w] : nullptr, fuse.on ? pwd[w] : nullptr, lane);
   if (!fuse.on) return;
   __syncwarp();
   // mel bins: MelModule::generate (:806-849) from the precomputed triangle weights; float accumulator fed through a
@@ -1024,6 +1037,92 @@ fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
     }
 }
 
+// The same chain with the epilogue turned by 90 degrees (fused MFCC graphs with at most 32 mel bins).  In the kernel
+// above a frame's epilogue runs on the lanes of ONE warp: 21 lanes walk their triangles (38 sequential taps for the
+// widest), one lane adds the 129 spectrum values in the prescribed order, 12 lanes form the dct -- ~600 warp instructions
+// per frame at a quarter of the lanes.  Here a CTA of four warps first transforms 32 frames (eight per warp, spectra kept
+// in shared memory) and then runs the epilogue with LANE = FRAME: a mel bin, the power sum or a dct coefficient is one
+// task for 32 frames at once (tasks handed out longest first through a shared counter), every lane performing exactly
+// the operation sequence of the kernel above for its frame -- same bits, ~100 instructions per frame.
+template <int N>
+__global__ void __launch_bounds__(256, 6)
+fe_spectrum_bfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ utts, const int *__restrict__ row_utt,
+                 int64_t n_rows, int H, float adv, float emph, int copy_borders, const float *__restrict__ window,
+                 const float2 *__restrict__ tw, int magnitude, int do_log, const FuseStatic fuse)
+{
+  constexpr int M = N / 2;
+  constexpr int WPB = 8, FPW = 4, FPC = WPB * FPW;              // 32 frames per CTA
+  constexpr int MAXB = 32, MAXC = 32;
+  static_assert((M & (M - 1)) == 0 && M >= 32 && M <= 128, "window of 128 or 256 samples");
+  constexpr int PW_FLOATS = FPC * (M + 1) > 2 * FPC * (MAXC + 1) ? FPC * (M + 1) : 2 * FPC * (MAXC + 1);
+  __shared__ float2 zs[WPB][M];
+  __shared__ __align__(8) float pw[PW_FLOATS];                  // spectra [frame][M + 1] (odd row length: lane = frame reads are
+                                                                // conflict free); later the merged rows [frame][MAXC + 1] doubles
+  __shared__ double melv[MAXB + 1][FPC];                        // [bin][frame]; the last row carries the power column
+  __shared__ int next_task;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r0 = (int64_t)blockIdx.x * FPC;
+  if (threadIdx.x == 0) next_task = 0;
+  for (int i = 0; i < FPW; i++) {
+    const int fl = w * FPW + i;
+    const int64_t r = r0 + fl;
+    wfft_frame<N>(pcm, utts, row_utt, r, r < n_rows, H, adv, emph, copy_borders, window, tw, magnitude, do_log, nullptr, zs[w],
+                  pw + fl * (M + 1), nullptr, lane);
+    __syncwarp();                                               // zs[w] is rewritten by the warp's next frame
+  }
+  __syncthreads();
+  // tasks: 0 = power sum (the longest), then the mel bins in pairs from the widest triangles down: two independent
+  // accumulator chains per lane
+  const float *sp = pw + lane * (M + 1);
+  const int has_pow = fuse.pow_col >= 0 ? 1 : 0;
+  const int n_tasks = (fuse.mel_dim + 1) / 2 + has_pow;
+  for (;;) {
+    int task = 0;
+    if (lane == 0) task = atomicAdd(&next_task, 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= n_tasks) break;
+    if (has_pow && task == 0) {
+      // the float accumulator of PowerModule (:875-885): a chain of FADDs (see fe_spectrum_fft)
+      float power = 0;
+#pragma unroll 4
+      for (int k = 0; k <= M; k++) power = __fadd_rn(power, sp[k]);
+      melv[MAXB][lane] = log(__dadd_rn((double)power, 1e-10));
+      continue;
+    }
+    // MelModule::generate (:806-849): float accumulator fed through a double product, `val += scale * data`
+    const int b0 = fuse.mel_dim - 1 - 2 * (task - has_pow), b1 = b0 - 1;     // b1 = -1: an odd bin out
+    const int t00 = __ldg(fuse.mel.desc + 3 * b0), n0 = __ldg(fuse.mel.desc + 3 * b0 + 1);
+    const double *sc0 = fuse.mel_scale_d + __ldg(fuse.mel.desc + 3 * b0 + 2);
+    const int t01 = b1 >= 0 ? __ldg(fuse.mel.desc + 3 * b1) : 0, n1 = b1 >= 0 ? __ldg(fuse.mel.desc + 3 * b1 + 1) : 0;
+    const double *sc1 = fuse.mel_scale_d + (b1 >= 0 ? __ldg(fuse.mel.desc + 3 * b1 + 2) : 0);
+    float v0 = 0, v1 = 0;
+    const int nn = max(n0, n1);
+    for (int i = 0; i < nn; i++) {                              // a tap past the spectrum reads its last bin
+      if (i < n0) v0 = (float)__dadd_rn((double)v0, __dmul_rn(__ldg(sc0 + i), (double)sp[min(t00 + i, M)]));
+      if (i < n1) v1 = (float)__dadd_rn((double)v1, __dmul_rn(__ldg(sc1 + i), (double)sp[min(t01 + i, M)]));
+    }
+    const float s0 = __ldg(fuse.mel.sum + b0);
+    melv[b0][lane] = fuse.mel_root ? pow((double)__fdiv_rn(v0, s0), 0.1) : (double)logf(__fadd_rn(__fdiv_rn(v0, s0), 1.f));
+    if (b1 >= 0) {
+      const float s1 = __ldg(fuse.mel.sum + b1);
+      melv[b1][lane] = fuse.mel_root ? pow((double)__fdiv_rn(v1, s1), 0.1) : (double)logf(__fadd_rn(__fdiv_rn(v1, s1), 1.f));
+    }
+  }
+  __syncthreads();                                              // the spectra are dead: their memory takes the merged rows
+  double *orow = reinterpret_cast<double *>(pw);                // [frame][MAXC + 1]
+  for (int c = w; c < fuse.dct_dim; c += WPB) {                // DCTModule::generate (:956-979), one coefficient x 32 frames
+    const double *tb = fuse.dct_table_d + (size_t)c * fuse.mel_dim;
+    double acc = 0.0;
+    for (int b = 0; b < fuse.mel_dim; b++) acc = __dadd_rn(acc, __dmul_rn(melv[b][lane], __ldg(tb + b)));
+    orow[lane * (MAXC + 1) + fuse.dct_col + c] = acc;
+  }
+  if (has_pow && w == 0) orow[lane * (MAXC + 1) + fuse.pow_col] = melv[MAXB][lane];
+  __syncthreads();
+  const int n_here = (int)min((int64_t)FPC, n_rows - r0);
+  double *o = fuse.out + r0 * fuse.odim;
+  for (int i = threadIdx.x; i < n_here * fuse.odim; i += blockDim.x) o[i] = orow[(i / fuse.odim) * (MAXC + 1) + i % fuse.odim];
+}
+
 // Fused tail  X -> delta -> delta -> merge(X, d1, d2) -> output rows without the halo (DeltaModule::generate :1019-1037
 // applied twice, MergerModule :1352-1364): one thread per (output row, column of X); the same operations in the same
 // order as the per-module kernels, the intermediate rows recomputed instead of stored.
@@ -1056,6 +1155,66 @@ __global__ void fe_delta2_merge(const double *__restrict__ src, int dim, int64_t
   o[c] = (T)x[0];
   o[dim + c] = (T)d1[FUSE_MAX_WIDTH];
   o[2 * dim + c] = (T)__ddiv_rn(acc, (double)norm2);
+}
+
+// The same fused tail, tiled: a CTA takes 64 consecutive rows of X into shared memory (+ the halo), forms the first delta
+// ONCE per (row, column) -- the kernel above recomputes it for each of the 2 w2 + 1 rows that use it: six double divisions
+// and a 64-bit index division per output element, 640 instructions -- and the second delta from that tile; the rows'
+// output positions are looked up once per row.  Operations and their order per value are the ones above: same bits.
+constexpr int DELTA_TILE_ROWS = 64;
+template <class T>
+__global__ void __launch_bounds__(256)
+fe_delta2_merge_tiled(const double *__restrict__ src, int dim, int64_t n_rows, const UttDesc *__restrict__ utts,
+                      const int *__restrict__ row_utt, int H, int w1, float norm1, int w2, float norm2, T *__restrict__ out)
+{
+  constexpr int R = DELTA_TILE_ROWS;
+  extern __shared__ double delta_sm[];
+  __shared__ long long qrow[R];
+  const int hx = w1 + w2, hd = w2;
+  double *xs = delta_sm;                                  // rows r0 - hx .. r0 + R + hx of X
+  double *ds = xs + (R + 2 * hx) * dim;                   // rows r0 - hd .. r0 + R + hd of the first delta
+  const int64_t r0 = (int64_t)blockIdx.x * R;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    const int64_t r = r0 + i;
+    long long q = -1;
+    if (r < n_rows) {
+      const UttDesc ud = utts[row_utt[r]];
+      const int64_t k = r - ud.row_off - H;                // frame within the utterance's output
+      if (k >= 0 && k < ud.n_rows_out) q = ud.out_off + k; // halo rows only feed their neighbours
+    }
+    qrow[i] = q;
+  }
+  {
+    const int64_t e0 = (r0 - hx) * dim, e_end = n_rows * dim;
+    const int nx = (R + 2 * hx) * dim;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+      const int64_t e = e0 + i;
+      xs[i] = (e >= 0 && e < e_end) ? src[e] : 0.0;       // rows outside the matrix feed no output row
+    }
+  }
+  __syncthreads();
+  {
+    const int nd = (R + 2 * hd) * dim;
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) {
+      const double *x = xs + i + w1 * dim;
+      double acc = 0;
+      for (int kk = 1; kk <= w1; kk++) acc = __dadd_rn(acc, __dmul_rn((double)kk, __dsub_rn(x[kk * dim], x[-kk * dim])));
+      ds[i] = __ddiv_rn(acc, (double)norm1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * dim; i += blockDim.x) {
+    const int rl = i / dim, c = i - rl * dim;
+    const long long q = qrow[rl];
+    if (q < 0) continue;
+    const double *d = ds + i + hd * dim;
+    double acc = 0;
+    for (int kk = 1; kk <= w2; kk++) acc = __dadd_rn(acc, __dmul_rn((double)kk, __dsub_rn(d[kk * dim], d[-kk * dim])));
+    T *o = out + q * (3 * dim);
+    o[c] = (T)xs[i + hx * dim];
+    o[dim + c] = (T)d[0];
+    o[2 * dim + c] = (T)__ddiv_rn(acc, (double)norm2);
+  }
 }
 
 // Generic window length: direct DFT with the twiddle table (O(N^2); correctness path for the
@@ -1472,12 +1631,19 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
 #define SPEC_WFFT(NN)                                                                                               \
   case NN: {                                                                                                        \
     constexpr int WPB_ = 8;                                                                                         \
+    if (NN <= 256 && fuse.on && fuse.mel_dim <= 32 && fuse.odim <= 32 && !one_warp_epilogue) {                      \
+      fe_spectrum_bfft<(NN <= 256 ? NN : 256)><<<grid1(n_rows, 32), 256, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance, \
+                                                               base.emph, base.copy_borders, win, tw,               \
+                                                               mod.magnitude, mod.log, fuse);                       \
+      break;                                                                                                        \
+    }                                                                                                               \
     fe_spectrum_wfft<NN><<<grid1(n_rows, WPB_), WPB_ * 32, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,  \
                                                                    base.emph, base.copy_borders, win, tw,           \
                                                                    mod.magnitude, mod.log, o, fuse);                \
     break;                                                                                                          \
   }
         const char *old_fft = getenv("AKUGPU_FE_OLDFFT");             // the shared-memory kernel, for comparisons
+        static const bool one_warp_epilogue = getenv("AKUGPU_FE_WFFT1") != nullptr;   // the frame-per-warp epilogue, for comparisons
         if (old_fft && (N & (N - 1)) == 0) {
           switch (N) {
             SPEC_FFT(128)
@@ -1576,7 +1742,20 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
   if (g_x >= 0) {
     const Module &D1 = fe.mods[g_d1], &D2 = fe.mods[g_d2];
     const int xd = fe.mods[g_x].dim;
-    if (out_f64)
+    const size_t tile_smem = ((size_t)(DELTA_TILE_ROWS + 2 * (D1.width + D2.width)) + (DELTA_TILE_ROWS + 2 * D2.width)) * xd * sizeof(double);
+    static const bool untiled = getenv("AKUGPU_FE_DELTA_UNTILED") != nullptr;      // the element-per-thread kernel, for comparisons
+    if (tile_smem <= 160 * 1024 && !untiled) {
+      const unsigned g = grid1(n_rows, DELTA_TILE_ROWS);
+      if (out_f64) {
+        ensure_dynamic_smem(ctx, (const void *)fe_delta2_merge_tiled<double>, tile_smem);
+        fe_delta2_merge_tiled<double><<<g, 256, tile_smem, st>>>(buf[g_x]->as<double>(), xd, n_rows, du, dr, H, D1.width, D1.norm, D2.width,
+                                                                 D2.norm, (double *)d_out + out_row_base * dim);
+      } else {
+        ensure_dynamic_smem(ctx, (const void *)fe_delta2_merge_tiled<float>, tile_smem);
+        fe_delta2_merge_tiled<float><<<g, 256, tile_smem, st>>>(buf[g_x]->as<double>(), xd, n_rows, du, dr, H, D1.width, D1.norm, D2.width,
+                                                                D2.norm, (float *)d_out + out_row_base * dim);
+      }
+    } else if (out_f64)
       fe_delta2_merge<double><<<grid1(n_rows * xd, 256), 256, 0, st>>>(buf[g_x]->as<double>(), xd, n_rows, du, dr, H, D1.width, D1.norm,
                                                                       D2.width, D2.norm, (double *)d_out + out_row_base * dim);
     else
