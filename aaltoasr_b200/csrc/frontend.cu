@@ -1037,6 +1037,12 @@ fe_spectrum_wfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
     }
 }
 
+static size_t bfft_smem_bytes(int N)
+{
+  const int M = N / 2, FPC = 32, WPB = 8, MAXB = 32, MAXC = 32;
+  const int pw_floats = std::max(FPC * (M + 1), 2 * FPC * (MAXC + 1));
+  return sizeof(double) * (MAXB + 1) * FPC + sizeof(float2) * WPB * M + sizeof(float) * pw_floats;
+}
 // The same chain with the epilogue turned by 90 degrees (fused MFCC graphs with at most 32 mel bins).  In the kernel
 // above a frame's epilogue runs on the lanes of ONE warp: 21 lanes walk their triangles (38 sequential taps for the
 // widest), one lane adds the 129 spectrum values in the prescribed order, 12 lanes form the dct -- ~600 warp instructions
@@ -1053,12 +1059,16 @@ fe_spectrum_bfft(const int16_t *__restrict__ pcm, const UttDesc *__restrict__ ut
   constexpr int M = N / 2;
   constexpr int WPB = 8, FPW = 4, FPC = WPB * FPW;              // 32 frames per CTA
   constexpr int MAXB = 32, MAXC = 32;
-  static_assert((M & (M - 1)) == 0 && M >= 32 && M <= 128, "window of 128 or 256 samples");
+  static_assert((M & (M - 1)) == 0 && M >= 32 && M <= 256, "window of 128, 256 or 512 samples");
   constexpr int PW_FLOATS = FPC * (M + 1) > 2 * FPC * (MAXC + 1) ? FPC * (M + 1) : 2 * FPC * (MAXC + 1);
-  __shared__ float2 zs[WPB][M];
-  __shared__ __align__(8) float pw[PW_FLOATS];                  // spectra [frame][M + 1] (odd row length: lane = frame reads are
-                                                                // conflict free); later the merged rows [frame][MAXC + 1] doubles
-  __shared__ double melv[MAXB + 1][FPC];                        // [bin][frame]; the last row carries the power column
+  // dynamic shared memory (57 KB at 512 samples): melv [bin][frame] (the last row carries the power column) | zs, one
+  // row per warp | pw = spectra [frame][M + 1] (odd row length: lane = frame reads are conflict free), later the merged
+  // rows [frame][MAXC + 1] doubles
+  extern __shared__ __align__(16) unsigned char bfft_sm[];
+  double (*melv)[FPC] = reinterpret_cast<double (*)[FPC]>(bfft_sm);
+  float2 (*zs)[M] = reinterpret_cast<float2 (*)[M]>(bfft_sm + sizeof(double) * (MAXB + 1) * FPC);
+  float *pw = reinterpret_cast<float *>(bfft_sm + sizeof(double) * (MAXB + 1) * FPC + sizeof(float2) * WPB * M);
+  static_assert(PW_FLOATS > 0, "");
   __shared__ int next_task;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r0 = (int64_t)blockIdx.x * FPC;
@@ -1631,8 +1641,10 @@ void run_graph(akugpu_ctx *ctx, const void *d_in, std::vector<UttDesc> &utts, in
 #define SPEC_WFFT(NN)                                                                                               \
   case NN: {                                                                                                        \
     constexpr int WPB_ = 8;                                                                                         \
-    if (NN <= 256 && fuse.on && fuse.mel_dim <= 32 && fuse.odim <= 32 && !one_warp_epilogue) {                      \
-      fe_spectrum_bfft<(NN <= 256 ? NN : 256)><<<grid1(n_rows, 32), 256, 0, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance, \
+    if (fuse.on && fuse.mel_dim <= 32 && fuse.odim <= 32 && !one_warp_epilogue) {                                   \
+      const size_t bsm = bfft_smem_bytes(NN);                                                                       \
+      ensure_dynamic_smem(ctx, (const void *)fe_spectrum_bfft<NN>, bsm);                                            \
+      fe_spectrum_bfft<NN><<<grid1(n_rows, 32), 256, bsm, st>>>(d_pcm, du, dr, n_rows, H, base.window_advance,      \
                                                                base.emph, base.copy_borders, win, tw,               \
                                                                mod.magnitude, mod.log, fuse);                       \
       break;                                                                                                        \
