@@ -323,12 +323,12 @@ def bench_feature_sweep(args, local):
             "e2e": {"value": head["e2e_frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": head["h2d"],
                     "d2h_bytes_per_step": head["d2h"], "ms_per_step": head["ms_e2e"]},
             "gpu_launches": int(head["launches"]),
-            "roofline": {"kernel": "fe_spectrum_wfft<256> (one warp per frame, FFT in registers, fused mel + power + dct + merge) + fe_delta2_merge",
+            "roofline": {"kernel": "fe_spectrum_bfft<256> (FFT in the registers of one warp per frame, 32 frames per CTA; fused mel + power + dct + merge with lane = frame) + fe_delta2_merge_tiled",
                          "bound": "hbm", "achieved": head["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": head["hbm_frac"],
                          "traffic": None, "peak_source": hbm_src,
                          "algorithmic": "2 * hop + 4 * dim = 412 B per frame (SURVEY.md 8d) x frames / time of a whole akugpu_features call",
-                         "note": "the stage is issue / latency bound, not bandwidth bound: ncu (profiles/r02_fe_spectrum_wfft_ncu_full.txt) shows "
-                                 "1761 warp instructions per frame at 79 % issue-slot utilisation, DRAM traffic 260 B per frame at 1.5 % of "
+                         "note": "the stage is issue / latency bound, not bandwidth bound: ncu (profiles/r02_fe_spectrum_bfft_ncu_full.txt) shows "
+                                 "1043 warp instructions per frame at 68 % issue-slot utilisation, DRAM traffic 260 B per frame at 2 % of "
                                  "DRAM throughput; the operations are the reference's float / double sequence, reproduced exactly"},
             "sweep": sweep, "cpu_baseline": None}
 
