@@ -975,7 +975,17 @@ class Watchdog:
         return False
 
 
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: whatever else writes to file descriptor 1 (NCCL's version banner, a library's
+    printf) is sent to stderr, and print() keeps a private copy of the original descriptor."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
