@@ -8,9 +8,9 @@ CUDA device is missing -- there is no CPU fallback.
 """
 from ._lib import AkuGpuError, load_library, library_path
 from .engine import AkuGpu, F32, F64
-from .hostapi import FeatureGenerator, HmmSet, PhoneProbs, SpeakerConfig, parse_speaker_file
+from .hostapi import FeatureGenerator, HmmSet, PhoneProbs, SpeakerConfig, StreamSession, parse_speaker_file
 
 PPToolbox = PhoneProbs      # the name of the reference's SWIG class (aku/swig/PPToolbox.i:59-66)
 
-__all__ = ["AkuGpu", "AkuGpuError", "F32", "F64", "FeatureGenerator", "HmmSet", "PhoneProbs", "PPToolbox", "SpeakerConfig", "parse_speaker_file",
+__all__ = ["AkuGpu", "AkuGpuError", "F32", "F64", "FeatureGenerator", "HmmSet", "PhoneProbs", "PPToolbox", "SpeakerConfig", "StreamSession", "parse_speaker_file",
            "load_library", "library_path"]

@@ -144,6 +144,33 @@ class HmmSet:
         return float(self._row[state])
 
 
+class StreamSession:
+    """The stream decoder's session (decoder/decode-stream.cc:150-207: one acoustic model for the life of the stream, one
+    scoring call per frame).  While the object is open the model sits in the shared memory of the SMs
+    (akugpu_stream_open) and log_probs() is a message to the resident kernel; the returned rows are a VIEW of the
+    context's pinned memory, valid until its next call.  Mirror of akugpu::StreamSession (csrc/host/akugpu.hh)."""
+
+    def __init__(self, engine, tiny=1e-30, idle_ms=100.0):
+        self.engine, self.tiny = engine, tiny
+        engine.stream_open(idle_ms)
+        self._open = True
+
+    def log_probs(self, feats):
+        x = np.ascontiguousarray(feats, dtype=np.float32)
+        return self.engine.stream_logprobs(x.reshape(1, -1) if x.ndim == 1 else x, tiny=self.tiny)
+
+    def close(self):
+        if self._open:
+            self._open = False
+            self.engine.stream_close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def parse_speaker_file(text):
     """The .spkc format of aku::SpeakerConfig::read_speaker_file (aku/SpeakerConfig.cc:20-147):
     `speaker|utterance <id|default>` / `{` / `[feature] <module>` / `{ key value ... }` / `}`.

@@ -310,3 +310,20 @@ def test_resident_scorer_full_size_models(engine, feats20s, S, K, seed):
         assert engine.launch_count() == l0
     finally:
         engine.stream_close()
+
+
+def test_stream_session_mirror(engine, ref_small):
+    """The Python mirror of akugpu::StreamSession: a per-frame loop over an utterance, rows returned as views."""
+    from aaltoasr_b200 import StreamSession
+    g = ref_small
+    load_model(engine, g["model"])
+    x = g["feats"][:40].astype(np.float32)
+    engine.stream_close()
+    want = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)
+    l0 = engine.launch_count()
+    with StreamSession(engine, tiny=1e-30, idle_ms=200.0) as ses:
+        for f in range(len(x)):
+            assert np.array_equal(ses.log_probs(x[f])[0], want[f])
+        assert np.array_equal(ses.log_probs(x[3:9]), want[3:9])
+    assert engine.launch_count() - l0 == 1                       # the kernel itself
+    assert not engine.stream_stats()["live"]
