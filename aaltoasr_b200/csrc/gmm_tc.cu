@@ -308,7 +308,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16, int box_cols)
+void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16, int box_cols, int box_rows)
 {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -321,7 +321,7 @@ void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, boo
   cuuint64_t dims[2] = {cols, rows};                  // innermost first
   cuuint64_t strides[1] = {cols * 2};                 // bytes, dims 1..
   if (box_cols != tc::BK && box_cols != tc::BK / 2) throw Error(AKUGPU_E_ARG, "tc_make_map: box of 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) columns");
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)tc::BM};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   box_cols == tc::BK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -164,8 +164,12 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int m0 = blockIdx.x * BM;
   const int n_begin = range_begin[blockIdx.y], n_end = range_begin[blockIdx.y + 1];
 
+  // cluster of CL frame tiles (launch attribute; 1 = none): every CTA fetches 1 / CL of each component tile of B' and
+  // multicasts it to all of them -- the same tile order in every CTA of a cluster (same blockIdx.y)
+  const uint32_t cl_size = STREAM ? 1u : cluster_nctarank(), cl_rank = STREAM ? 0u : cluster_ctarank();
+  const uint16_t cl_mask = (uint16_t)((1u << cl_size) - 1u);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < tslots; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < tslots; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cl_size); }
     for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS / EPI_GROUPS); }
     mbar_init(&a_full, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -178,6 +182,7 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  if (cl_size > 1) cluster_sync_all();                          // every CTA's barriers exist before a peer's copy or commit reaches them
 
   if (warp == 0) {
     if (elect_one()) {
@@ -197,6 +202,21 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             tma_load_2d(dst + 3 * BLOCK_BYTES, &mapB, half + kb * BK, n * BN, &full_bar[slot]);
             if (++slot == tslots) { slot = 0; ph ^= 1; }
           }
+      } else
+      if (cl_size > 1) {
+        // this CTA's rows of every k-block, to every CTA of the cluster: the slot is free when ALL of them have read it
+        // (their MMA commits arrive on every CTA's barrier), and every CTA's barrier counts the whole tile
+        const int rows = BN / (int)cl_size;
+        const uint32_t part = (uint32_t)cl_rank * (uint32_t)rows * 128u;
+        for (int n = n_begin; n < n_end; n++) {
+          mbar_wait(&empty_bar[slot], ph ^ 1);
+          mbar_expect_tx(&full_bar[slot], SLOT_BYTES);
+          unsigned char *dst = ring + (size_t)slot * SLOT_BYTES + part;
+#pragma unroll
+          for (int kb = 0; kb < KB; kb++)
+            tma_load_2d_mc(dst + kb * BLOCK_BYTES, &mapA, kb * BK, n * BN + (int)cl_rank * rows, &full_bar[slot], cl_mask);
+          if (++slot == tslots) { slot = 0; ph ^= 1; }
+        }
       } else
       for (int n = n_begin; n < n_end; n++) {
         mbar_wait(&empty_bar[slot], ph ^ 1);                 // a fresh barrier passes the wait on the previous phase
@@ -257,7 +277,8 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int j = 0; j < NCH; j++) umma_f16(d_corr, a_desc0 + chunk_off(NCH + j), b_desc0 + chunk_off(j), IDESC, 1u);
 #pragma unroll
         for (int j = 0; j < NCH; j++) umma_f16(d_main, a_desc0 + chunk_off(j), b_desc0 + chunk_off(j), IDESC, j > 0 ? 1u : 0u);
-        umma_commit(&empty_bar[slot]);         // ring slot reusable once these MMAs have read it
+        if (cl_size > 1) umma_commit_mc(&empty_bar[slot], cl_mask);      // ... in every CTA of the cluster: they all refill it
+        else umma_commit(&empty_bar[slot]);    // ring slot reusable once these MMAs have read it
         umma_commit(&tmem_full[a]);            // both accumulators of this tile complete
         if (++slot == tslots) { slot = 0; ph ^= 1; }
       }
@@ -468,6 +489,7 @@ gmm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (cl_size > 1) cluster_sync_all();      // no CTA leaves while a peer's copy or commit may still be on its way to it
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
@@ -505,7 +527,8 @@ static int tc16_tslots(int KB, int D, bool leave_room = false)
   if (force && atoi(force) >= 2) n = std::min(n, atoi(force));
   return n;
 }
-constexpr int TC16_STREAM_STAGES = 3;      // 3 x 64 KB stages of {Ah, Al, Bh, Bl}
+constexpr int TC16_STREAM_STAGES = 3;
+constexpr int TC16_DEFAULT_CLUSTER = 1;    // frame tiles per cluster sharing the fetch of B' (see launch_gmm_tc16)      // 3 x 64 KB stages of {Ah, Al, Bh, Bl}
 
 // Expansion width (terms incl. the two constant terms) and whether A' can stay resident in shared memory.
 static void tc16_shape(const HostModel &hm, int &L, int &NCH, bool &stream)
@@ -721,11 +744,31 @@ bool launch_gmm_tc16(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t 
   const size_t smem = p.stream ? 1024 + (size_t)tslots * 4 * tc16::BLOCK_BYTES
                                : 1024 + (size_t)(1 + tslots) * p.KB * tc16::BLOCK_BYTES + tc16_stage_x_bytes(p.D);
   StageScope sc(ctx, 1);
+  // cluster of frame tiles sharing the fetch of B' (tma multicast): AKUGPU_TC16_CLUSTER = 1 / 2 / 4
+  static const int want_cl = getenv("AKUGPU_TC16_CLUSTER") ? atoi(getenv("AKUGPU_TC16_CLUSTER")) : TC16_DEFAULT_CLUSTER;
+  int cl = (!p.stream && (want_cl == 2 || want_cl == 4) && ftiles % want_cl == 0) ? want_cl : 1;
+  if (cl > 1) tc_make_map(&mapA, p.B.p, (uint64_t)p.n_tiles * tc16::BN, (uint64_t)p.Kp, true, tc16::BK, tc16::BN / cl);
   auto launch = [&](auto kernel) {
     ensure_dynamic_smem(ctx, (const void *)kernel, smem);
-    kernel<<<dim3(ftiles, ysplit), tc16::THREADS, smem, ctx->stream>>>(mapA, mapB, p.KB, tslots, ranges, p.meta.as<int>(), feats, feats_f64,
-                                                                     f_begin, nf, p.D, p.center.as<double>(), p.escale.as<float>(), sll, ldF,
-                                                                     norm, p.flag.as<int>());
+    const int nkb = p.KB;
+    if (cl == 1) {
+      kernel<<<dim3(ftiles, ysplit), tc16::THREADS, smem, ctx->stream>>>(mapA, mapB, nkb, tslots, ranges, p.meta.as<int>(), feats, feats_f64,
+                                                                       f_begin, nf, p.D, p.center.as<double>(), p.escale.as<float>(), sll, ldF,
+                                                                       norm, p.flag.as<int>());
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(ftiles, ysplit);
+      cfg.blockDim = dim3(tc16::THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      AKU_CUDA(cudaLaunchKernelEx(&cfg, kernel, mapA, mapB, nkb, tslots, ranges, (const int *)p.meta.as<int>(), feats, feats_f64, f_begin, nf, p.D,
+                                  (const double *)p.center.as<double>(), (const float *)p.escale.as<float>(), sll, ldF, norm, p.flag.as<int>()));
+    }
   };
   if (p.stream) launch(gmm_tc16_kernel<0>);
   else switch (p.NCH) {

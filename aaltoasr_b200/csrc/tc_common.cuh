@@ -34,6 +34,20 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same load delivered to the same shared-memory offset of every CTA of the cluster named in `mask` (each destination's
+// barrier at the same offset receives the bytes).
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4, LBO = 1,
 // SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (Blackwell), layout type 2.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -56,6 +70,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the arrival delivered to the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -82,7 +101,7 @@ __device__ __forceinline__ bool elect_one()
 
 // host helpers implemented in gmm_tc.cu
 // boxes of 128 rows x 64 columns with SWIZZLE_128B (default) or 128 x 32 with SWIZZLE_64B
-void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16, int box_cols = 64);
+void tc_make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t cols, bool fp16, int box_cols = 64, int box_rows = 128);
 double tc_expanded_params(const HostModel &hm, bool full, int L, std::vector<double> &cen, std::vector<double> &theta,
                           std::vector<double> &gconst, std::vector<double> *q_of_gauss);
 // Largest cancelling magnitude q the expanded form is trusted with: predicted log-likelihood error 4e-7 * q <= 8e-5.
