@@ -32,6 +32,8 @@
 #include <string.h>
 #include <chrono>
 #include <atomic>
+#include <algorithm>
+#include <vector>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -87,7 +89,10 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
   constexpr uint32_t IDESC = umma_idesc(BM, NF, false);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[MAX_SLOTS], empty_bar[MAX_SLOTS], tmem_full[2], tmem_empty[2], a_full, call_bar, done_bar;
+  // accumulator sets: MAIN + CORR of one tile = 2 NF columns; all 512 columns = 16 sets, so that the MMA warp runs through the
+  // tiles of a call without waiting for the epilogue (set = running tile number mod 16, across calls)
+  constexpr int NSETS = 512 / (2 * NF);
+  __shared__ uint64_t full_bar[MAX_SLOTS], empty_bar[MAX_SLOTS], tmem_full[NSETS], tmem_empty[NSETS], a_full, call_bar, done_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ ResidentCmd s_cmd;
   __shared__ float2 part[2][2][SLOTS][NF];                    // [group][use parity][slot][frame] = {max, sum of exp}
@@ -105,14 +110,14 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nslots; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < NSETS; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
     mbar_init(&a_full, EPI_THREADS / 32);
     mbar_init(&call_bar, 1);
     mbar_init(&done_bar, EPI_THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(4 * NF) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -153,7 +158,7 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
       auto aoff = [](int c) -> uint32_t { return ((uint32_t)(c >> 2) * A_BLOCK + (uint32_t)(c & 3) * 32u) >> 4; };
       const uint64_t x_desc0 = umma_desc(smem_u32(smem));
       int rs = 0;
-      uint32_t rph = 0, cph = 0, aph = 0, u0 = 0, u1 = 0;
+      uint32_t rph = 0, cph = 0, aph = 0, g = 0;                  // g: running tile number
       for (;;) {
         mbar_wait(&call_bar, cph);
         cph ^= 1;
@@ -164,11 +169,9 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
         mbar_wait(&a_full, aph);
         aph ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int i = 0; i < T; i++) {
-          const int a = i & 1;
-          const uint32_t u = a ? u1 : u0;
+        for (int i = 0; i < T; i++, g++) {
+          const uint32_t a = g % NSETS, u = g / NSETS;
           mbar_wait(&tmem_empty[a], (u & 1) ^ 1);
-          if (a) u1++; else u0++;
           int slot;
           if (i < R) { slot = i; mbar_wait(&full_bar[slot], 0); }        // completed once, for good
           else { slot = R + rs; mbar_wait(&full_bar[slot], rph); }
@@ -285,7 +288,7 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
     const int tg = q * 32 + lane;                             // 0..127 within the group
     const int sl = q * 2 + (lane >> 4);                       // this lane's slot within the tile
     const int bar_id = 2 + group;
-    uint32_t cph = 0, use = 0;
+    uint32_t cph = 0, use = 0, g0 = 0;                          // g0: running number of the call's first tile
     for (;;) {
       mbar_wait(&call_bar, cph);
       cph ^= 1;
@@ -302,7 +305,8 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
           else if (!direct) stage_x[idx] = __ldcg(gx + idx);
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         bool ovf = false;
-        for (int task = et; task < NF * 2 * NCH; task += EPI_THREADS) {
+        // (only the rows of the call's frames: the other rows of A' are columns of D nobody reads)
+        for (int task = et; task < nf * 2 * NCH; task += EPI_THREADS) {
           const int r = task / (2 * NCH), v = task - r * (2 * NCH);   // vector = 8 consecutive K terms of frame r
           const float *x = stage_x + r * D;
           const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
@@ -341,10 +345,11 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
       const unsigned long long t_a = globaltimer_ns();
       // ===== epilogue (gmm_stream_kernel's): lane = component; a slot = 16 consecutive lanes =====
       for (int n = n_begin + group; n < n_end; n += 2, use++) {
+        const uint32_t g = g0 + (uint32_t)(n - n_begin), set = g % NSETS;
         if (tg < SLOTS) pmeta[group][use & 1][tg] = __ldg(meta + (size_t)n * SLOTS + tg);     // off the critical path
-        mbar_wait(&tmem_full[group], use & 1);
+        mbar_wait(&tmem_full[set], (g / NSETS) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + group * 2 * NF;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 2 * NF;
         float2(*pt)[NF] = part[group][use & 1];
         const int *pm = pmeta[group][use & 1];
         {
@@ -354,7 +359,7 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
           AKU_TMEM_LD_WAIT();
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[group]);
+          if (lane == 0) mbar_arrive(&tmem_empty[set]);
 #pragma unroll
           for (int c = 0; c < 16; c++) {
             if (c < nf) {                                        // kernel-uniform
@@ -391,6 +396,7 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
           }
         }
       }
+      g0 += (uint32_t)T;
       // ===== completion.  Every CTA has stored its results straight into mapped host memory.  A system-scope fence per
       // CTA costs 4.6 us when 148 execute one together, carrying the rows through device memory with a few copying
       // CTAs 3.7 us (both measured here); a device-scope fence + count per CTA and ONE system-scope fence by the last
@@ -421,7 +427,7 @@ gmm_resident_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_const
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(4 * NF) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -457,9 +463,9 @@ bool session_applicable(akugpu_ctx *ctx, int precision, int64_t n_frames, const 
 // `min_sectors` sectors are written (the kernel always reads the sectors of a one-frame command).
 static void session_send(StreamState &st, int n_ctas, unsigned int seq, unsigned int y, unsigned int z, const float *x, int nx, int min_sectors)
 {
-  unsigned int tmpl[tcr::PKT_WORDS];
+  alignas(64) unsigned int tmpl[tcr::PKT_WORDS];
   const int ns = std::max(min_sectors, (2 + nx + 6) / 7);
-  for (int k = 0; k < ns; k++)
+  for (int k = 0; k < ns; k++) {
     for (int j = 0; j < 7; j++) {
       const int p = 7 * k + j;
       unsigned int w = 0;
@@ -468,15 +474,29 @@ static void session_send(StreamState &st, int n_ctas, unsigned int seq, unsigned
       else if (p - 2 < nx) memcpy(&w, x + (p - 2), 4);
       tmpl[8 * k + j] = w;
     }
+    tmpl[8 * k + 7] = seq;
+  }
   unsigned int *base = reinterpret_cast<unsigned int *>(st.pkt_host);
-  for (int c = 0; c < n_ctas; c++) {
-    unsigned int *pk = base + (size_t)c * tcr::PKT_WORDS;
+  // CTAs with the most component tiles first: the last packet written is on the critical path of the call
+  const bool ordered = (int)st.session_order.size() == n_ctas;
+  for (int i = 0; i < n_ctas; i++) {
+    unsigned int *pk = base + (size_t)(ordered ? st.session_order[i] : i) * tcr::PKT_WORDS;
+#if defined(__x86_64__)
+    // non-temporal 16-byte stores in address order: a line leaves the write-combining buffer whole (or as a prefix of what
+    // was written), so a sector's tag never precedes its payload, and the host does not fight the polling device for
+    // ownership of 444 cache lines (2.2 -> 1.7 us for 148 packets, scripts/micro_mailbox2.cu)
+    for (int c = 0; c < 2 * ns; c++) _mm_stream_si128(reinterpret_cast<__m128i *>(pk + 4 * c), _mm_load_si128(reinterpret_cast<const __m128i *>(tmpl + 4 * c)));
+#else
     for (int k = 0; k < ns; k++) {
       memcpy(pk + 8 * k, tmpl + 8 * k, 28);
       std::atomic_thread_fence(std::memory_order_release);
       reinterpret_cast<volatile unsigned int *>(pk)[8 * k + 7] = seq;
     }
+#endif
   }
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
 }
 
 void session_launch(akugpu_ctx *ctx)
@@ -504,6 +524,13 @@ void session_launch(akugpu_ctx *ctx)
     for (int i = 0; i < tcr::MAX_GRID * tcr::PKT_WORDS; i++) pk[i] = (i & 7) == 7 ? st.seq : 0u;
   }
   st.session_grid = ysplit;
+  {   // the order in which a call's packets are written: CTAs by falling number of component tiles
+    std::vector<int> rb((size_t)ysplit + 1);
+    AKU_CUDA(cudaMemcpy(rb.data(), ranges, rb.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    st.session_order.resize((size_t)ysplit);
+    for (int i = 0; i < ysplit; i++) st.session_order[(size_t)i] = i;
+    std::stable_sort(st.session_order.begin(), st.session_order.end(), [&](int a, int b) { return rb[a + 1] - rb[a] > rb[b + 1] - rb[b]; });
+  }
   AKU_CUDA(cudaMemsetAsync(st.cnt.p, 0, 16, st.session_stream));
   const unsigned int cmd0[4] = {st.seq, 0u, 0u, 0u};           // the relayed command word the CTAs wait to see CHANGE
   AKU_CUDA(cudaMemcpyAsync(st.relay.p, cmd0, 16, cudaMemcpyHostToDevice, st.session_stream));
