@@ -328,3 +328,38 @@ def test_stream_session_mirror(engine, ref_small):
         assert np.array_equal(ses.log_probs(x[3:9]), want6)
     assert engine.launch_count() - l0 == 1                       # the kernel itself
     assert not engine.stream_stats()["live"]
+
+
+def test_resident_scorer_stress(engine, ref_small):
+    """A few thousand messages in a seeded random order: 1 / 2-frame commands (packets), 3 ... 16-frame commands (relayed by
+    CTA 0), pauses longer than the idle timer (the kernel ends and is started again), other entry points in between (the
+    kernel is told to end).  Every answer carries the bits of the launch-per-call scorer."""
+    g = ref_small
+    load_model(engine, g["model"])
+    rng = np.random.default_rng(20261017)
+    x = g["feats"][:64].astype(np.float32)
+    engine.stream_close()
+    blocks = [(int(s), int(n)) for n in (1, 2, 3, 4, 7, 16) for s in rng.integers(0, 64 - n, size=6)]
+    want = {b: engine.gmm_logprobs(x[b[0]:b[0] + b[1]], precision=F32, tiny=1e-30).copy() for b in blocks}
+    s0 = engine.stream_stats()
+    engine.stream_open(5.0)                                       # idle timer: 5 ms
+    try:
+        n_calls = 0
+        for it in range(3000):
+            b = blocks[int(rng.integers(0, len(blocks)))]
+            r = rng.random()
+            if r < 0.004:
+                time.sleep(0.02)                                  # the kernel ends on its timer
+            elif r < 0.008:
+                engine.gmm_lna(g["feats"][:8], precision=F64, lnabytes=2)     # another entry point: quit message first
+            if it & 1:
+                got = engine.stream_logprobs(x[b[0]:b[0] + b[1]], tiny=1e-30)
+            else:
+                got = engine.gmm_logprobs(x[b[0]:b[0] + b[1]], precision=F32, tiny=1e-30)
+            n_calls += 1
+            assert np.array_equal(got, want[b]), (it, b)
+        st = engine.stream_stats()
+        assert st["calls"] - s0["calls"] == n_calls
+        assert 2 <= st["launches"] - s0["launches"] <= 60          # restarted after every pause / foreign call, not more
+    finally:
+        engine.stream_close()
