@@ -1066,6 +1066,7 @@ int akugpu_stream_close(akugpu_ctx *ctx)
 {
   API_BEGIN          /* ends the kernel */
   ctx->stream_state.session_want = false;
+  session_release_device(ctx);
   API_END
 }
 

@@ -32,6 +32,8 @@
 #include <string.h>
 #include <chrono>
 #include <atomic>
+#include <mutex>
+#include <map>
 #include <algorithm>
 #include <vector>
 #if defined(__x86_64__)
@@ -477,6 +479,9 @@ static void session_send(StreamState &st, int n_ctas, unsigned int seq, unsigned
     tmpl[8 * k + 7] = seq;
   }
   unsigned int *base = reinterpret_cast<unsigned int *>(st.pkt_host);
+#if defined(__x86_64__)
+  _mm_sfence();       // whatever the caller stored before (the features of a relayed call) is ordered before the packets
+#endif
   // CTAs with the most component tiles first: the last packet written is on the critical path of the call
   const bool ordered = (int)st.session_order.size() == n_ctas;
   for (int i = 0; i < n_ctas; i++) {
@@ -499,11 +504,31 @@ static void session_send(StreamState &st, int n_ctas, unsigned int seq, unsigned
 #endif
 }
 
+// One resident kernel per device: a second one could not become resident beside the first (each takes all of the SMs'
+// shared memory) and the two would hand the device back and forth at the pace of their idle timers.
+static std::mutex g_session_mu;
+static std::map<int, akugpu_ctx *> g_session_owner;
+static void session_claim_device(akugpu_ctx *ctx)
+{
+  std::lock_guard<std::mutex> lock(g_session_mu);
+  auto it = g_session_owner.find(ctx->device);
+  if (it != g_session_owner.end() && it->second != ctx)
+    throw Error(AKUGPU_E_STATE, "another context of this process holds the resident scorer of this device (akugpu_stream_close it first)");
+  g_session_owner[ctx->device] = ctx;
+}
+void session_release_device(akugpu_ctx *ctx)
+{
+  std::lock_guard<std::mutex> lock(g_session_mu);
+  auto it = g_session_owner.find(ctx->device);
+  if (it != g_session_owner.end() && it->second == ctx) g_session_owner.erase(it);
+}
+
 void session_launch(akugpu_ctx *ctx)
 {
   PackedTC16 &p = ctx->ptc16;
   StreamState &st = ctx->stream_state;
   const int S = ctx->hm.S;
+  session_claim_device(ctx);
   stream_buffers(ctx, S);
   stream_map_ready(ctx);
   if (!st.session_stream) AKU_CUDA(cudaStreamCreateWithFlags(&st.session_stream, cudaStreamNonBlocking));
@@ -583,6 +608,7 @@ void session_destroy(akugpu_ctx *ctx)
 {
   StreamState &st = ctx->stream_state;
   try { session_quiesce(ctx); } catch (...) {}
+  session_release_device(ctx);
   if (st.session_stream) { cudaStreamDestroy(st.session_stream); st.session_stream = nullptr; }
   if (st.pkt_host) { cudaFreeHost(st.pkt_host); st.pkt_host = nullptr; st.pkt_dev = nullptr; }
 }

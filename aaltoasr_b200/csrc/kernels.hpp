@@ -53,6 +53,7 @@ bool session_score(akugpu_ctx *ctx, const void *feats, int feats_f64, int64_t n_
 void session_launch(akugpu_ctx *ctx);
 void session_quiesce(akugpu_ctx *ctx);
 void session_destroy(akugpu_ctx *ctx);
+void session_release_device(akugpu_ctx *ctx);   // akugpu_stream_close: another context may open a session on the device
 const float *session_rows(akugpu_ctx *ctx);      // the pinned result rows of the last session call
 
 // lna_kernels.cu

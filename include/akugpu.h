@@ -302,7 +302,8 @@ int akugpu_stream_probe(akugpu_ctx *ctx, double out[8]);
  * bits the launch-per-call scorer returns.  The kernel ends when it is told to (akugpu_stream_close, and ANY other
  * entry point of this context sends that message first: nothing of the library runs beside it) or by itself after
  * idle_ms without a call (<= 0: 100 ms); the next eligible call starts it again.  Other CUDA work of the process on
- * the same device waits for that moment too: open a session on a GPU the decoder owns.  Models the streaming scorer
+ * the same device waits for that moment too: open a session on a GPU the decoder owns (one session per device and process:
+ * a second context's akugpu_stream_open fails with AKUGPU_E_STATE until the first closes its session).  Models the streaming scorer
  * does not serve (akugpu_set_streaming) are refused with AKUGPU_E_STATE.
  * akugpu_stream_stats: out[0] = session requested, out[1] = kernel believed to be running, out[2] = kernel launches,
  * out[3] = calls served by it; out[4] / out[5] = the last call as the last CTA to finish saw it, in nanoseconds of the

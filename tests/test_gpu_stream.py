@@ -363,3 +363,28 @@ def test_resident_scorer_stress(engine, ref_small):
         assert 2 <= st["launches"] - s0["launches"] <= 60          # restarted after every pause / foreign call, not more
     finally:
         engine.stream_close()
+
+
+def test_one_resident_scorer_per_device(engine, ref_small):
+    """A second context of the process cannot open a session on a device whose resident scorer another context holds."""
+    from aaltoasr_b200 import AkuGpu
+    g = ref_small
+    load_model(engine, g["model"])
+    x = g["feats"][:1].astype(np.float32)
+    engine.stream_close()
+    want = engine.gmm_logprobs(x, precision=F32, tiny=1e-30)
+    other = AkuGpu(0)
+    try:
+        load_model(other, g["model"])
+        engine.stream_open(100.0)
+        with pytest.raises(Exception):
+            other.stream_open(100.0)
+        assert np.array_equal(other.gmm_logprobs(x, precision=F32, tiny=1e-30), want)      # served by one launch per call
+        assert np.array_equal(engine.stream_logprobs(x, tiny=1e-30), want)
+        engine.stream_close()
+        other.stream_open(100.0)                                                            # free now
+        assert np.array_equal(other.stream_logprobs(x, tiny=1e-30), want)
+        other.stream_close()
+    finally:
+        engine.stream_close()
+        other.close()
