@@ -1011,7 +1011,12 @@ int akugpu_stream_open(akugpu_ctx *ctx, double idle_ms)
     st.session_want = false;
     throw Error(AKUGPU_E_STATE, "the resident scorer serves diagonal models of the fp16x2 tensor-core scorer (no clustering, no model-level CMLLR, no hybrid split)");
   }
-  session_launch(ctx);
+  try {
+    session_launch(ctx);
+  } catch (...) {
+    st.session_want = false;
+    throw;
+  }
   API_END
 }
 
