@@ -17,10 +17,12 @@ constexpr int XS_DIM = 40;                         // centred features of up to 
 }  // namespace tcs
 
 // pinned, mapped host block of a context's streaming calls:
-//   bytes   0.. 63  device -> host: word 0 = sequence number of the last completed call, word 1 = fp16-range flag
+//   bytes   0.. 15  device -> host: word 0 = sequence number of the last completed call, word 1 = fp16-range flag
 //   bytes  16.. 31  device -> host: timings of the resident scorer's last call (akugpu_stream_stats)
-//   bytes 256..     centred features [STREAM_MAX_FRAMES][64] floats, then results [STREAM_MAX_FRAMES][S] floats
-constexpr int STREAM_HDR_WORD = 16, STREAM_X_BYTE = 256;
+//   bytes 256..     centred features [STREAM_MAX_FRAMES][64] floats (launch-per-call scorer with wide features; calls the
+//                   resident scorer relays through CTA 0), then results [STREAM_MAX_FRAMES][S] floats
+// (the resident scorer's commands travel in a block of their own: one 512-byte packet per CTA, gmm_resident.cu)
+constexpr int STREAM_X_BYTE = 256;
 void stream_buffers(akugpu_ctx *ctx, int S);
 void stream_map_ready(akugpu_ctx *ctx);
 
