@@ -187,6 +187,7 @@ struct StreamState {
   cudaStream_t session_stream = nullptr;
   void *pkt_host = nullptr, *pkt_dev = nullptr;      // one 512-byte command packet per CTA, pinned + mapped
   int session_grid = 0;
+  const void *known_host[2] = {nullptr, nullptr};    // buffers of recent session calls already classified as host memory
   std::vector<int> session_order;                    // CTA indices, most component tiles first
   int64_t session_launches = 0, session_calls = 0;
   std::chrono::steady_clock::time_point session_last;

@@ -456,7 +456,17 @@ bool session_applicable(akugpu_ctx *ctx, int precision, int64_t n_frames, const 
 {
   if (!ctx->stream_state.session_want) return false;
   if (!stream_applicable(ctx, precision, n_frames)) return false;
-  if (is_device_ptr(feats) || is_device_ptr(out)) return false;
+  // the two pointer queries cost ~1 us of a ~11 us call: a per-frame loop hands in the same two host buffers every time
+  // (under unified addressing a host address never turns into a device address within the life of the process)
+  StreamState &st = ctx->stream_state;
+  if (feats != st.known_host[0] && feats != st.known_host[1]) {
+    if (is_device_ptr(feats)) return false;
+    st.known_host[0] = feats;
+  }
+  if (out != st.known_host[0] && out != st.known_host[1]) {
+    if (is_device_ptr(out)) return false;
+    st.known_host[1] = out;
+  }
   return resident_slots(ctx->ptc16.NCH, ctx->ptc16.D) >= 1;
 }
 
