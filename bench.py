@@ -543,7 +543,9 @@ def sub_streaming(args, local, model2):
         native = {"F=%d" % F: eng.stream_latency(feats[100:100 + F], n_calls=1000) for F in (1, 4, 8)}
         # resident scorer (akugpu_stream_open): the parameter image stays in shared memory, a call is a message
         resident = {"us_per_call": {}, "native": {}}
+        t0 = time.perf_counter()
         eng.stream_open(200.0)
+        resident["open_ms"] = 1e3 * (time.perf_counter() - t0)    # launch + the CTAs' fill of their resident tiles begun
         try:
             rows_p = C.POINTER(C.c_float)()
             for F in ((1, 4, 8, 16) if name == "5000x16" else (1, 4, 8)):
