@@ -22,6 +22,8 @@
 #include "ctx.hpp"
 #include "kernels.hpp"
 #include "lna_common.cuh"
+#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace akugpu {
 
@@ -321,6 +323,91 @@ lna_f32_rows(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, cons
 }
 
 // Parity mode: one thread per frame, states in index order, doubles throughout.
+// lna_f32_rows with the scores brought in by TMA: one elected thread fetches a round's [states][32 frames] box into a
+// 3-deep shared-memory ring (48 KB in flight per CTA, no registers tied up by loads in flight: the register-staged kernel
+// above keeps 16 per thread and sits at 47 % warps active, stalled on them); the warps convert from shared memory -- lane =
+// frame, rows of 32 floats: conflict free -- with the arithmetic of lna_f32_rows, bit for bit, and store rows the same way.
+// Boxes that reach past the last state / frame are zero filled by the copy, like the guarded loads above.
+template <int B, bool NORM>
+__global__ void __launch_bounds__(256)
+lna_f32_rows_tma(const __grid_constant__ CUtensorMap mapS, int S, int64_t nf, const float2 *__restrict__ norm, uint8_t *__restrict__ out)
+{
+  constexpr int SPR = 128;                       // states per round
+  constexpr int SPW = SPR / 8;                   // states per warp and round (= one batch of 16)
+  constexpr int TW = SPR * B / 4;                // 32-bit words per frame row of the tile
+  constexpr int NST = 3;
+  constexpr uint32_t STAGE_BYTES = SPR * 32 * 4;
+  extern __shared__ __align__(128) unsigned char lna_sm[];
+  float (*in)[SPR][32] = reinterpret_cast<float (*)[SPR][32]>(lna_sm);
+  uint32_t (*tile)[32][TW + 1] = reinterpret_cast<uint32_t (*)[32][TW + 1]>(lna_sm + NST * STAGE_BYTES);
+  __shared__ uint64_t full[NST];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int64_t f0 = (int64_t)blockIdx.x * 32;
+  const int64_t f = f0 + lane;
+  const bool fvalid = f < nf;
+  const int rounds = (S + SPR - 1) / SPR;
+  if (tid == 0) {
+    for (int i = 0; i < NST; i++) tc::mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int r = 0; r < NST && r < rounds; r++) {
+      tc::mbar_expect_tx(&full[r], STAGE_BYTES);
+      tc::tma_load_2d(in[r], &mapS, (int)f0, r * SPR, &full[r]);
+    }
+  }
+  float Mx = 0.f, lognorm = 0.f;
+  if (NORM) {
+    const float2 nm = norm[fvalid ? f : 0];
+    // every state flushed to zero (Mx = -inf): Z = 1 and every record is the floor; +inf makes L - Mx = -inf
+    Mx = (nm.x == -INFINITY) ? INFINITY : nm.x;
+    lognorm = nm.y;
+  }
+  __syncthreads();                               // the barriers exist
+  for (int r = 0; r < rounds; r++) {
+    const int st = r % NST;
+    tc::mbar_wait(&full[st], (uint32_t)(r / NST) & 1u);
+    uint32_t(*tl)[TW + 1] = tile[r & 1];
+    float lp[SPW];
+#pragma unroll
+    for (int j = 0; j < SPW; ++j) lp[j] = in[st][w * SPW + j][lane];
+#pragma unroll
+    for (int j = 0; j < SPW; ++j) {
+      float L = lp[j];
+      if (L < LN_2M126) L = log_of_float_cast_rare(L);       // fp32-denormal / zero range of the float cast: rare
+      const float v = NORM ? (L - Mx) - lognorm : L;
+      lp[j] = fmaxf(v, LP_FLOOR);                            // also catches -inf and NaN
+    }
+    if (B == 2) {
+#pragma unroll
+      for (int j = 0; j < SPW; j += 2) {
+        const uint32_t c0 = NORM ? lna_code16_f32_neg(lp[j]) : lna_code16_f32(lp[j]);
+        const uint32_t c1 = NORM ? lna_code16_f32_neg(lp[j + 1]) : lna_code16_f32(lp[j + 1]);
+        tl[lane][(w * SPW + j) >> 1] = __byte_perm(c0, c1, 0x4501);   // big-endian codes, two per word
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < SPW; ++j) tl[lane][w * SPW + j] = __float_as_uint(lp[j]);
+    }
+    __syncthreads();                             // the stage has been read by every warp, the tile is complete
+    if (tid == 0 && r + NST < rounds) {
+      tc::mbar_expect_tx(&full[st], STAGE_BYTES);
+      tc::tma_load_2d(in[st], &mapS, (int)f0, (r + NST) * SPR, &full[st]);
+    }
+    const int nwords = min(SPR, S - r * SPR) * B / 4;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int fr = w * 4 + rr;
+      const int64_t gf = f0 + fr;
+      if (gf < nf) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((size_t)gf * S + (size_t)r * SPR) * B);
+#pragma unroll
+        for (int k = 0; k < (TW + 31) / 32; ++k)
+          if (lane + 32 * k < nwords) __stcs(dst + lane + 32 * k, tl[fr][lane + 32 * k]);
+      }
+    }
+    // no second barrier: the next round fills the other tile, and the one after that is behind the next barrier
+  }
+}
+
 template <int B>
 __global__ void __launch_bounds__(128)
 lna_f64(const double *__restrict__ lin, int64_t ldF, int S, int64_t nf, int normalize, uint8_t *__restrict__ out)
@@ -362,6 +449,29 @@ __global__ void checksum_kernel(const uint8_t *__restrict__ buf, int64_t nbytes,
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(acc, local);
 }
 
+constexpr int LNA_TMA_DEFAULT = 1;      // lna_f32_rows_tma (8.6 -> 7.2 ms per config-2 step); AKUGPU_LNA_TMA=0: the register-staged kernel
+typedef CUresult (*LnaEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static void lna_make_map(CUtensorMap *map, const float *sll, int S, int64_t nf, int64_t ldF)
+{
+  static LnaEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void *p = nullptr;
+    AKU_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw Error(AKUGPU_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = (LnaEncodeTiledFn)p;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)nf, (cuuint64_t)S};            // innermost first: frames, then states
+  cuuint64_t strides[1] = {(cuuint64_t)ldF * 4};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(sll), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(AKUGPU_E_CUDA, fmt("cuTensorMapEncodeTiled (LNA scores) failed (%d)", (int)r));
+}
+
 void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64_t nf, int lnabytes, int normalize,
                     const float2 *norm, uint8_t *out, float2 *norm_scratch)
 {
@@ -376,6 +486,24 @@ void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64
       AKU_CUDA(cudaGetLastError());
       ctx->launches++;
       norm = norm_scratch;
+    }
+    static const int use_tma = getenv("AKUGPU_LNA_TMA") ? atoi(getenv("AKUGPU_LNA_TMA")) : LNA_TMA_DEFAULT;
+    if (use_tma && (ldF * 4) % 16 == 0 && ((uintptr_t)sll & 15) == 0 && nf < (int64_t)1 << 31) {
+      // scores as a 2-D tensor [S][nf] of floats (row pitch ldF), boxes of 128 states x 32 frames
+      CUtensorMap mapS;
+      lna_make_map(&mapS, sll, S, nf, ldF);
+      auto go = [&](auto kernel, int B_) {
+        const size_t smem = 3 * (size_t)128 * 32 * 4 + 2 * (size_t)32 * (128 * B_ / 4 + 1) * 4;
+        ensure_dynamic_smem(ctx, (const void *)kernel, smem);
+        kernel<<<grid, 256, smem, ctx->stream>>>(mapS, S, nf, norm, out);
+      };
+      if (lnabytes == 2 && normalize) go(lna_f32_rows_tma<2, true>, 2);
+      else if (lnabytes == 2) go(lna_f32_rows_tma<2, false>, 2);
+      else if (normalize) go(lna_f32_rows_tma<4, true>, 4);
+      else go(lna_f32_rows_tma<4, false>, 4);
+      AKU_CUDA(cudaGetLastError());
+      ctx->launches++;
+      return;
     }
     if (lnabytes == 2 && normalize) lna_f32_rows<2, true><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
     else if (lnabytes == 2) lna_f32_rows<2, false><<<grid, 256, 0, ctx->stream>>>(sll, ldF, S, nf, norm, out);
