@@ -328,14 +328,13 @@ lna_f32_rows(const float *__restrict__ sll, int64_t ldF, int S, int64_t nf, cons
 // above keeps 16 per thread and sits at 47 % warps active, stalled on them); the warps convert from shared memory -- lane =
 // frame, rows of 32 floats: conflict free -- with the arithmetic of lna_f32_rows, bit for bit, and store rows the same way.
 // Boxes that reach past the last state / frame are zero filled by the copy, like the guarded loads above.
-template <int B, bool NORM>
+template <int B, bool NORM, int NST>
 __global__ void __launch_bounds__(256)
 lna_f32_rows_tma(const __grid_constant__ CUtensorMap mapS, int S, int64_t nf, const float2 *__restrict__ norm, uint8_t *__restrict__ out)
 {
   constexpr int SPR = 128;                       // states per round
   constexpr int SPW = SPR / 8;                   // states per warp and round (= one batch of 16)
   constexpr int TW = SPR * B / 4;                // 32-bit words per frame row of the tile
-  constexpr int NST = 3;
   constexpr uint32_t STAGE_BYTES = SPR * 32 * 4;
   extern __shared__ __align__(128) unsigned char lna_sm[];
   float (*in)[SPR][32] = reinterpret_cast<float (*)[SPR][32]>(lna_sm);
@@ -492,15 +491,19 @@ void launch_lna_f32(akugpu_ctx *ctx, const float *sll, int64_t ldF, int S, int64
       // scores as a 2-D tensor [S][nf] of floats (row pitch ldF), boxes of 128 states x 32 frames
       CUtensorMap mapS;
       lna_make_map(&mapS, sll, S, nf, ldF);
+      const int nst = (use_tma >= 2 && use_tma <= 4) ? use_tma : 3;       // ring depth (AKUGPU_LNA_TMA=2|3|4; 1 = default 3)
       auto go = [&](auto kernel, int B_) {
-        const size_t smem = 3 * (size_t)128 * 32 * 4 + 2 * (size_t)32 * (128 * B_ / 4 + 1) * 4;
+        const size_t smem = (size_t)nst * 128 * 32 * 4 + 2 * (size_t)32 * (128 * B_ / 4 + 1) * 4;
         ensure_dynamic_smem(ctx, (const void *)kernel, smem);
         kernel<<<grid, 256, smem, ctx->stream>>>(mapS, S, nf, norm, out);
       };
-      if (lnabytes == 2 && normalize) go(lna_f32_rows_tma<2, true>, 2);
-      else if (lnabytes == 2) go(lna_f32_rows_tma<2, false>, 2);
-      else if (normalize) go(lna_f32_rows_tma<4, true>, 4);
-      else go(lna_f32_rows_tma<4, false>, 4);
+#define LNA_TMA_GO(NST_)                                                         \
+      if (lnabytes == 2 && normalize) go(lna_f32_rows_tma<2, true, NST_>, 2);    \
+      else if (lnabytes == 2) go(lna_f32_rows_tma<2, false, NST_>, 2);           \
+      else if (normalize) go(lna_f32_rows_tma<4, true, NST_>, 4);                \
+      else go(lna_f32_rows_tma<4, false, NST_>, 4);
+      if (nst == 2) { LNA_TMA_GO(2) } else if (nst == 4) { LNA_TMA_GO(4) } else { LNA_TMA_GO(3) }
+#undef LNA_TMA_GO
       AKU_CUDA(cudaGetLastError());
       ctx->launches++;
       return;
