@@ -501,7 +501,22 @@ def sub_parity_mode(args, torch, eng, stream, pcm_d, pcm_p, uo, fo, n_utts=24):
     eng.phone_probs(pcm_d[:ns], sub_uo, precision=F64, lnabytes=LNABYTES, out=out_d)
     ms = _event_time(torch, stream, lambda: eng.phone_probs(pcm_d[:ns], sub_uo, precision=F64, lnabytes=LNABYTES, out=out_d), 2)
     ms_e = _event_time(torch, stream, lambda: eng.phone_probs(pcm_p[:ns], sub_uo, precision=F64, lnabytes=LNABYTES, out=out_p), 2)
+    # how far the headline (throughput) mode is from these bytes: the same utterances in F32, code by code (outside any timing)
+    codes = None
+    if LNABYTES == 2:
+        from aaltoasr_b200 import F32
+        eng.phone_probs(pcm_d[:ns], sub_uo, precision=F64, lnabytes=2, out=out_d)
+        out32 = torch.empty_like(out_d)
+        eng.phone_probs(pcm_d[:ns], sub_uo, precision=F32, lnabytes=2, out=out32)
+        torch.cuda.synchronize()
+        a, b = out_d.view(F, N_STATES, 2).to(torch.int32), out32.view(F, N_STATES, 2).to(torch.int32)
+        diff = ((a[..., 0] * 256 + a[..., 1]) - (b[..., 0] * 256 + b[..., 1])).abs()
+        codes = {"entries": int(F) * N_STATES, "differing_fraction": float((diff != 0).float().mean().item()),
+                 "max_abs_code_difference": int(diff.max().item()),
+                 "note": "2-byte codes of the throughput mode (the headline) against the parity mode's (= the reference's bytes), end to end from PCM"}
+        del a, b, diff, out32
     return {"metric": "acoustic frames/sec (MFCC+GMM log-lik -> LNA), parity mode", "value": F / (ms * 1e-3), "unit": "frames/s",
+            "throughput_mode_codes_vs_parity_mode": codes,
             "dtype": "f64", "steps": 2, "ms_per_step": ms,
             "config": {"workload": "%d utterances x 10 s of the headline workload, F64 parity arithmetic (gmm_diag_f64 + lna_f64: the "
                                    "reference's operations in double, LNA bytes identical to the reference's)" % n, "frames": F},
